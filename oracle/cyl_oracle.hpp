@@ -1,0 +1,224 @@
+// cyl_oracle.hpp -- CPU oracle for the cylindrical-EPOCH per-timestep PIC hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  This is a from-scratch FP64 restatement, in C++, of the
+// algorithm the reference implements in Fortran (reference files are cited per function
+// as `file:line`, relative to /root/reference/epoch_axial/src).  Nothing in the product
+// library (cylindrical_epoch_b200/csrc) includes, links or calls this code; only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+//
+// PARITY UNPINNED: the reference ships no golden vectors, fixtures or runnable tests for
+// the cylindrical path, and neither this container nor the GPU box
+// has a Fortran compiler or MPI, so the real reference cannot be run to produce any.  The
+// oracle is therefore anchored only by (i) the analytic expectation of
+// example_decks/current_density_test.deck (DOCUMENTATION.pdf section 7.2), (ii) exact
+// discrete charge continuity of the deposit, (iii) the axis-condition identities and
+// (iv) vacuum-propagation sanity checks -- see tests/test_oracle_*.py.
+//
+// Conventions (all mirror the reference so arrays can be compared element by element):
+//   * mode arrays are Fortran column-major (ix, ir, im), lower bounds (1-ng, 1-ng, 0),
+//     ng = 5, complex128 interleaved;
+//   * "x" is the cylinder axis, grid "y" is r, particle pos/p are Cartesian (x, y, z);
+//   * decomposition is x-slabs only (nprocx = nranks, nprocy = 1): every rank owns the
+//     axis and r_max (y_min_boundary = y_max_boundary = true).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace cylo {
+
+constexpr int NG = 5;    // constants.F90:544  ng = png + 2 (triangle shape, png = 3)
+constexpr int JNG = 5;   // constants.F90:545
+constexpr int PNG = 3;   // constants.F90:537
+
+// Boundary-condition codes, constants.F90:55-72
+enum BC {
+  BC_PERIODIC = 1, BC_OTHER = 2, BC_SIMPLE_LASER = 3, BC_SIMPLE_OUTFLOW = 4, BC_OPEN = 5,
+  BC_ZERO_GRADIENT = 7, BC_CLAMP = 8, BC_REFLECT = 9, BC_CONDUCT = 10, BC_THERMAL = 11,
+  BC_CPML_LASER = 12, BC_CPML_OUTFLOW = 13, BC_MIXED = 14, BC_ZERO_B = 16
+};
+// boundary location codes (0-based here; reference c_bd_x_min..c_bd_y_max = 1..4)
+enum BD { BD_X_MIN = 0, BD_X_MAX = 1, BD_Y_MIN = 2, BD_Y_MAX = 3 };
+
+// physical constants, constants.F90:171-201
+constexpr double PI = 3.141592653589793238462643383279503;
+constexpr double Q0 = 1.602176565e-19;
+constexpr double M0 = 9.10938291e-31;
+constexpr double C_LIGHT = 2.99792458e8;
+constexpr double KB = 1.3806488e-23;
+constexpr double EPSILON0 = 8.854187817620389850536563031710750e-12;
+
+// Minimal complex type with the naive (Fortran-rule) products; no FMA contraction is
+// allowed when this file is compiled (-ffp-contract=off), matching a generic x86-64
+// gfortran build of the reference.
+struct cplx {
+  double re, im;
+  cplx() : re(0.0), im(0.0) {}
+  cplx(double r) : re(r), im(0.0) {}
+  cplx(double r, double i) : re(r), im(i) {}
+};
+inline cplx operator+(cplx a, cplx b) { return cplx(a.re + b.re, a.im + b.im); }
+inline cplx operator-(cplx a, cplx b) { return cplx(a.re - b.re, a.im - b.im); }
+inline cplx operator-(cplx a) { return cplx(-a.re, -a.im); }
+inline cplx operator*(cplx a, cplx b) {
+  return cplx(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+inline cplx operator*(double s, cplx a) { return cplx(s * a.re, s * a.im); }
+inline cplx operator*(cplx a, double s) { return cplx(a.re * s, a.im * s); }
+inline cplx operator/(cplx a, double s) { return cplx(a.re / s, a.im / s); }
+inline cplx& operator+=(cplx& a, cplx b) { a.re += b.re; a.im += b.im; return a; }
+// real / complex, Smith's method as used by libgcc for COMPLEX division
+inline cplx recip(cplx z) {
+  if (std::abs(z.re) >= std::abs(z.im)) {
+    double r = z.im / z.re, den = z.re + z.im * r;
+    return cplx(1.0 / den, -r / den);
+  } else {
+    double r = z.re / z.im, den = z.im + z.re * r;
+    return cplx(r / den, -1.0 / den);
+  }
+}
+const cplx IMAGI(0.0, 1.0);
+
+// (ix, ir, im) array with Fortran bounds (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1)
+struct Arr3 {
+  int nx = 0, ny = 0, M = 0;
+  std::vector<cplx> d;
+  void alloc(int nx_, int ny_, int M_) {
+    nx = nx_; ny = ny_; M = M_;
+    d.assign((size_t)(nx + 2 * NG) * (ny + 2 * NG) * M, cplx());
+  }
+  inline cplx& operator()(int ix, int ir, int im) {
+    return d[((size_t)im * (ny + 2 * NG) + (size_t)(ir + NG - 1)) * (nx + 2 * NG) + (ix + NG - 1)];
+  }
+  inline const cplx& operator()(int ix, int ir, int im) const {
+    return d[((size_t)im * (ny + 2 * NG) + (size_t)(ir + NG - 1)) * (nx + 2 * NG) + (ix + NG - 1)];
+  }
+  void zero() { std::fill(d.begin(), d.end(), cplx()); }
+};
+// (ir, im) boundary snapshot, bounds (1-ng:ny+ng, 0:M-1), setup.F90:397-402
+struct Arr2 {
+  int ny = 0, M = 0;
+  std::vector<cplx> d;
+  void alloc(int ny_, int M_) { ny = ny_; M = M_; d.assign((size_t)(ny + 2 * NG) * M, cplx()); }
+  inline cplx& operator()(int ir, int im) { return d[(size_t)im * (ny + 2 * NG) + (ir + NG - 1)]; }
+  inline const cplx& operator()(int ir, int im) const { return d[(size_t)im * (ny + 2 * NG) + (ir + NG - 1)]; }
+};
+
+struct Particle {  // shared_data.F90:93-142 (default build: pos, p, weight)
+  double pos[3], p[3], w;
+};
+
+struct Species {   // shared_data.F90:190-280 (hot-path members only)
+  double charge, mass;
+  int bc_particle[4];
+  bool immobile, zero_current;
+  double npart_per_cell;                    // for window insertion
+  double density, temp[3], drift[3];        // uniform initial conditions
+};
+
+// KISS generator + polar Box-Muller, random_generator.f90:45-173
+struct Rng {
+  uint32_t x, y, z, w;
+  bool cached;
+  double cached_value;
+  void init(int seed);
+  double uniform();
+  double box_muller(double stdev, double mu);
+  void flush_cache() { cached = false; }
+};
+
+struct Laser {  // laser.f90 laser_block, restricted to what the decks in scope use
+  int boundary;            // BD_X_MIN or BD_X_MAX
+  double amp, omega, pol_angle, t_start, t_end;
+  double t_centre, t_width;   // t_profile = gauss(time, t_centre, t_width); t_width<=0 -> 1
+  double r_width;             // profile = gauss(y, 0, r_width); r_width<=0 -> 1
+  double phase;               // constant phase
+};
+
+struct Rank {
+  int nx, ny, M;
+  int x_coord, nprocx;
+  int cell_x_min, cell_x_max;   // global cell range, mpi_routines.F90:312-337
+  bool x_min_boundary, x_max_boundary;
+  double x_grid_min_local, x_grid_max_local, x_min_local, x_max_local;
+  Arr3 exm, erm, etm, bxm, brm, btm, jxm, jrm, jtm;
+  Arr3 bxm_old, brm_old, btm_old, jxm_old, jrm_old, jtm_old;
+  Arr2 exm_x_min, erm_x_min, etm_x_min, bxm_x_min, brm_x_min, btm_x_min;
+  Arr2 exm_x_max, erm_x_max, etm_x_max, bxm_x_max, brm_x_max, btm_x_max;
+  std::vector<std::vector<Particle>> parts;   // per species, in linked-list order
+  Rng rng;
+  // statistics of the last particle_bcs call (per species summed)
+  int64_t n_sent_left = 0, n_sent_right = 0, n_removed = 0, n_recv = 0;
+};
+
+struct Config {
+  int nx_global, ny_global, n_mode, nranks;
+  double x_min, x_max, y_max;      // y_min = 0 always (deck_control_block.F90:74-75)
+  double dt_multiplier;            // setup.F90:78 default 0.95
+  int bc_field[4];                 // raw deck codes; normalised by setup_boundaries
+  // moving window (window.F90:330-376)
+  int move_window;
+  double window_v_x, window_start_time, window_stop_time;
+  int bc_x_min_after_move, bc_x_max_after_move;
+};
+
+struct World {
+  Config cfg;
+  int M;
+  double dx, dy, dt, time;
+  int step;
+  double x_min, x_max, y_max, length_x;
+  double x_grid_min, xb_min;       // global grid origin (cell centre / cell edge)
+  double y_grid_min_local;
+  int bc_field[4];
+  bool add_laser[4];
+  std::vector<Species> species;
+  std::vector<Laser> lasers;
+  std::vector<Rank> ranks;
+  // window state
+  bool window_started = false;
+  double window_shift_fraction = 0.0;
+  int64_t window_shifts_total = 0;
+
+  explicit World(const Config& c);
+  int add_species(const Species& s);
+  void setup_boundaries();                       // boundary.F90:30-75
+  void setup_grid_x();                           // utilities.f90:343-372
+  void load_uniform(int ispecies);               // helper.F90:373-811, particle_temperature.F90:30-83
+  void snapshot_field_boundaries();              // setup.F90:393-423
+  void init_half_step();                         // epoch2d.F90:143-161
+
+  // hot path, World-level (all ranks, with the MPI exchanges emulated in-process)
+  void update_e_field(Rank& r);                  // fields.f90:53-182
+  void update_b_field(Rank& r);                  // fields.f90:186-312
+  void efield_bcs();                             // boundary.F90:1355-1413
+  void bfield_bcs(bool mpi_only);                // boundary.F90:1417-1476
+  void bfield_final_bcs();                       // boundary.F90:1505-1537
+  void update_eb_fields_half();                  // fields.f90:316-337
+  void update_eb_fields_final();                 // fields.f90:341-353
+  void push_particles();                         // particles.F90:28-734
+  void push_rank(Rank& r);                       //   the per-rank particle loop
+  void current_bcs_r_min_final(Rank& r);         // boundary.F90:1909-1959
+  void particle_bcs();                           // boundary.F90:1541-1889
+  void current_bcs();                            // boundary.F90:1893-1905
+  void current_finish();                         // current_smooth.F90:29-45
+  void moving_window();                          // window.F90:330-376
+  void step_once();                              // epoch2d.F90:189-266 loop body
+
+  // pieces
+  void halo_x(Arr3 Rank::*f, int row_lo_off, int row_hi_off);      // boundary.F90:500-553
+  void clamp_zero(Rank& r, Arr3& f, bool stag_x, bool stag_y, int bd);     // boundary.F90:772-829
+  void zero_gradient(Rank& r, Arr3& f, bool stag_x, bool stag_y, int bd);  // boundary.F90:654-707
+  void laser_sources(int bd, const Rank& r, std::vector<double>& s1, std::vector<double>& s2);
+  void outflow_bcs_x_min(Rank& r);               // laser.f90:411-520
+  void outflow_bcs_x_max(Rank& r);               // laser.f90:524-633
+  void outflow_bcs_r_max(Rank& r);               // laser.f90:637-690
+  void reflection_bcs(Rank& r, Arr3& a, int im, int flip_dir);     // boundary.F90:918-1015
+  void periodic_sum_x(Arr3 Rank::*f);            // boundary.F90:1133-1203
+  void insert_particles(Rank& r);                // window.F90:157-300
+  void shift_fields();                           // window.F90:98-153
+  int bc_allspecies(int bd) const;
+};
+
+}  // namespace cylo

@@ -1,0 +1,216 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (cylindrical_epoch_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NG = 5
+# boundary-condition codes (constants.F90:55-72)
+BC_PERIODIC, BC_OTHER, BC_SIMPLE_LASER, BC_SIMPLE_OUTFLOW, BC_OPEN = 1, 2, 3, 4, 5
+BC_ZERO_GRADIENT, BC_CLAMP, BC_REFLECT, BC_CONDUCT, BC_THERMAL = 7, 8, 9, 10, 11
+BC_ZERO_B = 16
+BD_X_MIN, BD_X_MAX, BD_Y_MIN, BD_Y_MAX = 0, 1, 2, 3
+
+FIELD_NAMES = ["exm", "erm", "etm", "bxm", "brm", "btm", "jxm", "jrm", "jtm",
+               "bxm_old", "brm_old", "btm_old", "jxm_old", "jrm_old", "jtm_old"]
+SNAP_NAMES = [f"{n}_x_min" for n in FIELD_NAMES[:6]] + [f"{n}_x_max" for n in FIELD_NAMES[:6]]
+
+OPS = dict(step=0, fields_half=1, push=2, current_finish=3, fields_final=4, moving_window=5,
+           init_half_step=6, particle_bcs=7, efield_bcs=8, bfield_bcs_mpi=9, bfield_final_bcs=10,
+           update_e=11, update_b=12, snapshot_boundaries=13, advance_half_time=14, push_no_bcs=15,
+           current_bcs=16, flush_rng=17)
+
+Q0 = 1.602176565e-19
+M0 = 9.10938291e-31
+C_LIGHT = 2.99792458e8
+KB = 1.3806488e-23
+EPSILON0 = 8.854187817620389850536563031710750e-12
+
+
+class CyloConfig(C.Structure):
+    _fields_ = [("nx_global", C.c_int32), ("ny_global", C.c_int32), ("n_mode", C.c_int32),
+                ("nranks", C.c_int32), ("x_min", C.c_double), ("x_max", C.c_double),
+                ("y_max", C.c_double), ("dt_multiplier", C.c_double), ("bc_field", C.c_int32 * 4),
+                ("move_window", C.c_int32), ("window_v_x", C.c_double),
+                ("window_start_time", C.c_double), ("window_stop_time", C.c_double),
+                ("bc_x_min_after_move", C.c_int32), ("bc_x_max_after_move", C.c_int32)]
+
+
+def build(force=False):
+    """Compile oracle/libcyl_oracle.so with the committed Makefile (g++, no FMA contraction)."""
+    so = os.path.join(_HERE, "libcyl_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.cylo_create.restype = C.c_void_p
+        L.cylo_create.argtypes = [C.POINTER(CyloConfig)]
+        L.cylo_destroy.argtypes = [C.c_void_p]
+        L.cylo_add_species.restype = C.c_int
+        L.cylo_add_species.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_int32), C.c_int,
+                                       C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double)]
+        L.cylo_add_laser.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 9
+        L.cylo_load_uniform.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.cylo_set_dt.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_get_bc_field.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+        L.cylo_get_bc_particle.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
+        L.cylo_rank_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        L.cylo_field_ptr.restype = C.c_void_p
+        L.cylo_field_ptr.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cylo_nparticles.restype = C.c_int64
+        L.cylo_nparticles.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.cylo_get_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.cylo_set_particles.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p]
+        L.cylo_stats.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]
+        L.cylo_laser_sources.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.cylo_call.restype = C.c_double
+        L.cylo_call.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_rng_uniform.restype = C.c_double
+        L.cylo_rng_uniform.argtypes = [C.c_void_p, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+class OracleWorld:
+    """All ranks (x-slabs) of one simulation, stepped in-process by the CPU oracle."""
+
+    def __init__(self, nx, ny, n_mode, x_min, x_max, y_max, bc_field, nranks=1, dt_multiplier=0.95,
+                 move_window=False, window_v_x=0.0, window_start_time=0.0, window_stop_time=1e300,
+                 bc_x_min_after_move=BC_SIMPLE_OUTFLOW, bc_x_max_after_move=BC_SIMPLE_OUTFLOW):
+        self.L = lib()
+        cfg = CyloConfig(nx, ny, n_mode, nranks, x_min, x_max, y_max, dt_multiplier,
+                         (C.c_int32 * 4)(*bc_field), int(move_window), window_v_x, window_start_time,
+                         window_stop_time, bc_x_min_after_move, bc_x_max_after_move)
+        self.h = C.c_void_p(self.L.cylo_create(C.byref(cfg)))
+        self.nranks = nranks
+        self.n_mode = n_mode
+        self.nx_global, self.ny_global = nx, ny
+        self.n_species = 0
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.cylo_destroy(self.h)
+            self.h = None
+
+    # --- configuration -------------------------------------------------------------------
+    def add_species(self, charge, mass, bc_particle, ppc=0.0, density=0.0, temp=(0, 0, 0),
+                    drift=(0, 0, 0), immobile=False, zero_current=False):
+        t = (C.c_double * 3)(*temp)
+        d = (C.c_double * 3)(*drift)
+        i = self.L.cylo_add_species(self.h, charge, mass, (C.c_int32 * 4)(*bc_particle), int(immobile),
+                                    int(zero_current), float(ppc), float(density), t, d)
+        self.n_species = i + 1
+        return i
+
+    def add_laser(self, boundary, amp, omega, pol_angle=0.0, t_start=0.0, t_end=1e300, t_centre=0.0,
+                  t_width=0.0, r_width=0.0, phase=0.0):
+        self.L.cylo_add_laser(self.h, boundary, amp, omega, pol_angle, t_start, t_end, t_centre, t_width,
+                              r_width, phase)
+
+    def load_uniform(self, isp):
+        self.L.cylo_load_uniform(self.h, isp)
+
+    # --- scalars ---------------------------------------------------------------------------
+    def scalars(self):
+        out = (C.c_double * 16)()
+        self.L.cylo_get_scalars(self.h, out)
+        keys = ["dx", "dy", "dt", "time", "x_min", "x_max", "y_max", "x_grid_min", "xb_min",
+                "y_grid_min_local", "length_x", "window_shift_fraction", "step", "window_started",
+                "window_shifts_total"]
+        return dict(zip(keys, list(out)[:15]))
+
+    def set_dt(self, dt):
+        self.L.cylo_set_dt(self.h, dt)
+
+    def set_time(self, t):
+        self.L.cylo_set_time(self.h, t)
+
+    def bc_field(self):
+        out = (C.c_int32 * 4)()
+        self.L.cylo_get_bc_field(self.h, out)
+        return list(out)
+
+    def bc_particle(self, isp):
+        out = (C.c_int32 * 4)()
+        self.L.cylo_get_bc_particle(self.h, isp, out)
+        return list(out)
+
+    def rank_info(self, k):
+        io = (C.c_int32 * 6)()
+        do = (C.c_double * 4)()
+        self.L.cylo_rank_info(self.h, k, io, do)
+        return dict(nx=io[0], ny=io[1], cell_x_min=io[2], cell_x_max=io[3], x_min_boundary=bool(io[4]),
+                    x_max_boundary=bool(io[5]), x_grid_min_local=do[0], x_grid_max_local=do[1],
+                    x_min_local=do[2], x_max_local=do[3])
+
+    # --- arrays (numpy views onto the oracle's memory; index [im, ir+NG-1, ix+NG-1]) -------
+    def field(self, k, name):
+        info = self.rank_info(k)
+        nx, ny = info["nx"], info["ny"]
+        if name in FIELD_NAMES:
+            fid = FIELD_NAMES.index(name)
+            shape = (self.n_mode, ny + 2 * NG, nx + 2 * NG)
+        else:
+            fid = 15 + SNAP_NAMES.index(name)
+            shape = (self.n_mode, ny + 2 * NG)
+        ptr = self.L.cylo_field_ptr(self.h, k, fid)
+        n = int(np.prod(shape))
+        buf = (C.c_double * (2 * n)).from_address(ptr)
+        return np.frombuffer(buf, dtype=np.complex128).reshape(shape)
+
+    def nparticles(self, k, isp):
+        return int(self.L.cylo_nparticles(self.h, k, isp))
+
+    def particles(self, k, isp):
+        """(n, 7) array: x, y, z, px, py, pz, weight (the reference's 7-double wire format)."""
+        n = self.nparticles(k, isp)
+        out = np.empty((n, 7), dtype=np.float64)
+        if n:
+            self.L.cylo_get_particles(self.h, k, isp, out.ctypes.data)
+        return out
+
+    def set_particles(self, k, isp, arr):
+        arr = np.ascontiguousarray(arr, dtype=np.float64).reshape(-1, 7)
+        self.L.cylo_set_particles(self.h, k, isp, arr.shape[0], arr.ctypes.data)
+
+    def stats(self, k):
+        out = (C.c_int64 * 4)()
+        self.L.cylo_stats(self.h, k, out)
+        return dict(sent_left=out[0], sent_right=out[1], removed=out[2], received=out[3])
+
+    def laser_sources(self, bd, k=0):
+        ny = self.rank_info(k)["ny"]
+        s1 = np.zeros(ny + 1)
+        s2 = np.zeros(ny + 1)
+        self.L.cylo_laser_sources(self.h, bd, k, s1.ctypes.data, s2.ctypes.data)
+        return s1, s2
+
+    # --- operators -------------------------------------------------------------------------
+    def call(self, op):
+        t = self.L.cylo_call(self.h, OPS[op])
+        if t < 0:
+            raise ValueError(op)
+        return t
+
+    def step(self, n=1):
+        t = 0.0
+        for _ in range(n):
+            t += self.call("step")
+        return t
