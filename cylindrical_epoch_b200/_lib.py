@@ -1,0 +1,109 @@
+"""ctypes binding of libcylgpu.so (include/cylgpu.h).  Fails loudly when the library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcylgpu.so")
+MAX_SPECIES = 8
+
+SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int,
+                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+class Config(C.Structure):
+    _fields_ = [("nx", C.c_int32), ("ny", C.c_int32), ("nx_global", C.c_int32), ("ny_global", C.c_int32),
+                ("n_mode", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+                ("x_min_boundary", C.c_int32), ("x_max_boundary", C.c_int32),
+                ("bc_field", C.c_int32 * 4), ("n_species", C.c_int32), ("device", C.c_int32),
+                ("transport", C.c_int32),
+                ("dx", C.c_double), ("dy", C.c_double), ("dt", C.c_double),
+                ("x_grid_min_local", C.c_double), ("y_grid_min_local", C.c_double),
+                ("x_min", C.c_double), ("x_max", C.c_double), ("y_max", C.c_double),
+                ("x_min_local", C.c_double), ("x_max_local", C.c_double),
+                ("nccl_unique_id", C.c_void_p), ("sendrecv", SENDRECV_FN), ("sendrecv_user", C.c_void_p),
+                ("fabric", C.c_void_p), ("particle_capacity", C.c_int64)]
+
+
+class SpeciesC(C.Structure):
+    _fields_ = [("charge", C.c_double), ("mass", C.c_double), ("bc_particle", C.c_int32 * 4),
+                ("immobile", C.c_int32), ("zero_current", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_particles", C.c_int64 * MAX_SPECIES), ("n_sent_left", C.c_int64),
+                ("n_sent_right", C.c_int64), ("n_removed", C.c_int64), ("n_recv", C.c_int64),
+                ("n_window_removed", C.c_int64), ("n_sorts", C.c_int64), ("kernel_launches", C.c_int64),
+                ("ms_fields", C.c_double), ("ms_push", C.c_double), ("ms_bcs", C.c_double),
+                ("ms_sort", C.c_double), ("ms_exchange", C.c_double)]
+
+
+# every symbol include/cylgpu.h declares: name -> (restype, argtypes)
+H = C.c_void_p
+_DP = C.POINTER(C.c_double)
+SYMBOLS = {
+    "cylgpu_last_error": (C.c_char_p, []),
+    "cylgpu_version": (C.c_int, []),
+    "cylgpu_fabric_create": (C.c_void_p, [C.c_int]),
+    "cylgpu_fabric_destroy": (None, [C.c_void_p]),
+    "cylgpu_nccl_unique_id": (C.c_int, [C.c_void_p]),
+    "cylgpu_create": (C.c_int, [C.POINTER(Config), C.POINTER(H)]),
+    "cylgpu_destroy": (C.c_int, [H]),
+    "cylgpu_set_species": (C.c_int, [H, C.c_int, C.POINTER(SpeciesC)]),
+    "cylgpu_set_dt": (C.c_int, [H, C.c_double]),
+    "cylgpu_set_bc_field": (C.c_int, [H, C.POINTER(C.c_int32)]),
+    "cylgpu_set_stream": (C.c_int, [H, C.c_void_p]),
+    "cylgpu_synchronize": (C.c_int, [H]),
+    "cylgpu_upload_field": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "cylgpu_download_field": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "cylgpu_upload_snapshot": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "cylgpu_download_snapshot": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "cylgpu_field_device_ptr": (C.c_void_p, [H, C.c_int]),
+    "cylgpu_snapshot_field_boundaries": (C.c_int, [H]),
+    "cylgpu_upload_particles": (C.c_int, [H, C.c_int, C.c_int64, C.c_void_p]),
+    "cylgpu_append_particles": (C.c_int, [H, C.c_int, C.c_int64, C.c_void_p]),
+    "cylgpu_download_particles": (C.c_int, [H, C.c_int, C.c_int64, C.c_void_p, C.POINTER(C.c_int64)]),
+    "cylgpu_particle_count": (C.c_int, [H, C.c_int, C.POINTER(C.c_int64)]),
+    "cylgpu_particle_cells": (C.c_int, [H, C.c_int, C.c_int64, C.c_void_p]),
+    "cylgpu_particle_device_ptr": (C.c_void_p, [H, C.c_int, C.c_int]),
+    "cylgpu_fields_half": (C.c_int, [H]),
+    "cylgpu_push": (C.c_int, [H]),
+    "cylgpu_current_finish": (C.c_int, [H]),
+    "cylgpu_fields_final": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cylgpu_window_shift": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), _DP]),
+    "cylgpu_update_e_field": (C.c_int, [H]),
+    "cylgpu_update_b_field": (C.c_int, [H]),
+    "cylgpu_efield_bcs": (C.c_int, [H]),
+    "cylgpu_bfield_bcs": (C.c_int, [H, C.c_int]),
+    "cylgpu_bfield_final_bcs": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cylgpu_particle_bcs": (C.c_int, [H]),
+    "cylgpu_push_no_bcs": (C.c_int, [H]),
+    "cylgpu_current_bcs": (C.c_int, [H]),
+    "cylgpu_sort_particles": (C.c_int, [H]),
+    "cylgpu_set_sort_interval": (C.c_int, [H, C.c_int]),
+    "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
+    "cylgpu_energy": (C.c_int, [H, _DP]),
+    "cylgpu_stats": (C.c_int, [H, C.POINTER(Stats)]),
+    "cylgpu_reset_stats": (C.c_int, [H]),
+    "cylgpu_set_timing": (C.c_int, [H, C.c_int]),
+}
+
+_LIB = None
+
+
+def load():
+    """dlopen libcylgpu.so and bind every symbol; raises if the library or a symbol is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m cylindrical_epoch_b200.build` "
+            "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)   # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib

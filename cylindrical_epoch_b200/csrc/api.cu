@@ -1,0 +1,406 @@
+// api.cu -- the extern "C" boundary declared in include/cylgpu.h.
+#include <cstdarg>
+#include <cstring>
+
+#include "ctx.cuh"
+
+namespace cylgpu {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static int check_handle(cylgpu_handle h) {
+  if (!h) { set_error("null cylgpu handle"); return 1; }
+  cudaError_t e = cudaSetDevice(h->device);
+  if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+static void set_neighbours(cylgpu_ctx* c) {
+  // MPI_CART_CREATE periodicity, mpi_routines.F90:186-199: x is periodic when the x_min
+  // field bc is periodic (or any species' x_min particle bc is)
+  bool periodic = c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  for (int i = 0; i < c->cfg.n_species; ++i)
+    if (c->species[i].set && c->species[i].sp.bc_particle[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC) periodic = true;
+  const int P = c->cfg.nranks, k = c->cfg.rank;
+  c->left = (k - 1 >= 0) ? k - 1 : (periodic ? P - 1 : -1);
+  c->right = (k + 1 < P) ? k + 1 : (periodic ? 0 : -1);
+}
+
+}  // namespace cylgpu
+
+using namespace cylgpu;
+
+extern "C" {
+
+const char* cylgpu_last_error(void) { return g_err; }
+int cylgpu_version(void) { return 100; }
+
+int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
+  if (!cfg || !out) { set_error("null argument"); return 1; }
+  *out = nullptr;
+  if (cfg->nx < 2 * NG || cfg->ny < 2 * NG) { set_error("nx and ny must be >= %d", 2 * NG); return 2; }
+  if (cfg->n_mode < 1 || cfg->n_mode > 16) { set_error("n_mode out of range"); return 2; }
+  if (cfg->n_species < 0 || cfg->n_species > CYLGPU_MAX_SPECIES) { set_error("n_species out of range"); return 2; }
+  if (cfg->rank < 0 || cfg->rank >= cfg->nranks) { set_error("bad rank/nranks"); return 2; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 10;
+  }
+  cylgpu_ctx* c = new cylgpu_ctx();
+  c->cfg = *cfg;
+  if (cfg->device >= 0) c->device = cfg->device;
+  else CUDA_TRY(cudaGetDevice(&c->device));
+  CUDA_TRY(cudaSetDevice(c->device));
+  Geom& g = c->g;
+  g.nx = cfg->nx; g.ny = cfg->ny; g.M = cfg->n_mode;
+  g.SX = g.nx + 2 * NG; g.SY = g.ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  c->dt = cfg->dt;
+  c->x_grid_min_local = cfg->x_grid_min_local;
+  c->x_min = cfg->x_min; c->x_max = cfg->x_max;
+  c->x_min_local = cfg->x_min_local; c->x_max_local = cfg->x_max_local;
+  for (int i = 0; i < 4; ++i) c->bc_field[i] = cfg->bc_field[i];
+  std::memset(&c->stats, 0, sizeof(c->stats));
+  c->timing = false;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  CUDA_TRY(cudaEventCreate(&c->ev0));
+  CUDA_TRY(cudaEventCreate(&c->ev1));
+  const size_t nelem = g.plane * g.M;
+  for (int k = 0; k < CYLGPU_NFIELDS; ++k) {
+    CUDA_TRY(cudaMalloc(&c->f[k], nelem * sizeof(cplx)));
+    CUDA_TRY(cudaMemsetAsync(c->f[k], 0, nelem * sizeof(cplx), c->stream));
+  }
+  CUDA_TRY(cudaMalloc(&c->spare, nelem * sizeof(cplx)));
+  for (int k = 0; k < CYLGPU_NSNAPS; ++k) {
+    CUDA_TRY(cudaMalloc(&c->snap[k], (size_t)g.SY * g.M * sizeof(cplx)));
+    CUDA_TRY(cudaMemsetAsync(c->snap[k], 0, (size_t)g.SY * g.M * sizeof(cplx), c->stream));
+  }
+  CUDA_TRY(cudaMalloc(&c->src, 4 * (size_t)(g.ny + 1) * sizeof(double)));
+  c->halo_elems = (size_t)3 * g.M * g.SY * NG;
+  CUDA_TRY(cudaMalloc(&c->sbuf_l, c->halo_elems * sizeof(cplx)));
+  CUDA_TRY(cudaMalloc(&c->sbuf_r, c->halo_elems * sizeof(cplx)));
+  CUDA_TRY(cudaMalloc(&c->rbuf_l, c->halo_elems * sizeof(cplx)));
+  CUDA_TRY(cudaMalloc(&c->rbuf_r, c->halo_elems * sizeof(cplx)));
+  CUDA_TRY(cudaMalloc(&c->counters, 32 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(c->counters, 0, 32 * sizeof(unsigned long long), c->stream));
+  CUDA_TRY(cudaMallocHost(&c->h_counters, 32 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMalloc(&c->d_energy, 2 * sizeof(double)));
+  if (build_tables(c)) return 1;
+  set_neighbours(c);
+  c->tr = make_transport(c);
+  if (!c->tr) return 6;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return 0;
+}
+
+int cylgpu_destroy(cylgpu_handle c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  destroy_transport(c->tr);
+  for (int k = 0; k < CYLGPU_NFIELDS; ++k) cudaFree(c->f[k]);
+  cudaFree(c->spare);
+  for (int k = 0; k < CYLGPU_NSNAPS; ++k) cudaFree(c->snap[k]);
+  cudaFree(c->tables); cudaFree(c->src);
+  cudaFree(c->sbuf_l); cudaFree(c->sbuf_r); cudaFree(c->rbuf_l); cudaFree(c->rbuf_r);
+  for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i)
+    for (int q = 0; q < 7; ++q) cudaFree(c->species[i].d[q]);
+  cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->hole_list);
+  cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->cell_count); cudaFree(c->scan_blocks);
+  cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
+  cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int cylgpu_set_species(cylgpu_handle c, int isp, const cylgpu_species* sp) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species || !sp) { set_error("bad species index"); return 2; }
+  c->species[isp].sp = *sp;
+  c->species[isp].set = true;
+  set_neighbours(c);
+  return 0;
+}
+
+int cylgpu_set_dt(cylgpu_handle c, double dt) {
+  TRY(check_handle(c));
+  c->dt = dt;
+  return 0;
+}
+
+int cylgpu_set_bc_field(cylgpu_handle c, const int32_t bc[4]) {
+  TRY(check_handle(c));
+  for (int i = 0; i < 4; ++i) c->bc_field[i] = bc[i];
+  // the Cartesian communicator is created once (mpi_routines.F90:179-227); neighbours stay
+  return 0;
+}
+
+int cylgpu_set_stream(cylgpu_handle c, void* stream) {
+  TRY(check_handle(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
+  if (stream) {
+    c->stream = (cudaStream_t)stream;
+  } else {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->own_stream = true;
+  }
+  return 0;
+}
+
+int cylgpu_synchronize(cylgpu_handle c) {
+  TRY(check_handle(c));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+static int field_ok(cylgpu_handle c, int id, int n) {
+  if (id < 0 || id >= n) { set_error("field/snapshot id %d out of range", id); return 2; }
+  (void)c;
+  return 0;
+}
+
+int cylgpu_upload_field(cylgpu_handle c, int id, const void* host) {
+  TRY(check_handle(c)); TRY(field_ok(c, id, CYLGPU_NFIELDS));
+  CUDA_TRY(cudaMemcpyAsync(c->f[id], host, c->g.plane * c->g.M * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int cylgpu_download_field(cylgpu_handle c, int id, void* host) {
+  TRY(check_handle(c)); TRY(field_ok(c, id, CYLGPU_NFIELDS));
+  CUDA_TRY(cudaMemcpyAsync(host, c->f[id], c->g.plane * c->g.M * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int cylgpu_upload_snapshot(cylgpu_handle c, int id, const void* host) {
+  TRY(check_handle(c)); TRY(field_ok(c, id, CYLGPU_NSNAPS));
+  CUDA_TRY(cudaMemcpyAsync(c->snap[id], host, (size_t)c->g.SY * c->g.M * sizeof(cplx), cudaMemcpyHostToDevice,
+                           c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int cylgpu_download_snapshot(cylgpu_handle c, int id, void* host) {
+  TRY(check_handle(c)); TRY(field_ok(c, id, CYLGPU_NSNAPS));
+  CUDA_TRY(cudaMemcpyAsync(host, c->snap[id], (size_t)c->g.SY * c->g.M * sizeof(cplx), cudaMemcpyDeviceToHost,
+                           c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+void* cylgpu_field_device_ptr(cylgpu_handle c, int id) {
+  if (!c || id < 0 || id >= CYLGPU_NFIELDS) return nullptr;
+  return c->f[id];
+}
+int cylgpu_snapshot_field_boundaries(cylgpu_handle c) {
+  TRY(check_handle(c));
+  return do_snapshot(c);
+}
+
+// ---- particles ----
+__global__ void __launch_bounds__(256) k_aos_to_soa(const double* __restrict__ aos, double* d0, double* d1,
+                                                    double* d2, double* d3, double* d4, double* d5, double* d6,
+                                                    int64_t base, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* p = aos + 7 * i;
+  d0[base + i] = p[0]; d1[base + i] = p[1]; d2[base + i] = p[2];
+  d3[base + i] = p[3]; d4[base + i] = p[4]; d5[base + i] = p[5]; d6[base + i] = p[6];
+}
+__global__ void __launch_bounds__(256) k_soa_to_aos(double* __restrict__ aos, const double* d0, const double* d1,
+                                                    const double* d2, const double* d3, const double* d4,
+                                                    const double* d5, const double* d6, int64_t base, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* p = aos + 7 * i;
+  p[0] = d0[base + i]; p[1] = d1[base + i]; p[2] = d2[base + i];
+  p[3] = d3[base + i]; p[4] = d4[base + i]; p[5] = d5[base + i]; p[6] = d6[base + i];
+}
+
+static const int64_t STAGE_PARTS = 1 << 22;   // staging chunk: 4 Mi particles = 224 MiB
+
+static int append_impl(cylgpu_handle c, int isp, int64_t n, const double* host_aos) {
+  if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
+  if (n < 0) { set_error("negative particle count"); return 2; }
+  SpeciesState& S = c->species[isp];
+  if (n == 0) return 0;
+  TRY(reserve_particles(c, isp, S.n + n));
+  double* stage = nullptr;
+  const int64_t chunk = n < STAGE_PARTS ? n : STAGE_PARTS;
+  CUDA_TRY(cudaMalloc(&stage, (size_t)chunk * 7 * sizeof(double)));
+  for (int64_t off = 0; off < n; off += chunk) {
+    const int64_t m = (n - off < chunk) ? n - off : chunk;
+    CUDA_TRY(cudaMemcpyAsync(stage, host_aos + 7 * off, (size_t)m * 7 * sizeof(double), cudaMemcpyHostToDevice,
+                             c->stream));
+    k_aos_to_soa<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(stage, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4],
+                                                                    S.d[5], S.d[6], S.n + off, m);
+    c->stats.kernel_launches += 1;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  CUDA_TRY(cudaFree(stage));
+  S.n += n;
+  c->stats.n_particles[isp] = S.n;
+  c->sorted_valid = false;
+  return 0;
+}
+
+int cylgpu_upload_particles(cylgpu_handle c, int isp, int64_t n, const double* host_aos) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
+  c->species[isp].n = 0;
+  c->stats.n_particles[isp] = 0;
+  return append_impl(c, isp, n, host_aos);
+}
+int cylgpu_append_particles(cylgpu_handle c, int isp, int64_t n, const double* host_aos) {
+  TRY(check_handle(c));
+  return append_impl(c, isp, n, host_aos);
+}
+
+int cylgpu_download_particles(cylgpu_handle c, int isp, int64_t capacity, double* host_aos, int64_t* n_out) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
+  SpeciesState& S = c->species[isp];
+  if (n_out) *n_out = S.n;
+  if (capacity < S.n) { set_error("download_particles: capacity %lld < count %lld", (long long)capacity, (long long)S.n); return 2; }
+  if (S.n == 0) return 0;
+  double* stage = nullptr;
+  const int64_t chunk = S.n < STAGE_PARTS ? S.n : STAGE_PARTS;
+  CUDA_TRY(cudaMalloc(&stage, (size_t)chunk * 7 * sizeof(double)));
+  for (int64_t off = 0; off < S.n; off += chunk) {
+    const int64_t m = (S.n - off < chunk) ? S.n - off : chunk;
+    k_soa_to_aos<<<(unsigned)((m + 255) / 256), 256, 0, c->stream>>>(stage, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4],
+                                                                    S.d[5], S.d[6], off, m);
+    c->stats.kernel_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(host_aos + 7 * off, stage, (size_t)m * 7 * sizeof(double), cudaMemcpyDeviceToHost,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+  }
+  CUDA_TRY(cudaFree(stage));
+  return 0;
+}
+
+int cylgpu_particle_count(cylgpu_handle c, int isp, int64_t* n_out) {
+  if (!c || isp < 0 || isp >= c->cfg.n_species || !n_out) { set_error("bad argument"); return 2; }
+  *n_out = c->species[isp].n;
+  return 0;
+}
+
+int cylgpu_particle_cells(cylgpu_handle c, int isp, int64_t capacity, int32_t* cells_out) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
+  return do_cells(c, isp, capacity, cells_out);
+}
+
+void* cylgpu_particle_device_ptr(cylgpu_handle c, int isp, int comp) {
+  if (!c || isp < 0 || isp >= c->cfg.n_species || comp < 0 || comp > 6) return nullptr;
+  return c->species[isp].d[comp];
+}
+
+// ---- hot path ----
+int cylgpu_update_e_field(cylgpu_handle c) { TRY(check_handle(c)); return launch_update_e(c); }
+int cylgpu_update_b_field(cylgpu_handle c) { TRY(check_handle(c)); return launch_update_b(c); }
+int cylgpu_efield_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_efield_bcs(c); }
+int cylgpu_bfield_bcs(cylgpu_handle c, int mpi_only) { TRY(check_handle(c)); return do_bfield_bcs(c, mpi_only != 0); }
+int cylgpu_bfield_final_bcs(cylgpu_handle c, const double* a, const double* b, const double* d, const double* e) {
+  TRY(check_handle(c));
+  return do_bfield_final_bcs(c, a, b, d, e);
+}
+int cylgpu_particle_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_particle_bcs(c); }
+int cylgpu_push_no_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_push(c); }
+int cylgpu_current_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_current_bcs(c); }
+int cylgpu_sort_particles(cylgpu_handle c) { TRY(check_handle(c)); return do_sort(c); }
+int cylgpu_set_sort_interval(cylgpu_handle c, int n) { TRY(check_handle(c)); c->sort_interval = n; return 0; }
+int cylgpu_set_push_variant(cylgpu_handle c, int v) { TRY(check_handle(c)); c->push_variant = v; return 0; }
+
+// fields.f90:316-337
+int cylgpu_fields_half(cylgpu_handle c) {
+  TRY(check_handle(c));
+  PhaseTimer t(c, &c->stats.ms_fields);
+  TRY(launch_update_e(c));
+  TRY(do_efield_bcs(c));
+  // bxm_old = bxm etc. (fields.f90:326-328)
+  const size_t bytes = c->g.plane * c->g.M * sizeof(cplx);
+  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BXM_OLD], c->f[CYLGPU_BXM], bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BRM_OLD], c->f[CYLGPU_BRM], bytes, cudaMemcpyDeviceToDevice, c->stream));
+  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BTM_OLD], c->f[CYLGPU_BTM], bytes, cudaMemcpyDeviceToDevice, c->stream));
+  TRY(launch_update_b(c));
+  return do_bfield_bcs(c, true);
+}
+
+// particles.F90:28-734 (push + r_min fold + particle_bcs)
+int cylgpu_push(cylgpu_handle c) {
+  TRY(check_handle(c));
+  {
+    PhaseTimer t(c, &c->stats.ms_push);
+    TRY(do_push(c));
+  }
+  PhaseTimer t(c, &c->stats.ms_bcs);
+  return do_particle_bcs(c);
+}
+
+int cylgpu_current_finish(cylgpu_handle c) {
+  TRY(check_handle(c));
+  PhaseTimer t(c, &c->stats.ms_bcs);
+  return do_current_finish(c);
+}
+
+// fields.f90:341-353
+int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2min, const double* s1max,
+                        const double* s2max) {
+  TRY(check_handle(c));
+  PhaseTimer t(c, &c->stats.ms_fields);
+  TRY(launch_update_b(c));
+  TRY(do_bfield_final_bcs(c, s1min, s2min, s1max, s2max));
+  TRY(launch_update_e(c));
+  return do_efield_bcs(c);
+}
+
+// window.F90:62-94, one cell.  grid5 = {x_grid_min_local, x_min, x_max, x_min_local,
+// x_max_local} AFTER the host's setup_grid_x for the shifted window.
+int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* const* new_aos, const double* grid5) {
+  TRY(check_handle(c));
+  if (!grid5) { set_error("window_shift needs the shifted grid"); return 2; }
+  if (n_new && new_aos) {
+    for (int isp = 0; isp < c->cfg.n_species; ++isp)
+      if (n_new[isp] > 0) TRY(append_impl(c, isp, n_new[isp], new_aos[isp]));
+  }
+  c->x_grid_min_local = grid5[0];
+  c->x_min = grid5[1]; c->x_max = grid5[2];
+  c->x_min_local = grid5[3]; c->x_max_local = grid5[4];
+  TRY(do_remove_behind(c));
+  return do_shift_fields(c);
+}
+
+int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return do_energy(c, out2); }
+
+int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {
+  if (!c || !out) { set_error("bad argument"); return 2; }
+  for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) c->stats.n_particles[i] = c->species[i].n;
+  *out = c->stats;
+  return 0;
+}
+int cylgpu_reset_stats(cylgpu_handle c) {
+  if (!c) return 2;
+  c->stats.kernel_launches = 0;
+  c->stats.ms_fields = c->stats.ms_push = c->stats.ms_bcs = c->stats.ms_sort = c->stats.ms_exchange = 0.0;
+  return 0;
+}
+int cylgpu_set_timing(cylgpu_handle c, int on) {
+  if (!c) return 2;
+  c->timing = on != 0;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,659 @@
+// bcs.cu -- field / current boundary conditions, x-halo exchange, laser + outflow line
+// updates, axis current fold, boundary snapshots and the moving-window field shift.
+// Replaces boundary.F90 (field_mode_bc, field_mode_clamp_zero, field_mode_zero_gradient,
+// particle_reflection_bcs_complex, particle_periodic_bcs_complex, efield_bcs, bfield_bcs,
+// bfield_final_bcs, current_bcs, current_bcs_r_min_final), laser.f90 outflow_bcs_*,
+// current_smooth.F90 current_finish and window.F90 shift_fields.
+#include "ctx.cuh"
+
+namespace cylgpu {
+
+enum { OP_NONE = 0, OP_CLAMP = 1, OP_ZEROGRAD = 2 };
+
+struct Tri {
+  cplx* f[3];
+  int op[3];
+  int stag[3];   // stagger of each array in the direction normal to the boundary
+};
+
+// x_min / x_max ghost fill: boundary.F90:772-829 (clamp) and :654-707 (zero gradient).
+// One thread per (row j, mode, array).
+__global__ void __launch_bounds__(128) k_edge_x(Geom g, Tri t, int side) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (j > g.ny + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int op = t.op[k];
+  if (op == OP_NONE) return;
+  cplx* f = t.f[k];
+  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
+  if (side == CYLGPU_BD_X_MIN) {
+    if (t.stag[k]) {
+      for (int i = 1; i <= NG - 1; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG - i, j, im)];
+      if (op == OP_CLAMP) f[g.at(0, j, im)] = C(0.0, 0.0);
+    } else {
+      for (int i = 1; i <= NG; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG + 1 - i, j, im)];
+    }
+  } else {
+    const int nn = g.nx;
+    if (t.stag[k]) {
+      if (op == OP_CLAMP) f[g.at(nn, j, im)] = C(0.0, 0.0);
+      for (int i = 1; i <= NG - 1; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn - i, j, im)];
+    } else {
+      for (int i = 1; i <= NG; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn + 1 - i, j, im)];
+    }
+  }
+}
+
+// r_max ghost fill; one thread per (column ix, mode, array)
+__global__ void __launch_bounds__(128) k_edge_y(Geom g, Tri t) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (ix > g.nx + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int op = t.op[k];
+  if (op == OP_NONE) return;
+  cplx* f = t.f[k];
+  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
+  const int nn = g.ny;
+  if (t.stag[k]) {
+    if (op == OP_CLAMP) f[g.at(ix, nn, im)] = C(0.0, 0.0);
+    for (int i = 1; i <= NG - 1; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn - i, im)];
+  } else {
+    for (int i = 1; i <= NG; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn + 1 - i, im)];
+  }
+}
+
+static void launch_edge(cylgpu_ctx* c, const Tri& t, int bd) {
+  const Geom& g = c->g;
+  if (bd == CYLGPU_BD_Y_MAX) {
+    k_edge_y<<<dim3((g.SX + 127) / 128, g.M, 3), 128, 0, c->stream>>>(g, t);
+  } else {
+    k_edge_x<<<dim3((g.SY + 127) / 128, g.M, 3), 128, 0, c->stream>>>(g, t, bd);
+  }
+  c->stats.kernel_launches += 1;
+}
+
+// ---- x halo: boundary.F90:158-169,500-553.  Buffer layout [comp][im][row][NG]. ----
+struct Halo3 {
+  cplx* f[3];
+  int skip[3];   // rows excluded at the top (the one-row shift of the r-staggered arrays,
+                 // boundary.F90:1362-1371,1428-1430: row ny+ng never takes part)
+};
+
+// mode 0: pack interior edge columns (send_l <- 1..ng, send_r <- nx+1-ng..nx)
+// mode 1: pack ghost columns          (send_l <- 1-ng..0, send_r <- nx+1..nx+ng)  [J sums]
+__global__ void __launch_bounds__(128) k_halo_pack(Geom g, Halo3 h, cplx* __restrict__ send_l,
+                                                   cplx* __restrict__ send_r, int mode) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = g.SY * NG;
+  if (t >= per) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int row = t / NG, i = t % NG + 1;   // i = 1..ng
+  const int j = row + 1 - NG;
+  if (j > g.ny + NG - h.skip[k]) return;
+  const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
+  const cplx* f = h.f[k];
+  if (mode == 0) {
+    if (send_l) send_l[b] = f[g.at(i, j, im)];
+    if (send_r) send_r[b] = f[g.at(g.nx - NG + i, j, im)];
+  } else {
+    if (send_l) send_l[b] = f[g.at(i - NG, j, im)];
+    if (send_r) send_r[b] = f[g.at(g.nx + i, j, im)];
+  }
+}
+
+// mode 0: ghost <- received (recv_l -> 1-ng..0, recv_r -> nx+1..nx+ng)
+// mode 1: interior += received (recv_l -> 1..ng, recv_r -> nx+1-ng..nx), boundary.F90:1192,1200
+__global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx* __restrict__ recv_l,
+                                                     const cplx* __restrict__ recv_r, int mode) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int per = g.SY * NG;
+  if (t >= per) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int row = t / NG, i = t % NG + 1;
+  const int j = row + 1 - NG;
+  if (j > g.ny + NG - h.skip[k]) return;
+  const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
+  cplx* f = h.f[k];
+  if (mode == 0) {
+    if (recv_l) f[g.at(i - NG, j, im)] = recv_l[b];
+    if (recv_r) f[g.at(g.nx + i, j, im)] = recv_r[b];
+  } else {
+    if (recv_l) { const size_t o = g.at(i, j, im); f[o] = f[o] + recv_l[b]; }
+    if (recv_r) { const size_t o = g.at(g.nx - NG + i, j, im); f[o] = f[o] + recv_r[b]; }
+  }
+}
+
+static int exchange3(cylgpu_ctx* c, const Halo3& h, int mode, bool send_l, bool send_r, bool recv_l,
+                     bool recv_r) {
+  const Geom& g = c->g;
+  if (!(send_l || send_r || recv_l || recv_r)) return 0;
+  const size_t bytes = c->halo_elems * sizeof(cplx);
+  dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+  if (send_l || send_r) {
+    k_halo_pack<<<grd, 128, 0, c->stream>>>(g, h, send_l ? c->sbuf_l : nullptr, send_r ? c->sbuf_r : nullptr,
+                                            mode);
+    c->stats.kernel_launches += 1;
+  }
+  TRY(transport_sendrecv(c, send_l ? c->sbuf_l : nullptr, send_l ? bytes : 0, recv_l ? c->rbuf_l : nullptr,
+                         recv_l ? bytes : 0, send_r ? c->sbuf_r : nullptr, send_r ? bytes : 0,
+                         recv_r ? c->rbuf_r : nullptr, recv_r ? bytes : 0));
+  if (recv_l || recv_r) {
+    k_halo_unpack<<<grd, 128, 0, c->stream>>>(g, h, recv_l ? c->rbuf_l : nullptr, recv_r ? c->rbuf_r : nullptr,
+                                              mode);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// field_mode_bc on three arrays at once: one packed message per neighbour instead of the
+// reference's 3 * n_mode MPI_SENDRECV pairs.
+int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip2) {
+  Halo3 h;
+  h.f[0] = c->f[f0]; h.f[1] = c->f[f1]; h.f[2] = c->f[f2];
+  h.skip[0] = skip0; h.skip[1] = skip1; h.skip[2] = skip2;
+  // MPI_SENDRECV with MPI_PROC_NULL neighbours is a no-op; ghost columns are only filled
+  // where `.NOT. x_max_boundary .OR. bc_field == periodic` (boundary.F90:531,544)
+  const bool has_l = c->left >= 0, has_r = c->right >= 0;
+  const bool fill_r = has_r && (!c->cfg.x_max_boundary || c->bc_field[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC);
+  const bool fill_l = has_l && (!c->cfg.x_min_boundary || c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC);
+  // what I send left is what my left neighbour uses to fill ITS right ghosts, and vice versa;
+  // with x-slabs the neighbour's fill condition mirrors mine
+  return exchange3(c, h, 0, fill_l, fill_r, fill_l, fill_r);
+}
+
+// ---- efield_bcs / bfield_bcs: boundary.F90:1355-1476 ----
+static void ops_for(int bc, int conduct0, int conduct1, int conduct2, int* op) {
+  op[0] = op[1] = op[2] = OP_NONE;
+  if (bc == CYLGPU_BC_CONDUCT) { op[0] = conduct0; op[1] = conduct1; op[2] = conduct2; }
+}
+
+static void general_ops(int bc, int* op) {
+  op[0] = op[1] = op[2] = OP_NONE;
+  if (bc == CYLGPU_BC_CLAMP || bc == CYLGPU_BC_SIMPLE_LASER || bc == CYLGPU_BC_SIMPLE_OUTFLOW)
+    op[0] = op[1] = op[2] = OP_CLAMP;
+  if (bc == CYLGPU_BC_ZERO_GRADIENT || bc == CYLGPU_BC_CPML_LASER || bc == CYLGPU_BC_CPML_OUTFLOW)
+    op[0] = op[1] = op[2] = OP_ZEROGRAD;
+}
+
+static bool on_boundary(const cylgpu_ctx* c, int bd) {
+  if (bd == CYLGPU_BD_X_MIN) return c->cfg.x_min_boundary != 0;
+  if (bd == CYLGPU_BD_X_MAX) return c->cfg.x_max_boundary != 0;
+  return true;   // nprocy = 1
+}
+
+// stagger flags (setup.F90:126-136): Exm (x:F,r:T) Erm (T,F) Etm (T,T) Bxm (T,F) Brm (F,T) Btm (F,F)
+static const int STAG_X[6] = {0, 1, 1, 1, 0, 0};
+static const int STAG_Y[6] = {1, 0, 1, 0, 1, 0};
+
+static int edge_bcs(cylgpu_ctx* c, int base, const int cond_x[3], const int cond_y[3]) {
+  Tri t;
+  for (int k = 0; k < 3; ++k) t.f[k] = c->f[base + k];
+  auto apply = [&](int bd, const int* op) {
+    if (op[0] == OP_NONE && op[1] == OP_NONE && op[2] == OP_NONE) return;
+    if (c->bc_field[bd] == CYLGPU_BC_PERIODIC) return;
+    if (!on_boundary(c, bd)) return;
+    for (int k = 0; k < 3; ++k) {
+      t.op[k] = op[k];
+      t.stag[k] = (bd == CYLGPU_BD_Y_MAX) ? STAG_Y[base + k] : STAG_X[base + k];
+    }
+    launch_edge(c, t, bd);
+  };
+  int op[3];
+  for (int bd : {CYLGPU_BD_X_MIN, CYLGPU_BD_X_MAX}) {
+    ops_for(c->bc_field[bd], cond_x[0], cond_x[1], cond_x[2], op);
+    apply(bd, op);
+  }
+  ops_for(c->bc_field[CYLGPU_BD_Y_MAX], cond_y[0], cond_y[1], cond_y[2], op);
+  apply(CYLGPU_BD_Y_MAX, op);
+  for (int bd : {CYLGPU_BD_X_MIN, CYLGPU_BD_X_MAX, CYLGPU_BD_Y_MAX}) {
+    general_ops(c->bc_field[bd], op);
+    apply(bd, op);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int do_efield_bcs(cylgpu_ctx* c) {
+  TRY(halo_x(c, CYLGPU_EXM, CYLGPU_ERM, CYLGPU_ETM, 1, 0, 1));
+  const int cx[3] = {OP_CLAMP, OP_ZEROGRAD, OP_ZEROGRAD};
+  const int cy[3] = {OP_ZEROGRAD, OP_CLAMP, OP_ZEROGRAD};
+  return edge_bcs(c, CYLGPU_EXM, cx, cy);
+}
+
+int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only) {
+  TRY(halo_x(c, CYLGPU_BXM, CYLGPU_BRM, CYLGPU_BTM, 0, 1, 0));
+  if (mpi_only) return 0;
+  const int cx[3] = {OP_ZEROGRAD, OP_CLAMP, OP_CLAMP};
+  const int cy[3] = {OP_CLAMP, OP_ZEROGRAD, OP_CLAMP};
+  return edge_bcs(c, CYLGPU_BXM, cx, cy);
+}
+
+// ---- laser / outflow line updates: laser.f90:411-690 ----
+struct FieldSet {
+  cplx *exm, *erm, *etm, *bxm, *brm, *btm, *jxm, *jrm, *jtm;
+  const cplx *bxo, *bro, *bto, *jxo, *jro, *jto;
+};
+
+// side 0: x_min (laser.f90:411-520), side 1: x_max (:524-633).  One thread per (ir, im).
+// REFERENCE QUIRKS reproduced: `r_d_vals` is declared (0:ny) but used whole-array against
+// (1:ny) sections, so element ir pairs with r_d_vals(ir-1); on x_max the same holds for
+// source_t (laser.f90:604).
+__global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cplx* __restrict__ snap_er,
+                                                   const cplx* __restrict__ snap_et,
+                                                   const cplx* __restrict__ snap_bx,
+                                                   const cplx* __restrict__ snap_br,
+                                                   const cplx* __restrict__ snap_bt,
+                                                   const double* __restrict__ s1, const double* __restrict__ s2,
+                                                   int side, double dx, double dy, double dt,
+                                                   double y_grid_min_local) {
+  const int ir = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ny
+  const int im = blockIdx.y;
+  if (ir > g.ny) return;
+  const double c = C_LIGHT;
+  const double dtc2 = dt * (c * c);
+  const double lx = dtc2 / dx, lr = dtc2 / dy;
+  const double sum = 1.0 / (lx + c), diff = lx - c, dt_eps = dt / EPSILON0;
+  const size_t sn = (size_t)im * g.SY + (ir + NG - 1);   // snapshot (ir, im)
+  const int nx = g.nx;
+  if (side == 0) {
+    F.bxm[g.at(0, ir, im)] = snap_bx[sn];
+    if (ir >= 1) {
+      const cplx source_t = (im == 1) ? C(s1[ir], s2[ir]) : C(0.0, 0.0);
+      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);   // r_d_vals(ir-1)
+      F.btm[g.at(1, ir, im)] =
+          sum * (4.0 * source_t + 2.0 * (snap_er[sn] + c * snap_bt[sn]) - 2.0 * F.erm[g.at(1, ir, im)]
+                 + (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(1, ir, im)]) / r_d_q
+                 + dt_eps * F.jrm[g.at(1, ir, im)] + diff * F.btm[g.at(2, ir, im)]);
+    }
+    if (ir >= 1 && ir <= g.ny - 1) {
+      // source_r = -i*s1 + s2
+      const cplx source_r = (im == 1) ? C(s2[ir], -s1[ir]) : C(0.0, 0.0);
+      F.brm[g.at(1, ir, im)] =
+          sum * (-4.0 * source_r - 2.0 * (snap_et[sn] + c * snap_br[sn]) + 2.0 * F.etm[g.at(1, ir, im)]
+                 - lr * (F.bxm[g.at(1, ir + 1, im)] - F.bxm[g.at(1, ir, im)])
+                 - dt_eps * F.jtm[g.at(1, ir, im)] + diff * F.brm[g.at(2, ir, im)]);
+    }
+  } else {
+    F.bxm[g.at(nx, ir, im)] = snap_bx[sn];
+    if (ir >= 1) {
+      const cplx source_t = (im == 1) ? C(s1[ir - 1], s2[ir - 1]) : C(0.0, 0.0);
+      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);
+      F.btm[g.at(nx, ir, im)] =
+          sum * (-4.0 * source_t - 2.0 * (snap_er[sn] + c * snap_bt[sn]) + 2.0 * F.erm[g.at(nx - 1, ir, im)]
+                 - (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(nx - 1, ir, im)]) / r_d_q
+                 - dt_eps * F.jrm[g.at(nx - 1, ir, im)] + diff * F.btm[g.at(nx - 1, ir, im)]);
+    }
+    if (ir >= 1 && ir <= g.ny - 1) {
+      const cplx source_r = (im == 1) ? C(s2[ir], -s1[ir]) : C(0.0, 0.0);
+      F.brm[g.at(nx, ir, im)] =
+          sum * (4.0 * source_r + 2.0 * (snap_et[sn] + c * snap_br[sn]) - 2.0 * F.etm[g.at(nx - 1, ir, im)]
+                 + lr * (F.bxm[g.at(nx - 1, ir + 1, im)] - F.bxm[g.at(nx - 1, ir, im)])
+                 + dt_eps * F.jtm[g.at(nx - 1, ir, im)] + diff * F.brm[g.at(nx - 1, ir, im)]);
+    }
+  }
+}
+
+// laser.f90:637-690.  REFERENCE QUIRK reproduced: icdt_2r is declared REAL(num) but assigned
+// a purely imaginary value, so it is 0 and the azimuthal coupling terms vanish.
+__global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int ix_l, int ix_h, double dx,
+                                                       double dy, double dt, double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
+  const int im = blockIdx.y;
+  if (ix > g.nx) return;
+  const int ny = g.ny;
+  const double c = C_LIGHT;
+  const double dtc2 = dt * (c * c);
+  const double inv_r = 1.0 / ((double)((float)ny - 1.5f) * dy + y_grid_min_local);
+  const double dtc2_4r = 0.25 * dtc2 * inv_r;
+  const double icdt_2r = 0.0;
+  const double lx = dtc2 / dx, ly = dtc2 / dy;
+  const double sum_x = 1.0 / (ly + c);
+  const double sum_t = 1.0 / (ly + c + dtc2_4r);
+  const double dt_2eps = 0.5 * dt / EPSILON0;
+  if (ix >= ix_l && ix <= ix_h) {
+    F.bxm[g.at(ix, ny, im)] =
+        sum_x * ((-F.bxm[g.at(ix, ny - 1, im)]) * (c - ly) - F.bxo[g.at(ix, ny, im)] * (-c + ly)
+                 - F.bxo[g.at(ix, ny - 1, im)] * (-c - ly) - ((c * dt) * inv_r) * F.etm[g.at(ix, ny - 1, im)]
+                 + (0.5 * lx) * (F.brm[g.at(ix + 1, ny - 1, im)] - F.brm[g.at(ix, ny - 1, im)]
+                                 + F.bro[g.at(ix + 1, ny - 1, im)] - F.bro[g.at(ix, ny - 1, im)])
+                 - (icdt_2r * (double)im) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)])
+                 - dt_2eps * (F.jtm[g.at(ix, ny - 1, im)] + F.jto[g.at(ix, ny - 1, im)]));
+  }
+  if (ix >= 1) {
+    F.btm[g.at(ix, ny, im)] =
+        sum_t * ((-F.btm[g.at(ix, ny - 1, im)]) * (c - ly + dtc2_4r) - F.bto[g.at(ix, ny, im)] * (-c + ly + dtc2_4r)
+                 - F.bto[g.at(ix, ny - 1, im)] * (-c - ly + dtc2_4r)
+                 - ((0.5 * lx) / c) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)]
+                                       - F.erm[g.at(ix - 1, ny, im)] - F.erm[g.at(ix - 1, ny - 1, im)])
+                 - ((icdt_2r * (double)im) * c) * (F.brm[g.at(ix, ny - 1, im)] + F.bro[g.at(ix, ny - 1, im)])
+                 + dt_2eps * (F.jxm[g.at(ix, ny - 1, im)] + F.jxo[g.at(ix, ny - 1, im)]));
+  }
+}
+
+// boundary.F90:1528-1531 zero_b on r_max
+__global__ void __launch_bounds__(128) k_zero_b_rmax(Geom g, cplx* bxm, cplx* brm, cplx* btm) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  const int im = blockIdx.y;
+  if (ix > g.nx + NG) return;
+  const size_t o = g.at(ix, g.ny, im);
+  bxm[o] = C(0.0, 0.0);
+  brm[o] = C(0.0, 0.0);
+  btm[o] = C(0.0, 0.0);
+}
+
+static FieldSet fieldset(cylgpu_ctx* c) {
+  FieldSet F;
+  F.exm = c->f[CYLGPU_EXM]; F.erm = c->f[CYLGPU_ERM]; F.etm = c->f[CYLGPU_ETM];
+  F.bxm = c->f[CYLGPU_BXM]; F.brm = c->f[CYLGPU_BRM]; F.btm = c->f[CYLGPU_BTM];
+  F.jxm = c->f[CYLGPU_JXM]; F.jrm = c->f[CYLGPU_JRM]; F.jtm = c->f[CYLGPU_JTM];
+  F.bxo = c->f[CYLGPU_BXM_OLD]; F.bro = c->f[CYLGPU_BRM_OLD]; F.bto = c->f[CYLGPU_BTM_OLD];
+  F.jxo = c->f[CYLGPU_JXM_OLD]; F.jro = c->f[CYLGPU_JRM_OLD]; F.jto = c->f[CYLGPU_JTM_OLD];
+  return F;
+}
+
+int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
+                        const double* s2max) {
+  const Geom& g = c->g;
+  TRY(do_bfield_bcs(c, false));
+  FieldSet F = fieldset(c);
+  const int nsrc = g.ny + 1;
+  // sources are host arrays evaluated by the Fortran laser blocks (laser.f90:442-461)
+  const double* hs[4] = {s1min, s2min, s1max, s2max};
+  for (int k = 0; k < 4; ++k) {
+    if (hs[k]) CUDA_TRY(cudaMemcpyAsync(c->src + (size_t)k * nsrc, hs[k], nsrc * sizeof(double),
+                                        cudaMemcpyHostToDevice, c->stream));
+    else CUDA_TRY(cudaMemsetAsync(c->src + (size_t)k * nsrc, 0, nsrc * sizeof(double), c->stream));
+  }
+  dim3 grd((g.ny + 1 + 127) / 128, g.M);
+  if (c->cfg.x_min_boundary) {
+    const int b = c->bc_field[CYLGPU_BD_X_MIN];
+    if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW) {
+      k_outflow_x<<<grd, 128, 0, c->stream>>>(g, F, c->snap[1], c->snap[2], c->snap[3], c->snap[4], c->snap[5],
+                                              c->src, c->src + nsrc, 0, c->cfg.dx, c->cfg.dy, c->dt,
+                                              c->cfg.y_grid_min_local);
+      c->stats.kernel_launches += 1;
+    }
+  }
+  if (c->cfg.x_max_boundary) {
+    const int b = c->bc_field[CYLGPU_BD_X_MAX];
+    if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW) {
+      k_outflow_x<<<grd, 128, 0, c->stream>>>(g, F, c->snap[7], c->snap[8], c->snap[9], c->snap[10], c->snap[11],
+                                              c->src + 2 * nsrc, c->src + 3 * nsrc, 1, c->cfg.dx, c->cfg.dy,
+                                              c->dt, c->cfg.y_grid_min_local);
+      c->stats.kernel_launches += 1;
+    }
+  }
+  if (c->bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
+    const int ix_l = c->cfg.x_min_boundary ? 1 : 0;
+    const int ix_h = c->cfg.x_max_boundary ? g.nx - 1 : g.nx;
+    k_outflow_r_max<<<dim3((g.nx + 1 + 127) / 128, g.M), 128, 0, c->stream>>>(
+        g, F, ix_l, ix_h, c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
+    c->stats.kernel_launches += 1;
+  } else if (c->bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
+    k_zero_b_rmax<<<dim3((g.SX + 127) / 128, g.M), 128, 0, c->stream>>>(g, F.bxm, F.brm, F.btm);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  // the source upload must have been consumed before the caller reuses its host arrays
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return do_bfield_bcs(c, true);
+}
+
+// ---- currents ----
+// current_bcs_r_min_final, boundary.F90:1909-1959: fold the rows below the axis back and set
+// the axis rows.  One thread per column; rows are independent between columns.
+__global__ void __launch_bounds__(128) k_r_min_final(Geom g, cplx* __restrict__ jxm, cplx* __restrict__ jrm,
+                                                     cplx* __restrict__ jtm) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  const int im = blockIdx.y;
+  if (ix > g.nx + NG) return;
+  const double mode_sign = (im & 1) ? -1.0 : 1.0;
+  for (int j = 2; j <= JNG; ++j) {
+    const size_t lo = g.at(ix, 1 - j, im);
+    const size_t a = g.at(ix, j - 1, im), b = g.at(ix, j, im);
+    jxm[a] = jxm[a] + mode_sign * jxm[lo];
+    jrm[b] = jrm[b] - mode_sign * jrm[lo];
+    jtm[a] = jtm[a] - mode_sign * jtm[lo];
+    jxm[lo] = C(0.0, 0.0);
+    jrm[lo] = C(0.0, 0.0);
+    jtm[lo] = C(0.0, 0.0);
+  }
+  {
+    const size_t a = g.at(ix, 1, im);
+    jrm[a] = jrm[a] - mode_sign * jrm[g.at(ix, 0, im)];
+  }
+  const size_t a0 = g.at(ix, 0, im), a1 = g.at(ix, 1, im), a2 = g.at(ix, 2, im);
+  if (im > 0) jxm[a0] = C(0.0, 0.0);
+  else jxm[a0] = (4.0 * jxm[a1] - jxm[a2]) / 3.0;
+  if (im == 1) {
+    const cplx jt0 = (C(0.0, -1.0) * (9.0 * jrm[a1] - jrm[a2])) / 8.0;
+    jtm[a0] = jt0;
+    jrm[a0] = C(0.0, 2.0) * jt0 - jrm[a1];
+  } else {
+    jtm[a0] = C(0.0, 0.0);
+    jrm[a0] = -jrm[a1];
+  }
+}
+
+int do_r_min_final(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  k_r_min_final<<<dim3((g.SX + 127) / 128, g.M), 128, 0, c->stream>>>(g, c->f[CYLGPU_JXM], c->f[CYLGPU_JRM],
+                                                                     c->f[CYLGPU_JTM]);
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// particle_reflection_bcs_complex, boundary.F90:918-1015 (the COMPLEX variant's index pairing).
+// x walls: one thread per (row, mode, comp); comp 0 = jx (flip_dir 1), 1 = jr, 2 = jt.
+__global__ void __launch_bounds__(128) k_jreflect_x(Geom g, cplx* jx, cplx* jr, cplx* jt, int side) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (j > g.ny + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  cplx* a = (k == 0) ? jx : (k == 1) ? jr : jt;
+  const bool flip = (k == 0);
+  if (side == 0) {
+    for (int i = 1; i <= NG - 1; ++i) {
+      if (flip) {
+        const size_t o = g.at(i, j, im), s = g.at(1 - i, j, im);
+        a[o] = a[o] - a[s];
+        a[s] = C(0.0, 0.0);
+      } else {
+        const size_t o = g.at(i, j, im), s = g.at(-i, j, im);
+        a[o] = a[o] + a[s];
+        a[s] = C(0.0, 0.0);
+      }
+    }
+  } else {
+    const int nn = g.nx;
+    for (int i = 1; i <= NG; ++i) {
+      if (flip) {
+        const size_t o = g.at(nn + 1 - i, j, im), s = g.at(nn + i, j, im);
+        a[o] = a[o] - a[s];
+        a[s] = C(0.0, 0.0);
+      } else {
+        const size_t o = g.at(nn - i, j, im), s = g.at(nn + i, j, im);
+        a[o] = a[o] + a[s];
+        a[s] = C(0.0, 0.0);
+      }
+    }
+  }
+}
+
+// r_max wall with the face-radius ratios of boundary.F90:988-1005
+__global__ void __launch_bounds__(128) k_jreflect_y(Geom g, cplx* jx, cplx* jr, cplx* jt, double dy,
+                                                    double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (ix > g.nx + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int nn = g.ny;
+  const double r_max = y_grid_min_local + ((double)g.ny - 0.5) * dy;
+  if (k == 1) {          // jr: flip_dir == 2
+    for (int i = 1; i <= NG; ++i) {
+      const double num = r_max + ((double)i - 0.5) * dy, den = r_max - ((double)i - 0.5) * dy;
+      const size_t o = g.at(ix, nn + 1 - i, im), s = g.at(ix, nn + i, im);
+      jr[o] = jr[o] - (jr[s] * num) / den;
+      jr[s] = C(0.0, 0.0);
+    }
+  } else if (k == 0) {   // jx: flip_dir == 1
+    for (int i = 1; i <= NG; ++i) {
+      const double num = r_max + (double)i * dy, den = r_max - (double)i * dy;
+      const size_t o = g.at(ix, nn - i, im), s = g.at(ix, nn + i, im);
+      jx[o] = jx[o] + (jx[s] * num) / den;
+      jx[s] = C(0.0, 0.0);
+    }
+  } else {
+    for (int i = 1; i <= NG; ++i) {
+      const size_t o = g.at(ix, nn - i, im), s = g.at(ix, nn + i, im);
+      jt[o] = jt[o] + jt[s];
+      jt[s] = C(0.0, 0.0);
+    }
+  }
+}
+
+// bc_allspecies (boundary.F90:60-75): common particle bc of all species, -1 if mixed
+static int bc_allspecies(const cylgpu_ctx* c, int bd) {
+  int b = -2;
+  for (int i = 0; i < c->cfg.n_species; ++i) {
+    if (!c->species[i].set) continue;
+    if (b == -2) b = c->species[i].sp.bc_particle[bd];
+    else if (b != c->species[i].sp.bc_particle[bd]) return -1;
+  }
+  return b == -2 ? CYLGPU_BC_OPEN : b;
+}
+
+int do_current_bcs(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  int bca[4];
+  for (int bd = 0; bd < 4; ++bd) {
+    bca[bd] = bc_allspecies(c, bd);
+    if (bd != CYLGPU_BD_Y_MIN && bca[bd] == -1) {
+      set_error("mixed per-species particle boundary conditions are not supported");
+      return 2;
+    }
+  }
+  cplx *jx = c->f[CYLGPU_JXM], *jr = c->f[CYLGPU_JRM], *jt = c->f[CYLGPU_JTM];
+  if (c->cfg.x_min_boundary && bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT) {
+    k_jreflect_x<<<dim3((g.SY + 127) / 128, g.M, 3), 128, 0, c->stream>>>(g, jx, jr, jt, 0);
+    c->stats.kernel_launches += 1;
+  }
+  if (c->cfg.x_max_boundary && bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT) {
+    k_jreflect_x<<<dim3((g.SY + 127) / 128, g.M, 3), 128, 0, c->stream>>>(g, jx, jr, jt, 1);
+    c->stats.kernel_launches += 1;
+  }
+  if (bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT) {
+    k_jreflect_y<<<dim3((g.SX + 127) / 128, g.M, 3), 128, 0, c->stream>>>(g, jx, jr, jt, c->cfg.dy,
+                                                                         c->cfg.y_grid_min_local);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  // particle_periodic_bcs_complex, boundary.F90:1133-1203: ADD the neighbour's ghost columns
+  // into my interior edge columns.  neighbour_local(+-1) is nulled on a domain boundary
+  // whose particle bc is not periodic.
+  const bool to_l = c->left >= 0 && !(c->cfg.x_min_boundary && bca[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC);
+  const bool to_r = c->right >= 0 && !(c->cfg.x_max_boundary && bca[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC);
+  Halo3 h;
+  h.f[0] = jx; h.f[1] = jr; h.f[2] = jt;
+  h.skip[0] = h.skip[1] = h.skip[2] = 0;
+  return exchange3(c, h, 1, to_l, to_r, to_l, to_r);
+}
+
+int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45, smoothing off
+  TRY(do_current_bcs(c));
+  return halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0);
+}
+
+// ---- setup_field_boundaries, setup.F90:393-423 (no cpml: nx0 = 1, nx1 = nx) ----
+struct Snaps { cplx* s[CYLGPU_NSNAPS]; };
+__global__ void __launch_bounds__(128) k_snapshot(Geom g, FieldSet F, Snaps S) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (row >= g.SY) return;
+  const int j = row + 1 - NG;
+  const size_t sn = (size_t)im * g.SY + row;
+  const int nx0 = 1, nx1 = g.nx;
+  S.s[0][sn] = 0.5 * (F.exm[g.at(nx0, j, im)] + F.exm[g.at(nx0 - 1, j, im)]);
+  S.s[1][sn] = F.erm[g.at(nx0 - 1, j, im)];
+  S.s[2][sn] = F.etm[g.at(nx0 - 1, j, im)];
+  S.s[3][sn] = F.bxm[g.at(nx0 - 1, j, im)];
+  S.s[4][sn] = 0.5 * (F.brm[g.at(nx0, j, im)] + F.brm[g.at(nx0 - 1, j, im)]);
+  S.s[5][sn] = 0.5 * (F.btm[g.at(nx0, j, im)] + F.btm[g.at(nx0 - 1, j, im)]);
+  S.s[6][sn] = 0.5 * (F.exm[g.at(nx1, j, im)] + F.exm[g.at(nx1 + 1, j, im)]);
+  S.s[7][sn] = F.erm[g.at(nx1, j, im)];
+  S.s[8][sn] = F.etm[g.at(nx1, j, im)];
+  S.s[9][sn] = F.bxm[g.at(nx1, j, im)];
+  S.s[10][sn] = 0.5 * (F.brm[g.at(nx1, j, im)] + F.brm[g.at(nx1 + 1, j, im)]);
+  S.s[11][sn] = 0.5 * (F.btm[g.at(nx1, j, im)] + F.btm[g.at(nx1 + 1, j, im)]);
+}
+
+int do_snapshot(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  Snaps S;
+  for (int k = 0; k < CYLGPU_NSNAPS; ++k) S.s[k] = c->snap[k];
+  k_snapshot<<<dim3((g.SY + 127) / 128, g.M), 128, 0, c->stream>>>(g, fieldset(c), S);
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---- moving window: shift_fields, window.F90:98-153 ----
+// Out-of-place shift by one cell into a spare array, then the pointers are swapped: a
+// pure streaming copy (1 read + 1 write per element) with no in-place hazard.
+__global__ void __launch_bounds__(256) k_shift_x(Geom g, const cplx* __restrict__ src, cplx* __restrict__ dst) {
+  const size_t n = g.plane * g.M;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(t % g.SX);
+    dst[t] = (col < g.SX - 1) ? src[t + 1] : src[t];   // last ghost column keeps its value
+  }
+}
+
+__global__ void __launch_bounds__(128) k_window_fill_xmax(Geom g, FieldSet F, Snaps S) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (row >= g.SY) return;
+  const int j = row + 1 - NG;
+  const int nx = g.nx;
+  const size_t sn = (size_t)im * g.SY + row;
+  // window.F90:114-131, statement order kept
+  F.exm[g.at(nx + 1, j, im)] = S.s[6][sn];
+  F.erm[g.at(nx, j, im)] = S.s[7][sn];
+  F.etm[g.at(nx, j, im)] = S.s[8][sn];
+  F.exm[g.at(nx, j, im)] = 0.5 * (F.exm[g.at(nx - 1, j, im)] + F.exm[g.at(nx + 1, j, im)]);
+  F.erm[g.at(nx - 1, j, im)] = 0.5 * (F.erm[g.at(nx - 2, j, im)] + F.erm[g.at(nx, j, im)]);
+  F.etm[g.at(nx - 1, j, im)] = 0.5 * (F.etm[g.at(nx - 2, j, im)] + F.etm[g.at(nx, j, im)]);
+  F.bxm[g.at(nx, j, im)] = S.s[9][sn];
+  F.brm[g.at(nx + 1, j, im)] = S.s[10][sn];
+  F.btm[g.at(nx + 1, j, im)] = S.s[11][sn];
+  F.bxm[g.at(nx - 1, j, im)] = 0.5 * (F.bxm[g.at(nx - 2, j, im)] + F.bxm[g.at(nx, j, im)]);
+  F.brm[g.at(nx, j, im)] = 0.5 * (F.brm[g.at(nx - 1, j, im)] + F.brm[g.at(nx + 1, j, im)]);
+  F.btm[g.at(nx, j, im)] = 0.5 * (F.btm[g.at(nx - 1, j, im)] + F.btm[g.at(nx + 1, j, im)]);
+}
+
+int do_shift_fields(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  const size_t n = g.plane * g.M;
+  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  for (int k = 0; k < 9; ++k) {   // exm erm etm bxm brm btm jxm jrm jtm
+    k_shift_x<<<blocks, 256, 0, c->stream>>>(g, c->f[k], c->spare);
+    c->stats.kernel_launches += 1;
+    cplx* t = c->f[k];
+    c->f[k] = c->spare;
+    c->spare = t;
+  }
+  CUDA_TRY(cudaGetLastError());
+  // field_mode_bc on each shifted array (window.F90:147-150): three packed exchanges
+  TRY(halo_x(c, CYLGPU_EXM, CYLGPU_ERM, CYLGPU_ETM, 0, 0, 0));
+  TRY(halo_x(c, CYLGPU_BXM, CYLGPU_BRM, CYLGPU_BTM, 0, 0, 0));
+  TRY(halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0));
+  if (c->cfg.x_max_boundary) {
+    Snaps S;
+    for (int k = 0; k < CYLGPU_NSNAPS; ++k) S.s[k] = c->snap[k];
+    k_window_fill_xmax<<<dim3((g.SY + 127) / 128, g.M), 128, 0, c->stream>>>(g, fieldset(c), S);
+    c->stats.kernel_launches += 1;
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace cylgpu

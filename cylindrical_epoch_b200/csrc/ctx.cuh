@@ -1,0 +1,184 @@
+// ctx.cuh -- internal state of one cylgpu handle (one x-slab on one B200).
+// Product code: never includes, links or calls anything under oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/cylgpu.h"
+
+#define NG 5     // constants.F90:544
+#define JNG 5    // constants.F90:545
+#define PNG 3    // constants.F90:537
+
+namespace cylgpu {
+
+// physical constants, constants.F90:171-201
+constexpr double PI = 3.141592653589793238462643383279503;
+constexpr double C_LIGHT = 2.99792458e8;
+constexpr double EPSILON0 = 8.854187817620389850536563031710750e-12;
+
+void set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      cylgpu::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,            \
+                        cudaGetErrorString(_e));                                         \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+#define TRY(expr)                 \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != 0) return _r;       \
+  } while (0)
+
+// ---- complex helpers on double2 (x = re, y = im) ----
+typedef double2 cplx;
+__host__ __device__ __forceinline__ cplx C(double re, double im) { return make_double2(re, im); }
+__host__ __device__ __forceinline__ cplx operator+(cplx a, cplx b) { return C(a.x + b.x, a.y + b.y); }
+__host__ __device__ __forceinline__ cplx operator-(cplx a, cplx b) { return C(a.x - b.x, a.y - b.y); }
+__host__ __device__ __forceinline__ cplx operator-(cplx a) { return C(-a.x, -a.y); }
+__host__ __device__ __forceinline__ cplx operator*(cplx a, cplx b) {
+  return C(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ cplx operator*(double s, cplx a) { return C(s * a.x, s * a.y); }
+__host__ __device__ __forceinline__ cplx operator*(cplx a, double s) { return C(a.x * s, a.y * s); }
+__host__ __device__ __forceinline__ cplx operator/(cplx a, double s) { return C(a.x / s, a.y / s); }
+__host__ __device__ __forceinline__ cplx& operator+=(cplx& a, cplx b) { a.x += b.x; a.y += b.y; return a; }
+// i * a
+__host__ __device__ __forceinline__ cplx mul_i(cplx a) { return C(-a.y, a.x); }
+
+// geometry of the mode arrays: (ix, ir, im) with bounds (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1)
+struct Geom {
+  int nx, ny, M;
+  int SX, SY;          // nx + 2ng, ny + 2ng
+  size_t plane;        // SX * SY
+  __host__ __device__ __forceinline__ size_t at(int ix, int ir, int im) const {
+    return ((size_t)im * SY + (size_t)(ir + NG - 1)) * SX + (size_t)(ix + NG - 1);
+  }
+};
+
+struct Transport;   // transport.cu
+
+struct SpeciesState {
+  cylgpu_species sp;
+  bool set = false;
+  double* d[7] = {0, 0, 0, 0, 0, 0, 0};   // SoA: x y z px py pz w
+  int64_t n = 0, cap = 0;
+};
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+};
+
+}  // namespace cylgpu
+
+struct cylgpu_ctx {
+  cylgpu_config cfg;
+  cylgpu::Geom g;
+  double dt;
+  double x_grid_min_local, x_min, x_max, x_min_local, x_max_local;
+  int bc_field[4];
+  int left, right;             // neighbour ranks for the Cartesian communicator (-1 = none)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int device = 0;
+
+  cylgpu::cplx* f[CYLGPU_NFIELDS] = {0};
+  cylgpu::cplx* spare = nullptr;          // out-of-place window shift target
+  cylgpu::cplx* snap[CYLGPU_NSNAPS] = {0};
+  double* tables = nullptr;               // 4 x (ny + 2*JNG + 1) radial tables (particles.F90:190-217)
+  int ntab = 0;
+  double* src = nullptr;                  // 4 x (ny+1) laser sources (device)
+
+  // halo staging: [3 comps][M][SY][NG] complex each
+  cylgpu::cplx *sbuf_l = nullptr, *sbuf_r = nullptr, *rbuf_l = nullptr, *rbuf_r = nullptr;
+  size_t halo_elems = 0;
+
+  cylgpu::SpeciesState species[CYLGPU_MAX_SPECIES];
+  // particle scratch
+  double* ptmp = nullptr;        // one SoA component worth of doubles (sort scatter target)
+  int64_t ptmp_cap = 0;
+  uint32_t* perm = nullptr;      // sort destination per particle
+  uint8_t* flag = nullptr;       // particle_bcs classification
+  uint32_t* hole_list = nullptr; // indices of leavers
+  uint32_t* lowhole = nullptr;   // holes below the new count
+  uint32_t* hightail = nullptr;  // keepers above the new count
+  int64_t pscratch_cap = 0;
+  int* cell_count = nullptr;     // (nx+2*CELL_PAD) * (ny+2*CELL_PAD) + 1
+  int* cell_fill = nullptr;
+  int* scan_blocks = nullptr;
+  int64_t ncell = 0;
+  double* psend_l = nullptr; double* psend_r = nullptr; double* precv = nullptr;
+  int64_t psend_l_cap = 0, psend_r_cap = 0, precv_cap = 0;
+  unsigned long long* counters = nullptr;   // device counters (8 of them)
+  unsigned long long* h_counters = nullptr; // pinned mirror
+  double* d_energy = nullptr;
+
+  cylgpu::Transport* tr = nullptr;
+
+  int sort_interval = 1;
+  int push_variant = 1;
+  int64_t pushes_since_sort = 0;
+  bool sorted_valid = false;
+
+  cylgpu_stats_t stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timing = true;
+};
+
+namespace cylgpu {
+
+// fields.cu
+int launch_update_e(cylgpu_ctx* c);
+int launch_update_b(cylgpu_ctx* c);
+// bcs.cu
+int do_efield_bcs(cylgpu_ctx* c);
+int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only);
+int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
+                        const double* s2max);
+int do_current_bcs(cylgpu_ctx* c);
+int do_current_finish(cylgpu_ctx* c);
+int do_r_min_final(cylgpu_ctx* c);
+int do_snapshot(cylgpu_ctx* c);
+int do_shift_fields(cylgpu_ctx* c);
+int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip2);
+// particles.cu
+int do_push(cylgpu_ctx* c);
+int do_particle_bcs(cylgpu_ctx* c);
+int do_sort(cylgpu_ctx* c);
+int do_remove_behind(cylgpu_ctx* c);
+int do_energy(cylgpu_ctx* c, double* out2);
+int do_cells(cylgpu_ctx* c, int isp, int64_t capn, int32_t* out);
+int reserve_particles(cylgpu_ctx* c, int isp, int64_t n);
+int build_tables(cylgpu_ctx* c);
+// transport.cu
+Transport* make_transport(cylgpu_ctx* c);
+void destroy_transport(Transport* t);
+int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, size_t rl_b, const void* sr,
+                       size_t sr_b, void* rr, size_t rr_b);
+
+struct PhaseTimer {   // accumulates device ms of a phase into a stats field
+  cylgpu_ctx* c;
+  double* acc;
+  PhaseTimer(cylgpu_ctx* c_, double* acc_) : c(c_), acc(acc_) {
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~PhaseTimer() {
+    if (c->timing) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      *acc += (double)ms;
+    }
+  }
+};
+
+}  // namespace cylgpu

@@ -1,0 +1,193 @@
+// fields.cu -- per-mode Yee-type FDTD half-step updates with the on-axis treatment.
+// Replaces update_e_field (fields.f90:53-182) and update_b_field (fields.f90:186-312).
+//
+// Layout: complex128 (double2) arrays, x fastest, then r, then mode -- identical to the
+// Fortran arrays, so x-adjacent threads read adjacent 16-byte elements (coalesced 512 B
+// per warp and component).  The stencils only reach +-1 in x and r; the second read of a
+// neighbour is served by L1/L2, so the HBM traffic is the algorithmic 12 (E) / 9 (B)
+// arrays per sweep.
+#include "ctx.cuh"
+
+namespace cylgpu {
+
+// E bulk: fields.f90:67-108.  ix = 0..nx, ir = 1..ny (y_min_boundary is always true for
+// x-slab decomposition), all modes.
+__global__ void __launch_bounds__(128) k_update_e_bulk(
+    Geom g, cplx* __restrict__ exm, cplx* __restrict__ erm, cplx* __restrict__ etm,
+    const cplx* __restrict__ bxm, const cplx* __restrict__ brm, const cplx* __restrict__ btm,
+    const cplx* __restrict__ jxm, const cplx* __restrict__ jrm, const cplx* __restrict__ jtm,
+    double dx, double dy, double dt, double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
+  const int ir = blockIdx.y + 1;
+  const int im = blockIdx.z;
+  if (ix > g.nx) return;
+  const double c = C_LIGHT;
+  const double c2 = c * c;
+  const double r_d = fabs((double)(ir - 1) * dy + y_grid_min_local);
+  const double r_p = r_d + 0.5 * dy;
+  const double fac_x = c2 / r_p;
+  const cplx im_fac_x = C(0.0, (double)im) * fac_x;
+  const cplx im_fac_r = (C(0.0, (double)im) * c2) / r_d;
+
+  const size_t o = g.at(ix, ir, im);
+  const size_t SX = g.SX;
+  const cplx bt = btm[o], bt_rp = btm[o + SX], bt_xp = btm[o + 1];
+  const cplx br = brm[o], br_xp = brm[o + 1];
+  const cplx bx = bxm[o], bx_rp = bxm[o + SX];
+
+  exm[o] = exm[o] + (((fac_x * 0.5) * (bt_rp + bt) + im_fac_x * br + (c2 * (bt_rp - bt)) / dy
+                      - jxm[o] / EPSILON0) * 0.5) * dt;
+  erm[o] = erm[o] + (((-im_fac_r) * bx - (c2 * (bt_xp - bt)) / dx - jrm[o] / EPSILON0) * 0.5) * dt;
+  etm[o] = etm[o] + (((c2 * (br_xp - br)) / dx - (c2 * (bx_rp - bx)) / dy - jtm[o] / EPSILON0) * 0.5) * dt;
+}
+
+// E axis rows and below-axis mirror: fields.f90:116-180.  One thread per column over the
+// FULL extent 1-ng..nx+ng (the reference uses whole-array sections here).
+__global__ void __launch_bounds__(128) k_update_e_axis(
+    Geom g, cplx* __restrict__ exm, cplx* __restrict__ erm, cplx* __restrict__ etm,
+    const cplx* __restrict__ btm, const cplx* __restrict__ jxm, double dy, double dt) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (ix > g.nx + NG) return;
+  const double c2 = C_LIGHT * C_LIGHT;
+  // m = 0
+  {
+    const size_t a0 = g.at(ix, 0, 0);
+    exm[a0] = exm[a0] + ((((4.0 * c2) / dy) * btm[g.at(ix, 1, 0)] - jxm[a0] / EPSILON0) * 0.5) * dt;
+    etm[a0] = C(0.0, 0.0);
+    erm[a0] = -erm[g.at(ix, 1, 0)];
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      etm[g.at(ix, ir, 0)] = -etm[g.at(ix, -ir, 0)];
+      erm[g.at(ix, ir, 0)] = -erm[g.at(ix, -ir + 1, 0)];
+      exm[g.at(ix, ir, 0)] = exm[g.at(ix, -ir, 0)];
+    }
+  }
+  if (g.M > 1) {
+    const size_t a0 = g.at(ix, 0, 1);
+    exm[a0] = C(0.0, 0.0);
+    const cplx er1 = erm[g.at(ix, 1, 1)];
+    // uses the OLD etm(ix,0,1), then overwrites it (statement order of fields.f90:146-149)
+    erm[a0] = C(0.0, 2.0) * etm[a0] - er1;
+    etm[a0] = (C(0.0, -1.0) / 8.0) * (9.0 * er1 - erm[g.at(ix, 2, 1)]);
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      etm[g.at(ix, ir, 1)] = etm[g.at(ix, -ir, 1)];
+      erm[g.at(ix, ir, 1)] = erm[g.at(ix, -ir + 1, 1)];
+      exm[g.at(ix, ir, 1)] = -exm[g.at(ix, -ir, 1)];
+    }
+  }
+  double mode_sign = 1.0;
+  for (int im = 2; im < g.M; ++im) {
+    const size_t a0 = g.at(ix, 0, im);
+    exm[a0] = C(0.0, 0.0);
+    etm[a0] = C(0.0, 0.0);
+    erm[a0] = -erm[g.at(ix, 1, im)];
+    erm[g.at(ix, 1, im)] = erm[g.at(ix, 2, im)] / 9.0;
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      etm[g.at(ix, ir, im)] = (-mode_sign) * etm[g.at(ix, -ir, im)];
+      erm[g.at(ix, ir, im)] = (-mode_sign) * erm[g.at(ix, -ir + 1, im)];
+      exm[g.at(ix, ir, im)] = mode_sign * exm[g.at(ix, -ir, im)];
+    }
+    mode_sign = -mode_sign;
+  }
+}
+
+// B bulk: fields.f90:203-241.  ix = 0..nx, ir = 1..ny-1.
+__global__ void __launch_bounds__(128) k_update_b_bulk(
+    Geom g, cplx* __restrict__ bxm, cplx* __restrict__ brm, cplx* __restrict__ btm,
+    const cplx* __restrict__ exm, const cplx* __restrict__ erm, const cplx* __restrict__ etm,
+    double dx, double dy, double dt, double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ir = blockIdx.y + 1;
+  const int im = blockIdx.z;
+  if (ix > g.nx) return;
+  const double r_d = fabs((double)(ir - 1) * dy + y_grid_min_local);
+  const double r_p = r_d + 0.5 * dy;
+  const cplx im_fac_x = C(0.0, (double)im) / r_d;
+  const cplx im_fac_r = C(0.0, (double)im) / r_p;
+  const size_t o = g.at(ix, ir, im);
+  const size_t SX = g.SX;
+  const cplx et = etm[o], et_rm = etm[o - SX], et_xm = etm[o - 1];
+  const cplx er = erm[o], er_xm = erm[o - 1];
+  const cplx ex = exm[o], ex_rm = exm[o - SX];
+
+  bxm[o] = bxm[o] - ((im_fac_x * er + (0.5 * (et + et_rm)) / r_d + (et - et_rm) / dy) * 0.5) * dt;
+  brm[o] = brm[o] + ((im_fac_r * ex + (et - et_xm) / dx) * 0.5) * dt;
+  btm[o] = btm[o] + (((-(er - er_xm)) / dx + (ex - ex_rm) / dy) * 0.5) * dt;
+}
+
+// B axis rows and mirror: fields.f90:249-310.  The m = 1 Brm(ix,0) FDTD update reads
+// etm(ix-1,0,1) which this kernel never writes, so one thread per column is race-free.
+__global__ void __launch_bounds__(128) k_update_b_axis(
+    Geom g, cplx* __restrict__ bxm, cplx* __restrict__ brm, cplx* __restrict__ btm,
+    const cplx* __restrict__ exm, const cplx* __restrict__ etm, double dx, double dy, double dt) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (ix > g.nx + NG) return;
+  {
+    brm[g.at(ix, 0, 0)] = C(0.0, 0.0);
+    bxm[g.at(ix, 0, 0)] = bxm[g.at(ix, 1, 0)];
+    btm[g.at(ix, 0, 0)] = -btm[g.at(ix, 1, 0)];
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      btm[g.at(ix, ir, 0)] = -btm[g.at(ix, -ir + 1, 0)];
+      brm[g.at(ix, ir, 0)] = -brm[g.at(ix, -ir, 0)];
+      bxm[g.at(ix, ir, 0)] = bxm[g.at(ix, -ir + 1, 0)];
+    }
+  }
+  if (g.M > 1) {
+    const size_t a0 = g.at(ix, 0, 1);
+    bxm[a0] = -bxm[g.at(ix, 1, 1)];
+    if (ix >= 2 - NG) {   // fields.f90:272-274 section 2-ng:nx+ng
+      brm[a0] = brm[a0] + (((C(0.0, 1.0) / dy) * exm[a0] + (etm[a0] - etm[a0 - 1]) / dx) * 0.5) * dt;
+    }
+    btm[a0] = C(0.0, -2.0) * brm[a0] - btm[g.at(ix, 1, 1)];
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      btm[g.at(ix, ir, 1)] = btm[g.at(ix, -ir + 1, 1)];
+      brm[g.at(ix, ir, 1)] = brm[g.at(ix, -ir, 1)];
+      bxm[g.at(ix, ir, 1)] = -bxm[g.at(ix, -ir + 1, 1)];
+    }
+  }
+  double mode_sign = 1.0;
+  for (int im = 2; im < g.M; ++im) {
+    bxm[g.at(ix, 0, im)] = -bxm[g.at(ix, 1, im)];
+    brm[g.at(ix, 0, im)] = C(0.0, 0.0);
+    btm[g.at(ix, 0, im)] = -btm[g.at(ix, 1, im)];
+    for (int ir = 1 - NG; ir <= -1; ++ir) {
+      btm[g.at(ix, ir, im)] = (-mode_sign) * btm[g.at(ix, -ir + 1, im)];
+      brm[g.at(ix, ir, im)] = (-mode_sign) * brm[g.at(ix, -ir, im)];
+      bxm[g.at(ix, ir, im)] = mode_sign * bxm[g.at(ix, -ir + 1, im)];
+    }
+    mode_sign = -mode_sign;
+  }
+}
+
+int launch_update_e(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  dim3 blk(128), grd((g.nx + 1 + 127) / 128, g.ny, g.M);
+  k_update_e_bulk<<<grd, blk, 0, c->stream>>>(g, c->f[CYLGPU_EXM], c->f[CYLGPU_ERM], c->f[CYLGPU_ETM],
+                                              c->f[CYLGPU_BXM], c->f[CYLGPU_BRM], c->f[CYLGPU_BTM],
+                                              c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], c->cfg.dx,
+                                              c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
+  k_update_e_axis<<<(g.SX + 127) / 128, 128, 0, c->stream>>>(g, c->f[CYLGPU_EXM], c->f[CYLGPU_ERM],
+                                                             c->f[CYLGPU_ETM], c->f[CYLGPU_BTM],
+                                                             c->f[CYLGPU_JXM], c->cfg.dy, c->dt);
+  c->stats.kernel_launches += 2;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int launch_update_b(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  if (g.ny > 1) {
+    dim3 blk(128), grd((g.nx + 1 + 127) / 128, g.ny - 1, g.M);
+    k_update_b_bulk<<<grd, blk, 0, c->stream>>>(g, c->f[CYLGPU_BXM], c->f[CYLGPU_BRM], c->f[CYLGPU_BTM],
+                                                c->f[CYLGPU_EXM], c->f[CYLGPU_ERM], c->f[CYLGPU_ETM],
+                                                c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
+    c->stats.kernel_launches += 1;
+  }
+  k_update_b_axis<<<(g.SX + 127) / 128, 128, 0, c->stream>>>(g, c->f[CYLGPU_BXM], c->f[CYLGPU_BRM],
+                                                             c->f[CYLGPU_BTM], c->f[CYLGPU_EXM],
+                                                             c->f[CYLGPU_ETM], c->cfg.dx, c->cfg.dy, c->dt);
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cylgpu

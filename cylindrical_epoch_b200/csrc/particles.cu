@@ -1,0 +1,777 @@
+// particles.cu -- particle push + gather + charge-conserving mode deposit, particle boundary
+// conditions / migration, and the cell sort of the SoA particle store.
+// Replaces push_particles (particles.F90:28-734), particle_bcs (boundary.F90:1541-1889),
+// partlist_sendrecv + pack/unpack_particle (partlist.F90:414-564,822-876) and
+// remove_particles (window.F90:304-325).
+#include <algorithm>
+#include <cmath>
+
+#include "push.cuh"
+
+namespace cylgpu {
+
+// ------------------------------------------------------------------------------------------
+// per-radius tables, particles.F90:190-217 (computed on the host in the reference's order,
+// r_low accumulated by repeated addition of dy)
+// ------------------------------------------------------------------------------------------
+int build_tables(cylgpu_ctx* c) {
+  const int ny = c->g.ny;
+  const int ntab = ny + 2 * JNG + 1;   // index iy in [0-jng, ny+jng] -> iy + JNG
+  const double dx = c->cfg.dx, dy = c->cfg.dy;
+  std::vector<double> t(4 * (size_t)ntab, 0.0);
+  double* rt = t.data();
+  double* xt = rt + ntab;
+  double* vol = xt + ntab;
+  double* ratio = vol + ntab;
+  double r_low = c->cfg.y_grid_min_local - (double)JNG * dy;
+  xt[0] = 1.0 / (2.0 * PI * std::fabs(r_low) * dx);
+  for (int iy = 1 - JNG; iy <= ny + JNG; ++iy) {
+    if (std::lround(2.0 * r_low / dy) == -1) {
+      rt[iy + JNG] = 1.0 / (PI * ((0.5 * dy) * (0.5 * dy)));
+    } else {
+      rt[iy + JNG] = 1.0 / (PI * std::fabs((r_low + dy) * (r_low + dy) - r_low * r_low));
+    }
+    xt[iy + JNG] = 1.0 / (2.0 * PI * std::fabs(r_low + dy) * dx);
+    r_low = r_low + dy;
+  }
+  for (int iy = 1 - JNG; iy <= ny + JNG; ++iy) {
+    vol[iy + JNG] = rt[iy + JNG] / dx;
+    ratio[iy + JNG] = xt[iy + JNG] / xt[iy + JNG - 1];
+  }
+  c->ntab = ntab;
+  if (!c->tables) CUDA_TRY(cudaMalloc(&c->tables, 4 * (size_t)ntab * sizeof(double)));
+  CUDA_TRY(cudaMemcpy(c->tables, t.data(), 4 * (size_t)ntab * sizeof(double), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// deposit, particles.F90:584-665, one particle, straight into HBM with FP64 reductions
+// (RED.E.ADD.F64 at L2).  Imaginary parts of mode 0 are identically zero and are skipped.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add(double* a, size_t o, cplx v, bool with_imag) {
+  atomicAdd(a + 2 * o, v.x);
+  if (with_imag) atomicAdd(a + 2 * o + 1, v.y);
+}
+
+__device__ __forceinline__ void deposit_global(const PushConst& P, const DepositIn& D) {
+  const Geom& g = P.g;
+  const double third = 1.0 / 3.0;
+  const double* inv_area_rt = P.tab + JNG;              // index by cy directly
+  const double* inv_area_xt = P.tab + P.ntab + JNG;
+  const double* inv_volume = P.tab + 2 * P.ntab + JNG;
+  const double* ratio_area_xt = P.tab + 3 * P.ntab + JNG;
+  cplx exp_imtheta0 = C(1.0, 0.0), exp_imdtheta = C(1.0, 0.0);
+  for (int im = 0; im < g.M; ++im) {
+    ModeFac mf;
+    if (im > 0) {
+      exp_imtheta0 = exp_imtheta0 * D.exp_itheta_05;
+      exp_imdtheta = exp_imdtheta * D.exp_idtheta;
+      mf = mode_factors(im, D.dtheta, exp_imtheta0, exp_imdtheta);
+    }
+    cplx jyh[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) jyh[k] = C(0.0, 0.0);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const int iy = ky - 2;
+      if (iy < D.ymin || iy > D.ymax) continue;
+      const int cy = D.cell_y2 + iy;
+      cplx w_rt, ym_fac_1;
+      if (im == 0) {
+        w_rt = C(D.gy[ky] + 0.5 * D.hy[ky], 0.0);
+        ym_fac_1 = C(0.5 * D.gy[ky] + third * D.hy[ky], 0.0);
+      } else {
+        w_rt = mf.f2 * D.gy[ky] + mf.f3 * D.hy[ky];
+        ym_fac_1 = mf.f3 * D.gy[ky] + mf.f4 * D.hy[ky];
+      }
+      const double fjx = D.fcx * __ldg(&inv_area_rt[cy]);
+      const double fjy = D.fcx * D.hy[ky] * __ldg(&inv_area_xt[cy]);
+      const double fjz = D.fcz * __ldg(&inv_volume[cy]);
+      const double ratio = __ldg(&ratio_area_xt[cy]);
+      cplx jxh = C(0.0, 0.0);
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int ix = kx - 2;
+        if (ix < D.xmin || ix > D.xmax) continue;
+        const int cx = D.cell_x2 + ix;
+        cplx w_xt;
+        if (im == 0) w_xt = C(D.gx[kx] + 0.5 * D.hx[kx], 0.0);
+        else w_xt = mf.f2 * D.gx[kx] + mf.f3 * D.hx[kx];
+        const cplx w_xr = D.gx[kx] * w_rt + D.hx[kx] * ym_fac_1;
+        jxh = jxh - (fjx * D.hx[kx]) * w_rt;
+        jyh[kx] = jyh[kx] * ratio - fjy * w_xt;
+        const cplx jzh = fjz * w_xr;
+        const size_t o = g.at(cx, cy, im);
+        red_add(P.jx, o + 1, jxh, im > 0);
+        red_add(P.jr, o + g.SX, jyh[kx], im > 0);
+        red_add(P.jt, o, jzh, im > 0);
+      }
+    }
+  }
+}
+
+// variant 0: one thread per particle, everything through L1/L2
+__global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict__ x, double* __restrict__ y,
+                                                 double* __restrict__ z, double* __restrict__ px,
+                                                 double* __restrict__ py, double* __restrict__ pz,
+                                                 const double* __restrict__ w, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
+  const double W = w[i];
+  DepositIn D;
+  push_one(P, X, Y, Z, PX, PY, PZ, W, D);
+  x[i] = X; y[i] = Y; z[i] = Z;
+  px[i] = PX; py[i] = PY; pz[i] = PZ;
+  if (P.deposit) deposit_global(P, D);
+}
+
+__global__ void __launch_bounds__(256) k_copy_zero(cplx* __restrict__ old0, cplx* __restrict__ old1,
+                                                   cplx* __restrict__ old2, cplx* __restrict__ j0,
+                                                   cplx* __restrict__ j1, cplx* __restrict__ j2, size_t n) {
+  const cplx zero = C(0.0, 0.0);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    old0[t] = j0[t]; j0[t] = zero;
+    old1[t] = j1[t]; j1[t] = zero;
+    old2[t] = j2[t]; j2[t] = zero;
+  }
+}
+
+int do_sort(cylgpu_ctx* c);
+
+int do_push(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  const size_t n = g.plane * g.M;
+  // particles.F90:163-169: j*_old = j*; j* = 0 (one fused streaming pass)
+  {
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 8);
+    k_copy_zero<<<blocks, 256, 0, c->stream>>>(c->f[CYLGPU_JXM_OLD], c->f[CYLGPU_JRM_OLD], c->f[CYLGPU_JTM_OLD],
+                                               c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], n);
+    c->stats.kernel_launches += 1;
+  }
+  if (c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval)) {
+    TRY(do_sort(c));
+  }
+  const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
+  const double dt = c->dt;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set || S.sp.immobile || S.n == 0) continue;
+    PushConst P;
+    P.g = g;
+    P.exm = c->f[CYLGPU_EXM]; P.erm = c->f[CYLGPU_ERM]; P.etm = c->f[CYLGPU_ETM];
+    P.bxm = c->f[CYLGPU_BXM]; P.brm = c->f[CYLGPU_BRM]; P.btm = c->f[CYLGPU_BTM];
+    P.jx = (double*)c->f[CYLGPU_JXM]; P.jr = (double*)c->f[CYLGPU_JRM]; P.jt = (double*)c->f[CYLGPU_JTM];
+    P.tab = c->tables; P.ntab = c->ntab;
+    P.x_grid_min_local = c->x_grid_min_local;
+    P.y_grid_min_local = c->cfg.y_grid_min_local;
+    P.idx = 1.0 / c->cfg.dx; P.idy = 1.0 / c->cfg.dy; P.idt = 1.0 / dt;
+    const double dto2 = dt / 2.0;
+    P.dtco2 = C_LIGHT * dto2;
+    const double dtfac = 0.5 * dt * fac;
+    P.part_mc = C_LIGHT * S.sp.mass;
+    P.ipart_mc = 1.0 / P.part_mc;
+    P.cmratio = S.sp.charge * dtfac * P.ipart_mc;
+    P.ccmratio = C_LIGHT * P.cmratio;
+    P.q_fac = S.sp.charge * fac;
+    P.deposit = S.sp.zero_current ? 0 : 1;
+    const int64_t nb = (S.n + 127) / 128;
+    k_push_v0<<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  c->pushes_since_sort += 1;
+  return do_r_min_final(c);
+}
+
+// ------------------------------------------------------------------------------------------
+// particle storage
+// ------------------------------------------------------------------------------------------
+int reserve_particles(cylgpu_ctx* c, int isp, int64_t n) {
+  cylgpu::SpeciesState& S = c->species[isp];
+  if (n <= S.cap) return 0;
+  int64_t cap = std::max<int64_t>(n, (int64_t)(S.cap * 1.25) + 1024);
+  for (int k = 0; k < 7; ++k) {
+    double* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, (size_t)cap * sizeof(double)));
+    if (S.n > 0) CUDA_TRY(cudaMemcpyAsync(p, S.d[k], (size_t)S.n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (S.d[k]) CUDA_TRY(cudaFree(S.d[k]));
+    S.d[k] = p;
+  }
+  S.cap = cap;
+  return 0;
+}
+
+static int reserve_pscratch(cylgpu_ctx* c, int64_t n) {
+  if (n <= c->pscratch_cap) return 0;
+  const int64_t cap = (int64_t)(n * 1.25) + 1024;
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (c->perm) cudaFree(c->perm);
+  if (c->flag) cudaFree(c->flag);
+  if (c->hole_list) cudaFree(c->hole_list);
+  if (c->lowhole) cudaFree(c->lowhole);
+  if (c->hightail) cudaFree(c->hightail);
+  CUDA_TRY(cudaMalloc(&c->perm, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->flag, (size_t)cap));
+  CUDA_TRY(cudaMalloc(&c->hole_list, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->lowhole, (size_t)cap * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&c->hightail, (size_t)cap * sizeof(uint32_t)));
+  c->pscratch_cap = cap;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// particle_bcs, boundary.F90:1541-1889 (non-cpml, non-thermal branches)
+// ------------------------------------------------------------------------------------------
+struct BcsConst {
+  double x_min, x_max, x_min_local, x_max_local, y_max;
+  double x_min_outer, x_max_outer, y_max_outer, x_shift;
+  int x_min_boundary, x_max_boundary;
+  int bc[4];
+};
+
+enum { FL_KEEP = 0, FL_LEFT = 1, FL_RIGHT = 2, FL_GONE = 3 };
+enum { CNT_HOLE = 0, CNT_LEFT = 1, CNT_RIGHT = 2, CNT_GONE = 3, CNT_TAIL = 4, CNT_LOW = 5, CNT_PACK_L = 6, CNT_PACK_R = 7 };
+
+__global__ void __launch_bounds__(256) k_pbcs_classify(BcsConst B, double* __restrict__ x, double* __restrict__ y,
+                                                       double* __restrict__ z, double* __restrict__ px,
+                                                       double* __restrict__ py, double* __restrict__ pz,
+                                                       uint8_t* __restrict__ flag, unsigned long long* cnt,
+                                                       int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int xbd = 0;
+  bool out_of_bounds = false;
+  double part_pos = x[i];
+  if (part_pos < B.x_min_local) {
+    xbd = -1;
+    int bc = -1;
+    if (B.x_min_boundary) {
+      xbd = 0;
+      bc = B.bc[CYLGPU_BD_X_MIN];
+      if (bc == CYLGPU_BC_REFLECT) {
+        x[i] = 2.0 * B.x_min - part_pos;
+        px[i] = -px[i];
+      } else if (bc == CYLGPU_BC_PERIODIC) {
+        xbd = -1;
+        x[i] = part_pos - (-1.0) * B.x_shift;
+      }
+    }
+    if (part_pos < B.x_min_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  if (part_pos >= B.x_max_local) {
+    xbd = 1;
+    int bc = -1;
+    if (B.x_max_boundary) {
+      xbd = 0;
+      bc = B.bc[CYLGPU_BD_X_MAX];
+      if (bc == CYLGPU_BC_REFLECT) {
+        x[i] = 2.0 * B.x_max - part_pos;
+        px[i] = -px[i];
+      } else if (bc == CYLGPU_BC_PERIODIC) {
+        xbd = 1;
+        x[i] = part_pos - B.x_shift;
+      }
+    }
+    if (part_pos >= B.x_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  const double Y = y[i], Z = z[i];
+  part_pos = sqrt(Y * Y + Z * Z);
+  if (part_pos >= B.y_max) {
+    const int bc = B.bc[CYLGPU_BD_Y_MAX];
+    if (bc == CYLGPU_BC_REFLECT) {
+      const double radial_reduction = 2.0 * B.y_max / part_pos - 1.0;
+      const double Yn = Y * radial_reduction, Zn = Z * radial_reduction;
+      y[i] = Yn;
+      z[i] = Zn;
+      const double inv_final_r = 1.0 / sqrt(Yn * Yn + Zn * Zn);
+      const double cos_theta = Yn * inv_final_r, sin_theta = Zn * inv_final_r;
+      const double PY = py[i], PZ = pz[i];
+      const double part_pr = PY * cos_theta + PZ * sin_theta;
+      const double part_pt = -PY * sin_theta + PZ * cos_theta;
+      py[i] = -part_pr * cos_theta - part_pt * sin_theta;
+      pz[i] = -part_pr * sin_theta + part_pt * cos_theta;
+    }
+    if (part_pos >= B.y_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  uint8_t f = FL_KEEP;
+  if (out_of_bounds) f = FL_GONE;
+  else if (xbd == -1) f = FL_LEFT;
+  else if (xbd == 1) f = FL_RIGHT;
+  flag[i] = f;
+  if (f != FL_KEEP) {
+    atomicAdd(&cnt[CNT_HOLE], 1ULL);
+    atomicAdd(&cnt[f], 1ULL);   // CNT_LEFT / CNT_RIGHT / CNT_GONE share the flag value
+  }
+}
+
+// window.F90:304-325 remove_particles: everything behind the new x_min goes
+__global__ void __launch_bounds__(256) k_flag_behind(const double* __restrict__ x, double x_min,
+                                                     uint8_t* __restrict__ flag, unsigned long long* cnt,
+                                                     int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool gone = x[i] < x_min;
+  flag[i] = gone ? FL_GONE : FL_KEEP;
+  if (gone) {
+    atomicAdd(&cnt[CNT_HOLE], 1ULL);
+    atomicAdd(&cnt[CNT_GONE], 1ULL);
+  }
+}
+
+struct Soa { double* d[7]; };
+
+// second pass: list the holes and pack the leavers in pack_particle order (7 doubles)
+__global__ void __launch_bounds__(256) k_collect(Soa s, const uint8_t* __restrict__ flag,
+                                                 uint32_t* __restrict__ hole_list, double* __restrict__ send_l,
+                                                 double* __restrict__ send_r, unsigned long long* cnt2,
+                                                 int64_t n) {
+  // cnt2[0] = holes listed, cnt2[1] = packed left, cnt2[2] = packed right
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t f = flag[i];
+  if (f == FL_KEEP) return;
+  const unsigned long long h = atomicAdd(&cnt2[0], 1ULL);
+  hole_list[h] = (uint32_t)i;
+  if (f == FL_LEFT || f == FL_RIGHT) {
+    const unsigned long long k = atomicAdd(&cnt2[f], 1ULL);
+    double* dst = ((f == FL_LEFT) ? send_l : send_r) + 7 * k;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) dst[q] = s.d[q][i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_tail_keepers(const uint8_t* __restrict__ flag, int64_t n_new, int64_t n,
+                                                      uint32_t* __restrict__ hightail, unsigned long long* cnt2) {
+  const int64_t i = n_new + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (flag[i] == FL_KEEP) hightail[atomicAdd(&cnt2[3], 1ULL)] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_low_holes(const uint32_t* __restrict__ hole_list, int64_t nholes,
+                                                   int64_t n_new, uint32_t* __restrict__ lowhole,
+                                                   unsigned long long* cnt2) {
+  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nholes) return;
+  const uint32_t i = hole_list[h];
+  if ((int64_t)i < n_new) lowhole[atomicAdd(&cnt2[4], 1ULL)] = i;
+}
+
+__global__ void __launch_bounds__(256) k_fill_holes(Soa s, const uint32_t* __restrict__ lowhole,
+                                                    const uint32_t* __restrict__ hightail,
+                                                    const unsigned long long* cnt2, int64_t nmax) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nmax || (unsigned long long)k >= cnt2[4]) return;
+  const uint32_t dst = lowhole[k], src = hightail[k];
+#pragma unroll
+  for (int q = 0; q < 7; ++q) s.d[q][dst] = s.d[q][src];
+}
+
+__global__ void __launch_bounds__(256) k_unpack(Soa s, int64_t base, const double* __restrict__ recv, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) s.d[q][base + k] = recv[7 * k + q];
+}
+
+static inline unsigned nblk(int64_t n, int b) { return (unsigned)((n + b - 1) / b); }
+
+static int ensure_dbuf(double** p, int64_t* cap, int64_t need, cudaStream_t st) {
+  if (need <= *cap) return 0;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (*p) cudaFree(*p);
+  const int64_t nc = (int64_t)(need * 1.5) + 4096;
+  CUDA_TRY(cudaMalloc(p, (size_t)nc * sizeof(double)));
+  *cap = nc;
+  return 0;
+}
+
+// compaction after flags + counts are known on the host: fills the holes below the new
+// count with the keepers above it (order is not preserved; the reference's list order only
+// matters for floating-point summation order)
+static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64_t nleft, int64_t nright,
+                   unsigned long long* cnt2) {
+  Soa s;
+  for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+  const int64_t n = S.n, n_new = n - nholes;
+  CUDA_TRY(cudaMemsetAsync(cnt2, 0, 8 * sizeof(unsigned long long), c->stream));
+  k_collect<<<nblk(n, 256), 256, 0, c->stream>>>(s, c->flag, c->hole_list, c->psend_l, c->psend_r, cnt2, n);
+  if (n_new > 0 && nholes > 0) {
+    k_tail_keepers<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->flag, n_new, n, c->hightail, cnt2);
+    k_low_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->hole_list, nholes, n_new, c->lowhole, cnt2);
+    k_fill_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(s, c->lowhole, c->hightail, cnt2, nholes);
+    c->stats.kernel_launches += 3;
+  }
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  S.n = n_new;
+  (void)nleft; (void)nright;
+  return 0;
+}
+
+int do_particle_bcs(cylgpu_ctx* c) {
+  BcsConst B;
+  const double dx = c->cfg.dx, dy = c->cfg.dy;
+  B.x_min = c->x_min; B.x_max = c->x_max;
+  B.x_min_local = c->x_min_local; B.x_max_local = c->x_max_local;
+  B.y_max = c->cfg.y_max;
+  double boundary_shift = dx * (double)((1 + PNG + 0) / 2);   // boundary.F90:1561-1563
+  B.x_min_outer = B.x_min - boundary_shift;
+  B.x_max_outer = B.x_max + boundary_shift;
+  boundary_shift = dy * (double)((1 + PNG + 0) / 2);
+  B.y_max_outer = B.y_max + boundary_shift;
+  B.x_shift = B.x_max - B.x_min;   // length_x
+  B.x_min_boundary = c->cfg.x_min_boundary;
+  B.x_max_boundary = c->cfg.x_max_boundary;
+  c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+
+  unsigned long long* cnt = c->counters;        // 8 for classify
+  unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
+  unsigned long long* xc = c->counters + 16;    // [0..1] send counts, [2..3] recv counts
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set) continue;
+    for (int k = 0; k < 4; ++k) B.bc[k] = S.sp.bc_particle[k];
+    TRY(reserve_pscratch(c, S.n));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (S.n > 0) {
+      k_pbcs_classify<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                            c->flag, cnt, S.n);
+      c->stats.kernel_launches += 1;
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
+    const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
+    const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
+    const int64_t ngone = (int64_t)c->h_counters[CNT_GONE];
+    c->stats.n_sent_left += nleft;
+    c->stats.n_sent_right += nright;
+    c->stats.n_removed += ngone;
+    TRY(ensure_dbuf(&c->psend_l, &c->psend_l_cap, 7 * nleft, c->stream));
+    TRY(ensure_dbuf(&c->psend_r, &c->psend_r_cap, 7 * nright, c->stream));
+    if (nholes > 0) TRY(compact(c, S, nholes, nleft, nright, cnt2));
+
+    // ---- exchange: partlist_sendrecv (count, then payload), boundary.F90:1867-1877 ----
+    const bool has_l = c->left >= 0, has_r = c->right >= 0;
+    if (has_l || has_r) {
+      c->h_counters[16] = (unsigned long long)nleft;
+      c->h_counters[17] = (unsigned long long)nright;
+      c->h_counters[18] = c->h_counters[19] = 0;
+      CUDA_TRY(cudaMemcpyAsync(xc, c->h_counters + 16, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                               c->stream));
+      TRY(transport_sendrecv(c, has_l ? xc + 0 : nullptr, has_l ? 8 : 0, has_l ? xc + 2 : nullptr, has_l ? 8 : 0,
+                             has_r ? xc + 1 : nullptr, has_r ? 8 : 0, has_r ? xc + 3 : nullptr, has_r ? 8 : 0));
+      CUDA_TRY(cudaMemcpyAsync(c->h_counters + 16, xc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      const int64_t from_l = has_l ? (int64_t)c->h_counters[18] : 0;
+      const int64_t from_r = has_r ? (int64_t)c->h_counters[19] : 0;
+      TRY(ensure_dbuf(&c->precv, &c->precv_cap, 7 * (from_l + from_r), c->stream));
+      double* rl = c->precv;
+      double* rr = c->precv + 7 * from_l;
+      TRY(transport_sendrecv(c, c->psend_l, has_l ? 7 * nleft * sizeof(double) : 0, rl, 7 * from_l * sizeof(double),
+                             c->psend_r, has_r ? 7 * nright * sizeof(double) : 0, rr,
+                             7 * from_r * sizeof(double)));
+      // the reference receives from the right neighbour first (ix = -1 iteration), then left
+      const int64_t nrecv = from_l + from_r;
+      if (nrecv > 0) {
+        TRY(reserve_particles(c, isp, S.n + nrecv));
+        Soa s;
+        for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+        if (from_r > 0) k_unpack<<<nblk(from_r, 256), 256, 0, c->stream>>>(s, S.n, rr, from_r);
+        if (from_l > 0) k_unpack<<<nblk(from_l, 256), 256, 0, c->stream>>>(s, S.n + from_r, rl, from_l);
+        c->stats.kernel_launches += (from_r > 0) + (from_l > 0);
+        S.n += nrecv;
+        c->stats.n_recv += nrecv;
+      }
+      CUDA_TRY(cudaGetLastError());
+    }
+    c->stats.n_particles[isp] = S.n;
+  }
+  return 0;
+}
+
+int do_remove_behind(cylgpu_ctx* c) {
+  c->stats.n_window_removed = 0;
+  if (!c->cfg.x_min_boundary) return 0;
+  unsigned long long* cnt = c->counters;
+  unsigned long long* cnt2 = c->counters + 8;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set || S.n == 0) continue;
+    TRY(reserve_pscratch(c, S.n));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+    k_flag_behind<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->flag, cnt, S.n);
+    c->stats.kernel_launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
+    if (nholes > 0) TRY(compact(c, S, nholes, 0, 0, cnt2));
+    c->stats.n_window_removed += nholes;
+    c->stats.n_particles[isp] = S.n;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// cell sort (counting sort on the reference's cell index, split_particle.F90:62-63)
+// ------------------------------------------------------------------------------------------
+#define CELL_PAD 3
+struct SortGeom {
+  int ncx, ncy;   // nx + 2*CELL_PAD, ny + 2*CELL_PAD
+  double x_grid_min_local, y_grid_min_local, dx, dy;
+};
+
+__device__ __forceinline__ void ref_cell(const SortGeom& G, double x, double y, double z, int& cx, int& cy) {
+  const double r = sqrt(y * y + z * z);
+  cx = (int)floor((x - G.x_grid_min_local) / G.dx + 1.5);
+  cy = (int)floor((r - G.y_grid_min_local) / G.dy + 1.5);
+}
+
+__device__ __forceinline__ int cell_key(const SortGeom& G, int cx, int cy) {
+  int kx = cx - 1 + CELL_PAD, ky = cy - 1 + CELL_PAD;
+  kx = max(0, min(G.ncx - 1, kx));
+  ky = max(0, min(G.ncy - 1, ky));
+  return ky * G.ncx + kx;
+}
+
+__global__ void __launch_bounds__(256) k_sort_hist(SortGeom G, const double* __restrict__ x,
+                                                   const double* __restrict__ y, const double* __restrict__ z,
+                                                   int* __restrict__ count, uint32_t* __restrict__ key,
+                                                   uint32_t* __restrict__ rank, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx, cy;
+  ref_cell(G, x[i], y[i], z[i], cx, cy);
+  const int k = cell_key(G, cx, cy);
+  key[i] = (uint32_t)k;
+  rank[i] = (uint32_t)atomicAdd(&count[k], 1);
+}
+
+// exclusive scan, 3 kernels; SCAN_B elements per block
+#define SCAN_B 1024
+__global__ void __launch_bounds__(SCAN_B) k_scan_block(int* __restrict__ a, int* __restrict__ block_sum, int64_t n) {
+  __shared__ int sh[SCAN_B];
+  const int64_t i = (int64_t)blockIdx.x * SCAN_B + threadIdx.x;
+  const int v = (i < n) ? a[i] : 0;
+  sh[threadIdx.x] = v;
+  __syncthreads();
+  for (int off = 1; off < SCAN_B; off <<= 1) {
+    int t = 0;
+    if ((int)threadIdx.x >= off) t = sh[threadIdx.x - off];
+    __syncthreads();
+    sh[threadIdx.x] += t;
+    __syncthreads();
+  }
+  if (i < n) a[i] = sh[threadIdx.x] - v;   // exclusive
+  if (threadIdx.x == SCAN_B - 1) block_sum[blockIdx.x] = sh[threadIdx.x];
+}
+__global__ void __launch_bounds__(SCAN_B) k_scan_sums(int* __restrict__ block_sum, int nb) {
+  __shared__ int sh[SCAN_B];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nb; base += SCAN_B) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nb) ? block_sum[i] : 0;
+    sh[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < SCAN_B; off <<= 1) {
+      int t = 0;
+      if ((int)threadIdx.x >= off) t = sh[threadIdx.x - off];
+      __syncthreads();
+      sh[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (i < nb) block_sum[i] = carry + sh[threadIdx.x] - v;
+    __syncthreads();
+    if (threadIdx.x == SCAN_B - 1) carry += sh[threadIdx.x];
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(SCAN_B) k_scan_add(int* __restrict__ a, const int* __restrict__ block_sum,
+                                                     int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * SCAN_B + threadIdx.x;
+  if (i < n) a[i] += block_sum[blockIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_sort_dest(const int* __restrict__ start, const uint32_t* __restrict__ key,
+                                                   uint32_t* __restrict__ rank_to_dest, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rank_to_dest[i] = (uint32_t)start[key[i]] + rank_to_dest[i];
+}
+
+__global__ void __launch_bounds__(256) k_scatter(const double* __restrict__ src, double* __restrict__ dst,
+                                                 const uint32_t* __restrict__ dest, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[dest[i]] = src[i];
+}
+
+int do_sort(cylgpu_ctx* c) {
+  SortGeom G;
+  G.ncx = c->g.nx + 2 * CELL_PAD;
+  G.ncy = c->g.ny + 2 * CELL_PAD;
+  G.x_grid_min_local = c->x_grid_min_local;
+  G.y_grid_min_local = c->cfg.y_grid_min_local;
+  G.dx = c->cfg.dx; G.dy = c->cfg.dy;
+  const int64_t ncell = (int64_t)G.ncx * G.ncy;
+  const int nb = (int)((ncell + SCAN_B - 1) / SCAN_B);
+  if (!c->cell_count || c->ncell != ncell) {
+    if (c->cell_count) cudaFree(c->cell_count);
+    if (c->scan_blocks) cudaFree(c->scan_blocks);
+    CUDA_TRY(cudaMalloc(&c->cell_count, (size_t)(ncell + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&c->scan_blocks, (size_t)(nb + 1) * sizeof(int)));
+    c->ncell = ncell;
+  }
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set || S.n == 0 || S.sp.immobile) continue;
+    if (S.n >= (int64_t)0xFFFFFFFFLL) { set_error("more than 2^32-1 particles per species per GPU"); return 3; }
+    TRY(reserve_pscratch(c, S.cap));
+    uint32_t* key = c->hole_list;   // scratch reuse: hole_list is idle during a sort
+    uint32_t* dest = c->perm;
+    CUDA_TRY(cudaMemsetAsync(c->cell_count, 0, (size_t)(ncell + 1) * sizeof(int), c->stream));
+    k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], c->cell_count, key, dest, S.n);
+    k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
+    k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
+    k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
+    k_sort_dest<<<nblk(S.n, 256), 256, 0, c->stream>>>(c->cell_count, key, dest, S.n);
+    c->stats.kernel_launches += 5;
+    // scatter each component into the spare array, then rotate the pointers (the old
+    // component array becomes the next spare): 8 B of scratch per particle, not 56
+    if (c->ptmp_cap < S.cap) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      if (c->ptmp) cudaFree(c->ptmp);
+      CUDA_TRY(cudaMalloc(&c->ptmp, (size_t)S.cap * sizeof(double)));
+    }
+    for (int q = 0; q < 7; ++q) {
+      k_scatter<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[q], c->ptmp, dest, S.n);
+      c->stats.kernel_launches += 1;
+      double* t = S.d[q];
+      S.d[q] = c->ptmp;
+      c->ptmp = t;
+    }
+    c->ptmp_cap = S.cap;   // the spare is now one of this species' old arrays
+    CUDA_TRY(cudaGetLastError());
+  }
+  c->sorted_valid = true;
+  c->pushes_since_sort = 0;
+  c->stats.n_sorts += 1;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// diagnostics
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_cells(SortGeom G, const double* __restrict__ x, const double* __restrict__ y,
+                                               const double* __restrict__ z, int32_t* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cx, cy;
+  ref_cell(G, x[i], y[i], z[i], cx, cy);
+  out[2 * i] = cx;
+  out[2 * i + 1] = cy;
+}
+
+int do_cells(cylgpu_ctx* c, int isp, int64_t capn, int32_t* out) {
+  cylgpu::SpeciesState& S = c->species[isp];
+  if (capn < S.n) { set_error("cells_out too small"); return 2; }
+  if (S.n == 0) return 0;
+  SortGeom G;
+  G.ncx = G.ncy = 0;
+  G.x_grid_min_local = c->x_grid_min_local;
+  G.y_grid_min_local = c->cfg.y_grid_min_local;
+  G.dx = c->cfg.dx; G.dy = c->cfg.dy;
+  int32_t* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, (size_t)S.n * 2 * sizeof(int32_t)));
+  k_cells<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], d, S.n);
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaMemcpyAsync(out, d, (size_t)S.n * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(d));
+  return 0;
+}
+
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[8];
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (threadIdx.x < 8) t = sh[threadIdx.x];
+  if (threadIdx.x < 32) for (int o = 4; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  __syncthreads();
+  return t;
+}
+
+// field energy: theta-average of (Re sum_m F_m e^{-im theta})^2 = Re(F_0)^2 + 1/2 sum_{m>0} |F_m|^2,
+// per cell i=1..nx, j=1..ny with volume 2 pi r dx dy, staggered components averaged to the centre
+__global__ void __launch_bounds__(256) k_field_energy(Geom g, const cplx* __restrict__ exm, const cplx* __restrict__ erm,
+                                                      const cplx* __restrict__ etm, const cplx* __restrict__ bxm,
+                                                      const cplx* __restrict__ brm, const cplx* __restrict__ btm,
+                                                      double dx, double dy, double y_grid_min_local,
+                                                      double* __restrict__ out) {
+  const int64_t ncell = (int64_t)g.nx * g.ny;
+  double acc = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ncell * g.M;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int im = (int)(t / ncell);
+    const int64_t q = t % ncell;
+    const int j = (int)(q / g.nx) + 1, i = (int)(q % g.nx) + 1;
+    const double r = y_grid_min_local + (double)(j - 1) * dy;
+    auto sq = [&](cplx v) { return (im == 0) ? v.x * v.x : 0.5 * (v.x * v.x + v.y * v.y); };
+    const size_t o = g.at(i, j, im);
+    const size_t SX = g.SX;
+    double e2 = 0.5 * (sq(exm[o]) + sq(exm[o - SX]))                      // Exm: r-staggered
+              + 0.5 * (sq(erm[o]) + sq(erm[o - 1]))                       // Erm: x-staggered
+              + 0.25 * (sq(etm[o]) + sq(etm[o - 1]) + sq(etm[o - SX]) + sq(etm[o - SX - 1]));
+    double b2 = 0.5 * (sq(bxm[o]) + sq(bxm[o - 1]))
+              + 0.5 * (sq(brm[o]) + sq(brm[o - SX]))
+              + sq(btm[o]);
+    acc += 0.5 * EPSILON0 * (e2 + C_LIGHT * C_LIGHT * b2) * (2.0 * PI * r * dx * dy);
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+__global__ void __launch_bounds__(256) k_kinetic_energy(const double* __restrict__ px, const double* __restrict__ py,
+                                                        const double* __restrict__ pz, const double* __restrict__ w,
+                                                        double mass, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  const double mc = mass * C_LIGHT;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double ux = px[i] / mc, uy = py[i] / mc, uz = pz[i] / mc;
+    const double u2 = ux * ux + uy * uy + uz * uz;
+    const double gm1 = u2 / (sqrt(1.0 + u2) + 1.0);   // gamma - 1 without cancellation
+    acc += w[i] * gm1 * mass * C_LIGHT * C_LIGHT;
+  }
+  acc = block_sum(acc);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+
+int do_energy(cylgpu_ctx* c, double* out2) {
+  const Geom& g = c->g;
+  CUDA_TRY(cudaMemsetAsync(c->d_energy, 0, 2 * sizeof(double), c->stream));
+  k_field_energy<<<148 * 4, 256, 0, c->stream>>>(g, c->f[CYLGPU_EXM], c->f[CYLGPU_ERM], c->f[CYLGPU_ETM],
+                                                 c->f[CYLGPU_BXM], c->f[CYLGPU_BRM], c->f[CYLGPU_BTM], c->cfg.dx,
+                                                 c->cfg.dy, c->cfg.y_grid_min_local, c->d_energy);
+  c->stats.kernel_launches += 1;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set || S.n == 0) continue;
+    k_kinetic_energy<<<148 * 4, 256, 0, c->stream>>>(S.d[3], S.d[4], S.d[5], S.d[6], S.sp.mass, S.n,
+                                                     c->d_energy + 1);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(out2, c->d_energy, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // namespace cylgpu

@@ -1,0 +1,373 @@
+"""Host-side mirror of the reference's hot-path module procedures over the cylgpu C-ABI.
+
+One `Slab` is one MPI rank of the reference (one x-slab, one GPU).  Method names and call
+order are the reference's (epoch2d.F90:189-266): `update_eb_fields_half`, `push_particles`,
+`current_finish`, `update_eb_fields_final`, `moving_window`, plus the pieces the reference
+also calls on their own (`particle_bcs`, `efield_bcs`, `bfield_bcs`, `bfield_final_bcs`).
+What stays on the host in the reference stays on the host here: time/step bookkeeping, the
+laser source evaluation (laser.f90:276-328,442-461), the window trigger logic
+(window.F90:330-376) and the generation of the freshly inserted plasma column.
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from .constants import *  # noqa: F401,F403
+from .constants import (BC_CLAMP, BC_CONDUCT, BC_CPML_LASER, BC_CPML_OUTFLOW, BC_OPEN, BC_OTHER, BC_PERIODIC,
+                        BC_REFLECT, BC_SIMPLE_LASER, BC_SIMPLE_OUTFLOW, BD_X_MAX, BD_X_MIN, BD_Y_MIN,
+                        FIELD_NAMES, NG, SNAP_NAMES, TRANSPORT_NONE)
+from .decomp import SlabGrid
+
+
+class CylGpuError(RuntimeError):
+    pass
+
+
+@dataclass
+class Species:   # shared_data.F90:190-280, hot-path members
+    charge: float
+    mass: float
+    bc_particle: tuple = (BC_OPEN, BC_OPEN, BC_OPEN, BC_OPEN)
+    immobile: bool = False
+    zero_current: bool = False
+    # used only for moving-window insertion (window.F90:157-300): uniform plasma
+    npart_per_cell: float = 0.0
+    density: float = 0.0
+    temp: tuple = (0.0, 0.0, 0.0)
+    drift: tuple = (0.0, 0.0, 0.0)
+
+
+@dataclass
+class Laser:     # laser.f90 laser_block restricted to what the decks in scope use
+    boundary: int
+    amp: float
+    omega: float
+    pol_angle: float = 0.0
+    t_start: float = 0.0
+    t_end: float = 1e300
+    t_centre: float = 0.0
+    t_width: float = 0.0      # <= 0 -> constant temporal envelope
+    r_width: float = 0.0      # <= 0 -> flat radial profile
+    phase: float = 0.0
+
+
+def normalise_bc_field(bc):
+    """setup_boundaries, boundary.F90:30-75: returns (bc_field, add_laser)."""
+    bc = list(bc)
+    add_laser = [False] * 4
+    for i in range(4):
+        if bc[i] == BC_OTHER:
+            bc[i] = BC_CLAMP
+        if bc[i] == BC_SIMPLE_LASER:
+            add_laser[i] = True
+        if bc[i] == BC_REFLECT:
+            bc[i] = BC_CLAMP
+        if bc[i] == BC_OPEN:
+            bc[i] = BC_SIMPLE_OUTFLOW
+    return bc, add_laser
+
+
+def normalise_bc_particle(bc):
+    """boundary.F90:109-123."""
+    bc = list(bc)
+    for i in range(4):
+        if i == BD_Y_MIN:
+            continue
+        if bc[i] in (BC_OTHER, BC_CONDUCT):
+            bc[i] = BC_REFLECT
+        if bc[i] in (BC_SIMPLE_LASER, BC_SIMPLE_OUTFLOW, BC_CPML_LASER, BC_CPML_OUTFLOW):
+            bc[i] = BC_OPEN
+    return bc
+
+
+class Slab:
+    def __init__(self, nx, ny, n_mode, x_min, x_max, y_max, bc_field, species, rank=0, nranks=1,
+                 dt_multiplier=0.95, lasers=(), transport=TRANSPORT_NONE, device=-1, fabric=None,
+                 nccl_unique_id=None, sendrecv=None, move_window=False, window_v_x=0.0,
+                 window_start_time=0.0, window_stop_time=1e300, bc_x_min_after_move=BC_SIMPLE_OUTFLOW,
+                 bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None):
+        self.L = _lib.load()
+        self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier)
+        g = self.grid
+        self.n_mode = n_mode
+        self.raw_bc_field = list(bc_field)
+        self.bc_field, self.add_laser = normalise_bc_field(bc_field)
+        self.species = list(species)
+        self.lasers = list(lasers)
+        self.dt = g.dt
+        self.time = 0.0
+        self.step = 0
+        self.move_window = move_window
+        self.window_v_x = window_v_x
+        self.window_start_time = window_start_time
+        self.window_stop_time = window_stop_time
+        self.bc_after_move = (bc_x_min_after_move, bc_x_max_after_move)
+        self.window_started = False
+        self.window_shift_fraction = 0.0
+        self.window_shifts_total = 0
+        self.insert_fn = insert_fn
+        self._keep = []   # ctypes objects that must outlive the handle
+
+        cfg = _lib.Config()
+        cfg.nx, cfg.ny, cfg.nx_global, cfg.ny_global = g.nx, g.ny, g.nx_global, g.ny_global
+        cfg.n_mode, cfg.rank, cfg.nranks = n_mode, rank, nranks
+        cfg.x_min_boundary, cfg.x_max_boundary = int(g.x_min_boundary), int(g.x_max_boundary)
+        cfg.bc_field = (C.c_int32 * 4)(*self.bc_field)
+        cfg.n_species = len(self.species)
+        cfg.device = device
+        cfg.transport = transport
+        cfg.dx, cfg.dy, cfg.dt = g.dx, g.dy, g.dt
+        cfg.x_grid_min_local, cfg.y_grid_min_local = g.x_grid_min_local, g.y_grid_min_local
+        cfg.x_min, cfg.x_max, cfg.y_max = g.x_min, g.x_max, g.y_max
+        cfg.x_min_local, cfg.x_max_local = g.x_min_local, g.x_max_local
+        if nccl_unique_id is not None:
+            buf = C.create_string_buffer(bytes(nccl_unique_id), 128)
+            self._keep.append(buf)
+            cfg.nccl_unique_id = C.cast(buf, C.c_void_p)
+        if sendrecv is not None:
+            cb = _lib.SENDRECV_FN(sendrecv)
+            self._keep.append(cb)
+            cfg.sendrecv = cb
+        if fabric is not None:
+            cfg.fabric = fabric
+        self.h = C.c_void_p()
+        self._ck(self.L.cylgpu_create(C.byref(cfg), C.byref(self.h)))
+        for i, sp in enumerate(self.species):
+            sc = _lib.SpeciesC(sp.charge, sp.mass, (C.c_int32 * 4)(*normalise_bc_particle(sp.bc_particle)),
+                               int(sp.immobile), int(sp.zero_current))
+            self._ck(self.L.cylgpu_set_species(self.h, i, C.byref(sc)))
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise CylGpuError(self.L.cylgpu_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.L.cylgpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def field_shape(self):
+        return (self.n_mode, self.grid.ny + 2 * NG, self.grid.nx + 2 * NG)
+
+    def upload_field(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        assert a.shape == self.field_shape, (a.shape, self.field_shape)
+        self._ck(self.L.cylgpu_upload_field(self.h, FIELD_NAMES.index(name), a.ctypes.data))
+
+    def download_field(self, name):
+        a = np.empty(self.field_shape, dtype=np.complex128)
+        self._ck(self.L.cylgpu_download_field(self.h, FIELD_NAMES.index(name), a.ctypes.data))
+        return a
+
+    def upload_snapshot(self, name, arr):
+        a = np.ascontiguousarray(arr, dtype=np.complex128)
+        assert a.shape == (self.n_mode, self.grid.ny + 2 * NG)
+        self._ck(self.L.cylgpu_upload_snapshot(self.h, SNAP_NAMES.index(name), a.ctypes.data))
+
+    def download_snapshot(self, name):
+        a = np.empty((self.n_mode, self.grid.ny + 2 * NG), dtype=np.complex128)
+        self._ck(self.L.cylgpu_download_snapshot(self.h, SNAP_NAMES.index(name), a.ctypes.data))
+        return a
+
+    def upload_particles(self, isp, aos):
+        a = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 7)
+        self._ck(self.L.cylgpu_upload_particles(self.h, isp, a.shape[0], a.ctypes.data))
+
+    def append_particles(self, isp, aos):
+        a = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 7)
+        self._ck(self.L.cylgpu_append_particles(self.h, isp, a.shape[0], a.ctypes.data))
+
+    def particle_count(self, isp):
+        n = C.c_int64()
+        self._ck(self.L.cylgpu_particle_count(self.h, isp, C.byref(n)))
+        return n.value
+
+    def download_particles(self, isp):
+        n = self.particle_count(isp)
+        a = np.empty((n, 7), dtype=np.float64)
+        nn = C.c_int64()
+        self._ck(self.L.cylgpu_download_particles(self.h, isp, n, a.ctypes.data, C.byref(nn)))
+        return a
+
+    def particle_cells(self, isp):
+        n = self.particle_count(isp)
+        a = np.empty((n, 2), dtype=np.int32)
+        self._ck(self.L.cylgpu_particle_cells(self.h, isp, n, a.ctypes.data))
+        return a
+
+    def stats(self):
+        s = _lib.Stats()
+        self._ck(self.L.cylgpu_stats(self.h, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._ck(self.L.cylgpu_reset_stats(self.h))
+
+    def energy(self):
+        out = (C.c_double * 2)()
+        self._ck(self.L.cylgpu_energy(self.h, out))
+        return out[0], out[1]
+
+    def synchronize(self):
+        self._ck(self.L.cylgpu_synchronize(self.h))
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.cylgpu_set_stream(self.h, stream_ptr))
+
+    def set_dt(self, dt):
+        self.dt = dt
+        self._ck(self.L.cylgpu_set_dt(self.h, dt))
+
+    def set_sort_interval(self, n):
+        self._ck(self.L.cylgpu_set_sort_interval(self.h, n))
+
+    def set_push_variant(self, v):
+        self._ck(self.L.cylgpu_set_push_variant(self.h, v))
+
+    def sort_particles(self):
+        self._ck(self.L.cylgpu_sort_particles(self.h))
+
+    # ------------------------------------------------------------------ host-side laser
+    def laser_sources(self, bd):
+        """source1/source2 on ir = 0..ny (laser.f90:442-461); host work in the reference too."""
+        ny = self.grid.ny
+        s1 = np.zeros(ny + 1)
+        s2 = np.zeros(ny + 1)
+        if not self.add_laser[bd]:
+            return s1, s2
+        yv = self.grid.y_grid_min_local + (np.arange(0, ny + 1, dtype=np.float64) - 1.0) * self.grid.dy
+        for L in self.lasers:
+            if L.boundary != bd or not (L.t_start <= self.time <= L.t_end):
+                continue
+            tprof = 1.0
+            if L.t_width > 0.0:
+                a = (self.time - L.t_centre) / L.t_width
+                tprof = math.exp(-(a * a))
+            t_env = tprof * L.amp
+            prof = np.ones(ny + 1)
+            if L.r_width > 0.0:
+                a = (yv - 0.0) / L.r_width
+                prof = np.exp(-(a * a))
+            base = t_env * prof * math.sin(L.omega * self.time + L.phase)
+            s1 = s1 + base * math.cos(L.pol_angle)
+            s2 = s2 + base * math.sin(L.pol_angle)
+        return s1, s2
+
+    def _src_ptrs(self):
+        s1a, s2a = self.laser_sources(BD_X_MIN)
+        s1b, s2b = self.laser_sources(BD_X_MAX)
+        self._src_keep = (s1a, s2a, s1b, s2b)
+        return [a.ctypes.data for a in self._src_keep]
+
+    # ------------------------------------------------------------------ the hot path
+    def update_eb_fields_half(self):          # fields.f90:316-337
+        self._ck(self.L.cylgpu_fields_half(self.h))
+
+    def push_particles(self):                 # particles.F90:28-734
+        self._ck(self.L.cylgpu_push(self.h))
+
+    def push_particles_no_bcs(self):
+        self._ck(self.L.cylgpu_push_no_bcs(self.h))
+
+    def current_finish(self):                 # current_smooth.F90:29-45
+        self._ck(self.L.cylgpu_current_finish(self.h))
+
+    def update_eb_fields_final(self):         # fields.f90:341-353
+        self._ck(self.L.cylgpu_fields_final(self.h, *self._src_ptrs()))
+
+    def update_e_field(self):
+        self._ck(self.L.cylgpu_update_e_field(self.h))
+
+    def update_b_field(self):
+        self._ck(self.L.cylgpu_update_b_field(self.h))
+
+    def efield_bcs(self):
+        self._ck(self.L.cylgpu_efield_bcs(self.h))
+
+    def bfield_bcs(self, mpi_only):
+        self._ck(self.L.cylgpu_bfield_bcs(self.h, int(mpi_only)))
+
+    def bfield_final_bcs(self):
+        self._ck(self.L.cylgpu_bfield_final_bcs(self.h, *self._src_ptrs()))
+
+    def particle_bcs(self):
+        self._ck(self.L.cylgpu_particle_bcs(self.h))
+
+    def current_bcs(self):
+        self._ck(self.L.cylgpu_current_bcs(self.h))
+
+    def snapshot_field_boundaries(self):      # setup.F90:393-423
+        self._ck(self.L.cylgpu_snapshot_field_boundaries(self.h))
+
+    def init_half_step(self):                 # epoch2d.F90:143-161
+        self.particle_bcs()
+        self.efield_bcs()
+        dt_store = self.dt
+        self.set_dt(self.dt / 2.0)
+        self.time = self.time + self.dt
+        self.bfield_final_bcs()
+        self.set_dt(dt_store)
+
+    def moving_window(self):                  # window.F90:330-376
+        if not self.move_window:
+            return
+        if not self.window_started:
+            if self.window_start_time <= self.time < self.window_stop_time:
+                raw = list(self.raw_bc_field)
+                raw[BD_X_MIN], raw[BD_X_MAX] = self.bc_after_move
+                self.raw_bc_field = raw
+                self.bc_field, self.add_laser = normalise_bc_field(raw)
+                self._ck(self.L.cylgpu_set_bc_field(self.h, (C.c_int32 * 4)(*self.bc_field)))
+                self.window_shift_fraction = 0.0
+                self.window_started = True
+        if not self.window_started or self.time >= self.window_stop_time or self.window_v_x <= 0.0:
+            return
+        self.window_shift_fraction = self.window_shift_fraction + self.dt * self.window_v_x / self.grid.dx
+        cells = int(math.floor(self.window_shift_fraction))
+        if cells > 0:
+            for _ in range(cells):
+                self._shift_window_once()
+            self.particle_bcs()
+            self.window_shift_fraction = self.window_shift_fraction - float(cells)
+
+    def _shift_window_once(self):             # window.F90:62-94, one cell
+        nsp = len(self.species)
+        n_new = (C.c_int64 * max(nsp, 1))()
+        ptrs = (C.c_void_p * max(nsp, 1))()
+        keep = []
+        if self.grid.x_max_boundary and self.insert_fn is not None:
+            for isp in range(nsp):
+                aos = self.insert_fn(self, isp)      # insert_particles stays on the host
+                if aos is not None and len(aos):
+                    a = np.ascontiguousarray(aos, dtype=np.float64).reshape(-1, 7)
+                    keep.append(a)
+                    n_new[isp] = a.shape[0]
+                    ptrs[isp] = a.ctypes.data
+        self.grid.shift()
+        g = self.grid
+        grid5 = (C.c_double * 5)(g.x_grid_min_local, g.x_min, g.x_max, g.x_min_local, g.x_max_local)
+        self._ck(self.L.cylgpu_window_shift(self.h, n_new, ptrs, grid5))
+        self.window_shifts_total += 1
+
+    def step_once(self, flush_rng=None):      # epoch2d.F90:189-266 loop body, optional physics off
+        self.update_eb_fields_half()
+        self.push_particles()
+        self.current_finish()
+        self.step += 1
+        self.time = self.time + self.dt / 2.0
+        if flush_rng is not None:
+            flush_rng()                       # output_routines -> random_flush_cache, diagnostics.F90:235
+        self.time = self.time + self.dt / 2.0
+        self.update_eb_fields_final()
+        self.moving_window()

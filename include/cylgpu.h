@@ -1,0 +1,208 @@
+/* cylgpu.h -- C-ABI of the B200-native per-timestep PIC hot path of cylindrical EPOCH.
+ *
+ * One `cylgpu_handle` == one MPI rank of the reference == one x-slab == one GPU.
+ * The reference has no plugin API: the seam is the set of argument-less Fortran module
+ * procedures that operate on `shared_data` globals.  Every entry point below names the
+ * reference procedure (file:line under /root/reference/epoch_axial/src) it replaces; the
+ * iso_c_binding stub a maintainer adds on the Fortran side is in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure (Fortran then calls
+ *     abort_code, utilities.f90:261); cylgpu_last_error() gives the message;
+ *   - mode arrays are Fortran column-major (ix, ir, im) with lower bounds
+ *     (1-ng, 1-ng, 0), ng = 5, COMPLEX(num) == interleaved re/im doubles
+ *     (shared_data.F90:474-478, mpi_routines.F90:385-400); the address passed is that of
+ *     element (1-ng, 1-ng, 0);
+ *   - "x" is the cylinder axis, grid "y" is r; particle pos/p are Cartesian (x, y, z);
+ *   - decomposition is x-slabs only (nprocx = nranks, nprocy = 1).
+ *   - no torch types, no C++ types: plain pointers and sizes only.
+ */
+#ifndef CYLGPU_H
+#define CYLGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CYLGPU_NG 5            /* constants.F90:544-545 (ng = jng = png + 2, triangle shape) */
+#define CYLGPU_NFIELDS 15      /* exm erm etm bxm brm btm jxm jrm jtm b*_old j*_old */
+#define CYLGPU_NSNAPS 12       /* {exm erm etm bxm brm btm}_x_min then _x_max, setup.F90:393-423 */
+#define CYLGPU_MAX_SPECIES 8
+
+/* boundary-condition codes, constants.F90:55-72 (values after setup_boundaries()
+ * normalisation, boundary.F90:44-57,109-123) */
+enum {
+  CYLGPU_BC_PERIODIC = 1, CYLGPU_BC_SIMPLE_LASER = 3, CYLGPU_BC_SIMPLE_OUTFLOW = 4,
+  CYLGPU_BC_OPEN = 5, CYLGPU_BC_ZERO_GRADIENT = 7, CYLGPU_BC_CLAMP = 8, CYLGPU_BC_REFLECT = 9,
+  CYLGPU_BC_CONDUCT = 10, CYLGPU_BC_CPML_LASER = 12, CYLGPU_BC_CPML_OUTFLOW = 13,
+  CYLGPU_BC_ZERO_B = 16
+};
+/* boundary ids (0-based; reference c_bd_x_min..c_bd_y_max = 1..4) */
+enum { CYLGPU_BD_X_MIN = 0, CYLGPU_BD_X_MAX = 1, CYLGPU_BD_Y_MIN = 2, CYLGPU_BD_Y_MAX = 3 };
+/* field ids for upload/download/device_ptr */
+enum {
+  CYLGPU_EXM = 0, CYLGPU_ERM, CYLGPU_ETM, CYLGPU_BXM, CYLGPU_BRM, CYLGPU_BTM,
+  CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, CYLGPU_BXM_OLD, CYLGPU_BRM_OLD, CYLGPU_BTM_OLD,
+  CYLGPU_JXM_OLD, CYLGPU_JRM_OLD, CYLGPU_JTM_OLD
+};
+/* transports for the x-neighbour exchange (MPI_SENDRECV in the reference) */
+enum {
+  CYLGPU_TRANSPORT_NONE = 0,     /* nranks == 1 (periodic wraps onto itself on the device) */
+  CYLGPU_TRANSPORT_NCCL = 1,     /* ncclSend/ncclRecv over NVLink; libnccl is dlopen()ed */
+  CYLGPU_TRANSPORT_CALLBACK = 2, /* caller-supplied sendrecv (e.g. torch.distributed) */
+  CYLGPU_TRANSPORT_FABRIC = 3    /* several handles inside ONE process (tests, 1 GPU) */
+};
+
+typedef struct cylgpu_ctx* cylgpu_handle;
+
+/* Caller-supplied exchange used by CYLGPU_TRANSPORT_CALLBACK.  All four buffers are DEVICE
+ * pointers; byte counts may be 0; rank -1 means "no neighbour" (MPI_PROC_NULL).  It must
+ * behave like the pair of MPI_SENDRECVs at boundary.F90:528,541: send `send_left` to
+ * `left`, `send_right` to `right`, receive `recv_left` from `left`, `recv_right` from
+ * `right`; the work may be left in flight on `stream` (a cudaStream_t). */
+typedef int (*cylgpu_sendrecv_fn)(void* user, int left, int right,
+                                  const void* send_left, size_t send_left_bytes,
+                                  void* recv_left, size_t recv_left_bytes,
+                                  const void* send_right, size_t send_right_bytes,
+                                  void* recv_right, size_t recv_right_bytes, void* stream);
+
+/* Everything the hot path reads from shared_data (shared_data.F90:473-488,656-667) that is
+ * not an array.  Filled by the Fortran shim after mpi_initialise / setup_grid / set_dt. */
+typedef struct cylgpu_config {
+  int32_t nx, ny;                /* local cells of this rank (mpi_routines.F90:312-337) */
+  int32_t nx_global, ny_global;
+  int32_t n_mode;                /* deck_control_block.F90:244 */
+  int32_t rank, nranks;          /* x_coords, nprocx (nprocy must be 1) */
+  int32_t x_min_boundary, x_max_boundary;   /* shared_data.F90:660 */
+  int32_t bc_field[4];           /* after setup_boundaries */
+  int32_t n_species;
+  int32_t device;                /* CUDA device ordinal; -1 = current device */
+  int32_t transport;             /* CYLGPU_TRANSPORT_* */
+  double dx, dy, dt;
+  double x_grid_min_local;       /* x(1) of this rank, utilities.f90:343-372 */
+  double y_grid_min_local;       /* y(1) = dy/2 on the axis rank, setup.F90:173-183 */
+  double x_min, x_max, y_max;    /* global physical domain (moves with the window) */
+  double x_min_local, x_max_local;
+  /* transport parameters */
+  const void* nccl_unique_id;    /* 128 bytes from ncclGetUniqueId (NCCL transport) */
+  cylgpu_sendrecv_fn sendrecv;   /* CALLBACK transport */
+  void* sendrecv_user;
+  void* fabric;                  /* FABRIC transport: from cylgpu_fabric_create */
+  int64_t particle_capacity;     /* per species; 0 = grow on demand */
+} cylgpu_config;
+
+/* shared_data.F90:190-280, hot-path members only */
+typedef struct cylgpu_species {
+  double charge, mass;
+  int32_t bc_particle[4];        /* after setup_boundaries: periodic / open / reflect */
+  int32_t immobile, zero_current;
+} cylgpu_species;
+
+/* cylgpu_stats: integer outputs that must match the reference bit-exactly */
+typedef struct cylgpu_stats_t {
+  int64_t n_particles[CYLGPU_MAX_SPECIES];   /* species_list(:)%attached_list%count */
+  int64_t n_sent_left, n_sent_right;         /* last particle_bcs, all species */
+  int64_t n_removed, n_recv;
+  int64_t n_window_removed;                  /* last window shift, remove_particles */
+  int64_t n_sorts;                           /* cell-tile sorts performed so far */
+  int64_t kernel_launches;                   /* kernels launched since create/reset */
+  /* device time (ms, CUDA events on the library stream) accumulated since reset */
+  double ms_fields, ms_push, ms_bcs, ms_sort, ms_exchange;
+} cylgpu_stats_t;
+
+const char* cylgpu_last_error(void);
+int cylgpu_version(void);
+
+/* in-process fabric joining `nranks` handles of one process (tests on a single GPU) */
+void* cylgpu_fabric_create(int nranks);
+void cylgpu_fabric_destroy(void* fabric);
+/* fills 128 bytes; wraps ncclGetUniqueId of the dlopen()ed libnccl */
+int cylgpu_nccl_unique_id(void* out128);
+
+/* replaces: allocation in mpi_initialise (mpi_routines.F90:385-400) + setup of the
+ * per-rank constants used by particles.F90:146-217 */
+int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out);
+int cylgpu_destroy(cylgpu_handle h);
+int cylgpu_set_species(cylgpu_handle h, int ispecies, const cylgpu_species* sp);
+/* epoch2d.F90:157-161 plays with dt around the start-up half step */
+int cylgpu_set_dt(cylgpu_handle h, double dt);
+/* window.F90:341-349: bc_field swapped to bc_*_after_move, setup_boundaries re-run */
+int cylgpu_set_bc_field(cylgpu_handle h, const int32_t bc_field[4]);
+/* run the library's work on a caller stream (cudaStream_t), NULL = library-owned stream */
+int cylgpu_set_stream(cylgpu_handle h, void* stream);
+int cylgpu_synchronize(cylgpu_handle h);
+
+/* host <-> device mirrors of the shared_data arrays.  `host` has the full Fortran extent
+ * (nx+2ng)*(ny+2ng)*n_mode complex; snapshots are (ny+2ng)*n_mode complex. */
+int cylgpu_upload_field(cylgpu_handle h, int field_id, const void* host);
+int cylgpu_download_field(cylgpu_handle h, int field_id, void* host);
+int cylgpu_upload_snapshot(cylgpu_handle h, int snap_id, const void* host);
+int cylgpu_download_snapshot(cylgpu_handle h, int snap_id, void* host);
+void* cylgpu_field_device_ptr(cylgpu_handle h, int field_id);
+/* setup.F90:393-423 setup_field_boundaries, evaluated on the device arrays */
+int cylgpu_snapshot_field_boundaries(cylgpu_handle h);
+
+/* particles: AoS on the wire exactly like pack_particle (partlist.F90:414-428):
+ * 7 doubles per particle = pos(3), p(3), weight.  `host_aos` is n*7 doubles. */
+int cylgpu_upload_particles(cylgpu_handle h, int ispecies, int64_t n, const double* host_aos);
+int cylgpu_append_particles(cylgpu_handle h, int ispecies, int64_t n, const double* host_aos);
+int cylgpu_download_particles(cylgpu_handle h, int ispecies, int64_t capacity, double* host_aos,
+                              int64_t* n_out);
+int cylgpu_particle_count(cylgpu_handle h, int ispecies, int64_t* n_out);
+/* per-particle (cell_x, cell_y) of split_particle.F90:62-63, int32 pairs, device order */
+int cylgpu_particle_cells(cylgpu_handle h, int ispecies, int64_t capacity, int32_t* cells_out);
+/* SoA device pointers: comp 0..6 = x y z px py pz w */
+void* cylgpu_particle_device_ptr(cylgpu_handle h, int ispecies, int comp);
+
+/* ---- the hot path, in driver order (epoch2d.F90:189-266) ---- */
+/* fields.f90:316-337 update_eb_fields_half */
+int cylgpu_fields_half(cylgpu_handle h);
+/* particles.F90:28-734 push_particles, including current_bcs_r_min_final
+ * (boundary.F90:1909) and particle_bcs (boundary.F90:1541) */
+int cylgpu_push(cylgpu_handle h);
+/* current_smooth.F90:29-45 current_finish (smoothing off) */
+int cylgpu_current_finish(cylgpu_handle h);
+/* fields.f90:341-353 update_eb_fields_final.  source1/source2 are the host-evaluated laser
+ * sources (laser.f90:442-461) on ir = 0..ny for x_min and x_max; NULL = no laser there. */
+int cylgpu_fields_final(cylgpu_handle h, const double* src1_xmin, const double* src2_xmin,
+                        const double* src1_xmax, const double* src2_xmax);
+/* window.F90:62-94 shift_window for ONE cell: append the host-generated column
+ * (insert_particles, window.F90:157-300; n_new[is] particles each, AoS, may be NULL),
+ * take the grid the host's setup_grid_x (utilities.f90:343-372) computed for the shifted
+ * window, grid5 = {x_grid_min_local, x_min, x_max, x_min_local, x_max_local},
+ * remove_particles (x_min rank), shift_fields.  The caller runs cylgpu_particle_bcs
+ * afterwards exactly like window.F90:364. */
+int cylgpu_window_shift(cylgpu_handle h, const int64_t* n_new, const double* const* new_aos,
+                        const double* grid5);
+
+/* ---- pieces, exposed because the reference calls them on their own ---- */
+int cylgpu_update_e_field(cylgpu_handle h);                 /* fields.f90:53-182 */
+int cylgpu_update_b_field(cylgpu_handle h);                 /* fields.f90:186-312 */
+int cylgpu_efield_bcs(cylgpu_handle h);                     /* boundary.F90:1355-1413 */
+int cylgpu_bfield_bcs(cylgpu_handle h, int mpi_only);       /* boundary.F90:1417-1476 */
+int cylgpu_bfield_final_bcs(cylgpu_handle h, const double* src1_xmin, const double* src2_xmin,
+                            const double* src1_xmax, const double* src2_xmax);  /* :1505-1537 */
+int cylgpu_particle_bcs(cylgpu_handle h);                   /* boundary.F90:1541-1889 */
+int cylgpu_push_no_bcs(cylgpu_handle h);                    /* particles.F90:163-730 + :1909 */
+int cylgpu_current_bcs(cylgpu_handle h);                    /* boundary.F90:1893-1905 */
+/* cell-tile sort of the SoA arrays (no reference counterpart: replaces the linked list) */
+int cylgpu_sort_particles(cylgpu_handle h);
+int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = never */
+/* 0 = one thread per particle, global atomics; 1 = cell-tile kernel (default) */
+int cylgpu_set_push_variant(cylgpu_handle h, int variant);
+
+/* diagnostics the new code must own: field + kinetic energy from the
+ * mode arrays with cylindrical volume elements; out[0] = field J, out[1] = kinetic J */
+int cylgpu_energy(cylgpu_handle h, double* out2);
+int cylgpu_stats(cylgpu_handle h, cylgpu_stats_t* out);
+int cylgpu_reset_stats(cylgpu_handle h);
+/* per-phase CUDA-event timers in cylgpu_stats (adds a host sync per phase); default off */
+int cylgpu_set_timing(cylgpu_handle h, int on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CYLGPU_H */

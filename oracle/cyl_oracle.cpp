@@ -729,7 +729,10 @@ void World::outflow_bcs_r_max(Rank& r) {   // laser.f90:637-690
   double dtc2 = dt * (c * c);
   double inv_r = 1.0 / ((double)((float)ny - 1.5f) * dy + y_grid_min_local);
   double dtc2_4r = 0.25 * dtc2 * inv_r;
-  cplx icdt_2r = (((0.5 * IMAGI) * c) * dt) * inv_r;
+  // REFERENCE QUIRK (reproduced): icdt_2r is declared REAL(num) (laser.f90:640) but assigned
+  // the purely imaginary 0.5*imagi*c*dt*inv_r, so Fortran keeps only its real part = 0 and
+  // the two azimuthal (im) coupling terms below vanish identically.
+  double icdt_2r = ((((0.5 * IMAGI) * c) * dt) * inv_r).re;
   double lx = dtc2 / dx, ly = dtc2 / dy;
   double sum_x = 1.0 / (ly + c);
   double sum_t = 1.0 / (ly + c + dtc2_4r);
@@ -787,10 +790,10 @@ void World::bfield_final_bcs() {   // boundary.F90:1505-1537
 // concurrently; it is only compiled in for the CPU-baseline timing build)
 void World::update_eb_fields_half() {   // fields.f90:316-337
   const int P = (int)ranks.size();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
   for (int k = 0; k < P; ++k) update_e_field(ranks[k]);
   efield_bcs();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
   for (int k = 0; k < P; ++k) {
     Rank& r = ranks[k];
     r.bxm_old.d = r.bxm.d;
@@ -803,10 +806,10 @@ void World::update_eb_fields_half() {   // fields.f90:316-337
 
 void World::update_eb_fields_final() {   // fields.f90:341-353
   const int P = (int)ranks.size();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
   for (int k = 0; k < P; ++k) update_b_field(ranks[k]);
   bfield_final_bcs();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
   for (int k = 0; k < P; ++k) update_e_field(ranks[k]);
   efield_bcs();
 }
@@ -1107,7 +1110,7 @@ void World::push_rank(Rank& r) {
 
 void World::push_particles() {
   const int P = (int)ranks.size();
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
   for (int k = 0; k < P; ++k) push_rank(ranks[k]);
   particle_bcs();
 }
@@ -1163,7 +1166,7 @@ void World::particle_bcs() {
   for (size_t isp = 0; isp < species.size(); ++isp) {
     const int* bc_species = species[isp].bc_particle;
     std::vector<std::vector<Particle>> send_l(P), send_r(P);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (P > 1)
     for (int k = 0; k < P; ++k) {
       Rank& r = ranks[k];
       std::vector<Particle>& pl = r.parts[isp];

@@ -56,6 +56,9 @@ def build(force=False):
 def lib():
     global _LIB
     if _LIB is None:
+        # idle OpenMP workers must sleep, not spin: the oracle's parallel regions are short and
+        # the test box is usually oversubscribed
+        os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         L = C.CDLL(build())
         L.cylo_create.restype = C.c_void_p
         L.cylo_create.argtypes = [C.POINTER(CyloConfig)]

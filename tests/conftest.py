@@ -1,0 +1,28 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__file__))):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def oracle_lib():
+    import pyoracle
+    return pyoracle.lib()
+
+
+@pytest.fixture(scope="session")
+def cylgpu_lib():
+    """The product library; built in-tree if stale (nvcc cross-compiles without a GPU)."""
+    from cylindrical_epoch_b200 import build, _lib
+    if os.path.isdir("/usr/local/cuda/bin"):
+        build.build()
+    return _lib.load()

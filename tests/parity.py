@@ -1,0 +1,141 @@
+"""Shared driver for the GPU parity tests: steps the CPU oracle and the CUDA product side by
+side from the same initial state and compares everything the north star names."""
+import threading
+
+import numpy as np
+
+import cylindrical_epoch_b200 as ce
+from cylindrical_epoch_b200.constants import FIELD_NAMES, TRANSPORT_FABRIC, TRANSPORT_NONE
+import decks
+
+# Relative tolerance (max-norm, relative to the array's max magnitude) on fields, currents and
+# particle phase space: deposit summation order differs (atomics) and nvcc contracts FMAs.
+TOL = 1.0e-10
+
+
+def by_weight(aos):
+    a = np.asarray(aos).reshape(-1, 7)
+    return a[np.lexsort((a[:, 0], a[:, 6]))]
+
+
+class Pair:
+    """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
+
+    def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None):
+        self.deck = deck
+        self.nranks = nranks
+        self.oracle = decks.make_oracle(deck, nranks=nranks)
+        self.fabric = None
+        kw = {}
+        if nranks > 1:
+            from cylindrical_epoch_b200 import _lib
+            self.fabric = _lib.load().cylgpu_fabric_create(nranks)
+            kw = dict(transport=TRANSPORT_FABRIC, fabric=self.fabric)
+        self.slabs = [decks.make_slab(deck, rank=k, nranks=nranks, **kw) for k in range(nranks)]
+        for k, s in enumerate(self.slabs):
+            decks.copy_state(self.oracle, s, k)
+            if variant is not None:
+                s.set_push_variant(variant)
+            if sort_interval is not None:
+                s.set_sort_interval(sort_interval)
+        if init_half_step:
+            self.oracle.call("init_half_step")
+            self.each(lambda s: s.init_half_step())
+
+    def each(self, fn):
+        """run fn on every slab; ranks > 1 need one host thread each (blocking exchanges)."""
+        if self.nranks == 1:
+            fn(self.slabs[0])
+            return
+        errs = []
+
+        def run(s):
+            try:
+                fn(s)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        ts = [threading.Thread(target=run, args=(s,)) for s in self.slabs]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def step(self, n=1):
+        for _ in range(n):
+            self.oracle.call("step")
+            self.each(lambda s: s.step_once())
+
+    def close(self):
+        for s in self.slabs:
+            s.close()
+        if self.fabric:
+            from cylindrical_epoch_b200 import _lib
+            _lib.load().cylgpu_fabric_destroy(self.fabric)
+            self.fabric = None
+
+    # ---- comparisons ----
+    def field_errors(self, names=FIELD_NAMES):
+        out = {}
+        for name in names:
+            worst = 0.0
+            # normalise by the global (all-rank) magnitude of the array
+            den = max(np.abs(self.oracle.field(k, name)).max() for k in range(self.nranks))
+            for k, s in enumerate(self.slabs):
+                d = np.abs(s.download_field(name) - self.oracle.field(k, name)).max()
+                worst = max(worst, d)
+            out[name] = 0.0 if worst == 0.0 else (float("inf") if den == 0.0 else worst / den)
+        return out
+
+    def check_fields(self, tol=TOL, names=FIELD_NAMES):
+        errs = self.field_errors(names)
+        bad = {k: v for k, v in errs.items() if not v <= tol}
+        assert not bad, f"field mismatch (tol {tol}): {bad}"
+        return errs
+
+    def check_particles(self, tol=TOL):
+        worst = 0.0
+        for isp in range(len(self.deck.species)):
+            for k, s in enumerate(self.slabs):
+                ref = self.oracle.particles(k, isp)
+                got = s.download_particles(isp)
+                # integer outputs: bit-exact
+                assert got.shape[0] == ref.shape[0], f"species {isp} rank {k}: count {got.shape[0]} != {ref.shape[0]}"
+                assert s.particle_count(isp) == self.oracle.nparticles(k, isp)
+                if ref.shape[0] == 0:
+                    continue
+                ref, got = by_weight(ref), by_weight(got)
+                assert np.array_equal(ref[:, 6], got[:, 6]), "weights must be carried bit-exactly"
+                for cols in ((0, 1, 2), (3, 4, 5)):
+                    den = np.abs(ref[:, cols]).max()
+                    if den > 0:
+                        worst = max(worst, np.abs(ref[:, cols] - got[:, cols]).max() / den)
+        assert worst <= tol, f"particle phase-space mismatch {worst} > {tol}"
+        return worst
+
+    def check_cells(self):
+        """bit-exact per-particle (cell_x, cell_y) of split_particle.F90:62-63"""
+        for isp in range(len(self.deck.species)):
+            for k, s in enumerate(self.slabs):
+                ref = self.oracle.particles(k, isp)
+                if ref.shape[0] == 0:
+                    continue
+                info = self.oracle.rank_info(k)
+                sc = self.oracle.scalars()
+                r = np.sqrt(ref[:, 1] ** 2 + ref[:, 2] ** 2)
+                cx = np.floor((ref[:, 0] - info["x_grid_min_local"]) / sc["dx"] + 1.5).astype(np.int32)
+                cy = np.floor((r - sc["y_grid_min_local"]) / sc["dy"] + 1.5).astype(np.int32)
+                got = s.download_particles(isp)
+                cells = s.particle_cells(isp)
+                o_ref = np.lexsort((ref[:, 0], ref[:, 6]))
+                o_got = np.lexsort((got[:, 0], got[:, 6]))
+                assert np.array_equal(cx[o_ref], cells[o_got, 0]), "cell_x differs"
+                assert np.array_equal(cy[o_ref], cells[o_got, 1]), "cell_y differs"
+
+    def check_counts(self):
+        for k, s in enumerate(self.slabs):
+            st = s.stats()
+            ref = self.oracle.stats(k)
+            assert (st.n_sent_left, st.n_sent_right, st.n_removed, st.n_recv) == (
+                ref["sent_left"], ref["sent_right"], ref["removed"], ref["received"]), (k, ref)

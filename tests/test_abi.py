@@ -1,0 +1,55 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads, and exports
+exactly the symbols include/cylgpu.h declares; compute calls fail loudly without a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cylgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cylgpu_[a-z0-9_]+)\s*\(", src)) - {"cylgpu_sendrecv_fn"})
+
+
+def test_library_exports_every_header_symbol(cylgpu_lib):
+    from cylindrical_epoch_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(cylgpu_lib, n), f"libcylgpu.so does not export {n}"
+    # and the ctypes table binds every one of them (no stale entries either way)
+    assert sorted(_lib.SYMBOLS) == names
+
+
+def test_struct_layouts_match_header(cylgpu_lib):
+    from cylindrical_epoch_b200 import _lib
+    # sizes follow from the field lists in the header (LP64)
+    assert ctypes.sizeof(_lib.SpeciesC) == 16 + 16 + 8
+    assert ctypes.sizeof(_lib.Stats) == 8 * (8 + 7) + 8 * 5
+    assert ctypes.sizeof(_lib.Config) == 4 * 16 + 8 * 10 + 8 * 5
+
+
+def test_no_cpu_fallback(cylgpu_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cylindrical_epoch_b200 as ce
+    with pytest.raises(ce.CylGpuError, match="no CPU fallback"):
+        ce.Slab(64, 32, 2, 0.0, 1e-5, 1e-5, [3, 5, 0, 5], [ce.Species(-1.6e-19, 9.1e-31)])
+
+
+def test_product_never_touches_the_oracle():
+    """the product package and its CUDA sources must not import/link/include oracle/"""
+    pkg = os.path.join(ROOT, "cylindrical_epoch_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in txt and "cyl_oracle" not in txt, f
+                assert not re.search(r"(import|from|include)\s+.*\boracle\b", txt), f
