@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the cylindrical-EPOCH per-timestep PIC hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path in driver order (epoch2d.F90:189-266):
+update_eb_fields_half -> push_particles (gather + Boris + deposit + particle_bcs) ->
+current_finish -> update_eb_fields_final, on synthetic plasma of a BASELINE.json shape.
+
+N = 1 workload: BASELINE.json configs[1], thermal periodic plasma, m = 0..1, 2048 x 256 grid,
+64 ppc (33.5 M macro-particles).  N > 1: the same slab per GPU (weak scaling, x-slabs in a
+periodic ring, NCCL send/recv for field halos, additive J ghosts and migrating particles).
+
+Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with all state resident
+in HBM; `e2e` is the same step driven through the C-ABI in host-authoritative mode (particles
+and the nine E/B/J mode arrays uploaded from pinned host memory before and downloaded after
+every step -- the drop-in's "sync every step" slow path).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: nx (per GPU), ny, n_mode, ppc, kind
+    "thermal_2048x256_m2_ppc64": dict(nx=2048, ny=256, n_mode=2, ppc=64, kind="thermal"),
+    "thermal_1024x256_m2_ppc64": dict(nx=1024, ny=256, n_mode=2, ppc=64, kind="thermal"),
+    "thermal_512x128_m2_ppc16": dict(nx=512, ny=128, n_mode=2, ppc=16, kind="thermal"),
+    "modes5_4096x512_m5_ppc16": dict(nx=4096, ny=512, n_mode=5, ppc=16, kind="thermal"),
+}
+DEFAULT_WORKLOAD = "thermal_2048x256_m2_ppc64"
+
+TEMP_K = 1.16e7        # ~1 keV
+DENSITY = 1.0e24       # m^-3
+DXY = 0.5e-6
+
+
+def algorithmic_bytes_per_particle_step(n_mode, ppc):
+    """7 doubles read + 6 written per particle, plus 6M complex field reads and
+    3M complex J writes per cell amortised over ppc."""
+    return 104.0 + 144.0 * n_mode / ppc
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured"
+    except Exception:   # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, mass):
+    """Uniform thermal load in the shape of helper.F90:552-583 / particle_temperature.F90:388-398
+    (positions uniform in x and r per cell, theta uniform, weight = n 2 pi r dx dy / ppc).
+    numpy RNG -- the bench does not need the reference's KISS stream."""
+    from cylindrical_epoch_b200.constants import KB
+    n = nx * ny * ppc
+    out = np.empty((n, 7), dtype=np.float64)
+    ix = np.repeat(np.tile(np.arange(nx, dtype=np.float64), ny), ppc)
+    iy = np.repeat(np.arange(ny, dtype=np.float64), nx * ppc)
+    out[:, 0] = x_grid_min_local + ix * dx + (rng.random(n) - 0.5) * dx
+    r = 0.5 * dy + iy * dy + (rng.random(n) - 0.5) * dy
+    th = 2.0 * np.pi * rng.random(n)
+    out[:, 1] = r * np.cos(th)
+    out[:, 2] = r * np.sin(th)
+    sd = np.sqrt(TEMP_K * KB * mass)
+    out[:, 3:6] = rng.normal(0.0, sd, size=(n, 3))
+    out[:, 6] = DENSITY * 2.0 * np.pi * dx * dy * r / ppc
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:   # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:   # noqa: BLE001
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = float(parts[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the CPU restatement of the reference (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_port_rate(wl, max_seconds=25.0, steps=2):
+    """particle-steps/s and cell-mode-updates/s of the oracle (kind "port": the reference is
+    Fortran + MPI and cannot be compiled in this image) on a BOUNDED sample of the workload:
+    same ny / n_mode / ppc / temperature, x extent cut to 32 cells per host thread, one
+    x-slab per thread (the reference's own MPI decomposition, emulated with OpenMP)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import decks
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:   # noqa: BLE001
+        pass
+    nranks = max(1, min(cores, 64))
+    os.environ.setdefault("OMP_NUM_THREADS", str(nranks))
+    nx_sample = 32 * nranks
+    d = decks.thermal(nx=nx_sample, ny=wl["ny"], n_mode=wl["n_mode"], ppc=wl["ppc"], temp_k=TEMP_K,
+                      density=DENSITY)
+    t0 = time.time()
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    t_load = time.time() - t0
+    npart = sum(w.nparticles(k, 0) for k in range(nranks))
+    w.call("step")   # warm-up
+    t_push = t_fields = 0.0
+    done = 0
+    t_start = time.time()
+    for _ in range(steps):
+        tf = w.call("fields_half")
+        tp = w.call("push")
+        tc = w.call("current_finish")
+        w.call("advance_half_time"); w.call("advance_half_time")
+        tf2 = w.call("fields_final")
+        t_push += tp
+        t_fields += tf + tf2
+        done += 1
+        if time.time() - t_start > max_seconds:
+            break
+        _ = tc
+    total = time.time() - t_start
+    return dict(value=npart * done / total, unit="particle-steps/s", cores=nranks, kind="port",
+                sample=f"{nx_sample}x{wl['ny']} cells, m=0..{wl['n_mode'] - 1}, {wl['ppc']} ppc = {npart} "
+                       f"particles, {done} steps, {nranks} x-slabs on {nranks} OpenMP threads "
+                       f"(load {t_load:.1f}s untimed)",
+                field_cell_mode_updates_per_s=nx_sample * wl["ny"] * wl["n_mode"] * done / max(t_fields, 1e-9),
+                push_only_particle_steps_per_s=npart * done / max(t_push, 1e-9))
+
+
+def run_reference(args, wl_name, wl):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    res = None
+    t0 = time.time()
+    for _ in range(max(1, args.warmup > 0)):
+        pass
+    res = cpu_port_rate(wl, max_seconds=60.0, steps=max(1, min(args.steps, 3)))
+    ms = 1e3 * (time.time() - t0)
+    line = {
+        "impl": "reference", "metric": "particle-steps/sec (push+gather+deposit)", "value": res["value"],
+        "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "note": "CPU restatement of the reference (oracle port), bounded sample"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "field_cell_mode_updates_per_s": res["field_cell_mode_updates_per_s"],
+        "e2e": {"value": res["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args, wl_name, wl):
+    import torch
+    import cylindrical_epoch_b200 as ce
+    from cylindrical_epoch_b200 import build as cbuild
+    from cylindrical_epoch_b200.constants import (BC_OPEN, BC_PERIODIC, BC_REFLECT, BC_ZERO_B, FIELD_NAMES, M0, Q0,
+                                                  TRANSPORT_NCCL, TRANSPORT_NONE)
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    if not os.path.exists(os.path.join(ROOT, "cylindrical_epoch_b200", "libcylgpu.so")):
+        cbuild.build()
+    torch.cuda.set_device(local)
+    dist = None
+    uid = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        from cylindrical_epoch_b200 import _lib
+        import ctypes
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            rc = _lib.load().cylgpu_nccl_unique_id(buf)
+            assert rc == 0, _lib.load().cylgpu_last_error()
+        t = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        uid = bytes(t.cpu().numpy().tobytes())
+
+    nx, ny, M, ppc = wl["nx"], wl["ny"], wl["n_mode"], wl["ppc"]
+    nxg = nx * world
+    bcp = (BC_PERIODIC, BC_PERIODIC, BC_OPEN, BC_REFLECT)
+    species = [ce.Species(-Q0, M0, bcp, False, False, ppc, DENSITY, (TEMP_K,) * 3)]
+    slab = ce.Slab(nxg, ny, M, 0.0, nxg * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], species,
+                   rank=rank, nranks=world, transport=TRANSPORT_NCCL if world > 1 else TRANSPORT_NONE,
+                   device=local, nccl_unique_id=uid)
+    g = slab.grid
+    rng = np.random.default_rng(7842432 + rank)
+    # pinned host image of the particle list (also the e2e upload source)
+    n0 = nx * ny * ppc
+    host_p = torch.empty((n0 + n0 // 8, 7), dtype=torch.float64, pin_memory=True)
+    hp = host_p.numpy()
+    hp[:n0] = thermal_particles(rng, nx, ny, ppc, g.dx, g.dy, g.x_grid_min_local, M0)
+    slab.upload_particles(0, hp[:n0])
+    # run the library on a torch-owned stream so that torch.cuda.Event brackets its work
+    tstream = torch.cuda.Stream(device=local)
+    slab.set_stream(tstream.cuda_stream)
+    slab.init_half_step()
+    slab.L.cylgpu_set_timing(slab.h, 1)
+
+    def barrier():
+        slab.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        slab.synchronize()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        slab.step_once()
+    e_f0, e_k0 = slab.energy()
+    slab.reset_stats()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record(tstream)
+    n_steps_particles = 0
+    for _ in range(args.steps):
+        n_steps_particles += slab.particle_count(0)
+        slab.step_once()
+    ev1.record(tstream)
+    barrier()
+    wall_host = time.perf_counter() - t0
+    wall = ev0.elapsed_time(ev1) * 1e-3   # device time, CUDA events on the launching stream
+    clk = clocks.stop()
+    st = slab.stats()
+    e_f1, e_k1 = slab.energy()
+    # max over ranks of the device-event time; particle-steps summed over ranks
+    tt = torch.tensor([wall, float(n_steps_particles)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        tmax = tt.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = tt.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        wall = float(tmax[0])
+        total_psteps = float(tsum[1])
+    else:
+        total_psteps = float(n_steps_particles)
+    value = total_psteps / wall
+    field_rate = nxg * ny * M * args.steps / (st.ms_fields * 1e-3) if st.ms_fields > 0 else None
+
+    # roofline of the dominant kernel (fused push + gather + deposit), per launch
+    peak, peak_kind = measured_peaks()
+    bp = algorithmic_bytes_per_particle_step(M, ppc)
+    roof = None
+    if st.n_push_kernel > 0:
+        dur = st.ms_push_kernel * 1e-3 / st.n_push_kernel
+        per_launch = n_steps_particles / args.steps
+        achieved = bp * per_launch / dur / 1e9
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_kind, "kernel": "k_push (gather+Boris+deposit)",
+                "kernel_ms_per_launch": dur * 1e3, "algorithmic_bytes_per_particle_step": bp,
+                "kernel_particle_steps_per_s": per_launch / dur,
+                "kernel_share_of_step": st.ms_push_kernel / (wall * 1e3)}
+
+    line = {
+        "metric": "particle-steps/sec (push+gather+deposit)", "value": value, "unit": "particle-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl_name, "grid_per_gpu": [nx, ny], "n_mode": M, "ppc": ppc,
+                   "particles_per_gpu": n0, "decomposition": f"{world} x-slabs, periodic ring",
+                   "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2; no flush needed" % (n0 * 56 / 1e9),
+                   "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host},
+        "field_cell_mode_updates_per_s": field_rate,
+        "phase_ms_per_step": {"fields": st.ms_fields / args.steps, "push_total": st.ms_push / args.steps,
+                              "push_kernel": st.ms_push_kernel / args.steps, "bcs_and_exchange": st.ms_bcs / args.steps},
+        "energy": {"field_J": e_f1, "kinetic_J": e_k1,
+                   "relative_drift_over_timed_steps": abs((e_f1 + e_k1) - (e_f0 + e_k0)) / (e_f0 + e_k0)},
+        "roofline": roof, "clocks": clk, "gpu_launches": int(st.kernel_launches),
+    }
+
+    # ---- e2e: host-authoritative round trip through the C-ABI every step ----
+    if not args.no_e2e:
+        names = FIELD_NAMES[:9]
+        host_f = {nm: torch.empty(slab.field_shape, dtype=torch.complex128, pin_memory=True) for nm in names}
+        for nm in names:
+            host_f[nm].numpy()[...] = slab.download_field(nm)
+        import ctypes as C
+        npart = slab.particle_count(0)
+        nn = C.c_int64()
+        slab._ck(slab.L.cylgpu_download_particles(slab.h, 0, hp.shape[0], hp.ctypes.data, C.byref(nn)))
+        e2e_steps = max(1, min(args.steps, 3))
+        h2d = d2h = 0
+        barrier()
+        t0 = time.perf_counter()
+        psteps = 0
+        for _ in range(e2e_steps):
+            npart = int(nn.value)
+            slab._ck(slab.L.cylgpu_upload_particles(slab.h, 0, npart, hp.ctypes.data))
+            for nm in names:
+                slab._ck(slab.L.cylgpu_upload_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
+            h2d = npart * 56 + len(names) * host_f[names[0]].numel() * 16
+            slab.step_once()
+            psteps += npart
+            for nm in names:
+                slab._ck(slab.L.cylgpu_download_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
+            slab._ck(slab.L.cylgpu_download_particles(slab.h, 0, hp.shape[0], hp.ctypes.data, C.byref(nn)))
+            d2h = int(nn.value) * 56 + len(names) * host_f[names[0]].numel() * 16
+        barrier()
+        w2 = time.perf_counter() - t0
+        tt = torch.tensor([w2, float(psteps)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            a = tt.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = tt.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            w2, psteps = float(a[0]), float(b[1])
+        line["e2e"] = {"value": psteps / w2, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
+                       "what": "upload particles + 9 E/B/J mode arrays from pinned host, one full step, download them"}
+
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            cb = cpu_port_rate(wl, max_seconds=20.0, steps=2)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"]["field_cell_mode_updates_per_s"] = cb["field_cell_mode_updates_per_s"]
+        except Exception as e:   # noqa: BLE001
+            line["cpu_baseline"] = {"error": str(e)}
+    slab.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, args.workload, wl)
+    else:
+        run_ours(args, args.workload, wl)
+
+
+if __name__ == "__main__":
+    main()

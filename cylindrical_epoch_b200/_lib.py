@@ -35,7 +35,8 @@ class Stats(C.Structure):
                 ("n_sent_right", C.c_int64), ("n_removed", C.c_int64), ("n_recv", C.c_int64),
                 ("n_window_removed", C.c_int64), ("n_sorts", C.c_int64), ("kernel_launches", C.c_int64),
                 ("ms_fields", C.c_double), ("ms_push", C.c_double), ("ms_bcs", C.c_double),
-                ("ms_sort", C.c_double), ("ms_exchange", C.c_double)]
+                ("ms_sort", C.c_double), ("ms_exchange", C.c_double), ("ms_push_kernel", C.c_double),
+                ("n_push_kernel", C.c_int64)]
 
 
 # every symbol include/cylgpu.h declares: name -> (restype, argtypes)

@@ -76,6 +76,8 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   c->own_stream = true;
   CUDA_TRY(cudaEventCreate(&c->ev0));
   CUDA_TRY(cudaEventCreate(&c->ev1));
+  CUDA_TRY(cudaEventCreate(&c->evk0));
+  CUDA_TRY(cudaEventCreate(&c->evk1));
   const size_t nelem = g.plane * g.M;
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) {
     CUDA_TRY(cudaMalloc(&c->f[k], nelem * sizeof(cplx)));
@@ -121,7 +123,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->cell_count); cudaFree(c->scan_blocks);
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -395,6 +397,8 @@ int cylgpu_reset_stats(cylgpu_handle c) {
   if (!c) return 2;
   c->stats.kernel_launches = 0;
   c->stats.ms_fields = c->stats.ms_push = c->stats.ms_bcs = c->stats.ms_sort = c->stats.ms_exchange = 0.0;
+  c->stats.ms_push_kernel = 0.0;
+  c->stats.n_push_kernel = 0;
   return 0;
 }
 int cylgpu_set_timing(cylgpu_handle c, int on) {

@@ -129,7 +129,7 @@ struct cylgpu_ctx {
   bool sorted_valid = false;
 
   cylgpu_stats_t stats;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timing = true;
 };
 

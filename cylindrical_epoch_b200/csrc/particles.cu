@@ -176,8 +176,19 @@ int do_push(cylgpu_ctx* c) {
     P.q_fac = S.sp.charge * fac;
     P.deposit = S.sp.zero_current ? 0 : 1;
     const int64_t nb = (S.n + 127) / 128;
+    if (c->timing) cudaEventRecord(c->evk0, c->stream);
     k_push_v0<<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n);
     c->stats.kernel_launches += 1;
+    if (c->timing) {
+      // per-launch device time of the fused kernel (the roofline numerator's clock); the
+      // host sync is free here: particle_bcs needs one right after the push anyway
+      cudaEventRecord(c->evk1, c->stream);
+      cudaEventSynchronize(c->evk1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, c->evk0, c->evk1);
+      c->stats.ms_push_kernel += (double)ms;
+      c->stats.n_push_kernel += 1;
+    }
   }
   CUDA_TRY(cudaGetLastError());
   c->pushes_since_sort += 1;

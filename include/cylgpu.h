@@ -111,6 +111,9 @@ typedef struct cylgpu_stats_t {
   int64_t kernel_launches;                   /* kernels launched since create/reset */
   /* device time (ms, CUDA events on the library stream) accumulated since reset */
   double ms_fields, ms_push, ms_bcs, ms_sort, ms_exchange;
+  /* the fused push+gather+deposit kernel(s) alone, and how many times it was launched */
+  double ms_push_kernel;
+  int64_t n_push_kernel;
 } cylgpu_stats_t;
 
 const char* cylgpu_last_error(void);

@@ -29,7 +29,7 @@ def test_struct_layouts_match_header(cylgpu_lib):
     from cylindrical_epoch_b200 import _lib
     # sizes follow from the field lists in the header (LP64)
     assert ctypes.sizeof(_lib.SpeciesC) == 16 + 16 + 8
-    assert ctypes.sizeof(_lib.Stats) == 8 * (8 + 7) + 8 * 5
+    assert ctypes.sizeof(_lib.Stats) == 8 * (8 + 7) + 8 * 5 + 16
     assert ctypes.sizeof(_lib.Config) == 4 * 16 + 8 * 10 + 8 * 5
 
 

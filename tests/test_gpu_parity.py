@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import decks
-from parity import Pair, TOL, by_weight
+from parity import Pair, TOL, TOL_HOT, by_weight
 from cylindrical_epoch_b200.constants import FIELD_NAMES
 
 pytestmark = pytest.mark.gpu
@@ -58,8 +58,8 @@ def test_thermal_periodic_reflect(variant):
         for _ in range(3):
             p.step(5)
             p.check_counts()
-            p.check_fields()
-            p.check_particles()
+            p.check_fields(TOL_HOT)
+            p.check_particles(TOL_HOT)
         assert p.slabs[0].particle_count(0) == n0   # periodic + reflect conserve particles
         p.check_cells()
     finally:
@@ -72,8 +72,8 @@ def test_drift_reflecting_box_three_modes():
     try:
         p.step(12)
         p.check_counts()
-        p.check_fields()
-        p.check_particles()
+        p.check_fields(TOL_HOT)
+        p.check_particles(TOL_HOT)
         p.check_cells()
     finally:
         p.close()
@@ -97,7 +97,7 @@ def test_push_only_currents():
     try:
         p.oracle.call("push_no_bcs")
         p.slabs[0].push_particles_no_bcs()
-        errs = p.check_fields(1e-11, ["jxm", "jrm", "jtm"])
+        errs = p.check_fields(TOL_HOT, ["jxm", "jrm", "jtm"])
         p.check_particles(1e-13)
         print(errs)
     finally:
@@ -128,12 +128,13 @@ def test_two_ranks_fabric(deckname):
     field halos, additive J ghosts, particle migration counts"""
     d = decks.lwfa(nx=96, ny=24, n_mode=2, ppc_e=4) if deckname == "lwfa" else decks.thermal(nx=64, ny=24, ppc=6)
     p = Pair(d, nranks=2)
+    tol = TOL if deckname == "lwfa" else TOL_HOT
     try:
         for _ in range(3):
             p.step(6)
             p.check_counts()
-            p.check_fields()
-            p.check_particles()
+            p.check_fields(tol)
+            p.check_particles(tol)
     finally:
         p.close()
 
