@@ -244,7 +244,8 @@ def run_ours(args, wl_name, wl):
     nx, ny, M, ppc = wl["nx"], wl["ny"], wl["n_mode"], wl["ppc"]
     nxg = nx * world
     bcp = (BC_PERIODIC, BC_PERIODIC, BC_OPEN, BC_REFLECT)
-    species = [ce.Species(-Q0, M0, bcp, False, False, ppc, DENSITY, (TEMP_K,) * 3)]
+    species = [ce.Species(-Q0, M0, bcp, False, bool(int(os.environ.get('BENCH_ZERO_CURRENT', '0'))), ppc, DENSITY,
+                          (TEMP_K,) * 3)]
     slab = ce.Slab(nxg, ny, M, 0.0, nxg * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], species,
                    rank=rank, nranks=world, transport=TRANSPORT_NCCL if world > 1 else TRANSPORT_NONE,
                    device=local, nccl_unique_id=uid)
@@ -261,6 +262,10 @@ def run_ours(args, wl_name, wl):
     slab.set_stream(tstream.cuda_stream)
     slab.init_half_step()
     slab.L.cylgpu_set_timing(slab.h, 1)
+    if "BENCH_VARIANT" in os.environ:
+        slab.set_push_variant(int(os.environ["BENCH_VARIANT"]))
+    if "BENCH_SORT_INTERVAL" in os.environ:
+        slab.set_sort_interval(int(os.environ["BENCH_SORT_INTERVAL"]))
 
     def barrier():
         slab.synchronize()

@@ -126,6 +126,265 @@ __global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict
   if (P.deposit) deposit_global(P, D);
 }
 
+// ------------------------------------------------------------------------------------------
+// variant 1: warp-window deposit.
+//
+// FP64 atomics are the bottleneck of variant 0: ~144 RED.F64 per particle at ~1 RED per
+// clock per SM (measured: 8.1 of 9.9 ms).  Shared-memory FP atomics are CAS loops on
+// sm_100a (ATOMS.CAST.SPIN) and slower still, so the reduction is done in REGISTERS:
+// particles are sorted by the staggered cell (cell_x2, cell_y2) of their upcoming
+// half-step position, so the 32 lanes of a warp deposit into (nearly) the same 5-row x
+// WX-column window of nodes.  Per (row, mode) every lane evaluates its contribution to each
+// window slot (zero outside its own 5-point footprint), the warp runs a shuffle
+// reduce-scatter (31 exchanges per 32 values, after which lane j holds the warp total of
+// value j) and each lane issues ONE RED per 32 values: ~10 REDs per particle instead of
+// 144.  Lanes whose footprint does not fit the warp window (sort drift, row ends) fall back
+// to per-particle REDs, so correctness never depends on the sort.
+// ------------------------------------------------------------------------------------------
+#define WX 7   // window width in x: 5-point footprint + up to 2 cells of base shift
+
+// reduce-scatter over the warp: on return lane j holds sum over lanes of v[j] in v[0]
+__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool hi = lane & 16;
+    const double send = hi ? v[i] : v[i + 16];
+    const double keep = hi ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool hi = lane & 8;
+    const double send = hi ? v[i] : v[i + 8];
+    const double keep = hi ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool hi = lane & 4;
+    const double send = hi ? v[i] : v[i + 4];
+    const double keep = hi ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool hi = lane & 2;
+    const double send = hi ? v[i] : v[i + 2];
+    const double keep = hi ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool hi = lane & 1;
+    const double send = hi ? v[0] : v[1];
+    const double keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
+
+// Value stream of one window row: element e of
+//   [m=0: jx(WX) jr(WX) jt(WX) real] [m=1: jx(WX re,im) jr(...) jt(...)] [m=2: ...] ...
+// decoded to (mode, comp, slot, reim); returns false for padding
+__device__ __forceinline__ bool decode_row_element(int e, int M, int& im, int& comp, int& slot, int& reim) {
+  if (e < 3 * WX) { im = 0; comp = e / WX; slot = e % WX; reim = 0; return true; }
+  const int q = e - 3 * WX;
+  im = 1 + q / (6 * WX);
+  if (im >= M) return false;
+  const int r = q % (6 * WX);
+  comp = r / (2 * WX);
+  slot = (r % (2 * WX)) >> 1;
+  reim = r & 1;
+  return true;
+}
+
+template <int M>
+struct RowStream {   // compile-time fill position of the 32-value chunk buffer
+  static constexpr int V = 3 * WX + 6 * WX * (M - 1);
+  static constexpr int NCHUNK = (V + 31) / 32;
+};
+
+template <int M>
+__device__ __forceinline__ void deposit_window(const PushConst& P, const DepositIn& D, bool active, int lane,
+                                               int base_x, int base_y, int sx) {
+  const Geom& g = P.g;
+  const double third = 1.0 / 3.0;
+  const double* inv_area_rt = P.tab + JNG;
+  const double* inv_area_xt = P.tab + P.ntab + JNG;
+  const double* inv_volume = P.tab + 2 * P.ntab + JNG;
+  const double* ratio_area_xt = P.tab + 3 * P.ntab + JNG;
+
+  // x factors in the window frame (slot s <-> cx = base_x - 2 + s); zero outside the footprint
+  double gxw[WX], hxw[WX], Hxw[WX];
+  const int slo = sx + D.xmin + 2, shi = sx + D.xmax + 2;
+#pragma unroll
+  for (int s = 0; s < WX; ++s) {
+    double gv = 0.0, hv = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      if (s - k >= 0 && s - k <= WX - 5) {   // compile-time feasible shifts only
+        const bool sel = (sx == s - k);
+        gv = sel ? D.gx[k] : gv;
+        hv = sel ? D.hx[k] : hv;
+      }
+    }
+    const bool in = active && s >= slo && s <= shi;
+    gxw[s] = in ? gv : 0.0;
+    hxw[s] = in ? hv : 0.0;
+  }
+  {
+    double run = 0.0;
+#pragma unroll
+    for (int s = 0; s < WX; ++s) {
+      run = run + hxw[s];
+      Hxw[s] = (active && s >= slo && s <= shi) ? run : 0.0;
+    }
+  }
+  const double fcx = active ? D.fcx : 0.0;
+  const double fcz = active ? D.fcz : 0.0;
+
+  // mode factors for every m > 0 (registers: 6 doubles per mode)
+  cplx f2[M > 1 ? M - 1 : 1], f3[M > 1 ? M - 1 : 1], f4[M > 1 ? M - 1 : 1];
+  {
+    cplx e0 = C(1.0, 0.0), ed = C(1.0, 0.0);
+#pragma unroll
+    for (int im = 1; im < M; ++im) {
+      e0 = e0 * D.exp_itheta_05;
+      ed = ed * D.exp_idtheta;
+      const ModeFac mf = mode_factors(im, D.dtheta, e0, ed);
+      f2[im - 1] = mf.f2; f3[im - 1] = mf.f3; f4[im - 1] = mf.f4;
+    }
+  }
+  // running radial prefix jyh per (mode, slot)
+  cplx jyh[M][WX];
+#pragma unroll
+  for (int im = 0; im < M; ++im)
+#pragma unroll
+    for (int s = 0; s < WX; ++s) jyh[im][s] = C(0.0, 0.0);
+
+#pragma unroll 1
+  for (int ky = 0; ky < 5; ++ky) {
+    const int iy = ky - 2;
+    const int cy = base_y + iy;
+    const bool row_on = active && iy >= D.ymin && iy <= D.ymax;
+    if (!__any_sync(0xffffffffu, row_on)) continue;
+    // dynamic ky indexing of the 5-vectors through selects (keeps them in registers)
+    double gyk = 0.0, hyk = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      gyk = (k == ky) ? D.gy[k] : gyk;
+      hyk = (k == ky) ? D.hy[k] : hyk;
+    }
+    if (!row_on) { gyk = 0.0; hyk = 0.0; }
+    const double iart = __ldg(&inv_area_rt[cy]), iaxt = __ldg(&inv_area_xt[cy]);
+    const double ivol = __ldg(&inv_volume[cy]), ratio = __ldg(&ratio_area_xt[cy]);
+    const double fjx = fcx * iart;
+    const double fjy = fcx * hyk * iaxt;
+    const double fjz = fcz * ivol;
+
+    double v[32];
+    int fill = 0;      // compile-time after unrolling
+    int chunk = 0;
+    auto flush = [&](int nvalid) {
+      const double tot = warp_reduce_scatter32(v, lane);
+      const int e = chunk * 32 + lane;
+      int im, comp, slot, reim;
+      if (lane < nvalid && tot != 0.0 && decode_row_element(e, M, im, comp, slot, reim)) {
+        const int cx = base_x - 2 + slot;
+        size_t o = g.at(cx, cy, im);
+        double* arr = (comp == 0) ? P.jx : (comp == 1) ? P.jr : P.jt;
+        o += (comp == 0) ? 1 : (comp == 1) ? (size_t)g.SX : 0;
+        atomicAdd(arr + 2 * o + reim, tot);
+      }
+      chunk += 1;
+    };
+#define PUSH_VALUE(val)                      \
+    do {                                     \
+      v[fill] = (val);                       \
+      fill += 1;                             \
+      if (fill == 32) { flush(32); fill = 0; } \
+    } while (0)
+
+    // ---- m = 0 (all real) ----
+    {
+      const double w_rt = gyk + 0.5 * hyk;
+      const double ym1 = 0.5 * gyk + third * hyk;
+#pragma unroll
+      for (int s = 0; s < WX; ++s) PUSH_VALUE(-(fjx * Hxw[s]) * w_rt);
+#pragma unroll
+      for (int s = 0; s < WX; ++s) {
+        const double w_xt = gxw[s] + 0.5 * hxw[s];
+        const double nv = row_on ? (jyh[0][s].x * ratio - fjy * w_xt) : jyh[0][s].x;
+        jyh[0][s].x = nv;
+        PUSH_VALUE((row_on && s >= slo && s <= shi) ? nv : 0.0);
+      }
+#pragma unroll
+      for (int s = 0; s < WX; ++s) PUSH_VALUE(fjz * (gxw[s] * w_rt + hxw[s] * ym1));
+    }
+    // ---- m > 0 ----
+#pragma unroll
+    for (int im = 1; im < M; ++im) {
+      const cplx w_rt = f2[im - 1] * gyk + f3[im - 1] * hyk;
+      const cplx ym1 = f3[im - 1] * gyk + f4[im - 1] * hyk;
+#pragma unroll
+      for (int s = 0; s < WX; ++s) {
+        const double a = -(fjx * Hxw[s]);
+        PUSH_VALUE(a * w_rt.x);
+        PUSH_VALUE(a * w_rt.y);
+      }
+#pragma unroll
+      for (int s = 0; s < WX; ++s) {
+        const cplx w_xt = f2[im - 1] * gxw[s] + f3[im - 1] * hxw[s];
+        cplx nv = jyh[im][s];
+        if (row_on) nv = nv * ratio - fjy * w_xt;
+        jyh[im][s] = nv;
+        const bool on = row_on && s >= slo && s <= shi;
+        PUSH_VALUE(on ? nv.x : 0.0);
+        PUSH_VALUE(on ? nv.y : 0.0);
+      }
+#pragma unroll
+      for (int s = 0; s < WX; ++s) {
+        const cplx w_xr = gxw[s] * w_rt + hxw[s] * ym1;
+        PUSH_VALUE(fjz * w_xr.x);
+        PUSH_VALUE(fjz * w_xr.y);
+      }
+    }
+    if (fill > 0) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (k >= fill) v[k] = 0.0;
+      flush(fill);
+    }
+#undef PUSH_VALUE
+  }
+}
+
+template <int M>
+__global__ void __launch_bounds__(128) k_push_v1(PushConst P, double* __restrict__ x, double* __restrict__ y,
+                                                 double* __restrict__ z, double* __restrict__ px,
+                                                 double* __restrict__ py, double* __restrict__ pz,
+                                                 const double* __restrict__ w, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < n;
+  DepositIn D;
+  D.cell_x2 = 0x3fffffff; D.cell_y2 = 0x3fffffff;
+  if (valid) {
+    double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
+    const double W = w[i];
+    push_one(P, X, Y, Z, PX, PY, PZ, W, D);
+    x[i] = X; y[i] = Y; z[i] = Z;
+    px[i] = PX; py[i] = PY; pz[i] = PZ;
+  }
+  if (!P.deposit) return;
+  const int base_x = __reduce_min_sync(0xffffffffu, D.cell_x2);
+  const int base_y = __reduce_min_sync(0xffffffffu, D.cell_y2);
+  if (base_x == 0x3fffffff) return;   // whole warp beyond n
+  const int sx = D.cell_x2 - base_x;
+  const bool inwin = valid && sx <= WX - 5 && D.cell_y2 == base_y;
+  if (valid && !inwin) deposit_global(P, D);
+  deposit_window<M>(P, D, inwin, lane, base_x, base_y, inwin ? sx : 0);
+}
+
 __global__ void __launch_bounds__(256) k_copy_zero(cplx* __restrict__ old0, cplx* __restrict__ old1,
                                                    cplx* __restrict__ old2, cplx* __restrict__ j0,
                                                    cplx* __restrict__ j1, cplx* __restrict__ j2, size_t n) {
@@ -177,7 +436,20 @@ int do_push(cylgpu_ctx* c) {
     P.deposit = S.sp.zero_current ? 0 : 1;
     const int64_t nb = (S.n + 127) / 128;
     if (c->timing) cudaEventRecord(c->evk0, c->stream);
-    k_push_v0<<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n);
+#define LAUNCH_V1(MM) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n)
+    if (c->push_variant == 1 && g.M >= 1 && g.M <= 6) {
+      switch (g.M) {
+        case 1: LAUNCH_V1(1); break;
+        case 2: LAUNCH_V1(2); break;
+        case 3: LAUNCH_V1(3); break;
+        case 4: LAUNCH_V1(4); break;
+        case 5: LAUNCH_V1(5); break;
+        default: LAUNCH_V1(6); break;
+      }
+    } else {
+      k_push_v0<<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n);
+    }
+#undef LAUNCH_V1
     c->stats.kernel_launches += 1;
     if (c->timing) {
       // per-launch device time of the fused kernel (the roofline numerator's clock); the
@@ -535,12 +807,31 @@ int do_remove_behind(cylgpu_ctx* c) {
 struct SortGeom {
   int ncx, ncy;   // nx + 2*CELL_PAD, ny + 2*CELL_PAD
   double x_grid_min_local, y_grid_min_local, dx, dy;
+  // prediction of the upcoming half-step position (particles.F90:303-309)
+  double ipart_mc, dtco2, idx, idy;
 };
 
 __device__ __forceinline__ void ref_cell(const SortGeom& G, double x, double y, double z, int& cx, int& cy) {
   const double r = sqrt(y * y + z * z);
   cx = (int)floor((x - G.x_grid_min_local) / G.dx + 1.5);
   cy = (int)floor((r - G.y_grid_min_local) / G.dy + 1.5);
+}
+
+// The sort bucket is the STAGGERED cell (cell_x2, cell_y2) the particle will have after the
+// half-step drift of the next push (particles.F90:303-309,369-374): every particle of a
+// bucket gathers from the same field nodes and deposits into the same 5x5 node window,
+// which is what the warp-window deposit needs.  Same arithmetic as push_one(); a rare
+// last-bit disagreement only costs the fallback path, never correctness.
+__device__ __forceinline__ void stag_cell(const SortGeom& G, double x, double y, double z, double px, double py,
+                                          double pz, int& cx2, int& cy2) {
+  const double ux = px * G.ipart_mc, uy = py * G.ipart_mc, uz = pz * G.ipart_mc;
+  const double root = G.dtco2 / sqrt(ux * ux + uy * uy + uz * uz + 1.0);
+  x = x + ux * root;
+  y = y + uy * root;
+  z = z + uz * root;
+  const double r = sqrt(y * y + z * z);
+  cx2 = (int)floor((x - G.x_grid_min_local) * G.idx) + 1;
+  cy2 = (int)floor((r - G.y_grid_min_local) * G.idy) + 1;
 }
 
 __device__ __forceinline__ int cell_key(const SortGeom& G, int cx, int cy) {
@@ -552,12 +843,14 @@ __device__ __forceinline__ int cell_key(const SortGeom& G, int cx, int cy) {
 
 __global__ void __launch_bounds__(256) k_sort_hist(SortGeom G, const double* __restrict__ x,
                                                    const double* __restrict__ y, const double* __restrict__ z,
-                                                   int* __restrict__ count, uint32_t* __restrict__ key,
-                                                   uint32_t* __restrict__ rank, int64_t n) {
+                                                   const double* __restrict__ px, const double* __restrict__ py,
+                                                   const double* __restrict__ pz, int* __restrict__ count,
+                                                   uint32_t* __restrict__ key, uint32_t* __restrict__ rank,
+                                                   int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int cx, cy;
-  ref_cell(G, x[i], y[i], z[i], cx, cy);
+  stag_cell(G, x[i], y[i], z[i], px[i], py[i], pz[i], cx, cy);
   const int k = cell_key(G, cx, cy);
   key[i] = (uint32_t)k;
   rank[i] = (uint32_t)atomicAdd(&count[k], 1);
@@ -631,6 +924,7 @@ int do_sort(cylgpu_ctx* c) {
   G.x_grid_min_local = c->x_grid_min_local;
   G.y_grid_min_local = c->cfg.y_grid_min_local;
   G.dx = c->cfg.dx; G.dy = c->cfg.dy;
+  G.idx = 1.0 / c->cfg.dx; G.idy = 1.0 / c->cfg.dy;
   const int64_t ncell = (int64_t)G.ncx * G.ncy;
   const int nb = (int)((ncell + SCAN_B - 1) / SCAN_B);
   if (!c->cell_count || c->ncell != ncell) {
@@ -648,7 +942,10 @@ int do_sort(cylgpu_ctx* c) {
     uint32_t* key = c->hole_list;   // scratch reuse: hole_list is idle during a sort
     uint32_t* dest = c->perm;
     CUDA_TRY(cudaMemsetAsync(c->cell_count, 0, (size_t)(ncell + 1) * sizeof(int), c->stream));
-    k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], c->cell_count, key, dest, S.n);
+    G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
+    G.dtco2 = C_LIGHT * (c->dt / 2.0);
+    k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                      c->cell_count, key, dest, S.n);
     k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
     k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
     k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
