@@ -14,7 +14,7 @@ HEADERS = ["ctx.cuh", "push.cuh", os.path.join("..", "..", "include", "cylgpu.h"
 LIB = os.path.join(HERE, "libcylgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("CYLGPU_DEFS", "").split()
 
 
 def _stale(target, deps):

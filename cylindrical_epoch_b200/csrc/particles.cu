@@ -142,6 +142,9 @@ __global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict
 // to per-particle REDs, so correctness never depends on the sort.
 // ------------------------------------------------------------------------------------------
 #define WX 7   // window width in x: 5-point footprint + up to 2 cells of base shift
+#ifndef PUSH_MINB
+#define PUSH_MINB 3   // CTAs of 128 threads per SM the push kernel is compiled for (168 registers)
+#endif
 
 // reduce-scatter over the warp: on return lane j holds sum over lanes of v[j] in v[0]
 __device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
@@ -359,7 +362,7 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
 }
 
 template <int M>
-__global__ void __launch_bounds__(128) k_push_v1(PushConst P, double* __restrict__ x, double* __restrict__ y,
+__global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double* __restrict__ x, double* __restrict__ y,
                                                  double* __restrict__ z, double* __restrict__ px,
                                                  double* __restrict__ py, double* __restrict__ pz,
                                                  const double* __restrict__ w, int64_t n) {
