@@ -162,3 +162,37 @@ def test_energy_diagnostic_thermal():
         assert drift < 5e-2
     finally:
         p.close()
+
+
+def test_against_committed_golden_vectors():
+    """CUDA path vs tests/golden/lwfa_48x16_m2_20steps.npz (made by tests/golden/make_golden.py):
+    no oracle call at run time"""
+    import os
+    from golden.make_golden import deck, NSTEPS
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lwfa_48x16_m2_20steps.npz"))
+    d = deck()
+    s = decks.make_slab(d)
+    try:
+        for isp in range(2):
+            s.upload_particles(isp, ref[f"init_particles_{isp}"])
+        s.init_half_step()
+        for _ in range(NSTEPS):
+            s.step_once()
+        qnc = sum(abs(sp.charge) * sp.density for sp in d.species) * 2.99792458e8
+        for name in ("exm", "erm", "etm", "bxm", "brm", "btm", "jxm", "jrm", "jtm"):
+            a = ref[name]
+            den = np.abs(a).max()
+            if name.startswith("j"):
+                den = max(den, 1e-3 * qnc)
+            err = np.abs(s.download_field(name) - a).max() / den
+            assert err <= TOL, (name, err)
+        for isp in range(2):
+            got = by_weight(s.download_particles(isp))
+            a = ref[f"particles_{isp}"]
+            assert got.shape == a.shape
+            assert np.array_equal(got[:, 6], a[:, 6])
+            for cols in ((0, 1, 2), (3, 4, 5)):
+                assert np.abs(got[:, cols] - a[:, cols]).max() <= TOL * np.abs(a[:, cols]).max()
+        assert [s.particle_count(0), s.particle_count(1)] == list(ref["counts"][:2])
+    finally:
+        s.close()
