@@ -1,0 +1,22 @@
+"""Multi-GPU parity (needs >= 2 GPUs on the box; skipped otherwise): one process per GPU under
+torch.distributed.run, the library's NCCL transport and the torch.distributed CALLBACK transport
+against the oracle with the same x-slab decomposition."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.mark.parametrize("mode", ["nccl", "callback"])
+def test_two_gpu_parity(mode, cylgpu_lib):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "nccl_parity_worker.py"), mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert "NCCL_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
