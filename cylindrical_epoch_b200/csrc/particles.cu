@@ -143,49 +143,33 @@ __global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict
 // ------------------------------------------------------------------------------------------
 #define WX 7   // window width in x: 5-point footprint + up to 2 cells of base shift
 #ifndef PUSH_MINB
-#define PUSH_MINB 3   // CTAs of 128 threads per SM the push kernel is compiled for (168 registers)
+#define PUSH_MINB 4   // CTAs of 128 threads per SM the push kernel is compiled for (128 registers)
 #endif
 
-// reduce-scatter over the warp: on return lane j holds sum over lanes of v[j] in v[0]
-__device__ __forceinline__ double warp_reduce_scatter32(double (&v)[32], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool hi = lane & 16;
-    const double send = hi ? v[i] : v[i + 16];
-    const double keep = hi ? v[i + 16] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool hi = lane & 8;
-    const double send = hi ? v[i] : v[i + 8];
-    const double keep = hi ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool hi = lane & 4;
-    const double send = hi ? v[i] : v[i + 4];
-    const double keep = hi ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool hi = lane & 2;
-    const double send = hi ? v[i] : v[i + 2];
-    const double keep = hi ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    const bool hi = lane & 1;
-    const double send = hi ? v[0] : v[1];
-    const double keep = hi ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  return v[0];
+// One exchange of the reduce-scatter: lanes with bit `bit` set keep `b`, the others keep `a`;
+// each sends the one it does not keep to its partner and adds what it receives.
+__device__ __forceinline__ double rs_exchange(double a, double b, bool hi, int bit) {
+  const double send = hi ? a : b;
+  const double keep = hi ? b : a;
+  return keep + __shfl_xor_sync(0xffffffffu, send, bit);
 }
 
-// Value stream of one window row: element e of
+// Levels 2..5 of the 64-value reduce-scatter on the 32 level-1 results.  On return w[0], w[1]
+// hold the warp totals of stream positions  p_i = i + 2 b0 + 4 b1 + 8 b2 + 16 b3 + 32 b4
+// (b_k = bit k of the lane id), i = 0, 1.
+__device__ __forceinline__ void warp_reduce_scatter_tail(double (&w)[32], int lane) {
+  const bool h8 = lane & 8, h4 = lane & 4, h2 = lane & 2, h1 = lane & 1;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) w[i] = rs_exchange(w[i], w[i + 16], h8, 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = rs_exchange(w[i], w[i + 8], h4, 4);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) w[i] = rs_exchange(w[i], w[i + 4], h2, 2);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) w[i] = rs_exchange(w[i], w[i + 2], h1, 1);
+}
+
+// Value stream of one window row, in generation order g:
 //   [m=0: jx(WX) jr(WX) jt(WX) real] [m=1: jx(WX re,im) jr(...) jt(...)] [m=2: ...] ...
 // decoded to (mode, comp, slot, reim); returns false for padding
 __device__ __forceinline__ bool decode_row_element(int e, int M, int& im, int& comp, int& slot, int& reim) {
@@ -201,12 +185,6 @@ __device__ __forceinline__ bool decode_row_element(int e, int M, int& im, int& c
 }
 
 template <int M>
-struct RowStream {   // compile-time fill position of the 32-value chunk buffer
-  static constexpr int V = 3 * WX + 6 * WX * (M - 1);
-  static constexpr int NCHUNK = (V + 31) / 32;
-};
-
-template <int M>
 __device__ __forceinline__ void deposit_window(const PushConst& P, const DepositIn& D, bool active, int lane,
                                                int base_x, int base_y, int sx) {
   const Geom& g = P.g;
@@ -217,7 +195,7 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
   const double* ratio_area_xt = P.tab + 3 * P.ntab + JNG;
 
   // x factors in the window frame (slot s <-> cx = base_x - 2 + s); zero outside the footprint
-  double gxw[WX], hxw[WX], Hxw[WX];
+  double gxw[WX], hxw[WX];
   const int slo = sx + D.xmin + 2, shi = sx + D.xmax + 2;
 #pragma unroll
   for (int s = 0; s < WX; ++s) {
@@ -234,18 +212,10 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
     gxw[s] = in ? gv : 0.0;
     hxw[s] = in ? hv : 0.0;
   }
-  {
-    double run = 0.0;
-#pragma unroll
-    for (int s = 0; s < WX; ++s) {
-      run = run + hxw[s];
-      Hxw[s] = (active && s >= slo && s <= shi) ? run : 0.0;
-    }
-  }
   const double fcx = active ? D.fcx : 0.0;
   const double fcz = active ? D.fcz : 0.0;
 
-  // mode factors for every m > 0 (registers: 6 doubles per mode)
+  // mode factors for every m > 0 (6 doubles per mode)
   cplx f2[M > 1 ? M - 1 : 1], f3[M > 1 ? M - 1 : 1], f4[M > 1 ? M - 1 : 1];
   {
     cplx e0 = C(1.0, 0.0), ed = C(1.0, 0.0);
@@ -257,12 +227,12 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
       f2[im - 1] = mf.f2; f3[im - 1] = mf.f3; f4[im - 1] = mf.f4;
     }
   }
-  // running radial prefix jyh per (mode, slot)
-  cplx jyh[M][WX];
-#pragma unroll
-  for (int im = 0; im < M; ++im)
-#pragma unroll
-    for (int s = 0; s < WX; ++s) jyh[im][s] = C(0.0, 0.0);
+  // The radial prefix of particles.F90:658, jyh(ix) = jyh(ix)*ratio - fjy*w_xt(ix), is separable:
+  // jyh(ix) = -w_xt(ix) * S with the real, mode-independent recurrence S = S*ratio + fjy.
+  double S = 0.0;
+  const bool h16 = lane & 16;
+  const int b0 = lane & 1, b1 = (lane >> 1) & 1, b2 = (lane >> 2) & 1, b3 = (lane >> 3) & 1, b4 = (lane >> 4) & 1;
+  const int pos0 = 2 * b0 + 4 * b1 + 8 * b2 + 16 * b3 + 32 * b4;
 
 #pragma unroll 1
   for (int ky = 0; ky < 5; ++ky) {
@@ -280,82 +250,99 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
     if (!row_on) { gyk = 0.0; hyk = 0.0; }
     const double iart = __ldg(&inv_area_rt[cy]), iaxt = __ldg(&inv_area_xt[cy]);
     const double ivol = __ldg(&inv_volume[cy]), ratio = __ldg(&ratio_area_xt[cy]);
-    const double fjx = fcx * iart;
-    const double fjy = fcx * hyk * iaxt;
-    const double fjz = fcz * ivol;
+    const double fjx = row_on ? fcx * iart : 0.0;
+    const double fjz = row_on ? fcz * ivol : 0.0;
+    if (row_on) S = S * ratio + (fcx * hyk) * iaxt;
+    const double Srow = row_on ? S : 0.0;
 
-    double v[32];
-    int fill = 0;      // compile-time after unrolling
+    // 64-value super-chunks: values are generated in pairs (stream positions i and i + 32), the
+    // level-1 exchange is done as soon as a pair exists, so only 32 partial sums are ever live
+    double w[32];
+    double pend = 0.0;
+    int gen = 0;       // compile-time after unrolling
     int chunk = 0;
-    auto flush = [&](int nvalid) {
-      const double tot = warp_reduce_scatter32(v, lane);
-      const int e = chunk * 32 + lane;
-      int im, comp, slot, reim;
-      if (lane < nvalid && tot != 0.0 && decode_row_element(e, M, im, comp, slot, reim)) {
-        const int cx = base_x - 2 + slot;
-        size_t o = g.at(cx, cy, im);
-        double* arr = (comp == 0) ? P.jx : (comp == 1) ? P.jr : P.jt;
-        o += (comp == 0) ? 1 : (comp == 1) ? (size_t)g.SX : 0;
-        atomicAdd(arr + 2 * o + reim, tot);
+    auto flush = [&]() {
+      warp_reduce_scatter_tail(w, lane);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int p = pos0 + i;
+        const int gidx = (p < 32) ? 2 * p : 2 * (p - 32) + 1;
+        const int e = chunk * 64 + gidx;
+        int im, comp, slot, reim;
+        if (w[i] != 0.0 && decode_row_element(e, M, im, comp, slot, reim)) {
+          const int cx = base_x - 2 + slot;
+          size_t o = g.at(cx, cy, im);
+          double* arr = (comp == 0) ? P.jx : (comp == 1) ? P.jr : P.jt;
+          o += (comp == 0) ? 1 : (comp == 1) ? (size_t)g.SX : 0;
+          atomicAdd(arr + 2 * o + reim, w[i]);
+        }
       }
       chunk += 1;
     };
-#define PUSH_VALUE(val)                      \
-    do {                                     \
-      v[fill] = (val);                       \
-      fill += 1;                             \
-      if (fill == 32) { flush(32); fill = 0; } \
+#define PUSH_VALUE(val)                                            \
+    do {                                                           \
+      if ((gen & 1) == 0) {                                        \
+        pend = (val);                                              \
+      } else {                                                     \
+        w[gen >> 1] = rs_exchange(pend, (val), h16, 16);           \
+      }                                                            \
+      gen += 1;                                                    \
+      if (gen == 64) { flush(); gen = 0; }                         \
     } while (0)
 
     // ---- m = 0 (all real) ----
     {
       const double w_rt = gyk + 0.5 * hyk;
       const double ym1 = 0.5 * gyk + third * hyk;
-#pragma unroll
-      for (int s = 0; s < WX; ++s) PUSH_VALUE(-(fjx * Hxw[s]) * w_rt);
+      const double a = -(fjx * w_rt);
+      double run = 0.0;
 #pragma unroll
       for (int s = 0; s < WX; ++s) {
-        const double w_xt = gxw[s] + 0.5 * hxw[s];
-        const double nv = row_on ? (jyh[0][s].x * ratio - fjy * w_xt) : jyh[0][s].x;
-        jyh[0][s].x = nv;
-        PUSH_VALUE((row_on && s >= slo && s <= shi) ? nv : 0.0);
+        run = run + hxw[s];
+        PUSH_VALUE((s <= shi) ? a * run : 0.0);
       }
 #pragma unroll
-      for (int s = 0; s < WX; ++s) PUSH_VALUE(fjz * (gxw[s] * w_rt + hxw[s] * ym1));
+      for (int s = 0; s < WX; ++s) PUSH_VALUE(-(Srow * (gxw[s] + 0.5 * hxw[s])));
+      const double bz = fjz * w_rt, cz = fjz * ym1;
+#pragma unroll
+      for (int s = 0; s < WX; ++s) PUSH_VALUE(gxw[s] * bz + hxw[s] * cz);
     }
     // ---- m > 0 ----
 #pragma unroll
     for (int im = 1; im < M; ++im) {
       const cplx w_rt = f2[im - 1] * gyk + f3[im - 1] * hyk;
       const cplx ym1 = f3[im - 1] * gyk + f4[im - 1] * hyk;
+      const cplx a = (-fjx) * w_rt;
+      double run = 0.0;
 #pragma unroll
       for (int s = 0; s < WX; ++s) {
-        const double a = -(fjx * Hxw[s]);
-        PUSH_VALUE(a * w_rt.x);
-        PUSH_VALUE(a * w_rt.y);
+        run = run + hxw[s];
+        const double rr = (s <= shi) ? run : 0.0;
+        PUSH_VALUE(a.x * rr);
+        PUSH_VALUE(a.y * rr);
       }
+      const cplx sf2 = (-Srow) * f2[im - 1], sf3 = (-Srow) * f3[im - 1];
 #pragma unroll
       for (int s = 0; s < WX; ++s) {
-        const cplx w_xt = f2[im - 1] * gxw[s] + f3[im - 1] * hxw[s];
-        cplx nv = jyh[im][s];
-        if (row_on) nv = nv * ratio - fjy * w_xt;
-        jyh[im][s] = nv;
-        const bool on = row_on && s >= slo && s <= shi;
-        PUSH_VALUE(on ? nv.x : 0.0);
-        PUSH_VALUE(on ? nv.y : 0.0);
+        PUSH_VALUE(sf2.x * gxw[s] + sf3.x * hxw[s]);
+        PUSH_VALUE(sf2.y * gxw[s] + sf3.y * hxw[s]);
       }
+      const cplx bz = fjz * w_rt, cz = fjz * ym1;
 #pragma unroll
       for (int s = 0; s < WX; ++s) {
-        const cplx w_xr = gxw[s] * w_rt + hxw[s] * ym1;
-        PUSH_VALUE(fjz * w_xr.x);
-        PUSH_VALUE(fjz * w_xr.y);
+        PUSH_VALUE(gxw[s] * bz.x + hxw[s] * cz.x);
+        PUSH_VALUE(gxw[s] * bz.y + hxw[s] * cz.y);
       }
     }
-    if (fill > 0) {
+    if (gen > 0) {
+      // pad the last super-chunk with zeros
 #pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (k >= fill) v[k] = 0.0;
-      flush(fill);
+      for (int k = 0; k < 64; ++k)
+        if (k >= gen) {
+          if ((k & 1) == 0) pend = 0.0;
+          else w[k >> 1] = (k == gen) ? rs_exchange(pend, 0.0, h16, 16) : 0.0;
+        }
+      flush();
     }
 #undef PUSH_VALUE
   }
