@@ -118,9 +118,12 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->tables); cudaFree(c->src);
   cudaFree(c->sbuf_l); cudaFree(c->sbuf_r); cudaFree(c->rbuf_l); cudaFree(c->rbuf_r);
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i)
+{
     for (int q = 0; q < 7; ++q) cudaFree(c->species[i].d[q]);
+    cudaFree(c->species[i].cell_start);
+  }
   cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->hole_list);
-  cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->cell_count); cudaFree(c->scan_blocks);
+  cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->scan_blocks);
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1);

@@ -12,6 +12,7 @@
 #define NG 5     // constants.F90:544
 #define JNG 5    // constants.F90:545
 #define PNG 3    // constants.F90:537
+#define CELL_PAD 3   // ghost cells on each side covered by the particle sort buckets
 
 namespace cylgpu {
 
@@ -71,6 +72,8 @@ struct SpeciesState {
   bool set = false;
   double* d[7] = {0, 0, 0, 0, 0, 0, 0};   // SoA: x y z px py pz w
   int64_t n = 0, cap = 0;
+  int* cell_start = nullptr;   // exclusive scan of the sort buckets of the last sort, ncell + 1 entries
+  int64_t cell_start_n = 0;
 };
 
 struct Timer {
@@ -111,8 +114,6 @@ struct cylgpu_ctx {
   uint32_t* lowhole = nullptr;   // holes below the new count
   uint32_t* hightail = nullptr;  // keepers above the new count
   int64_t pscratch_cap = 0;
-  int* cell_count = nullptr;     // (nx+2*CELL_PAD) * (ny+2*CELL_PAD) + 1
-  int* cell_fill = nullptr;
   int* scan_blocks = nullptr;
   int64_t ncell = 0;
   double* psend_l = nullptr; double* psend_r = nullptr; double* precv = nullptr;
@@ -124,7 +125,9 @@ struct cylgpu_ctx {
   cylgpu::Transport* tr = nullptr;
 
   int sort_interval = 1;
-  int push_variant = 1;
+  // 0 per-particle REDs, 1 warp-window shuffle deposit, 2 strip CTAs + shared-memory field patch,
+  // 3 strip CTAs + DMMA outer-product deposit
+  int push_variant = 3;
   int64_t pushes_since_sort = 0;
   bool sorted_valid = false;
 

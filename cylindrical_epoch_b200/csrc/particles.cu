@@ -7,6 +7,7 @@
 #include <cmath>
 
 #include "push.cuh"
+#include "deposit_mma.cuh"
 
 namespace cylgpu {
 
@@ -111,6 +112,7 @@ __device__ __forceinline__ void deposit_global(const PushConst& P, const Deposit
 }
 
 // variant 0: one thread per particle, everything through L1/L2
+template <int M>
 __global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict__ x, double* __restrict__ y,
                                                  double* __restrict__ z, double* __restrict__ px,
                                                  double* __restrict__ py, double* __restrict__ pz,
@@ -120,7 +122,7 @@ __global__ void __launch_bounds__(128) k_push_v0(PushConst P, double* __restrict
   double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
   const double W = w[i];
   DepositIn D;
-  push_one(P, X, Y, Z, PX, PY, PZ, W, D);
+  push_one<M>(P, X, Y, Z, PX, PY, PZ, W, D);
   x[i] = X; y[i] = Y; z[i] = Z;
   px[i] = PX; py[i] = PY; pz[i] = PZ;
   if (P.deposit) deposit_global(P, D);
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
   if (valid) {
     double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
     const double W = w[i];
-    push_one(P, X, Y, Z, PX, PY, PZ, W, D);
+    push_one<M>(P, X, Y, Z, PX, PY, PZ, W, D);
     x[i] = X; y[i] = Y; z[i] = Z;
     px[i] = PX; py[i] = PY; pz[i] = PZ;
   }
@@ -373,6 +375,107 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
   const bool inwin = valid && sx <= WX - 5 && D.cell_y2 == base_y;
   if (valid && !inwin) deposit_global(P, D);
   deposit_window<M>(P, D, inwin, lane, base_x, base_y, inwin ? sx : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// variant 2: strip CTAs.  The sort of this push (do_sort) left the particles ordered by the
+// staggered cell (cell_y2, cell_x2) they occupy after the half-step drift, with the start of
+// every cell in `cell_start`.  One CTA owns a strip of STRIP_C consecutive cells of one row:
+// it stages the (STRIP_C + 3) x 4 node patch of all 6 M mode arrays that those cells gather
+// from in shared memory (mode 0 as reals), then walks its particles 128 at a time: gather from
+// shared memory, Boris, store, warp-window deposit.  Lanes whose cell is not the predicted
+// one (clamped sort keys, last-bit disagreements) gather from the mode arrays instead, and
+// the window deposit runs as many passes as the warp has distinct windows (normally one), so
+// nothing depends on the sort being exact.
+// ------------------------------------------------------------------------------------------
+#define STRIP_C 16
+#define STRIP_PC (STRIP_C + 3)
+
+__device__ __forceinline__ const cplx* field_ptr(const PushConst& P, int comp) {
+  return comp == 0 ? P.exm : comp == 1 ? P.erm : comp == 2 ? P.etm : comp == 3 ? P.bxm : comp == 4 ? P.brm : P.btm;
+}
+
+// shared memory of one strip CTA (dynamic): [mode-0 patch: 6*CS doubles][m>0 patch: 6*(M-1)*CS cplx]
+// [DMMA staging: 4 warps * MMA_WARP_DOUBLES doubles (variant 3 only)]
+template <int M>
+constexpr size_t strip_smem_bytes(bool mma) {
+  return (size_t)6 * PATCH_ROWS * STRIP_PC * 8 + (size_t)6 * (M - 1) * PATCH_ROWS * STRIP_PC * 16 +
+         (mma ? (size_t)4 * MMA_WARP_DOUBLES * 8 : 0);
+}
+
+template <int M, bool MMA>
+__global__ void __launch_bounds__(128, PUSH_MINB) k_push_v2(PushConst P, double* __restrict__ x, double* __restrict__ y,
+                                                 double* __restrict__ z, double* __restrict__ px,
+                                                 double* __restrict__ py, double* __restrict__ pz,
+                                                 const double* __restrict__ w, int64_t n,
+                                                 const int* __restrict__ cell_start, int ncx, int nstrip_x) {
+  constexpr int PC = STRIP_PC, CS = PATCH_ROWS * PC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* s0 = reinterpret_cast<double*>(smem_raw);
+  cplx* sm = reinterpret_cast<cplx*>(smem_raw + (size_t)6 * CS * 8);
+  double* wbuf = reinterpret_cast<double*>(smem_raw + (size_t)6 * CS * 8 + (size_t)6 * (M - 1) * CS * 16) +
+                 (threadIdx.x >> 5) * MMA_WARP_DOUBLES;
+  const int srow = blockIdx.x / nstrip_x, scol = blockIdx.x - srow * nstrip_x;
+  const int kx0 = scol * STRIP_C;
+  const int nk = min(STRIP_C, ncx - kx0);
+  const int key0 = srow * ncx + kx0;
+  const int begin = cell_start[key0], end = cell_start[key0 + nk];
+  if (begin >= end) return;
+  const int c0 = kx0 + 1 - CELL_PAD, row0 = srow + 1 - CELL_PAD;   // cell_x2 / cell_y2 of the strip origin
+  const Geom& g = P.g;
+  // stage the patch: node (c0 - 1 + col, row0 - 1 + r)
+  {
+    const int ncol = nk + 3;
+    for (int t = threadIdx.x; t < 6 * M * CS; t += blockDim.x) {
+      const int col = t % PC;
+      int q = t / PC;
+      const int r = q % PATCH_ROWS; q /= PATCH_ROWS;
+      const int im = q % M, comp = q / M;
+      if (col < ncol) {
+        const size_t o = g.at(c0 - 1 + col, row0 - 1 + r, im);
+        if (im == 0) s0[(comp * PATCH_ROWS + r) * PC + col] = __ldg((const double*)(field_ptr(P, comp) + o));
+        else sm[((comp * (M - 1) + im - 1) * PATCH_ROWS + r) * PC + col] = __ldg(field_ptr(P, comp) + o);
+      }
+    }
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (int base = begin; base < end; base += blockDim.x) {
+    const int iraw = base + threadIdx.x;
+    const bool valid = iraw < end;
+    const int i = valid ? iraw : end - 1;   // idle lanes shadow the last particle: finite data, no store
+    DepositIn D;
+    {
+      double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
+      const double W = w[i];
+      PushMid S;
+      push_pre(P, X, Y, Z, PX, PY, PZ, S, D);
+      Fields6 F;
+      if (S.cell_y2 == row0 && S.cell_x2 >= c0 && S.cell_x2 < c0 + nk) F = gather_patch<M, PC>(s0, sm, S, c0, row0);
+      else F = gather_global<M>(P, S);
+      push_post(P, S, F, X, Y, Z, PX, PY, PZ, W, D);
+      if (valid) {
+        x[i] = X; y[i] = Y; z[i] = Z;
+        px[i] = PX; py[i] = PY; pz[i] = PZ;
+      }
+    }
+    if (!P.deposit) continue;
+    // window passes: the first pending lane names the row, the smallest pending cell_x2 of
+    // that row the window origin; every pass retires at least that lane
+    unsigned pending = __ballot_sync(0xffffffffu, valid);
+#pragma unroll 1
+    while (pending) {
+      const int leader = __ffs(pending) - 1;
+      const int base_y = __shfl_sync(0xffffffffu, D.cell_y2, leader);
+      const bool mine = ((pending >> lane) & 1u) && D.cell_y2 == base_y;
+      const int base_x = __reduce_min_sync(0xffffffffu, mine ? D.cell_x2 : 0x3fffffff);
+      const int sx = D.cell_x2 - base_x;
+      const bool inwin = mine && sx <= (MMA ? MMA_WX : WX) - 5;
+      if (MMA) deposit_mma<M>(P, D, inwin, lane, base_x, base_y, sx, wbuf);
+      else deposit_window<M>(P, D, inwin, lane, base_x, base_y, inwin ? sx : 0);
+      pending &= ~__ballot_sync(0xffffffffu, inwin);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256) k_copy_zero(cplx* __restrict__ old0, cplx* __restrict__ old1,
@@ -426,20 +529,36 @@ int do_push(cylgpu_ctx* c) {
     P.deposit = S.sp.zero_current ? 0 : 1;
     const int64_t nb = (S.n + 127) / 128;
     if (c->timing) cudaEventRecord(c->evk0, c->stream);
-#define LAUNCH_V1(MM) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n)
-    if (c->push_variant == 1 && g.M >= 1 && g.M <= 6) {
-      switch (g.M) {
-        case 1: LAUNCH_V1(1); break;
-        case 2: LAUNCH_V1(2); break;
-        case 3: LAUNCH_V1(3); break;
-        case 4: LAUNCH_V1(4); break;
-        case 5: LAUNCH_V1(5); break;
-        default: LAUNCH_V1(6); break;
-      }
-    } else {
-      k_push_v0<<<(unsigned)nb, 128, 0, c->stream>>>(P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n);
+    const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;
+    const int nstrip_x = (ncx + STRIP_C - 1) / STRIP_C;
+    const bool strips = c->push_variant >= 2 && c->sort_interval == 1 && c->sorted_valid &&
+                        c->pushes_since_sort == 0 && S.cell_start != nullptr;
+#define PUSH_ARGS P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n
+#define LAUNCH_STRIP(MM, MMA)                                                                              \
+    do {                                                                                                   \
+      const size_t shb = strip_smem_bytes<MM>(MMA);                                                        \
+      CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
+      k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(PUSH_ARGS, S.cell_start, ncx, nstrip_x); \
+    } while (0)
+#define LAUNCH_M(MM)                                                                                       \
+    do {                                                                                                   \
+      if (strips && c->push_variant == 3) LAUNCH_STRIP(MM, true);                                          \
+      else if (strips) LAUNCH_STRIP(MM, false);                                                            \
+      else if (c->push_variant >= 1) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);       \
+      else k_push_v0<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);                                 \
+    } while (0)
+    switch (g.M) {
+      case 1: LAUNCH_M(1); break;
+      case 2: LAUNCH_M(2); break;
+      case 3: LAUNCH_M(3); break;
+      case 4: LAUNCH_M(4); break;
+      case 5: LAUNCH_M(5); break;
+      case 6: LAUNCH_M(6); break;
+      default: set_error("n_mode = %d not supported by the push kernels (1..6)", g.M); return 2;
     }
-#undef LAUNCH_V1
+#undef LAUNCH_M
+#undef LAUNCH_STRIP
+#undef PUSH_ARGS
     c->stats.kernel_launches += 1;
     if (c->timing) {
       // per-launch device time of the fused kernel (the roofline numerator's clock); the
@@ -793,7 +912,6 @@ int do_remove_behind(cylgpu_ctx* c) {
 // ------------------------------------------------------------------------------------------
 // cell sort (counting sort on the reference's cell index, split_particle.F90:62-63)
 // ------------------------------------------------------------------------------------------
-#define CELL_PAD 3
 struct SortGeom {
   int ncx, ncy;   // nx + 2*CELL_PAD, ny + 2*CELL_PAD
   double x_grid_min_local, y_grid_min_local, dx, dy;
@@ -916,30 +1034,36 @@ int do_sort(cylgpu_ctx* c) {
   G.dx = c->cfg.dx; G.dy = c->cfg.dy;
   G.idx = 1.0 / c->cfg.dx; G.idy = 1.0 / c->cfg.dy;
   const int64_t ncell = (int64_t)G.ncx * G.ncy;
-  const int nb = (int)((ncell + SCAN_B - 1) / SCAN_B);
-  if (!c->cell_count || c->ncell != ncell) {
-    if (c->cell_count) cudaFree(c->cell_count);
+  const int64_t nscan = ncell + 1;   // one extra zero bucket: its exclusive-scan value is the particle total
+  const int nb = (int)((nscan + SCAN_B - 1) / SCAN_B);
+  if (!c->scan_blocks || c->ncell != ncell) {
     if (c->scan_blocks) cudaFree(c->scan_blocks);
-    CUDA_TRY(cudaMalloc(&c->cell_count, (size_t)(ncell + 1) * sizeof(int)));
     CUDA_TRY(cudaMalloc(&c->scan_blocks, (size_t)(nb + 1) * sizeof(int)));
     c->ncell = ncell;
   }
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     cylgpu::SpeciesState& S = c->species[isp];
     if (!S.set || S.n == 0 || S.sp.immobile) continue;
-    if (S.n >= (int64_t)0xFFFFFFFFLL) { set_error("more than 2^32-1 particles per species per GPU"); return 3; }
+    if (S.n >= (int64_t)0x7FFFFFFFLL) { set_error("more than 2^31-1 particles per species per GPU"); return 3; }
     TRY(reserve_pscratch(c, S.cap));
+    // per-species cell starts: the strip push kernel reads them after the sort
+    if (!S.cell_start || S.cell_start_n != nscan) {
+      if (S.cell_start) cudaFree(S.cell_start);
+      CUDA_TRY(cudaMalloc(&S.cell_start, (size_t)nscan * sizeof(int)));
+      S.cell_start_n = nscan;
+    }
+    int* count = S.cell_start;
     uint32_t* key = c->hole_list;   // scratch reuse: hole_list is idle during a sort
     uint32_t* dest = c->perm;
-    CUDA_TRY(cudaMemsetAsync(c->cell_count, 0, (size_t)(ncell + 1) * sizeof(int), c->stream));
+    CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)nscan * sizeof(int), c->stream));
     G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
     G.dtco2 = C_LIGHT * (c->dt / 2.0);
     k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
-                                                      c->cell_count, key, dest, S.n);
-    k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
+                                                      count, key, dest, S.n);
+    k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
     k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
-    k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(c->cell_count, c->scan_blocks, ncell);
-    k_sort_dest<<<nblk(S.n, 256), 256, 0, c->stream>>>(c->cell_count, key, dest, S.n);
+    k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
+    k_sort_dest<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, dest, S.n);
     c->stats.kernel_launches += 5;
     // scatter each component into the spare array, then rotate the pointers (the old
     // component array becomes the next spare): 8 B of scratch per particle, not 56

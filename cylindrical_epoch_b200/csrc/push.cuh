@@ -28,21 +28,6 @@ __device__ __forceinline__ void tri3(double cf, double& w0, double& w1, double& 
   w2 = 0.25 + cf2 - cf;
 }
 
-// 3x3 weighted complex sum with the reference's association order (e_part.inc:7-16)
-__device__ __forceinline__ cplx gather9(const cplx* __restrict__ F, size_t o, size_t SX, double wy0, double wy1,
-                                        double wy2, double wx0, double wx1, double wx2) {
-  cplx s0 = wx0 * __ldg(&F[o]);
-  s0 = s0 + wx1 * __ldg(&F[o + 1]);
-  s0 = s0 + wx2 * __ldg(&F[o + 2]);
-  cplx s1 = wx0 * __ldg(&F[o + SX]);
-  s1 = s1 + wx1 * __ldg(&F[o + SX + 1]);
-  s1 = s1 + wx2 * __ldg(&F[o + SX + 2]);
-  cplx s2 = wx0 * __ldg(&F[o + 2 * SX]);
-  s2 = s2 + wx1 * __ldg(&F[o + 2 * SX + 1]);
-  s2 = s2 + wx2 * __ldg(&F[o + 2 * SX + 2]);
-  return (wy0 * s0 + wy1 * s1) + wy2 * s2;
-}
-
 // Everything the deposit needs from the push of one particle
 struct DepositIn {
   double gx[5], gy[5], hx[5], hy[5];   // index k <-> offset k-2; h = new - old weights
@@ -62,29 +47,43 @@ __device__ __forceinline__ void place3(double* v, int d, double w0, double w1, d
   }
 }
 
-// particles.F90:296-582.  Advances (x,y,z,px,py,pz) by one step and fills `D`.
-__device__ __forceinline__ void push_one(const PushConst& P, double& part_x, double& part_y, double& part_z,
-                                         double& px, double& py, double& pz, double part_weight, DepositIn& D) {
-  const Geom& g = P.g;
-  const double c = C_LIGHT;
-  double part_ux = px * P.ipart_mc, part_uy = py * P.ipart_mc, part_uz = pz * P.ipart_mc;
+// ------------------------------------------------------------------------------------------
+// push_particles, particles.F90:296-582, split in three so that the gather can read either
+// the mode arrays in HBM/L2 (gather_global) or the strip patch staged in shared memory
+// (gather_patch).  All arithmetic keeps the reference's operation order.
+// ------------------------------------------------------------------------------------------
+struct W3 { double w0, w1, w2; };
+struct Fields6 { double ex, er, et, bx, br, bt; };
 
-  double gamma_rel = sqrt(part_ux * part_ux + part_uy * part_uy + part_uz * part_uz + 1.0);
-  double root = P.dtco2 / gamma_rel;
-  part_x = part_x + part_ux * root;
-  part_y = part_y + part_uy * root;
-  part_z = part_z + part_uz * root;
+// state carried from the half-step (pre) to the Boris rotation and deposit set-up (post)
+struct PushMid {
+  double ux, uy, uz;              // u = p / mc at time t
+  cplx exp_min_itheta;            // e^{-i theta} at t + dt/2
+  double theta_05;
+  int cell_x1, cell_y1, cell_x2, cell_y2;
+  W3 gx, gy, hx, hy;              // centred (g) and staggered (h) triangle weights
+};
 
-  double part_x_local = part_x - P.x_grid_min_local;
-  double part_r = sqrt(part_y * part_y + part_z * part_z);
-  double part_r_local = part_r - P.y_grid_min_local;
+// particles.F90:296-388: half-step drift, r / theta, cells, shape weights
+__device__ __forceinline__ void push_pre(const PushConst& P, double& part_x, double& part_y, double& part_z,
+                                         double px, double py, double pz, PushMid& S, DepositIn& D) {
+  S.ux = px * P.ipart_mc; S.uy = py * P.ipart_mc; S.uz = pz * P.ipart_mc;
+  const double gamma_rel = sqrt(S.ux * S.ux + S.uy * S.uy + S.uz * S.uz + 1.0);
+  const double root = P.dtco2 / gamma_rel;
+  part_x = part_x + S.ux * root;
+  part_y = part_y + S.uy * root;
+  part_z = part_z + S.uz * root;
 
-  const cplx exp_min_itheta = C(part_y, -part_z) / part_r;
-  const double theta_05 = atan2(part_z, part_y);
+  const double part_x_local = part_x - P.x_grid_min_local;
+  const double part_r = sqrt(part_y * part_y + part_z * part_z);
+  const double part_r_local = part_r - P.y_grid_min_local;
+
+  S.exp_min_itheta = C(part_y, -part_z) / part_r;
+  S.theta_05 = atan2(part_z, part_y);
   // exp_itheta_05 = 1 / exp_min_itheta_05: real/complex division (Smith's algorithm, as
   // emitted by gfortran/libgcc for COMPLEX division)
   {
-    const double zr = exp_min_itheta.x, zi = exp_min_itheta.y;
+    const double zr = S.exp_min_itheta.x, zi = S.exp_min_itheta.y;
     if (fabs(zr) >= fabs(zi)) {
       const double r = zi / zr, den = zr + zi * r;
       D.exp_itheta_05 = C(1.0 / den, -r / den);
@@ -94,60 +93,146 @@ __device__ __forceinline__ void push_one(const PushConst& P, double& part_x, dou
     }
   }
 
-  double cell_x_r = part_x_local * P.idx;
-  double cell_y_r = part_r_local * P.idy;
+  const double cell_x_r = part_x_local * P.idx;
+  const double cell_y_r = part_r_local * P.idy;
   int cell_x1 = (int)floor(cell_x_r + 0.5);
   double cell_frac_x = (double)cell_x1 - cell_x_r;
-  cell_x1 += 1;
+  S.cell_x1 = cell_x1 + 1;
   int cell_y1 = (int)floor(cell_y_r + 0.5);
   double cell_frac_y = (double)cell_y1 - cell_y_r;
-  cell_y1 += 1;
-
-  double gx0, gx1, gx2, gy0, gy1, gy2;
-  tri3(cell_frac_x, gx0, gx1, gx2);
-  tri3(cell_frac_y, gy0, gy1, gy2);
+  S.cell_y1 = cell_y1 + 1;
+  tri3(cell_frac_x, S.gx.w0, S.gx.w1, S.gx.w2);
+  tri3(cell_frac_y, S.gy.w0, S.gy.w1, S.gy.w2);
 
   int cell_x2 = (int)floor(cell_x_r);
   cell_frac_x = (double)cell_x2 - cell_x_r + 0.5;
-  cell_x2 += 1;
+  S.cell_x2 = cell_x2 + 1;
   int cell_y2 = (int)floor(cell_y_r);
   cell_frac_y = (double)cell_y2 - cell_y_r + 0.5;
-  cell_y2 += 1;
+  S.cell_y2 = cell_y2 + 1;
+  tri3(cell_frac_x, S.hx.w0, S.hx.w1, S.hx.w2);
+  tri3(cell_frac_y, S.hy.w0, S.hy.w1, S.hy.w2);
+}
 
-  double hx0, hx1, hx2, hy0, hy1, hy2;
-  tri3(cell_frac_x, hx0, hx1, hx2);
-  tri3(cell_frac_y, hy0, hy1, hy2);
+// 3x3 weighted sum of a REAL array with element stride ES (mode 0: the imaginary part of the
+// m = 0 gather never reaches the particle, e_part.inc:18 takes the real part of 1 * sum)
+template <int ES, bool LDG>
+__device__ __forceinline__ double gather9_r(const double* __restrict__ F, size_t o, size_t SX, const W3& wy,
+                                            const W3& wx) {
+  auto L = [&](size_t k) -> double { return LDG ? __ldg(&F[ES * k]) : F[ES * k]; };
+  double s0 = wx.w0 * L(o);
+  s0 = s0 + wx.w1 * L(o + 1);
+  s0 = s0 + wx.w2 * L(o + 2);
+  double s1 = wx.w0 * L(o + SX);
+  s1 = s1 + wx.w1 * L(o + SX + 1);
+  s1 = s1 + wx.w2 * L(o + SX + 2);
+  double s2 = wx.w0 * L(o + 2 * SX);
+  s2 = s2 + wx.w1 * L(o + 2 * SX + 1);
+  s2 = s2 + wx.w2 * L(o + 2 * SX + 2);
+  return (wy.w0 * s0 + wy.w1 * s1) + wy.w2 * s2;
+}
+template <bool LDG>
+__device__ __forceinline__ cplx gather9_c(const cplx* __restrict__ F, size_t o, size_t SX, const W3& wy,
+                                          const W3& wx) {
+  auto L = [&](size_t k) -> cplx { return LDG ? __ldg(&F[k]) : F[k]; };
+  cplx s0 = wx.w0 * L(o);
+  s0 = s0 + wx.w1 * L(o + 1);
+  s0 = s0 + wx.w2 * L(o + 2);
+  cplx s1 = wx.w0 * L(o + SX);
+  s1 = s1 + wx.w1 * L(o + SX + 1);
+  s1 = s1 + wx.w2 * L(o + SX + 2);
+  cplx s2 = wx.w0 * L(o + 2 * SX);
+  s2 = s2 + wx.w1 * L(o + 2 * SX + 1);
+  s2 = s2 + wx.w2 * L(o + 2 * SX + 2);
+  return (wy.w0 * s0 + wy.w1 * s1) + wy.w2 * s2;
+}
+// real part of e * g  (cplx product, e_part.inc:18)
+__device__ __forceinline__ double re_mul(cplx e, cplx g) { return e.x * g.x - e.y * g.y; }
 
-  // gather (e_part.inc / b_part.inc)
+// e_part.inc / b_part.inc straight from the mode arrays (through L1/L2)
+template <int M>
+__device__ __forceinline__ Fields6 gather_global(const PushConst& P, const PushMid& S) {
+  const Geom& g = P.g;
   const size_t SX = g.SX;
-  double ex_part = 0, er_part = 0, et_part = 0, bx_part = 0, br_part = 0, bt_part = 0;
+  Fields6 F;
   {
-    cplx e = C(1.0, 0.0);
-    for (int im = 0; im < g.M; ++im) {
-      const size_t o12 = g.at(cell_x1 - 1, cell_y2 - 1, im);
-      const size_t o21 = g.at(cell_x2 - 1, cell_y1 - 1, im);
-      const size_t o22 = g.at(cell_x2 - 1, cell_y2 - 1, im);
-      const size_t o11 = g.at(cell_x1 - 1, cell_y1 - 1, im);
-      ex_part = ex_part + (e * gather9(P.exm, o12, SX, hy0, hy1, hy2, gx0, gx1, gx2)).x;
-      er_part = er_part + (e * gather9(P.erm, o21, SX, gy0, gy1, gy2, hx0, hx1, hx2)).x;
-      et_part = et_part + (e * gather9(P.etm, o22, SX, hy0, hy1, hy2, hx0, hx1, hx2)).x;
-      bx_part = bx_part + (e * gather9(P.bxm, o21, SX, gy0, gy1, gy2, hx0, hx1, hx2)).x;
-      br_part = br_part + (e * gather9(P.brm, o12, SX, hy0, hy1, hy2, gx0, gx1, gx2)).x;
-      bt_part = bt_part + (e * gather9(P.btm, o11, SX, gy0, gy1, gy2, gx0, gx1, gx2)).x;
-      e = e * exp_min_itheta;
-    }
+    const size_t o12 = g.at(S.cell_x1 - 1, S.cell_y2 - 1, 0), o21 = g.at(S.cell_x2 - 1, S.cell_y1 - 1, 0);
+    const size_t o22 = g.at(S.cell_x2 - 1, S.cell_y2 - 1, 0), o11 = g.at(S.cell_x1 - 1, S.cell_y1 - 1, 0);
+    F.ex = 0.0 + gather9_r<2, true>((const double*)P.exm, o12, SX, S.hy, S.gx);
+    F.er = 0.0 + gather9_r<2, true>((const double*)P.erm, o21, SX, S.gy, S.hx);
+    F.et = 0.0 + gather9_r<2, true>((const double*)P.etm, o22, SX, S.hy, S.hx);
+    F.bx = 0.0 + gather9_r<2, true>((const double*)P.bxm, o21, SX, S.gy, S.hx);
+    F.br = 0.0 + gather9_r<2, true>((const double*)P.brm, o12, SX, S.hy, S.gx);
+    F.bt = 0.0 + gather9_r<2, true>((const double*)P.btm, o11, SX, S.gy, S.gx);
   }
-  const double ey_part = er_part * exp_min_itheta.x + et_part * exp_min_itheta.y;
-  const double ez_part = -er_part * exp_min_itheta.y + et_part * exp_min_itheta.x;
-  const double by_part = br_part * exp_min_itheta.x + bt_part * exp_min_itheta.y;
-  const double bz_part = -br_part * exp_min_itheta.y + bt_part * exp_min_itheta.x;
+  cplx e = S.exp_min_itheta;
+#pragma unroll
+  for (int im = 1; im < M; ++im) {
+    const size_t o12 = g.at(S.cell_x1 - 1, S.cell_y2 - 1, im), o21 = g.at(S.cell_x2 - 1, S.cell_y1 - 1, im);
+    const size_t o22 = g.at(S.cell_x2 - 1, S.cell_y2 - 1, im), o11 = g.at(S.cell_x1 - 1, S.cell_y1 - 1, im);
+    F.ex = F.ex + re_mul(e, gather9_c<true>(P.exm, o12, SX, S.hy, S.gx));
+    F.er = F.er + re_mul(e, gather9_c<true>(P.erm, o21, SX, S.gy, S.hx));
+    F.et = F.et + re_mul(e, gather9_c<true>(P.etm, o22, SX, S.hy, S.hx));
+    F.bx = F.bx + re_mul(e, gather9_c<true>(P.bxm, o21, SX, S.gy, S.hx));
+    F.br = F.br + re_mul(e, gather9_c<true>(P.brm, o12, SX, S.hy, S.gx));
+    F.bt = F.bt + re_mul(e, gather9_c<true>(P.btm, o11, SX, S.gy, S.gx));
+    e = e * S.exp_min_itheta;
+  }
+  return F;
+}
+
+// Strip patch in shared memory: PR rows x PC columns per (component, mode); mode 0 real only.
+//   s0[(comp*PR + row)*PC + col]                        double
+//   sm[((comp*(M-1) + im-1)*PR + row)*PC + col]         cplx
+// patch (row 0, col 0) is the node (c0 - 1, row0 - 1) of the mode arrays.
+#define PATCH_ROWS 4
+template <int M, int PC>
+__device__ __forceinline__ Fields6 gather_patch(const double* __restrict__ s0, const cplx* __restrict__ sm,
+                                                const PushMid& S, int c0, int row0) {
+  const int lx1 = S.cell_x1 - c0, ly1 = S.cell_y1 - row0, lx2 = S.cell_x2 - c0;   // ly2 == 0
+  const int o12 = lx1, o21 = ly1 * PC + lx2, o22 = lx2, o11 = ly1 * PC + lx1;
+  constexpr int CS = PATCH_ROWS * PC;
+  Fields6 F;
+  F.ex = 0.0 + gather9_r<1, false>(s0 + 0 * CS, o12, PC, S.hy, S.gx);
+  F.er = 0.0 + gather9_r<1, false>(s0 + 1 * CS, o21, PC, S.gy, S.hx);
+  F.et = 0.0 + gather9_r<1, false>(s0 + 2 * CS, o22, PC, S.hy, S.hx);
+  F.bx = 0.0 + gather9_r<1, false>(s0 + 3 * CS, o21, PC, S.gy, S.hx);
+  F.br = 0.0 + gather9_r<1, false>(s0 + 4 * CS, o12, PC, S.hy, S.gx);
+  F.bt = 0.0 + gather9_r<1, false>(s0 + 5 * CS, o11, PC, S.gy, S.gx);
+  cplx e = S.exp_min_itheta;
+#pragma unroll
+  for (int im = 1; im < M; ++im) {
+    const cplx* b = sm + (size_t)(im - 1) * CS;
+    constexpr int MS = (M - 1) * CS;
+    F.ex = F.ex + re_mul(e, gather9_c<false>(b + 0 * MS, o12, PC, S.hy, S.gx));
+    F.er = F.er + re_mul(e, gather9_c<false>(b + 1 * MS, o21, PC, S.gy, S.hx));
+    F.et = F.et + re_mul(e, gather9_c<false>(b + 2 * MS, o22, PC, S.hy, S.hx));
+    F.bx = F.bx + re_mul(e, gather9_c<false>(b + 3 * MS, o21, PC, S.gy, S.hx));
+    F.br = F.br + re_mul(e, gather9_c<false>(b + 4 * MS, o12, PC, S.hy, S.gx));
+    F.bt = F.bt + re_mul(e, gather9_c<false>(b + 5 * MS, o11, PC, S.gy, S.gx));
+    e = e * S.exp_min_itheta;
+  }
+  return F;
+}
+
+// particles.F90:393-582: rotate (r,theta)->(y,z), Boris, full-step move, deposit set-up
+__device__ __forceinline__ void push_post(const PushConst& P, const PushMid& S, const Fields6& F, double& part_x,
+                                          double& part_y, double& part_z, double& px, double& py, double& pz,
+                                          double part_weight, DepositIn& D) {
+  const double c = C_LIGHT;
+  const cplx emi = S.exp_min_itheta;
+  const double ex_part = F.ex, bx_part = F.bx;
+  const double ey_part = F.er * emi.x + F.et * emi.y;
+  const double ez_part = -F.er * emi.y + F.et * emi.x;
+  const double by_part = F.br * emi.x + F.bt * emi.y;
+  const double bz_part = -F.br * emi.y + F.bt * emi.x;
 
   // Boris rotation (particles.F90:405-451)
-  const double uxm = part_ux + P.cmratio * ex_part;
-  const double uym = part_uy + P.cmratio * ey_part;
-  const double uzm = part_uz + P.cmratio * ez_part;
-  gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
-  root = P.ccmratio / gamma_rel;
+  const double uxm = S.ux + P.cmratio * ex_part;
+  const double uym = S.uy + P.cmratio * ey_part;
+  const double uzm = S.uz + P.cmratio * ez_part;
+  double gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+  double root = P.ccmratio / gamma_rel;
   const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
   const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
   const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
@@ -157,9 +242,9 @@ __device__ __forceinline__ void push_one(const PushConst& P, double& part_x, dou
                       + 2.0 * ((tauy * tauz + taux) * uzm + (tauy * taux - tauz) * uxm)) * tau;
   const double uzp = ((1.0 - taux2 - tauy2 + tauz2) * uzm
                       + 2.0 * ((tauz * taux + tauy) * uxm + (tauz * tauy - taux) * uym)) * tau;
-  part_ux = uxp + P.cmratio * ex_part;
-  part_uy = uyp + P.cmratio * ey_part;
-  part_uz = uzp + P.cmratio * ez_part;
+  const double part_ux = uxp + P.cmratio * ex_part;
+  const double part_uy = uyp + P.cmratio * ey_part;
+  const double part_uz = uzp + P.cmratio * ez_part;
 
   const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
   gamma_rel = sqrt(part_u2 + 1.0);
@@ -177,33 +262,33 @@ __device__ __forceinline__ void push_one(const PushConst& P, double& part_x, dou
 
   const double part_vy = part_uy * c * igamma;
   const double part_vz = part_uz * c * igamma;
-  part_r = sqrt(part_y * part_y + part_z * part_z);
+  double part_r = sqrt(part_y * part_y + part_z * part_z);
   const cplx exp_itheta_10 = C(part_y, part_z) / part_r;
   const double part_vt = -part_vy * exp_itheta_10.y + part_vz * exp_itheta_10.x;
 
   // position at t + 1.5 dt (particles.F90:515-523); the stored position is not touched
-  part_x_local = part_x + delta_x - P.x_grid_min_local;
+  const double part_x_local = part_x + delta_x - P.x_grid_min_local;
   const double y15 = part_y + delta_y, z15 = part_z + delta_z;
   part_r = sqrt(y15 * y15 + z15 * z15);
-  part_r_local = part_r - P.y_grid_min_local;
+  const double part_r_local = part_r - P.y_grid_min_local;
   const cplx exp_itheta_15 = C(y15, z15) / part_r;
   const double theta_15 = atan2(z15, y15);
-  D.exp_idtheta = exp_itheta_15 * exp_min_itheta;
-  D.dtheta = theta_15 - theta_05;
+  D.exp_idtheta = exp_itheta_15 * emi;
+  D.dtheta = theta_15 - S.theta_05;
 
-  cell_x_r = part_x_local * P.idx;
-  cell_y_r = part_r_local * P.idy;
+  const double cell_x_r = part_x_local * P.idx;
+  const double cell_y_r = part_r_local * P.idy;
   int cell_x3 = (int)floor(cell_x_r);
-  cell_frac_x = (double)cell_x3 - cell_x_r + 0.5;
+  const double cell_frac_x = (double)cell_x3 - cell_x_r + 0.5;
   cell_x3 += 1;
   int cell_y3 = (int)floor(cell_y_r);
-  cell_frac_y = (double)cell_y3 - cell_y_r + 0.5;
+  const double cell_frac_y = (double)cell_y3 - cell_y_r + 0.5;
   cell_y3 += 1;
-  const int dcellx = cell_x3 - cell_x2, dcelly = cell_y3 - cell_y2;
+  const int dcellx = cell_x3 - S.cell_x2, dcelly = cell_y3 - S.cell_y2;
 
   // gx = old hx (placed at offsets -1..1), hx = new - old
-  place3(D.gx, 0, hx0, hx1, hx2);
-  place3(D.gy, 0, hy0, hy1, hy2);
+  place3(D.gx, 0, S.hx.w0, S.hx.w1, S.hx.w2);
+  place3(D.gy, 0, S.hy.w0, S.hy.w1, S.hy.w2);
   double n0, n1, n2;
   tri3(cell_frac_x, n0, n1, n2);
   place3(D.hx, dcellx, n0, n1, n2);
@@ -219,11 +304,21 @@ __device__ __forceinline__ void push_one(const PushConst& P, double& part_x, dou
   D.xmax = 1 + (dcellx + 1) / 2;
   D.ymin = -1 + (dcelly - 1) / 2;
   D.ymax = 1 + (dcelly + 1) / 2;
-  D.cell_x2 = cell_x2;
-  D.cell_y2 = cell_y2;
+  D.cell_x2 = S.cell_x2;
+  D.cell_y2 = S.cell_y2;
   const double q_weight_fac = P.q_fac * part_weight;
   D.fcx = q_weight_fac * P.idt;
   D.fcz = q_weight_fac * part_vt;
+}
+
+// the whole push of one particle against the mode arrays in HBM/L2
+template <int M>
+__device__ __forceinline__ void push_one(const PushConst& P, double& part_x, double& part_y, double& part_z,
+                                         double& px, double& py, double& pz, double part_weight, DepositIn& D) {
+  PushMid S;
+  push_pre(P, part_x, part_y, part_z, px, py, pz, S, D);
+  const Fields6 F = gather_global<M>(P, S);
+  push_post(P, S, F, part_x, part_y, part_z, px, py, pz, part_weight, D);
 }
 
 // the four theta-integrated mode factors m_fac_1..4 of particles.F90:588-626 for mode im > 0
