@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcylgpu.so")
+# CYLGPU_LIB: an alternative build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("CYLGPU_LIB") or os.path.join(_HERE, "libcylgpu.so")
 MAX_SPECIES = 8
 
 SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int,

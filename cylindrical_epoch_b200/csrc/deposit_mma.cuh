@@ -24,10 +24,17 @@ namespace cylgpu {
 
 #define MMA_WX 8          // window slots in x: 5-point footprint + up to 3 cells of origin shift
 #define MMA_PITCH 40      // doubles per tile row: 32 columns + pad (conflict-free LDS.128 fragments)
-#define MMA_ROWS 24       // V tile (8 rows) + two U tiles (double buffer)
+#ifndef MMA_VSLOTS
+#define MMA_VSLOTS 2      // resident V tiles: 2 = gx and run/hx side by side, 1 = one tile re-staged per part
+#endif
+#define MMA_ROWS (8 * MMA_VSLOTS + 16)   // V tiles + two U tiles of 8 rows
 #define MMA_WARP_DOUBLES (MMA_ROWS * MMA_PITCH)
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
+#ifdef CYL_KNOCK_DMMA   // tuning experiment: one DFMA per lane instead of the tensor op (wrong results)
+  c[0] = fma(a, b, c[0]); c[1] = fma(b, a, c[1]);
+  return;
+#endif
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
@@ -53,8 +60,11 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
   const double* inv_volume = P.tab + 2 * P.ntab + JNG;
   const double* ratio_area_xt = P.tab + 3 * P.ntab + JNG;
 
-  double* Vs = wbuf;
-  double* Us = wbuf + 8 * MMA_PITCH;          // two tiles of 8 rows
+  // per-warp staging: two V tiles (slot A: run, later hx; slot B: gx) and two U tiles
+  double* VA = wbuf;
+  double* VB = wbuf + (MMA_VSLOTS > 1 ? 1 : 0) * 8 * MMA_PITCH;
+  double* VH = wbuf + (MMA_VSLOTS > 2 ? 2 : 0) * 8 * MMA_PITCH;   // hx tile (slot A unless 3 slots)
+  double* Us = wbuf + MMA_VSLOTS * 8 * MMA_PITCH;
   const int fm = lane >> 2, fk = lane & 3;    // fragment coordinates: row (A) / column (B) and k
   const int frag_off = fm * MMA_PITCH + 2 * fk;
 
@@ -77,34 +87,27 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
 
   // V column of this particle: value k of the 5-point footprint goes to window slot sx + k, the
   // three remaining slots get zeros.  Outside [xmin, xmax] gx and hx are exact zeros already.
-  auto store_v = [&](const double (&v)[5]) {
+  auto store_v = [&](double* V, const double (&v)[5]) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) Vs[((sx + k) & 7) * MMA_PITCH + lane] = (k < 5) ? v[k] : 0.0;
+    for (int k = 0; k < 8; ++k) V[((sx + k) & 7) * MMA_PITCH + lane] = (k < 5) ? v[k] : 0.0;
   };
-  double bfrag[8];
-  auto load_b = [&]() {
+  // a pair of 8-row U tiles against one V tile: 8 k-steps, B fragment shared by both tiles
+  auto mma_pair = [&](const double* V, bool two, double (&acc0)[2][2], double (&acc1)[2][2]) {
 #pragma unroll
     for (int J = 0; J < 4; ++J) {
-      const double2 t = *reinterpret_cast<const double2*>(Vs + frag_off + 8 * J);
-      bfrag[2 * J] = t.x; bfrag[2 * J + 1] = t.y;
-    }
-  };
-  // one 8-row tile of U: stage, read back as A fragments, 8 k-steps
-  auto tile = [&](int t, const double (&u)[8], double (&acc0)[2], double (&acc1)[2]) {
-    double* Ut = Us + (t & 1) * 8 * MMA_PITCH;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) Ut[r * MMA_PITCH + lane] = u[r];
-    __syncwarp();
-    if (t == 0) load_b();
-#pragma unroll
-    for (int J = 0; J < 4; ++J) {
-      const double2 a = *reinterpret_cast<const double2*>(Ut + frag_off + 8 * J);
-      dmma884(acc0, a.x, bfrag[2 * J]);
-      dmma884(acc1, a.y, bfrag[2 * J + 1]);
+      const double2 b = *reinterpret_cast<const double2*>(V + frag_off + 8 * J);
+      const double2 a0 = *reinterpret_cast<const double2*>(Us + frag_off + 8 * J);
+      dmma884(acc0[0], a0.x, b.x);
+      dmma884(acc0[1], a0.y, b.y);
+      if (two) {
+        const double2 a1 = *reinterpret_cast<const double2*>(Us + 8 * MMA_PITCH + frag_off + 8 * J);
+        dmma884(acc1[0], a1.x, b.x);
+        dmma884(acc1[1], a1.y, b.y);
+      }
     }
   };
   // RED the accumulators of one component: lane (fm, fk) holds rows 8t + fm, slots 2fk, 2fk+1
-  auto flush = [&](double* __restrict__ arr, size_t shift, double (&acc)[T][2][2]) {
+  auto flush = [&](double* __restrict__ arr, size_t shift, double (&acc)[T + 1][2][2]) {
 #pragma unroll
     for (int t = 0; t < T; ++t) {
       const int c = 8 * t + fm;
@@ -112,31 +115,47 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
       const int im = (coef + 1) >> 1, reim = coef ? ((coef + 1) & 1) : 0;
       const size_t o = g.at(base_x - 2 + 2 * fk, base_y - 2 + ky, im) + shift;
       const double v0 = acc[t][0][0] + acc[t][1][0], v1 = acc[t][0][1] + acc[t][1][1];
+#ifdef CYL_KNOCK_RED   // tuning experiment: keep the arithmetic alive, never issue the RED
+      if (c < R) {
+        if (v0 == 1.2345e300) atomicAdd(arr + 2 * o + reim, v0);
+        if (v1 == 1.2345e300) atomicAdd(arr + 2 * (o + 1) + reim, v1);
+      }
+#else
       if (c < R) {
         if (v0 != 0.0) atomicAdd(arr + 2 * o + reim, v0);
         if (v1 != 0.0) atomicAdd(arr + 2 * (o + 1) + reim, v1);
       }
+#endif
     }
   };
-  // coefficient c of a part -> (row ky, mode im, re/im), all compile-time after unrolling
-#define MMA_PART(UEXPR, ACC)                                                   \
+  // One part = all T tiles of a coefficient block against the V tile `VT`.  Coefficient c of a
+  // part -> (row ky, mode im, re/im), all compile-time after unrolling.  Tiles go in pairs
+  // (both staged before one __syncwarp); the leading __syncwarp retires every fragment read
+  // of the previous pair before its buffers are overwritten.
+#define MMA_PART(VT, UEXPR, ACC)                                               \
   do {                                                                         \
-    _Pragma("unroll") for (int t = 0; t < T; ++t) {                            \
-      double u[8];                                                             \
-      _Pragma("unroll") for (int r = 0; r < 8; ++r) {                          \
-        const int c = 8 * t + r;                                               \
-        const int ky = (c < R) ? c / NC : 0, coef = (c < R) ? c % NC : 0;      \
-        const int im = (coef + 1) >> 1;                                        \
-        const bool imag = coef > 0 && ((coef + 1) & 1);                        \
-        double val = 0.0;                                                      \
-        if (c < R) { UEXPR; }                                                  \
-        u[r] = val;                                                            \
+    _Pragma("unroll") for (int t0 = 0; t0 < T; t0 += 2) {                      \
+      if (t0 > 0) __syncwarp();                                                \
+      _Pragma("unroll") for (int tt = 0; tt < 2; ++tt) {                       \
+        const int t = t0 + tt;                                                 \
+        if (t < T) {                                                           \
+          _Pragma("unroll") for (int r = 0; r < 8; ++r) {                      \
+            const int c = 8 * t + r;                                           \
+            const int ky = (c < R) ? c / NC : 0, coef = (c < R) ? c % NC : 0;  \
+            const int im = (coef + 1) >> 1;                                    \
+            const bool imag = coef > 0 && ((coef + 1) & 1);                    \
+            double val = 0.0;                                                  \
+            if (c < R) { UEXPR; }                                              \
+            Us[(tt * 8 + r) * MMA_PITCH + lane] = val;                         \
+          }                                                                    \
+        }                                                                      \
       }                                                                        \
-      tile(t, u, ACC[t][0], ACC[t][1]);                                        \
+      __syncwarp();                                                            \
+      mma_pair(VT, t0 + 1 < T, ACC[t0], ACC[t0 + 1]);                          \
     }                                                                          \
   } while (0)
 
-  double acc[T][2][2];
+  double acc[T + 1][2][2];   // one spare so that the odd tile of the last pair has a (dead) target
   auto zero_acc = [&]() {
 #pragma unroll
     for (int t = 0; t < T; ++t) { acc[t][0][0] = acc[t][0][1] = acc[t][1][0] = acc[t][1][1] = 0.0; }
@@ -152,12 +171,13 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
     for (int k = 0; k < 5; ++k) { run = run + D.hx[k]; v[k] = run; }
     if (D.xmax < 2) v[4] = 0.0;     // ix = 2 is outside the footprint (particles.F90:646 loop bound)
     __syncwarp();
-    store_v(v);
+    store_v(VA, v);
+    if (MMA_VSLOTS == 3) { store_v(VB, D.gx); store_v(VH, D.hx); }   // all x-shape tiles up front: gx, hx die here
     double fjx[5];
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) fjx[ky] = fcx * __ldg(&inv_area_rt[base_y - 2 + ky]);
     zero_acc();
-    MMA_PART({
+    MMA_PART(VA, {
       if (coef == 0) val = -(fjx[ky] * (gy[ky] + 0.5 * hy[ky]));
       else {
         const cplx w_rt = f2[im - 1] * gy[ky] + f3[im - 1] * hy[ky];
@@ -167,6 +187,10 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
     }, acc);
     flush(P.jx, 1, acc);
   }
+  // gx -> slot B, hx -> slot A (the run tile is dead after the sync)
+  __syncwarp();
+  if (MMA_VSLOTS < 3) store_v(VB, D.gx);
+  if (MMA_VSLOTS == 2) store_v(VA, D.hx);
   // ---------------- jr: -S(ky) (f2 gx + f3 hx) ----------------
   {
     double S[5];
@@ -179,18 +203,15 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
         S[ky] = s;
       }
       if (D.ymax < 2) S[4] = 0.0;   // iy = 2 is outside the footprint
-      if (D.ymin > -2) S[0] = 0.0;  // (already an exact zero: hy[0] == 0; kept for clarity)
     }
-    __syncwarp();
-    store_v(D.gx);
     zero_acc();
-    MMA_PART({
+    MMA_PART(VB, {
       if (coef == 0) val = -S[ky];
       else { const cplx a = (-S[ky]) * f2[im - 1]; val = imag ? a.y : a.x; }
     }, acc);
     __syncwarp();
-    store_v(D.hx);
-    MMA_PART({
+    if (MMA_VSLOTS == 1) store_v(VA, D.hx);
+    MMA_PART(VH, {
       if (coef == 0) val = -(0.5 * S[ky]);
       else { const cplx a = (-S[ky]) * f3[im - 1]; val = imag ? a.y : a.x; }
     }, acc);
@@ -201,10 +222,10 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
     double fjz[5];
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) fjz[ky] = fcz * __ldg(&inv_volume[base_y - 2 + ky]);
-    __syncwarp();
-    store_v(D.gx);
     zero_acc();
-    MMA_PART({
+    __syncwarp();
+    if (MMA_VSLOTS == 1) store_v(VB, D.gx);
+    MMA_PART(VB, {
       if (coef == 0) val = fjz[ky] * (gy[ky] + 0.5 * hy[ky]);
       else {
         const cplx w_rt = f2[im - 1] * gy[ky] + f3[im - 1] * hy[ky];
@@ -213,8 +234,8 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
       }
     }, acc);
     __syncwarp();
-    store_v(D.hx);
-    MMA_PART({
+    if (MMA_VSLOTS == 1) store_v(VA, D.hx);
+    MMA_PART(VH, {
       if (coef == 0) val = fjz[ky] * (0.5 * gy[ky] + third * hy[ky]);
       else {
         const cplx ym1 = f3[im - 1] * gy[ky] + f4[im - 1] * hy[ky];

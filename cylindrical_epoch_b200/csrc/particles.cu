@@ -388,7 +388,9 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
 // the window deposit runs as many passes as the warp has distinct windows (normally one), so
 // nothing depends on the sort being exact.
 // ------------------------------------------------------------------------------------------
+#ifndef STRIP_C
 #define STRIP_C 16
+#endif
 #define STRIP_PC (STRIP_C + 3)
 
 __device__ __forceinline__ const cplx* field_ptr(const PushConst& P, int comp) {

@@ -31,7 +31,7 @@ def test_field_solver_vacuum_laser():
         p.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_lwfa_steps(variant):
     d = decks.lwfa(nx=96, ny=32, n_mode=2, ppc_e=4, ppc_p=1)
     p = Pair(d, variant=variant)
@@ -49,7 +49,7 @@ def test_lwfa_steps(variant):
         p.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_thermal_periodic_reflect(variant):
     d = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8)
     p = Pair(d, variant=variant)
@@ -88,6 +88,56 @@ def test_five_modes():
         p.check_particles()
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("n_mode", [1, 2, 3, 4, 6])
+def test_every_mode_count_strip_mma(n_mode):
+    """the default push (strip CTAs + DMMA deposit) is a template on n_mode: every instantiation,
+    hot start so that J is exercised before any field feedback, then full steps"""
+    d = decks.thermal(nx=40, ny=20, n_mode=n_mode, ppc=5, temp_k=2e8)
+    p = Pair(d, variant=3)
+    try:
+        p.step(4)
+        p.check_counts()
+        errs = p.check_fields(TOL_HOT)
+        worst = p.check_particles(TOL_HOT)
+        print(n_mode, max(errs.values()), worst)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("ppc", [1, 2])
+def test_sparse_plasma_multi_window(variant, ppc):
+    """1-2 particles per cell: a warp spans many cells of a strip, so the window deposit needs
+    several passes per batch (and, with 32+ cells per batch, windows that restart mid-warp)"""
+    d = decks.thermal(nx=70, ny=18, n_mode=2, ppc=ppc, temp_k=1e8)
+    p = Pair(d, variant=variant)
+    try:
+        p.step(6)
+        p.check_counts()
+        p.check_fields(TOL_HOT)
+        p.check_particles(TOL_HOT)
+        p.check_cells()
+    finally:
+        p.close()
+
+
+def test_variants_agree_on_current():
+    """all four deposit implementations produce the same J from the same particles (1e-12 of |J|max)"""
+    d = decks.thermal(nx=48, ny=24, n_mode=3, ppc=9, temp_k=5e8)
+    js = []
+    for variant in (0, 1, 2, 3):
+        p = Pair(d, init_half_step=False, variant=variant)
+        try:
+            p.slabs[0].push_particles_no_bcs()
+            js.append([p.slabs[0].download_field(n) for n in ("jxm", "jrm", "jtm")])
+        finally:
+            p.close()
+    for k in range(3):
+        den = np.abs(js[0][k]).max()
+        for v in range(1, 4):
+            assert np.abs(js[v][k] - js[0][k]).max() <= 1e-12 * den, (k, v)
 
 
 def test_push_only_currents():
