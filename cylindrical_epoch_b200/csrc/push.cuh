@@ -28,6 +28,75 @@ __device__ __forceinline__ void tri3(double cf, double& w0, double& w1, double& 
   w2 = 0.25 + cf2 - cf;
 }
 
+// ------------------------------------------------------------------------------------------
+// Division / square root.  The reference divides and takes square roots with IEEE
+// semantics; CUDA's correctly rounded FP64 div/sqrt cost a MUFU seed, ~8 dependent DFMAs, a
+// range check and a slow-path call each, and the push has 6 + 15 of them per particle.  The
+// kernels use branch-free Newton/Goldschmidt forms instead (all operands here are finite,
+// normal and non-zero): results agree with the IEEE ones to <= 1 ulp, far inside the parity
+// tolerance.  -DCYL_REFERENCE_MATH restores the correctly rounded operations.
+// ------------------------------------------------------------------------------------------
+#ifndef CYL_REFERENCE_MATH
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);     // seed is good to ~2^-20: two Newton steps reach rounding level
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ double div_nr(double a, double b) {
+  const double r = rcp_nr(b);
+  const double q = a * r;
+  return fma(fma(-b, q, a), r, q);
+}
+// s = sqrt(x), is = 1 / sqrt(x)  (coupled Goldschmidt iteration + one correction each)
+__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& is) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = x * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  const double d = fma(-g, g, x);
+  s = fma(d, h, g);
+  is = h + h;
+}
+#else
+__device__ __forceinline__ double rcp_nr(double x) { return 1.0 / x; }
+__device__ __forceinline__ double div_nr(double a, double b) { return a / b; }
+__device__ __forceinline__ void sqrt_rsqrt(double x, double& s, double& is) { s = sqrt(x); is = 1.0 / s; }
+#endif
+
+// dtheta = ATAN2(z15, y15) - ATAN2(z05, y05)  (particles.F90:520-523) from ed = e^{i dtheta},
+// which the push has anyway: the principal angle of ed by the arcsine series when it is small
+// (|sin| < 1/16: relative error < 2^-53; virtually every particle away from the axis), one
+// ATAN2 otherwise.  The reference's difference of two principal angles jumps by 2 pi when the
+// particle crosses the theta = pi cut (the negative y axis); that jump enters m_fac_1..4
+// through m*dtheta and is reproduced: the straight path from (y05, z05) to (y15, z15) crosses
+// the cut iff z changes sign and the rotation sense matches (sign of sin dtheta).
+__device__ __forceinline__ double delta_theta(cplx ed, bool up05, bool up15) {
+  const double s = ed.y, s2 = s * s;
+  double d;
+  if (ed.x > 0.0 && fabs(s) < 0.0625) {
+    double p = 143.0 / 10240.0;
+    p = fma(p, s2, 231.0 / 13312.0);
+    p = fma(p, s2, 63.0 / 2816.0);
+    p = fma(p, s2, 35.0 / 1152.0);
+    p = fma(p, s2, 5.0 / 112.0);
+    p = fma(p, s2, 3.0 / 40.0);
+    p = fma(p, s2, 1.0 / 6.0);
+    d = fma(p * s2, s, s);
+  } else {
+    d = atan2(s, ed.x);
+  }
+  const double two_pi = 6.283185307179586476925286766559;
+  if (up05 && !up15 && s > 0.0) d -= two_pi;
+  else if (!up05 && up15 && s < 0.0) d += two_pi;
+  return d;
+}
+
 // Everything the deposit needs from the push of one particle
 struct DepositIn {
   double gx[5], gy[5], hx[5], hy[5];   // index k <-> offset k-2; h = new - old weights
@@ -68,13 +137,28 @@ struct PushMid {
 __device__ __forceinline__ void push_pre(const PushConst& P, double& part_x, double& part_y, double& part_z,
                                          double px, double py, double pz, PushMid& S, DepositIn& D) {
   S.ux = px * P.ipart_mc; S.uy = py * P.ipart_mc; S.uz = pz * P.ipart_mc;
+#ifndef CYL_REFERENCE_MATH
+  double gamma_rel, igamma;
+  sqrt_rsqrt(S.ux * S.ux + S.uy * S.uy + S.uz * S.uz + 1.0, gamma_rel, igamma);
+  const double root = P.dtco2 * igamma;
+#else
   const double gamma_rel = sqrt(S.ux * S.ux + S.uy * S.uy + S.uz * S.uz + 1.0);
   const double root = P.dtco2 / gamma_rel;
+#endif
   part_x = part_x + S.ux * root;
   part_y = part_y + S.uy * root;
   part_z = part_z + S.uz * root;
 
   const double part_x_local = part_x - P.x_grid_min_local;
+#ifndef CYL_REFERENCE_MATH
+  double part_r, ipart_r;
+  sqrt_rsqrt(part_y * part_y + part_z * part_z, part_r, ipart_r);
+  const double part_r_local = part_r - P.y_grid_min_local;
+  S.exp_min_itheta = C(part_y * ipart_r, -part_z * ipart_r);
+  S.theta_05 = 0.0;   // not needed: delta theta comes from e^{i dtheta} (push_post)
+  // exp_itheta_05 = 1 / exp_min_itheta_05 = conj / |.|^2, and |.|^2 = 1 to rounding
+  D.exp_itheta_05 = C(S.exp_min_itheta.x, -S.exp_min_itheta.y);
+#else
   const double part_r = sqrt(part_y * part_y + part_z * part_z);
   const double part_r_local = part_r - P.y_grid_min_local;
 
@@ -92,6 +176,7 @@ __device__ __forceinline__ void push_pre(const PushConst& P, double& part_x, dou
       D.exp_itheta_05 = C(r / den, -1.0 / den);
     }
   }
+#endif
 
   const double cell_x_r = part_x_local * P.idx;
   const double cell_y_r = part_r_local * P.idy;
@@ -231,11 +316,12 @@ __device__ __forceinline__ void push_post(const PushConst& P, const PushMid& S, 
   const double uxm = S.ux + P.cmratio * ex_part;
   const double uym = S.uy + P.cmratio * ey_part;
   const double uzm = S.uz + P.cmratio * ez_part;
-  double gamma_rel = sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
-  double root = P.ccmratio / gamma_rel;
+  double gamma_rel, igamma;
+  sqrt_rsqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0, gamma_rel, igamma);
+  double root = P.ccmratio * igamma;
   const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
   const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;
-  const double tau = 1.0 / (1.0 + taux2 + tauy2 + tauz2);
+  const double tau = rcp_nr(1.0 + taux2 + tauy2 + tauz2);
   const double uxp = ((1.0 + taux2 - tauy2 - tauz2) * uxm
                       + 2.0 * ((taux * tauy + tauz) * uym + (taux * tauz - tauy) * uzm)) * tau;
   const double uyp = ((1.0 - taux2 + tauy2 - tauz2) * uym
@@ -247,8 +333,7 @@ __device__ __forceinline__ void push_post(const PushConst& P, const PushMid& S, 
   const double part_uz = uzp + P.cmratio * ez_part;
 
   const double part_u2 = part_ux * part_ux + part_uy * part_uy + part_uz * part_uz;
-  gamma_rel = sqrt(part_u2 + 1.0);
-  const double igamma = 1.0 / gamma_rel;
+  sqrt_rsqrt(part_u2 + 1.0, gamma_rel, igamma);
   root = P.dtco2 * igamma;
   const double delta_x = part_ux * root, delta_y = part_uy * root, delta_z = part_uz * root;
   part_x = part_x + delta_x;
@@ -262,19 +347,24 @@ __device__ __forceinline__ void push_post(const PushConst& P, const PushMid& S, 
 
   const double part_vy = part_uy * c * igamma;
   const double part_vz = part_uz * c * igamma;
-  double part_r = sqrt(part_y * part_y + part_z * part_z);
-  const cplx exp_itheta_10 = C(part_y, part_z) / part_r;
+  double part_r, ipart_r;
+  sqrt_rsqrt(part_y * part_y + part_z * part_z, part_r, ipart_r);
+  const cplx exp_itheta_10 = C(part_y * ipart_r, part_z * ipart_r);
   const double part_vt = -part_vy * exp_itheta_10.y + part_vz * exp_itheta_10.x;
 
   // position at t + 1.5 dt (particles.F90:515-523); the stored position is not touched
   const double part_x_local = part_x + delta_x - P.x_grid_min_local;
   const double y15 = part_y + delta_y, z15 = part_z + delta_z;
-  part_r = sqrt(y15 * y15 + z15 * z15);
+  sqrt_rsqrt(y15 * y15 + z15 * z15, part_r, ipart_r);
   const double part_r_local = part_r - P.y_grid_min_local;
-  const cplx exp_itheta_15 = C(y15, z15) / part_r;
-  const double theta_15 = atan2(z15, y15);
+  const cplx exp_itheta_15 = C(y15 * ipart_r, z15 * ipart_r);
   D.exp_idtheta = exp_itheta_15 * emi;
+#ifndef CYL_REFERENCE_MATH
+  D.dtheta = delta_theta(D.exp_idtheta, emi.y <= 0.0, z15 >= 0.0);
+#else
+  const double theta_15 = atan2(z15, y15);
   D.dtheta = theta_15 - S.theta_05;
+#endif
 
   const double cell_x_r = part_x_local * P.idx;
   const double cell_y_r = part_r_local * P.idy;
@@ -336,7 +426,7 @@ __device__ __forceinline__ ModeFac mode_factors(int im, double dtheta, cplx exp_
     F.f3 = f1 * C(0.5 - 0.125 * m2dth2, third * mdth);
     F.f4 = f1 * C(third - 0.1 * m2dth2, 0.25 * mdth);
   } else {
-    const double inv_mdth = 1.0 / mdth;
+    const double inv_mdth = rcp_nr(mdth);
     const double inv_m2dth2 = inv_mdth * inv_mdth;
     const cplx f1 = (2.0 * inv_mdth) * exp_imtheta0;
     F.f2 = f1 * (C(0.0, -1.0) * (exp_imdtheta - C(1.0, 0.0)));
