@@ -24,10 +24,7 @@ namespace cylgpu {
 
 #define MMA_WX 8          // window slots in x: 5-point footprint + up to 3 cells of origin shift
 #define MMA_PITCH 40      // doubles per tile row: 32 columns + pad (conflict-free LDS.128 fragments)
-#ifndef MMA_VSLOTS
-#define MMA_VSLOTS 2      // resident V tiles: 2 = gx and run/hx side by side, 1 = one tile re-staged per part
-#endif
-#define MMA_ROWS (8 * MMA_VSLOTS + 16)   // V tiles + two U tiles of 8 rows
+#define MMA_ROWS 40       // three V tiles (run, gx, hx) + two U tiles, 8 rows each
 #define MMA_WARP_DOUBLES (MMA_ROWS * MMA_PITCH)
 
 __device__ __forceinline__ void dmma884(double (&c)[2], double a, double b) {
@@ -50,21 +47,24 @@ struct MmaGeom {
 // the warp must call this (inactive lanes contribute exact zeros; their D must be finite).
 template <int M>
 __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn& D, bool active, int lane,
-                                            int base_x, int base_y, int sx, double* __restrict__ wbuf) {
+                                            int base_x, int base_y, int sx, double* __restrict__ wbuf,
+                                            const double* __restrict__ stab, int stab_row) {
   typedef MmaGeom<M> G;
   constexpr int NC = G::NC, R = G::R, T = G::T;
   const Geom& g = P.g;
   const double third = 1.0 / 3.0;
-  const double* inv_area_rt = P.tab + JNG;
-  const double* inv_area_xt = P.tab + P.ntab + JNG;
-  const double* inv_volume = P.tab + 2 * P.ntab + JNG;
-  const double* ratio_area_xt = P.tab + 3 * P.ntab + JNG;
+  // radial tables of the 5 window rows: the strip's copy in shared memory (stab[t*5 + ky], staged
+  // for base_y == stab_row) or, for a window of another row, the global tables
+  const bool tab_sm = (base_y == stab_row);
+  auto tab = [&](int t, int ky) -> double {
+    return tab_sm ? stab[t * 5 + ky] : __ldg(P.tab + t * P.ntab + JNG + base_y - 2 + ky);
+  };
 
-  // per-warp staging: two V tiles (slot A: run, later hx; slot B: gx) and two U tiles
+  // per-warp staging: three V tiles (A: run, B: gx, H: hx) and two U tiles
   double* VA = wbuf;
-  double* VB = wbuf + (MMA_VSLOTS > 1 ? 1 : 0) * 8 * MMA_PITCH;
-  double* VH = wbuf + (MMA_VSLOTS > 2 ? 2 : 0) * 8 * MMA_PITCH;   // hx tile (slot A unless 3 slots)
-  double* Us = wbuf + MMA_VSLOTS * 8 * MMA_PITCH;
+  double* VB = wbuf + 8 * MMA_PITCH;
+  double* VH = wbuf + 16 * MMA_PITCH;
+  double* Us = wbuf + 24 * MMA_PITCH;
   const int fm = lane >> 2, fk = lane & 3;    // fragment coordinates: row (A) / column (B) and k
   const int frag_off = fm * MMA_PITCH + 2 * fk;
 
@@ -109,64 +109,71 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
       }
     }
   };
-  // RED the accumulators of one component: lane (fm, fk) holds rows 8t + fm, slots 2fk, 2fk+1
-  auto flush = [&](double* __restrict__ arr, size_t shift, double (&acc)[T + 1][2][2]) {
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const int c = 8 * t + fm;
-      const int ky = c / NC, coef = c - ky * NC;
-      const int im = (coef + 1) >> 1, reim = coef ? ((coef + 1) & 1) : 0;
-      const size_t o = g.at(base_x - 2 + 2 * fk, base_y - 2 + ky, im) + shift;
-      const double v0 = acc[t][0][0] + acc[t][1][0], v1 = acc[t][0][1] + acc[t][1][1];
+  // RED one accumulated 8-row tile: lane (fm, fk) holds row 8t + fm, slots 2fk, 2fk+1
+  auto flush_tile = [&](double* __restrict__ arr, size_t shift, int t, const double (&acc)[2][2]) {
+    const int c = 8 * t + fm;
+    const int ky = c / NC, coef = c - ky * NC;
+    const int im = (coef + 1) >> 1, reim = coef ? ((coef + 1) & 1) : 0;
+    const size_t o = g.at(base_x - 2 + 2 * fk, base_y - 2 + ky, im) + shift;
+    const double v0 = acc[0][0] + acc[1][0], v1 = acc[0][1] + acc[1][1];
 #ifdef CYL_KNOCK_RED   // tuning experiment: keep the arithmetic alive, never issue the RED
-      if (c < R) {
-        if (v0 == 1.2345e300) atomicAdd(arr + 2 * o + reim, v0);
-        if (v1 == 1.2345e300) atomicAdd(arr + 2 * (o + 1) + reim, v1);
-      }
-#else
-      if (c < R) {
-        if (v0 != 0.0) atomicAdd(arr + 2 * o + reim, v0);
-        if (v1 != 0.0) atomicAdd(arr + 2 * (o + 1) + reim, v1);
-      }
-#endif
+    if (c < R) {
+      if (v0 == 1.2345e300) atomicAdd(arr + 2 * o + reim, v0);
+      if (v1 == 1.2345e300) atomicAdd(arr + 2 * (o + 1) + reim, v1);
     }
+#else
+    if (c < R) {
+      if (v0 != 0.0) atomicAdd(arr + 2 * o + reim, v0);
+      if (v1 != 0.0) atomicAdd(arr + 2 * (o + 1) + reim, v1);
+    }
+#endif
   };
-  // One part = all T tiles of a coefficient block against the V tile `VT`.  Coefficient c of a
-  // part -> (row ky, mode im, re/im), all compile-time after unrolling.  Tiles go in pairs
-  // (both staged before one __syncwarp); the leading __syncwarp retires every fragment read
-  // of the previous pair before its buffers are overwritten.
-#define MMA_PART(VT, UEXPR, ACC)                                               \
+  // Stage the pair of U tiles (t0, t0+1) of one coefficient block.  Coefficient c of a block
+  // -> (row ky, mode im, re/im), all compile-time after unrolling.
+#define MMA_STAGE(T0, UEXPR)                                                   \
   do {                                                                         \
-    _Pragma("unroll") for (int t0 = 0; t0 < T; t0 += 2) {                      \
-      if (t0 > 0) __syncwarp();                                                \
-      _Pragma("unroll") for (int tt = 0; tt < 2; ++tt) {                       \
-        const int t = t0 + tt;                                                 \
-        if (t < T) {                                                           \
-          _Pragma("unroll") for (int r = 0; r < 8; ++r) {                      \
-            const int c = 8 * t + r;                                           \
-            const int ky = (c < R) ? c / NC : 0, coef = (c < R) ? c % NC : 0;  \
-            const int im = (coef + 1) >> 1;                                    \
-            const bool imag = coef > 0 && ((coef + 1) & 1);                    \
-            double val = 0.0;                                                  \
-            if (c < R) { UEXPR; }                                              \
-            Us[(tt * 8 + r) * MMA_PITCH + lane] = val;                         \
-          }                                                                    \
+    _Pragma("unroll") for (int tt = 0; tt < 2; ++tt) {                         \
+      const int t = (T0) + tt;                                                 \
+      if (t < T) {                                                             \
+        _Pragma("unroll") for (int r = 0; r < 8; ++r) {                        \
+          const int c = 8 * t + r;                                             \
+          const int ky = (c < R) ? c / NC : 0, coef = (c < R) ? c % NC : 0;    \
+          const int im = (coef + 1) >> 1;                                      \
+          const bool imag = coef > 0 && ((coef + 1) & 1);                      \
+          double val = 0.0;                                                    \
+          if (c < R) { UEXPR; }                                                \
+          Us[(tt * 8 + r) * MMA_PITCH + lane] = val;                           \
         }                                                                      \
       }                                                                        \
+    }                                                                          \
+  } while (0)
+  // One component, tile pair by tile pair: [stage U1, mma with V1] (+ [stage U2, mma with V2])
+  // into the same accumulators, then RED.  A __syncwarp before each staging retires the
+  // fragment reads of the previous one, a second one publishes the new tiles; only two tiles
+  // of accumulators are ever live, whatever n_mode is.
+#define MMA_COMPONENT(ARR, SHIFT, V1, UEXPR1, TWO, V2, UEXPR2)                 \
+  do {                                                                         \
+    _Pragma("unroll") for (int t0 = 0; t0 < T; t0 += 2) {                      \
+      double acc0[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, acc1[2][2] = {{0.0, 0.0}, {0.0, 0.0}}; \
       __syncwarp();                                                            \
-      mma_pair(VT, t0 + 1 < T, ACC[t0], ACC[t0 + 1]);                          \
+      MMA_STAGE(t0, UEXPR1);                                                   \
+      __syncwarp();                                                            \
+      mma_pair(V1, t0 + 1 < T, acc0, acc1);                                    \
+      if (TWO) {                                                               \
+        __syncwarp();                                                          \
+        MMA_STAGE(t0, UEXPR2);                                                 \
+        __syncwarp();                                                          \
+        mma_pair(V2, t0 + 1 < T, acc0, acc1);                                  \
+      }                                                                        \
+      flush_tile(ARR, SHIFT, t0, acc0);                                        \
+      if (t0 + 1 < T) flush_tile(ARR, SHIFT, t0 + 1, acc1);                    \
     }                                                                          \
   } while (0)
 
-  double acc[T + 1][2][2];   // one spare so that the odd tile of the last pair has a (dead) target
-  auto zero_acc = [&]() {
-#pragma unroll
-    for (int t = 0; t < T; ++t) { acc[t][0][0] = acc[t][0][1] = acc[t][1][0] = acc[t][1][1] = 0.0; }
-  };
   const double* gy = D.gy;
   const double* hy = D.hy;
 
-  // ---------------- jx: a(ky, c) x run(s) ----------------
+  // all three x-shape tiles up front (gx, hx are dead afterwards): run = prefix sum of hx
   {
     double v[5];
     double run = 0.0;
@@ -175,25 +182,23 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
     if (D.xmax < 2) v[4] = 0.0;     // ix = 2 is outside the footprint (particles.F90:646 loop bound)
     __syncwarp();
     store_v(VA, v);
-    if (MMA_VSLOTS == 3) { store_v(VB, D.gx); store_v(VH, D.hx); }   // all x-shape tiles up front: gx, hx die here
+    store_v(VB, D.gx);
+    store_v(VH, D.hx);
+  }
+  // ---------------- jx: a(ky, c) x run(s) ----------------
+  {
     double fjx[5];
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) fjx[ky] = fcx * __ldg(&inv_area_rt[base_y - 2 + ky]);
-    zero_acc();
-    MMA_PART(VA, {
+    for (int ky = 0; ky < 5; ++ky) fjx[ky] = fcx * tab(0, ky);
+    MMA_COMPONENT(P.jx, 1, VA, {
       if (coef == 0) val = -(fjx[ky] * (gy[ky] + 0.5 * hy[ky]));
       else {
         const cplx w_rt = f2[im - 1] * gy[ky] + f3[im - 1] * hy[ky];
         const cplx a = (-fjx[ky]) * w_rt;
         val = imag ? a.y : a.x;
       }
-    }, acc);
-    flush(P.jx, 1, acc);
+    }, false, VA, {});
   }
-  // gx -> slot B, hx -> slot A (the run tile is dead after the sync)
-  __syncwarp();
-  if (MMA_VSLOTS < 3) store_v(VB, D.gx);
-  if (MMA_VSLOTS == 2) store_v(VA, D.hx);
   // ---------------- jr: -S(ky) (f2 gx + f3 hx) ----------------
   {
     double S[5];
@@ -201,54 +206,42 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
       double s = 0.0;
 #pragma unroll
       for (int ky = 0; ky < 5; ++ky) {
-        const int cy = base_y - 2 + ky;
-        s = s * __ldg(&ratio_area_xt[cy]) + (fcx * hy[ky]) * __ldg(&inv_area_xt[cy]);
+        s = s * tab(3, ky) + (fcx * hy[ky]) * tab(1, ky);
         S[ky] = s;
       }
       if (D.ymax < 2) S[4] = 0.0;   // iy = 2 is outside the footprint
     }
-    zero_acc();
-    MMA_PART(VB, {
+    MMA_COMPONENT(P.jr, (size_t)g.SX, VB, {
       if (coef == 0) val = -S[ky];
       else { const cplx a = (-S[ky]) * f2[im - 1]; val = imag ? a.y : a.x; }
-    }, acc);
-    __syncwarp();
-    if (MMA_VSLOTS == 1) store_v(VA, D.hx);
-    MMA_PART(VH, {
+    }, true, VH, {
       if (coef == 0) val = -(0.5 * S[ky]);
       else { const cplx a = (-S[ky]) * f3[im - 1]; val = imag ? a.y : a.x; }
-    }, acc);
-    flush(P.jr, (size_t)g.SX, acc);
+    });
   }
   // ---------------- jt: fjz(ky) (w_rt gx + ym_fac_1 hx) ----------------
   {
     double fjz[5];
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) fjz[ky] = fcz * __ldg(&inv_volume[base_y - 2 + ky]);
-    zero_acc();
-    __syncwarp();
-    if (MMA_VSLOTS == 1) store_v(VB, D.gx);
-    MMA_PART(VB, {
+    for (int ky = 0; ky < 5; ++ky) fjz[ky] = fcz * tab(2, ky);
+    MMA_COMPONENT(P.jt, 0, VB, {
       if (coef == 0) val = fjz[ky] * (gy[ky] + 0.5 * hy[ky]);
       else {
         const cplx w_rt = f2[im - 1] * gy[ky] + f3[im - 1] * hy[ky];
         const cplx a = fjz[ky] * w_rt;
         val = imag ? a.y : a.x;
       }
-    }, acc);
-    __syncwarp();
-    if (MMA_VSLOTS == 1) store_v(VA, D.hx);
-    MMA_PART(VH, {
+    }, true, VH, {
       if (coef == 0) val = fjz[ky] * (0.5 * gy[ky] + third * hy[ky]);
       else {
         const cplx ym1 = f3[im - 1] * gy[ky] + f4[im - 1] * hy[ky];
         const cplx a = fjz[ky] * ym1;
         val = imag ? a.y : a.x;
       }
-    }, acc);
-    flush(P.jt, 0, acc);
+    });
   }
-#undef MMA_PART
+#undef MMA_STAGE
+#undef MMA_COMPONENT
 }
 
 }  // namespace cylgpu

@@ -402,11 +402,18 @@ __device__ __forceinline__ const cplx* field_ptr(const PushConst& P, int comp) {
 template <int M>
 constexpr size_t strip_smem_bytes(bool mma) {
   return (size_t)6 * PATCH_ROWS * STRIP_PC * 8 + (size_t)6 * (M - 1) * PATCH_ROWS * STRIP_PC * 16 +
-         (mma ? (size_t)4 * MMA_WARP_DOUBLES * 8 : 0);
+         (mma ? (size_t)4 * MMA_WARP_DOUBLES * 8 : 0) + 32 * 8;
 }
 
+// CTAs per SM the strip kernel is compiled for.  The kernel is bound by the LSU/shared-memory
+// data pipe (82 % busy), so register spills (local memory goes through the same pipe) cost more
+// than the warps they buy: 3 CTAs x 168 registers beat 4 x 128 and 5 x 96 (measured).  Above
+// three modes the per-mode factors need still more registers and the patch more shared memory.
+#ifndef STRIP_MINB
+#define STRIP_MINB(M) ((M) <= 3 ? 3 : 2)
+#endif
 template <int M, bool MMA>
-__global__ void __launch_bounds__(128, PUSH_MINB) k_push_v2(PushConst P, double* __restrict__ x, double* __restrict__ y,
+__global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, double* __restrict__ x, double* __restrict__ y,
                                                  double* __restrict__ z, double* __restrict__ px,
                                                  double* __restrict__ py, double* __restrict__ pz,
                                                  const double* __restrict__ w, int64_t n,
@@ -415,8 +422,8 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v2(PushConst P, double*
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s0 = reinterpret_cast<double*>(smem_raw);
   cplx* sm = reinterpret_cast<cplx*>(smem_raw + (size_t)6 * CS * 8);
-  double* wbuf = reinterpret_cast<double*>(smem_raw + (size_t)6 * CS * 8 + (size_t)6 * (M - 1) * CS * 16) +
-                 (threadIdx.x >> 5) * MMA_WARP_DOUBLES;
+  double* stab = reinterpret_cast<double*>(smem_raw + (size_t)6 * CS * 8 + (size_t)6 * (M - 1) * CS * 16);
+  double* wbuf = stab + 32 + (threadIdx.x >> 5) * MMA_WARP_DOUBLES;
   const int srow = blockIdx.x / nstrip_x, scol = blockIdx.x - srow * nstrip_x;
   const int kx0 = scol * STRIP_C;
   const int nk = min(STRIP_C, ncx - kx0);
@@ -440,12 +447,28 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v2(PushConst P, double*
       }
     }
   }
+  // radial tables of the window rows row0-2 .. row0+2 (particles.F90:190-217): [table][ky]
+  if (threadIdx.x < 20) {
+    const int t = threadIdx.x / 5, ky = threadIdx.x - 5 * t;
+    stab[threadIdx.x] = __ldg(P.tab + t * P.ntab + JNG + row0 - 2 + ky);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   for (int base = begin; base < end; base += blockDim.x) {
     const int iraw = base + threadIdx.x;
     const bool valid = iraw < end;
     const int i = valid ? iraw : end - 1;   // idle lanes shadow the last particle: finite data, no store
+    {
+      // pull the next batch into L1 while this one computes (DRAM latency >> one batch of a warp)
+      const int inext = min(iraw + (int)blockDim.x, end - 1);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(x + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(y + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(z + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(px + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(py + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + inext));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(w + inext));
+    }
     DepositIn D;
     {
       double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
@@ -473,7 +496,7 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v2(PushConst P, double*
       const int base_x = __reduce_min_sync(0xffffffffu, mine ? D.cell_x2 : 0x3fffffff);
       const int sx = D.cell_x2 - base_x;
       const bool inwin = mine && sx <= (MMA ? MMA_WX : WX) - 5;
-      if (MMA) deposit_mma<M>(P, D, inwin, lane, base_x, base_y, sx, wbuf);
+      if (MMA) deposit_mma<M>(P, D, inwin, lane, base_x, base_y, sx, wbuf, stab, row0);
       else deposit_window<M>(P, D, inwin, lane, base_x, base_y, inwin ? sx : 0);
       pending &= ~__ballot_sync(0xffffffffu, inwin);
     }
