@@ -120,6 +120,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i)
 {
     for (int q = 0; q < 7; ++q) cudaFree(c->species[i].d[q]);
+    for (int q = 0; q < 7; ++q) cudaFree(c->species[i].alt[q]);
     cudaFree(c->species[i].cell_start);
   }
   cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->hole_list);

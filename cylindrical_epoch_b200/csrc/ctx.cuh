@@ -72,6 +72,8 @@ struct SpeciesState {
   bool set = false;
   double* d[7] = {0, 0, 0, 0, 0, 0, 0};   // SoA: x y z px py pz w
   int64_t n = 0, cap = 0;
+  double* alt[7] = {0, 0, 0, 0, 0, 0, 0};   // second buffer set: the strip push writes the sorted list here
+  int64_t alt_cap = 0;
   int* cell_start = nullptr;   // exclusive scan of the sort buckets of the last sort, ncell + 1 entries
   int64_t cell_start_n = 0;
 };

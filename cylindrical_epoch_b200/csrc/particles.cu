@@ -397,6 +397,9 @@ __device__ __forceinline__ const cplx* field_ptr(const PushConst& P, int comp) {
   return comp == 0 ? P.exm : comp == 1 ? P.erm : comp == 2 ? P.etm : comp == 3 ? P.bxm : comp == 4 ? P.brm : P.btm;
 }
 
+struct SoaIn { const double* d[7]; };
+struct SoaOut { double* d[7]; };
+
 // shared memory of one strip CTA (dynamic): [mode-0 patch: 6*CS doubles][m>0 patch: 6*(M-1)*CS cplx]
 // [DMMA staging: 4 warps * MMA_WARP_DOUBLES doubles (variant 3 only)]
 template <int M>
@@ -413,11 +416,10 @@ constexpr size_t strip_smem_bytes(bool mma) {
 #define STRIP_MINB(M) ((M) <= 3 ? 3 : 2)
 #endif
 template <int M, bool MMA>
-__global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, double* __restrict__ x, double* __restrict__ y,
-                                                 double* __restrict__ z, double* __restrict__ px,
-                                                 double* __restrict__ py, double* __restrict__ pz,
-                                                 const double* __restrict__ w, int64_t n,
-                                                 const int* __restrict__ cell_start, int ncx, int nstrip_x) {
+__global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, SoaIn in, SoaOut out,
+                                                                const uint32_t* __restrict__ src,
+                                                                const int* __restrict__ cell_start, int ncx,
+                                                                int nstrip_x) {
   constexpr int PC = STRIP_PC, CS = PATCH_ROWS * PC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s0 = reinterpret_cast<double*>(smem_raw);
@@ -457,22 +459,13 @@ __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, dou
   for (int base = begin; base < end; base += blockDim.x) {
     const int iraw = base + threadIdx.x;
     const bool valid = iraw < end;
-    const int i = valid ? iraw : end - 1;   // idle lanes shadow the last particle: finite data, no store
-    {
-      // pull the next batch into L1 while this one computes (DRAM latency >> one batch of a warp)
-      const int inext = min(iraw + (int)blockDim.x, end - 1);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(x + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(y + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(z + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(px + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(py + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(pz + inext));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(w + inext));
-    }
+    // sorted slot -> particle: the sort only built the permutation, the move happens here.
+    // Idle lanes shadow the last particle of the strip: finite data, no store.
+    const uint32_t j = __ldg(&src[valid ? iraw : end - 1]);
     DepositIn D;
     {
-      double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
-      const double W = w[i];
+      double X = in.d[0][j], Y = in.d[1][j], Z = in.d[2][j], PX = in.d[3][j], PY = in.d[4][j], PZ = in.d[5][j];
+      const double W = in.d[6][j];
       PushMid S;
       push_pre(P, X, Y, Z, PX, PY, PZ, S, D);
       Fields6 F;
@@ -480,8 +473,9 @@ __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, dou
       else F = gather_global<M>(P, S);
       push_post(P, S, F, X, Y, Z, PX, PY, PZ, W, D);
       if (valid) {
-        x[i] = X; y[i] = Y; z[i] = Z;
-        px[i] = PX; py[i] = PY; pz[i] = PZ;
+        out.d[0][iraw] = X; out.d[1][iraw] = Y; out.d[2][iraw] = Z;
+        out.d[3][iraw] = PX; out.d[4][iraw] = PY; out.d[5][iraw] = PZ;
+        out.d[6][iraw] = W;
       }
     }
     if (!P.deposit) continue;
@@ -515,6 +509,7 @@ __global__ void __launch_bounds__(256) k_copy_zero(cplx* __restrict__ old0, cplx
 }
 
 int do_sort(cylgpu_ctx* c);
+int do_sort_species(cylgpu_ctx* c, int isp, bool physical);
 
 int do_push(cylgpu_ctx* c) {
   const Geom& g = c->g;
@@ -526,14 +521,16 @@ int do_push(cylgpu_ctx* c) {
                                                c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], n);
     c->stats.kernel_launches += 1;
   }
-  if (c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval)) {
-    TRY(do_sort(c));
-  }
+  const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  // strip kernels read through the sort permutation and write the second buffer set: the sort
+  // then only has to build the permutation (no scatter passes)
+  const bool strips = c->push_variant >= 2 && c->sort_interval == 1;
   const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
   const double dt = c->dt;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     cylgpu::SpeciesState& S = c->species[isp];
     if (!S.set || S.sp.immobile || S.n == 0) continue;
+    if (need_sort) TRY(do_sort_species(c, isp, /*physical=*/!strips));
     PushConst P;
     P.g = g;
     P.exm = c->f[CYLGPU_EXM]; P.erm = c->f[CYLGPU_ERM]; P.etm = c->f[CYLGPU_ETM];
@@ -556,14 +553,14 @@ int do_push(cylgpu_ctx* c) {
     if (c->timing) cudaEventRecord(c->evk0, c->stream);
     const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;
     const int nstrip_x = (ncx + STRIP_C - 1) / STRIP_C;
-    const bool strips = c->push_variant >= 2 && c->sort_interval == 1 && c->sorted_valid &&
-                        c->pushes_since_sort == 0 && S.cell_start != nullptr;
+    SoaIn pin; SoaOut pout;
+    for (int q = 0; q < 7; ++q) { pin.d[q] = S.d[q]; pout.d[q] = S.alt[q]; }
 #define PUSH_ARGS P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n
 #define LAUNCH_STRIP(MM, MMA)                                                                              \
     do {                                                                                                   \
       const size_t shb = strip_smem_bytes<MM>(MMA);                                                        \
       CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
-      k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(PUSH_ARGS, S.cell_start, ncx, nstrip_x); \
+      k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x); \
     } while (0)
 #define LAUNCH_M(MM)                                                                                       \
     do {                                                                                                   \
@@ -584,6 +581,7 @@ int do_push(cylgpu_ctx* c) {
 #undef LAUNCH_M
 #undef LAUNCH_STRIP
 #undef PUSH_ARGS
+    if (strips) for (int q = 0; q < 7; ++q) std::swap(S.d[q], S.alt[q]);
     c->stats.kernel_launches += 1;
     if (c->timing) {
       // per-launch device time of the fused kernel (the roofline numerator's clock); the
@@ -597,6 +595,11 @@ int do_push(cylgpu_ctx* c) {
     }
   }
   CUDA_TRY(cudaGetLastError());
+  if (need_sort) {
+    c->sorted_valid = true;
+    c->pushes_since_sort = 0;
+    c->stats.n_sorts += 1;
+  }
   c->pushes_since_sort += 1;
   return do_r_min_final(c);
 }
@@ -981,12 +984,24 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortGeom G, const double* __r
                                                    uint32_t* __restrict__ key, uint32_t* __restrict__ rank,
                                                    int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int k = -1;
+  if (i < n) {
+    int cx, cy;
+    stag_cell(G, x[i], y[i], z[i], px[i], py[i], pz[i], cx, cy);
+    k = cell_key(G, cx, cy);
+  }
+  // the list is almost sorted from the previous step, so the lanes of a warp share a few
+  // buckets: one atomic per distinct bucket per warp instead of one per particle
+  const unsigned act = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
-  int cx, cy;
-  stag_cell(G, x[i], y[i], z[i], px[i], py[i], pz[i], cx, cy);
-  const int k = cell_key(G, cx, cy);
+  const unsigned peers = __match_any_sync(act, k);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&count[k], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
   key[i] = (uint32_t)k;
-  rank[i] = (uint32_t)atomicAdd(&count[k], 1);
+  rank[i] = (uint32_t)(base + __popc(peers & ((1u << lane) - 1u)));
 }
 
 // exclusive scan, 3 kernels; SCAN_B elements per block
@@ -1043,6 +1058,15 @@ __global__ void __launch_bounds__(256) k_sort_dest(const int* __restrict__ start
   rank_to_dest[i] = (uint32_t)start[key[i]] + rank_to_dest[i];
 }
 
+// sorted slot -> particle index (the strip push gathers through it; no data moves here)
+__global__ void __launch_bounds__(256) k_sort_src(const int* __restrict__ start, const uint32_t* __restrict__ key,
+                                                  const uint32_t* __restrict__ rank, uint32_t* __restrict__ src,
+                                                  int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  src[(uint32_t)start[key[i]] + rank[i]] = (uint32_t)i;
+}
+
 __global__ void __launch_bounds__(256) k_scatter(const double* __restrict__ src, double* __restrict__ dst,
                                                  const uint32_t* __restrict__ dest, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1050,7 +1074,11 @@ __global__ void __launch_bounds__(256) k_scatter(const double* __restrict__ src,
   dst[dest[i]] = src[i];
 }
 
-int do_sort(cylgpu_ctx* c) {
+// One species.  physical = true moves the particle data into bucket order (7 scatter passes
+// through one rotating spare array); physical = false only builds the permutation `c->perm`
+// (sorted slot -> particle) and the bucket starts, and makes sure the second buffer set
+// exists: the strip push kernel gathers through the permutation and writes the sorted list.
+int do_sort_species(cylgpu_ctx* c, int isp, bool physical) {
   SortGeom G;
   G.ncx = c->g.nx + 2 * CELL_PAD;
   G.ncy = c->g.ny + 2 * CELL_PAD;
@@ -1066,47 +1094,67 @@ int do_sort(cylgpu_ctx* c) {
     CUDA_TRY(cudaMalloc(&c->scan_blocks, (size_t)(nb + 1) * sizeof(int)));
     c->ncell = ncell;
   }
-  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
-    cylgpu::SpeciesState& S = c->species[isp];
-    if (!S.set || S.n == 0 || S.sp.immobile) continue;
-    if (S.n >= (int64_t)0x7FFFFFFFLL) { set_error("more than 2^31-1 particles per species per GPU"); return 3; }
-    TRY(reserve_pscratch(c, S.cap));
-    // per-species cell starts: the strip push kernel reads them after the sort
-    if (!S.cell_start || S.cell_start_n != nscan) {
-      if (S.cell_start) cudaFree(S.cell_start);
-      CUDA_TRY(cudaMalloc(&S.cell_start, (size_t)nscan * sizeof(int)));
-      S.cell_start_n = nscan;
-    }
-    int* count = S.cell_start;
-    uint32_t* key = c->hole_list;   // scratch reuse: hole_list is idle during a sort
-    uint32_t* dest = c->perm;
-    CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)nscan * sizeof(int), c->stream));
-    G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
-    G.dtco2 = C_LIGHT * (c->dt / 2.0);
-    k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
-                                                      count, key, dest, S.n);
-    k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
-    k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
-    k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
-    k_sort_dest<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, dest, S.n);
-    c->stats.kernel_launches += 5;
-    // scatter each component into the spare array, then rotate the pointers (the old
-    // component array becomes the next spare): 8 B of scratch per particle, not 56
-    if (c->ptmp_cap < S.cap) {
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
-      if (c->ptmp) cudaFree(c->ptmp);
-      CUDA_TRY(cudaMalloc(&c->ptmp, (size_t)S.cap * sizeof(double)));
-    }
-    for (int q = 0; q < 7; ++q) {
-      k_scatter<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[q], c->ptmp, dest, S.n);
-      c->stats.kernel_launches += 1;
-      double* t = S.d[q];
-      S.d[q] = c->ptmp;
-      c->ptmp = t;
-    }
-    c->ptmp_cap = S.cap;   // the spare is now one of this species' old arrays
-    CUDA_TRY(cudaGetLastError());
+  cylgpu::SpeciesState& S = c->species[isp];
+  if (!S.set || S.n == 0 || S.sp.immobile) return 0;
+  if (S.n >= (int64_t)0x7FFFFFFFLL) { set_error("more than 2^31-1 particles per species per GPU"); return 3; }
+  TRY(reserve_pscratch(c, S.cap));
+  // per-species bucket starts: the strip push kernel reads them after the sort
+  if (!S.cell_start || S.cell_start_n != nscan) {
+    if (S.cell_start) cudaFree(S.cell_start);
+    CUDA_TRY(cudaMalloc(&S.cell_start, (size_t)nscan * sizeof(int)));
+    S.cell_start_n = nscan;
   }
+  int* count = S.cell_start;
+  uint32_t* key = c->hole_list;    // scratch reuse: the particle_bcs lists are idle during a sort
+  uint32_t* rank = c->lowhole;
+  uint32_t* perm = c->perm;
+  CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)nscan * sizeof(int), c->stream));
+  G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
+  G.dtco2 = C_LIGHT * (c->dt / 2.0);
+  k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                    count, key, rank, S.n);
+  k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
+  k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
+  k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
+  c->stats.kernel_launches += 4;
+  if (!physical) {
+    k_sort_src<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, rank, perm, S.n);
+    c->stats.kernel_launches += 1;
+    if (S.alt_cap < S.cap) {
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      for (int q = 0; q < 7; ++q) {
+        if (S.alt[q]) CUDA_TRY(cudaFree(S.alt[q]));
+        S.alt[q] = nullptr;
+        CUDA_TRY(cudaMalloc(&S.alt[q], (size_t)S.cap * sizeof(double)));
+      }
+      S.alt_cap = S.cap;
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  k_sort_dest<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, rank, S.n);   // rank -> destination
+  c->stats.kernel_launches += 1;
+  // scatter each component into the spare array, then rotate the pointers (the old
+  // component array becomes the next spare): 8 B of scratch per particle, not 56
+  if (c->ptmp_cap < S.cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->ptmp) cudaFree(c->ptmp);
+    CUDA_TRY(cudaMalloc(&c->ptmp, (size_t)S.cap * sizeof(double)));
+  }
+  for (int q = 0; q < 7; ++q) {
+    k_scatter<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[q], c->ptmp, rank, S.n);
+    c->stats.kernel_launches += 1;
+    double* t = S.d[q];
+    S.d[q] = c->ptmp;
+    c->ptmp = t;
+  }
+  c->ptmp_cap = S.cap;   // the spare is now one of this species' old arrays
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int do_sort(cylgpu_ctx* c) {
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) TRY(do_sort_species(c, isp, true));
   c->sorted_valid = true;
   c->pushes_since_sort = 0;
   c->stats.n_sorts += 1;
