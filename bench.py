@@ -12,9 +12,10 @@ N = 1 workload: BASELINE.json configs[1], thermal periodic plasma, m = 0..1, 204
 periodic ring, NCCL send/recv for field halos, additive J ghosts and migrating particles).
 
 Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with all state resident
-in HBM; `e2e` is the same step driven through the C-ABI in host-authoritative mode (particles
-and the nine E/B/J mode arrays uploaded from pinned host memory before and downloaded after
-every step -- the drop-in's "sync every step" slow path).
+in HBM; `e2e` is the same step driven through the C-ABI in host-authoritative mode (the particle
+list and the nine E/B/J mode arrays live in pinned host memory, are uploaded before and downloaded
+after every step; cylgpu_push_host streams the list through the GPU in chunks -- the drop-in's
+"host owns the particles" path).
 """
 import argparse
 import json
@@ -372,23 +373,31 @@ def run_ours(args, wl_name, wl):
         npart = slab.particle_count(0)
         nn = C.c_int64()
         slab._ck(slab.L.cylgpu_download_particles(slab.h, 0, hp.shape[0], hp.ctypes.data, C.byref(nn)))
-        e2e_steps = max(1, min(args.steps, 3))
+        e2e_steps = max(1, min(args.steps, 5))
         h2d = d2h = 0
+        # from here on the particle list lives in the pinned host array and is streamed through
+        # the GPU by cylgpu_push_host (upload | push + deposit + particle_bcs | download overlap)
+        slab.attach_host_lists([hp], [int(nn.value)])
+        slab.L.cylgpu_upload_particles(slab.h, 0, 0, hp.ctypes.data)   # nothing stays on the device
+        nfield_bytes = len(names) * host_f[names[0]].numel() * 16
+
+        def e2e_step():
+            n_before = slab.host_counts[0]
+            for nm in names:
+                slab._ck(slab.L.cylgpu_upload_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
+            slab.step_once()
+            for nm in names:
+                slab._ck(slab.L.cylgpu_download_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
+            return n_before, slab.host_counts[0]
+        e2e_step()   # warm-up: staging buffers, streams
         barrier()
         t0 = time.perf_counter()
         psteps = 0
         for _ in range(e2e_steps):
-            npart = int(nn.value)
-            slab._ck(slab.L.cylgpu_upload_particles(slab.h, 0, npart, hp.ctypes.data))
-            for nm in names:
-                slab._ck(slab.L.cylgpu_upload_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
-            h2d = npart * 56 + len(names) * host_f[names[0]].numel() * 16
-            slab.step_once()
-            psteps += npart
-            for nm in names:
-                slab._ck(slab.L.cylgpu_download_field(slab.h, FIELD_NAMES.index(nm), host_f[nm].numpy().ctypes.data))
-            slab._ck(slab.L.cylgpu_download_particles(slab.h, 0, hp.shape[0], hp.ctypes.data, C.byref(nn)))
-            d2h = int(nn.value) * 56 + len(names) * host_f[names[0]].numel() * 16
+            n_before, n_after = e2e_step()
+            psteps += n_before
+            h2d = n_before * 56 + nfield_bytes
+            d2h = n_after * 56 + nfield_bytes
         barrier()
         w2 = time.perf_counter() - t0
         tt = torch.tensor([w2, float(psteps)], dtype=torch.float64, device="cuda")
@@ -398,7 +407,9 @@ def run_ours(args, wl_name, wl):
             w2, psteps = float(a[0]), float(b[1])
         line["e2e"] = {"value": psteps / w2, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d),
                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
-                       "what": "upload particles + 9 E/B/J mode arrays from pinned host, one full step, download them"}
+                       "what": "particle list and the 9 E/B/J mode arrays live in pinned host memory: every step uploads "
+                               "them, runs the full step and downloads them (cylgpu_push_host streams the list in "
+                               "chunks, both PCIe directions busy)"}
 
     if rank == 0 and world == 1 and not args.no_cpu:
         try:

@@ -70,6 +70,9 @@ SYMBOLS = {
     "cylgpu_particle_device_ptr": (C.c_void_p, [H, C.c_int, C.c_int]),
     "cylgpu_fields_half": (C.c_int, [H]),
     "cylgpu_push": (C.c_int, [H]),
+    "cylgpu_push_host": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                   C.POINTER(C.c_int64)]),
+    "cylgpu_set_host_chunk": (C.c_int, [H, C.c_int64]),
     "cylgpu_current_finish": (C.c_int, [H]),
     "cylgpu_fields_final": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cylgpu_window_shift": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), _DP]),

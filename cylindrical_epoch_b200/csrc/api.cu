@@ -128,6 +128,18 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1);
+  for (int k = 0; k < 3; ++k) {
+    cudaFree(c->hs.in[k]);
+    if (c->hs.ev_up[k]) cudaEventDestroy(c->hs.ev_up[k]);
+    if (c->hs.ev_unpacked[k]) cudaEventDestroy(c->hs.ev_unpacked[k]);
+  }
+  for (int k = 0; k < 2; ++k) {
+    cudaFree(c->hs.out[k]);
+    if (c->hs.ev_packed[k]) cudaEventDestroy(c->hs.ev_packed[k]);
+    if (c->hs.ev_down[k]) cudaEventDestroy(c->hs.ev_down[k]);
+  }
+  if (c->hs.up) cudaStreamDestroy(c->hs.up);
+  if (c->hs.down) cudaStreamDestroy(c->hs.down);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return 0;
@@ -354,6 +366,21 @@ int cylgpu_push(cylgpu_handle c) {
   }
   PhaseTimer t(c, &c->stats.ms_bcs);
   return do_particle_bcs(c);
+}
+
+// the same for particle lists that stay in host memory (streamed through the GPU in chunks)
+int cylgpu_push_host(cylgpu_handle c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
+                     int64_t* n_out) {
+  TRY(check_handle(c));
+  if (!n_in || !host_aos || !capacity || !n_out) { set_error("push_host: null argument"); return 2; }
+  PhaseTimer t(c, &c->stats.ms_push);
+  return do_push_host(c, n_in, host_aos, capacity, n_out);
+}
+int cylgpu_set_host_chunk(cylgpu_handle c, int64_t particles) {
+  TRY(check_handle(c));
+  if (particles < 1024 || particles > (int64_t)1 << 30) { set_error("host chunk must be in [1024, 2^30] particles"); return 2; }
+  c->host_chunk = particles;
+  return 0;
 }
 
 int cylgpu_current_finish(cylgpu_handle c) {

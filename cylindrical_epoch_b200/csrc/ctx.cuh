@@ -82,6 +82,15 @@ struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
 };
 
+// streams, events and staging of the host-resident particle path (do_push_host)
+struct HostStream {
+  cudaStream_t up = nullptr, down = nullptr;
+  cudaEvent_t ev_up[3] = {0, 0, 0}, ev_unpacked[3] = {0, 0, 0}, ev_packed[2] = {0, 0}, ev_down[2] = {0, 0};
+  double* in[3] = {0, 0, 0};    // AoS chunks on their way in
+  double* out[2] = {0, 0};      // AoS chunks on their way out
+  int64_t cap = 0;              // particles per staging buffer
+};
+
 }  // namespace cylgpu
 
 struct cylgpu_ctx {
@@ -125,6 +134,8 @@ struct cylgpu_ctx {
   double* d_energy = nullptr;
 
   cylgpu::Transport* tr = nullptr;
+  cylgpu::HostStream hs;
+  int64_t host_chunk = 1 << 21;   // particles per chunk of the host-resident path (117 MB)
 
   int sort_interval = 1;
   // 0 per-particle REDs, 1 warp-window shuffle deposit, 2 strip CTAs + shared-memory field patch,
@@ -157,6 +168,8 @@ int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip
 // particles.cu
 int do_push(cylgpu_ctx* c);
 int do_particle_bcs(cylgpu_ctx* c);
+int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
+                 int64_t* n_out);
 int do_sort(cylgpu_ctx* c);
 int do_remove_behind(cylgpu_ctx* c);
 int do_energy(cylgpu_ctx* c, double* out2);

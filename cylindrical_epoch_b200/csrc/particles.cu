@@ -511,90 +511,99 @@ __global__ void __launch_bounds__(256) k_copy_zero(cplx* __restrict__ old0, cplx
 int do_sort(cylgpu_ctx* c);
 int do_sort_species(cylgpu_ctx* c, int isp, bool physical);
 
-int do_push(cylgpu_ctx* c) {
+// particles.F90:163-169: j*_old = j*; j* = 0 (one fused streaming pass)
+static int push_prologue(cylgpu_ctx* c) {
   const Geom& g = c->g;
   const size_t n = g.plane * g.M;
-  // particles.F90:163-169: j*_old = j*; j* = 0 (one fused streaming pass)
-  {
-    const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 8);
-    k_copy_zero<<<blocks, 256, 0, c->stream>>>(c->f[CYLGPU_JXM_OLD], c->f[CYLGPU_JRM_OLD], c->f[CYLGPU_JTM_OLD],
-                                               c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], n);
-    c->stats.kernel_launches += 1;
-  }
-  const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)148 * 8);
+  k_copy_zero<<<blocks, 256, 0, c->stream>>>(c->f[CYLGPU_JXM_OLD], c->f[CYLGPU_JRM_OLD], c->f[CYLGPU_JTM_OLD],
+                                             c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], n);
+  c->stats.kernel_launches += 1;
+  return 0;
+}
+
+// particles.F90:146-734 for the S.n particles of one species currently in S.d: (sort,) gather,
+// Boris, store, deposit.  `time_kernel` brackets the fused kernel with events and a host sync.
+static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel) {
+  const Geom& g = c->g;
   // strip kernels read through the sort permutation and write the second buffer set: the sort
   // then only has to build the permutation (no scatter passes)
   const bool strips = c->push_variant >= 2 && c->sort_interval == 1;
   const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
   const double dt = c->dt;
-  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
-    cylgpu::SpeciesState& S = c->species[isp];
-    if (!S.set || S.sp.immobile || S.n == 0) continue;
-    if (need_sort) TRY(do_sort_species(c, isp, /*physical=*/!strips));
-    PushConst P;
-    P.g = g;
-    P.exm = c->f[CYLGPU_EXM]; P.erm = c->f[CYLGPU_ERM]; P.etm = c->f[CYLGPU_ETM];
-    P.bxm = c->f[CYLGPU_BXM]; P.brm = c->f[CYLGPU_BRM]; P.btm = c->f[CYLGPU_BTM];
-    P.jx = (double*)c->f[CYLGPU_JXM]; P.jr = (double*)c->f[CYLGPU_JRM]; P.jt = (double*)c->f[CYLGPU_JTM];
-    P.tab = c->tables; P.ntab = c->ntab;
-    P.x_grid_min_local = c->x_grid_min_local;
-    P.y_grid_min_local = c->cfg.y_grid_min_local;
-    P.idx = 1.0 / c->cfg.dx; P.idy = 1.0 / c->cfg.dy; P.idt = 1.0 / dt;
-    const double dto2 = dt / 2.0;
-    P.dtco2 = C_LIGHT * dto2;
-    const double dtfac = 0.5 * dt * fac;
-    P.part_mc = C_LIGHT * S.sp.mass;
-    P.ipart_mc = 1.0 / P.part_mc;
-    P.cmratio = S.sp.charge * dtfac * P.ipart_mc;
-    P.ccmratio = C_LIGHT * P.cmratio;
-    P.q_fac = S.sp.charge * fac;
-    P.deposit = S.sp.zero_current ? 0 : 1;
-    const int64_t nb = (S.n + 127) / 128;
-    if (c->timing) cudaEventRecord(c->evk0, c->stream);
-    const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;
-    const int nstrip_x = (ncx + STRIP_C - 1) / STRIP_C;
-    SoaIn pin; SoaOut pout;
-    for (int q = 0; q < 7; ++q) { pin.d[q] = S.d[q]; pout.d[q] = S.alt[q]; }
+  cylgpu::SpeciesState& S = c->species[isp];
+  if (!S.set || S.sp.immobile || S.n == 0) return 0;
+  if (need_sort) TRY(do_sort_species(c, isp, /*physical=*/!strips));
+  PushConst P;
+  P.g = g;
+  P.exm = c->f[CYLGPU_EXM]; P.erm = c->f[CYLGPU_ERM]; P.etm = c->f[CYLGPU_ETM];
+  P.bxm = c->f[CYLGPU_BXM]; P.brm = c->f[CYLGPU_BRM]; P.btm = c->f[CYLGPU_BTM];
+  P.jx = (double*)c->f[CYLGPU_JXM]; P.jr = (double*)c->f[CYLGPU_JRM]; P.jt = (double*)c->f[CYLGPU_JTM];
+  P.tab = c->tables; P.ntab = c->ntab;
+  P.x_grid_min_local = c->x_grid_min_local;
+  P.y_grid_min_local = c->cfg.y_grid_min_local;
+  P.idx = 1.0 / c->cfg.dx; P.idy = 1.0 / c->cfg.dy; P.idt = 1.0 / dt;
+  const double dto2 = dt / 2.0;
+  P.dtco2 = C_LIGHT * dto2;
+  const double dtfac = 0.5 * dt * fac;
+  P.part_mc = C_LIGHT * S.sp.mass;
+  P.ipart_mc = 1.0 / P.part_mc;
+  P.cmratio = S.sp.charge * dtfac * P.ipart_mc;
+  P.ccmratio = C_LIGHT * P.cmratio;
+  P.q_fac = S.sp.charge * fac;
+  P.deposit = S.sp.zero_current ? 0 : 1;
+  const int64_t nb = (S.n + 127) / 128;
+  if (time_kernel) cudaEventRecord(c->evk0, c->stream);
+  const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;
+  const int nstrip_x = (ncx + STRIP_C - 1) / STRIP_C;
+  SoaIn pin; SoaOut pout;
+  for (int q = 0; q < 7; ++q) { pin.d[q] = S.d[q]; pout.d[q] = S.alt[q]; }
 #define PUSH_ARGS P, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5], S.d[6], S.n
 #define LAUNCH_STRIP(MM, MMA)                                                                              \
-    do {                                                                                                   \
-      const size_t shb = strip_smem_bytes<MM>(MMA);                                                        \
-      CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
-      k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x); \
-    } while (0)
+  do {                                                                                                     \
+    const size_t shb = strip_smem_bytes<MM>(MMA);                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
+    k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x); \
+  } while (0)
 #define LAUNCH_M(MM)                                                                                       \
-    do {                                                                                                   \
-      if (strips && c->push_variant == 3) LAUNCH_STRIP(MM, true);                                          \
-      else if (strips) LAUNCH_STRIP(MM, false);                                                            \
-      else if (c->push_variant >= 1) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);       \
-      else k_push_v0<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);                                 \
-    } while (0)
-    switch (g.M) {
-      case 1: LAUNCH_M(1); break;
-      case 2: LAUNCH_M(2); break;
-      case 3: LAUNCH_M(3); break;
-      case 4: LAUNCH_M(4); break;
-      case 5: LAUNCH_M(5); break;
-      case 6: LAUNCH_M(6); break;
-      default: set_error("n_mode = %d not supported by the push kernels (1..6)", g.M); return 2;
-    }
+  do {                                                                                                     \
+    if (strips && c->push_variant == 3) LAUNCH_STRIP(MM, true);                                            \
+    else if (strips) LAUNCH_STRIP(MM, false);                                                              \
+    else if (c->push_variant >= 1) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);         \
+    else k_push_v0<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);                                   \
+  } while (0)
+  switch (g.M) {
+    case 1: LAUNCH_M(1); break;
+    case 2: LAUNCH_M(2); break;
+    case 3: LAUNCH_M(3); break;
+    case 4: LAUNCH_M(4); break;
+    case 5: LAUNCH_M(5); break;
+    case 6: LAUNCH_M(6); break;
+    default: set_error("n_mode = %d not supported by the push kernels (1..6)", g.M); return 2;
+  }
 #undef LAUNCH_M
 #undef LAUNCH_STRIP
 #undef PUSH_ARGS
-    if (strips) for (int q = 0; q < 7; ++q) std::swap(S.d[q], S.alt[q]);
-    c->stats.kernel_launches += 1;
-    if (c->timing) {
-      // per-launch device time of the fused kernel (the roofline numerator's clock); the
-      // host sync is free here: particle_bcs needs one right after the push anyway
-      cudaEventRecord(c->evk1, c->stream);
-      cudaEventSynchronize(c->evk1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->evk0, c->evk1);
-      c->stats.ms_push_kernel += (double)ms;
-      c->stats.n_push_kernel += 1;
-    }
+  if (strips) for (int q = 0; q < 7; ++q) std::swap(S.d[q], S.alt[q]);
+  c->stats.kernel_launches += 1;
+  if (time_kernel) {
+    // per-launch device time of the fused kernel (the roofline numerator's clock); the
+    // host sync is free here: particle_bcs needs one right after the push anyway
+    cudaEventRecord(c->evk1, c->stream);
+    cudaEventSynchronize(c->evk1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->evk0, c->evk1);
+    c->stats.ms_push_kernel += (double)ms;
+    c->stats.n_push_kernel += 1;
   }
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int do_push(cylgpu_ctx* c) {
+  TRY(push_prologue(c));
+  const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) TRY(push_species(c, isp, need_sort, c->timing));
   if (need_sort) {
     c->sorted_valid = true;
     c->pushes_since_sort = 0;
@@ -810,13 +819,14 @@ static int ensure_dbuf(double** p, int64_t* cap, int64_t need, cudaStream_t st) 
 // compaction after flags + counts are known on the host: fills the holes below the new
 // count with the keepers above it (order is not preserved; the reference's list order only
 // matters for floating-point summation order)
-static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64_t nleft, int64_t nright,
+static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64_t off_l, int64_t off_r,
                    unsigned long long* cnt2) {
   Soa s;
   for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
   const int64_t n = S.n, n_new = n - nholes;
   CUDA_TRY(cudaMemsetAsync(cnt2, 0, 8 * sizeof(unsigned long long), c->stream));
-  k_collect<<<nblk(n, 256), 256, 0, c->stream>>>(s, c->flag, c->hole_list, c->psend_l, c->psend_r, cnt2, n);
+  k_collect<<<nblk(n, 256), 256, 0, c->stream>>>(s, c->flag, c->hole_list, c->psend_l + 7 * off_l, c->psend_r + 7 * off_r,
+                                                 cnt2, n);
   if (n_new > 0 && nholes > 0) {
     k_tail_keepers<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->flag, n_new, n, c->hightail, cnt2);
     k_low_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->hole_list, nholes, n_new, c->lowhole, cnt2);
@@ -826,11 +836,10 @@ static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64
   c->stats.kernel_launches += 1;
   CUDA_TRY(cudaGetLastError());
   S.n = n_new;
-  (void)nleft; (void)nright;
   return 0;
 }
 
-int do_particle_bcs(cylgpu_ctx* c) {
+static BcsConst make_bcs_const(cylgpu_ctx* c) {
   BcsConst B;
   const double dx = c->cfg.dx, dy = c->cfg.dy;
   B.x_min = c->x_min; B.x_max = c->x_max;
@@ -844,74 +853,245 @@ int do_particle_bcs(cylgpu_ctx* c) {
   B.x_shift = B.x_max - B.x_min;   // length_x
   B.x_min_boundary = c->cfg.x_min_boundary;
   B.x_max_boundary = c->cfg.x_max_boundary;
-  c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  return B;
+}
 
+// grow a device buffer of doubles, keeping its first `keep` entries
+static int grow_dbuf_keep(double** p, int64_t* cap, int64_t need, int64_t keep, cudaStream_t st) {
+  if (need <= *cap) return 0;
+  const int64_t nc = (int64_t)(need * 1.5) + 4096;
+  double* q = nullptr;
+  CUDA_TRY(cudaMalloc(&q, (size_t)nc * sizeof(double)));
+  if (*p && keep > 0) CUDA_TRY(cudaMemcpyAsync(q, *p, (size_t)keep * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (*p) cudaFree(*p);
+  *p = q;
+  *cap = nc;
+  return 0;
+}
+
+// boundary.F90:1541-1865 for the S.n particles of one species in S.d: boundary conditions,
+// classification, removal of the leavers (hole filling) and packing of the migrants behind the
+// `off_l` / `off_r` particles already waiting in psend_l / psend_r.  One host sync (the counts).
+static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off_l, int64_t off_r, int64_t* nleft_out,
+                                 int64_t* nright_out) {
   unsigned long long* cnt = c->counters;        // 8 for classify
   unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
+  cylgpu::SpeciesState& S = c->species[isp];
+  for (int k = 0; k < 4; ++k) B.bc[k] = S.sp.bc_particle[k];
+  TRY(reserve_pscratch(c, S.n));
+  CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+  if (S.n > 0) {
+    k_pbcs_classify<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                          c->flag, cnt, S.n);
+    c->stats.kernel_launches += 1;
+  }
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
+  const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
+  const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
+  const int64_t ngone = (int64_t)c->h_counters[CNT_GONE];
+  c->stats.n_sent_left += nleft;
+  c->stats.n_sent_right += nright;
+  c->stats.n_removed += ngone;
+  TRY(grow_dbuf_keep(&c->psend_l, &c->psend_l_cap, 7 * (off_l + nleft), 7 * off_l, c->stream));
+  TRY(grow_dbuf_keep(&c->psend_r, &c->psend_r_cap, 7 * (off_r + nright), 7 * off_r, c->stream));
+  if (nholes > 0) TRY(compact(c, S, nholes, off_l, off_r, cnt2));
+  *nleft_out = nleft;
+  *nright_out = nright;
+  return 0;
+}
+
+// partlist_sendrecv (count, then payload), boundary.F90:1867-1877.  The received particles end
+// up in c->precv as [from_l block][from_r block] in pack_particle order.
+static int pbcs_exchange(cylgpu_ctx* c, int64_t nleft, int64_t nright, int64_t* from_l_out, int64_t* from_r_out) {
   unsigned long long* xc = c->counters + 16;    // [0..1] send counts, [2..3] recv counts
+  const bool has_l = c->left >= 0, has_r = c->right >= 0;
+  *from_l_out = *from_r_out = 0;
+  if (!has_l && !has_r) return 0;
+  c->h_counters[16] = (unsigned long long)nleft;
+  c->h_counters[17] = (unsigned long long)nright;
+  c->h_counters[18] = c->h_counters[19] = 0;
+  CUDA_TRY(cudaMemcpyAsync(xc, c->h_counters + 16, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                           c->stream));
+  TRY(transport_sendrecv(c, has_l ? xc + 0 : nullptr, has_l ? 8 : 0, has_l ? xc + 2 : nullptr, has_l ? 8 : 0,
+                         has_r ? xc + 1 : nullptr, has_r ? 8 : 0, has_r ? xc + 3 : nullptr, has_r ? 8 : 0));
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters + 16, xc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int64_t from_l = has_l ? (int64_t)c->h_counters[18] : 0;
+  const int64_t from_r = has_r ? (int64_t)c->h_counters[19] : 0;
+  TRY(ensure_dbuf(&c->precv, &c->precv_cap, 7 * (from_l + from_r), c->stream));
+  double* rl = c->precv;
+  double* rr = c->precv + 7 * from_l;
+  TRY(transport_sendrecv(c, c->psend_l, has_l ? 7 * nleft * sizeof(double) : 0, rl, 7 * from_l * sizeof(double),
+                         c->psend_r, has_r ? 7 * nright * sizeof(double) : 0, rr,
+                         7 * from_r * sizeof(double)));
+  *from_l_out = from_l;
+  *from_r_out = from_r;
+  return 0;
+}
+
+int do_particle_bcs(cylgpu_ctx* c) {
+  const BcsConst B = make_bcs_const(c);
+  c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     cylgpu::SpeciesState& S = c->species[isp];
     if (!S.set) continue;
-    for (int k = 0; k < 4; ++k) B.bc[k] = S.sp.bc_particle[k];
-    TRY(reserve_pscratch(c, S.n));
-    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
-    if (S.n > 0) {
-      k_pbcs_classify<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
-                                                            c->flag, cnt, S.n);
-      c->stats.kernel_launches += 1;
-    }
-    CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                             c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
-    const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
-    const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
-    const int64_t ngone = (int64_t)c->h_counters[CNT_GONE];
-    c->stats.n_sent_left += nleft;
-    c->stats.n_sent_right += nright;
-    c->stats.n_removed += ngone;
-    TRY(ensure_dbuf(&c->psend_l, &c->psend_l_cap, 7 * nleft, c->stream));
-    TRY(ensure_dbuf(&c->psend_r, &c->psend_r_cap, 7 * nright, c->stream));
-    if (nholes > 0) TRY(compact(c, S, nholes, nleft, nright, cnt2));
-
-    // ---- exchange: partlist_sendrecv (count, then payload), boundary.F90:1867-1877 ----
-    const bool has_l = c->left >= 0, has_r = c->right >= 0;
-    if (has_l || has_r) {
-      c->h_counters[16] = (unsigned long long)nleft;
-      c->h_counters[17] = (unsigned long long)nright;
-      c->h_counters[18] = c->h_counters[19] = 0;
-      CUDA_TRY(cudaMemcpyAsync(xc, c->h_counters + 16, 4 * sizeof(unsigned long long), cudaMemcpyHostToDevice,
-                               c->stream));
-      TRY(transport_sendrecv(c, has_l ? xc + 0 : nullptr, has_l ? 8 : 0, has_l ? xc + 2 : nullptr, has_l ? 8 : 0,
-                             has_r ? xc + 1 : nullptr, has_r ? 8 : 0, has_r ? xc + 3 : nullptr, has_r ? 8 : 0));
-      CUDA_TRY(cudaMemcpyAsync(c->h_counters + 16, xc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                               c->stream));
-      CUDA_TRY(cudaStreamSynchronize(c->stream));
-      const int64_t from_l = has_l ? (int64_t)c->h_counters[18] : 0;
-      const int64_t from_r = has_r ? (int64_t)c->h_counters[19] : 0;
-      TRY(ensure_dbuf(&c->precv, &c->precv_cap, 7 * (from_l + from_r), c->stream));
-      double* rl = c->precv;
-      double* rr = c->precv + 7 * from_l;
-      TRY(transport_sendrecv(c, c->psend_l, has_l ? 7 * nleft * sizeof(double) : 0, rl, 7 * from_l * sizeof(double),
-                             c->psend_r, has_r ? 7 * nright * sizeof(double) : 0, rr,
-                             7 * from_r * sizeof(double)));
-      // the reference receives from the right neighbour first (ix = -1 iteration), then left
-      const int64_t nrecv = from_l + from_r;
-      if (nrecv > 0) {
-        TRY(reserve_particles(c, isp, S.n + nrecv));
-        Soa s;
-        for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
-        if (from_r > 0) k_unpack<<<nblk(from_r, 256), 256, 0, c->stream>>>(s, S.n, rr, from_r);
-        if (from_l > 0) k_unpack<<<nblk(from_l, 256), 256, 0, c->stream>>>(s, S.n + from_r, rl, from_l);
-        c->stats.kernel_launches += (from_r > 0) + (from_l > 0);
-        S.n += nrecv;
-        c->stats.n_recv += nrecv;
-      }
+    int64_t nleft = 0, nright = 0, from_l = 0, from_r = 0;
+    TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright));
+    TRY(pbcs_exchange(c, nleft, nright, &from_l, &from_r));
+    // the reference receives from the right neighbour first (ix = -1 iteration), then left
+    const int64_t nrecv = from_l + from_r;
+    if (nrecv > 0) {
+      TRY(reserve_particles(c, isp, S.n + nrecv));
+      Soa s;
+      for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+      const double* rl = c->precv;
+      const double* rr = c->precv + 7 * from_l;
+      if (from_r > 0) k_unpack<<<nblk(from_r, 256), 256, 0, c->stream>>>(s, S.n, rr, from_r);
+      if (from_l > 0) k_unpack<<<nblk(from_l, 256), 256, 0, c->stream>>>(s, S.n + from_r, rl, from_l);
+      c->stats.kernel_launches += (from_r > 0) + (from_l > 0);
+      S.n += nrecv;
+      c->stats.n_recv += nrecv;
       CUDA_TRY(cudaGetLastError());
     }
     c->stats.n_particles[isp] = S.n;
   }
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// push_particles + particle_bcs for particle lists that live in HOST memory (the reference's
+// linked lists flattened in pack_particle order, partlist.F90:414-428): the list is streamed
+// through the GPU in chunks on three streams -- upload chunk k+2 | sort + push + deposit +
+// boundary conditions of chunk k | download chunk k-1 -- so that the step runs at the PCIe
+// rate (both directions busy) instead of upload + compute + download in sequence, and a
+// species never has to fit in HBM.  The survivors are written back in place (compacted; the
+// output offset never overtakes the input offset), the migrants of all chunks are exchanged
+// once at the end and appended.  J accumulates over the chunks exactly as over one list.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_all(Soa s, double* __restrict__ aos, int64_t n) {
+  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+#pragma unroll
+  for (int q = 0; q < 7; ++q) aos[7 * k + q] = s.d[q][k];
+}
+
+static int host_stream_setup(cylgpu_ctx* c, int64_t chunk) {
+  cylgpu::HostStream& H = c->hs;
+  if (!H.up) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&H.up, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&H.down, cudaStreamNonBlocking));
+    for (int k = 0; k < 3; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&H.ev_up[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&H.ev_unpacked[k], cudaEventDisableTiming));
+    }
+    for (int k = 0; k < 2; ++k) {
+      CUDA_TRY(cudaEventCreateWithFlags(&H.ev_packed[k], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&H.ev_down[k], cudaEventDisableTiming));
+    }
+  }
+  if (H.cap < chunk) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int k = 0; k < 3; ++k) { if (H.in[k]) cudaFree(H.in[k]); H.in[k] = nullptr; }
+    for (int k = 0; k < 2; ++k) { if (H.out[k]) cudaFree(H.out[k]); H.out[k] = nullptr; }
+    for (int k = 0; k < 3; ++k) CUDA_TRY(cudaMalloc(&H.in[k], (size_t)chunk * 7 * sizeof(double)));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaMalloc(&H.out[k], (size_t)chunk * 7 * sizeof(double)));
+    H.cap = chunk;
+  }
+  return 0;
+}
+
+int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
+                 int64_t* n_out) {
+  cylgpu::HostStream& H = c->hs;
+  const int64_t chunk = c->host_chunk;
+  TRY(host_stream_setup(c, chunk));
+  const BcsConst B = make_bcs_const(c);
+  c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  TRY(push_prologue(c));
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set) continue;
+    if (!host_aos[isp]) {   // device-resident species: the ordinary path
+      const bool need_sort = c->sort_interval > 0;
+      TRY(push_species(c, isp, need_sort, false));
+      continue;
+    }
+    const int64_t n = n_in[isp];
+    if (n < 0 || n > capacity[isp]) { set_error("push_host: bad particle count for species %d", isp); return 2; }
+    double* host = host_aos[isp];
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    TRY(reserve_particles(c, isp, std::min<int64_t>(chunk, std::max<int64_t>(n, 1))));
+    // everything queued on the library stream so far (fields, J prologue) precedes the chunks
+    int64_t out_off = 0, acc_l = 0, acc_r = 0;
+    auto chunk_len = [&](int64_t k) { return std::min<int64_t>(chunk, n - k * chunk); };
+    auto enqueue_upload = [&](int64_t k) -> int {
+      const int b = (int)(k % 3);
+      if (k >= 3) CUDA_TRY(cudaStreamWaitEvent(H.up, H.ev_unpacked[b], 0));   // buffer consumed by chunk k-3
+      CUDA_TRY(cudaMemcpyAsync(H.in[b], host + 7 * k * chunk, (size_t)chunk_len(k) * 7 * sizeof(double),
+                               cudaMemcpyHostToDevice, H.up));
+      CUDA_TRY(cudaEventRecord(H.ev_up[b], H.up));
+      return 0;
+    };
+    for (int64_t k = 0; k < std::min<int64_t>(2, nchunks); ++k) TRY(enqueue_upload(k));
+    for (int64_t k = 0; k < nchunks; ++k) {
+      if (k + 2 < nchunks) TRY(enqueue_upload(k + 2));
+      const int b = (int)(k % 3), ob = (int)(k % 2);
+      const int64_t m = chunk_len(k);
+      CUDA_TRY(cudaStreamWaitEvent(c->stream, H.ev_up[b], 0));
+      Soa s;
+      for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+      k_unpack<<<nblk(m, 256), 256, 0, c->stream>>>(s, 0, H.in[b], m);
+      CUDA_TRY(cudaEventRecord(H.ev_unpacked[b], c->stream));
+      c->stats.kernel_launches += 1;
+      S.n = m;
+      if (!S.sp.immobile) TRY(push_species(c, isp, c->sort_interval > 0, false));
+      int64_t nleft = 0, nright = 0;
+      TRY(pbcs_classify_compact(c, isp, B, acc_l, acc_r, &nleft, &nright));   // host sync: counts
+      acc_l += nleft;
+      acc_r += nright;
+      const int64_t kept = S.n;
+      if (kept > 0) {
+        if (k >= 2) CUDA_TRY(cudaStreamWaitEvent(c->stream, H.ev_down[ob], 0));   // staging buffer free again
+        for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+        k_pack_all<<<nblk(kept, 256), 256, 0, c->stream>>>(s, H.out[ob], kept);
+        c->stats.kernel_launches += 1;
+        CUDA_TRY(cudaEventRecord(H.ev_packed[ob], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(H.down, H.ev_packed[ob], 0));
+        CUDA_TRY(cudaMemcpyAsync(host + 7 * out_off, H.out[ob], (size_t)kept * 7 * sizeof(double),
+                                 cudaMemcpyDeviceToHost, H.down));
+        CUDA_TRY(cudaEventRecord(H.ev_down[ob], H.down));
+        out_off += kept;
+      }
+    }
+    S.n = 0;
+    // one exchange for the migrants of all chunks; arrivals are appended right-then-left
+    int64_t from_l = 0, from_r = 0;
+    TRY(pbcs_exchange(c, acc_l, acc_r, &from_l, &from_r));
+    const int64_t nrecv = from_l + from_r;
+    if (out_off + nrecv > capacity[isp]) {
+      set_error("push_host: species %d needs room for %lld particles, capacity %lld", isp,
+                (long long)(out_off + nrecv), (long long)capacity[isp]);
+      return 2;
+    }
+    CUDA_TRY(cudaStreamSynchronize(H.down));
+    if (from_r > 0)
+      CUDA_TRY(cudaMemcpyAsync(host + 7 * out_off, c->precv + 7 * from_l, (size_t)from_r * 7 * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+    if (from_l > 0)
+      CUDA_TRY(cudaMemcpyAsync(host + 7 * (out_off + from_r), c->precv, (size_t)from_l * 7 * sizeof(double),
+                               cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    c->stats.n_recv += nrecv;
+    n_out[isp] = out_off + nrecv;
+    c->stats.n_particles[isp] = 0;
+  }
+  c->sorted_valid = false;
+  return do_r_min_final(c);
 }
 
 int do_remove_behind(cylgpu_ctx* c) {

@@ -109,6 +109,8 @@ class Slab:
         self.window_shift_fraction = 0.0
         self.window_shifts_total = 0
         self.insert_fn = insert_fn
+        self.host_lists = None
+        self.host_counts = None
         self._keep = []   # ctypes objects that must outlive the handle
 
         cfg = _lib.Config()
@@ -275,7 +277,38 @@ class Slab:
         self._ck(self.L.cylgpu_fields_half(self.h))
 
     def push_particles(self):                 # particles.F90:28-734
+        if self.host_lists is not None:       # particle lists stay on the host (streamed push)
+            self.host_counts = self.push_particles_host(self.host_lists, self.host_counts)
+            return
         self._ck(self.L.cylgpu_push(self.h))
+
+    def attach_host_lists(self, lists, counts):
+        """From now on the species whose entry in `lists` is an (capacity, 7) float64 array live
+        in host memory: push_particles streams them through the GPU (cylgpu_push_host)."""
+        self.host_lists = list(lists)
+        self.host_counts = [int(c) for c in counts]
+
+    def push_particles_host(self, lists, counts):
+        """push_particles + particle_bcs for particle lists that stay in host memory.
+        lists[isp]: writable C-contiguous float64 array (capacity, 7) in pack_particle order
+        (or None: species isp is device-resident); counts[isp]: particles in it.  Survivors
+        and arrivals are written back in place; returns the new counts."""
+        nsp = len(self.species)
+        n_in = (C.c_int64 * nsp)(*[int(c) for c in counts])
+        cap = (C.c_int64 * nsp)()
+        ptr = (C.c_void_p * nsp)()
+        for i, a in enumerate(lists):
+            if a is None:
+                continue
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.flags.writeable and a.shape[1] == 7
+            cap[i] = a.shape[0]
+            ptr[i] = a.ctypes.data
+        n_out = (C.c_int64 * nsp)(*[int(c) for c in counts])
+        self._ck(self.L.cylgpu_push_host(self.h, n_in, ptr, cap, n_out))
+        return [int(v) for v in n_out]
+
+    def set_host_chunk(self, particles):
+        self._ck(self.L.cylgpu_set_host_chunk(self.h, int(particles)))
 
     def push_particles_no_bcs(self):
         self._ck(self.L.cylgpu_push_no_bcs(self.h))

@@ -166,6 +166,19 @@ int cylgpu_fields_half(cylgpu_handle h);
 /* particles.F90:28-734 push_particles, including current_bcs_r_min_final
  * (boundary.F90:1909) and particle_bcs (boundary.F90:1541) */
 int cylgpu_push(cylgpu_handle h);
+/* The same push_particles + particle_bcs for species whose particle list STAYS IN HOST MEMORY
+ * (the reference's linked lists, shared_data.F90:159-171, flattened in pack_particle order,
+ * partlist.F90:414-428: x y z px py pz w).  host_aos[isp] holds n_in[isp] particles and has
+ * room for capacity[isp]; the list is streamed through the GPU in chunks (upload | sort + push +
+ * deposit + boundary conditions | download run concurrently on three streams), the survivors
+ * are written back in place, compacted, followed by the particles received from the
+ * neighbours; n_out[isp] is the new count.  A NULL host_aos[isp] leaves species isp to its
+ * device-resident list (pushed as by cylgpu_push, WITHOUT particle_bcs).  Use pinned memory
+ * (cudaHostRegister on the Fortran array) for full PCIe rate. */
+int cylgpu_push_host(cylgpu_handle h, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
+                     int64_t* n_out);
+/* particles per chunk of cylgpu_push_host (default 2^21) */
+int cylgpu_set_host_chunk(cylgpu_handle h, int64_t particles);
 /* current_smooth.F90:29-45 current_finish (smoothing off) */
 int cylgpu_current_finish(cylgpu_handle h);
 /* fields.f90:341-353 update_eb_fields_final.  source1/source2 are the host-evaluated laser

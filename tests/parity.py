@@ -35,7 +35,8 @@ def by_weight(aos):
 class Pair:
     """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
 
-    def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None):
+    def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None, host_resident=False,
+                 host_chunk=None):
         self.deck = deck
         self.nranks = nranks
         self.oracle = decks.make_oracle(deck, nranks=nranks)
@@ -55,6 +56,19 @@ class Pair:
         if init_half_step:
             self.oracle.call("init_half_step")
             self.each(lambda s: s.init_half_step())
+        if host_resident:
+            # the particle lists move to host memory (with head room for arrivals) and stay there
+            for s in self.slabs:
+                lists, counts = [], []
+                for isp in range(len(deck.species)):
+                    a = s.download_particles(isp)
+                    buf = np.zeros((a.shape[0] + a.shape[0] // 4 + 64, 7))
+                    buf[:a.shape[0]] = a
+                    lists.append(buf)
+                    counts.append(a.shape[0])
+                s.attach_host_lists(lists, counts)
+                if host_chunk is not None:
+                    s.set_host_chunk(host_chunk)
 
     def each(self, fn):
         """run fn on every slab; ranks > 1 need one host thread each (blocking exchanges)."""
@@ -116,10 +130,13 @@ class Pair:
         for isp in range(len(self.deck.species)):
             for k, s in enumerate(self.slabs):
                 ref = self.oracle.particles(k, isp)
-                got = s.download_particles(isp)
+                if s.host_lists is not None:
+                    got = s.host_lists[isp][:s.host_counts[isp]]
+                else:
+                    got = s.download_particles(isp)
+                    assert s.particle_count(isp) == self.oracle.nparticles(k, isp)
                 # integer outputs: bit-exact
                 assert got.shape[0] == ref.shape[0], f"species {isp} rank {k}: count {got.shape[0]} != {ref.shape[0]}"
-                assert s.particle_count(isp) == self.oracle.nparticles(k, isp)
                 if ref.shape[0] == 0:
                     continue
                 ref, got = by_weight(ref), by_weight(got)

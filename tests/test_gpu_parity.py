@@ -197,6 +197,28 @@ def test_two_ranks_fabric(deckname):
         p.close()
 
 
+@pytest.mark.parametrize("deckname,nranks", [("lwfa", 1), ("thermal", 1), ("thermal", 2), ("lwfa", 2)])
+def test_host_resident_lists_streamed_push(deckname, nranks):
+    """cylgpu_push_host: the particle lists stay in host memory and are streamed through the GPU
+    in chunks (several chunks per step here); same fields, currents, particles and migration
+    counts as the oracle."""
+    if deckname == "lwfa":
+        d, tol = decks.lwfa(nx=96, ny=32, n_mode=2, ppc_e=4, ppc_p=1), 1e-9
+    else:
+        d, tol = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8), TOL_HOT
+    p = Pair(d, nranks=nranks, host_resident=True, host_chunk=2048)
+    try:
+        for _ in range(3):
+            p.step(5)
+            p.check_counts()
+            p.check_fields(tol)
+            p.check_particles(tol)
+        st = p.slabs[0].stats()
+        assert st.n_particles[0] == 0    # nothing is left on the device between steps
+    finally:
+        p.close()
+
+
 def test_energy_diagnostic_thermal():
     d = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8)
     p = Pair(d)
