@@ -123,7 +123,7 @@ int cylgpu_destroy(cylgpu_handle c) {
     for (int q = 0; q < 7; ++q) cudaFree(c->species[i].alt[q]);
     cudaFree(c->species[i].cell_start);
   }
-  cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->hole_list);
+  cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->tailmark); cudaFree(c->hole_list);
   cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->scan_blocks);
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
@@ -360,12 +360,8 @@ int cylgpu_fields_half(cylgpu_handle c) {
 // particles.F90:28-734 (push + r_min fold + particle_bcs)
 int cylgpu_push(cylgpu_handle c) {
   TRY(check_handle(c));
-  {
-    PhaseTimer t(c, &c->stats.ms_push);
-    TRY(do_push(c));
-  }
-  PhaseTimer t(c, &c->stats.ms_bcs);
-  return do_particle_bcs(c);
+  PhaseTimer t(c, &c->stats.ms_push);
+  return do_push_bcs(c);
 }
 
 // the same for particle lists that stay in host memory (streamed through the GPU in chunks)

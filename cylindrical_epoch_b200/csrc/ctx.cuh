@@ -120,8 +120,9 @@ struct cylgpu_ctx {
   double* ptmp = nullptr;        // one SoA component worth of doubles (sort scatter target)
   int64_t ptmp_cap = 0;
   uint32_t* perm = nullptr;      // sort destination per particle
-  uint8_t* flag = nullptr;       // particle_bcs classification
-  uint32_t* hole_list = nullptr; // indices of leavers
+  uint8_t* flag = nullptr;       // fate (left / right / gone) of the h-th leaver
+  uint8_t* tailmark = nullptr;   // leavers among the last `nholes` slots
+  uint32_t* hole_list = nullptr; // indices of leavers (stand-alone particle_bcs)
   uint32_t* lowhole = nullptr;   // holes below the new count
   uint32_t* hightail = nullptr;  // keepers above the new count
   int64_t pscratch_cap = 0;
@@ -147,6 +148,7 @@ struct cylgpu_ctx {
   cylgpu_stats_t stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
   bool timing = true;
+  bool kernel_time_pending = false;
 };
 
 namespace cylgpu {
@@ -167,6 +169,7 @@ int do_shift_fields(cylgpu_ctx* c);
 int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip2);
 // particles.cu
 int do_push(cylgpu_ctx* c);
+int do_push_bcs(cylgpu_ctx* c);
 int do_particle_bcs(cylgpu_ctx* c);
 int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
                  int64_t* n_out);

@@ -378,6 +378,128 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
 }
 
 // ------------------------------------------------------------------------------------------
+// particle_bcs, boundary.F90:1541-1889 (non-cpml, non-thermal branches), one particle.  Used by
+// the stand-alone classification kernel (on the arrays) and, fused, by the strip push kernel
+// (on the registers it is about to store): the deposit of a push always sees the position
+// before the boundary treatment, as in the reference where particle_bcs follows the push.
+// ------------------------------------------------------------------------------------------
+struct BcsConst {
+  double x_min, x_max, x_min_local, x_max_local, y_max;
+  double x_min_outer, x_max_outer, y_max_outer, x_shift;
+  double y_max2_inside;   // r^2 below this is inside y_max whatever the rounding of the square root
+  int x_min_boundary, x_max_boundary;
+  int bc[4];
+};
+
+enum { FL_KEEP = 0, FL_LEFT = 1, FL_RIGHT = 2, FL_GONE = 3 };
+enum { CNT_HOLE = 0, CNT_LEFT = 1, CNT_RIGHT = 2, CNT_GONE = 3, CNT_TAIL = 4, CNT_LOW = 5, CNT_PACK_L = 6, CNT_PACK_R = 7 };
+
+struct MemParticle {   // a particle in the SoA arrays: components are touched only when a rule needs them
+  double *x, *y, *z, *px, *py, *pz;
+  __device__ __forceinline__ double gx() const { return *x; }
+  __device__ __forceinline__ double gy() const { return *y; }
+  __device__ __forceinline__ double gz() const { return *z; }
+  __device__ __forceinline__ double gpx() const { return *px; }
+  __device__ __forceinline__ double gpy() const { return *py; }
+  __device__ __forceinline__ double gpz() const { return *pz; }
+  __device__ __forceinline__ void sx(double v) { *x = v; }
+  __device__ __forceinline__ void sy(double v) { *y = v; }
+  __device__ __forceinline__ void sz(double v) { *z = v; }
+  __device__ __forceinline__ void spx(double v) { *px = v; }
+  __device__ __forceinline__ void spy(double v) { *py = v; }
+  __device__ __forceinline__ void spz(double v) { *pz = v; }
+};
+struct RegParticle {   // a particle in registers
+  double &x, &y, &z, &px, &py, &pz;
+  __device__ __forceinline__ double gx() const { return x; }
+  __device__ __forceinline__ double gy() const { return y; }
+  __device__ __forceinline__ double gz() const { return z; }
+  __device__ __forceinline__ double gpx() const { return px; }
+  __device__ __forceinline__ double gpy() const { return py; }
+  __device__ __forceinline__ double gpz() const { return pz; }
+  __device__ __forceinline__ void sx(double v) { x = v; }
+  __device__ __forceinline__ void sy(double v) { y = v; }
+  __device__ __forceinline__ void sz(double v) { z = v; }
+  __device__ __forceinline__ void spx(double v) { px = v; }
+  __device__ __forceinline__ void spy(double v) { py = v; }
+  __device__ __forceinline__ void spz(double v) { pz = v; }
+};
+
+template <class A>
+__device__ __forceinline__ uint8_t particle_bcs_one(const BcsConst& B, A& a) {
+  int xbd = 0;
+  bool out_of_bounds = false;
+  double part_pos = a.gx();
+  if (part_pos < B.x_min_local) {
+    xbd = -1;
+    int bc = -1;
+    if (B.x_min_boundary) {
+      xbd = 0;
+      bc = B.bc[CYLGPU_BD_X_MIN];
+      if (bc == CYLGPU_BC_REFLECT) {
+        a.sx(2.0 * B.x_min - part_pos);
+        a.spx(-a.gpx());
+      } else if (bc == CYLGPU_BC_PERIODIC) {
+        xbd = -1;
+        a.sx(part_pos - (-1.0) * B.x_shift);
+      }
+    }
+    if (part_pos < B.x_min_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  if (part_pos >= B.x_max_local) {
+    xbd = 1;
+    int bc = -1;
+    if (B.x_max_boundary) {
+      xbd = 0;
+      bc = B.bc[CYLGPU_BD_X_MAX];
+      if (bc == CYLGPU_BC_REFLECT) {
+        a.sx(2.0 * B.x_max - part_pos);
+        a.spx(-a.gpx());
+      } else if (bc == CYLGPU_BC_PERIODIC) {
+        xbd = 1;
+        a.sx(part_pos - B.x_shift);
+      }
+    }
+    if (part_pos >= B.x_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  const double Y = a.gy(), Z = a.gz();
+  const double r2 = Y * Y + Z * Z;
+  // the square root (boundary.F90:1744) only where it can matter: all but the outermost particles
+  // are inside by a margin no rounding can bridge
+  if (r2 >= B.y_max2_inside && (part_pos = sqrt(r2)) >= B.y_max) {
+    const int bc = B.bc[CYLGPU_BD_Y_MAX];
+    if (bc == CYLGPU_BC_REFLECT) {
+      const double radial_reduction = 2.0 * B.y_max / part_pos - 1.0;
+      const double Yn = Y * radial_reduction, Zn = Z * radial_reduction;
+      a.sy(Yn);
+      a.sz(Zn);
+      const double inv_final_r = 1.0 / sqrt(Yn * Yn + Zn * Zn);
+      const double cos_theta = Yn * inv_final_r, sin_theta = Zn * inv_final_r;
+      const double PY = a.gpy(), PZ = a.gpz();
+      const double part_pr = PY * cos_theta + PZ * sin_theta;
+      const double part_pt = -PY * sin_theta + PZ * cos_theta;
+      a.spy(-part_pr * cos_theta - part_pt * sin_theta);
+      a.spz(-part_pr * sin_theta + part_pt * cos_theta);
+    }
+    if (part_pos >= B.y_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
+  }
+  uint8_t f = FL_KEEP;
+  if (out_of_bounds) f = FL_GONE;
+  else if (xbd == -1) f = FL_LEFT;
+  else if (xbd == 1) f = FL_RIGHT;
+  return f;
+}
+
+// a particle that leaves the list: its slot becomes a hole, its fate (left / right / gone) is kept
+__device__ __forceinline__ void record_leaver(uint32_t* __restrict__ hole_list, uint8_t* __restrict__ hole_flag,
+                                              unsigned long long* cnt, uint32_t i, uint8_t f) {
+  const unsigned long long h = atomicAdd(&cnt[CNT_HOLE], 1ULL);
+  hole_list[h] = i;
+  hole_flag[h] = f;
+  atomicAdd(&cnt[f], 1ULL);   // CNT_LEFT / CNT_RIGHT / CNT_GONE share the flag value
+}
+
+// ------------------------------------------------------------------------------------------
 // variant 2: strip CTAs.  The sort of this push (do_sort) left the particles ordered by the
 // staggered cell (cell_y2, cell_x2) they occupy after the half-step drift, with the start of
 // every cell in `cell_start`.  One CTA owns a strip of STRIP_C consecutive cells of one row:
@@ -415,11 +537,19 @@ constexpr size_t strip_smem_bytes(bool mma) {
 #ifndef STRIP_MINB
 #define STRIP_MINB(M) ((M) <= 3 ? 3 : 2)
 #endif
+struct FusedBcs {   // particle_bcs fused into the strip push (enabled = 0: the push leaves it to k_pbcs_classify)
+  BcsConst B;
+  uint32_t* hole_list;
+  uint8_t* hole_flag;
+  unsigned long long* cnt;
+  int enabled;
+};
+
 template <int M, bool MMA>
 __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, SoaIn in, SoaOut out,
                                                                 const uint32_t* __restrict__ src,
                                                                 const int* __restrict__ cell_start, int ncx,
-                                                                int nstrip_x) {
+                                                                int nstrip_x, const __grid_constant__ FusedBcs FB) {
   constexpr int PC = STRIP_PC, CS = PATCH_ROWS * PC;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* s0 = reinterpret_cast<double*>(smem_raw);
@@ -461,9 +591,9 @@ __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, Soa
     const bool valid = iraw < end;
     // sorted slot -> particle: the sort only built the permutation, the move happens here.
     // Idle lanes shadow the last particle of the strip: finite data, no store.
-    const uint32_t j = __ldg(&src[valid ? iraw : end - 1]);
     DepositIn D;
     {
+      const uint32_t j = __ldg(&src[valid ? iraw : end - 1]);
       double X = in.d[0][j], Y = in.d[1][j], Z = in.d[2][j], PX = in.d[3][j], PY = in.d[4][j], PZ = in.d[5][j];
       const double W = in.d[6][j];
       PushMid S;
@@ -473,6 +603,11 @@ __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, Soa
       else F = gather_global<M>(P, S);
       push_post(P, S, F, X, Y, Z, PX, PY, PZ, W, D);
       if (valid) {
+        if (FB.enabled) {   // boundary.F90:1541-1865 on the values about to be stored
+          RegParticle a{X, Y, Z, PX, PY, PZ};
+          const uint8_t f = particle_bcs_one(FB.B, a);
+          if (f != FL_KEEP) record_leaver(FB.hole_list, FB.hole_flag, FB.cnt, (uint32_t)iraw, f);
+        }
         out.d[0][iraw] = X; out.d[1][iraw] = Y; out.d[2][iraw] = Z;
         out.d[3][iraw] = PX; out.d[4][iraw] = PY; out.d[5][iraw] = PZ;
         out.d[6][iraw] = W;
@@ -524,7 +659,13 @@ static int push_prologue(cylgpu_ctx* c) {
 
 // particles.F90:146-734 for the S.n particles of one species currently in S.d: (sort,) gather,
 // Boris, store, deposit.  `time_kernel` brackets the fused kernel with events and a host sync.
-static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel) {
+static BcsConst make_bcs_const(cylgpu_ctx* c);
+static int reserve_pscratch(cylgpu_ctx* c, int64_t n);
+
+// `fuse_bcs`: the strip kernel also applies particle_bcs to what it stores and lists the leavers
+// (counters zeroed here); *fused_out says whether it did (only the strip variants can).
+static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel, bool fuse_bcs = false,
+                        bool* fused_out = nullptr) {
   const Geom& g = c->g;
   // strip kernels read through the sort permutation and write the second buffer set: the sort
   // then only has to build the permutation (no scatter passes)
@@ -532,8 +673,22 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
   const double dt = c->dt;
   cylgpu::SpeciesState& S = c->species[isp];
+  if (fused_out) *fused_out = false;
   if (!S.set || S.sp.immobile || S.n == 0) return 0;
   if (need_sort) TRY(do_sort_species(c, isp, /*physical=*/!strips));
+  FusedBcs FB;
+  FB.enabled = 0;
+  if (fuse_bcs && strips) {
+    TRY(reserve_pscratch(c, S.n));
+    FB.B = make_bcs_const(c);
+    for (int k = 0; k < 4; ++k) FB.B.bc[k] = S.sp.bc_particle[k];
+    FB.hole_list = c->hole_list;  // the sort's key / rank scratch: k_sort_src is done with it by now
+    FB.hole_flag = c->flag;
+    FB.cnt = c->counters;
+    FB.enabled = 1;
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (fused_out) *fused_out = true;
+  }
   PushConst P;
   P.g = g;
   P.exm = c->f[CYLGPU_EXM]; P.erm = c->f[CYLGPU_ERM]; P.etm = c->f[CYLGPU_ETM];
@@ -563,7 +718,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   do {                                                                                                     \
     const size_t shb = strip_smem_bytes<MM>(MMA);                                                          \
     CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
-    k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x); \
+    k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x, FB); \
   } while (0)
 #define LAUNCH_M(MM)                                                                                       \
   do {                                                                                                     \
@@ -587,23 +742,32 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   if (strips) for (int q = 0; q < 7; ++q) std::swap(S.d[q], S.alt[q]);
   c->stats.kernel_launches += 1;
   if (time_kernel) {
-    // per-launch device time of the fused kernel (the roofline numerator's clock); the
-    // host sync is free here: particle_bcs needs one right after the push anyway
+    // per-launch device time of the fused kernel (the roofline numerator's clock); read by
+    // push_kernel_time() after the host sync that particle_bcs needs anyway
     cudaEventRecord(c->evk1, c->stream);
-    cudaEventSynchronize(c->evk1);
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, c->evk0, c->evk1);
-    c->stats.ms_push_kernel += (double)ms;
-    c->stats.n_push_kernel += 1;
+    c->kernel_time_pending = true;
   }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
+static void push_kernel_time(cylgpu_ctx* c) {
+  if (!c->kernel_time_pending) return;
+  c->kernel_time_pending = false;
+  cudaEventSynchronize(c->evk1);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, c->evk0, c->evk1);
+  c->stats.ms_push_kernel += (double)ms;
+  c->stats.n_push_kernel += 1;
+}
+
 int do_push(cylgpu_ctx* c) {
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
-  for (int isp = 0; isp < c->cfg.n_species; ++isp) TRY(push_species(c, isp, need_sort, c->timing));
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    TRY(push_species(c, isp, need_sort, c->timing));
+    push_kernel_time(c);
+  }
   if (need_sort) {
     c->sorted_valid = true;
     c->pushes_since_sort = 0;
@@ -638,11 +802,13 @@ static int reserve_pscratch(cylgpu_ctx* c, int64_t n) {
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   if (c->perm) cudaFree(c->perm);
   if (c->flag) cudaFree(c->flag);
+  if (c->tailmark) cudaFree(c->tailmark);
   if (c->hole_list) cudaFree(c->hole_list);
   if (c->lowhole) cudaFree(c->lowhole);
   if (c->hightail) cudaFree(c->hightail);
   CUDA_TRY(cudaMalloc(&c->perm, (size_t)cap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&c->flag, (size_t)cap));
+  CUDA_TRY(cudaMalloc(&c->tailmark, (size_t)cap));
   CUDA_TRY(cudaMalloc(&c->hole_list, (size_t)cap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&c->lowhole, (size_t)cap * sizeof(uint32_t)));
   CUDA_TRY(cudaMalloc(&c->hightail, (size_t)cap * sizeof(uint32_t)));
@@ -651,140 +817,59 @@ static int reserve_pscratch(cylgpu_ctx* c, int64_t n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// particle_bcs, boundary.F90:1541-1889 (non-cpml, non-thermal branches)
+// particle_bcs, boundary.F90:1541-1889: host side (the per-particle rules are particle_bcs_one)
 // ------------------------------------------------------------------------------------------
-struct BcsConst {
-  double x_min, x_max, x_min_local, x_max_local, y_max;
-  double x_min_outer, x_max_outer, y_max_outer, x_shift;
-  int x_min_boundary, x_max_boundary;
-  int bc[4];
-};
-
-enum { FL_KEEP = 0, FL_LEFT = 1, FL_RIGHT = 2, FL_GONE = 3 };
-enum { CNT_HOLE = 0, CNT_LEFT = 1, CNT_RIGHT = 2, CNT_GONE = 3, CNT_TAIL = 4, CNT_LOW = 5, CNT_PACK_L = 6, CNT_PACK_R = 7 };
-
 __global__ void __launch_bounds__(256) k_pbcs_classify(BcsConst B, double* __restrict__ x, double* __restrict__ y,
                                                        double* __restrict__ z, double* __restrict__ px,
                                                        double* __restrict__ py, double* __restrict__ pz,
-                                                       uint8_t* __restrict__ flag, unsigned long long* cnt,
-                                                       int64_t n) {
+                                                       uint32_t* __restrict__ hole_list, uint8_t* __restrict__ hole_flag,
+                                                       unsigned long long* cnt, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int xbd = 0;
-  bool out_of_bounds = false;
-  double part_pos = x[i];
-  if (part_pos < B.x_min_local) {
-    xbd = -1;
-    int bc = -1;
-    if (B.x_min_boundary) {
-      xbd = 0;
-      bc = B.bc[CYLGPU_BD_X_MIN];
-      if (bc == CYLGPU_BC_REFLECT) {
-        x[i] = 2.0 * B.x_min - part_pos;
-        px[i] = -px[i];
-      } else if (bc == CYLGPU_BC_PERIODIC) {
-        xbd = -1;
-        x[i] = part_pos - (-1.0) * B.x_shift;
-      }
-    }
-    if (part_pos < B.x_min_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
-  }
-  if (part_pos >= B.x_max_local) {
-    xbd = 1;
-    int bc = -1;
-    if (B.x_max_boundary) {
-      xbd = 0;
-      bc = B.bc[CYLGPU_BD_X_MAX];
-      if (bc == CYLGPU_BC_REFLECT) {
-        x[i] = 2.0 * B.x_max - part_pos;
-        px[i] = -px[i];
-      } else if (bc == CYLGPU_BC_PERIODIC) {
-        xbd = 1;
-        x[i] = part_pos - B.x_shift;
-      }
-    }
-    if (part_pos >= B.x_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
-  }
-  const double Y = y[i], Z = z[i];
-  part_pos = sqrt(Y * Y + Z * Z);
-  if (part_pos >= B.y_max) {
-    const int bc = B.bc[CYLGPU_BD_Y_MAX];
-    if (bc == CYLGPU_BC_REFLECT) {
-      const double radial_reduction = 2.0 * B.y_max / part_pos - 1.0;
-      const double Yn = Y * radial_reduction, Zn = Z * radial_reduction;
-      y[i] = Yn;
-      z[i] = Zn;
-      const double inv_final_r = 1.0 / sqrt(Yn * Yn + Zn * Zn);
-      const double cos_theta = Yn * inv_final_r, sin_theta = Zn * inv_final_r;
-      const double PY = py[i], PZ = pz[i];
-      const double part_pr = PY * cos_theta + PZ * sin_theta;
-      const double part_pt = -PY * sin_theta + PZ * cos_theta;
-      py[i] = -part_pr * cos_theta - part_pt * sin_theta;
-      pz[i] = -part_pr * sin_theta + part_pt * cos_theta;
-    }
-    if (part_pos >= B.y_max_outer && bc != CYLGPU_BC_PERIODIC) out_of_bounds = true;
-  }
-  uint8_t f = FL_KEEP;
-  if (out_of_bounds) f = FL_GONE;
-  else if (xbd == -1) f = FL_LEFT;
-  else if (xbd == 1) f = FL_RIGHT;
-  flag[i] = f;
-  if (f != FL_KEEP) {
-    atomicAdd(&cnt[CNT_HOLE], 1ULL);
-    atomicAdd(&cnt[f], 1ULL);   // CNT_LEFT / CNT_RIGHT / CNT_GONE share the flag value
-  }
+  MemParticle a{x + i, y + i, z + i, px + i, py + i, pz + i};
+  const uint8_t f = particle_bcs_one(B, a);
+  if (f != FL_KEEP) record_leaver(hole_list, hole_flag, cnt, (uint32_t)i, f);
 }
 
 // window.F90:304-325 remove_particles: everything behind the new x_min goes
 __global__ void __launch_bounds__(256) k_flag_behind(const double* __restrict__ x, double x_min,
-                                                     uint8_t* __restrict__ flag, unsigned long long* cnt,
-                                                     int64_t n) {
+                                                     uint32_t* __restrict__ hole_list, uint8_t* __restrict__ hole_flag,
+                                                     unsigned long long* cnt, int64_t n) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const bool gone = x[i] < x_min;
-  flag[i] = gone ? FL_GONE : FL_KEEP;
-  if (gone) {
-    atomicAdd(&cnt[CNT_HOLE], 1ULL);
-    atomicAdd(&cnt[CNT_GONE], 1ULL);
-  }
+  if (x[i] < x_min) record_leaver(hole_list, hole_flag, cnt, (uint32_t)i, FL_GONE);
 }
 
 struct Soa { double* d[7]; };
 
-// second pass: list the holes and pack the leavers in pack_particle order (7 doubles)
-__global__ void __launch_bounds__(256) k_collect(Soa s, const uint8_t* __restrict__ flag,
-                                                 uint32_t* __restrict__ hole_list, double* __restrict__ send_l,
-                                                 double* __restrict__ send_r, unsigned long long* cnt2,
-                                                 int64_t n) {
-  // cnt2[0] = holes listed, cnt2[1] = packed left, cnt2[2] = packed right
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint8_t f = flag[i];
-  if (f == FL_KEEP) return;
-  const unsigned long long h = atomicAdd(&cnt2[0], 1ULL);
-  hole_list[h] = (uint32_t)i;
+// second pass over the leavers: pack the migrants in pack_particle order (7 doubles), split the
+// holes into those below the new count (to be filled) and those in the tail (marked)
+__global__ void __launch_bounds__(256) k_collect(Soa s, const uint32_t* __restrict__ hole_list,
+                                                 const uint8_t* __restrict__ hole_flag, int64_t nholes, int64_t n_new,
+                                                 double* __restrict__ send_l, double* __restrict__ send_r,
+                                                 uint32_t* __restrict__ lowhole, uint8_t* __restrict__ tailmark,
+                                                 unsigned long long* cnt2) {
+  // cnt2[1] = packed left, cnt2[2] = packed right, cnt2[4] = holes below the new count
+  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= nholes) return;
+  const uint32_t i = hole_list[h];
+  const uint8_t f = hole_flag[h];
   if (f == FL_LEFT || f == FL_RIGHT) {
     const unsigned long long k = atomicAdd(&cnt2[f], 1ULL);
     double* dst = ((f == FL_LEFT) ? send_l : send_r) + 7 * k;
 #pragma unroll
     for (int q = 0; q < 7; ++q) dst[q] = s.d[q][i];
   }
+  if ((int64_t)i >= n_new) tailmark[(int64_t)i - n_new] = 1;
+  else lowhole[atomicAdd(&cnt2[4], 1ULL)] = i;
 }
 
-__global__ void __launch_bounds__(256) k_tail_keepers(const uint8_t* __restrict__ flag, int64_t n_new, int64_t n,
-                                                      uint32_t* __restrict__ hightail, unsigned long long* cnt2) {
-  const int64_t i = n_new + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  if (flag[i] == FL_KEEP) hightail[atomicAdd(&cnt2[3], 1ULL)] = (uint32_t)i;
-}
-
-__global__ void __launch_bounds__(256) k_low_holes(const uint32_t* __restrict__ hole_list, int64_t nholes,
-                                                   int64_t n_new, uint32_t* __restrict__ lowhole,
-                                                   unsigned long long* cnt2) {
-  const int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= nholes) return;
-  const uint32_t i = hole_list[h];
-  if ((int64_t)i < n_new) lowhole[atomicAdd(&cnt2[4], 1ULL)] = i;
+__global__ void __launch_bounds__(256) k_tail_keepers(const uint8_t* __restrict__ tailmark, int64_t n_new,
+                                                      int64_t nholes, uint32_t* __restrict__ hightail,
+                                                      unsigned long long* cnt2) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nholes) return;
+  if (!tailmark[t]) hightail[atomicAdd(&cnt2[3], 1ULL)] = (uint32_t)(n_new + t);
 }
 
 __global__ void __launch_bounds__(256) k_fill_holes(Soa s, const uint32_t* __restrict__ lowhole,
@@ -816,24 +901,24 @@ static int ensure_dbuf(double** p, int64_t* cap, int64_t need, cudaStream_t st) 
   return 0;
 }
 
-// compaction after flags + counts are known on the host: fills the holes below the new
-// count with the keepers above it (order is not preserved; the reference's list order only
-// matters for floating-point summation order)
+// compaction once the leavers are listed and counted (counts on the host): fills the holes below
+// the new count with the keepers above it (order is not preserved; the reference's list order
+// only matters for floating-point summation order)
 static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64_t off_l, int64_t off_r,
                    unsigned long long* cnt2) {
   Soa s;
   for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
   const int64_t n = S.n, n_new = n - nholes;
   CUDA_TRY(cudaMemsetAsync(cnt2, 0, 8 * sizeof(unsigned long long), c->stream));
-  k_collect<<<nblk(n, 256), 256, 0, c->stream>>>(s, c->flag, c->hole_list, c->psend_l + 7 * off_l, c->psend_r + 7 * off_r,
-                                                 cnt2, n);
-  if (n_new > 0 && nholes > 0) {
-    k_tail_keepers<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->flag, n_new, n, c->hightail, cnt2);
-    k_low_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->hole_list, nholes, n_new, c->lowhole, cnt2);
-    k_fill_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(s, c->lowhole, c->hightail, cnt2, nholes);
-    c->stats.kernel_launches += 3;
-  }
+  CUDA_TRY(cudaMemsetAsync(c->tailmark, 0, (size_t)nholes, c->stream));
+  k_collect<<<nblk(nholes, 256), 256, 0, c->stream>>>(s, c->hole_list, c->flag, nholes, n_new, c->psend_l + 7 * off_l,
+                                                      c->psend_r + 7 * off_r, c->lowhole, c->tailmark, cnt2);
   c->stats.kernel_launches += 1;
+  if (n_new > 0) {
+    k_tail_keepers<<<nblk(nholes, 256), 256, 0, c->stream>>>(c->tailmark, n_new, nholes, c->hightail, cnt2);
+    k_fill_holes<<<nblk(nholes, 256), 256, 0, c->stream>>>(s, c->lowhole, c->hightail, cnt2, nholes);
+    c->stats.kernel_launches += 2;
+  }
   CUDA_TRY(cudaGetLastError());
   S.n = n_new;
   return 0;
@@ -851,6 +936,7 @@ static BcsConst make_bcs_const(cylgpu_ctx* c) {
   boundary_shift = dy * (double)((1 + PNG + 0) / 2);
   B.y_max_outer = B.y_max + boundary_shift;
   B.x_shift = B.x_max - B.x_min;   // length_x
+  B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
   B.x_min_boundary = c->cfg.x_min_boundary;
   B.x_max_boundary = c->cfg.x_max_boundary;
   return B;
@@ -874,21 +960,24 @@ static int grow_dbuf_keep(double** p, int64_t* cap, int64_t need, int64_t keep, 
 // classification, removal of the leavers (hole filling) and packing of the migrants behind the
 // `off_l` / `off_r` particles already waiting in psend_l / psend_r.  One host sync (the counts).
 static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off_l, int64_t off_r, int64_t* nleft_out,
-                                 int64_t* nright_out) {
+                                 int64_t* nright_out, bool classified_by_push = false) {
   unsigned long long* cnt = c->counters;        // 8 for classify
   unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
   cylgpu::SpeciesState& S = c->species[isp];
   for (int k = 0; k < 4; ++k) B.bc[k] = S.sp.bc_particle[k];
-  TRY(reserve_pscratch(c, S.n));
-  CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
-  if (S.n > 0) {
-    k_pbcs_classify<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
-                                                          c->flag, cnt, S.n);
-    c->stats.kernel_launches += 1;
+  if (!classified_by_push) {
+    TRY(reserve_pscratch(c, S.n));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (S.n > 0) {
+      k_pbcs_classify<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                            c->hole_list, c->flag, cnt, S.n);
+      c->stats.kernel_launches += 1;
+    }
   }
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  push_kernel_time(c);
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
@@ -934,33 +1023,60 @@ static int pbcs_exchange(cylgpu_ctx* c, int64_t nleft, int64_t nright, int64_t* 
   return 0;
 }
 
+// particle_bcs of one species: (classification,) compaction, exchange, arrivals appended
+static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classified_by_push) {
+  cylgpu::SpeciesState& S = c->species[isp];
+  int64_t nleft = 0, nright = 0, from_l = 0, from_r = 0;
+  TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright, classified_by_push));
+  TRY(pbcs_exchange(c, nleft, nright, &from_l, &from_r));
+  // the reference receives from the right neighbour first (ix = -1 iteration), then left
+  const int64_t nrecv = from_l + from_r;
+  if (nrecv > 0) {
+    TRY(reserve_particles(c, isp, S.n + nrecv));
+    Soa s;
+    for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+    const double* rl = c->precv;
+    const double* rr = c->precv + 7 * from_l;
+    if (from_r > 0) k_unpack<<<nblk(from_r, 256), 256, 0, c->stream>>>(s, S.n, rr, from_r);
+    if (from_l > 0) k_unpack<<<nblk(from_l, 256), 256, 0, c->stream>>>(s, S.n + from_r, rl, from_l);
+    c->stats.kernel_launches += (from_r > 0) + (from_l > 0);
+    S.n += nrecv;
+    c->stats.n_recv += nrecv;
+    CUDA_TRY(cudaGetLastError());
+  }
+  c->stats.n_particles[isp] = S.n;
+  return 0;
+}
+
 int do_particle_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
-  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
-    cylgpu::SpeciesState& S = c->species[isp];
-    if (!S.set) continue;
-    int64_t nleft = 0, nright = 0, from_l = 0, from_r = 0;
-    TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright));
-    TRY(pbcs_exchange(c, nleft, nright, &from_l, &from_r));
-    // the reference receives from the right neighbour first (ix = -1 iteration), then left
-    const int64_t nrecv = from_l + from_r;
-    if (nrecv > 0) {
-      TRY(reserve_particles(c, isp, S.n + nrecv));
-      Soa s;
-      for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
-      const double* rl = c->precv;
-      const double* rr = c->precv + 7 * from_l;
-      if (from_r > 0) k_unpack<<<nblk(from_r, 256), 256, 0, c->stream>>>(s, S.n, rr, from_r);
-      if (from_l > 0) k_unpack<<<nblk(from_l, 256), 256, 0, c->stream>>>(s, S.n + from_r, rl, from_l);
-      c->stats.kernel_launches += (from_r > 0) + (from_l > 0);
-      S.n += nrecv;
-      c->stats.n_recv += nrecv;
-      CUDA_TRY(cudaGetLastError());
-    }
-    c->stats.n_particles[isp] = S.n;
-  }
+  for (int isp = 0; isp < c->cfg.n_species; ++isp)
+    if (c->species[isp].set) TRY(pbcs_species(c, isp, B, false));
   return 0;
+}
+
+// push_particles including its particle_bcs call (particles.F90:28-734): species by species,
+// the strip kernel applying the boundary rules to what it stores, so that the list is read
+// once per step
+int do_push_bcs(cylgpu_ctx* c) {
+  const BcsConst B = make_bcs_const(c);
+  c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  TRY(push_prologue(c));
+  const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    if (!c->species[isp].set) continue;
+    bool fused = false;
+    TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
+    TRY(pbcs_species(c, isp, B, fused));
+  }
+  if (need_sort) {
+    c->sorted_valid = true;
+    c->pushes_since_sort = 0;
+    c->stats.n_sorts += 1;
+  }
+  c->pushes_since_sort += 1;
+  return do_r_min_final(c);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1049,9 +1165,10 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
       CUDA_TRY(cudaEventRecord(H.ev_unpacked[b], c->stream));
       c->stats.kernel_launches += 1;
       S.n = m;
-      if (!S.sp.immobile) TRY(push_species(c, isp, c->sort_interval > 0, false));
+      bool fused = false;
+      TRY(push_species(c, isp, c->sort_interval > 0, false, true, &fused));
       int64_t nleft = 0, nright = 0;
-      TRY(pbcs_classify_compact(c, isp, B, acc_l, acc_r, &nleft, &nright));   // host sync: counts
+      TRY(pbcs_classify_compact(c, isp, B, acc_l, acc_r, &nleft, &nright, fused));   // host sync: counts
       acc_l += nleft;
       acc_r += nright;
       const int64_t kept = S.n;
@@ -1104,7 +1221,7 @@ int do_remove_behind(cylgpu_ctx* c) {
     if (!S.set || S.n == 0) continue;
     TRY(reserve_pscratch(c, S.n));
     CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
-    k_flag_behind<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->flag, cnt, S.n);
+    k_flag_behind<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->hole_list, c->flag, cnt, S.n);
     c->stats.kernel_launches += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                              c->stream));
