@@ -438,10 +438,16 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     wl = WORKLOADS[args.workload]
+    # stdout carries exactly one JSON line: whatever libraries print there (NCCL's version banner,
+    # torchrun notices) goes to stderr while the run is in progress
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference(args, args.workload, wl)
     else:
         run_ours(args, args.workload, wl)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

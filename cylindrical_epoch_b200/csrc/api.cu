@@ -74,10 +74,6 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   c->timing = false;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->own_stream = true;
-  CUDA_TRY(cudaEventCreate(&c->ev0));
-  CUDA_TRY(cudaEventCreate(&c->ev1));
-  CUDA_TRY(cudaEventCreate(&c->evk0));
-  CUDA_TRY(cudaEventCreate(&c->evk1));
   const size_t nelem = g.plane * g.M;
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) {
     CUDA_TRY(cudaMalloc(&c->f[k], nelem * sizeof(cplx)));
@@ -90,10 +86,10 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   }
   CUDA_TRY(cudaMalloc(&c->src, 4 * (size_t)(g.ny + 1) * sizeof(double)));
   c->halo_elems = (size_t)3 * g.M * g.SY * NG;
-  CUDA_TRY(cudaMalloc(&c->sbuf_l, c->halo_elems * sizeof(cplx)));
-  CUDA_TRY(cudaMalloc(&c->sbuf_r, c->halo_elems * sizeof(cplx)));
-  CUDA_TRY(cudaMalloc(&c->rbuf_l, c->halo_elems * sizeof(cplx)));
-  CUDA_TRY(cudaMalloc(&c->rbuf_r, c->halo_elems * sizeof(cplx)));
+  CUDA_TRY(cudaMalloc(&c->sbuf_l, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
+  CUDA_TRY(cudaMalloc(&c->sbuf_r, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
+  CUDA_TRY(cudaMalloc(&c->rbuf_l, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
+  CUDA_TRY(cudaMalloc(&c->rbuf_r, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
   CUDA_TRY(cudaMalloc(&c->counters, 32 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(c->counters, 0, 32 * sizeof(unsigned long long), c->stream));
   CUDA_TRY(cudaMallocHost(&c->h_counters, 32 * sizeof(unsigned long long)));
@@ -127,7 +123,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->scan_blocks);
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->evk0); cudaEventDestroy(c->evk1);
+  c->timers.destroy();
   for (int k = 0; k < 3; ++k) {
     cudaFree(c->hs.in[k]);
     if (c->hs.ev_up[k]) cudaEventDestroy(c->hs.ev_up[k]);
@@ -416,12 +412,14 @@ int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return 
 
 int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {
   if (!c || !out) { set_error("bad argument"); return 2; }
+  c->timers.drain();
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) c->stats.n_particles[i] = c->species[i].n;
   *out = c->stats;
   return 0;
 }
 int cylgpu_reset_stats(cylgpu_handle c) {
   if (!c) return 2;
+  c->timers.drain();
   c->stats.kernel_launches = 0;
   c->stats.ms_fields = c->stats.ms_push = c->stats.ms_bcs = c->stats.ms_sort = c->stats.ms_exchange = 0.0;
   c->stats.ms_push_kernel = 0.0;

@@ -81,8 +81,9 @@ struct Halo3 {
 
 // mode 0: pack interior edge columns (send_l <- 1..ng, send_r <- nx+1-ng..nx)
 // mode 1: pack ghost columns          (send_l <- 1-ng..0, send_r <- nx+1..nx+ng)  [J sums]
+// mode 2: both, ghost block first then interior block (`half` elements apart)  [J sum + J halo in one message]
 __global__ void __launch_bounds__(128) k_halo_pack(Geom g, Halo3 h, cplx* __restrict__ send_l,
-                                                   cplx* __restrict__ send_r, int mode) {
+                                                   cplx* __restrict__ send_r, int mode, size_t half) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = g.SY * NG;
   if (t >= per) return;
@@ -98,13 +99,19 @@ __global__ void __launch_bounds__(128) k_halo_pack(Geom g, Halo3 h, cplx* __rest
   } else {
     if (send_l) send_l[b] = f[g.at(i - NG, j, im)];
     if (send_r) send_r[b] = f[g.at(g.nx + i, j, im)];
+    if (mode == 2) {
+      if (send_l) send_l[half + b] = f[g.at(i, j, im)];
+      if (send_r) send_r[half + b] = f[g.at(g.nx - NG + i, j, im)];
+    }
   }
 }
 
 // mode 0: ghost <- received (recv_l -> 1-ng..0, recv_r -> nx+1..nx+ng)
 // mode 1: interior += received (recv_l -> 1..ng, recv_r -> nx+1-ng..nx), boundary.F90:1192,1200
+// mode 2: mode 1, and ghost <- the neighbour's interior edge AFTER its own sum, which is its
+//         interior block + my ghost value (the very two operands the neighbour adds)
 __global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx* __restrict__ recv_l,
-                                                     const cplx* __restrict__ recv_r, int mode) {
+                                                     const cplx* __restrict__ recv_r, int mode, size_t half) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int per = g.SY * NG;
   if (t >= per) return;
@@ -120,6 +127,10 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx
   } else {
     if (recv_l) { const size_t o = g.at(i, j, im); f[o] = f[o] + recv_l[b]; }
     if (recv_r) { const size_t o = g.at(g.nx - NG + i, j, im); f[o] = f[o] + recv_r[b]; }
+    if (mode == 2) {
+      if (recv_l) { const size_t o = g.at(i - NG, j, im); f[o] = recv_l[half + b] + f[o]; }
+      if (recv_r) { const size_t o = g.at(g.nx + i, j, im); f[o] = recv_r[half + b] + f[o]; }
+    }
   }
 }
 
@@ -127,11 +138,11 @@ static int exchange3(cylgpu_ctx* c, const Halo3& h, int mode, bool send_l, bool 
                      bool recv_r) {
   const Geom& g = c->g;
   if (!(send_l || send_r || recv_l || recv_r)) return 0;
-  const size_t bytes = c->halo_elems * sizeof(cplx);
+  const size_t bytes = (mode == 2 ? 2 : 1) * c->halo_elems * sizeof(cplx);
   dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
   if (send_l || send_r) {
     k_halo_pack<<<grd, 128, 0, c->stream>>>(g, h, send_l ? c->sbuf_l : nullptr, send_r ? c->sbuf_r : nullptr,
-                                            mode);
+                                            mode, c->halo_elems);
     c->stats.kernel_launches += 1;
   }
   TRY(transport_sendrecv(c, send_l ? c->sbuf_l : nullptr, send_l ? bytes : 0, recv_l ? c->rbuf_l : nullptr,
@@ -139,7 +150,7 @@ static int exchange3(cylgpu_ctx* c, const Halo3& h, int mode, bool send_l, bool 
                          recv_r ? c->rbuf_r : nullptr, recv_r ? bytes : 0));
   if (recv_l || recv_r) {
     k_halo_unpack<<<grd, 128, 0, c->stream>>>(g, h, recv_l ? c->rbuf_l : nullptr, recv_r ? c->rbuf_r : nullptr,
-                                              mode);
+                                              mode, c->halo_elems);
     c->stats.kernel_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
@@ -523,8 +534,12 @@ static int bc_allspecies(const cylgpu_ctx* c, int bd) {
   return b == -2 ? CYLGPU_BC_OPEN : b;
 }
 
-int do_current_bcs(cylgpu_ctx* c) {
+// `with_halo`: current_finish follows the sum with the J halo (field_mode_bc on jxm, jrm, jtm);
+// when both exchanges go to the same neighbours they travel as one message.  *halo_done tells
+// the caller whether the ghosts are already filled.
+static int current_bcs_impl(cylgpu_ctx* c, bool with_halo, bool* halo_done) {
   const Geom& g = c->g;
+  if (halo_done) *halo_done = false;
   int bca[4];
   for (int bd = 0; bd < 4; ++bd) {
     bca[bd] = bc_allspecies(c, bd);
@@ -556,11 +571,24 @@ int do_current_bcs(cylgpu_ctx* c) {
   Halo3 h;
   h.f[0] = jx; h.f[1] = jr; h.f[2] = jt;
   h.skip[0] = h.skip[1] = h.skip[2] = 0;
+  if (with_halo) {
+    const bool has_l = c->left >= 0, has_r = c->right >= 0;
+    const bool fill_r = has_r && (!c->cfg.x_max_boundary || c->bc_field[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC);
+    const bool fill_l = has_l && (!c->cfg.x_min_boundary || c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC);
+    if (fill_l == to_l && fill_r == to_r && (to_l || to_r)) {
+      *halo_done = true;
+      return exchange3(c, h, 2, to_l, to_r, to_l, to_r);
+    }
+  }
   return exchange3(c, h, 1, to_l, to_r, to_l, to_r);
 }
 
+int do_current_bcs(cylgpu_ctx* c) { return current_bcs_impl(c, false, nullptr); }
+
 int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45, smoothing off
-  TRY(do_current_bcs(c));
+  bool halo_done = false;
+  TRY(current_bcs_impl(c, true, &halo_done));
+  if (halo_done) return 0;
   return halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0);
 }
 

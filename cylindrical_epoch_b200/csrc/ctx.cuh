@@ -82,6 +82,33 @@ struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
 };
 
+// Device-time accounting without host syncs: each timed span records a pair of events from a
+// pool; the elapsed times are read and accumulated when the statistics are asked for (or the
+// pool runs low), so that timing never stalls the step.
+struct TimerPool {
+  struct Span { cudaEvent_t a, b; double* acc; int64_t* count; };
+  std::vector<cudaEvent_t> idle;
+  std::vector<Span> pending;
+  cudaEvent_t get() {
+    if (idle.empty()) { cudaEvent_t e = nullptr; cudaEventCreate(&e); return e; }
+    cudaEvent_t e = idle.back(); idle.pop_back(); return e;
+  }
+  void drain() {
+    for (Span& s : pending) {
+      cudaEventSynchronize(s.b);
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { *s.acc += (double)ms; if (s.count) *s.count += 1; }
+      idle.push_back(s.a); idle.push_back(s.b);
+    }
+    pending.clear();
+  }
+  void destroy() {
+    drain();
+    for (cudaEvent_t e : idle) cudaEventDestroy(e);
+    idle.clear();
+  }
+};
+
 // streams, events and staging of the host-resident particle path (do_push_host)
 struct HostStream {
   cudaStream_t up = nullptr, down = nullptr;
@@ -146,9 +173,8 @@ struct cylgpu_ctx {
   bool sorted_valid = false;
 
   cylgpu_stats_t stats;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  cylgpu::TimerPool timers;
   bool timing = true;
-  bool kernel_time_pending = false;
 };
 
 namespace cylgpu {
@@ -185,21 +211,24 @@ void destroy_transport(Transport* t);
 int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, size_t rl_b, const void* sr,
                        size_t sr_b, void* rr, size_t rr_b);
 
-struct PhaseTimer {   // accumulates device ms of a phase into a stats field
+struct PhaseTimer {   // accumulates the device ms of a span into a stats field (read at cylgpu_stats)
   cylgpu_ctx* c;
   double* acc;
-  PhaseTimer(cylgpu_ctx* c_, double* acc_) : c(c_), acc(acc_) {
-    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+  int64_t* count;
+  cudaEvent_t a = nullptr;
+  PhaseTimer(cylgpu_ctx* c_, double* acc_, int64_t* count_ = nullptr, bool enabled = true)
+      : c(c_), acc(acc_), count(count_) {
+    if (c->timing && enabled) { a = c->timers.get(); cudaEventRecord(a, c->stream); }
   }
-  ~PhaseTimer() {
-    if (c->timing) {
-      cudaEventRecord(c->ev1, c->stream);
-      cudaEventSynchronize(c->ev1);
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-      *acc += (double)ms;
-    }
+  void stop() {
+    if (!a) return;
+    cudaEvent_t b = c->timers.get();
+    cudaEventRecord(b, c->stream);
+    c->timers.pending.push_back({a, b, acc, count});
+    a = nullptr;
+    if (c->timers.pending.size() >= 4096) c->timers.drain();
   }
+  ~PhaseTimer() { stop(); }
 };
 
 }  // namespace cylgpu

@@ -708,7 +708,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   P.q_fac = S.sp.charge * fac;
   P.deposit = S.sp.zero_current ? 0 : 1;
   const int64_t nb = (S.n + 127) / 128;
-  if (time_kernel) cudaEventRecord(c->evk0, c->stream);
+  PhaseTimer kernel_timer(c, &c->stats.ms_push_kernel, &c->stats.n_push_kernel, time_kernel);
   const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;
   const int nstrip_x = (ncx + STRIP_C - 1) / STRIP_C;
   SoaIn pin; SoaOut pout;
@@ -741,24 +741,9 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
 #undef PUSH_ARGS
   if (strips) for (int q = 0; q < 7; ++q) std::swap(S.d[q], S.alt[q]);
   c->stats.kernel_launches += 1;
-  if (time_kernel) {
-    // per-launch device time of the fused kernel (the roofline numerator's clock); read by
-    // push_kernel_time() after the host sync that particle_bcs needs anyway
-    cudaEventRecord(c->evk1, c->stream);
-    c->kernel_time_pending = true;
-  }
+  kernel_timer.stop();   // per-launch device time of the fused kernel (the roofline numerator's clock)
   CUDA_TRY(cudaGetLastError());
   return 0;
-}
-
-static void push_kernel_time(cylgpu_ctx* c) {
-  if (!c->kernel_time_pending) return;
-  c->kernel_time_pending = false;
-  cudaEventSynchronize(c->evk1);
-  float ms = 0.f;
-  cudaEventElapsedTime(&ms, c->evk0, c->evk1);
-  c->stats.ms_push_kernel += (double)ms;
-  c->stats.n_push_kernel += 1;
 }
 
 int do_push(cylgpu_ctx* c) {
@@ -766,7 +751,6 @@ int do_push(cylgpu_ctx* c) {
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     TRY(push_species(c, isp, need_sort, c->timing));
-    push_kernel_time(c);
   }
   if (need_sort) {
     c->sorted_valid = true;
@@ -977,7 +961,6 @@ static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  push_kernel_time(c);
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
