@@ -76,6 +76,13 @@ SYMBOLS = {
     "cylgpu_current_finish": (C.c_int, [H]),
     "cylgpu_fields_final": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cylgpu_window_shift": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), _DP]),
+    "cylgpu_rng_init": (C.c_int, [H, C.c_int]),
+    "cylgpu_rng_set_state": (C.c_int, [H, C.POINTER(C.c_int32), C.c_int, C.c_double]),
+    "cylgpu_rng_get_state": (C.c_int, [H, C.POINTER(C.c_int32), C.POINTER(C.c_int), _DP]),
+    "cylgpu_rng_flush_cache": (C.c_int, [H]),
+    "cylgpu_rng_uniform": (C.c_int, [H, _DP]),
+    "cylgpu_insert_particles": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_double, C.c_double, C.POINTER(C.c_int64)]),
     "cylgpu_update_e_field": (C.c_int, [H]),
     "cylgpu_update_b_field": (C.c_int, [H]),
     "cylgpu_efield_bcs": (C.c_int, [H]),

@@ -408,6 +408,53 @@ int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* con
   return do_shift_fields(c);
 }
 
+// ---- moving-window plasma column with the reference's random stream ----
+int cylgpu_rng_init(cylgpu_handle c, int seed) {
+  TRY(check_handle(c));
+  kiss_init(c->rng, seed);
+  return 0;
+}
+int cylgpu_rng_set_state(cylgpu_handle c, const int32_t* xyzw, int cached, double cached_value) {
+  TRY(check_handle(c));
+  if (!xyzw) { set_error("rng_set_state: null state"); return 2; }
+  c->rng.x = (uint32_t)xyzw[0]; c->rng.y = (uint32_t)xyzw[1]; c->rng.z = (uint32_t)xyzw[2]; c->rng.w = (uint32_t)xyzw[3];
+  c->rng.cached = cached != 0;
+  c->rng.cached_value = cached_value;
+  return 0;
+}
+int cylgpu_rng_get_state(cylgpu_handle c, int32_t* xyzw, int* cached, double* cached_value) {
+  TRY(check_handle(c));
+  if (!xyzw || !cached || !cached_value) { set_error("rng_get_state: null argument"); return 2; }
+  xyzw[0] = (int32_t)c->rng.x; xyzw[1] = (int32_t)c->rng.y; xyzw[2] = (int32_t)c->rng.z; xyzw[3] = (int32_t)c->rng.w;
+  *cached = c->rng.cached;
+  *cached_value = c->rng.cached_value;
+  return 0;
+}
+int cylgpu_rng_flush_cache(cylgpu_handle c) {   // random_flush_cache, called by output_routines every step
+  TRY(check_handle(c));
+  c->rng.cached = 0;
+  return 0;
+}
+int cylgpu_rng_uniform(cylgpu_handle c, double* out) {
+  TRY(check_handle(c));
+  if (!out) { set_error("rng_uniform: null argument"); return 2; }
+  *out = kiss_uniform(c->rng);
+  return 0;
+}
+int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell, const double* density,
+                            const double* temperature, const double* drift, double dmin, double dmax,
+                            int64_t* n_inserted) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species || !c->species[isp].set) { set_error("bad species index"); return 2; }
+  if (!density || !temperature || !drift) { set_error("insert_particles: null profile"); return 2; }
+  std::vector<double> aos;
+  TRY(do_insert_particles(c, isp, x_grid_max, npart_per_cell, density, temperature, drift, dmin, dmax, aos));
+  const int64_t n = (int64_t)(aos.size() / 7);
+  if (n_inserted) *n_inserted = n;
+  if (n > 0) TRY(append_impl(c, isp, n, aos.data()));
+  return 0;
+}
+
 int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return do_energy(c, out2); }
 
 int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {

@@ -82,6 +82,13 @@ struct Timer {
   cudaEvent_t a = nullptr, b = nullptr;
 };
 
+// random_state_type, random_generator.f90:26-30
+struct KissState {
+  uint32_t x = 0, y = 0, z = 0, w = 0;
+  int cached = 0;
+  double cached_value = 0.0;
+};
+
 // Device-time accounting without host syncs: each timed span records a pair of events from a
 // pool; the elapsed times are read and accumulated when the statistics are asked for (or the
 // pool runs low), so that timing never stalls the step.
@@ -163,6 +170,7 @@ struct cylgpu_ctx {
 
   cylgpu::Transport* tr = nullptr;
   cylgpu::HostStream hs;
+  cylgpu::KissState rng;          // this rank's random stream (window insertion)
   int64_t host_chunk = 1 << 21;   // particles per chunk of the host-resident path (117 MB)
 
   int sort_interval = 1;
@@ -205,6 +213,13 @@ int do_energy(cylgpu_ctx* c, double* out2);
 int do_cells(cylgpu_ctx* c, int isp, int64_t capn, int32_t* out);
 int reserve_particles(cylgpu_ctx* c, int isp, int64_t n);
 int build_tables(cylgpu_ctx* c);
+// window_insert.cu
+void kiss_init(KissState& s, int seed);
+double kiss_uniform(KissState& s);
+double kiss_box_muller(KissState& s, double stdev, double mu);
+int do_insert_particles(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell, const double* density,
+                        const double* temperature, const double* drift, double dmin, double dmax,
+                        std::vector<double>& aos);
 // transport.cu
 Transport* make_transport(cylgpu_ctx* c);
 void destroy_transport(Transport* t);

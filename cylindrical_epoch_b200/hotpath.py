@@ -38,6 +38,8 @@ class Species:   # shared_data.F90:190-280, hot-path members
     density: float = 0.0
     temp: tuple = (0.0, 0.0, 0.0)
     drift: tuple = (0.0, 0.0, 0.0)
+    density_min: float = 0.0          # initial_conditions%density_min / density_max
+    density_max: float = 1.0e300
 
 
 @dataclass
@@ -137,6 +139,7 @@ class Slab:
             cfg.fabric = fabric
         self.h = C.c_void_p()
         self._ck(self.L.cylgpu_create(C.byref(cfg), C.byref(self.h)))
+        self.rng_init(7842432 + rank)         # setup.F90:563-567
         for i, sp in enumerate(self.species):
             sc = _lib.SpeciesC(sp.charge, sp.mass, (C.c_int32 * 4)(*normalise_bc_particle(sp.bc_particle)),
                                int(sp.immobile), int(sp.zero_current))
@@ -230,6 +233,41 @@ class Slab:
     def set_dt(self, dt):
         self.dt = dt
         self._ck(self.L.cylgpu_set_dt(self.h, dt))
+
+    # ------------------------------------------------------------------ random stream (window insertion)
+    def rng_init(self, seed):                 # random_init, random_generator.f90:81-108
+        self._ck(self.L.cylgpu_rng_init(self.h, int(seed)))
+
+    def rng_set_state(self, xyzw, cached, cached_value):
+        self._ck(self.L.cylgpu_rng_set_state(self.h, (C.c_int32 * 4)(*[int(v) for v in xyzw]), int(cached),
+                                             float(cached_value)))
+
+    def rng_get_state(self):
+        xyzw = (C.c_int32 * 4)()
+        cached = C.c_int()
+        cv = C.c_double()
+        self._ck(self.L.cylgpu_rng_get_state(self.h, xyzw, C.byref(cached), C.byref(cv)))
+        return list(xyzw), int(cached.value), float(cv.value)
+
+    def rng_flush_cache(self):                # random_flush_cache, diagnostics.F90:235
+        self._ck(self.L.cylgpu_rng_flush_cache(self.h))
+
+    def rng_uniform(self):
+        v = C.c_double()
+        self._ck(self.L.cylgpu_rng_uniform(self.h, C.byref(v)))
+        return v.value
+
+    def insert_particles(self, isp):          # window.F90:157-300, uniform profiles of `Species`
+        sp = self.species[isp]
+        nrow = self.grid.ny + 2
+        dens = np.full(nrow, float(sp.density))
+        temp = np.repeat(np.asarray(sp.temp, dtype=np.float64), nrow)     # (3, ny+2), radial index fastest
+        drift = np.repeat(np.asarray(sp.drift, dtype=np.float64), nrow)
+        n = C.c_int64()
+        self._ck(self.L.cylgpu_insert_particles(self.h, isp, self.grid.x_grid_max, float(sp.npart_per_cell),
+                                                dens.ctypes.data, temp.ctypes.data, drift.ctypes.data,
+                                                float(sp.density_min), float(sp.density_max), C.byref(n)))
+        return n.value
 
     def set_sort_interval(self, n):
         self._ck(self.L.cylgpu_set_sort_interval(self.h, n))
@@ -379,7 +417,12 @@ class Slab:
         n_new = (C.c_int64 * max(nsp, 1))()
         ptrs = (C.c_void_p * max(nsp, 1))()
         keep = []
-        if self.grid.x_max_boundary and self.insert_fn is not None:
+        if self.insert_fn is None:
+            # insert_particles with the rank's KISS stream, species in deck order (window.F90:191)
+            for isp in range(nsp):
+                if self.species[isp].npart_per_cell > 0 and self.species[isp].density > 0:
+                    self.insert_particles(isp)
+        elif self.grid.x_max_boundary:
             for isp in range(nsp):
                 aos = self.insert_fn(self, isp)      # insert_particles stays on the host
                 if aos is not None and len(aos):
@@ -399,8 +442,9 @@ class Slab:
         self.current_finish()
         self.step += 1
         self.time = self.time + self.dt / 2.0
+        self.rng_flush_cache()                # output_routines -> random_flush_cache, diagnostics.F90:235
         if flush_rng is not None:
-            flush_rng()                       # output_routines -> random_flush_cache, diagnostics.F90:235
+            flush_rng()
         self.time = self.time + self.dt / 2.0
         self.update_eb_fields_final()
         self.moving_window()

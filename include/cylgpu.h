@@ -194,6 +194,27 @@ int cylgpu_fields_final(cylgpu_handle h, const double* src1_xmin, const double* 
 int cylgpu_window_shift(cylgpu_handle h, const int64_t* n_new, const double* const* new_aos,
                         const double* grid5);
 
+/* ---- plasma column of the moving window with the reference's random stream ----
+ * insert_particles (window.F90:157-300) draws from the rank's KISS stream
+ * (random_generator.f90:45-173), which the loader used before it: either hand the stream over
+ * (cylgpu_rng_set_state with the six members of random_state_type after loading) or start it
+ * as the reference does (cylgpu_rng_init(7842432 + rank), setup.F90:563-567).
+ * cylgpu_rng_flush_cache mirrors random_flush_cache (diagnostics.F90:235, once per step). */
+int cylgpu_rng_init(cylgpu_handle h, int seed);
+int cylgpu_rng_set_state(cylgpu_handle h, const int32_t* xyzw, int box_muller_cached, double cached_random_value);
+int cylgpu_rng_get_state(cylgpu_handle h, int32_t* xyzw, int* box_muller_cached, double* cached_random_value);
+int cylgpu_rng_flush_cache(cylgpu_handle h);
+int cylgpu_rng_uniform(cylgpu_handle h, double* out);
+/* insert_particles for one species, to be called for every species in order BEFORE
+ * cylgpu_window_shift (shift_window, window.F90:62-94).  x_grid_max = x_global(nx_global)
+ * before the shift; density(0:ny+1), temperature(0:ny+1,1:3), drift(0:ny+1,1:3): the deck
+ * functions on the column ix = nx as the reference evaluates them (window.F90:203-220),
+ * Fortran order; dmin/dmax = initial_conditions%density_min/max.  A no-op on ranks that do
+ * not own x_max.  The new particles are appended to the device list. */
+int cylgpu_insert_particles(cylgpu_handle h, int ispecies, double x_grid_max, double npart_per_cell,
+                            const double* density, const double* temperature, const double* drift, double dmin,
+                            double dmax, int64_t* n_inserted);
+
 /* ---- pieces, exposed because the reference calls them on their own ---- */
 int cylgpu_update_e_field(cylgpu_handle h);                 /* fields.f90:53-182 */
 int cylgpu_update_b_field(cylgpu_handle h);                 /* fields.f90:186-312 */

@@ -161,4 +161,12 @@ double cylo_call(void* wp, int op) {
 
 double cylo_rng_uniform(void* wp, int k) { return ((World*)wp)->ranks[k].rng.uniform(); }
 
+// the six members of random_state_type (random_generator.f90:26-30) of rank k
+void cylo_rng_get_state(void* wp, int k, int32_t* xyzw, int* cached, double* cached_value) {
+  const Rng& r = ((World*)wp)->ranks[k].rng;
+  xyzw[0] = (int32_t)r.x; xyzw[1] = (int32_t)r.y; xyzw[2] = (int32_t)r.z; xyzw[3] = (int32_t)r.w;
+  *cached = r.cached ? 1 : 0;
+  *cached_value = r.cached_value;
+}
+
 }  // extern "C"

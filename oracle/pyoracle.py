@@ -87,6 +87,9 @@ def lib():
         L.cylo_call.argtypes = [C.c_void_p, C.c_int]
         L.cylo_rng_uniform.restype = C.c_double
         L.cylo_rng_uniform.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_rng_get_state.restype = None
+        L.cylo_rng_get_state.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
 
@@ -204,6 +207,14 @@ class OracleWorld:
         s2 = np.zeros(ny + 1)
         self.L.cylo_laser_sources(self.h, bd, k, s1.ctypes.data, s2.ctypes.data)
         return s1, s2
+
+    def rng_state(self, k):
+        """(x, y, z, w), box_muller_cached, cached_random_value of rank k's KISS stream"""
+        xyzw = (C.c_int32 * 4)()
+        cached = C.c_int()
+        cv = C.c_double()
+        self.L.cylo_rng_get_state(self.h, k, xyzw, C.byref(cached), C.byref(cv))
+        return list(xyzw), int(cached.value), float(cv.value)
 
     # --- operators -------------------------------------------------------------------------
     def call(self, op):

@@ -219,6 +219,48 @@ def test_host_resident_lists_streamed_push(deckname, nranks):
         p.close()
 
 
+def test_kiss_stream_matches_oracle():
+    """random(), random_box_muller() of random_generator.f90: the product's stream is the oracle's, bit for bit"""
+    d = decks.lwfa(nx=32, ny=12, n_mode=1, ppc_e=1)
+    p = Pair(d, init_half_step=False)
+    try:
+        s = p.slabs[0]
+        assert s.rng_get_state() == p.oracle.rng_state(0)
+        a = [s.rng_uniform() for _ in range(2000)]
+        b = [p.oracle.L.cylo_rng_uniform(p.oracle.h, 0) for _ in range(2000)]
+        assert a == b
+        assert s.rng_get_state() == p.oracle.rng_state(0)
+        s.rng_init(7842432)   # setup.F90:563-567: seed + 1000 warm-up draws
+        import pyoracle
+        fresh = decks.make_oracle(d, load=False)
+        assert s.rng_get_state() == fresh.rng_state(0)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_moving_window_with_plasma(nranks):
+    """C3's shape in small: laser + plasma + moving window.  Every shift drops the particles behind
+    x_min, shifts the nine arrays and loads a fresh column with the rank's KISS stream
+    (window.F90:62-300): inserted particles, counts and fields must match the oracle's."""
+    d = decks.lwfa(nx=64, ny=24, n_mode=2, ppc_e=4, ppc_p=1, window=True, t_centre=30e-15)
+    p = Pair(d, nranks=nranks)
+    try:
+        n0 = [p.oracle.nparticles(nranks - 1, i) for i in range(2)]
+        for _ in range(4):
+            p.step(10)
+            assert int(p.oracle.scalars()["window_shifts_total"]) == p.slabs[0].window_shifts_total
+            p.check_counts()
+            p.check_fields(1e-9)
+            p.check_particles(1e-9)
+        assert p.slabs[0].window_shifts_total >= 20
+        assert p.slabs[-1].rng_get_state() == p.oracle.rng_state(nranks - 1)
+        p.check_cells()
+        assert n0[0] > 0
+    finally:
+        p.close()
+
+
 def test_energy_diagnostic_thermal():
     d = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8)
     p = Pair(d)

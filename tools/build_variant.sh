@@ -3,7 +3,7 @@
 set -e
 cd "$(dirname "$0")/../cylindrical_epoch_b200"
 mkdir -p build/$1
-for f in api fields bcs particles transport; do
+for f in api fields bcs particles transport window_insert; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $2 -c csrc/$f.cu -o build/$1/$f.o &
 done
 wait
