@@ -41,52 +41,53 @@ __global__ void __launch_bounds__(128) k_update_e_bulk(
   etm[o] = etm[o] + (((c2 * (br_xp - br)) / dx - (c2 * (bx_rp - bx)) / dy - jtm[o] / EPSILON0) * 0.5) * dt;
 }
 
-// E axis rows and below-axis mirror: fields.f90:116-180.  One thread per column over the
-// FULL extent 1-ng..nx+ng (the reference uses whole-array sections here).
+// E axis rows and below-axis mirror: fields.f90:116-180, over the FULL extent 1-ng..nx+ng (the
+// reference uses whole-array sections here).  One thread per (column, mode, task): task 0 is
+// the axis row (statement order of the reference kept inside the thread), task k = 1..ng-1 the
+// mirror row ir = -k, which only reads rows >= 1 that the axis task never writes except
+// erm(ix,1,m>=2) -- and the erm mirrors read rows 2..ng.
 __global__ void __launch_bounds__(128) k_update_e_axis(
     Geom g, cplx* __restrict__ exm, cplx* __restrict__ erm, cplx* __restrict__ etm,
     const cplx* __restrict__ btm, const cplx* __restrict__ jxm, double dy, double dt) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
   if (ix > g.nx + NG) return;
+  const int im = blockIdx.y, task = blockIdx.z;
   const double c2 = C_LIGHT * C_LIGHT;
-  // m = 0
-  {
-    const size_t a0 = g.at(ix, 0, 0);
-    exm[a0] = exm[a0] + ((((4.0 * c2) / dy) * btm[g.at(ix, 1, 0)] - jxm[a0] / EPSILON0) * 0.5) * dt;
-    etm[a0] = C(0.0, 0.0);
-    erm[a0] = -erm[g.at(ix, 1, 0)];
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
+  // mirror parity of the modes m >= 2 (fields.f90:171-175); m = 0, 1 are written out below
+  const double mode_sign = (im & 1) ? -1.0 : 1.0;
+  if (task > 0) {
+    const int ir = -task;
+    if (im == 1) {
+      etm[g.at(ix, ir, 1)] = etm[g.at(ix, -ir, 1)];
+      erm[g.at(ix, ir, 1)] = erm[g.at(ix, -ir + 1, 1)];
+      exm[g.at(ix, ir, 1)] = -exm[g.at(ix, -ir, 1)];
+    } else if (im == 0) {
       etm[g.at(ix, ir, 0)] = -etm[g.at(ix, -ir, 0)];
       erm[g.at(ix, ir, 0)] = -erm[g.at(ix, -ir + 1, 0)];
       exm[g.at(ix, ir, 0)] = exm[g.at(ix, -ir, 0)];
+    } else {
+      etm[g.at(ix, ir, im)] = (-mode_sign) * etm[g.at(ix, -ir, im)];
+      erm[g.at(ix, ir, im)] = (-mode_sign) * erm[g.at(ix, -ir + 1, im)];
+      exm[g.at(ix, ir, im)] = mode_sign * exm[g.at(ix, -ir, im)];
     }
+    return;
   }
-  if (g.M > 1) {
-    const size_t a0 = g.at(ix, 0, 1);
+  const size_t a0 = g.at(ix, 0, im);
+  if (im == 0) {
+    exm[a0] = exm[a0] + ((((4.0 * c2) / dy) * btm[g.at(ix, 1, 0)] - jxm[a0] / EPSILON0) * 0.5) * dt;
+    etm[a0] = C(0.0, 0.0);
+    erm[a0] = -erm[g.at(ix, 1, 0)];
+  } else if (im == 1) {
     exm[a0] = C(0.0, 0.0);
     const cplx er1 = erm[g.at(ix, 1, 1)];
     // uses the OLD etm(ix,0,1), then overwrites it (statement order of fields.f90:146-149)
     erm[a0] = C(0.0, 2.0) * etm[a0] - er1;
     etm[a0] = (C(0.0, -1.0) / 8.0) * (9.0 * er1 - erm[g.at(ix, 2, 1)]);
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
-      etm[g.at(ix, ir, 1)] = etm[g.at(ix, -ir, 1)];
-      erm[g.at(ix, ir, 1)] = erm[g.at(ix, -ir + 1, 1)];
-      exm[g.at(ix, ir, 1)] = -exm[g.at(ix, -ir, 1)];
-    }
-  }
-  double mode_sign = 1.0;
-  for (int im = 2; im < g.M; ++im) {
-    const size_t a0 = g.at(ix, 0, im);
+  } else {
     exm[a0] = C(0.0, 0.0);
     etm[a0] = C(0.0, 0.0);
     erm[a0] = -erm[g.at(ix, 1, im)];
     erm[g.at(ix, 1, im)] = erm[g.at(ix, 2, im)] / 9.0;
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
-      etm[g.at(ix, ir, im)] = (-mode_sign) * etm[g.at(ix, -ir, im)];
-      erm[g.at(ix, ir, im)] = (-mode_sign) * erm[g.at(ix, -ir + 1, im)];
-      exm[g.at(ix, ir, im)] = mode_sign * exm[g.at(ix, -ir, im)];
-    }
-    mode_sign = -mode_sign;
   }
 }
 
@@ -114,47 +115,48 @@ __global__ void __launch_bounds__(128) k_update_b_bulk(
   btm[o] = btm[o] + (((-(er - er_xm)) / dx + (ex - ex_rm) / dy) * 0.5) * dt;
 }
 
-// B axis rows and mirror: fields.f90:249-310.  The m = 1 Brm(ix,0) FDTD update reads
-// etm(ix-1,0,1) which this kernel never writes, so one thread per column is race-free.
+// B axis rows and mirror: fields.f90:249-310, one thread per (column, mode, task) as for E.  The
+// m = 1 Brm(ix,0) FDTD update reads etm(ix-1,0,1), which this kernel never writes; the mirrors
+// read rows >= 1 only.
 __global__ void __launch_bounds__(128) k_update_b_axis(
     Geom g, cplx* __restrict__ bxm, cplx* __restrict__ brm, cplx* __restrict__ btm,
     const cplx* __restrict__ exm, const cplx* __restrict__ etm, double dx, double dy, double dt) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
   if (ix > g.nx + NG) return;
-  {
-    brm[g.at(ix, 0, 0)] = C(0.0, 0.0);
-    bxm[g.at(ix, 0, 0)] = bxm[g.at(ix, 1, 0)];
-    btm[g.at(ix, 0, 0)] = -btm[g.at(ix, 1, 0)];
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
+  const int im = blockIdx.y, task = blockIdx.z;
+  const double mode_sign = (im & 1) ? -1.0 : 1.0;
+  if (task > 0) {
+    const int ir = -task;
+    if (im == 0) {
       btm[g.at(ix, ir, 0)] = -btm[g.at(ix, -ir + 1, 0)];
       brm[g.at(ix, ir, 0)] = -brm[g.at(ix, -ir, 0)];
       bxm[g.at(ix, ir, 0)] = bxm[g.at(ix, -ir + 1, 0)];
+    } else if (im == 1) {
+      btm[g.at(ix, ir, 1)] = btm[g.at(ix, -ir + 1, 1)];
+      brm[g.at(ix, ir, 1)] = brm[g.at(ix, -ir, 1)];
+      bxm[g.at(ix, ir, 1)] = -bxm[g.at(ix, -ir + 1, 1)];
+    } else {
+      btm[g.at(ix, ir, im)] = (-mode_sign) * btm[g.at(ix, -ir + 1, im)];
+      brm[g.at(ix, ir, im)] = (-mode_sign) * brm[g.at(ix, -ir, im)];
+      bxm[g.at(ix, ir, im)] = mode_sign * bxm[g.at(ix, -ir + 1, im)];
     }
+    return;
   }
-  if (g.M > 1) {
-    const size_t a0 = g.at(ix, 0, 1);
+  const size_t a0 = g.at(ix, 0, im);
+  if (im == 0) {
+    brm[a0] = C(0.0, 0.0);
+    bxm[a0] = bxm[g.at(ix, 1, 0)];
+    btm[a0] = -btm[g.at(ix, 1, 0)];
+  } else if (im == 1) {
     bxm[a0] = -bxm[g.at(ix, 1, 1)];
     if (ix >= 2 - NG) {   // fields.f90:272-274 section 2-ng:nx+ng
       brm[a0] = brm[a0] + (((C(0.0, 1.0) / dy) * exm[a0] + (etm[a0] - etm[a0 - 1]) / dx) * 0.5) * dt;
     }
     btm[a0] = C(0.0, -2.0) * brm[a0] - btm[g.at(ix, 1, 1)];
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
-      btm[g.at(ix, ir, 1)] = btm[g.at(ix, -ir + 1, 1)];
-      brm[g.at(ix, ir, 1)] = brm[g.at(ix, -ir, 1)];
-      bxm[g.at(ix, ir, 1)] = -bxm[g.at(ix, -ir + 1, 1)];
-    }
-  }
-  double mode_sign = 1.0;
-  for (int im = 2; im < g.M; ++im) {
-    bxm[g.at(ix, 0, im)] = -bxm[g.at(ix, 1, im)];
-    brm[g.at(ix, 0, im)] = C(0.0, 0.0);
-    btm[g.at(ix, 0, im)] = -btm[g.at(ix, 1, im)];
-    for (int ir = 1 - NG; ir <= -1; ++ir) {
-      btm[g.at(ix, ir, im)] = (-mode_sign) * btm[g.at(ix, -ir + 1, im)];
-      brm[g.at(ix, ir, im)] = (-mode_sign) * brm[g.at(ix, -ir, im)];
-      bxm[g.at(ix, ir, im)] = mode_sign * bxm[g.at(ix, -ir + 1, im)];
-    }
-    mode_sign = -mode_sign;
+  } else {
+    bxm[a0] = -bxm[g.at(ix, 1, im)];
+    brm[a0] = C(0.0, 0.0);
+    btm[a0] = -btm[g.at(ix, 1, im)];
   }
 }
 
@@ -165,7 +167,7 @@ int launch_update_e(cylgpu_ctx* c) {
                                               c->f[CYLGPU_BXM], c->f[CYLGPU_BRM], c->f[CYLGPU_BTM],
                                               c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM], c->cfg.dx,
                                               c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
-  k_update_e_axis<<<(g.SX + 127) / 128, 128, 0, c->stream>>>(g, c->f[CYLGPU_EXM], c->f[CYLGPU_ERM],
+  k_update_e_axis<<<dim3((g.SX + 127) / 128, g.M, NG), 128, 0, c->stream>>>(g, c->f[CYLGPU_EXM], c->f[CYLGPU_ERM],
                                                              c->f[CYLGPU_ETM], c->f[CYLGPU_BTM],
                                                              c->f[CYLGPU_JXM], c->cfg.dy, c->dt);
   c->stats.kernel_launches += 2;
@@ -182,7 +184,7 @@ int launch_update_b(cylgpu_ctx* c) {
                                                 c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
     c->stats.kernel_launches += 1;
   }
-  k_update_b_axis<<<(g.SX + 127) / 128, 128, 0, c->stream>>>(g, c->f[CYLGPU_BXM], c->f[CYLGPU_BRM],
+  k_update_b_axis<<<dim3((g.SX + 127) / 128, g.M, NG), 128, 0, c->stream>>>(g, c->f[CYLGPU_BXM], c->f[CYLGPU_BRM],
                                                              c->f[CYLGPU_BTM], c->f[CYLGPU_EXM],
                                                              c->f[CYLGPU_ETM], c->cfg.dx, c->cfg.dy, c->dt);
   c->stats.kernel_launches += 1;
