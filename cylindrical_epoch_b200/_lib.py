@@ -73,6 +73,7 @@ SYMBOLS = {
     "cylgpu_push_host": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                    C.POINTER(C.c_int64)]),
     "cylgpu_set_host_chunk": (C.c_int, [H, C.c_int64]),
+    "cylgpu_set_current_smoothing": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "cylgpu_current_finish": (C.c_int, [H]),
     "cylgpu_fields_final": (C.c_int, [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cylgpu_window_shift": (C.c_int, [H, C.POINTER(C.c_int64), C.POINTER(C.c_void_p), _DP]),

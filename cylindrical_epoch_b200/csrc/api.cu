@@ -112,6 +112,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->spare);
   for (int k = 0; k < CYLGPU_NSNAPS; ++k) cudaFree(c->snap[k]);
   cudaFree(c->tables); cudaFree(c->src);
+  for (int s = 0; s < 2; ++s) for (int k = 0; k < 3; ++k) cudaFree(c->smooth_wk[s][k]);
   cudaFree(c->sbuf_l); cudaFree(c->sbuf_r); cudaFree(c->rbuf_l); cudaFree(c->rbuf_r);
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i)
 {
@@ -372,6 +373,21 @@ int cylgpu_set_host_chunk(cylgpu_handle c, int64_t particles) {
   TRY(check_handle(c));
   if (particles < 1024 || particles > (int64_t)1 << 30) { set_error("host chunk must be in [1024, 2^30] particles"); return 2; }
   c->host_chunk = particles;
+  return 0;
+}
+
+// smooth_currents / smooth_its / smooth_compensation / smooth_strides of the control block
+// (deck_control_block.F90:447-466, shared_data.F90:468-472)
+int cylgpu_set_current_smoothing(cylgpu_handle c, int enable, int its, int comp_its, int nstrides,
+                                 const int32_t* strides) {
+  TRY(check_handle(c));
+  if (its < 0 || comp_its < 0 || nstrides < 0 || (nstrides > 0 && !strides)) { set_error("bad smoothing settings"); return 2; }
+  for (int k = 0; k < nstrides; ++k)
+    if (strides[k] < 1 || strides[k] > NG) { set_error("smooth_strides must lie in 1..%d", NG); return 2; }
+  c->smooth_currents = enable != 0;
+  c->smooth_its = its;
+  c->smooth_comp_its = comp_its;
+  c->smooth_strides.assign(strides, strides + nstrides);
   return 0;
 }
 

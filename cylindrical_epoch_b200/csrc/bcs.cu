@@ -585,11 +585,89 @@ static int current_bcs_impl(cylgpu_ctx* c, bool with_halo, bool* halo_done) {
 
 int do_current_bcs(cylgpu_ctx* c) { return current_bcs_impl(c, false, nullptr); }
 
-int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45, smoothing off
+// ---- smooth_mode_array, current_smooth.F90:145-196: strided compensated binomial filter ----
+struct Tri3 { cplx* f[3]; };
+// dst(1:nx,1:ny) = alpha*src + (src(ix-s) + src(ix+s) + src(iy-s) + src(iy+s))*beta, three arrays
+__global__ void __launch_bounds__(128) k_smooth(Geom g, Tri3 src, Tri3 dst, double alpha, double beta, int stride) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ix > g.nx) return;
+  const int iy = blockIdx.y + 1;
+  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
+  const cplx* w = src.f[k];
+  const size_t o = g.at(ix, iy, im);
+  const size_t sy = (size_t)stride * g.SX;
+  dst.f[k][o] = alpha * w[o] + (w[o - stride] + w[o + stride] + w[o - sy] + w[o + sy]) * beta;
+}
+// dst(1:nx,1:ny) = src(1:nx,1:ny)
+__global__ void __launch_bounds__(128) k_copy_interior(Geom g, Tri3 src, Tri3 dst) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ix > g.nx) return;
+  const int iy = blockIdx.y + 1;
+  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
+  const size_t o = g.at(ix, iy, im);
+  dst.f[k][o] = src.f[k][o];
+}
+
+static int halo_ptrs(cylgpu_ctx* c, cplx* f0, cplx* f1, cplx* f2) {   // field_mode_bc on three arrays
+  Halo3 h;
+  h.f[0] = f0; h.f[1] = f1; h.f[2] = f2;
+  h.skip[0] = h.skip[1] = h.skip[2] = 0;
+  const bool has_l = c->left >= 0, has_r = c->right >= 0;
+  const bool fill_r = has_r && (!c->cfg.x_max_boundary || c->bc_field[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC);
+  const bool fill_l = has_l && (!c->cfg.x_min_boundary || c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC);
+  return exchange3(c, h, 0, fill_l, fill_r, fill_l, fill_r);
+}
+
+// The reference filters one array after the other through a work copy whose interior is
+// rewritten after every pass and whose ghosts only change through field_mode_bc.  Here the three
+// arrays go together (one packed halo message per pass) and the copy-back is replaced by
+// ping-pong between two work sets that both start as full copies: outside the halo-filled
+// columns their ghosts never change, and the halo-filled ones are refreshed from the source
+// before every pass, so each pass reads exactly what the reference's wk_array holds.  As in the
+// reference, beta keeps its initial value when alpha changes, alpha changes only after pass
+// its+1, and the ghosts of J itself are left as current_finish's halo filled them.
+static int do_smooth_current(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  std::vector<int> strides = c->smooth_strides.empty() ? std::vector<int>{1} : c->smooth_strides;
+  for (int sdv : strides)
+    if (sdv < 1 || sdv > NG) { set_error("smooth_strides must lie in 1..%d (sng <= jng)", NG); return 2; }
+  const size_t bytes = g.plane * g.M * sizeof(cplx);
+  cplx* J[3] = {c->f[CYLGPU_JXM], c->f[CYLGPU_JRM], c->f[CYLGPU_JTM]};
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 3; ++k) {
+      if (!c->smooth_wk[s][k]) CUDA_TRY(cudaMalloc(&c->smooth_wk[s][k], bytes));
+      CUDA_TRY(cudaMemcpyAsync(c->smooth_wk[s][k], J[k], bytes, cudaMemcpyDeviceToDevice, c->stream));
+    }
+  double alpha = 0.5;
+  const double beta = (1.0 - alpha) * 0.25;
+  int cur = 0;
+  const dim3 grd((g.nx + 127) / 128, g.ny, 3 * g.M);
+  for (int it = 1; it <= c->smooth_its + c->smooth_comp_its; ++it) {
+    for (int stride : strides) {
+      cplx** W = c->smooth_wk[cur];
+      cplx** D = c->smooth_wk[cur ^ 1];
+      TRY(halo_ptrs(c, W[0], W[1], W[2]));
+      Tri3 src{{W[0], W[1], W[2]}}, dst{{D[0], D[1], D[2]}};
+      k_smooth<<<grd, 128, 0, c->stream>>>(g, src, dst, alpha, beta, stride);
+      c->stats.kernel_launches += 1;
+      cur ^= 1;
+    }
+    if (it > c->smooth_its) alpha = (double)c->smooth_its * 0.5 + 1.0;
+  }
+  cplx** W = c->smooth_wk[cur];
+  Tri3 src{{W[0], W[1], W[2]}}, dst{{J[0], J[1], J[2]}};
+  k_copy_interior<<<grd, 128, 0, c->stream>>>(g, src, dst);
+  c->stats.kernel_launches += 1;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45
   bool halo_done = false;
   TRY(current_bcs_impl(c, true, &halo_done));
-  if (halo_done) return 0;
-  return halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0);
+  if (!halo_done) TRY(halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0));
+  if (c->smooth_currents) TRY(do_smooth_current(c));
+  return 0;
 }
 
 // ---- setup_field_boundaries, setup.F90:393-423 (no cpml: nx0 = 1, nx1 = nx) ----

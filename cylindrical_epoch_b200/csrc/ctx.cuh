@@ -168,6 +168,13 @@ struct cylgpu_ctx {
   unsigned long long* h_counters = nullptr; // pinned mirror
   double* d_energy = nullptr;
 
+  // current smoothing (current_smooth.F90:49-57,145-196): control-block settings and the two
+  // ping-pong work sets of three mode arrays, allocated on first use
+  bool smooth_currents = false;
+  int smooth_its = 1, smooth_comp_its = 0;
+  std::vector<int> smooth_strides;
+  cylgpu::cplx* smooth_wk[2][3] = {{0, 0, 0}, {0, 0, 0}};
+
   cylgpu::Transport* tr = nullptr;
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)

@@ -351,6 +351,11 @@ class Slab:
     def push_particles_no_bcs(self):
         self._ck(self.L.cylgpu_push_no_bcs(self.h))
 
+    def set_current_smoothing(self, enable, its=1, comp_its=0, strides=()):
+        """smooth_currents, smooth_its, smooth_compensation, smooth_strides (deck_control_block.F90:447-466)"""
+        arr = (C.c_int32 * max(len(strides), 1))(*strides)
+        self._ck(self.L.cylgpu_set_current_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr))
+
     def current_finish(self):                 # current_smooth.F90:29-45
         self._ck(self.L.cylgpu_current_finish(self.h))
 

@@ -179,6 +179,11 @@ int cylgpu_push_host(cylgpu_handle h, const int64_t* n_in, double* const* host_a
                      int64_t* n_out);
 /* particles per chunk of cylgpu_push_host (default 2^21) */
 int cylgpu_set_host_chunk(cylgpu_handle h, int64_t particles);
+/* Current smoothing of current_finish (smooth_current, current_smooth.F90:49-57,145-196): the
+ * control block's smooth_currents, smooth_its, smooth_compensation (0/1) and smooth_strides
+ * (deck_control_block.F90:447-466; nstrides = 0 means stride 1; strides up to ng = 5). */
+int cylgpu_set_current_smoothing(cylgpu_handle h, int enable, int its, int comp_its, int nstrides,
+                                 const int32_t* strides);
 /* current_smooth.F90:29-45 current_finish (smoothing off) */
 int cylgpu_current_finish(cylgpu_handle h);
 /* fields.f90:341-353 update_eb_fields_final.  source1/source2 are the host-evaluated laser

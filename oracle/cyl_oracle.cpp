@@ -1419,11 +1419,55 @@ void World::current_bcs() {
   periodic_sum_x(&Rank::jtm);
 }
 
-void World::current_finish() {   // current_smooth.F90:29-45 (smoothing off)
+void World::current_finish() {   // current_smooth.F90:29-45
   current_bcs();
   halo_x(&Rank::jxm, 0, 0);
   halo_x(&Rank::jrm, 0, 0);
   halo_x(&Rank::jtm, 0, 0);
+  if (smooth_currents) {   // smooth_current, current_smooth.F90:49-57
+    smooth_mode_array(&Rank::jxm);
+    smooth_mode_array(&Rank::jrm);
+    smooth_mode_array(&Rank::jtm);
+  }
+}
+
+// current_smooth.F90:145-196, strided compensated binomial filter.  Restated with its two
+// oddities: beta is computed once from the initial alpha = 0.5 and kept when alpha changes, and
+// alpha changes at the END of iteration its+1, so a single compensation pass (comp_its = 1)
+// still runs with alpha = 0.5.  Strides up to ng (sng <= jng, so ng_l = jng) are supported.
+void World::smooth_mode_array(Arr3 Rank::*f) {
+  std::vector<int> stride_inner = smooth_strides.empty() ? std::vector<int>{1} : smooth_strides;
+  double alpha = 0.5;
+  const double beta = (1.0 - alpha) * 0.25;
+  for (Rank& r : ranks) {
+    r.wk.alloc(r.nx, r.ny, M);
+    r.wk.d = (r.*f).d;
+  }
+  for (int it = 1; it <= smooth_its + smooth_comp_its; ++it) {
+    for (int cstride : stride_inner) {
+      halo_x(&Rank::wk, 0, 0);   // field_mode_bc(wk_array, ng_l)
+      for (Rank& r : ranks) {
+        Arr3& a = r.*f;
+        const Arr3& w = r.wk;
+        for (int im = 0; im < M; ++im)
+          for (int iy = 1; iy <= r.ny; ++iy)
+            for (int ix = 1; ix <= r.nx; ++ix)
+              a(ix, iy, im) = alpha * w(ix, iy, im) +
+                              (w(ix - cstride, iy, im) + w(ix + cstride, iy, im) + w(ix, iy - cstride, im) +
+                               w(ix, iy + cstride, im)) * beta;
+        for (int im = 0; im < M; ++im)
+          for (int iy = 1; iy <= r.ny; ++iy)
+            for (int ix = 1; ix <= r.nx; ++ix) r.wk(ix, iy, im) = a(ix, iy, im);
+      }
+    }
+    if (it > smooth_its) alpha = (double)smooth_its * 0.5 + 1.0;
+  }
+  for (Rank& r : ranks) {
+    Arr3& a = r.*f;
+    for (int im = 0; im < M; ++im)
+      for (int iy = 1; iy <= r.ny; ++iy)
+        for (int ix = 1; ix <= r.nx; ++ix) a(ix, iy, im) = r.wk(ix, iy, im);
+  }
 }
 
 // ---------------------------------------------------------------------------------------

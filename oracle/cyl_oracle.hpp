@@ -144,6 +144,7 @@ struct Rank {
   double x_grid_min_local, x_grid_max_local, x_min_local, x_max_local;
   Arr3 exm, erm, etm, bxm, brm, btm, jxm, jrm, jtm;
   Arr3 bxm_old, brm_old, btm_old, jxm_old, jrm_old, jtm_old;
+  Arr3 wk;   // work array of smooth_mode_array (current_smooth.F90:145-196)
   Arr2 exm_x_min, erm_x_min, etm_x_min, bxm_x_min, brm_x_min, btm_x_min;
   Arr2 exm_x_max, erm_x_max, etm_x_max, bxm_x_max, brm_x_max, btm_x_max;
   std::vector<std::vector<Particle>> parts;   // per species, in linked-list order
@@ -203,6 +204,10 @@ struct World {
   void particle_bcs();                           // boundary.F90:1541-1889
   void current_bcs();                            // boundary.F90:1893-1905
   void current_finish();                         // current_smooth.F90:29-45
+  void smooth_mode_array(Arr3 Rank::*f);         // current_smooth.F90:145-196
+  bool smooth_currents = false;                  // shared_data.F90:468-472
+  int smooth_its = 1, smooth_comp_its = 0;
+  std::vector<int> smooth_strides;
   void moving_window();                          // window.F90:330-376
   void step_once();                              // epoch2d.F90:189-266 loop body
 

@@ -67,6 +67,13 @@ void cylo_get_scalars(void* wp, double* out) {
   out[13] = w->window_started ? 1.0 : 0.0; out[14] = (double)w->window_shifts_total;
 }
 void cylo_set_dt(void* w, double dt) { ((World*)w)->dt = dt; }
+void cylo_set_smoothing(void* wp, int enable, int its, int comp_its, int nstrides, const int32_t* strides) {
+  World* w = (World*)wp;
+  w->smooth_currents = enable != 0;
+  w->smooth_its = its;
+  w->smooth_comp_its = comp_its;
+  w->smooth_strides.assign(strides, strides + nstrides);
+}
 void cylo_set_time(void* w, double t) { ((World*)w)->time = t; }
 void cylo_get_bc_field(void* w, int32_t* out) { for (int i = 0; i < 4; ++i) out[i] = ((World*)w)->bc_field[i]; }
 void cylo_get_bc_particle(void* w, int isp, int32_t* out) {

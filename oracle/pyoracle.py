@@ -72,6 +72,8 @@ def lib():
         L.cylo_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.cylo_set_dt.argtypes = [C.c_void_p, C.c_double]
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_set_smoothing.restype = None
+        L.cylo_set_smoothing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.cylo_get_bc_field.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.cylo_get_bc_particle.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32)]
         L.cylo_rank_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
@@ -144,6 +146,11 @@ class OracleWorld:
 
     def set_dt(self, dt):
         self.L.cylo_set_dt(self.h, dt)
+
+    def set_smoothing(self, enable, its=1, comp_its=0, strides=()):
+        """smooth_currents, smooth_its, smooth_compensation, smooth_strides of the control block"""
+        arr = (C.c_int32 * max(len(strides), 1))(*strides)
+        self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
 
     def set_time(self, t):
         self.L.cylo_set_time(self.h, t)

@@ -36,7 +36,7 @@ class Pair:
     """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
 
     def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None, host_resident=False,
-                 host_chunk=None):
+                 host_chunk=None, smoothing=None):
         self.deck = deck
         self.nranks = nranks
         self.oracle = decks.make_oracle(deck, nranks=nranks)
@@ -54,6 +54,10 @@ class Pair:
                 s.set_push_variant(variant)
             if sort_interval is not None:
                 s.set_sort_interval(sort_interval)
+            if smoothing is not None:
+                s.set_current_smoothing(True, **smoothing)
+        if smoothing is not None:
+            self.oracle.set_smoothing(True, **smoothing)
         if init_half_step:
             self.oracle.call("init_half_step")
             self.each(lambda s: s.init_half_step())

@@ -219,6 +219,35 @@ def test_host_resident_lists_streamed_push(deckname, nranks):
         p.close()
 
 
+@pytest.mark.parametrize("deckname,nranks,smoothing", [
+    ("lwfa", 1, dict(its=1, comp_its=1, strides=(1, 2, 3, 4))),     # smooth_strides = auto
+    ("lwfa", 2, dict(its=1, comp_its=1, strides=(1, 2, 3, 4))),
+    ("thermal", 2, dict(its=2, comp_its=2, strides=(1,))),            # alpha changes after pass its+1
+    ("thermal", 1, dict(its=1, comp_its=0, strides=())),              # default stride
+])
+def test_current_smoothing(deckname, nranks, smoothing):
+    """smooth_current (current_smooth.F90:49-57,145-196) inside current_finish: strided compensated
+    binomial filter of jxm, jrm, jtm with halo exchange between the passes"""
+    if deckname == "lwfa":
+        d, tol = decks.lwfa(nx=96, ny=32, n_mode=2, ppc_e=4, ppc_p=1), 1e-9
+    else:
+        d, tol = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8), TOL_HOT
+    p = Pair(d, nranks=nranks, smoothing=smoothing)
+    q = Pair(d, nranks=1)
+    try:
+        p.step(12)
+        q.step(12)
+        p.check_counts()
+        p.check_fields(tol)
+        p.check_particles(tol)
+        # and the filter really ran: J differs from the unsmoothed run
+        a, b = p.oracle.field(0, "jxm"), q.oracle.field(0, "jxm")
+        assert np.abs(a[:, 5:-5, 5:a.shape[2] // 2] - b[:, 5:-5, 5:a.shape[2] // 2]).max() > 1e-3 * np.abs(b).max()
+    finally:
+        p.close()
+        q.close()
+
+
 def test_kiss_stream_matches_oracle():
     """random(), random_box_muller() of random_generator.f90: the product's stream is the oracle's, bit for bit"""
     d = decks.lwfa(nx=32, ny=12, n_mode=1, ppc_e=1)
