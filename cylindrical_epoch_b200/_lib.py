@@ -93,6 +93,7 @@ SYMBOLS = {
     "cylgpu_push_no_bcs": (C.c_int, [H]),
     "cylgpu_current_bcs": (C.c_int, [H]),
     "cylgpu_sort_particles": (C.c_int, [H]),
+    "cylgpu_set_pusher": (C.c_int, [H, C.c_int]),
     "cylgpu_set_sort_interval": (C.c_int, [H, C.c_int]),
     "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
     "cylgpu_energy": (C.c_int, [H, _DP]),

@@ -707,6 +707,8 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   P.ccmratio = C_LIGHT * P.cmratio;
   P.q_fac = S.sp.charge * fac;
   P.deposit = S.sp.zero_current ? 0 : 1;
+  P.hc_push = c->hc_push ? 1 : 0;
+  P.hc_alpha = 0.5 * S.sp.charge * dt / S.sp.mass;
   const int64_t nb = (S.n + 127) / 128;
   PhaseTimer kernel_timer(c, &c->stats.ms_push_kernel, &c->stats.n_push_kernel, time_kernel);
   const int ncx = g.nx + 2 * CELL_PAD, ncy = g.ny + 2 * CELL_PAD;

@@ -17,7 +17,9 @@ struct PushConst {
   double idx, idy, idt, dtco2;
   double cmratio, ccmratio, part_mc, ipart_mc;
   double q_fac;              // part_q * fac  (q_weight_fac = q_fac * weight)
+  double hc_alpha;           // 0.5 * part_q * dt / part_m (Higuera-Cary, particles.F90:413)
   int deposit;
+  int hc_push;               // the reference's -DHC_PUSH build
 };
 
 // triangle weights (unnormalised, sum = 2): gx.inc / hx_dcell.inc
@@ -317,7 +319,19 @@ __device__ __forceinline__ void push_post(const PushConst& P, const PushMid& S, 
   const double uym = S.uy + P.cmratio * ey_part;
   const double uzm = S.uz + P.cmratio * ez_part;
   double gamma_rel, igamma;
-  sqrt_rsqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0, gamma_rel, igamma);
+  if (P.hc_push) {
+    // Higuera-Cary gamma (particles.F90:409-421); not the default build, plain IEEE operations
+    gamma_rel = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+    const double beta_x = P.hc_alpha * bx_part, beta_y = P.hc_alpha * by_part, beta_z = P.hc_alpha * bz_part;
+    const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+    const double sigma = gamma_rel - beta2;
+    const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+    gamma_rel = sigma + sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u));
+    gamma_rel = sqrt(0.5 * gamma_rel);
+    igamma = 1.0 / gamma_rel;
+  } else {
+    sqrt_rsqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0, gamma_rel, igamma);
+  }
   double root = P.ccmratio * igamma;
   const double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
   const double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;

@@ -269,6 +269,9 @@ class Slab:
                                                 float(sp.density_min), float(sp.density_max), C.byref(n)))
         return n.value
 
+    def set_pusher(self, higuera_cary):       # -DHC_PUSH, particles.F90:409-421
+        self._ck(self.L.cylgpu_set_pusher(self.h, int(bool(higuera_cary))))
+
     def set_sort_interval(self, n):
         self._ck(self.L.cylgpu_set_sort_interval(self.h, n))
 

@@ -230,6 +230,9 @@ int cylgpu_bfield_final_bcs(cylgpu_handle h, const double* src1_xmin, const doub
 int cylgpu_particle_bcs(cylgpu_handle h);                   /* boundary.F90:1541-1889 */
 int cylgpu_push_no_bcs(cylgpu_handle h);                    /* particles.F90:163-730 + :1909 */
 int cylgpu_current_bcs(cylgpu_handle h);                    /* boundary.F90:1893-1905 */
+/* Momentum rotation: 0 = Boris (default build), 1 = Higuera-Cary (the reference's -DHC_PUSH
+ * build, particles.F90:409-421). */
+int cylgpu_set_pusher(cylgpu_handle h, int higuera_cary);
 /* cell-tile sort of the SoA arrays (no reference counterpart: replaces the linked list) */
 int cylgpu_sort_particles(cylgpu_handle h);
 int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = never */

@@ -964,7 +964,19 @@ void World::push_rank(Rank& r) {
       double uxm = part_ux + cmratio * ex_part;
       double uym = part_uy + cmratio * ey_part;
       double uzm = part_uz + cmratio * ez_part;
-      gamma_rel = std::sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+      if (hc_push) {
+        // Higuera-Cary (particles.F90:409-421, -DHC_PUSH)
+        gamma_rel = uxm * uxm + uym * uym + uzm * uzm + 1.0;
+        const double alpha = 0.5 * part_q * dt / sp.mass;
+        const double beta_x = alpha * bx_part, beta_y = alpha * by_part, beta_z = alpha * bz_part;
+        const double beta2 = beta_x * beta_x + beta_y * beta_y + beta_z * beta_z;
+        const double sigma = gamma_rel - beta2;
+        const double beta_dot_u = beta_x * uxm + beta_y * uym + beta_z * uzm;
+        gamma_rel = sigma + std::sqrt(sigma * sigma + 4.0 * (beta2 + beta_dot_u * beta_dot_u));
+        gamma_rel = std::sqrt(0.5 * gamma_rel);
+      } else {
+        gamma_rel = std::sqrt(uxm * uxm + uym * uym + uzm * uzm + 1.0);
+      }
       root = ccmratio / gamma_rel;
       double taux = bx_part * root, tauy = by_part * root, tauz = bz_part * root;
       double taux2 = taux * taux, tauy2 = tauy * tauy, tauz2 = tauz * tauz;

@@ -206,6 +206,7 @@ struct World {
   void current_finish();                         // current_smooth.F90:29-45
   void smooth_mode_array(Arr3 Rank::*f);         // current_smooth.F90:145-196
   bool smooth_currents = false;                  // shared_data.F90:468-472
+  bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
   int smooth_its = 1, smooth_comp_its = 0;
   std::vector<int> smooth_strides;
   void moving_window();                          // window.F90:330-376

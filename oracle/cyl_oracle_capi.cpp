@@ -67,6 +67,7 @@ void cylo_get_scalars(void* wp, double* out) {
   out[13] = w->window_started ? 1.0 : 0.0; out[14] = (double)w->window_shifts_total;
 }
 void cylo_set_dt(void* w, double dt) { ((World*)w)->dt = dt; }
+void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
 void cylo_set_smoothing(void* wp, int enable, int its, int comp_its, int nstrides, const int32_t* strides) {
   World* w = (World*)wp;
   w->smooth_currents = enable != 0;

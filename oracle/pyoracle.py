@@ -72,6 +72,8 @@ def lib():
         L.cylo_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.cylo_set_dt.argtypes = [C.c_void_p, C.c_double]
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_set_hc_push.restype = None
+        L.cylo_set_hc_push.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_smoothing.restype = None
         L.cylo_set_smoothing.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
         L.cylo_get_bc_field.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
@@ -151,6 +153,10 @@ class OracleWorld:
         """smooth_currents, smooth_its, smooth_compensation, smooth_strides of the control block"""
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
         self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
+
+    def set_hc_push(self, on):
+        """the reference's -DHC_PUSH build: Higuera-Cary gamma instead of Boris'"""
+        self.L.cylo_set_hc_push(self.h, int(on))
 
     def set_time(self, t):
         self.L.cylo_set_time(self.h, t)

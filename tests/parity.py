@@ -36,10 +36,12 @@ class Pair:
     """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
 
     def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None, host_resident=False,
-                 host_chunk=None, smoothing=None):
+                 host_chunk=None, smoothing=None, hc_push=False, prepare=None):
         self.deck = deck
         self.nranks = nranks
         self.oracle = decks.make_oracle(deck, nranks=nranks)
+        if prepare is not None:
+            prepare(self.oracle)    # edit the initial state before the product copies it
         self.fabric = None
         kw = {}
         if nranks > 1:
@@ -58,6 +60,10 @@ class Pair:
                 s.set_current_smoothing(True, **smoothing)
         if smoothing is not None:
             self.oracle.set_smoothing(True, **smoothing)
+        if hc_push:
+            self.oracle.set_hc_push(True)
+            for s in self.slabs:
+                s.set_pusher(True)
         if init_half_step:
             self.oracle.call("init_half_step")
             self.each(lambda s: s.init_half_step())

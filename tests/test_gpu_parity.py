@@ -248,6 +248,31 @@ def test_current_smoothing(deckname, nranks, smoothing):
         q.close()
 
 
+@pytest.mark.parametrize("variant", [0, 3])
+def test_higuera_cary_pusher(variant):
+    """the reference's -DHC_PUSH build (particles.F90:409-421): Higuera-Cary gamma in the rotation.
+    Hot plasma (u ~ 0.5) in a strong axial field (omega_c dt ~ 1), where the two pushers differ."""
+    d = decks.thermal(nx=48, ny=24, n_mode=2, ppc=4, temp_k=1.0e9)
+
+    def strong_bx(oracle):
+        oracle.field(0, "bxm")[0, :, :] = 5.0e3    # tesla, m = 0
+
+    p = Pair(d, variant=variant, hc_push=True, prepare=strong_bx)
+    q = Pair(d, variant=variant, prepare=strong_bx)
+    try:
+        p.step(6)
+        q.step(6)
+        for r in (p, q):
+            r.check_counts()
+            r.check_fields(TOL_HOT)
+            r.check_particles(TOL_HOT)
+        a, b = by_weight(p.oracle.particles(0, 0)), by_weight(q.oracle.particles(0, 0))
+        assert np.abs(a[:, 3:6] - b[:, 3:6]).max() > 1e-4 * np.abs(b[:, 3:6]).max()   # a different pusher
+    finally:
+        p.close()
+        q.close()
+
+
 def test_kiss_stream_matches_oracle():
     """random(), random_box_muller() of random_generator.f90: the product's stream is the oracle's, bit for bit"""
     d = decks.lwfa(nx=32, ny=12, n_mode=1, ppc_e=1)
