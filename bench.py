@@ -340,9 +340,9 @@ def run_ours(args, wl_name, wl):
                 "binding_pipes_from_ncu": ({k: ncu[k] for k in ("lsu_data_pipe_pct", "fp64_pipe_pct", "dmma_pipe_pct",
                                                                   "issue_active_pct", "shared_atomics",
                                                                   "global_red_instructions", "source")} if ncu else None),
-                "note": "FP64 arithmetic (about 0.75 k FP64 instructions + 81 DMMA per 32 particle-steps) puts the "
-                        "FP64-pipe floor of this kernel at ~2.6x the HBM floor; the kernel is bound by the "
-                        "LSU/shared-memory data pipe, see DESIGN.md 3.1",
+                "note": "FP64 arithmetic (704 FP64 instructions + 76 DMMA per 32 particle-steps) puts the "
+                        "FP64-pipe floor of this kernel at 4.6x its HBM floor (2.6 vs 0.56 ms); it is co-limited by the "
+                        "shared-memory data pipe (2.9 ms floor), the FP64 pipe and issue at 12 warps per SM, see DESIGN.md 3.1",
                 "kernel_ms_per_launch": dur * 1e3, "algorithmic_bytes_per_particle_step": bp,
                 "kernel_particle_steps_per_s": per_launch / dur,
                 "kernel_share_of_step": st.ms_push_kernel / (wall * 1e3)}
