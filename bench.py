@@ -93,54 +93,68 @@ def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, mass):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons of this rank's GPU sampled DURING the timed region (the numbers
+    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints, read through NVML in-process:
+    one nvidia-smi per rank enumerating all GPUs under the driver lock stalled 4- and 8-rank runs)."""
 
     def __init__(self, index=0):
-        self.lines = []
-        self.proc = None
         self.index = index
+        self.samples = []      # (sm_mhz, sm_max_mhz, reasons bitmask)
+        self.on = False
+        self.nvml = None
+        self.handle = None
+        self.thread = None
+        try:   # in-process NVML: no nvidia-smi start-up (which enumerates every GPU under the driver lock)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:   # noqa: BLE001
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(local):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if local < len(ids) and ids[local].isdigit():
+                return int(ids[local])
+        return local
+
+    def _loop(self):
+        nv = self.nvml
+        while self.on:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((sm, rs))
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(0.02)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:   # noqa: BLE001
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        if self.nvml is None:
+            return
+        self.on = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:   # noqa: BLE001
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                smax = float(parts[1])
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        self.on = False
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        nv = self.nvml
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        reasons = sorted(nm for nm, bit in names.items() if any(rs & bit for _, rs in self.samples))
+        sm = [v for v, _ in self.samples]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.sm_max, "reasons": reasons,
+                "samples": len(sm), "source": "NVML, sampled every 20 ms during the timed region"}
 
 
 def dist_env():
@@ -239,6 +253,15 @@ def run_ours(args, wl_name, wl):
     if not os.path.exists(os.path.join(ROOT, "cylindrical_epoch_b200", "libcylgpu.so")):
         cbuild.build()
     torch.cuda.set_device(local)
+    if world > 1 and hasattr(os, "sched_setaffinity") and not os.environ.get("BENCH_NO_PIN"):
+        # one disjoint block of host cores per rank: the step is a chain of short kernels, and ranks whose
+        # launching thread shares cores with the other ranks' spinning threads fall behind their neighbours
+        try:
+            cpus = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cpus) // world)
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]) or set(cpus))
+        except OSError:
+            pass
     dist = None
     uid = None
     if world > 1:
@@ -292,9 +315,10 @@ def run_ours(args, wl_name, wl):
         slab.step_once()
     e_f0, e_k0 = slab.energy()
     slab.reset_stats()
-    clocks = ClockSampler(local)
+    clocks = ClockSampler(local) if rank == 0 else None   # rank 0's GPU stands for the box
     barrier()
-    clocks.start()
+    if clocks:
+        clocks.start()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
@@ -307,8 +331,12 @@ def run_ours(args, wl_name, wl):
     barrier()
     wall_host = time.perf_counter() - t0
     wall = ev0.elapsed_time(ev1) * 1e-3   # device time, CUDA events on the launching stream
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks else None
     st = slab.stats()
+    if os.environ.get("BENCH_RANK_PHASES"):
+        sys.stderr.write("rank %d: wall %.3f ms/step fields %.3f push %.3f (kernel %.3f sort %.3f) bcs %.3f exchange %.3f\n" % (
+            rank, 1e3 * ev0.elapsed_time(ev1) * 1e-3 / args.steps, st.ms_fields / args.steps, st.ms_push / args.steps,
+            st.ms_push_kernel / args.steps, st.ms_sort / args.steps, st.ms_bcs / args.steps, st.ms_exchange / args.steps))
     e_f1, e_k1 = slab.energy()
     # max over ranks of the device-event time; particle-steps summed over ranks
     tt = torch.tensor([wall, float(n_steps_particles)], dtype=torch.float64, device="cuda")
@@ -357,7 +385,9 @@ def run_ours(args, wl_name, wl):
                    "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host},
         "field_cell_mode_updates_per_s": field_rate,
         "phase_ms_per_step": {"fields": st.ms_fields / args.steps, "push_total": st.ms_push / args.steps,
-                              "push_kernel": st.ms_push_kernel / args.steps, "bcs_and_exchange": st.ms_bcs / args.steps},
+                              "push_kernel": st.ms_push_kernel / args.steps, "sort": st.ms_sort / args.steps,
+                              "current_finish": st.ms_bcs / args.steps,
+                              "neighbour_exchanges_incl_waiting": st.ms_exchange / args.steps},
         "energy": {"field_J": e_f1, "kinetic_J": e_k1,
                    "relative_drift_over_timed_steps": abs((e_f1 + e_k1) - (e_f0 + e_k0)) / (e_f0 + e_k0)},
         "roofline": roof, "clocks": clk, "gpu_launches": int(st.kernel_launches),

@@ -2,6 +2,9 @@
 #include <cstdarg>
 #include <cstring>
 
+#include <cstdlib>
+#include <functional>
+
 #include "ctx.cuh"
 
 namespace cylgpu {
@@ -98,6 +101,10 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   set_neighbours(c);
   c->tr = make_transport(c);
   if (!c->tr) return 6;
+  // several ranks on one host: host syncs yield the core (CYLGPU_BLOCKING_WAIT=0/1 overrides)
+  c->blocking_wait = c->cfg.nranks > 1 && c->cfg.transport != CYLGPU_TRANSPORT_FABRIC;
+  if (const char* e = getenv("CYLGPU_BLOCKING_WAIT")) c->blocking_wait = atoi(e) != 0;
+  if (const char* e = getenv("CYLGPU_GRAPHS")) c->use_graphs = atoi(e) != 0;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   *out = c;
   return 0;
@@ -107,6 +114,8 @@ int cylgpu_destroy(cylgpu_handle c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  // the captured field phases hold NCCL send/recv nodes: they go before the communicator
+  for (int k = 0; k < 2; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
   destroy_transport(c->tr);
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) cudaFree(c->f[k]);
   cudaFree(c->spare);
@@ -125,6 +134,8 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->psend_l); cudaFree(c->psend_r); cudaFree(c->precv);
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   c->timers.destroy();
+  if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+  if (c->src_stage) { cudaFreeHost(c->src_stage); for (int k = 0; k < 8; ++k) cudaEventDestroy(c->src_event[k]); }
   for (int k = 0; k < 3; ++k) {
     cudaFree(c->hs.in[k]);
     if (c->hs.ev_up[k]) cudaEventDestroy(c->hs.ev_up[k]);
@@ -154,12 +165,14 @@ int cylgpu_set_species(cylgpu_handle c, int isp, const cylgpu_species* sp) {
 int cylgpu_set_dt(cylgpu_handle c, double dt) {
   TRY(check_handle(c));
   c->dt = dt;
+  c->graph_epoch += 1;
   return 0;
 }
 
 int cylgpu_set_bc_field(cylgpu_handle c, const int32_t bc[4]) {
   TRY(check_handle(c));
   for (int i = 0; i < 4; ++i) c->bc_field[i] = bc[i];
+  c->graph_epoch += 1;
   // the Cartesian communicator is created once (mpi_routines.F90:179-227); neighbours stay
   return 0;
 }
@@ -167,6 +180,7 @@ int cylgpu_set_bc_field(cylgpu_handle c, const int32_t bc[4]) {
 int cylgpu_set_stream(cylgpu_handle c, void* stream) {
   TRY(check_handle(c));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  c->graph_epoch += 1;
   if (c->own_stream) { cudaStreamDestroy(c->stream); c->own_stream = false; }
   if (stream) {
     c->stream = (cudaStream_t)stream;
@@ -340,10 +354,56 @@ int cylgpu_set_pusher(cylgpu_handle c, int higuera_cary) { TRY(check_handle(c));
 int cylgpu_set_sort_interval(cylgpu_handle c, int n) { TRY(check_handle(c)); c->sort_interval = n; return 0; }
 int cylgpu_set_push_variant(cylgpu_handle c, int v) { TRY(check_handle(c)); c->push_variant = v; return 0; }
 
-// fields.f90:316-337
-int cylgpu_fields_half(cylgpu_handle c) {
-  TRY(check_handle(c));
-  PhaseTimer t(c, &c->stats.ms_fields);
+// Run one field phase: directly, or -- once its parameters have been the same for three calls and
+// the transport can be captured (none / NCCL) -- as a replayed CUDA graph, so that the ~15 short
+// dependent launches of the phase cost one launch and do not depend on the host keeping ahead.
+static int run_field_phase(cylgpu_ctx* c, int which, const std::function<int()>& body) {
+  cylgpu_ctx::PhaseGraph& G = c->graphs[which];
+  const bool capturable = c->use_graphs && !G.failed &&
+                          (c->cfg.transport == CYLGPU_TRANSPORT_NONE || c->cfg.transport == CYLGPU_TRANSPORT_NCCL);
+  if (!capturable) return body();
+  if (G.seen_epoch == c->graph_epoch) G.stable_calls += 1;
+  else { G.seen_epoch = c->graph_epoch; G.stable_calls = 0; }
+  if (G.exec && G.epoch == c->graph_epoch) {
+    CUDA_TRY(cudaGraphLaunch(G.exec, c->stream));
+    c->stats.kernel_launches += G.launches;
+    return 0;
+  }
+  if (G.stable_calls < 3) return body();
+  // capture
+  if (G.exec) { cudaGraphExecDestroy(G.exec); G.exec = nullptr; }
+  const bool timing = c->timing;
+  const int64_t launches0 = c->stats.kernel_launches;
+  c->timing = false;   // events recorded inside a capture cannot be read back
+  cudaGraph_t graph = nullptr;
+  int rc = 0;
+  if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    c->timing = timing;
+    G.failed = true;
+    return body();
+  }
+  rc = body();
+  const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+  c->timing = timing;
+  G.launches = c->stats.kernel_launches - launches0;
+  c->stats.kernel_launches = launches0;
+  if (rc != 0 || ce != cudaSuccess || !graph ||
+      cudaGraphInstantiate(&G.exec, graph, nullptr, nullptr, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    G.exec = nullptr;
+    G.failed = true;   // this configuration cannot be captured: stay on direct launches
+    return body();
+  }
+  cudaGraphDestroy(graph);
+  G.epoch = c->graph_epoch;
+  CUDA_TRY(cudaGraphLaunch(G.exec, c->stream));
+  c->stats.kernel_launches += G.launches;
+  return 0;
+}
+
+static int fields_half_body(cylgpu_ctx* c) {
   TRY(launch_update_e(c));
   TRY(do_efield_bcs(c));
   // bxm_old = bxm etc. (fields.f90:326-328)
@@ -353,6 +413,13 @@ int cylgpu_fields_half(cylgpu_handle c) {
   CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BTM_OLD], c->f[CYLGPU_BTM], bytes, cudaMemcpyDeviceToDevice, c->stream));
   TRY(launch_update_b(c));
   return do_bfield_bcs(c, true);
+}
+
+// fields.f90:316-337
+int cylgpu_fields_half(cylgpu_handle c) {
+  TRY(check_handle(c));
+  PhaseTimer t(c, &c->stats.ms_fields);
+  return run_field_phase(c, 0, [c]() { return fields_half_body(c); });
 }
 
 // particles.F90:28-734 (push + r_min fold + particle_bcs)
@@ -403,10 +470,13 @@ int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2mi
                         const double* s2max) {
   TRY(check_handle(c));
   PhaseTimer t(c, &c->stats.ms_fields);
-  TRY(launch_update_b(c));
-  TRY(do_bfield_final_bcs(c, s1min, s2min, s1max, s2max));
-  TRY(launch_update_e(c));
-  return do_efield_bcs(c);
+  TRY(upload_laser_sources(c, s1min, s2min, s1max, s2max));
+  return run_field_phase(c, 1, [c]() -> int {
+    TRY(launch_update_b(c));
+    TRY(do_bfield_final_bcs_device(c));
+    TRY(launch_update_e(c));
+    return do_efield_bcs(c);
+  });
 }
 
 // window.F90:62-94, one cell.  grid5 = {x_grid_min_local, x_min, x_max, x_min_local,
@@ -414,6 +484,7 @@ int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2mi
 int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* const* new_aos, const double* grid5) {
   TRY(check_handle(c));
   if (!grid5) { set_error("window_shift needs the shifted grid"); return 2; }
+  c->graph_epoch += 1;   // shift_fields swaps array pointers
   if (n_new && new_aos) {
     for (int isp = 0; isp < c->cfg.n_species; ++isp)
       if (n_new[isp] > 0) TRY(append_impl(c, isp, n_new[isp], new_aos[isp]));

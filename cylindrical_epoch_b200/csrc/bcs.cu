@@ -4,6 +4,8 @@
 // particle_reflection_bcs_complex, particle_periodic_bcs_complex, efield_bcs, bfield_bcs,
 // bfield_final_bcs, current_bcs, current_bcs_r_min_final), laser.f90 outflow_bcs_*,
 // current_smooth.F90 current_finish and window.F90 shift_fields.
+#include <cstring>
+
 #include "ctx.cuh"
 
 namespace cylgpu {
@@ -363,19 +365,41 @@ static FieldSet fieldset(cylgpu_ctx* c) {
   return F;
 }
 
-int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
-                        const double* s2max) {
+// host laser sources -> device (outside any captured graph: the staging slot rotates)
+int upload_laser_sources(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
+                         const double* s2max) {
+  const Geom& g = c->g;
+  const int nsrc = g.ny + 1;
+  // sources are host arrays evaluated by the Fortran laser blocks (laser.f90:442-461).  They are
+  // copied into a pinned staging slot of the library (8 rotating slots, each guarded by an event),
+  // so that the caller may reuse its arrays at once and the step needs no host sync here.
+  const double* hs[4] = {s1min, s2min, s1max, s2max};
+  {
+    const size_t slot_doubles = (size_t)4 * nsrc;
+    if (!c->src_stage) {
+      CUDA_TRY(cudaMallocHost(&c->src_stage, 8 * slot_doubles * sizeof(double)));
+      for (int k = 0; k < 8; ++k) CUDA_TRY(cudaEventCreateWithFlags(&c->src_event[k], cudaEventDisableTiming));
+    }
+    const int slot = c->src_slot;
+    c->src_slot = (c->src_slot + 1) & 7;
+    CUDA_TRY(cudaEventSynchronize(c->src_event[slot]));   // long done unless the host runs 8 steps ahead
+    double* st = c->src_stage + slot * slot_doubles;
+    for (int k = 0; k < 4; ++k) {
+      if (hs[k]) std::memcpy(st + (size_t)k * nsrc, hs[k], nsrc * sizeof(double));
+      else std::memset(st + (size_t)k * nsrc, 0, nsrc * sizeof(double));
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->src, st, slot_doubles * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(cudaEventRecord(c->src_event[slot], c->stream));
+  }
+  return 0;
+}
+
+// bfield_final_bcs, boundary.F90:1505-1537, with the sources already in c->src
+int do_bfield_final_bcs_device(cylgpu_ctx* c) {
   const Geom& g = c->g;
   TRY(do_bfield_bcs(c, false));
   FieldSet F = fieldset(c);
   const int nsrc = g.ny + 1;
-  // sources are host arrays evaluated by the Fortran laser blocks (laser.f90:442-461)
-  const double* hs[4] = {s1min, s2min, s1max, s2max};
-  for (int k = 0; k < 4; ++k) {
-    if (hs[k]) CUDA_TRY(cudaMemcpyAsync(c->src + (size_t)k * nsrc, hs[k], nsrc * sizeof(double),
-                                        cudaMemcpyHostToDevice, c->stream));
-    else CUDA_TRY(cudaMemsetAsync(c->src + (size_t)k * nsrc, 0, nsrc * sizeof(double), c->stream));
-  }
   dim3 grd((g.ny + 1 + 127) / 128, g.M);
   if (c->cfg.x_min_boundary) {
     const int b = c->bc_field[CYLGPU_BD_X_MIN];
@@ -406,9 +430,13 @@ int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min,
     c->stats.kernel_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
-  // the source upload must have been consumed before the caller reuses its host arrays
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
   return do_bfield_bcs(c, true);
+}
+
+int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
+                        const double* s2max) {
+  TRY(upload_laser_sources(c, s1min, s2min, s1max, s2max));
+  return do_bfield_final_bcs_device(c);
 }
 
 // ---- currents ----

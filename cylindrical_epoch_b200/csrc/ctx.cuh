@@ -144,6 +144,9 @@ struct cylgpu_ctx {
   double* tables = nullptr;               // 4 x (ny + 2*JNG + 1) radial tables (particles.F90:190-217)
   int ntab = 0;
   double* src = nullptr;                  // 4 x (ny+1) laser sources (device)
+  double* src_stage = nullptr;            // pinned staging: 8 slots of 4 x (ny+1)
+  cudaEvent_t src_event[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int src_slot = 0;
 
   // halo staging: [3 comps][M][SY][NG] complex each
   cylgpu::cplx *sbuf_l = nullptr, *sbuf_r = nullptr, *rbuf_l = nullptr, *rbuf_r = nullptr;
@@ -175,6 +178,20 @@ struct cylgpu_ctx {
   std::vector<int> smooth_strides;
   cylgpu::cplx* smooth_wk[2][3] = {{0, 0, 0}, {0, 0, 0}};
 
+  // The two field phases are chains of ~15 short launches each: replayed as CUDA graphs once their
+  // parameters have been stable for a few steps (dt, bc_field, array pointers, stream: `graph_epoch`).
+  struct PhaseGraph {
+    cudaGraphExec_t exec = nullptr;
+    uint64_t epoch = ~0ull;       // epoch the executable was captured for
+    uint64_t seen_epoch = ~0ull;  // epoch of the previous call
+    int stable_calls = 0;
+    int64_t launches = 0;         // kernel launches inside (for the statistics)
+    bool failed = false;
+  };
+  PhaseGraph graphs[2];
+  uint64_t graph_epoch = 0;
+  bool use_graphs = true;
+
   cylgpu::Transport* tr = nullptr;
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)
@@ -191,6 +208,8 @@ struct cylgpu_ctx {
   cylgpu_stats_t stats;
   cylgpu::TimerPool timers;
   bool timing = true;
+  bool blocking_wait = false;     // host syncs yield the core instead of spinning (multi-rank hosts)
+  cudaEvent_t ev_wait = nullptr;
 };
 
 namespace cylgpu {
@@ -203,6 +222,9 @@ int do_efield_bcs(cylgpu_ctx* c);
 int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only);
 int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
                         const double* s2max);
+int upload_laser_sources(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
+                         const double* s2max);
+int do_bfield_final_bcs_device(cylgpu_ctx* c);
 int do_current_bcs(cylgpu_ctx* c);
 int do_current_finish(cylgpu_ctx* c);
 int do_r_min_final(cylgpu_ctx* c);

@@ -55,10 +55,11 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
   const double third = 1.0 / 3.0;
   // radial tables of the 5 window rows: the strip's copy in shared memory (stab[t*5 + ky], staged
   // for base_y == stab_row) or, for a window of another row, the global tables
+  // (one generic pointer, so that only one of the two loads is ever issued)
   const bool tab_sm = (base_y == stab_row);
-  auto tab = [&](int t, int ky) -> double {
-    return tab_sm ? stab[t * 5 + ky] : __ldg(P.tab + t * P.ntab + JNG + base_y - 2 + ky);
-  };
+  const double* tab_base = tab_sm ? stab : P.tab + JNG + base_y - 2;
+  const int tab_stride = tab_sm ? 5 : P.ntab;
+  auto tab = [&](int t, int ky) -> double { return tab_base[t * tab_stride + ky]; };
 
   // per-warp staging: three V tiles (A: run, B: gx, H: hx) and two U tiles
   double* VA = wbuf;
@@ -141,8 +142,9 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
           const int im = (coef + 1) >> 1;                                      \
           const bool imag = coef > 0 && ((coef + 1) & 1);                      \
           double val = 0.0;                                                    \
-          if (c < R) { UEXPR; }                                                \
-          Us[(tt * 8 + r) * MMA_PITCH + lane] = val;                           \
+          /* rows >= R are padding: their accumulators are never flushed, so   \
+             whatever the tile holds there is harmless and need not be stored */ \
+          if (c < R) { UEXPR; Us[(tt * 8 + r) * MMA_PITCH + lane] = val; }     \
         }                                                                      \
       }                                                                        \
     }                                                                          \

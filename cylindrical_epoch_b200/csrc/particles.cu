@@ -675,7 +675,10 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   cylgpu::SpeciesState& S = c->species[isp];
   if (fused_out) *fused_out = false;
   if (!S.set || S.sp.immobile || S.n == 0) return 0;
-  if (need_sort) TRY(do_sort_species(c, isp, /*physical=*/!strips));
+  if (need_sort) {
+    PhaseTimer sort_timer(c, &c->stats.ms_sort);
+    TRY(do_sort_species(c, isp, /*physical=*/!strips));
+  }
   FusedBcs FB;
   FB.enabled = 0;
   if (fuse_bcs && strips) {
@@ -719,7 +722,11 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
 #define LAUNCH_STRIP(MM, MMA)                                                                              \
   do {                                                                                                     \
     const size_t shb = strip_smem_bytes<MM>(MMA);                                                          \
-    CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
+    static bool smem_opted_in[64] = {false};   /* per instantiation and device: the attribute is a driver call */ \
+    if (!smem_opted_in[c->device & 63]) {                                                                  \
+      CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
+      smem_opted_in[c->device & 63] = true;                                                                \
+    }                                                                                                      \
     k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x, FB); \
   } while (0)
 #define LAUNCH_M(MM)                                                                                       \
@@ -910,6 +917,20 @@ static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64
   return 0;
 }
 
+// The step's host syncs (particle counts) wait for the whole push kernel.  With one rank per GPU on
+// a shared host, a spinning wait steals cycles from the other ranks' launching threads; the
+// blocking wait (one event, cudaEventBlockingSync) yields the core instead.
+static int host_wait(cylgpu_ctx* c) {
+  if (!c->blocking_wait) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
+  if (!c->ev_wait) CUDA_TRY(cudaEventCreateWithFlags(&c->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming));
+  CUDA_TRY(cudaEventRecord(c->ev_wait, c->stream));
+  CUDA_TRY(cudaEventSynchronize(c->ev_wait));
+  return 0;
+}
+
 static BcsConst make_bcs_const(cylgpu_ctx* c) {
   BcsConst B;
   const double dx = c->cfg.dx, dy = c->cfg.dy;
@@ -962,7 +983,7 @@ static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off
   }
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TRY(host_wait(c));
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
@@ -994,7 +1015,7 @@ static int pbcs_exchange(cylgpu_ctx* c, int64_t nleft, int64_t nright, int64_t* 
                          has_r ? xc + 1 : nullptr, has_r ? 8 : 0, has_r ? xc + 3 : nullptr, has_r ? 8 : 0));
   CUDA_TRY(cudaMemcpyAsync(c->h_counters + 16, xc, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                            c->stream));
-  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  TRY(host_wait(c));
   const int64_t from_l = has_l ? (int64_t)c->h_counters[18] : 0;
   const int64_t from_r = has_r ? (int64_t)c->h_counters[19] : 0;
   TRY(ensure_dbuf(&c->precv, &c->precv_cap, 7 * (from_l + from_r), c->stream));

@@ -149,6 +149,7 @@ int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, siz
   if (left < 0 && right < 0) return 0;
   switch (t->kind) {
     case CYLGPU_TRANSPORT_NCCL: {
+      PhaseTimer timer(c, &c->stats.ms_exchange);   // device time of the exchanges (includes waiting for the peers)
       int r = t->ncclGroupStart();
       // ncclUint8 = 1
       // order matters when left == right (2 ranks, periodic): per peer NCCL matches sends
