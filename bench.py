@@ -253,15 +253,6 @@ def run_ours(args, wl_name, wl):
     if not os.path.exists(os.path.join(ROOT, "cylindrical_epoch_b200", "libcylgpu.so")):
         cbuild.build()
     torch.cuda.set_device(local)
-    if world > 1 and hasattr(os, "sched_setaffinity") and not os.environ.get("BENCH_NO_PIN"):
-        # one disjoint block of host cores per rank: the step is a chain of short kernels, and ranks whose
-        # launching thread shares cores with the other ranks' spinning threads fall behind their neighbours
-        try:
-            cpus = sorted(os.sched_getaffinity(0))
-            per = max(1, len(cpus) // world)
-            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]) or set(cpus))
-        except OSError:
-            pass
     dist = None
     uid = None
     if world > 1:
