@@ -38,6 +38,9 @@ WORKLOADS = {
     "thermal_1024x256_m2_ppc64": dict(nx=1024, ny=256, n_mode=2, ppc=64, kind="thermal"),
     "thermal_512x128_m2_ppc16": dict(nx=512, ny=128, n_mode=2, ppc=16, kind="thermal"),
     "modes5_4096x512_m5_ppc16": dict(nx=4096, ny=512, n_mode=5, ppc=16, kind="thermal"),
+    # BASELINE.json configs[2]: laser wakefield, moving window at c, open boundaries (x-slabs over the GPUs)
+    "lwfa_8192x512_m2_ppc32": dict(nx=8192, ny=512, n_mode=2, ppc=32, kind="lwfa"),
+    "lwfa_1024x128_m2_ppc16": dict(nx=1024, ny=128, n_mode=2, ppc=16, kind="lwfa"),
 }
 DEFAULT_WORKLOAD = "thermal_2048x256_m2_ppc64"
 
@@ -72,7 +75,7 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, mass):
+def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, mass, temp_k=None, density=None):
     """Uniform thermal load in the shape of helper.F90:552-583 / particle_temperature.F90:388-398
     (positions uniform in x and r per cell, theta uniform, weight = n 2 pi r dx dy / ppc).
     numpy RNG -- the bench does not need the reference's KISS stream."""
@@ -86,9 +89,9 @@ def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, mass):
     th = 2.0 * np.pi * rng.random(n)
     out[:, 1] = r * np.cos(th)
     out[:, 2] = r * np.sin(th)
-    sd = np.sqrt(TEMP_K * KB * mass)
-    out[:, 3:6] = rng.normal(0.0, sd, size=(n, 3))
-    out[:, 6] = DENSITY * 2.0 * np.pi * dx * dy * r / ppc
+    sd = np.sqrt((TEMP_K if temp_k is None else temp_k) * KB * mass)
+    out[:, 3:6] = rng.normal(0.0, sd, size=(n, 3)) if sd > 0 else 0.0
+    out[:, 6] = (DENSITY if density is None else density) * 2.0 * np.pi * dx * dy * r / ppc
     return out
 
 
@@ -270,19 +273,36 @@ def run_ours(args, wl_name, wl):
 
     nx, ny, M, ppc = wl["nx"], wl["ny"], wl["n_mode"], wl["ppc"]
     nxg = nx * world
-    bcp = (BC_PERIODIC, BC_PERIODIC, BC_OPEN, BC_REFLECT)
-    species = [ce.Species(-Q0, M0, bcp, False, bool(int(os.environ.get('BENCH_ZERO_CURRENT', '0'))), ppc, DENSITY,
-                          (TEMP_K,) * 3)]
-    slab = ce.Slab(nxg, ny, M, 0.0, nxg * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], species,
-                   rank=rank, nranks=world, transport=TRANSPORT_NCCL if world > 1 else TRANSPORT_NONE,
-                   device=local, nccl_unique_id=uid)
+    lwfa = wl["kind"] == "lwfa"
+    transport = TRANSPORT_NCCL if world > 1 else TRANSPORT_NONE
+    if lwfa:
+        # scaled Wakefield_Lifschitz09 deck (example_decks): dx = lambda/25, dy = lambda/3, n = 7.5e24 m^-3,
+        # a0 ~ 1.26 pulse from x_min, open boundaries, window moving at c from t = 0, cold electrons
+        from cylindrical_epoch_b200.constants import BC_SIMPLE_LASER, BD_X_MIN, C_LIGHT, EPSILON0
+        lam = 0.8e-6
+        dx_, dy_, dens, temp = lam / 25.0, lam / 3.0, 7.5e24, 0.0
+        open4 = (BC_OPEN, BC_OPEN, BC_OPEN, BC_OPEN)
+        species = [ce.Species(-Q0, M0, open4, False, False, ppc, dens, (0.0,) * 3)]
+        amp = 100.0 * np.sqrt(3.4e18 / (C_LIGHT * EPSILON0 / 2.0))
+        lasers = [ce.Laser(boundary=BD_X_MIN, amp=amp, omega=2.0 * np.pi * C_LIGHT / lam, t_centre=30e-15,
+                           t_width=10e-15, r_width=min(5.0e-6, 0.4 * ny * dy_))]
+        slab = ce.Slab(nxg, ny, M, 0.0, nxg * dx_, ny * dy_, [BC_SIMPLE_LASER, BC_OPEN, 0, BC_OPEN], species,
+                       rank=rank, nranks=world, transport=transport, device=local, nccl_unique_id=uid,
+                       lasers=lasers, move_window=True, window_v_x=C_LIGHT, window_start_time=0.0)
+    else:
+        dens, temp = DENSITY, TEMP_K
+        bcp = (BC_PERIODIC, BC_PERIODIC, BC_OPEN, BC_REFLECT)
+        species = [ce.Species(-Q0, M0, bcp, False, bool(int(os.environ.get('BENCH_ZERO_CURRENT', '0'))), ppc, DENSITY,
+                              (TEMP_K,) * 3)]
+        slab = ce.Slab(nxg, ny, M, 0.0, nxg * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], species,
+                       rank=rank, nranks=world, transport=transport, device=local, nccl_unique_id=uid)
     g = slab.grid
     rng = np.random.default_rng(7842432 + rank)
     # pinned host image of the particle list (also the e2e upload source)
     n0 = nx * ny * ppc
     host_p = torch.empty((n0 + n0 // 8, 7), dtype=torch.float64, pin_memory=True)
     hp = host_p.numpy()
-    hp[:n0] = thermal_particles(rng, nx, ny, ppc, g.dx, g.dy, g.x_grid_min_local, M0)
+    hp[:n0] = thermal_particles(rng, nx, ny, ppc, g.dx, g.dy, g.x_grid_min_local, M0, temp, dens)
     slab.upload_particles(0, hp[:n0])
     # run the library on a torch-owned stream so that torch.cuda.Event brackets its work
     tstream = torch.cuda.Stream(device=local)
@@ -305,6 +325,7 @@ def run_ours(args, wl_name, wl):
     for _ in range(args.warmup):
         slab.step_once()
     e_f0, e_k0 = slab.energy()
+    shifts0 = slab.window_shifts_total
     slab.reset_stats()
     clocks = ClockSampler(local) if rank == 0 else None   # rank 0's GPU stands for the box
     barrier()
@@ -371,7 +392,10 @@ def run_ours(args, wl_name, wl):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": wl_name, "grid_per_gpu": [nx, ny], "n_mode": M, "ppc": ppc,
-                   "particles_per_gpu": n0, "decomposition": f"{world} x-slabs, periodic ring",
+                   "particles_per_gpu": n0,
+                   "decomposition": f"{world} x-slabs, " + ("open ends, moving window (%d shifts in the timed steps)"
+                                                            % (slab.window_shifts_total - shifts0) if lwfa
+                                                            else "periodic ring"),
                    "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2; no flush needed" % (n0 * 56 / 1e9),
                    "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host},
         "field_cell_mode_updates_per_s": field_rate,
@@ -385,7 +409,7 @@ def run_ours(args, wl_name, wl):
     }
 
     # ---- e2e: host-authoritative round trip through the C-ABI every step ----
-    if not args.no_e2e:
+    if not args.no_e2e and not lwfa:   # (the moving window appends to the device-resident list)
         names = FIELD_NAMES[:9]
         host_f = {nm: torch.empty(slab.field_shape, dtype=torch.complex128, pin_memory=True) for nm in names}
         for nm in names:
@@ -432,7 +456,7 @@ def run_ours(args, wl_name, wl):
                                "them, runs the full step and downloads them (cylgpu_push_host streams the list in "
                                "chunks, both PCIe directions busy)"}
 
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not lwfa:
         try:
             cb = cpu_port_rate(wl, max_seconds=20.0, steps=2)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}

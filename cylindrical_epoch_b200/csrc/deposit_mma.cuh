@@ -88,12 +88,9 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
 
   // V column of this particle: value k of the 5-point footprint goes to window slot sx + k, the
   // three remaining slots get zeros.  Outside [xmin, xmax] gx and hx are exact zeros already.
-  int voff[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) voff[k] = ((sx + k) & 7) * MMA_PITCH + lane;
   auto store_v = [&](double* V, const double (&v)[5]) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) V[voff[k]] = (k < 5) ? v[k] : 0.0;
+    for (int k = 0; k < 8; ++k) V[((sx + k) & 7) * MMA_PITCH + lane] = (k < 5) ? v[k] : 0.0;
   };
   // a pair of 8-row U tiles against one V tile: 8 k-steps, B fragment shared by both tiles
   auto mma_pair = [&](const double* V, bool two, double (&acc0)[2][2], double (&acc1)[2][2]) {
