@@ -543,6 +543,17 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
   return 0;
 }
 
+// calc_number_density_modes (calc_df.F90:588-661) from the device-resident lists: no particle
+// download on dump steps.  host_out: (nx+2ng, ny+2ng, n_mode) complex128, Fortran order.
+int cylgpu_number_density_modes(cylgpu_handle c, int species, void* host_out) {
+  TRY(check_handle(c));
+  if (species >= c->cfg.n_species || !host_out) { set_error("number_density_modes: bad argument"); return 2; }
+  TRY(do_number_density_modes(c, species));
+  CUDA_TRY(cudaMemcpyAsync(host_out, c->spare, c->g.plane * c->g.M * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return do_energy(c, out2); }
 
 int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {

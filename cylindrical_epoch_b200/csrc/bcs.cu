@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) k_halo_pack(Geom g, Halo3 h, cplx* __rest
   if (j > g.ny + NG - h.skip[k]) return;
   const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
   const cplx* f = h.f[k];
+  if (!f) return;   // exchanges of fewer than three arrays
   if (mode == 0) {
     if (send_l) send_l[b] = f[g.at(i, j, im)];
     if (send_r) send_r[b] = f[g.at(g.nx - NG + i, j, im)];
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx
   if (j > g.ny + NG - h.skip[k]) return;
   const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
   cplx* f = h.f[k];
+  if (!f) return;
   if (mode == 0) {
     if (recv_l) f[g.at(i - NG, j, im)] = recv_l[b];
     if (recv_r) f[g.at(g.nx + i, j, im)] = recv_r[b];
@@ -695,6 +697,159 @@ int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45
   TRY(current_bcs_impl(c, true, &halo_done));
   if (!halo_done) TRY(halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0));
   if (c->smooth_currents) TRY(do_smooth_current(c));
+  return 0;
+}
+
+// ---- calc_number_density_modes, calc_df.F90:588-661 ----
+// particle_to_grid.inc + triangle/gxfac.inc (with the r < dy fold onto the axis cell), number density =
+// weight / macro-particle volume (partlist.F90:999-1013), mode factor 1 or 2 e^{i m theta}.  A
+// diagnostic (dump steps only): per-particle REDs.
+__global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __restrict__ x, const double* __restrict__ y,
+                                                        const double* __restrict__ z, const double* __restrict__ w,
+                                                        int64_t n, double* __restrict__ out, double x_grid_min_local,
+                                                        double y_grid_min_local, double dx, double dy) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double Y = y[i], Z = z[i];
+  const double part_r = sqrt(Y * Y + Z * Z);
+  const double cell_x_r = (x[i] - x_grid_min_local) / dx;
+  const double cell_y_r = (part_r - y_grid_min_local) / dy;
+  int cell_x = (int)floor(cell_x_r + 0.5);
+  int cell_y = (int)floor(cell_y_r + 0.5);
+  const double cell_frac_x = (double)cell_x - cell_x_r;
+  const double cell_frac_y = (double)cell_y - cell_y_r;
+  cell_x += 1;
+  cell_y += 1;
+  const double cx2 = cell_frac_x * cell_frac_x;
+  const double gx[3] = {0.5 * (0.25 + cx2 + cell_frac_x), 0.75 - cx2, 0.5 * (0.25 + cx2 - cell_frac_x)};
+  const double cy2 = cell_frac_y * cell_frac_y;
+  double gy[3] = {0.5 * (0.25 + cy2 + cell_frac_y), 0.75 - cy2, 0.5 * (0.25 + cy2 - cell_frac_y)};
+  if (part_r < dy) {
+    gy[1] = gy[1] + gy[0];
+    gy[0] = 0.0;
+  }
+  const double part_num_dens = w[i] / (2.0 * PI * dx * dy * part_r);
+  const cplx exp_itheta = C(Y, Z) / part_r;
+  cplx exp_imtheta = C(1.0, 0.0);
+  for (int im = 0; im < g.M; ++im) {
+    cplx mode_fac = C(1.0, 0.0);
+    if (im > 0) {
+      exp_imtheta = exp_imtheta * exp_itheta;
+      mode_fac = 2.0 * exp_imtheta;
+    }
+#pragma unroll
+    for (int iy = -1; iy <= 1; ++iy)
+#pragma unroll
+      for (int ix = -1; ix <= 1; ++ix) {
+        const double v = (gx[ix + 1] * gy[iy + 1]) * part_num_dens;
+        if (v == 0.0) continue;
+        const size_t o = 2 * g.at(cell_x + ix, cell_y + iy, im);
+        atomicAdd(out + o, v * mode_fac.x);
+        if (im > 0) atomicAdd(out + o + 1, v * mode_fac.y);
+      }
+  }
+}
+
+// particle_reflection_bcs, the real-valued variant (boundary.F90:833-914, flip_direction absent):
+// bd 0 x_min (ng-1 ghost columns fold onto 1..ng-1), 1 x_max, 3 r_max (ng ghosts each)
+__global__ void __launch_bounds__(128) k_density_reflect(Geom g, cplx* __restrict__ a, int bd) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (bd == CYLGPU_BD_Y_MAX) {
+    if (t >= g.SX) return;
+    const int ix = t + 1 - NG;
+    for (int i = 1; i <= NG; ++i) {
+      const size_t in = g.at(ix, g.ny + 1 - i, im), gh = g.at(ix, g.ny + i, im);
+      a[in] = a[in] + a[gh];
+      a[gh] = C(0.0, 0.0);
+    }
+    return;
+  }
+  if (t >= g.SY) return;
+  const int j = t + 1 - NG;
+  if (bd == CYLGPU_BD_X_MIN) {
+    for (int i = 1; i <= NG - 1; ++i) {
+      const size_t in = g.at(i, j, im), gh = g.at(1 - i, j, im);
+      a[in] = a[in] + a[gh];
+      a[gh] = C(0.0, 0.0);
+    }
+  } else {
+    for (int i = 1; i <= NG; ++i) {
+      const size_t in = g.at(g.nx + 1 - i, j, im), gh = g.at(g.nx + i, j, im);
+      a[in] = a[in] + a[gh];
+      a[gh] = C(0.0, 0.0);
+    }
+  }
+}
+
+// field_mode_zero_gradient for a cell-centred array (boundary.F90:654-707): ghost i <- interior mirror
+__global__ void __launch_bounds__(128) k_density_zero_gradient(Geom g, cplx* __restrict__ a, int bd) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (bd == CYLGPU_BD_X_MIN || bd == CYLGPU_BD_X_MAX) {
+    if (t >= g.SY) return;
+    const int j = t + 1 - NG;
+    for (int i = 1; i <= NG; ++i) {
+      if (bd == CYLGPU_BD_X_MIN) a[g.at(i - NG, j, im)] = a[g.at(NG + 1 - i, j, im)];
+      else a[g.at(g.nx + i, j, im)] = a[g.at(g.nx + 1 - i, j, im)];
+    }
+  } else {
+    if (t >= g.SX) return;
+    const int ix = t + 1 - NG;
+    for (int i = 1; i <= NG; ++i) {
+      if (bd == CYLGPU_BD_Y_MIN) a[g.at(ix, i - NG, im)] = a[g.at(ix, NG + 1 - i, im)];
+      else a[g.at(ix, g.ny + i, im)] = a[g.at(ix, g.ny + 1 - i, im)];
+    }
+  }
+}
+
+// species < 0: sum over the species that carry current (calc_df.F90:606-616).  Result in c->spare.
+int do_number_density_modes(cylgpu_ctx* c, int species) {
+  const Geom& g = c->g;
+  int bca[4];
+  for (int bd = 0; bd < 4; ++bd) {
+    bca[bd] = bc_allspecies(c, bd);
+    if (bd != CYLGPU_BD_Y_MIN && bca[bd] == -1) {
+      set_error("mixed per-species particle boundary conditions are not supported");
+      return 2;
+    }
+  }
+  cplx* a = c->spare;
+  CUDA_TRY(cudaMemsetAsync(a, 0, g.plane * g.M * sizeof(cplx), c->stream));
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    const SpeciesState& S = c->species[isp];
+    if (!S.set || S.n == 0) continue;
+    if (species >= 0 && isp != species) continue;
+    if (species < 0 && S.sp.zero_current) continue;
+    k_number_density<<<(unsigned)((S.n + 255) / 256), 256, 0, c->stream>>>(
+        g, S.d[0], S.d[1], S.d[2], S.d[6], S.n, (double*)a, c->x_grid_min_local, c->cfg.y_grid_min_local, c->cfg.dx,
+        c->cfg.dy);
+    c->stats.kernel_launches += 1;
+  }
+  const dim3 gx_((g.SY + 127) / 128, g.M), gy_((g.SX + 127) / 128, g.M);
+  if (c->cfg.x_min_boundary && bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT)
+    k_density_reflect<<<gx_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_X_MIN);
+  if (c->cfg.x_max_boundary && bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT)
+    k_density_reflect<<<gx_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_X_MAX);
+  if (bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT) k_density_reflect<<<gy_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_Y_MAX);
+  // particle_periodic_bcs (boundary.F90:1019-1129): neighbours' ghost columns add into my edge columns
+  {
+    const bool to_l = c->left >= 0 && !(c->cfg.x_min_boundary && bca[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC);
+    const bool to_r = c->right >= 0 && !(c->cfg.x_max_boundary && bca[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC);
+    Halo3 h;
+    h.f[0] = a; h.f[1] = nullptr; h.f[2] = nullptr;
+    h.skip[0] = h.skip[1] = h.skip[2] = 0;
+    TRY(exchange3(c, h, 1, to_l, to_r, to_l, to_r));
+  }
+  if (c->bc_field[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC && c->cfg.x_min_boundary)
+    k_density_zero_gradient<<<gx_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_X_MIN);
+  if (c->bc_field[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC && c->cfg.x_max_boundary)
+    k_density_zero_gradient<<<gx_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_X_MAX);
+  if (c->bc_field[CYLGPU_BD_Y_MIN] != CYLGPU_BC_PERIODIC)
+    k_density_zero_gradient<<<gy_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_Y_MIN);
+  if (c->bc_field[CYLGPU_BD_Y_MAX] != CYLGPU_BC_PERIODIC)
+    k_density_zero_gradient<<<gy_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_Y_MAX);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 

@@ -219,6 +219,11 @@ class Slab:
     def reset_stats(self):
         self._ck(self.L.cylgpu_reset_stats(self.h))
 
+    def number_density_modes(self, isp=-1):   # calc_df.F90:588-661
+        a = np.empty(self.field_shape, dtype=np.complex128)
+        self._ck(self.L.cylgpu_number_density_modes(self.h, int(isp), a.ctypes.data))
+        return a
+
     def energy(self):
         out = (C.c_double * 2)()
         self._ck(self.L.cylgpu_energy(self.h, out))

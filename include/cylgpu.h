@@ -239,6 +239,11 @@ int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = neve
 /* 0 = one thread per particle, global atomics; 1 = cell-tile kernel (default) */
 int cylgpu_set_push_variant(cylgpu_handle h, int variant);
 
+/* calc_number_density_modes (calc_df.F90:588-661) of one species (ispecies >= 0) or of all
+ * current-carrying species (ispecies < 0), computed from the device-resident lists including
+ * calc_boundary_modes and the zero-gradient ghost fill; host_out is a complex(num) array
+ * (1-ng:nx+ng, 1-ng:ny+ng, 0:n_mode-1).  Lets dump steps skip the particle download. */
+int cylgpu_number_density_modes(cylgpu_handle h, int ispecies, void* host_out);
 /* diagnostics the new code must own: field + kinetic energy from the
  * mode arrays with cylindrical volume elements; out[0] = field J, out[1] = kinetic J */
 int cylgpu_energy(cylgpu_handle h, double* out2);

@@ -1483,6 +1483,108 @@ void World::smooth_mode_array(Arr3 Rank::*f) {
 }
 
 // ---------------------------------------------------------------------------------------
+// calc_number_density_modes, calc_df.F90:588-661: per-mode number density on the cell centres.
+// particle_to_grid.inc + triangle/gxfac.inc weights (with the r < dy fold onto the axis cell),
+// number density = weight / macro-particle volume 2 pi dx dy r (partlist.F90:999-1013), mode
+// factor 1 (m = 0) or 2 e^{i m theta}; then calc_boundary_modes (real-valued
+// processor_summation_bcs on the real and imaginary parts: particle_reflection_bcs
+// boundary.F90:833-914, particle_periodic_bcs :1019-1129) and field_mode_zero_gradient
+// (:654-707, centred stagger) on all four boundaries.  Result in Rank::wk.
+// ---------------------------------------------------------------------------------------
+void World::calc_number_density_modes(int current_species) {
+  for (int i = 0; i < 4; ++i) assert(bc_allspecies(i) != BC_MIXED);
+  const bool spec_sum = current_species < 0;
+  for (Rank& r : ranks) {
+    r.wk.alloc(r.nx, r.ny, M);
+    for (size_t isp = 0; isp < species.size(); ++isp) {
+      if (!spec_sum && (int)isp != current_species) continue;
+      if (spec_sum && species[isp].zero_current) continue;
+      for (const Particle& p : r.parts[isp]) {
+        const double part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
+        const double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx;
+        const double cell_y_r = (part_r - y_grid_min_local) / dy;
+        int cell_x = (int)std::floor(cell_x_r + 0.5);
+        int cell_y = (int)std::floor(cell_y_r + 0.5);
+        const double cell_frac_x = (double)cell_x - cell_x_r;
+        const double cell_frac_y = (double)cell_y - cell_y_r;
+        cell_x = cell_x + 1;
+        cell_y = cell_y + 1;
+        const double cx2 = cell_frac_x * cell_frac_x;
+        double gx[3] = {0.5 * (0.25 + cx2 + cell_frac_x), 0.75 - cx2, 0.5 * (0.25 + cx2 - cell_frac_x)};
+        const double cy2 = cell_frac_y * cell_frac_y;
+        double gy[3] = {0.5 * (0.25 + cy2 + cell_frac_y), 0.75 - cy2, 0.5 * (0.25 + cy2 - cell_frac_y)};
+        if (part_r < dy) {
+          gy[1] = gy[1] + gy[0];
+          gy[0] = 0.0;
+        }
+        const double macro_part_volume = 2.0 * PI * dx * dy * part_r;
+        const double part_num_dens = p.w / macro_part_volume;
+        const cplx exp_itheta = cplx(p.pos[1], p.pos[2]) / part_r;
+        cplx exp_imtheta = cplx(1.0);
+        for (int im = 0; im < M; ++im) {
+          cplx mode_fac;
+          if (im == 0) {
+            mode_fac = cplx(1.0);
+          } else {
+            exp_imtheta = exp_imtheta * exp_itheta;
+            mode_fac = 2.0 * exp_imtheta;
+          }
+          for (int iy = -1; iy <= 1; ++iy)
+            for (int ix = -1; ix <= 1; ++ix)
+              r.wk(cell_x + ix, cell_y + iy, im) =
+                  r.wk(cell_x + ix, cell_y + iy, im) + ((gx[ix + 1] * gy[iy + 1]) * part_num_dens) * mode_fac;
+        }
+      }
+    }
+  }
+  // particle_reflection_bcs (the real-valued variant: at x_min only ng-1 ghost columns fold back)
+  for (Rank& r : ranks) {
+    Arr3& a = r.wk;
+    const int nx = r.nx, ny = r.ny;
+    for (int im = 0; im < M; ++im) {
+      if (r.x_min_boundary && bc_allspecies(BD_X_MIN) == BC_REFLECT)
+        for (int i = 1; i <= NG - 1; ++i)
+          for (int j = 1 - NG; j <= ny + NG; ++j) {
+            a(i, j, im) = a(i, j, im) + a(1 - i, j, im);
+            a(1 - i, j, im) = cplx(0.0);
+          }
+      if (r.x_max_boundary && bc_allspecies(BD_X_MAX) == BC_REFLECT)
+        for (int i = 1; i <= NG; ++i)
+          for (int j = 1 - NG; j <= ny + NG; ++j) {
+            a(nx + 1 - i, j, im) = a(nx + 1 - i, j, im) + a(nx + i, j, im);
+            a(nx + i, j, im) = cplx(0.0);
+          }
+      if (bc_allspecies(BD_Y_MAX) == BC_REFLECT)
+        for (int i = 1; i <= NG; ++i)
+          for (int ix = 1 - NG; ix <= nx + NG; ++ix) {
+            a(ix, ny + 1 - i, im) = a(ix, ny + 1 - i, im) + a(ix, ny + i, im);
+            a(ix, ny + i, im) = cplx(0.0);
+          }
+    }
+  }
+  periodic_sum_x(&Rank::wk);   // particle_periodic_bcs, x part (no r neighbours)
+  // field_mode_zero_gradient, c_stagger_centre, boundaries 1..4
+  for (Rank& r : ranks) {
+    Arr3& a = r.wk;
+    const int nx = r.nx, ny = r.ny;
+    for (int im = 0; im < M; ++im) {
+      if (bc_field[BD_X_MIN] != BC_PERIODIC && r.x_min_boundary)
+        for (int i = 1; i <= NG; ++i)
+          for (int j = 1 - NG; j <= ny + NG; ++j) a(i - NG, j, im) = a(NG + 1 - i, j, im);
+      if (bc_field[BD_X_MAX] != BC_PERIODIC && r.x_max_boundary)
+        for (int i = 1; i <= NG; ++i)
+          for (int j = 1 - NG; j <= ny + NG; ++j) a(nx + i, j, im) = a(nx + 1 - i, j, im);
+      if (bc_field[BD_Y_MIN] != BC_PERIODIC)
+        for (int i = 1; i <= NG; ++i)
+          for (int ix = 1 - NG; ix <= nx + NG; ++ix) a(ix, i - NG, im) = a(ix, NG + 1 - i, im);
+      if (bc_field[BD_Y_MAX] != BC_PERIODIC)
+        for (int i = 1; i <= NG; ++i)
+          for (int ix = 1 - NG; ix <= nx + NG; ++ix) a(ix, ny + i, im) = a(ix, ny + 1 - i, im);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Moving window: window.F90:62-153, :157-300, :304-376
 // ---------------------------------------------------------------------------------------
 void World::insert_particles(Rank& r) {

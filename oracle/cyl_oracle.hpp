@@ -205,6 +205,7 @@ struct World {
   void current_bcs();                            // boundary.F90:1893-1905
   void current_finish();                         // current_smooth.F90:29-45
   void smooth_mode_array(Arr3 Rank::*f);         // current_smooth.F90:145-196
+  void calc_number_density_modes(int species);   // calc_df.F90:588-661 -> Rank::wk (species < 0: all)
   bool smooth_currents = false;                  // shared_data.F90:468-472
   bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
   int smooth_its = 1, smooth_comp_its = 0;

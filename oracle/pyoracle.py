@@ -72,6 +72,10 @@ def lib():
         L.cylo_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.cylo_set_dt.argtypes = [C.c_void_p, C.c_double]
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_number_density_modes.restype = None
+        L.cylo_number_density_modes.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_wk_ptr.restype = C.c_void_p
+        L.cylo_wk_ptr.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_hc_push.restype = None
         L.cylo_set_hc_push.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_smoothing.restype = None
@@ -153,6 +157,18 @@ class OracleWorld:
         """smooth_currents, smooth_its, smooth_compensation, smooth_strides of the control block"""
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
         self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
+
+    def number_density_modes(self, species=-1):
+        """calc_number_density_modes (calc_df.F90:588-661) for one species (or all, -1): list of
+        per-rank complex arrays [im, ir+NG-1, ix+NG-1] (copies)"""
+        self.L.cylo_number_density_modes(self.h, int(species))
+        out = []
+        for k in range(self.nranks):
+            info = self.rank_info(k)
+            shape = (self.n_mode, info["ny"] + 2 * NG, info["nx"] + 2 * NG)
+            buf = (C.c_double * (2 * shape[0] * shape[1] * shape[2])).from_address(self.L.cylo_wk_ptr(self.h, k))
+            out.append(np.frombuffer(buf, dtype=np.complex128).reshape(shape).copy())
+        return out
 
     def set_hc_push(self, on):
         """the reference's -DHC_PUSH build: Higuera-Cary gamma instead of Boris'"""

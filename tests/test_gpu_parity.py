@@ -273,6 +273,33 @@ def test_higuera_cary_pusher(variant):
         q.close()
 
 
+@pytest.mark.parametrize("deckname,nranks", [("lwfa", 1), ("lwfa", 2), ("thermal", 2), ("drift", 1)])
+def test_number_density_modes(deckname, nranks):
+    """calc_number_density_modes (calc_df.F90:588-661) from the device-resident lists: deposit with the
+    axis fold, reflection / periodic summation of the ghosts, zero-gradient ghost fill"""
+    d = {"lwfa": lambda: decks.lwfa(nx=64, ny=24, n_mode=2, ppc_e=4, ppc_p=1),
+         "thermal": lambda: decks.thermal(nx=64, ny=32, n_mode=2, ppc=8),
+         "drift": lambda: decks.drift()}[deckname]()
+    p = Pair(d, nranks=nranks)
+    try:
+        p.step(5)
+        for isp in [-1] + list(range(len(d.species))):
+            ref = p.oracle.number_density_modes(isp)
+            got = [None] * nranks
+            p.each(lambda s: got.__setitem__(p.slabs.index(s), s.number_density_modes(isp)))
+            den = max(np.abs(r).max() for r in ref)
+            assert den > 0
+            for k in range(nranks):
+                err = np.abs(got[k] - ref[k]).max() / den
+                assert err < 1e-12, (deckname, isp, k, err)
+        # uniform plasma: the m = 0 density in the bulk is the deck's density
+        n0 = p.oracle.number_density_modes(0)[0][0]
+        bulk = n0[8:-8, 8:-8].real
+        assert abs(np.median(bulk) / d.species[0].density - 1.0) < 0.2
+    finally:
+        p.close()
+
+
 def test_kiss_stream_matches_oracle():
     """random(), random_box_muller() of random_generator.f90: the product's stream is the oracle's, bit for bit"""
     d = decks.lwfa(nx=32, ny=12, n_mode=1, ppc_e=1)
