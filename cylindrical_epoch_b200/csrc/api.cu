@@ -548,10 +548,18 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
 int cylgpu_number_density_modes(cylgpu_handle c, int species, void* host_out) {
   TRY(check_handle(c));
   if (species >= c->cfg.n_species || !host_out) { set_error("number_density_modes: bad argument"); return 2; }
-  TRY(do_number_density_modes(c, species));
+  TRY(do_number_density_modes(c, species, false));
   CUDA_TRY(cudaMemcpyAsync(host_out, c->spare, c->g.plane * c->g.M * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+// calc_charge_density (calc_df.F90:442-519); host_out: real (nx+2ng, ny+2ng) array
+int cylgpu_charge_density(cylgpu_handle c, int species, double* host_out) {
+  TRY(check_handle(c));
+  if (species >= c->cfg.n_species || !host_out) { set_error("charge_density: bad argument"); return 2; }
+  TRY(do_number_density_modes(c, species, true));
+  return download_real_part_mode0(c, c->spare, host_out);
 }
 
 int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return do_energy(c, out2); }

@@ -707,7 +707,8 @@ int do_current_finish(cylgpu_ctx* c) {   // current_smooth.F90:29-45
 __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __restrict__ x, const double* __restrict__ y,
                                                         const double* __restrict__ z, const double* __restrict__ w,
                                                         int64_t n, double* __restrict__ out, double x_grid_min_local,
-                                                        double y_grid_min_local, double dx, double dy) {
+                                                        double y_grid_min_local, double dx, double dy, double wfac,
+                                                        int nmodes) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double Y = y[i], Z = z[i];
@@ -728,10 +729,10 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
     gy[1] = gy[1] + gy[0];
     gy[0] = 0.0;
   }
-  const double part_num_dens = w[i] / (2.0 * PI * dx * dy * part_r);
+  const double part_num_dens = (wfac * w[i]) / (2.0 * PI * dx * dy * part_r);   // wfac = 1, or the charge (calc_df.F90:479)
   const cplx exp_itheta = C(Y, Z) / part_r;
   cplx exp_imtheta = C(1.0, 0.0);
-  for (int im = 0; im < g.M; ++im) {
+  for (int im = 0; im < nmodes; ++im) {
     cplx mode_fac = C(1.0, 0.0);
     if (im > 0) {
       exp_imtheta = exp_imtheta * exp_itheta;
@@ -803,8 +804,15 @@ __global__ void __launch_bounds__(128) k_density_zero_gradient(Geom g, cplx* __r
   }
 }
 
+__global__ void __launch_bounds__(256) k_real_part(const cplx* __restrict__ a, double* __restrict__ out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i].x;
+}
+
 // species < 0: sum over the species that carry current (calc_df.F90:606-616).  Result in c->spare.
-int do_number_density_modes(cylgpu_ctx* c, int species) {
+// charge: calc_charge_density (calc_df.F90:442-519) -- wdata = charge * weight, no azimuthal factors
+// (mode 0 only; the real part is the answer).
+int do_number_density_modes(cylgpu_ctx* c, int species, bool charge) {
   const Geom& g = c->g;
   int bca[4];
   for (int bd = 0; bd < 4; ++bd) {
@@ -823,7 +831,7 @@ int do_number_density_modes(cylgpu_ctx* c, int species) {
     if (species < 0 && S.sp.zero_current) continue;
     k_number_density<<<(unsigned)((S.n + 255) / 256), 256, 0, c->stream>>>(
         g, S.d[0], S.d[1], S.d[2], S.d[6], S.n, (double*)a, c->x_grid_min_local, c->cfg.y_grid_min_local, c->cfg.dx,
-        c->cfg.dy);
+        c->cfg.dy, charge ? S.sp.charge : 1.0, charge ? 1 : g.M);
     c->stats.kernel_launches += 1;
   }
   const dim3 gx_((g.SY + 127) / 128, g.M), gy_((g.SX + 127) / 128, g.M);
@@ -850,6 +858,16 @@ int do_number_density_modes(cylgpu_ctx* c, int species) {
   if (c->bc_field[CYLGPU_BD_Y_MAX] != CYLGPU_BC_PERIODIC)
     k_density_zero_gradient<<<gy_, 128, 0, c->stream>>>(g, a, CYLGPU_BD_Y_MAX);
   CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int download_real_part_mode0(cylgpu_ctx* c, const cplx* a, double* host_out) {
+  double* tmp = nullptr;
+  CUDA_TRY(cudaMalloc(&tmp, c->g.plane * sizeof(double)));
+  k_real_part<<<(unsigned)((c->g.plane + 255) / 256), 256, 0, c->stream>>>(a, tmp, c->g.plane);
+  CUDA_TRY(cudaMemcpyAsync(host_out, tmp, c->g.plane * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  CUDA_TRY(cudaFree(tmp));
   return 0;
 }
 

@@ -227,7 +227,8 @@ int upload_laser_sources(cylgpu_ctx* c, const double* s1min, const double* s2min
 int do_bfield_final_bcs_device(cylgpu_ctx* c);
 int do_current_bcs(cylgpu_ctx* c);
 int do_current_finish(cylgpu_ctx* c);
-int do_number_density_modes(cylgpu_ctx* c, int species);
+int do_number_density_modes(cylgpu_ctx* c, int species, bool charge);
+int download_real_part_mode0(cylgpu_ctx* c, const cplx* a, double* host_out);
 int do_r_min_final(cylgpu_ctx* c);
 int do_snapshot(cylgpu_ctx* c);
 int do_shift_fields(cylgpu_ctx* c);

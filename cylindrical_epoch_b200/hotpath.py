@@ -224,6 +224,11 @@ class Slab:
         self._ck(self.L.cylgpu_number_density_modes(self.h, int(isp), a.ctypes.data))
         return a
 
+    def charge_density(self, isp=-1):         # calc_df.F90:442-519
+        a = np.empty(self.field_shape[1:], dtype=np.float64)
+        self._ck(self.L.cylgpu_charge_density(self.h, int(isp), a.ctypes.data))
+        return a
+
     def energy(self):
         out = (C.c_double * 2)()
         self._ck(self.L.cylgpu_energy(self.h, out))

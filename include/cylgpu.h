@@ -244,6 +244,8 @@ int cylgpu_set_push_variant(cylgpu_handle h, int variant);
  * calc_boundary_modes and the zero-gradient ghost fill; host_out is a complex(num) array
  * (1-ng:nx+ng, 1-ng:ny+ng, 0:n_mode-1).  Lets dump steps skip the particle download. */
 int cylgpu_number_density_modes(cylgpu_handle h, int ispecies, void* host_out);
+/* calc_charge_density (calc_df.F90:442-519): real array (1-ng:nx+ng, 1-ng:ny+ng) */
+int cylgpu_charge_density(cylgpu_handle h, int ispecies, double* host_out);
 /* diagnostics the new code must own: field + kinetic energy from the
  * mode arrays with cylindrical volume elements; out[0] = field J, out[1] = kinetic J */
 int cylgpu_energy(cylgpu_handle h, double* out2);

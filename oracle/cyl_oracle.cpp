@@ -1491,7 +1491,13 @@ void World::smooth_mode_array(Arr3 Rank::*f) {
 // boundary.F90:833-914, particle_periodic_bcs :1019-1129) and field_mode_zero_gradient
 // (:654-707, centred stagger) on all four boundaries.  Result in Rank::wk.
 // ---------------------------------------------------------------------------------------
-void World::calc_number_density_modes(int current_species) {
+void World::calc_number_density_modes(int current_species) { density_deposit_and_bcs(current_species, false); }
+
+// calc_charge_density, calc_df.F90:442-519: the same deposit of wdata = charge * weight into a real
+// array (no azimuthal factors), calc_boundary + field_zero_gradient.  Result: real part of mode 0.
+void World::calc_charge_density(int current_species) { density_deposit_and_bcs(current_species, true); }
+
+void World::density_deposit_and_bcs(int current_species, bool charge) {
   for (int i = 0; i < 4; ++i) assert(bc_allspecies(i) != BC_MIXED);
   const bool spec_sum = current_species < 0;
   for (Rank& r : ranks) {
@@ -1518,10 +1524,11 @@ void World::calc_number_density_modes(int current_species) {
           gy[0] = 0.0;
         }
         const double macro_part_volume = 2.0 * PI * dx * dy * part_r;
-        const double part_num_dens = p.w / macro_part_volume;
+        const double wdata = charge ? species[isp].charge * p.w : p.w;
+        const double part_num_dens = wdata / macro_part_volume;
         const cplx exp_itheta = cplx(p.pos[1], p.pos[2]) / part_r;
         cplx exp_imtheta = cplx(1.0);
-        for (int im = 0; im < M; ++im) {
+        for (int im = 0; im < (charge ? 1 : M); ++im) {
           cplx mode_fac;
           if (im == 0) {
             mode_fac = cplx(1.0);

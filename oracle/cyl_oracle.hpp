@@ -206,6 +206,8 @@ struct World {
   void current_finish();                         // current_smooth.F90:29-45
   void smooth_mode_array(Arr3 Rank::*f);         // current_smooth.F90:145-196
   void calc_number_density_modes(int species);   // calc_df.F90:588-661 -> Rank::wk (species < 0: all)
+  void calc_charge_density(int species);         // calc_df.F90:442-519 -> Rank::wk, mode 0, real part
+  void density_deposit_and_bcs(int species, bool charge);
   bool smooth_currents = false;                  // shared_data.F90:468-472
   bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
   int smooth_its = 1, smooth_comp_its = 0;

@@ -70,6 +70,7 @@ void cylo_set_dt(void* w, double dt) { ((World*)w)->dt = dt; }
 void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
 // calc_number_density_modes into each rank's work array; returns rank k's pointer afterwards via cylo_wk_ptr
 void cylo_number_density_modes(void* w, int species) { ((World*)w)->calc_number_density_modes(species); }
+void cylo_charge_density(void* w, int species) { ((World*)w)->calc_charge_density(species); }
 void* cylo_wk_ptr(void* w, int k) { return (void*)((World*)w)->ranks[k].wk.d.data(); }
 void cylo_set_smoothing(void* wp, int enable, int its, int comp_its, int nstrides, const int32_t* strides) {
   World* w = (World*)wp;

@@ -74,6 +74,8 @@ def lib():
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
         L.cylo_number_density_modes.restype = None
         L.cylo_number_density_modes.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_charge_density.restype = None
+        L.cylo_charge_density.argtypes = [C.c_void_p, C.c_int]
         L.cylo_wk_ptr.restype = C.c_void_p
         L.cylo_wk_ptr.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_hc_push.restype = None
@@ -158,10 +160,17 @@ class OracleWorld:
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
         self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
 
-    def number_density_modes(self, species=-1):
+    def charge_density(self, species=-1):
+        """calc_charge_density (calc_df.F90:442-519): list of per-rank real arrays [ir+NG-1, ix+NG-1]"""
+        return [a[0].real.copy() for a in self.number_density_modes(species, _charge=True)]
+
+    def number_density_modes(self, species=-1, _charge=False):
         """calc_number_density_modes (calc_df.F90:588-661) for one species (or all, -1): list of
         per-rank complex arrays [im, ir+NG-1, ix+NG-1] (copies)"""
-        self.L.cylo_number_density_modes(self.h, int(species))
+        if _charge:
+            self.L.cylo_charge_density(self.h, int(species))
+        else:
+            self.L.cylo_number_density_modes(self.h, int(species))
         out = []
         for k in range(self.nranks):
             info = self.rank_info(k)

@@ -292,6 +292,12 @@ def test_number_density_modes(deckname, nranks):
             for k in range(nranks):
                 err = np.abs(got[k] - ref[k]).max() / den
                 assert err < 1e-12, (deckname, isp, k, err)
+            refq = p.oracle.charge_density(isp)          # calc_charge_density, calc_df.F90:442-519
+            gotq = [None] * nranks
+            p.each(lambda s: gotq.__setitem__(p.slabs.index(s), s.charge_density(isp)))
+            denq = max(np.abs(r).max() for r in refq)
+            for k in range(nranks):
+                assert np.abs(gotq[k] - refq[k]).max() <= 1e-12 * denq, (deckname, isp, k)
         # uniform plasma: the m = 0 density in the bulk is the deck's density
         n0 = p.oracle.number_density_modes(0)[0][0]
         bulk = n0[8:-8, 8:-8].real
