@@ -4,6 +4,9 @@ path -- SURVEY.md section 4/8c -- so the anchors are analytic and structural):
   * exact discrete charge continuity of the mode-0 deposit,
   * axis-condition identities of update_e/b_field,
   * vacuum propagation of an injected pulse at c,
+  * Boris rotation angle and |p| conservation in a uniform axial field,
+  * cold-plasma (Langmuir) oscillation at omega_p: gather + push + deposit + Maxwell closed loop,
+  * Gauss's law residual of mode 0 frozen to rounding over many steps,
   * KISS / Box-Muller sanity, loader statistics,
   * committed golden vectors (tests/golden) guarding the oracle against drift."""
 import math
@@ -156,6 +159,134 @@ def test_vacuum_pulse_propagates_at_c():
         pos.append(((env ** 2 * xs).sum() / (env ** 2).sum(), w.scalars()["time"]))
     v = (pos[1][0] - pos[0][0]) / (pos[1][1] - pos[0][1])
     assert abs(v / C_LIGHT - 1.0) < 0.02, v / C_LIGHT
+
+
+def test_boris_rotation_angle_in_uniform_axial_field():
+    """push_particles alone (no field update): a particle in uniform Bx gyrates in the y-z plane
+    by exactly 2 atan(q B dt / (2 gamma m)) per step (Boris), |p| is conserved to rounding, p_x is
+    untouched -- this exercises the (r, theta) -> (y, z) rotation of the gathered mode fields."""
+    d = decks.thermal(nx=32, ny=32, n_mode=2, ppc=1, temp_k=0.0, density=1.0)   # no self-field to speak of
+    w = decks.make_oracle(d)
+    B0 = 2.0e3
+    w.field(0, "bxm")[0, :, :] = B0
+    sc = w.scalars()
+    p0 = 0.8 * M0 * C_LIGHT
+    parts = w.particles(0, 0)[:4].copy()
+    for k, ang in enumerate((0.3, 1.7, 3.9, 5.5)):
+        r = (10.0 + 2.0 * k) * sc["dy"]
+        parts[k, 0] = 16.0 * sc["dx"]
+        parts[k, 1], parts[k, 2] = r * math.cos(ang), r * math.sin(ang)
+        parts[k, 3], parts[k, 4], parts[k, 5] = 0.25 * p0, p0 * math.cos(2.0 * ang), p0 * math.sin(2.0 * ang)
+    w.set_particles(0, 0, parts)
+    gamma = math.sqrt(1.0 + (parts[0, 3] ** 2 + p0 ** 2) / (M0 * C_LIGHT) ** 2)
+    dphi = 2.0 * math.atan(-Q0 * B0 * sc["dt"] / (2.0 * gamma * M0))
+    nsteps = 12
+    for _ in range(nsteps):
+        w.call("push_no_bcs")
+    out = w.particles(0, 0)
+    for k in range(4):
+        a0 = math.atan2(parts[k, 5], parts[k, 4])
+        a1 = math.atan2(out[k, 5], out[k, 4])
+        turned = (a1 - a0 + math.pi) % (2.0 * math.pi) - math.pi
+        expect = (-nsteps * dphi + math.pi) % (2.0 * math.pi) - math.pi   # electrons: u x B with q < 0
+        assert abs(abs(turned) - abs(expect)) < 1e-9, (k, turned, expect)
+        assert abs(math.hypot(out[k, 4], out[k, 5]) / p0 - 1.0) < 1e-13
+        assert abs(out[k, 3] / parts[k, 3] - 1.0) < 1e-13
+
+
+def _langmuir_world(nx=32, ny=12, ppc=8):
+    d = decks.thermal(nx=nx, ny=ny, n_mode=1, ppc=ppc, temp_k=0.0, density=1.0e24)
+    w = decks.make_oracle(d)
+    sc = w.scalars()
+    L = nx * sc["dx"]
+    parts = w.particles(0, 0).copy()
+    v1 = 1.0e-4 * C_LIGHT
+    parts[:, 3] = M0 * v1 * np.sin(2.0 * np.pi * parts[:, 0] / L)
+    w.set_particles(0, 0, parts)
+    w.call("init_half_step")
+    return d, w, sc
+
+
+def test_cold_plasma_oscillates_at_omega_p():
+    """the closed loop gather -> push -> deposit -> Maxwell: a cold electron plasma with a small sinusoidal
+    v_x perturbation rings at omega_p = sqrt(n e^2 / (eps0 m)) (Langmuir), the field energy exchanging with
+    the kinetic energy; period from the zero crossings of Ex (mode 0)."""
+    d, w, sc = _langmuir_world()
+    omega_p = math.sqrt(1.0e24 * Q0 ** 2 / (EPSILON0 * M0))
+    nsteps = int(2.6 * 2.0 * math.pi / omega_p / sc["dt"])
+    sig, t = [], []
+    j, i = fidx(8, 6)
+    for _ in range(nsteps):
+        w.step(1)
+        sig.append(w.field(0, "exm")[0, j, i].real)
+        t.append(w.scalars()["time"])
+    sig, t = np.array(sig), np.array(t)
+    assert np.abs(sig).max() > 0
+    zc = [t[k] - sig[k] * (t[k + 1] - t[k]) / (sig[k + 1] - sig[k]) for k in range(len(sig) - 1)
+          if sig[k] * sig[k + 1] < 0]
+    assert len(zc) >= 4
+    period = 2.0 * np.mean(np.diff(zc))
+    assert abs(period * omega_p / (2.0 * math.pi) - 1.0) < 0.03, period * omega_p / (2.0 * math.pi)
+
+
+def _node_charge(pos, weight, q, sc, nx, ny):
+    """charge on the staggered nodes with the deposit's own (unnormalised triangle) weights,
+    particles.F90:369-388 / DOCUMENTATION eq. 96: Q(cx, cy) = q w fac hx hy"""
+    dx, dy = sc["dx"], sc["dy"]
+    Qg = np.zeros((ny + 2 * NGH, nx + 2 * NGH))
+    xr = (pos[:, 0] - sc["x_grid_min"]) / dx
+    rr = (np.hypot(pos[:, 1], pos[:, 2]) - sc["y_grid_min_local"]) / dy
+    for k in range(pos.shape[0]):
+        out = []
+        for c_r in (xr[k], rr[k]):
+            c2 = math.floor(c_r)
+            f = c2 - c_r + 0.5
+            out.append((c2 + 1, [0.25 + f * f + f, 1.5 - 2 * f * f, 0.25 + f * f - f]))
+        (cx2, wx), (cy2, wy) = out
+        for a in range(3):
+            for b in range(3):
+                Qg[fidx(cx2 - 1 + b, cy2 - 1 + a)] += q * weight[k] * 0.25 * wx[b] * wy[a]
+    return Qg
+
+
+def test_gauss_law_residual_is_frozen():
+    """Integral form of Gauss's law on the deposit's control volumes (mode 0):
+         A_rt(cy) [Ex(cx+1,cy) - Ex(cx,cy)] + A_xt(cy) Er(cx,cy+1) - A_xt(cy-1) Er(cx,cy)  -  Q(cx,cy)/eps0
+    with Q the mean of the node charges at t+1/2 and t+3/2 (E at t+1 has seen half of each of the two
+    currents) stays frozen to rounding while the plasma rings: the charge-conserving deposit
+    (particles.F90:584-665) and update_e_field (fields.f90:67-108) are discretely consistent, and
+    div curl B vanishes on this mesh.  (Electrons only: the residual itself is the missing ion background.)"""
+    d, w, sc = _langmuir_world(nx=24, ny=12, ppc=4)
+    nx, ny, dt = d.nx, d.ny, sc["dt"]
+    tabs = _tables(ny, sc["dx"], sc["dy"])
+
+    def residual():
+        ex = w.field(0, "exm")[0].real
+        er = w.field(0, "erm")[0].real
+        pr = w.particles(0, 0)
+        u = pr[:, 3:6] / (M0 * C_LIGHT)
+        delta = u * (C_LIGHT * dt / 2.0) / np.sqrt(1 + (u * u).sum(1))[:, None]
+        Q = 0.5 * (_node_charge(pr[:, 0:3] + delta, pr[:, 6], -Q0, sc, nx, ny) +
+                   _node_charge(pr[:, 0:3] - delta, pr[:, 6], -Q0, sc, nx, ny))
+        res = np.zeros((ny, nx))
+        for cy in range(3, ny - 3):
+            a_rt, a_xt = tabs[cy]
+            a_xt_m = tabs[cy - 1][1]
+            for cx in range(3, nx - 3):
+                flux = (a_rt * (ex[fidx(cx + 1, cy)] - ex[fidx(cx, cy)])
+                        + a_xt * er[fidx(cx, cy + 1)] - a_xt_m * er[fidx(cx, cy)])
+                res[cy, cx] = flux - Q[fidx(cx, cy)] / EPSILON0
+                fluxes[cy, cx] = flux
+        return res, fluxes.copy()
+
+    fluxes = np.zeros((ny, nx))
+    w.step(3)       # past the start-up step, whose first half update has no current yet
+    r0, f0 = residual()
+    w.step(50)      # about half a plasma period
+    r1, f1 = residual()
+    moved = np.abs(f1 - f0).max()          # how much flux and charge each changed (they must cancel)
+    assert moved > 0
+    assert np.abs(r1 - r0).max() < 1e-8 * moved, np.abs(r1 - r0).max() / moved   # measured 5e-12
 
 
 def test_rng_and_loader_statistics():
