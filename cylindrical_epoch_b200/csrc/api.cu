@@ -115,7 +115,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   // the captured field phases hold NCCL send/recv nodes: they go before the communicator
-  for (int k = 0; k < 2; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
+  for (int k = 0; k < 3; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
   destroy_transport(c->tr);
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) cudaFree(c->f[k]);
   cudaFree(c->spare);
@@ -158,6 +158,7 @@ int cylgpu_set_species(cylgpu_handle c, int isp, const cylgpu_species* sp) {
   if (isp < 0 || isp >= c->cfg.n_species || !sp) { set_error("bad species index"); return 2; }
   c->species[isp].sp = *sp;
   c->species[isp].set = true;
+  c->graph_epoch += 1;
   set_neighbours(c);
   return 0;
 }
@@ -452,6 +453,7 @@ int cylgpu_set_current_smoothing(cylgpu_handle c, int enable, int its, int comp_
   if (its < 0 || comp_its < 0 || nstrides < 0 || (nstrides > 0 && !strides)) { set_error("bad smoothing settings"); return 2; }
   for (int k = 0; k < nstrides; ++k)
     if (strides[k] < 1 || strides[k] > NG) { set_error("smooth_strides must lie in 1..%d", NG); return 2; }
+  c->graph_epoch += 1;
   c->smooth_currents = enable != 0;
   c->smooth_its = its;
   c->smooth_comp_its = comp_its;
@@ -462,7 +464,7 @@ int cylgpu_set_current_smoothing(cylgpu_handle c, int enable, int its, int comp_
 int cylgpu_current_finish(cylgpu_handle c) {
   TRY(check_handle(c));
   PhaseTimer t(c, &c->stats.ms_bcs);
-  return do_current_finish(c);
+  return run_field_phase(c, 2, [c]() { return do_current_finish(c); });
 }
 
 // fields.f90:341-353

@@ -178,7 +178,7 @@ struct cylgpu_ctx {
   std::vector<int> smooth_strides;
   cylgpu::cplx* smooth_wk[2][3] = {{0, 0, 0}, {0, 0, 0}};
 
-  // The two field phases are chains of ~15 short launches each: replayed as CUDA graphs once their
+  // The field phases and current_finish are chains of short launches: replayed as CUDA graphs once their
   // parameters have been stable for a few steps (dt, bc_field, array pointers, stream: `graph_epoch`).
   struct PhaseGraph {
     cudaGraphExec_t exec = nullptr;
@@ -188,7 +188,7 @@ struct cylgpu_ctx {
     int64_t launches = 0;         // kernel launches inside (for the statistics)
     bool failed = false;
   };
-  PhaseGraph graphs[2];
+  PhaseGraph graphs[3];          // fields_half, fields_final, current_finish
   uint64_t graph_epoch = 0;
   bool use_graphs = true;
 
