@@ -1544,51 +1544,8 @@ void World::density_deposit_and_bcs(int current_species, bool charge) {
       }
     }
   }
-  // particle_reflection_bcs (the real-valued variant: at x_min only ng-1 ghost columns fold back)
-  for (Rank& r : ranks) {
-    Arr3& a = r.wk;
-    const int nx = r.nx, ny = r.ny;
-    for (int im = 0; im < M; ++im) {
-      if (r.x_min_boundary && bc_allspecies(BD_X_MIN) == BC_REFLECT)
-        for (int i = 1; i <= NG - 1; ++i)
-          for (int j = 1 - NG; j <= ny + NG; ++j) {
-            a(i, j, im) = a(i, j, im) + a(1 - i, j, im);
-            a(1 - i, j, im) = cplx(0.0);
-          }
-      if (r.x_max_boundary && bc_allspecies(BD_X_MAX) == BC_REFLECT)
-        for (int i = 1; i <= NG; ++i)
-          for (int j = 1 - NG; j <= ny + NG; ++j) {
-            a(nx + 1 - i, j, im) = a(nx + 1 - i, j, im) + a(nx + i, j, im);
-            a(nx + i, j, im) = cplx(0.0);
-          }
-      if (bc_allspecies(BD_Y_MAX) == BC_REFLECT)
-        for (int i = 1; i <= NG; ++i)
-          for (int ix = 1 - NG; ix <= nx + NG; ++ix) {
-            a(ix, ny + 1 - i, im) = a(ix, ny + 1 - i, im) + a(ix, ny + i, im);
-            a(ix, ny + i, im) = cplx(0.0);
-          }
-    }
-  }
-  periodic_sum_x(&Rank::wk);   // particle_periodic_bcs, x part (no r neighbours)
-  // field_mode_zero_gradient, c_stagger_centre, boundaries 1..4
-  for (Rank& r : ranks) {
-    Arr3& a = r.wk;
-    const int nx = r.nx, ny = r.ny;
-    for (int im = 0; im < M; ++im) {
-      if (bc_field[BD_X_MIN] != BC_PERIODIC && r.x_min_boundary)
-        for (int i = 1; i <= NG; ++i)
-          for (int j = 1 - NG; j <= ny + NG; ++j) a(i - NG, j, im) = a(NG + 1 - i, j, im);
-      if (bc_field[BD_X_MAX] != BC_PERIODIC && r.x_max_boundary)
-        for (int i = 1; i <= NG; ++i)
-          for (int j = 1 - NG; j <= ny + NG; ++j) a(nx + i, j, im) = a(nx + 1 - i, j, im);
-      if (bc_field[BD_Y_MIN] != BC_PERIODIC)
-        for (int i = 1; i <= NG; ++i)
-          for (int ix = 1 - NG; ix <= nx + NG; ++ix) a(ix, i - NG, im) = a(ix, NG + 1 - i, im);
-      if (bc_field[BD_Y_MAX] != BC_PERIODIC)
-        for (int i = 1; i <= NG; ++i)
-          for (int ix = 1 - NG; ix <= nx + NG; ++ix) a(ix, ny + i, im) = a(ix, ny + 1 - i, im);
-    }
-  }
+  moment_summation_bcs(&Rank::wk);   // calc_boundary_modes (cyl_moments.cpp)
+  centre_zero_gradient(&Rank::wk);   // field_mode_zero_gradient, c_stagger_centre, boundaries 1..4
 }
 
 // ---------------------------------------------------------------------------------------

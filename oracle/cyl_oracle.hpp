@@ -136,6 +136,12 @@ struct Laser {  // laser.f90 laser_block, restricted to what the decks in scope 
   double phase;               // constant phase
 };
 
+// the real-valued particle moments of io/calc_df.F90 (cyl_moments.cpp)
+enum Moment {
+  MOM_MASS_DENSITY = 0, MOM_NUMBER_DENSITY = 1, MOM_EKBAR = 2, MOM_EKFLUX = 3, MOM_PPC = 4,
+  MOM_AVERAGE_WEIGHT = 5, MOM_TEMPERATURE = 6, MOM_SPECIES_CURRENT = 7, MOM_AVERAGE_MOMENTUM = 8
+};
+
 struct Rank {
   int nx, ny, M;
   int x_coord, nprocx;
@@ -145,6 +151,7 @@ struct Rank {
   Arr3 exm, erm, etm, bxm, brm, btm, jxm, jrm, jtm;
   Arr3 bxm_old, brm_old, btm_old, jxm_old, jrm_old, jtm_old;
   Arr3 wk;   // work array of smooth_mode_array (current_smooth.F90:145-196)
+  Arr3 m0, m1, m2, m3, m4;   // work arrays of calc_moment (cyl_moments.cpp); real data in mode 0
   Arr2 exm_x_min, erm_x_min, etm_x_min, bxm_x_min, brm_x_min, btm_x_min;
   Arr2 exm_x_max, erm_x_max, etm_x_max, bxm_x_max, brm_x_max, btm_x_max;
   std::vector<std::vector<Particle>> parts;   // per species, in linked-list order
@@ -208,6 +215,9 @@ struct World {
   void calc_number_density_modes(int species);   // calc_df.F90:588-661 -> Rank::wk (species < 0: all)
   void calc_charge_density(int species);         // calc_df.F90:442-519 -> Rank::wk, mode 0, real part
   void density_deposit_and_bcs(int species, bool charge);
+  void calc_moment(int kind, int species, int direction);   // calc_df.F90:59-1221 -> Rank::m0 (cyl_moments.cpp)
+  void moment_summation_bcs(Arr3 Rank::*f);      // calc_boundary, calc_df.F90:24-31
+  void centre_zero_gradient(Arr3 Rank::*f);      // boundary.F90:597-707, c_stagger_centre
   bool smooth_currents = false;                  // shared_data.F90:468-472
   bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
   int smooth_its = 1, smooth_comp_its = 0;

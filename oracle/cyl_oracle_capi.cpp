@@ -71,6 +71,9 @@ void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
 // calc_number_density_modes into each rank's work array; returns rank k's pointer afterwards via cylo_wk_ptr
 void cylo_number_density_modes(void* w, int species) { ((World*)w)->calc_number_density_modes(species); }
 void cylo_charge_density(void* w, int species) { ((World*)w)->calc_charge_density(species); }
+// calc_df.F90 moments (cyl_moments.cpp): result in the real part of mode 0 of rank k's m0
+void cylo_moment(void* w, int kind, int species, int direction) { ((World*)w)->calc_moment(kind, species, direction); }
+void* cylo_moment_ptr(void* w, int k) { return (void*)((World*)w)->ranks[k].m0.d.data(); }
 void* cylo_wk_ptr(void* w, int k) { return (void*)((World*)w)->ranks[k].wk.d.data(); }
 void cylo_set_smoothing(void* wp, int enable, int its, int comp_its, int nstrides, const int32_t* strides) {
   World* w = (World*)wp;

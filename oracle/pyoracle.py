@@ -28,6 +28,10 @@ OPS = dict(step=0, fields_half=1, push=2, current_finish=3, fields_final=4, movi
            update_e=11, update_b=12, snapshot_boundaries=13, advance_half_time=14, push_no_bcs=15,
            current_bcs=16, flush_rng=17)
 
+# calc_df.F90 moments (cyl_moments.cpp / include/cylgpu.h CYLGPU_MOM_*)
+MOMENTS = dict(mass_density=0, number_density=1, ekbar=2, ekflux=3, ppc=4, average_weight=5, temperature=6,
+               species_current=7, average_momentum=8)
+
 Q0 = 1.602176565e-19
 M0 = 9.10938291e-31
 C_LIGHT = 2.99792458e8
@@ -47,7 +51,7 @@ class CyloConfig(C.Structure):
 def build(force=False):
     """Compile oracle/libcyl_oracle.so with the committed Makefile (g++, no FMA contraction)."""
     so = os.path.join(_HERE, "libcyl_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_moments.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
@@ -74,6 +78,10 @@ def lib():
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
         L.cylo_number_density_modes.restype = None
         L.cylo_number_density_modes.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_moment.restype = None
+        L.cylo_moment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.cylo_moment_ptr.restype = C.c_void_p
+        L.cylo_moment_ptr.argtypes = [C.c_void_p, C.c_int]
         L.cylo_charge_density.restype = None
         L.cylo_charge_density.argtypes = [C.c_void_p, C.c_int]
         L.cylo_wk_ptr.restype = C.c_void_p
@@ -159,6 +167,20 @@ class OracleWorld:
         """smooth_currents, smooth_its, smooth_compensation, smooth_strides of the control block"""
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
         self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
+
+    def moment(self, kind, species=-1, direction=0):
+        """one of the real-valued calc_df.F90 moments (MOMENTS keys; direction: +-1/2/3 = c_dir_x/y/z,
+        0 = absent): list of per-rank real arrays [ir+NG-1, ix+NG-1] (copies)"""
+        self.L.cylo_moment(self.h, MOMENTS[kind] if isinstance(kind, str) else int(kind), int(species),
+                           int(direction))
+        out = []
+        for k in range(self.nranks):
+            info = self.rank_info(k)
+            shape = (self.n_mode, info["ny"] + 2 * NG, info["nx"] + 2 * NG)
+            buf = (C.c_double * (2 * shape[0] * shape[1] * shape[2])).from_address(
+                self.L.cylo_moment_ptr(self.h, k))
+            out.append(np.frombuffer(buf, dtype=np.complex128).reshape(shape)[0].real.copy())
+        return out
 
     def charge_density(self, species=-1):
         """calc_charge_density (calc_df.F90:442-519): list of per-rank real arrays [ir+NG-1, ix+NG-1]"""
