@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "fields.cu", "bcs.cu", "particles.cu", "transport.cu", "window_insert.cu"]
-HEADERS = ["ctx.cuh", "push.cuh", "deposit_mma.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
+HEADERS = ["ctx.cuh", "push.cuh", "deposit_mma.cuh", "moments.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
 LIB = os.path.join(HERE, "libcylgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -556,6 +556,13 @@ int cylgpu_number_density_modes(cylgpu_handle c, int species, void* host_out) {
   return 0;
 }
 
+// the other calc_df.F90 moments (moments.cuh); host_out: real (nx+2ng, ny+2ng) array
+int cylgpu_particle_moment(cylgpu_handle c, int kind, int species, int direction, double* host_out) {
+  TRY(check_handle(c));
+  if (species >= c->cfg.n_species || !host_out) { set_error("particle_moment: bad argument"); return 2; }
+  return do_particle_moment(c, kind, species, direction, host_out);
+}
+
 // calc_charge_density (calc_df.F90:442-519); host_out: real (nx+2ng, ny+2ng) array
 int cylgpu_charge_density(cylgpu_handle c, int species, double* host_out) {
   TRY(check_handle(c));

@@ -4,6 +4,7 @@
 // particle_reflection_bcs_complex, particle_periodic_bcs_complex, efield_bcs, bfield_bcs,
 // bfield_final_bcs, current_bcs, current_bcs_r_min_final), laser.f90 outflow_bcs_*,
 // current_smooth.F90 current_finish and window.F90 shift_fields.
+#include <cfloat>
 #include <cstring>
 
 #include "ctx.cuh"
@@ -138,15 +139,18 @@ __global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx
   }
 }
 
+// `gg`: geometry of the arrays when it is not the handle's (the single-plane work arrays of the
+// particle moments, moments.cuh); the staging buffers are sized for the handle's n_mode >= 1.
 static int exchange3(cylgpu_ctx* c, const Halo3& h, int mode, bool send_l, bool send_r, bool recv_l,
-                     bool recv_r) {
-  const Geom& g = c->g;
+                     bool recv_r, const Geom* gg = nullptr) {
+  const Geom& g = gg ? *gg : c->g;
   if (!(send_l || send_r || recv_l || recv_r)) return 0;
-  const size_t bytes = (mode == 2 ? 2 : 1) * c->halo_elems * sizeof(cplx);
+  const size_t halo_elems = gg ? (size_t)3 * g.M * g.SY * NG : c->halo_elems;
+  const size_t bytes = (mode == 2 ? 2 : 1) * halo_elems * sizeof(cplx);
   dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
   if (send_l || send_r) {
     k_halo_pack<<<grd, 128, 0, c->stream>>>(g, h, send_l ? c->sbuf_l : nullptr, send_r ? c->sbuf_r : nullptr,
-                                            mode, c->halo_elems);
+                                            mode, halo_elems);
     c->stats.kernel_launches += 1;
   }
   TRY(transport_sendrecv(c, send_l ? c->sbuf_l : nullptr, send_l ? bytes : 0, recv_l ? c->rbuf_l : nullptr,
@@ -154,7 +158,7 @@ static int exchange3(cylgpu_ctx* c, const Halo3& h, int mode, bool send_l, bool 
                          recv_r ? c->rbuf_r : nullptr, recv_r ? bytes : 0));
   if (recv_l || recv_r) {
     k_halo_unpack<<<grd, 128, 0, c->stream>>>(g, h, recv_l ? c->rbuf_l : nullptr, recv_r ? c->rbuf_r : nullptr,
-                                              mode, c->halo_elems);
+                                              mode, halo_elems);
     c->stats.kernel_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
@@ -962,5 +966,7 @@ int do_shift_fields(cylgpu_ctx* c) {
   }
   return 0;
 }
+
+#include "moments.cuh"
 
 }  // namespace cylgpu

@@ -228,6 +228,7 @@ int do_bfield_final_bcs_device(cylgpu_ctx* c);
 int do_current_bcs(cylgpu_ctx* c);
 int do_current_finish(cylgpu_ctx* c);
 int do_number_density_modes(cylgpu_ctx* c, int species, bool charge);
+int do_particle_moment(cylgpu_ctx* c, int kind, int species, int direction, double* host_out);
 int download_real_part_mode0(cylgpu_ctx* c, const cplx* a, double* host_out);
 int do_r_min_final(cylgpu_ctx* c);
 int do_snapshot(cylgpu_ctx* c);

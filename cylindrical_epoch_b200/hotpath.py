@@ -229,6 +229,20 @@ class Slab:
         self._ck(self.L.cylgpu_charge_density(self.h, int(isp), a.ctypes.data))
         return a
 
+    # calc_df.F90 moments (include/cylgpu.h CYLGPU_MOM_*): calc_mass_density :59, calc_number_density :523,
+    # calc_ekbar :140, calc_ekflux :249, calc_ppc :665, calc_average_weight :716, calc_temperature :782,
+    # calc_per_species_current :1037, calc_average_momentum :1143
+    MOMENTS = dict(mass_density=0, number_density=1, ekbar=2, ekflux=3, ppc=4, average_weight=5, temperature=6,
+                   species_current=7, average_momentum=8)
+
+    def moment(self, kind, isp=-1, direction=0):
+        """real array [ir+ng-1, ix+ng-1] of one calc_df.F90 moment of species isp (< 0: all that carry
+        current); direction 1/2/3 = c_dir_x/y/z, negative for the backward ekflux, 0 = absent"""
+        a = np.empty(self.field_shape[1:], dtype=np.float64)
+        k = self.MOMENTS[kind] if isinstance(kind, str) else int(kind)
+        self._ck(self.L.cylgpu_particle_moment(self.h, k, int(isp), int(direction), a.ctypes.data))
+        return a
+
     def energy(self):
         out = (C.c_double * 2)()
         self._ck(self.L.cylgpu_energy(self.h, out))

@@ -246,6 +246,23 @@ int cylgpu_set_push_variant(cylgpu_handle h, int variant);
 int cylgpu_number_density_modes(cylgpu_handle h, int ispecies, void* host_out);
 /* calc_charge_density (calc_df.F90:442-519): real array (1-ng:nx+ng, 1-ng:ny+ng) */
 int cylgpu_charge_density(cylgpu_handle h, int ispecies, double* host_out);
+/* The other particle moments of io/calc_df.F90, from the device-resident lists (no particle
+ * download at dump steps).  host_out: real array (1-ng:nx+ng, 1-ng:ny+ng), with the reference's
+ * calc_boundary and field_zero_gradient ghost treatment.  ispecies < 0 is the reference's
+ * `current_species <= 0` (all species that carry current).  direction: 1, 2, 3 = c_dir_x, _y, _z
+ * (constants.F90:231-233), negative for the backward ekflux, 0 = argument absent. */
+enum {
+  CYLGPU_MOM_MASS_DENSITY = 0,     /* calc_mass_density        calc_df.F90:59-136   */
+  CYLGPU_MOM_NUMBER_DENSITY = 1,   /* calc_number_density      calc_df.F90:523-584  */
+  CYLGPU_MOM_EKBAR = 2,            /* calc_ekbar               calc_df.F90:140-245  */
+  CYLGPU_MOM_EKFLUX = 3,           /* calc_ekflux              calc_df.F90:249-391  (direction +-1..3) */
+  CYLGPU_MOM_PPC = 4,              /* calc_ppc                 calc_df.F90:665-712  */
+  CYLGPU_MOM_AVERAGE_WEIGHT = 5,   /* calc_average_weight      calc_df.F90:716-778  */
+  CYLGPU_MOM_TEMPERATURE = 6,      /* calc_temperature         calc_df.F90:782-1033 (direction 0..3) */
+  CYLGPU_MOM_SPECIES_CURRENT = 7,  /* calc_per_species_current calc_df.F90:1037-1139 (direction 1..3) */
+  CYLGPU_MOM_AVERAGE_MOMENTUM = 8  /* calc_average_momentum    calc_df.F90:1143-1221 (direction 1..3) */
+};
+int cylgpu_particle_moment(cylgpu_handle h, int kind, int ispecies, int direction, double* host_out);
 /* diagnostics the new code must own: field + kinetic energy from the
  * mode arrays with cylindrical volume elements; out[0] = field J, out[1] = kinetic J */
 int cylgpu_energy(cylgpu_handle h, double* out2);
