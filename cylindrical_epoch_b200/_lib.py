@@ -98,6 +98,10 @@ SYMBOLS = {
     "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
     "cylgpu_number_density_modes": (C.c_int, [H, C.c_int, C.c_void_p]),
     "cylgpu_charge_density": (C.c_int, [H, C.c_int, C.c_void_p]),
+    "cylgpu_insert_particles_device": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_double, C.c_double, C.c_uint64, C.c_uint64,
+                                                 C.POINTER(C.c_int64)]),
+    "cylgpu_philox4x32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cylgpu_particle_moment": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cylgpu_energy": (C.c_int, [H, _DP]),
     "cylgpu_stats": (C.c_int, [H, C.POINTER(Stats)]),

@@ -10,11 +10,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "fields.cu", "bcs.cu", "particles.cu", "transport.cu", "window_insert.cu"]
-HEADERS = ["ctx.cuh", "push.cuh", "deposit_mma.cuh", "moments.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
+HEADERS = ["ctx.cuh", "push.cuh", "deposit_mma.cuh", "moments.cuh", "philox.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
 LIB = os.path.join(HERE, "libcylgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall"] + os.environ.get("CYLGPU_DEFS", "").split()
+
+
+# window_insert.cu: the device-side column must give the oracle's weights and x positions bit for bit,
+# so its one kernel is compiled without FMA contraction (it runs once per window shift)
+EXTRA = {"window_insert.cu": ["-fmad=false"]}
 
 
 def _stale(target, deps):
@@ -34,7 +39,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(HERE, "build", s.replace(".cu", ".o"))
         objs.append(obj)
         if force or _stale(obj, [src] + hdrs):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + FLAGS + EXTRA.get(s, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -6,6 +6,7 @@
 #include <functional>
 
 #include "ctx.cuh"
+#include "philox.cuh"
 
 namespace cylgpu {
 
@@ -135,6 +136,9 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   c->timers.destroy();
   if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+  if (c->ins_pin) cudaFreeHost(c->ins_pin);
+  cudaFree(c->ins_dev);
+  if (c->ins_ev) cudaEventDestroy(c->ins_ev);
   if (c->src_stage) { cudaFreeHost(c->src_stage); for (int k = 0; k < 8; ++k) cudaEventDestroy(c->src_event[k]); }
   for (int k = 0; k < 3; ++k) {
     cudaFree(c->hs.in[k]);
@@ -542,6 +546,25 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
   const int64_t n = (int64_t)(aos.size() / 7);
   if (n_inserted) *n_inserted = n;
   if (n > 0) TRY(append_impl(c, isp, n, aos.data()));
+  return 0;
+}
+
+// insert_particles generated on the device from a counter-based stream (window_insert.cu)
+int cylgpu_insert_particles_device(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell,
+                                   const double* density, const double* temperature, const double* drift, double dmin,
+                                   double dmax, uint64_t seed, uint64_t column, int64_t* n_inserted) {
+  TRY(check_handle(c));
+  if (isp < 0 || isp >= c->cfg.n_species || !c->species[isp].set) { set_error("bad species index"); return 2; }
+  if (!density || !temperature || !drift) { set_error("insert_particles_device: null profile"); return 2; }
+  return do_insert_particles_device(c, isp, x_grid_max, npart_per_cell, density, temperature, drift, dmin, dmax, seed,
+                                    column, n_inserted);
+}
+// Philox4x32-10 on the host (no device needed): lets the stream be checked against the published
+// known-answer vectors and lets a host reproduce any particle of a device-generated column
+int cylgpu_philox4x32(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4) {
+  if (!ctr4 || !key2 || !out4) { set_error("philox4x32: null argument"); return 2; }
+  const Philox4 p = philox4x32_10(ctr4[0], ctr4[1], ctr4[2], ctr4[3], key2[0], key2[1]);
+  for (int i = 0; i < 4; ++i) out4[i] = p.v[i];
   return 0;
 }
 

@@ -195,6 +195,11 @@ struct cylgpu_ctx {
   cylgpu::Transport* tr = nullptr;
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)
+  // device-side column (cylgpu_insert_particles_device): profile + row-offset staging
+  double* ins_pin = nullptr;
+  double* ins_dev = nullptr;
+  size_t ins_cap = 0;
+  cudaEvent_t ins_ev = nullptr;
   int64_t host_chunk = 1 << 21;   // particles per chunk of the host-resident path (117 MB)
 
   int sort_interval = 1;
@@ -253,6 +258,9 @@ double kiss_box_muller(KissState& s, double stdev, double mu);
 int do_insert_particles(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell, const double* density,
                         const double* temperature, const double* drift, double dmin, double dmax,
                         std::vector<double>& aos);
+int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell, const double* density,
+                               const double* temperature, const double* drift, double dmin, double dmax, uint64_t seed,
+                               uint64_t column, int64_t* n_inserted);
 // transport.cu
 Transport* make_transport(cylgpu_ctx* c);
 void destroy_transport(Transport* t);

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "ctx.cuh"
+#include "philox.cuh"
 
 namespace cylgpu {
 
@@ -109,6 +110,152 @@ int do_insert_particles(cylgpu_ctx* c, int isp, double x_grid_max, double npart_
       aos.insert(aos.end(), p, p + 7);
     }
   }
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Device-side column: the same per-particle arithmetic as above
+// (window.F90:226-296), but every particle draws from its own counter of a Philox4x32-10 stream
+// instead of the rank's sequential KISS stream, so the column is generated by one kernel straight
+// into the SoA list -- no host loop over particles, no upload, and the plasma no longer depends
+// on how many ranks share the grid.  Not bit-identical to the reference's column by construction
+// (a different generator; Gaussians by the trigonometric Box-Muller transform instead of the
+// polar rejection loop); the oracle restates this very stream for the parity tests.
+//   block 0: (r offset, theta)   block 1: (x offset, ua1)   block 2: (ub1, ua2)   block 3: (ub2, -)
+//   (px, py) = sqrt(-2 ln(1 - ua1)) (cos, sin)(2 pi ub1),  pz = sqrt(-2 ln(1 - ua2)) cos(2 pi ub2)
+// ------------------------------------------------------------------------------------------
+struct ColumnArgs {
+  ColumnStream rs;
+  const double* prof;        // [density | temperature(3) | drift(3)] x (ny + 2), density already clamped
+  const int64_t* row_start;  // ny + 1 entries, row iy -> [row_start[iy-1], row_start[iy])
+  double *x, *y, *z, *px, *py, *pz, *w;
+  int64_t base;
+  int ny, iy_global_offset;
+  double dx, dy, x0, y_grid_min_local, mass;
+};
+
+__global__ void __launch_bounds__(128) k_insert_column(ColumnArgs a) {
+  const int iy = blockIdx.x + 1;
+  const int64_t r0 = a.row_start[iy - 1];
+  const int64_t ncell = a.row_start[iy] - r0;
+  const int nrow = a.ny + 2;
+  const double y_iy = a.y_grid_min_local + (double)(iy - 1) * a.dy;
+  for (int64_t ip = threadIdx.x; ip < ncell; ip += blockDim.x) {
+    const uint32_t iyg = (uint32_t)(iy + a.iy_global_offset);
+    const Philox4 b0 = a.rs.block(iyg, (uint32_t)ip, 0), b1 = a.rs.block(iyg, (uint32_t)ip, 1);
+    const Philox4 b2 = a.rs.block(iyg, (uint32_t)ip, 2), b3 = a.rs.block(iyg, (uint32_t)ip, 3);
+    const double cell_frac_y = 0.5 - philox_u53(b0.v[0], b0.v[1]);
+    const double part_r = y_iy - cell_frac_y * a.dy;
+    const double part_theta = 2.0 * PI * philox_u53(b0.v[2], b0.v[3]);
+    const double X = a.x0 + philox_u53(b1.v[0], b1.v[1]) * a.dx;
+    const double wdata = (2.0 * PI * a.dx * a.dy * part_r) / (double)ncell;
+    const double cy2 = cell_frac_y * cell_frac_y;
+    const double gy[3] = {0.5 * (0.25 + cy2 + cell_frac_y), 0.75 - cy2, 0.5 * (0.25 + cy2 - cell_frac_y)};
+    const double rad1 = sqrt(-2.0 * log(1.0 - philox_u53(b1.v[2], b1.v[3])));
+    const double ang1 = 2.0 * PI * philox_u53(b2.v[0], b2.v[1]);
+    const double rad2 = sqrt(-2.0 * log(1.0 - philox_u53(b2.v[2], b2.v[3])));
+    const double ang2 = 2.0 * PI * philox_u53(b3.v[0], b3.v[1]);
+    const double gauss[3] = {rad1 * cos(ang1), rad1 * sin(ang1), rad2 * cos(ang2)};
+    double p[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double temp_local = 0.0, drift_local = 0.0;
+#pragma unroll
+      for (int k = -1; k <= 1; ++k) {
+        temp_local = temp_local + gy[k + 1] * a.prof[(1 + i) * nrow + iy + k];
+        drift_local = drift_local + gy[k + 1] * a.prof[(4 + i) * nrow + iy + k];
+      }
+      p[i] = gauss[i] * sqrt(temp_local * KB * a.mass) + drift_local;   // particle_temperature.F90:388-398
+    }
+    double weight_local = 0.0;
+#pragma unroll
+    for (int k = -1; k <= 1; ++k) weight_local = weight_local + gy[k + 1] * a.prof[iy + k];
+    const int64_t o = a.base + r0 + ip;
+    a.x[o] = X;
+    a.y[o] = part_r * cos(part_theta);
+    a.z[o] = part_r * sin(part_theta);
+    a.px[o] = p[0];
+    a.py[o] = p[1];
+    a.pz[o] = p[2];
+    a.w[o] = weight_local * wdata;
+  }
+}
+
+int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell_real,
+                               const double* density_in, const double* temperature, const double* drift, double dmin,
+                               double dmax, uint64_t seed, uint64_t column, int64_t* n_inserted) {
+  if (n_inserted) *n_inserted = 0;
+  if (!c->cfg.x_max_boundary) return 0;   // only the rightmost rank injects (window.F90:176)
+  SpeciesState& S = c->species[isp];
+  const int ny = c->g.ny, nrow = ny + 2;
+  const int64_t npart_per_cell = (int64_t)std::floor(npart_per_cell_real);
+  const double npart_frac = npart_per_cell_real - (double)npart_per_cell;
+  if (npart_per_cell + 1 >= (int64_t)1 << 30) { set_error("insert_particles_device: npart_per_cell too large"); return 2; }
+  const ColumnStream rs = column_stream(seed, isp, column);
+  // staging: 7 profile rows then the row offsets, pinned so that the upload never blocks
+  const size_t words = (size_t)7 * nrow + (size_t)(ny + 1);
+  if (c->ins_cap < words) {
+    if (c->ins_ev) CUDA_TRY(cudaEventSynchronize(c->ins_ev));
+    if (c->ins_pin) cudaFreeHost(c->ins_pin);
+    if (c->ins_dev) cudaFree(c->ins_dev);
+    c->ins_pin = nullptr; c->ins_dev = nullptr; c->ins_cap = 0;
+    CUDA_TRY(cudaMallocHost(&c->ins_pin, words * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->ins_dev, words * sizeof(double)));
+    if (!c->ins_ev) CUDA_TRY(cudaEventCreateWithFlags(&c->ins_ev, cudaEventDisableTiming));
+    c->ins_cap = words;
+  } else {
+    CUDA_TRY(cudaEventSynchronize(c->ins_ev));   // the previous column's upload has left the pinned buffer
+  }
+  double* prof = c->ins_pin;
+  int64_t* row_start = reinterpret_cast<int64_t*>(c->ins_pin + (size_t)7 * nrow);
+  for (int iy = 0; iy < nrow; ++iy) {   // window.F90:203-209
+    double d = density_in[iy];
+    if (d > dmax) d = dmax;
+    if (d < dmin) d = 0.0;
+    prof[iy] = d;
+  }
+  for (int i = 0; i < 3 * nrow; ++i) {
+    prof[nrow + i] = temperature[i];
+    prof[4 * nrow + i] = drift[i];
+  }
+  // every rank owns all radial cells (nprocy = 1): the global radial index is the local one
+  const int iy_global_offset = 0;
+  int64_t total = 0;
+  row_start[0] = 0;
+  for (int iy = 1; iy <= ny; ++iy) {
+    int64_t ncell = 0;
+    if (!(prof[iy] < dmin)) {
+      int64_t n_frac = 0;
+      if (npart_frac > 0.0 && rs.cell_uniform((uint32_t)(iy + iy_global_offset)) < npart_frac) n_frac = 1;
+      ncell = npart_per_cell + n_frac;
+    }
+    total += ncell;
+    row_start[iy] = total;
+  }
+  if (n_inserted) *n_inserted = total;
+  if (total == 0) return 0;
+  TRY(reserve_particles(c, isp, S.n + total));
+  CUDA_TRY(cudaMemcpyAsync(c->ins_dev, c->ins_pin, words * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaEventRecord(c->ins_ev, c->stream));
+  ColumnArgs a;
+  a.rs = rs;
+  a.prof = c->ins_dev;
+  a.row_start = reinterpret_cast<const int64_t*>(c->ins_dev + (size_t)7 * nrow);
+  a.x = S.d[0]; a.y = S.d[1]; a.z = S.d[2]; a.px = S.d[3]; a.py = S.d[4]; a.pz = S.d[5]; a.w = S.d[6];
+  a.base = S.n;
+  a.ny = ny;
+  a.iy_global_offset = iy_global_offset;
+  a.dx = c->cfg.dx; a.dy = c->cfg.dy;
+  a.x0 = x_grid_max + 0.5 * c->cfg.dx;
+  a.y_grid_min_local = c->cfg.y_grid_min_local;
+  a.mass = S.sp.mass;
+  k_insert_column<<<ny, 128, 0, c->stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  c->stats.kernel_launches += 1;
+  S.n += total;
+  c->stats.n_particles[isp] = S.n;
+  c->sorted_valid = false;
   return 0;
 }
 

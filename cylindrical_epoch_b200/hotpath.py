@@ -90,7 +90,7 @@ class Slab:
                  dt_multiplier=0.95, lasers=(), transport=TRANSPORT_NONE, device=-1, fabric=None,
                  nccl_unique_id=None, sendrecv=None, move_window=False, window_v_x=0.0,
                  window_start_time=0.0, window_stop_time=1e300, bc_x_min_after_move=BC_SIMPLE_OUTFLOW,
-                 bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None):
+                 bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None, device_insert_seed=None):
         self.L = _lib.load()
         self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier)
         g = self.grid
@@ -111,6 +111,9 @@ class Slab:
         self.window_shift_fraction = 0.0
         self.window_shifts_total = 0
         self.insert_fn = insert_fn
+        # not None: the plasma column of the moving window is generated on the device from the
+        # counter-based stream of cylgpu_insert_particles_device (seeded with this number)
+        self.device_insert_seed = device_insert_seed
         self.host_lists = None
         self.host_counts = None
         self._keep = []   # ctypes objects that must outlive the handle
@@ -293,6 +296,20 @@ class Slab:
                                                 float(sp.density_min), float(sp.density_max), C.byref(n)))
         return n.value
 
+    def insert_particles_device(self, isp, seed, column):
+        """insert_particles (window.F90:157-300) generated by one kernel from the Philox stream
+        (seed, species, column): no host loop, no upload, independent of the number of ranks"""
+        sp = self.species[isp]
+        nrow = self.grid.ny + 2
+        dens = np.full(nrow, float(sp.density))
+        temp = np.repeat(np.asarray(sp.temp, dtype=np.float64), nrow)
+        drift = np.repeat(np.asarray(sp.drift, dtype=np.float64), nrow)
+        n = C.c_int64()
+        self._ck(self.L.cylgpu_insert_particles_device(
+            self.h, isp, self.grid.x_grid_max, float(sp.npart_per_cell), dens.ctypes.data, temp.ctypes.data,
+            drift.ctypes.data, float(sp.density_min), float(sp.density_max), int(seed), int(column), C.byref(n)))
+        return n.value
+
     def set_pusher(self, higuera_cary):       # -DHC_PUSH, particles.F90:409-421
         self._ck(self.L.cylgpu_set_pusher(self.h, int(bool(higuera_cary))))
 
@@ -449,7 +466,11 @@ class Slab:
         n_new = (C.c_int64 * max(nsp, 1))()
         ptrs = (C.c_void_p * max(nsp, 1))()
         keep = []
-        if self.insert_fn is None:
+        if self.device_insert_seed is not None:
+            for isp in range(nsp):
+                if self.species[isp].npart_per_cell > 0 and self.species[isp].density > 0:
+                    self.insert_particles_device(isp, self.device_insert_seed, self.window_shifts_total)
+        elif self.insert_fn is None:
             # insert_particles with the rank's KISS stream, species in deck order (window.F90:191)
             for isp in range(nsp):
                 if self.species[isp].npart_per_cell > 0 and self.species[isp].density > 0:

@@ -220,6 +220,22 @@ int cylgpu_insert_particles(cylgpu_handle h, int ispecies, double x_grid_max, do
                             const double* density, const double* temperature, const double* drift, double dmin,
                             double dmax, int64_t* n_inserted);
 
+/* The same column generated ON THE DEVICE from a counter-based stream: one
+ * kernel writes the new particles straight into the SoA list, with no host loop or upload, and
+ * the plasma does not depend on the number of ranks.  Same arguments and per-particle arithmetic
+ * as cylgpu_insert_particles (window.F90:187-298); NOT bit-identical to the reference's column
+ * (documented non-bit-parity mode): the uniforms come from Philox4x32-10 with
+ *   key = (seed low word, seed high word + ispecies),
+ *   counter = (column low word, column high word, radial cell iy, 4 * ip + block)
+ * for particle ip of cell iy (blocks 0..3; (.., .., iy, 0xFFFFFFFF) decides the cell's fractional
+ * particle), 53-bit uniforms from word pairs, and the momenta use the trigonometric Box-Muller
+ * transform.  column = a number that is unique per inserted column (the total number of window
+ * shifts so far).  cylgpu_philox4x32 evaluates the generator on the host. */
+int cylgpu_insert_particles_device(cylgpu_handle h, int ispecies, double x_grid_max, double npart_per_cell,
+                                   const double* density, const double* temperature, const double* drift,
+                                   double dmin, double dmax, uint64_t seed, uint64_t column, int64_t* n_inserted);
+int cylgpu_philox4x32(const uint32_t* ctr4, const uint32_t* key2, uint32_t* out4);
+
 /* ---- pieces, exposed because the reference calls them on their own ---- */
 int cylgpu_update_e_field(cylgpu_handle h);                 /* fields.f90:53-182 */
 int cylgpu_update_b_field(cylgpu_handle h);                 /* fields.f90:186-312 */

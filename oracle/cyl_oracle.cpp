@@ -1649,7 +1649,10 @@ void World::moving_window() {
   if (window_shift_cells > 0) {
     double window_shift_real = (double)window_shift_cells;
     for (int iw = 0; iw < window_shift_cells; ++iw) {   // shift_window, window.F90:62-94
-      for (Rank& r : ranks) insert_particles(r);
+      for (Rank& r : ranks) {
+        if (counter_insert) insert_particles_counter(r);
+        else insert_particles(r);
+      }
       x_grid_min = x_grid_min + dx;       // x_global(1) + dx
       xb_min = xb_min + dx;               // xb_global(1) + dx
       x_min = xb_min;

@@ -171,6 +171,8 @@ struct Config {
   int bc_x_min_after_move, bc_x_max_after_move;
 };
 
+void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);   // cyl_philox.cpp
+
 struct World {
   Config cfg;
   int M;
@@ -236,6 +238,9 @@ struct World {
   void reflection_bcs(Rank& r, Arr3& a, int im, int flip_dir);     // boundary.F90:918-1015
   void periodic_sum_x(Arr3 Rank::*f);            // boundary.F90:1133-1203
   void insert_particles(Rank& r);                // window.F90:157-300
+  void insert_particles_counter(Rank& r);        // the same with Philox counters (cyl_philox.cpp)
+  bool counter_insert = false;                   // moving_window uses insert_particles_counter
+  uint64_t counter_seed = 0;
   void shift_fields();                           // window.F90:98-153
   int bc_allspecies(int bd) const;
 };

@@ -71,6 +71,20 @@ void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
 // calc_number_density_modes into each rank's work array; returns rank k's pointer afterwards via cylo_wk_ptr
 void cylo_number_density_modes(void* w, int species) { ((World*)w)->calc_number_density_modes(species); }
 void cylo_charge_density(void* w, int species) { ((World*)w)->calc_charge_density(species); }
+// counter-based plasma column (cyl_philox.cpp)
+void cylo_set_counter_insert(void* w, int on, uint64_t seed) {
+  ((World*)w)->counter_insert = on != 0;
+  ((World*)w)->counter_seed = seed;
+}
+// one column with a given column number (tests of the device kernel against a single column)
+void cylo_insert_column(void* wp, uint64_t column) {
+  World* w = (World*)wp;
+  const int64_t keep = w->window_shifts_total;
+  w->window_shifts_total = (int64_t)column;
+  for (Rank& r : w->ranks) w->insert_particles_counter(r);
+  w->window_shifts_total = keep;
+}
+void cylo_philox4x32(const uint32_t* ctr, const uint32_t* key, uint32_t* out) { philox4x32_10(ctr, key, out); }
 // calc_df.F90 moments (cyl_moments.cpp): result in the real part of mode 0 of rank k's m0
 void cylo_moment(void* w, int kind, int species, int direction) { ((World*)w)->calc_moment(kind, species, direction); }
 void* cylo_moment_ptr(void* w, int k) { return (void*)((World*)w)->ranks[k].m0.d.data(); }

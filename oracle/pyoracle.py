@@ -51,10 +51,19 @@ class CyloConfig(C.Structure):
 def build(force=False):
     """Compile oracle/libcyl_oracle.so with the committed Makefile (g++, no FMA contraction)."""
     so = os.path.join(_HERE, "libcyl_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_moments.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_moments.cpp", "cyl_philox.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
+
+
+def philox4x32(ctr, key):
+    """Philox4x32-10 of the oracle (cyl_philox.cpp): 4 counter words, 2 key words -> 4 words"""
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    o = (C.c_uint32 * 4)()
+    lib().cylo_philox4x32(c, k, o)
+    return list(o)
 
 
 def lib():
@@ -78,6 +87,10 @@ def lib():
         L.cylo_set_time.argtypes = [C.c_void_p, C.c_double]
         L.cylo_number_density_modes.restype = None
         L.cylo_number_density_modes.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_set_counter_insert.restype = None
+        L.cylo_set_counter_insert.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.cylo_philox4x32.restype = None
+        L.cylo_philox4x32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.cylo_moment.restype = None
         L.cylo_moment.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.cylo_moment_ptr.restype = C.c_void_p
@@ -167,6 +180,10 @@ class OracleWorld:
         """smooth_currents, smooth_its, smooth_compensation, smooth_strides of the control block"""
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
         self.L.cylo_set_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr)
+
+    def set_counter_insert(self, on, seed=0):
+        """moving window: generate the new column from Philox counters (cyl_philox.cpp) instead of KISS"""
+        self.L.cylo_set_counter_insert(self.h, int(on), int(seed))
 
     def moment(self, kind, species=-1, direction=0):
         """one of the real-valued calc_df.F90 moments (MOMENTS keys; direction: +-1/2/3 = c_dir_x/y/z,

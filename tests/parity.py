@@ -36,7 +36,7 @@ class Pair:
     """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
 
     def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None, host_resident=False,
-                 host_chunk=None, smoothing=None, hc_push=False, prepare=None):
+                 host_chunk=None, smoothing=None, hc_push=False, prepare=None, slab_kw=None):
         self.deck = deck
         self.nranks = nranks
         self.oracle = decks.make_oracle(deck, nranks=nranks)
@@ -48,6 +48,7 @@ class Pair:
             from cylindrical_epoch_b200 import _lib
             self.fabric = _lib.load().cylgpu_fabric_create(nranks)
             kw = dict(transport=TRANSPORT_FABRIC, fabric=self.fabric)
+        kw.update(slab_kw or {})
         self.slabs = [decks.make_slab(deck, rank=k, nranks=nranks, **kw) for k in range(nranks)]
         for k, s in enumerate(self.slabs):
             decks.copy_state(self.oracle, s, k)
