@@ -40,6 +40,17 @@ class Stats(C.Structure):
                 ("n_push_kernel", C.c_int64)]
 
 
+class SdfDesc(C.Structure):   # cylgpu_sdf_desc
+    _fields_ = [("nx_global", C.c_int32), ("ny_global", C.c_int32), ("n_mode", C.c_int32), ("n_species", C.c_int32),
+                ("nx_local", C.c_int32), ("cell_x_min", C.c_int32),
+                ("step", C.c_int32), ("restart", C.c_int32), ("jobid1", C.c_int32), ("jobid2", C.c_int32),
+                ("have_extents", C.c_int32), ("pad_", C.c_int32),
+                ("time", C.c_double), ("x_min", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
+                ("species_name", C.c_char_p * MAX_SPECIES),
+                ("npart_global", C.c_int64 * MAX_SPECIES), ("npart_offset", C.c_int64 * MAX_SPECIES),
+                ("npart_local", C.c_int64 * MAX_SPECIES), ("part_extents", (C.c_double * 6) * MAX_SPECIES)]
+
+
 # every symbol include/cylgpu.h declares: name -> (restype, argtypes)
 H = C.c_void_p
 _DP = C.POINTER(C.c_double)
@@ -102,6 +113,11 @@ SYMBOLS = {
                                                  C.c_double, C.c_double, C.c_uint64, C.c_uint64,
                                                  C.POINTER(C.c_int64)]),
     "cylgpu_philox4x32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cylgpu_sdf_write_host": (C.c_int, [C.c_char_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cylgpu_sdf_read_host": (C.c_int, [C.c_char_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p), C.c_double, C.c_double,
+                                       C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "cylgpu_sdf_dump": (C.c_int, [H, C.c_char_p, C.POINTER(SdfDesc)]),
+    "cylgpu_sdf_load": (C.c_int, [H, C.c_char_p, C.POINTER(SdfDesc)]),
     "cylgpu_particle_moment": (C.c_int, [H, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "cylgpu_energy": (C.c_int, [H, _DP]),
     "cylgpu_stats": (C.c_int, [H, C.POINTER(Stats)]),

@@ -549,6 +549,89 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
   return 0;
 }
 
+// ---- SDF dump / restart (sdf_io.cu) ----
+int cylgpu_sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
+                          const double* const* particles_aos) {
+  return sdf_write_host(path, d, fields15, particles_aos);
+}
+int cylgpu_sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, double x_lo, double x_hi,
+                         double* const* particles_aos, const int64_t* capacity) {
+  std::vector<std::vector<double>> parts;
+  TRY(sdf_read_host(path, d, fields15, x_lo, x_hi, &parts));
+  if (!particles_aos) return 0;
+  for (int s = 0; s < d->n_species; ++s) {
+    const int64_t n = (int64_t)(parts[(size_t)s].size() / 7);
+    if (n == 0) continue;
+    if (!capacity || !particles_aos[s] || capacity[s] < n) {
+      set_error("sdf_read_host: species %d needs room for %lld particles", s, (long long)n);
+      return 2;
+    }
+    memcpy(particles_aos[s], parts[(size_t)s].data(), (size_t)n * 7 * sizeof(double));
+  }
+  return 0;
+}
+int cylgpu_sdf_dump(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
+  TRY(check_handle(c));
+  if (!d || !path) { set_error("sdf_dump: null argument"); return 2; }
+  const Geom& g = c->g;
+  if (d->nx_local != g.nx || d->ny_global != g.ny || d->n_mode != g.M || d->n_species != c->cfg.n_species) {
+    set_error("sdf_dump: the descriptor does not match the handle");
+    return 2;
+  }
+  const size_t nf = g.plane * g.M;
+  std::vector<std::vector<cplx>> host((size_t)CYLGPU_NFIELDS, std::vector<cplx>(nf));
+  const void* fptr[CYLGPU_NFIELDS];
+  for (int k = 0; k < CYLGPU_NFIELDS; ++k) {
+    CUDA_TRY(cudaMemcpyAsync(host[(size_t)k].data(), c->f[k], nf * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+    fptr[k] = host[(size_t)k].data();
+  }
+  std::vector<std::vector<double>> parts((size_t)d->n_species);
+  const double* pptr[CYLGPU_MAX_SPECIES] = {0};
+  for (int s = 0; s < d->n_species; ++s) {
+    const int64_t n = c->species[s].n;
+    d->npart_local[s] = n;
+    parts[(size_t)s].resize((size_t)(7 * n));
+    if (n > 0) TRY(cylgpu_download_particles(c, s, n, parts[(size_t)s].data(), nullptr));
+    pptr[s] = parts[(size_t)s].data();
+    if (c->cfg.nranks == 1) { d->npart_global[s] = n; d->npart_offset[s] = 0; }
+    if (!d->have_extents) {
+      double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+      for (int64_t i = 0; i < n; ++i)
+        for (int q = 0; q < 3; ++q) {
+          const double v = parts[(size_t)s][(size_t)(7 * i + q)];
+          if (v < lo[q]) lo[q] = v;
+          if (v > hi[q]) hi[q] = v;
+        }
+      for (int q = 0; q < 3; ++q) { d->part_extents[s][q] = n ? lo[q] : 0.0; d->part_extents[s][3 + q] = n ? hi[q] : 0.0; }
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return sdf_write_host(path, d, fptr, pptr);
+}
+int cylgpu_sdf_load(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
+  TRY(check_handle(c));
+  if (!d || !path) { set_error("sdf_load: null argument"); return 2; }
+  const Geom& g = c->g;
+  if (d->nx_local != g.nx || d->ny_global != g.ny || d->n_mode != g.M || d->n_species != c->cfg.n_species) {
+    set_error("sdf_load: the descriptor does not match the handle");
+    return 2;
+  }
+  const size_t nf = g.plane * g.M;
+  std::vector<std::vector<cplx>> host((size_t)CYLGPU_NFIELDS, std::vector<cplx>(nf, C(0.0, 0.0)));
+  void* fptr[CYLGPU_NFIELDS];
+  for (int k = 0; k < CYLGPU_NFIELDS; ++k) fptr[k] = host[(size_t)k].data();
+  std::vector<std::vector<double>> parts;
+  // the slab owns x_min_local <= x < x_max_local (boundary.F90:1607,1685)
+  TRY(sdf_read_host(path, d, fptr, c->x_min_local, c->x_max_local, &parts));
+  for (int k = 0; k < CYLGPU_NFIELDS; ++k)
+    CUDA_TRY(cudaMemcpyAsync(c->f[k], host[(size_t)k].data(), nf * sizeof(cplx), cudaMemcpyHostToDevice, c->stream));
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int s = 0; s < d->n_species; ++s)
+    TRY(cylgpu_upload_particles(c, s, (int64_t)(parts[(size_t)s].size() / 7), parts[(size_t)s].data()));
+  c->graph_epoch++;
+  return 0;
+}
+
 // insert_particles generated on the device from a counter-based stream (window_insert.cu)
 int cylgpu_insert_particles_device(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell,
                                    const double* density, const double* temperature, const double* drift, double dmin,

@@ -261,6 +261,11 @@ int do_insert_particles(cylgpu_ctx* c, int isp, double x_grid_max, double npart_
 int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell, const double* density,
                                const double* temperature, const double* drift, double dmin, double dmax, uint64_t seed,
                                uint64_t column, int64_t* n_inserted);
+// sdf_io.cu
+int sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
+                   const double* const* particles_aos);
+int sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, double x_lo, double x_hi,
+                  std::vector<std::vector<double>>* particles);
 // transport.cu
 Transport* make_transport(cylgpu_ctx* c);
 void destroy_transport(Transport* t);

@@ -246,6 +246,51 @@ class Slab:
         self._ck(self.L.cylgpu_particle_moment(self.h, k, int(isp), int(direction), a.ctypes.data))
         return a
 
+    # ------------------------------------------------------------------ SDF dump / restart
+    def _sdf_desc(self, species_names, step=None, time=None, restart=False):
+        g = self.grid
+        d = _lib.SdfDesc()
+        d.nx_global, d.ny_global, d.n_mode, d.n_species = g.nx_global, g.ny_global, self.n_mode, len(self.species)
+        d.nx_local, d.cell_x_min = g.nx, g.cell_x_min
+        d.step = self.step if step is None else int(step)
+        d.time = self.time if time is None else float(time)
+        d.restart = int(bool(restart))
+        d.x_min, d.dx, d.dy = g.xb_min, g.dx, g.dy
+        self._sdf_names = [n.encode() if isinstance(n, str) else n for n in species_names]
+        for i, n in enumerate(self._sdf_names):
+            d.species_name[i] = n
+        return d
+
+    def sdf_dump(self, path, species_names, npart_global=None, npart_offset=None, restart=False):
+        """one SDF file in the reference's layout (io/diagnostics.F90:497-575,2033-2110,3040-3160) written
+        from the device mirrors; with several ranks pass the global particle counts and this rank's offsets
+        (the reference's species_offset) -- every rank calls with the same path"""
+        d = self._sdf_desc(species_names, restart=restart)
+        if npart_global is not None:
+            for i in range(len(self.species)):
+                d.npart_global[i] = int(npart_global[i])
+                d.npart_offset[i] = int(npart_offset[i])
+        self._ck(self.L.cylgpu_sdf_dump(self.h, str(path).encode(), C.byref(d)))
+        return d
+
+    def sdf_load(self, path, species_names):
+        """restart of the hot-path state from such a file (housekeeping/setup.F90:1196-1260,1424-1466):
+        interior of the 15 mode arrays, this slab's particles, step and time; the ghosts are then
+        re-derived by the boundary routines"""
+        d = self._sdf_desc(species_names)
+        self._ck(self.L.cylgpu_sdf_load(self.h, str(path).encode(), C.byref(d)))
+        self.step, self.time = int(d.step), float(d.time)
+        self.efield_bcs()
+        self.bfield_bcs(False)
+        # J ghosts: the halo of current_finish without smoothing the stored (already smoothed) currents again
+        sm = getattr(self, "_smoothing", (False, 1, 0, ()))
+        if sm[0]:
+            self.set_current_smoothing(False)
+        self._ck(self.L.cylgpu_current_finish(self.h))
+        if sm[0]:
+            self.set_current_smoothing(*sm)
+        return d
+
     def energy(self):
         out = (C.c_double * 2)()
         self._ck(self.L.cylgpu_energy(self.h, out))
@@ -398,6 +443,7 @@ class Slab:
     def set_current_smoothing(self, enable, its=1, comp_its=0, strides=()):
         """smooth_currents, smooth_its, smooth_compensation, smooth_strides (deck_control_block.F90:447-466)"""
         arr = (C.c_int32 * max(len(strides), 1))(*strides)
+        self._smoothing = (bool(enable), int(its), int(comp_its), tuple(strides))
         self._ck(self.L.cylgpu_set_current_smoothing(self.h, int(enable), int(its), int(comp_its), len(strides), arr))
 
     def current_finish(self):                 # current_smooth.F90:29-45

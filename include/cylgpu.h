@@ -279,6 +279,41 @@ enum {
   CYLGPU_MOM_AVERAGE_MOMENTUM = 8  /* calc_average_momentum    calc_df.F90:1143-1221 (direction 1..3) */
 };
 int cylgpu_particle_moment(cylgpu_handle h, int kind, int ispecies, int direction, double* host_out);
+/* ---- SDF dump / restart of the hot-path state straight from the device mirrors ----
+ * (SURVEY.md 8(f)4).  One SDF 1.4 file in the reference's layout: the 'grid' mesh, the 30 mode-array
+ * blocks of write_mode_field (io/diagnostics.F90:497-575,2033-2110: ids exm_real .. jtm_old_imag,
+ * dims (nx_global, ny_global, n_mode), the r-staggered arrays shifted by one row so that file row 1
+ * is the axis) and per species 'grid/<name>' with weight/ px/ py/ pz/<name> (:3040-3160).  Every rank
+ * of an x-slab run calls with the same path and writes its own pieces (pwrite at offsets that follow
+ * from the global sizes); the rank that owns x_min adds the metadata.  The caller supplies what the
+ * reference gets from MPI: npart_global and npart_offset (species_offset) per species.  With
+ * have_extents = 0 the particle-grid extents in the metadata are those of the writing rank. */
+typedef struct {
+  int32_t nx_global, ny_global, n_mode, n_species;
+  int32_t nx_local, cell_x_min;          /* this rank's global cells cell_x_min .. cell_x_min + nx_local - 1 (1-based) */
+  int32_t step, restart, jobid1, jobid2; /* file header: step, restart_flag, jobid (sdf_write_header) */
+  int32_t have_extents, pad_;
+  double time, x_min, dx, dy;            /* xb_global(i) = x_min + (i-1) dx, yb_global(j) = (j-1) dy */
+  const char* species_name[CYLGPU_MAX_SPECIES];
+  int64_t npart_global[CYLGPU_MAX_SPECIES], npart_offset[CYLGPU_MAX_SPECIES], npart_local[CYLGPU_MAX_SPECIES];
+  double part_extents[CYLGPU_MAX_SPECIES][6];   /* min x, y, z then max x, y, z */
+} cylgpu_sdf_desc;
+/* host arrays in, no device needed: fields15[id] = complex(num) (1-ng:nx_local+ng, 1-ng:ny+ng, 0:n_mode-1)
+ * for the 15 field ids above, particles_aos[s] = npart_local[s] records of 7 doubles */
+int cylgpu_sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
+                          const double* const* particles_aos);
+/* the inverse for this rank's slab: interior of the 15 arrays (ghosts untouched; the shift undone as in
+ * housekeeping/setup.F90:1199-1210) and the particles with x_lo <= x < x_hi; fills step, time,
+ * npart_global and npart_local; particles_aos may be NULL (counts only), else capacity[s] records each */
+int cylgpu_sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, double x_lo, double x_hi,
+                         double* const* particles_aos, const int64_t* capacity);
+/* the same between the file and the device-resident state.  dump: npart_local is taken from the
+ * device lists; on one rank npart_global / npart_offset / extents are filled in too.  load: ghosts
+ * are zeroed, the caller re-derives them (cylgpu_efield_bcs, cylgpu_bfield_bcs, cylgpu_current_finish
+ * as the restart of the reference does through its boundary routines) */
+int cylgpu_sdf_dump(cylgpu_handle h, const char* path, cylgpu_sdf_desc* d);
+int cylgpu_sdf_load(cylgpu_handle h, const char* path, cylgpu_sdf_desc* d);
+
 /* diagnostics the new code must own: field + kinetic energy from the
  * mode arrays with cylindrical volume elements; out[0] = field J, out[1] = kinetic J */
 int cylgpu_energy(cylgpu_handle h, double* out2);

@@ -1,0 +1,206 @@
+"""SDF dump / restart of the hot-path state (csrc/sdf_io.cu), CPU only.
+
+The writer is checked THROUGH THE REFERENCE'S OWN SDF READER: oracle/sdf_ref/Makefile compiles the
+reference's SDF C library and its sdf2ascii utility from /root/reference where they lie (into
+oracle/_ref/, test infrastructure), and oracle/sdf_ref/sdf_ref_dump.c exports what that reader
+parsed.  So this row of SURVEY.md section 8 is pinned by reference code run here, not only by
+our own restatement.  (The host-level entry points work on host arrays: no GPU involved.)
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import decks
+from cylindrical_epoch_b200 import _lib
+from cylindrical_epoch_b200.constants import FIELD_NAMES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+NG = 5
+
+# io/diagnostics.F90:497-575: block order, names, units; stagger codes constants.F90:291-299 / sdf_common.f90:184-195
+GROUPS = [("Electric Field Modes", "V/m", [("exm", 2), ("erm", 1), ("etm", 3)]),
+          ("Magnetic Field Modes", "T", [("bxm", 1), ("brm", 2), ("btm", 4)]),
+          ("Magnetic Field Modes", "T", [("bxm_old", 1), ("brm_old", 2), ("btm_old", 4)]),
+          ("Current Modes", "A/m^2", [("jxm", 2), ("jrm", 1), ("jtm", 3)]),
+          ("Current Modes", "A/m^2", [("jxm_old", 2), ("jrm_old", 1), ("jtm_old", 3)])]
+NAMES = [b"electron", b"proton"]
+
+
+def ref_tools():
+    """oracle/_ref/{sdf_ref_dump,sdf2ascii}: built from the reference tree when it is present"""
+    exe = os.path.join(REF_DIR, "sdf_ref_dump")
+    if not os.path.exists(exe) and os.path.isdir("/root/reference/SDF/C/src"):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "sdf_ref"), "-s"])
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref not built and /root/reference absent")
+    return exe, os.path.join(REF_DIR, "sdf2ascii")
+
+
+def make_desc(w, d, k, nranks, counts, offsets, totals, step=7):
+    sc, info = w.scalars(), w.rank_info(k)
+    desc = _lib.SdfDesc()
+    desc.nx_global, desc.ny_global, desc.n_mode, desc.n_species = d.nx, d.ny, d.n_mode, len(d.species)
+    desc.nx_local, desc.cell_x_min = info["nx"], info["cell_x_min"]
+    desc.step, desc.time, desc.restart, desc.jobid1, desc.jobid2 = step, sc["time"], 1, 1234, 56
+    desc.x_min, desc.dx, desc.dy = sc["xb_min"], sc["dx"], sc["dy"]
+    for i in range(len(d.species)):
+        desc.species_name[i] = NAMES[i]
+        desc.npart_local[i], desc.npart_offset[i], desc.npart_global[i] = counts[i], offsets[i], totals[i]
+    return desc
+
+
+def write_world(w, d, path, order=None):
+    nr = w.nranks
+    nsp = len(d.species)
+    lib = _lib.load()
+    counts = [[w.nparticles(k, i) for i in range(nsp)] for k in range(nr)]
+    totals = [sum(counts[k][i] for k in range(nr)) for i in range(nsp)]
+    state = []
+    for k in (order or range(nr)):
+        offsets = [sum(counts[q][i] for q in range(k)) for i in range(nsp)]
+        desc = make_desc(w, d, k, nr, counts[k], offsets, totals)
+        fields = [np.ascontiguousarray(w.field(k, n)) for n in FIELD_NAMES]
+        parts = [np.ascontiguousarray(w.particles(k, i).reshape(-1, 7)) for i in range(nsp)]
+        fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
+        pp = (C.c_void_p * 8)(*([p.ctypes.data for p in parts] + [None] * (8 - nsp)))
+        rc = lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp)
+        assert rc == 0, lib.cylgpu_last_error()
+        state.append((k, fields, parts))
+    return sorted(state, key=lambda t: t[0])
+
+
+def parse_ref(exe, path, outdir):
+    os.makedirs(outdir, exist_ok=True)
+    r = subprocess.run([exe, path, outdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    hdr = dict(t.split("=", 1) for t in lines[0].split()[1:])
+    blocks = []
+    for ln in lines[1:]:
+        # name= may contain blanks: split on the known keys
+        keys = ["n", "id", "name", "blocktype", "datatype", "ndims", "dims", "units", "mesh", "stagger", "species",
+                "geometry", "extents", "labels"]
+        pos = [(ln.find(" " + k + "="), k) for k in keys if (" " + k + "=") in ln]
+        pos.sort()
+        b = {}
+        for (p, k), nxt in zip(pos, pos[1:] + [(len(ln), None)]):
+            b[k] = ln[p + len(k) + 2:nxt[0]]
+        blocks.append(b)
+    return hdr, blocks
+
+
+def global_mode_array(state, d, name, part, shift):
+    """what the file must hold for one block: (n_mode, ny, nx_global), row j <- array row j - shift"""
+    cols = []
+    for _, fields, _ in state:
+        a = fields[FIELD_NAMES.index(name)]
+        a = a.real if part == 0 else a.imag
+        cols.append(a[:, NG - shift:NG - shift + d.ny, NG:-NG])
+    return np.concatenate(cols, axis=2)
+
+
+@pytest.mark.parametrize("nranks,order", [(1, None), (2, [1, 0]), (3, [2, 0, 1])])
+def test_dump_is_read_back_by_the_reference_reader(tmp_path, nranks, order, cylgpu_lib):
+    exe, ascii_exe = ref_tools()
+    d = decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=3, ppc_p=1)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    w.step(5)
+    path = str(tmp_path / "0007.sdf")
+    state = write_world(w, d, path, order)
+    hdr, blocks = parse_ref(exe, path, str(tmp_path / "out"))
+    assert hdr["step"] == "7" and hdr["code"] == "Epoch2d" and hdr["version"] == "1.4" and hdr["restart"] == "1"
+    assert float(hdr["time"]) == w.scalars()["time"]
+    assert int(hdr["nblocks"]) == len(blocks) == 1 + 30 + 2 + 8
+
+    def data(n, sub=None):
+        f = os.path.join(str(tmp_path / "out"), f"{n}.bin" if sub is None else f"{n}.{sub}.bin")
+        return np.fromfile(f, dtype=np.float64)
+
+    sc = w.scalars()
+    g = blocks[0]
+    assert (g["id"], g["name"], g["blocktype"], g["ndims"], g["labels"]) == ("grid", "Grid/Grid", "1", "2", "X,Y")
+    assert np.array_equal(data(0, 0), sc["xb_min"] + np.arange(d.nx + 1) * sc["dx"])
+    assert np.array_equal(data(0, 1), np.arange(d.ny + 1) * sc["dy"])
+    n = 1
+    for group, units, comps in GROUPS:
+        for part, tag in enumerate(("real", "imag")):
+            for stem, stagger in comps:
+                b = blocks[n]
+                assert b["id"] == f"{stem}_{tag}"
+                assert b["name"] == f"{group}/{stem.capitalize()}/{tag}"
+                assert (b["blocktype"], b["datatype"], b["ndims"]) == ("3", "4", "3")
+                assert b["dims"] == f"{d.nx},{d.ny},{d.n_mode}" and b["units"] == units and b["mesh"] == "mode_grid"
+                assert int(b["stagger"]) == stagger
+                shift = 1 if stagger in (2, 3) else 0      # io/diagnostics.F90:2085-2097
+                want = global_mode_array(state, d, stem, part, shift)
+                got = data(n).reshape(d.n_mode, d.ny, d.nx)
+                assert np.array_equal(got, want), b["id"]
+                n += 1
+    allp = [np.concatenate([st[2][i] for st in state]) for i in range(2)]
+    for i, nm in enumerate(("electron", "proton")):
+        b = blocks[n]
+        assert (b["id"], b["name"], b["blocktype"], b["species"]) == (f"grid/{nm}", f"Grid/Particles/{nm}", "2", nm)
+        for c in range(3):
+            assert np.array_equal(data(n, c), allp[i][:, c])
+        n += 1
+    for var, units, col in (("Weight", "", 6), ("Px", "kg.m/s", 3), ("Py", "kg.m/s", 4), ("Pz", "kg.m/s", 5)):
+        for i, nm in enumerate(("electron", "proton")):
+            b = blocks[n]
+            assert b["id"] == f"{var.lower()}/{nm}" and b["name"] == f"Particles/{var}/{nm}"
+            assert (b["blocktype"], b["units"], b["mesh"], b["species"]) == ("4", units, f"grid/{nm}", nm)
+            assert np.array_equal(data(n), allp[i][:, col])
+            n += 1
+    # the reference's own utility walks the file without complaint and lists every block
+    r = subprocess.run([ascii_exe, "-c", "-v", "exm_real", path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "exm_real" in r.stdout
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_read_host_round_trip(tmp_path, nranks, cylgpu_lib):
+    d = decks.thermal(nx=24, ny=12, n_mode=2, ppc=4)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    w.step(3)
+    path = str(tmp_path / "r.sdf")
+    lib = _lib.load()
+    state = write_world(w, d, path)
+    for k, fields, parts in state:
+        info = w.rank_info(k)
+        desc = make_desc(w, d, k, nranks, [0], [0], [0], step=0)
+        desc.time = 0.0
+        out = [np.full_like(f, 7.0 + 1.0j) for f in fields]          # ghosts must stay untouched
+        fp = (C.c_void_p * 15)(*[a.ctypes.data for a in out])
+        cap = (C.c_int64 * 8)(*([parts[0].shape[0] + 10] + [0] * 7))
+        pbuf = np.zeros((parts[0].shape[0] + 10, 7))
+        pp = (C.c_void_p * 8)(*([pbuf.ctypes.data] + [None] * 7))
+        rc = lib.cylgpu_sdf_read_host(path.encode(), C.byref(desc), fp, info["x_min_local"], info["x_max_local"], pp, cap)
+        assert rc == 0, lib.cylgpu_last_error()
+        assert desc.step == 7 and desc.time == w.scalars()["time"]
+        assert desc.npart_local[0] == parts[0].shape[0]
+        assert desc.npart_global[0] == sum(s[2][0].shape[0] for s in state)
+        # same particles (file order within a slab is the list order)
+        assert np.array_equal(pbuf[:parts[0].shape[0]], parts[0])
+        for name, f, o in zip(FIELD_NAMES, fields, out):
+            stag = dict(exm=1, etm=1, brm=1, jxm=1, jtm=1).get(name.replace("_old", ""), 0)
+            rows = slice(NG - stag, NG - stag + d.ny)
+            assert np.array_equal(o[:, rows, NG:-NG], f[:, rows, NG:-NG]), name
+            mask = np.ones(o.shape, dtype=bool)
+            mask[:, rows, NG:-NG] = False
+            assert np.all(o[mask] == 7.0 + 1.0j), name
+
+
+def test_bad_descriptors_fail_loudly(tmp_path, cylgpu_lib):
+    lib = _lib.load()
+    desc = _lib.SdfDesc()
+    fp = (C.c_void_p * 15)()
+    pp = (C.c_void_p * 8)()
+    assert lib.cylgpu_sdf_write_host(str(tmp_path / "x.sdf").encode(), C.byref(desc), fp, pp) != 0
+    assert b"descriptor" in lib.cylgpu_last_error()
+    assert lib.cylgpu_sdf_read_host(b"/nonexistent/file.sdf", C.byref(desc), fp, 0.0, 1.0, None, None) != 0
+    assert b"cannot open" in lib.cylgpu_last_error()
