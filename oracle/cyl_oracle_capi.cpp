@@ -156,7 +156,7 @@ enum Op {
   OP_MOVING_WINDOW = 5, OP_INIT_HALF_STEP = 6, OP_PARTICLE_BCS = 7, OP_EFIELD_BCS = 8,
   OP_BFIELD_BCS_MPI = 9, OP_BFIELD_FINAL_BCS = 10, OP_UPDATE_E = 11, OP_UPDATE_B = 12,
   OP_SNAPSHOT_BOUNDARIES = 13, OP_ADVANCE_HALF_TIME = 14, OP_PUSH_NO_BCS = 15, OP_CURRENT_BCS = 16,
-  OP_FLUSH_RNG = 17
+  OP_FLUSH_RNG = 17, OP_BFIELD_BCS = 18
 };
 
 // returns elapsed seconds of the call
@@ -181,6 +181,7 @@ double cylo_call(void* wp, int op) {
     case OP_ADVANCE_HALF_TIME: w->time = w->time + w->dt / 2.0; break;
     case OP_PUSH_NO_BCS: for (Rank& r : w->ranks) w->push_rank(r); break;
     case OP_CURRENT_BCS: w->current_bcs(); break;
+    case OP_BFIELD_BCS: w->bfield_bcs(false); break;
     case OP_FLUSH_RNG: for (Rank& r : w->ranks) r.rng.flush_cache(); break;
     default: return -1.0;
   }

@@ -26,7 +26,7 @@ SNAP_NAMES = [f"{n}_x_min" for n in FIELD_NAMES[:6]] + [f"{n}_x_max" for n in FI
 OPS = dict(step=0, fields_half=1, push=2, current_finish=3, fields_final=4, moving_window=5,
            init_half_step=6, particle_bcs=7, efield_bcs=8, bfield_bcs_mpi=9, bfield_final_bcs=10,
            update_e=11, update_b=12, snapshot_boundaries=13, advance_half_time=14, push_no_bcs=15,
-           current_bcs=16, flush_rng=17)
+           current_bcs=16, flush_rng=17, bfield_bcs=18)
 
 # calc_df.F90 moments (cyl_moments.cpp / include/cylgpu.h CYLGPU_MOM_*)
 MOMENTS = dict(mass_density=0, number_density=1, ekbar=2, ekflux=3, ppc=4, average_weight=5, temperature=6,
