@@ -244,3 +244,39 @@ def test_restart_through_the_file_continues_exactly_in_a_conducting_box(tmp_path
         for name in FIELD_NAMES[:9]:
             assert np.array_equal(a.field(k, name), b.field(k, name)), name
         assert np.array_equal(a.particles(k, 0), b.particles(k, 0))
+
+
+def test_reference_dump_bridge_self_check(tmp_path, cylgpu_lib):
+    """tools/check_against_reference_dumps.py is the one-command way to pin the oracle against dumps of the
+    real reference (which cannot be built here).  Self-check with two dumps of the oracle itself: the tool
+    must load A, advance to B's step and report agreement to rounding in a conducting box."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import check_against_reference_dumps as bridge
+    d = decks.drift(nx=36, ny=12, n_mode=2)
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(2)
+    a, b = str(tmp_path / "a.sdf"), str(tmp_path / "b.sdf")
+
+    def dump(path, step):
+        st = write_world(w, d, path)
+        # write_world stamps step 7; restamp through the descriptor of a second write
+        lib = _lib.load()
+        k, fields, parts = st[0]
+        desc = make_desc(w, d, 0, 1, [parts[0].shape[0]], [0], [parts[0].shape[0]], step=step)
+        fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
+        pp = (C.c_void_p * 8)(*([parts[0].ctypes.data] + [None] * 7))
+        assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp) == 0
+
+    dump(a, 2)
+    w.step(5)
+    dump(b, 7)
+    sp = d.species[0]
+    deck = dict(nx=d.nx, ny=d.ny, n_mode=d.n_mode, x_min=d.x_min, x_max=d.x_max, y_max=d.y_max,
+                bc_field=list(d.bc_field), dt_multiplier=d.dt_multiplier, nranks=1,
+                species=[dict(name="electron", charge=sp.charge, mass=sp.mass, bc_particle=list(sp.bc_particle))])
+    deck_path = str(tmp_path / "deck.json")
+    json.dump(deck, open(deck_path, "w"))
+    assert bridge.main([deck_path, a, b, "--tol", "1e-12"]) == 0
