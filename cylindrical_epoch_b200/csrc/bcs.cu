@@ -75,69 +75,7 @@ static void launch_edge(cylgpu_ctx* c, const Tri& t, int bd) {
   c->stats.kernel_launches += 1;
 }
 
-// ---- x halo: boundary.F90:158-169,500-553.  Buffer layout [comp][im][row][NG]. ----
-struct Halo3 {
-  cplx* f[3];
-  int skip[3];   // rows excluded at the top (the one-row shift of the r-staggered arrays,
-                 // boundary.F90:1362-1371,1428-1430: row ny+ng never takes part)
-};
-
-// mode 0: pack interior edge columns (send_l <- 1..ng, send_r <- nx+1-ng..nx)
-// mode 1: pack ghost columns          (send_l <- 1-ng..0, send_r <- nx+1..nx+ng)  [J sums]
-// mode 2: both, ghost block first then interior block (`half` elements apart)  [J sum + J halo in one message]
-__global__ void __launch_bounds__(128) k_halo_pack(Geom g, Halo3 h, cplx* __restrict__ send_l,
-                                                   cplx* __restrict__ send_r, int mode, size_t half) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = g.SY * NG;
-  if (t >= per) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  const int row = t / NG, i = t % NG + 1;   // i = 1..ng
-  const int j = row + 1 - NG;
-  if (j > g.ny + NG - h.skip[k]) return;
-  const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
-  const cplx* f = h.f[k];
-  if (!f) return;   // exchanges of fewer than three arrays
-  if (mode == 0) {
-    if (send_l) send_l[b] = f[g.at(i, j, im)];
-    if (send_r) send_r[b] = f[g.at(g.nx - NG + i, j, im)];
-  } else {
-    if (send_l) send_l[b] = f[g.at(i - NG, j, im)];
-    if (send_r) send_r[b] = f[g.at(g.nx + i, j, im)];
-    if (mode == 2) {
-      if (send_l) send_l[half + b] = f[g.at(i, j, im)];
-      if (send_r) send_r[half + b] = f[g.at(g.nx - NG + i, j, im)];
-    }
-  }
-}
-
-// mode 0: ghost <- received (recv_l -> 1-ng..0, recv_r -> nx+1..nx+ng)
-// mode 1: interior += received (recv_l -> 1..ng, recv_r -> nx+1-ng..nx), boundary.F90:1192,1200
-// mode 2: mode 1, and ghost <- the neighbour's interior edge AFTER its own sum, which is its
-//         interior block + my ghost value (the very two operands the neighbour adds)
-__global__ void __launch_bounds__(128) k_halo_unpack(Geom g, Halo3 h, const cplx* __restrict__ recv_l,
-                                                     const cplx* __restrict__ recv_r, int mode, size_t half) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int per = g.SY * NG;
-  if (t >= per) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  const int row = t / NG, i = t % NG + 1;
-  const int j = row + 1 - NG;
-  if (j > g.ny + NG - h.skip[k]) return;
-  const size_t b = ((size_t)(k * g.M + im) * g.SY + row) * NG + (i - 1);
-  cplx* f = h.f[k];
-  if (!f) return;
-  if (mode == 0) {
-    if (recv_l) f[g.at(i - NG, j, im)] = recv_l[b];
-    if (recv_r) f[g.at(g.nx + i, j, im)] = recv_r[b];
-  } else {
-    if (recv_l) { const size_t o = g.at(i, j, im); f[o] = f[o] + recv_l[b]; }
-    if (recv_r) { const size_t o = g.at(g.nx - NG + i, j, im); f[o] = f[o] + recv_r[b]; }
-    if (mode == 2) {
-      if (recv_l) { const size_t o = g.at(i - NG, j, im); f[o] = recv_l[half + b] + f[o]; }
-      if (recv_r) { const size_t o = g.at(g.nx + i, j, im); f[o] = recv_r[half + b] + f[o]; }
-    }
-  }
-}
+#include "bc_kernels.cuh"
 
 // `gg`: geometry of the arrays when it is not the handle's (the single-plane work arrays of the
 // particle moments, moments.cuh); the staging buffers are sized for the handle's n_mode >= 1.
@@ -753,64 +691,6 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
         if (im > 0) atomicAdd(out + o + 1, v * mode_fac.y);
       }
   }
-}
-
-// particle_reflection_bcs, the real-valued variant (boundary.F90:833-914, flip_direction absent):
-// bd 0 x_min (ng-1 ghost columns fold onto 1..ng-1), 1 x_max, 3 r_max (ng ghosts each)
-__global__ void __launch_bounds__(128) k_density_reflect(Geom g, cplx* __restrict__ a, int bd) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int im = blockIdx.y;
-  if (bd == CYLGPU_BD_Y_MAX) {
-    if (t >= g.SX) return;
-    const int ix = t + 1 - NG;
-    for (int i = 1; i <= NG; ++i) {
-      const size_t in = g.at(ix, g.ny + 1 - i, im), gh = g.at(ix, g.ny + i, im);
-      a[in] = a[in] + a[gh];
-      a[gh] = C(0.0, 0.0);
-    }
-    return;
-  }
-  if (t >= g.SY) return;
-  const int j = t + 1 - NG;
-  if (bd == CYLGPU_BD_X_MIN) {
-    for (int i = 1; i <= NG - 1; ++i) {
-      const size_t in = g.at(i, j, im), gh = g.at(1 - i, j, im);
-      a[in] = a[in] + a[gh];
-      a[gh] = C(0.0, 0.0);
-    }
-  } else {
-    for (int i = 1; i <= NG; ++i) {
-      const size_t in = g.at(g.nx + 1 - i, j, im), gh = g.at(g.nx + i, j, im);
-      a[in] = a[in] + a[gh];
-      a[gh] = C(0.0, 0.0);
-    }
-  }
-}
-
-// field_mode_zero_gradient for a cell-centred array (boundary.F90:654-707): ghost i <- interior mirror
-__global__ void __launch_bounds__(128) k_density_zero_gradient(Geom g, cplx* __restrict__ a, int bd) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const int im = blockIdx.y;
-  if (bd == CYLGPU_BD_X_MIN || bd == CYLGPU_BD_X_MAX) {
-    if (t >= g.SY) return;
-    const int j = t + 1 - NG;
-    for (int i = 1; i <= NG; ++i) {
-      if (bd == CYLGPU_BD_X_MIN) a[g.at(i - NG, j, im)] = a[g.at(NG + 1 - i, j, im)];
-      else a[g.at(g.nx + i, j, im)] = a[g.at(g.nx + 1 - i, j, im)];
-    }
-  } else {
-    if (t >= g.SX) return;
-    const int ix = t + 1 - NG;
-    for (int i = 1; i <= NG; ++i) {
-      if (bd == CYLGPU_BD_Y_MIN) a[g.at(ix, i - NG, im)] = a[g.at(ix, NG + 1 - i, im)];
-      else a[g.at(ix, g.ny + i, im)] = a[g.at(ix, g.ny + 1 - i, im)];
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) k_real_part(const cplx* __restrict__ a, double* __restrict__ out, size_t n) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[i].x;
 }
 
 // species < 0: sum over the species that carry current (calc_df.F90:606-616).  Result in c->spare.

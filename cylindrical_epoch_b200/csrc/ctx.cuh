@@ -9,17 +9,9 @@
 
 #include "../../include/cylgpu.h"
 
-#define NG 5     // constants.F90:544
-#define JNG 5    // constants.F90:545
-#define PNG 3    // constants.F90:537
-#define CELL_PAD 3   // ghost cells on each side covered by the particle sort buckets
+#include "geom.cuh"
 
 namespace cylgpu {
-
-// physical constants, constants.F90:171-201
-constexpr double PI = 3.141592653589793238462643383279503;
-constexpr double C_LIGHT = 2.99792458e8;
-constexpr double EPSILON0 = 8.854187817620389850536563031710750e-12;
 
 void set_error(const char* fmt, ...);
 
@@ -38,32 +30,6 @@ void set_error(const char* fmt, ...);
     int _r = (expr);              \
     if (_r != 0) return _r;       \
   } while (0)
-
-// ---- complex helpers on double2 (x = re, y = im) ----
-typedef double2 cplx;
-__host__ __device__ __forceinline__ cplx C(double re, double im) { return make_double2(re, im); }
-__host__ __device__ __forceinline__ cplx operator+(cplx a, cplx b) { return C(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ cplx operator-(cplx a, cplx b) { return C(a.x - b.x, a.y - b.y); }
-__host__ __device__ __forceinline__ cplx operator-(cplx a) { return C(-a.x, -a.y); }
-__host__ __device__ __forceinline__ cplx operator*(cplx a, cplx b) {
-  return C(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-__host__ __device__ __forceinline__ cplx operator*(double s, cplx a) { return C(s * a.x, s * a.y); }
-__host__ __device__ __forceinline__ cplx operator*(cplx a, double s) { return C(a.x * s, a.y * s); }
-__host__ __device__ __forceinline__ cplx operator/(cplx a, double s) { return C(a.x / s, a.y / s); }
-__host__ __device__ __forceinline__ cplx& operator+=(cplx& a, cplx b) { a.x += b.x; a.y += b.y; return a; }
-// i * a
-__host__ __device__ __forceinline__ cplx mul_i(cplx a) { return C(-a.y, a.x); }
-
-// geometry of the mode arrays: (ix, ir, im) with bounds (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1)
-struct Geom {
-  int nx, ny, M;
-  int SX, SY;          // nx + 2ng, ny + 2ng
-  size_t plane;        // SX * SY
-  __host__ __device__ __forceinline__ size_t at(int ix, int ir, int im) const {
-    return ((size_t)im * SY + (size_t)(ir + NG - 1)) * SX + (size_t)(ix + NG - 1);
-  }
-};
 
 struct Transport;   // transport.cu
 

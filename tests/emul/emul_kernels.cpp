@@ -1,0 +1,184 @@
+// emul_kernels.cpp -- TEST INFRASTRUCTURE: runs the product's kernel SOURCES (the very headers nvcc
+// compiles into libcylgpu.so) on the CPU through cuda_emul.hpp, with the launch sequences of
+// csrc/moments.cuh::do_particle_moment and csrc/window_insert.cu::do_insert_particles_device
+// restated for one slab.  tests/test_kernel_emulation.py compares the results with the oracle.
+#include <cstring>
+#include <vector>
+
+#include "cuda_emul.hpp"
+
+#include "../../include/cylgpu.h"
+#include "../../cylindrical_epoch_b200/csrc/geom.cuh"
+#include "../../cylindrical_epoch_b200/csrc/philox.cuh"
+
+namespace cylgpu {
+#include "../../cylindrical_epoch_b200/csrc/bc_kernels.cuh"
+#include "../../cylindrical_epoch_b200/csrc/moments_kernels.cuh"
+#include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
+}  // namespace cylgpu
+
+using namespace cylgpu;
+
+namespace {
+
+struct SlabCfg {
+  Geom g1;
+  int bca[4], bc_field[4];
+  bool periodic_self;   // one slab whose x neighbours are itself (left = right = rank 0)
+};
+
+// exchange3 of bcs.cu for one slab: pack, what goes left arrives from the right and vice versa, unpack
+void exchange_self(const SlabCfg& S, cplx* a0, cplx* a1, int mode) {
+  const Geom& g = S.g1;
+  Halo3 h;
+  h.f[0] = a0; h.f[1] = a1; h.f[2] = nullptr;
+  h.skip[0] = h.skip[1] = h.skip[2] = 0;
+  const size_t elems = (size_t)3 * g.M * g.SY * NG;
+  std::vector<cplx> sl(2 * elems), sr(2 * elems);
+  const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+  emul_launch(k_halo_pack, grd, dim3(128), g, h, sl.data(), sr.data(), mode, elems);
+  emul_launch(k_halo_unpack, grd, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), mode, elems);
+}
+
+void summation_bcs(const SlabCfg& S, cplx* a0, cplx* a1) {   // moments.cuh::moment_summation_bcs
+  const Geom& g1 = S.g1;
+  const dim3 gx_((g1.SY + 127) / 128, 1), gy_((g1.SX + 127) / 128, 1);
+  cplx* arr[2] = {a0, a1};
+  for (int k = 0; k < 2; ++k) {
+    cplx* a = arr[k];
+    if (!a) continue;
+    if (S.bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g1, a, (int)CYLGPU_BD_X_MIN);
+    if (S.bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g1, a, (int)CYLGPU_BD_X_MAX);
+    if (S.bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gy_, dim3(128), g1, a, (int)CYLGPU_BD_Y_MAX);
+  }
+  const bool to_l = S.periodic_self && S.bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  const bool to_r = S.periodic_self && S.bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC;
+  if (to_l && to_r) exchange_self(S, a0, a1, 1);
+}
+
+void zero_gradient(const SlabCfg& S, cplx* a) {   // moments.cuh::moment_zero_gradient
+  const Geom& g1 = S.g1;
+  const dim3 gx_((g1.SY + 127) / 128, 1), gy_((g1.SX + 127) / 128, 1);
+  if (S.bc_field[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gx_, dim3(128), g1, a, (int)CYLGPU_BD_X_MIN);
+  if (S.bc_field[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gx_, dim3(128), g1, a, (int)CYLGPU_BD_X_MAX);
+  if (S.bc_field[CYLGPU_BD_Y_MIN] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g1, a, (int)CYLGPU_BD_Y_MIN);
+  if (S.bc_field[CYLGPU_BD_Y_MAX] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g1, a, (int)CYLGPU_BD_Y_MAX);
+}
+
+}  // namespace
+
+extern "C" {
+
+// One slab (x_min_boundary = x_max_boundary = true).  soa[s]: 7 arrays of n[s] doubles (x y z px py pz w);
+// bca: common particle bc per boundary; out: real (nx+2ng) x (ny+2ng) plane.  Returns 0, or 2 for an
+// unknown moment (the product's error path).
+int emul_particle_moment(int nx, int ny, int kind, int direction, int nsel, const double* const* soa, const int64_t* n,
+                         const double* mass, const double* charge, double x_grid_min_local, double y_grid_min_local,
+                         double dx, double dy, const int32_t* bca, const int32_t* bc_field, double* out) {
+  SlabCfg S;
+  S.g1.nx = nx; S.g1.ny = ny; S.g1.M = 1;
+  S.g1.SX = nx + 2 * NG; S.g1.SY = ny + 2 * NG;
+  S.g1.plane = (size_t)S.g1.SX * S.g1.SY;
+  for (int i = 0; i < 4; ++i) { S.bca[i] = bca[i]; S.bc_field[i] = bc_field[i]; }
+  S.periodic_self = bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  const Geom g1 = S.g1;
+  const size_t np = g1.plane;
+  std::vector<cplx> A(np, C(0.0, 0.0)), B(np, C(0.0, 0.0)), D(np, C(0.0, 0.0));
+  auto for_each_species = [&](auto&& launch) {
+    for (int s = 0; s < nsel; ++s) {
+      if (n[s] == 0) continue;
+      MomentArgs a;
+      a.x = soa[7 * s + 0]; a.y = soa[7 * s + 1]; a.z = soa[7 * s + 2];
+      a.px = soa[7 * s + 3]; a.py = soa[7 * s + 4]; a.pz = soa[7 * s + 5]; a.w = soa[7 * s + 6];
+      a.n = n[s];
+      a.x_grid_min_local = x_grid_min_local; a.y_grid_min_local = y_grid_min_local;
+      a.dx = dx; a.dy = dy;
+      a.mass = mass[s]; a.charge = charge[s];
+      a.kind = kind; a.direction = direction;
+      launch(a, dim3((unsigned)((n[s] + 255) / 256)));
+    }
+  };
+  const dim3 pb((unsigned)((np + 255) / 256));
+  int finish_mode = 0;
+  double dof = 1.0;
+  cplx* result = A.data();
+  if (kind == CYLGPU_MOM_PPC || kind == CYLGPU_MOM_AVERAGE_WEIGHT) {
+    for_each_species([&](const MomentArgs& a, dim3 blocks) { emul_launch(k_moment_count, blocks, dim3(256), g1, a, (double*)A.data()); });
+    finish_mode = kind == CYLGPU_MOM_AVERAGE_WEIGHT ? 1 : 0;
+  } else if (kind == CYLGPU_MOM_TEMPERATURE) {
+    for_each_species([&](const MomentArgs& a, dim3 blocks) {
+      emul_launch(k_temperature_means, blocks, dim3(256), g1, a, (double*)A.data(), (double*)B.data());
+    });
+    summation_bcs(S, A.data(), B.data());
+    emul_launch(k_temperature_normalise, pb, dim3(256), A.data(), B.data(), np);
+    if (S.periodic_self) exchange_self(S, A.data(), B.data(), 0);
+    for_each_species([&](const MomentArgs& a, dim3 blocks) {
+      emul_launch(k_temperature_sigma, blocks, dim3(256), g1, a, (const cplx*)A.data(), (const cplx*)B.data(), (double*)D.data());
+    });
+    summation_bcs(S, D.data(), nullptr);
+    finish_mode = 2;
+    dof = direction > 0 ? 1.0 : 3.0;
+    result = D.data();
+  } else if (kind == CYLGPU_MOM_MASS_DENSITY || kind == CYLGPU_MOM_NUMBER_DENSITY || kind == CYLGPU_MOM_SPECIES_CURRENT ||
+             kind == CYLGPU_MOM_EKBAR || kind == CYLGPU_MOM_EKFLUX || kind == CYLGPU_MOM_AVERAGE_MOMENTUM) {
+    for_each_species([&](const MomentArgs& a, dim3 blocks) { emul_launch(k_moment_deposit, blocks, dim3(256), g1, a, (double*)A.data()); });
+    summation_bcs(S, A.data(), nullptr);
+    zero_gradient(S, A.data());
+    finish_mode = (kind == CYLGPU_MOM_EKBAR || kind == CYLGPU_MOM_EKFLUX || kind == CYLGPU_MOM_AVERAGE_MOMENTUM) ? 1 : 0;
+  } else {
+    return 2;
+  }
+  emul_launch(k_moment_finish, pb, dim3(256), (const cplx*)result, out, np, finish_mode, dof);
+  return 0;
+}
+
+// window_insert.cu::do_insert_particles_device for the x_max slab: returns the number of particles
+// written (7 SoA arrays of capacity cap each), or -1 if cap is too small.
+int64_t emul_insert_column(int ny, int isp, double x_grid_max, double npart_per_cell_real, const double* density_in,
+                           const double* temperature, const double* drift, double dmin, double dmax, uint64_t seed,
+                           uint64_t column, double dx, double dy, double y_grid_min_local, double mass, int64_t cap,
+                           double* const* soa) {
+  const int nrow = ny + 2;
+  const int64_t npart_per_cell = (int64_t)std::floor(npart_per_cell_real);
+  const double npart_frac = npart_per_cell_real - (double)npart_per_cell;
+  const ColumnStream rs = column_stream(seed, isp, column);
+  std::vector<double> stage((size_t)7 * nrow + (size_t)(ny + 1));
+  double* prof = stage.data();
+  int64_t* row_start = reinterpret_cast<int64_t*>(stage.data() + (size_t)7 * nrow);
+  for (int iy = 0; iy < nrow; ++iy) {
+    double d = density_in[iy];
+    if (d > dmax) d = dmax;
+    if (d < dmin) d = 0.0;
+    prof[iy] = d;
+  }
+  for (int i = 0; i < 3 * nrow; ++i) { prof[nrow + i] = temperature[i]; prof[4 * nrow + i] = drift[i]; }
+  int64_t total = 0;
+  row_start[0] = 0;
+  for (int iy = 1; iy <= ny; ++iy) {
+    int64_t ncell = 0;
+    if (!(prof[iy] < dmin)) {
+      int64_t n_frac = 0;
+      if (npart_frac > 0.0 && rs.cell_uniform((uint32_t)iy) < npart_frac) n_frac = 1;
+      ncell = npart_per_cell + n_frac;
+    }
+    total += ncell;
+    row_start[iy] = total;
+  }
+  if (total > cap) return -1;
+  ColumnArgs a;
+  a.rs = rs;
+  a.prof = prof;
+  a.row_start = row_start;
+  a.x = soa[0]; a.y = soa[1]; a.z = soa[2]; a.px = soa[3]; a.py = soa[4]; a.pz = soa[5]; a.w = soa[6];
+  a.base = 0;
+  a.ny = ny;
+  a.iy_global_offset = 0;
+  a.dx = dx; a.dy = dy;
+  a.x0 = x_grid_max + 0.5 * dx;
+  a.y_grid_min_local = y_grid_min_local;
+  a.mass = mass;
+  emul_launch(k_insert_column, dim3((unsigned)ny), dim3(128), a);
+  return total;
+}
+
+}  // extern "C"

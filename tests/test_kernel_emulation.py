@@ -1,0 +1,120 @@
+"""The product's barrier-free CUDA kernels, compiled from the SAME header files nvcc uses
+(csrc/moments_kernels.cuh, bc_kernels.cuh, insert_kernel.cuh, philox.cuh), run thread by thread on the
+CPU through the emulation shim of tests/emul/ and compared with the oracle.
+
+Why: the container these kernels were written in has no GPU and the round's GPU budget was spent,
+so this is the check of their arithmetic and indexing that could be made before their first run on
+a B200 (tests/test_zz_gpu_*.py are the parity tests proper, through the C-ABI).  It is test
+infrastructure, not a CPU path of the product: nothing under cylindrical_epoch_b200/ uses it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import decks
+import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = [("mass_density", 0), ("number_density", 0), ("ekbar", 0), ("ekflux", 1), ("ekflux", -2), ("ekflux", 3),
+         ("ppc", 0), ("average_weight", 0), ("temperature", 0), ("temperature", 2), ("species_current", 1),
+         ("species_current", 3), ("average_momentum", 2)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s"])
+    L = C.CDLL(os.path.join(HERE, "emul", "libemul_kernels.so"))
+    L.emul_particle_moment.restype = C.c_int
+    L.emul_particle_moment.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.c_double, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_int32),
+                                       C.POINTER(C.c_int32), C.c_void_p]
+    L.emul_insert_column.restype = C.c_int64
+    L.emul_insert_column.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_double, C.c_double,
+                                     C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_void_p)]
+    return L
+
+
+def emul_moment(L, w, d, kind, species, direction):
+    sc, info = w.scalars(), w.rank_info(0)
+    sel = [i for i in range(len(d.species)) if (species < 0 and not d.species[i].zero_current) or i == species]
+    soa = []
+    for i in sel:
+        p = w.particles(0, i).reshape(-1, 7)
+        soa += [np.ascontiguousarray(p[:, c]) for c in range(7)]
+    ptrs = (C.c_void_p * len(soa))(*[a.ctypes.data for a in soa])
+    n = (C.c_int64 * len(sel))(*[w.nparticles(0, i) for i in sel])
+    mass = (C.c_double * len(sel))(*[d.species[i].mass for i in sel])
+    charge = (C.c_double * len(sel))(*[d.species[i].charge for i in sel])
+    bca = (C.c_int32 * 4)(*w.bc_particle(0))
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    out = np.zeros((info["ny"] + 2 * po.NG, info["nx"] + 2 * po.NG))
+    rc = L.emul_particle_moment(info["nx"], info["ny"], po.MOMENTS[kind], direction, len(sel), ptrs, n, mass, charge,
+                                info["x_grid_min_local"], sc["y_grid_min_local"], sc["dx"], sc["dy"], bca, bcf,
+                                out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+@pytest.mark.parametrize("deck_name", ["thermal", "drift", "lwfa"])
+def test_moment_kernels_match_the_oracle(emul, deck_name):
+    d = {"thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=6),
+         "drift": lambda: decks.drift(nx=20, ny=10, n_mode=2),
+         "lwfa": lambda: decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=2)}[deck_name]()
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(3)
+    for kind, direction in CASES:
+        for species in [-1] + list(range(len(d.species))):
+            want = w.moment(kind, species, direction)[0]
+            got = emul_moment(emul, w, d, kind, species, direction)
+            scale = np.abs(want).max()
+            assert scale > 0
+            if kind == "ppc":
+                assert np.array_equal(got, want)
+            else:
+                # same operation order particle by particle (the emulation visits them in list order): rounding only
+                assert np.abs(got - want).max() <= 1e-13 * scale, (deck_name, kind, direction, species)
+
+
+def test_unknown_moment_is_refused(emul):
+    out = np.zeros((10 + 10, 20 + 10))
+    z = (C.c_int32 * 4)(9, 9, 5, 9)
+    assert emul.emul_particle_moment(20, 10, 99, 0, 0, None, None, None, None, 0.0, 0.0, 1.0, 1.0, z, z,
+                                     out.ctypes.data) == 2
+
+
+@pytest.mark.parametrize("ppc", [8, 2.5])
+def test_insert_column_kernel_matches_the_oracle_column(emul, ppc):
+    """k_insert_column (one thread per particle, Philox counters) against oracle/cyl_philox.cpp: same libm
+    on the CPU, so every component is bit-identical -- stream layout, counts, offsets and arithmetic"""
+    seed, column = 0x123456789ABC, 7
+    d = decks.lwfa(nx=32, ny=16, n_mode=1, ppc_e=ppc, ppc_p=0, window=True)
+    d.species[0].temp = (2.0e5, 1.0e5, 3.0e5)
+    d.species[0].drift = (1.0e-24, -2.0e-24, 0.5e-24)
+    w = decks.make_oracle(d)
+    w.set_counter_insert(True, seed)
+    w.set_particles(0, 0, np.zeros((0, 7)))
+    w.L.cylo_insert_column.restype = None
+    w.L.cylo_insert_column.argtypes = [C.c_void_p, C.c_uint64]
+    w.L.cylo_insert_column(w.h, column)
+    ref = w.particles(0, 0).reshape(-1, 7)
+    sc = w.scalars()
+    sp = d.species[0]
+    nrow = d.ny + 2
+    dens = np.full(nrow, float(sp.density))
+    temp = np.repeat(np.asarray(sp.temp, dtype=np.float64), nrow)
+    drift = np.repeat(np.asarray(sp.drift, dtype=np.float64), nrow)
+    cap = ref.shape[0] + 16
+    soa = [np.zeros(cap) for _ in range(7)]
+    ptrs = (C.c_void_p * 7)(*[a.ctypes.data for a in soa])
+    x_grid_max = sc["x_grid_min"] + (d.nx - 1) * sc["dx"]
+    n = emul.emul_insert_column(d.ny, 0, x_grid_max, float(ppc), dens.ctypes.data, temp.ctypes.data, drift.ctypes.data,
+                                0.0, 1e300, seed, column, sc["dx"], sc["dy"], sc["y_grid_min_local"], sp.mass, cap, ptrs)
+    assert n == ref.shape[0] and n > 0
+    got = np.stack([a[:n] for a in soa], axis=1)
+    assert np.array_equal(got, ref)
