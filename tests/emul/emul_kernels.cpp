@@ -67,12 +67,14 @@ void zero_gradient(const SlabCfg& S, cplx* a) {   // moments.cuh::moment_zero_gr
 
 }  // namespace
 
+#define EMUL_API __attribute__((visibility("default")))
+
 extern "C" {
 
 // One slab (x_min_boundary = x_max_boundary = true).  soa[s]: 7 arrays of n[s] doubles (x y z px py pz w);
 // bca: common particle bc per boundary; out: real (nx+2ng) x (ny+2ng) plane.  Returns 0, or 2 for an
 // unknown moment (the product's error path).
-int emul_particle_moment(int nx, int ny, int kind, int direction, int nsel, const double* const* soa, const int64_t* n,
+EMUL_API int emul_particle_moment(int nx, int ny, int kind, int direction, int nsel, const double* const* soa, const int64_t* n,
                          const double* mass, const double* charge, double x_grid_min_local, double y_grid_min_local,
                          double dx, double dy, const int32_t* bca, const int32_t* bc_field, double* out) {
   SlabCfg S;
@@ -134,7 +136,7 @@ int emul_particle_moment(int nx, int ny, int kind, int direction, int nsel, cons
 
 // window_insert.cu::do_insert_particles_device for the x_max slab: returns the number of particles
 // written (7 SoA arrays of capacity cap each), or -1 if cap is too small.
-int64_t emul_insert_column(int ny, int isp, double x_grid_max, double npart_per_cell_real, const double* density_in,
+EMUL_API int64_t emul_insert_column(int ny, int isp, double x_grid_max, double npart_per_cell_real, const double* density_in,
                            const double* temperature, const double* drift, double dmin, double dmax, uint64_t seed,
                            uint64_t column, double dx, double dy, double y_grid_min_local, double mass, int64_t cap,
                            double* const* soa) {
