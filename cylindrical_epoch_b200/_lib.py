@@ -44,7 +44,8 @@ class SdfDesc(C.Structure):   # cylgpu_sdf_desc
     _fields_ = [("nx_global", C.c_int32), ("ny_global", C.c_int32), ("n_mode", C.c_int32), ("n_species", C.c_int32),
                 ("nx_local", C.c_int32), ("cell_x_min", C.c_int32),
                 ("step", C.c_int32), ("restart", C.c_int32), ("jobid1", C.c_int32), ("jobid2", C.c_int32),
-                ("have_extents", C.c_int32), ("pad_", C.c_int32),
+                ("have_extents", C.c_int32), ("derived_mask", C.c_uint32), ("derived_sum", C.c_int32),
+                ("derived_species", C.c_int32),
                 ("time", C.c_double), ("x_min", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
                 ("species_name", C.c_char_p * MAX_SPECIES),
                 ("npart_global", C.c_int64 * MAX_SPECIES), ("npart_offset", C.c_int64 * MAX_SPECIES),
@@ -113,7 +114,9 @@ SYMBOLS = {
                                                  C.c_double, C.c_double, C.c_uint64, C.c_uint64,
                                                  C.POINTER(C.c_int64)]),
     "cylgpu_philox4x32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "cylgpu_sdf_write_host": (C.c_int, [C.c_char_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "cylgpu_sdf_write_host": (C.c_int, [C.c_char_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p)]),
+    "cylgpu_sdf_derived_count": (C.c_int, [C.POINTER(SdfDesc)]),
     "cylgpu_sdf_read_host": (C.c_int, [C.c_char_p, C.POINTER(SdfDesc), C.POINTER(C.c_void_p), C.c_double, C.c_double,
                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "cylgpu_sdf_dump": (C.c_int, [H, C.c_char_p, C.POINTER(SdfDesc)]),

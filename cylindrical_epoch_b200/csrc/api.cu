@@ -551,9 +551,10 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
 
 // ---- SDF dump / restart (sdf_io.cu) ----
 int cylgpu_sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
-                          const double* const* particles_aos) {
-  return sdf_write_host(path, d, fields15, particles_aos);
+                          const double* const* particles_aos, const double* const* derived) {
+  return sdf_write_host(path, d, fields15, particles_aos, derived);
 }
+int cylgpu_sdf_derived_count(const cylgpu_sdf_desc* d) { return d ? sdf_derived_count(d) : 0; }
 int cylgpu_sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, double x_lo, double x_hi,
                          double* const* particles_aos, const int64_t* capacity) {
   std::vector<std::vector<double>> parts;
@@ -606,7 +607,31 @@ int cylgpu_sdf_dump(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
     }
   }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  return sdf_write_host(path, d, fptr, pptr);
+  // derived variables straight from the device lists (moments.cuh); table order of sdf_io.cu / cylgpu.h
+  static const int kind_of[CYLGPU_SDF_NDERIVED] = {
+      CYLGPU_MOM_EKBAR, CYLGPU_MOM_MASS_DENSITY, -1 /* charge density */, CYLGPU_MOM_NUMBER_DENSITY, CYLGPU_MOM_PPC,
+      CYLGPU_MOM_AVERAGE_WEIGHT, CYLGPU_MOM_AVERAGE_MOMENTUM, CYLGPU_MOM_AVERAGE_MOMENTUM, CYLGPU_MOM_AVERAGE_MOMENTUM,
+      CYLGPU_MOM_TEMPERATURE, CYLGPU_MOM_TEMPERATURE, CYLGPU_MOM_TEMPERATURE, CYLGPU_MOM_TEMPERATURE,
+      CYLGPU_MOM_SPECIES_CURRENT, CYLGPU_MOM_SPECIES_CURRENT, CYLGPU_MOM_SPECIES_CURRENT,
+      CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX};
+  static const int dir_of[CYLGPU_SDF_NDERIVED] = {0, 0, 0, 0, 0, 0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, -1, -2, -3};
+  const int nder = sdf_derived_count(d);
+  std::vector<std::vector<double>> der((size_t)nder, std::vector<double>(g.plane));
+  std::vector<const double*> dptr((size_t)nder);
+  int q = 0;
+  for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v) {
+    if (!(d->derived_mask & (1u << v))) continue;
+    for (int s = d->derived_sum ? -1 : 0; s < (d->derived_species ? d->n_species : 0); ++s, ++q) {
+      if (kind_of[v] < 0) {
+        TRY(do_number_density_modes(c, s, true));
+        TRY(download_real_part_mode0(c, c->spare, der[(size_t)q].data()));
+      } else {
+        TRY(do_particle_moment(c, kind_of[v], s, dir_of[v], der[(size_t)q].data()));
+      }
+      dptr[(size_t)q] = der[(size_t)q].data();
+    }
+  }
+  return sdf_write_host(path, d, fptr, pptr, nder ? dptr.data() : nullptr);
 }
 int cylgpu_sdf_load(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
   TRY(check_handle(c));

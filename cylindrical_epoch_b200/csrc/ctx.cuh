@@ -229,7 +229,8 @@ int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double
                                uint64_t column, int64_t* n_inserted);
 // sdf_io.cu
 int sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
-                   const double* const* particles_aos);
+                   const double* const* particles_aos, const double* const* derived);
+int sdf_derived_count(const cylgpu_sdf_desc* d);
 int sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, double x_lo, double x_hi,
                   std::vector<std::vector<double>>* particles);
 // transport.cu

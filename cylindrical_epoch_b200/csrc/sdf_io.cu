@@ -76,6 +76,20 @@ inline int row_shift(int32_t stagger) { return (stagger == STAG_FACE_Y || stagge
 struct PointVar { const char* name; const char* units; int comp; };   // comp: index into the 7-double record
 const PointVar POINT_VARS[4] = {{"Weight", "", 6}, {"Px", "kg.m/s", 3}, {"Py", "kg.m/s", 4}, {"Pz", "kg.m/s", 5}};
 
+// write_nspecies_field call sites, io/diagnostics.F90:765-835 (poynt_flux reads the legacy Cartesian arrays: not offered)
+struct DerivedVar { const char* id; const char* name; const char* units; };
+const DerivedVar DERIVED[CYLGPU_SDF_NDERIVED] = {
+    {"ekbar", "Average_Particle_Energy", "J"}, {"mass_density", "Mass_Density", "kg/m^3"},
+    {"charge_density", "Charge_Density", "C/m^3"}, {"number_density", "Number_Density", "1/m^3"},
+    {"ppc", "Particles_Per_Cell", "n_particles"}, {"average_weight", "Particles_Average_Weight", "weight"},
+    {"average_px", "Particles_Average_Px", "kg.m/s"}, {"average_py", "Particles_Average_Py", "kg.m/s"},
+    {"average_pz", "Particles_Average_Pz", "kg.m/s"}, {"temperature", "Temperature", "K"},
+    {"temperature_x", "Temperature_x", "K"}, {"temperature_y", "Temperature_y", "K"},
+    {"temperature_z", "Temperature_z", "K"}, {"jx", "Jx", "A/m^2"}, {"jy", "Jy", "A/m^2"}, {"jz", "Jz", "A/m^2"},
+    {"ekflux/x_max", "Particle_Energy_Flux/x_max", "W/m^2"}, {"ekflux/y_max", "Particle_Energy_Flux/y_max", "W/m^2"},
+    {"ekflux/z_max", "Particle_Energy_Flux/z_max", "W/m^2"}, {"ekflux/x_min", "Particle_Energy_Flux/x_min", "W/m^2"},
+    {"ekflux/y_min", "Particle_Energy_Flux/y_min", "W/m^2"}, {"ekflux/z_min", "Particle_Energy_Flux/z_min", "W/m^2"}};
+
 struct Bytes {
   std::vector<unsigned char> b;
   template <class T> void put(T v) { const unsigned char* p = reinterpret_cast<const unsigned char*>(&v); b.insert(b.end(), p, p + sizeof(T)); }
@@ -198,6 +212,23 @@ std::vector<Block> build_blocks(const cylgpu_sdf_desc* d) {
       b.data_length = d->npart_global[s] * 8;
       bl.push_back(b);
     }
+  for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v) {   // write_nspecies_field, io/diagnostics.F90:2222-2232,2396-2431
+    if (!(d->derived_mask & (1u << v))) continue;
+    for (int s = d->derived_sum ? -1 : 0; s < (d->derived_species ? d->n_species : 0); ++s) {
+      Block b;
+      b.id = DERIVED[v].id;
+      b.name = std::string("Derived/") + DERIVED[v].name;
+      if (s >= 0) { b.id += std::string("/") + d->species_name[s]; b.name += std::string("/") + d->species_name[s]; }
+      b.blocktype = BT_PLAIN_VARIABLE; b.ndims = 2;
+      b.meta.put<double>(1.0);
+      b.meta.str(DERIVED[v].units, ID_LEN);
+      b.meta.str("grid", ID_LEN);
+      b.meta.put<int32_t>(nxg); b.meta.put<int32_t>(nyg);
+      b.meta.put<int32_t>(0);   // c_stagger_cell_centre
+      b.data_length = (int64_t)nxg * nyg * 8;
+      bl.push_back(b);
+    }
+  }
   int64_t pos = FILE_HEADER_LEN;
   for (Block& b : bl) {
     b.start = pos;
@@ -222,8 +253,15 @@ struct Fd {
 
 // fields15[id]: host array of field id (include/cylgpu.h CYLGPU_EXM ..), complex(num)
 // (1-ng:nx_local+ng, 1-ng:ny+ng, 0:M-1); particles_aos[s]: npart_local[s] records of 7 doubles.
+int sdf_derived_count(const cylgpu_sdf_desc* d) {
+  int n = 0;
+  for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v)
+    if (d->derived_mask & (1u << v)) n += (d->derived_sum ? 1 : 0) + (d->derived_species ? d->n_species : 0);
+  return n;
+}
+
 int sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
-                   const double* const* particles_aos) {
+                   const double* const* particles_aos, const double* const* derived) {
   TRY(check_desc(d));
   if (!path || !fields15) { set_error("sdf: null argument"); return 2; }
   const std::vector<Block> bl = build_blocks(d);
@@ -313,6 +351,31 @@ int sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const
       const Block* b = find_block(bl, lower(std::string(POINT_VARS[v].name) + "/" + d->species_name[s]));
       for (int64_t i = 0; i < nl; ++i) col[(size_t)i] = p[7 * i + POINT_VARS[v].comp];
       TRY(pwrite_all(f.fd, col.data(), (size_t)nl * 8, b->data_location + d->npart_offset[s] * 8));
+    }
+  }
+  // derived variables: the interior of a cell-centred real array per block
+  if (sdf_derived_count(d) > 0) {
+    if (!derived) { set_error("sdf: derived variables selected but no arrays given"); return 2; }
+    int q = 0;
+    std::vector<double> rows((size_t)nxl * nyg);
+    for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v) {
+      if (!(d->derived_mask & (1u << v))) continue;
+      for (int s = d->derived_sum ? -1 : 0; s < (d->derived_species ? d->n_species : 0); ++s, ++q) {
+        const double* a = derived[q];
+        if (!a) { set_error("sdf: derived array %d missing", q); return 2; }
+        std::string id = DERIVED[v].id;
+        if (s >= 0) id += std::string("/") + d->species_name[s];
+        const Block* b = find_block(bl, id);
+        for (int j = 1; j <= nyg; ++j)
+          memcpy(rows.data() + (size_t)(j - 1) * nxl, a + (size_t)(j + NG - 1) * SX + NG, (size_t)nxl * 8);
+        if (nxl == nxg) {
+          TRY(pwrite_all(f.fd, rows.data(), rows.size() * 8, b->data_location));
+        } else {
+          for (int j = 0; j < nyg; ++j)
+            TRY(pwrite_all(f.fd, rows.data() + (size_t)j * nxl, (size_t)nxl * 8,
+                           b->data_location + ((int64_t)j * nxg + (d->cell_x_min - 1)) * 8));
+        }
+      }
     }
   }
   if (fsync(f.fd) != 0) { set_error("sdf: fsync: %s", strerror(errno)); return 1; }

@@ -261,11 +261,21 @@ class Slab:
             d.species_name[i] = n
         return d
 
-    def sdf_dump(self, path, species_names, npart_global=None, npart_offset=None, restart=False):
+    # derived variables of write_nspecies_field in the reference's order (io/diagnostics.F90:765-835)
+    SDF_DERIVED = ["ekbar", "mass_density", "charge_density", "number_density", "ppc", "average_weight",
+                   "average_px", "average_py", "average_pz", "temperature", "temperature_x", "temperature_y",
+                   "temperature_z", "jx", "jy", "jz", "ekflux/x_max", "ekflux/y_max", "ekflux/z_max",
+                   "ekflux/x_min", "ekflux/y_min", "ekflux/z_min"]
+
+    def sdf_dump(self, path, species_names, npart_global=None, npart_offset=None, restart=False, derived=(),
+                 derived_sum=True, derived_species=True):
         """one SDF file in the reference's layout (io/diagnostics.F90:497-575,2033-2110,3040-3160) written
         from the device mirrors; with several ranks pass the global particle counts and this rank's offsets
         (the reference's species_offset) -- every rank calls with the same path"""
         d = self._sdf_desc(species_names, restart=restart)
+        for name in derived:      # computed on the device from the resident lists (cylgpu_particle_moment)
+            d.derived_mask |= 1 << self.SDF_DERIVED.index(name)
+        d.derived_sum, d.derived_species = int(derived_sum), int(derived_species)
         if npart_global is not None:
             for i in range(len(self.species)):
                 d.npart_global[i] = int(npart_global[i])

@@ -292,7 +292,15 @@ typedef struct {
   int32_t nx_global, ny_global, n_mode, n_species;
   int32_t nx_local, cell_x_min;          /* this rank's global cells cell_x_min .. cell_x_min + nx_local - 1 (1-based) */
   int32_t step, restart, jobid1, jobid2; /* file header: step, restart_flag, jobid (sdf_write_header) */
-  int32_t have_extents, pad_;
+  int32_t have_extents;
+  /* derived variables of write_nspecies_field (io/diagnostics.F90:765-835) to add to the dump, computed
+   * on the device by cylgpu_sdf_dump: bit v of derived_mask selects entry v of the reference's list
+   * (0 ekbar, 1 mass_density, 2 charge_density, 3 number_density, 4 ppc, 5 average_weight, 6..8
+   * average_px/py/pz, 9 temperature, 10..12 temperature_x/y/z, 13..15 jx/jy/jz, 16..21 ekflux x_max,
+   * y_max, z_max, x_min, y_min, z_min); derived_sum: the species-summed block 'Derived/<Name>'
+   * (dump_sum), derived_species: one block per species 'Derived/<Name>/<species>' (dump_species) */
+  uint32_t derived_mask;
+  int32_t derived_sum, derived_species;
   double time, x_min, dx, dy;            /* xb_global(i) = x_min + (i-1) dx, yb_global(j) = (j-1) dy */
   const char* species_name[CYLGPU_MAX_SPECIES];
   int64_t npart_global[CYLGPU_MAX_SPECIES], npart_offset[CYLGPU_MAX_SPECIES], npart_local[CYLGPU_MAX_SPECIES];
@@ -300,8 +308,13 @@ typedef struct {
 } cylgpu_sdf_desc;
 /* host arrays in, no device needed: fields15[id] = complex(num) (1-ng:nx_local+ng, 1-ng:ny+ng, 0:n_mode-1)
  * for the 15 field ids above, particles_aos[s] = npart_local[s] records of 7 doubles */
+#define CYLGPU_SDF_NDERIVED 22
 int cylgpu_sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const* fields15,
-                          const double* const* particles_aos);
+                          const double* const* particles_aos, const double* const* derived);
+/* derived: one real array (1-ng:nx_local+ng, 1-ng:ny+ng) per derived block, in file order -- for every
+ * selected variable the sum block (if derived_sum) then the species blocks (if derived_species);
+ * cylgpu_sdf_derived_count(d) says how many.  NULL when derived_mask is 0. */
+int cylgpu_sdf_derived_count(const cylgpu_sdf_desc* d);
 /* the inverse for this rank's slab: interior of the 15 arrays (ghosts untouched; the shift undone as in
  * housekeeping/setup.F90:1199-1210) and the particles with x_lo <= x < x_hi; fills step, time,
  * npart_global and npart_local; particles_aos may be NULL (counts only), else capacity[s] records each */

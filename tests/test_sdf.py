@@ -67,7 +67,7 @@ def write_world(w, d, path, order=None):
         parts = [np.ascontiguousarray(w.particles(k, i).reshape(-1, 7)) for i in range(nsp)]
         fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
         pp = (C.c_void_p * 8)(*([p.ctypes.data for p in parts] + [None] * (8 - nsp)))
-        rc = lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp)
+        rc = lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None)
         assert rc == 0, lib.cylgpu_last_error()
         state.append((k, fields, parts))
     return sorted(state, key=lambda t: t[0])
@@ -200,7 +200,7 @@ def test_bad_descriptors_fail_loudly(tmp_path, cylgpu_lib):
     desc = _lib.SdfDesc()
     fp = (C.c_void_p * 15)()
     pp = (C.c_void_p * 8)()
-    assert lib.cylgpu_sdf_write_host(str(tmp_path / "x.sdf").encode(), C.byref(desc), fp, pp) != 0
+    assert lib.cylgpu_sdf_write_host(str(tmp_path / "x.sdf").encode(), C.byref(desc), fp, pp, None) != 0
     assert b"descriptor" in lib.cylgpu_last_error()
     assert lib.cylgpu_sdf_read_host(b"/nonexistent/file.sdf", C.byref(desc), fp, 0.0, 1.0, None, None) != 0
     assert b"cannot open" in lib.cylgpu_last_error()
@@ -268,7 +268,7 @@ def test_reference_dump_bridge_self_check(tmp_path, cylgpu_lib):
         desc = make_desc(w, d, 0, 1, [parts[0].shape[0]], [0], [parts[0].shape[0]], step=step)
         fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
         pp = (C.c_void_p * 8)(*([parts[0].ctypes.data] + [None] * 7))
-        assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp) == 0
+        assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None) == 0
 
     dump(a, 2)
     w.step(5)
@@ -280,3 +280,51 @@ def test_reference_dump_bridge_self_check(tmp_path, cylgpu_lib):
     deck_path = str(tmp_path / "deck.json")
     json.dump(deck, open(deck_path, "w"))
     assert bridge.main([deck_path, a, b, "--tol", "1e-12"]) == 0
+
+
+def test_derived_variable_blocks(tmp_path, cylgpu_lib):
+    """write_nspecies_field (io/diagnostics.F90:765-835,2222-2232,2396-2431): 'Derived/<Name>[/<species>]' blocks
+    on the 'grid' mesh, cell centred, interior of the calc_df arrays -- here fed with the oracle's moments and
+    read back through the reference's reader"""
+    exe, _ = ref_tools()
+    lib = _lib.load()
+    d = decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=3, ppc_p=1)
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(3)
+    counts = [w.nparticles(0, i) for i in range(2)]
+    desc = make_desc(w, d, 0, 1, counts, [0, 0], counts)
+    sel = {3: ("number_density", "Number_Density", "1/m^3", ("number_density", 0)),
+           9: ("temperature", "Temperature", "K", ("temperature", 0)),
+           14: ("jy", "Jy", "A/m^2", ("species_current", 2)),
+           19: ("ekflux/x_min", "Particle_Energy_Flux/x_min", "W/m^2", ("ekflux", -1))}
+    for v in sel:
+        desc.derived_mask |= 1 << v
+    desc.derived_sum, desc.derived_species = 1, 1
+    assert lib.cylgpu_sdf_derived_count(C.byref(desc)) == 4 * 3
+    arrays, expect = [], []
+    for v in sorted(sel):
+        bid, name, units, (kind, direction) = sel[v]
+        for s in (-1, 0, 1):
+            a = np.ascontiguousarray(w.moment(kind, s, direction)[0])
+            arrays.append(a)
+            suffix = "" if s < 0 else "/" + NAMES[s].decode()
+            expect.append((bid + suffix, "Derived/" + name + suffix, units, a[NG:-NG, NG:-NG]))
+    fields = [np.ascontiguousarray(w.field(0, n)) for n in FIELD_NAMES]
+    parts = [np.ascontiguousarray(w.particles(0, i).reshape(-1, 7)) for i in range(2)]
+    fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
+    pp = (C.c_void_p * 8)(*([p.ctypes.data for p in parts] + [None] * 6))
+    dp = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+    path = str(tmp_path / "derived.sdf")
+    assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, dp) == 0, lib.cylgpu_last_error()
+    hdr, blocks = parse_ref(exe, path, str(tmp_path / "out"))
+    assert int(hdr["nblocks"]) == 41 + 12
+    for n, (bid, name, units, want) in enumerate(expect, start=41):
+        b = blocks[n]
+        assert (b["id"], b["name"], b["units"], b["mesh"], b["stagger"], b["blocktype"], b["ndims"]) == \
+            (bid, name, units, "grid", "0", "3", "2"), b
+        assert b["dims"].startswith(f"{d.nx},{d.ny}")
+        got = np.fromfile(os.path.join(str(tmp_path / "out"), f"{n}.bin")).reshape(d.ny, d.nx)
+        assert np.array_equal(got, want), bid
+    # selected but not supplied: refused
+    assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None) != 0

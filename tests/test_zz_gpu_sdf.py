@@ -33,8 +33,27 @@ def test_dump_from_device_then_restart(tmp_path, nranks):
 
         def dump(s):
             k = p.slabs.index(s)
-            ds[k] = s.sdf_dump(path, ["electron"], npart_global=[total], npart_offset=[sum(counts[:k])], restart=True)
+            ds[k] = s.sdf_dump(path, ["electron"], npart_global=[total], npart_offset=[sum(counts[:k])], restart=True,
+                               derived=("number_density", "temperature", "jx"))
         p.each(dump)
+        # the derived blocks were computed on the device (cylgpu_particle_moment): compare with the oracle's
+        # moments through the reference's reader when oracle/_ref travelled with the snapshot
+        import os
+        import subprocess
+        exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "sdf_ref_dump")
+        if os.path.exists(exe):
+            out = str(tmp_path / "out")
+            os.makedirs(out)
+            r = subprocess.run([exe, path, out], capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr
+            ids = [ln.split(" id=")[1].split(" ")[0] for ln in r.stdout.splitlines()[1:]]
+            for bid, (kind, direction) in (("number_density", ("number_density", 0)), ("temperature", ("temperature", 0)),
+                                           ("jx", ("species_current", 1))):
+                for suffix, isp in (("", -1), ("/electron", 0)):
+                    n = ids.index(bid + suffix)
+                    got = np.fromfile(os.path.join(out, f"{n}.bin")).reshape(d.ny, d.nx)
+                    ref = np.concatenate([m[5:-5, 5:-5] for m in p.oracle.moment(kind, isp, direction)], axis=1)
+                    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (bid, suffix)
         # a second pair of slabs restarts from the file and both continue
         q = Pair(d, nranks=nranks)
         q.oracle = p.oracle            # one oracle: it is the uninterrupted run
