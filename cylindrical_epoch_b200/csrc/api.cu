@@ -616,7 +616,8 @@ int cylgpu_sdf_dump(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
       CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX, CYLGPU_MOM_EKFLUX};
   static const int dir_of[CYLGPU_SDF_NDERIVED] = {0, 0, 0, 0, 0, 0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, -1, -2, -3};
   const int nder = sdf_derived_count(d);
-  std::vector<std::vector<double>> der((size_t)nder, std::vector<double>(g.plane));
+  const int nreal = nder - ((d->derived_mask & (1u << CYLGPU_SDF_NDERIVED)) ? d->n_species : 0);
+  std::vector<std::vector<double>> der((size_t)nreal, std::vector<double>(g.plane));
   std::vector<const double*> dptr((size_t)nder);
   int q = 0;
   for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v) {
@@ -629,6 +630,16 @@ int cylgpu_sdf_dump(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
         TRY(do_particle_moment(c, kind_of[v], s, dir_of[v], der[(size_t)q].data()));
       }
       dptr[(size_t)q] = der[(size_t)q].data();
+    }
+  }
+  std::vector<std::vector<cplx>> dmode;
+  if (d->derived_mask & (1u << CYLGPU_SDF_NDERIVED)) {   // calc_number_density_modes per species
+    dmode.assign((size_t)d->n_species, std::vector<cplx>(nf));
+    for (int s = 0; s < d->n_species; ++s, ++q) {
+      TRY(do_number_density_modes(c, s, false));
+      CUDA_TRY(cudaMemcpyAsync(dmode[(size_t)s].data(), c->spare, nf * sizeof(cplx), cudaMemcpyDeviceToHost, c->stream));
+      CUDA_TRY(cudaStreamSynchronize(c->stream));
+      dptr[(size_t)q] = reinterpret_cast<const double*>(dmode[(size_t)s].data());
     }
   }
   return sdf_write_host(path, d, fptr, pptr, nder ? dptr.data() : nullptr);

@@ -93,11 +93,14 @@ const DerivedVar DERIVED[CYLGPU_SDF_NDERIVED] = {
 struct Bytes {
   std::vector<unsigned char> b;
   template <class T> void put(T v) { const unsigned char* p = reinterpret_cast<const unsigned char*>(&v); b.insert(b.end(), p, p + sizeof(T)); }
-  void str(const std::string& s, int len) {   // blank-trimmed, NUL-padded fixed-length field (sdf_output.c:145-165)
+  // blank-trimmed, NUL-padded fixed-length field.  Like the Fortran writer (sdf_safe_copy_id / _string,
+  // SDF/FORTRAN/src/sdf_common.f90) a name may fill all `len` characters -- longer ones are cut there,
+  // e.g. 'number_density_mode/electron/Real' is stored as its first 32 characters.
+  void str(const std::string& s, int len) {
     size_t a = 0, e = s.size();
     while (a < e && isspace((unsigned char)s[a])) ++a;
     while (e > a && isspace((unsigned char)s[e - 1])) --e;
-    for (int i = 0; i < len; ++i) b.push_back((size_t)i < e - a && i < len - 1 ? (unsigned char)s[a + i] : 0);
+    for (int i = 0; i < len; ++i) b.push_back((size_t)i < e - a ? (unsigned char)s[a + i] : 0);
   }
 };
 
@@ -229,8 +232,25 @@ std::vector<Block> build_blocks(const cylgpu_sdf_desc* d) {
       bl.push_back(b);
     }
   }
+  if (d->derived_mask & (1u << CYLGPU_SDF_NDERIVED))   // write_nspecies_field_mode, io/diagnostics.F90:2596-2676
+    for (int s = 0; s < d->n_species; ++s)
+      for (int part = 0; part < 2; ++part) {
+        Block b;
+        const std::string tail = std::string("/") + d->species_name[s] + (part ? "/Imaginary" : "/Real");
+        b.id = "number_density_mode" + tail;
+        b.name = "Number_Density_Mode" + tail;
+        b.blocktype = BT_PLAIN_VARIABLE; b.ndims = 3;
+        b.meta.put<double>(1.0);
+        b.meta.str("1/m^3", ID_LEN);
+        b.meta.str("mode_grid", ID_LEN);
+        b.meta.put<int32_t>(nxg); b.meta.put<int32_t>(nyg); b.meta.put<int32_t>(M);
+        b.meta.put<int32_t>(0);   // c_stagger_cell_centre
+        b.data_length = (int64_t)nxg * nyg * M * 8;
+        bl.push_back(b);
+      }
   int64_t pos = FILE_HEADER_LEN;
   for (Block& b : bl) {
+    if (b.id.size() > (size_t)ID_LEN) b.id.resize(ID_LEN);
     b.start = pos;
     b.data_location = pos + BLOCK_HEADER_LEN + (int64_t)b.meta.b.size();
     b.next = b.data_location + b.data_length;
@@ -239,7 +259,8 @@ std::vector<Block> build_blocks(const cylgpu_sdf_desc* d) {
   return bl;
 }
 
-const Block* find_block(const std::vector<Block>& bl, const std::string& id) {
+const Block* find_block(const std::vector<Block>& bl, std::string id) {
+  if (id.size() > (size_t)ID_LEN) id.resize(ID_LEN);
   for (const Block& b : bl) if (b.id == id) return &b;
   return nullptr;
 }
@@ -257,6 +278,7 @@ int sdf_derived_count(const cylgpu_sdf_desc* d) {
   int n = 0;
   for (int v = 0; v < CYLGPU_SDF_NDERIVED; ++v)
     if (d->derived_mask & (1u << v)) n += (d->derived_sum ? 1 : 0) + (d->derived_species ? d->n_species : 0);
+  if (d->derived_mask & (1u << CYLGPU_SDF_NDERIVED)) n += d->n_species;   // number_density_mode: one complex array each
   return n;
 }
 
@@ -374,6 +396,31 @@ int sdf_write_host(const char* path, const cylgpu_sdf_desc* d, const void* const
           for (int j = 0; j < nyg; ++j)
             TRY(pwrite_all(f.fd, rows.data() + (size_t)j * nxl, (size_t)nxl * 8,
                            b->data_location + ((int64_t)j * nxg + (d->cell_x_min - 1)) * 8));
+        }
+      }
+    }
+  }
+  if (d->derived_mask & (1u << CYLGPU_SDF_NDERIVED)) {
+    // the per-species density modes: complex arrays (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1) behind the real-valued ones
+    int q = sdf_derived_count(d) - d->n_species;
+    for (int s = 0; s < d->n_species; ++s, ++q) {
+      const double* a = derived ? derived[q] : nullptr;
+      if (!a) { set_error("sdf: number_density_mode array of species %d missing", s); return 2; }
+      for (int part = 0; part < 2; ++part) {
+        for (int im = 0; im < M; ++im)
+          for (int j = 1; j <= nyg; ++j) {
+            const double* src = a + 2 * (((size_t)im * SY + (size_t)(j + NG - 1)) * SX + NG) + part;
+            double* dst = slab.data() + ((size_t)im * nyg + (j - 1)) * nxl;
+            for (int i = 0; i < nxl; ++i) dst[i] = src[2 * (size_t)i];
+          }
+        const Block* b = find_block(bl, std::string("number_density_mode/") + d->species_name[s] + (part ? "/Imaginary" : "/Real"));
+        if (nxl == nxg) {
+          TRY(pwrite_all(f.fd, slab.data(), slab.size() * 8, b->data_location));
+        } else {
+          for (int im = 0; im < M; ++im)
+            for (int j = 0; j < nyg; ++j)
+              TRY(pwrite_all(f.fd, slab.data() + ((size_t)im * nyg + j) * nxl, (size_t)nxl * 8,
+                             b->data_location + (((int64_t)im * nyg + j) * nxg + (d->cell_x_min - 1)) * 8));
         }
       }
     }

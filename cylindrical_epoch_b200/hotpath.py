@@ -265,7 +265,7 @@ class Slab:
     SDF_DERIVED = ["ekbar", "mass_density", "charge_density", "number_density", "ppc", "average_weight",
                    "average_px", "average_py", "average_pz", "temperature", "temperature_x", "temperature_y",
                    "temperature_z", "jx", "jy", "jz", "ekflux/x_max", "ekflux/y_max", "ekflux/z_max",
-                   "ekflux/x_min", "ekflux/y_min", "ekflux/z_min"]
+                   "ekflux/x_min", "ekflux/y_min", "ekflux/z_min", "number_density_mode"]
 
     def sdf_dump(self, path, species_names, npart_global=None, npart_offset=None, restart=False, derived=(),
                  derived_sum=True, derived_species=True):

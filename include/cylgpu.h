@@ -297,7 +297,9 @@ typedef struct {
    * on the device by cylgpu_sdf_dump: bit v of derived_mask selects entry v of the reference's list
    * (0 ekbar, 1 mass_density, 2 charge_density, 3 number_density, 4 ppc, 5 average_weight, 6..8
    * average_px/py/pz, 9 temperature, 10..12 temperature_x/y/z, 13..15 jx/jy/jz, 16..21 ekflux x_max,
-   * y_max, z_max, x_min, y_min, z_min); derived_sum: the species-summed block 'Derived/<Name>'
+   * y_max, z_max, x_min, y_min, z_min; 22 number_density_mode: write_nspecies_field_mode :781-783,2596-2676,
+   * per species 'Number_Density_Mode/<species>/Real' and '/Imaginary', complex arrays behind the others);
+   * derived_sum: the species-summed block 'Derived/<Name>'
    * (dump_sum), derived_species: one block per species 'Derived/<Name>/<species>' (dump_species) */
   uint32_t derived_mask;
   int32_t derived_sum, derived_species;

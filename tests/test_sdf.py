@@ -326,5 +326,23 @@ def test_derived_variable_blocks(tmp_path, cylgpu_lib):
         assert b["dims"].startswith(f"{d.nx},{d.ny}")
         got = np.fromfile(os.path.join(str(tmp_path / "out"), f"{n}.bin")).reshape(d.ny, d.nx)
         assert np.array_equal(got, want), bid
+    # number_density_mode: per species, complex, on the mode grid (io/diagnostics.F90:2596-2676)
+    desc.derived_mask |= 1 << 22
+    assert lib.cylgpu_sdf_derived_count(C.byref(desc)) == 4 * 3 + 2
+    modes = [np.ascontiguousarray(w.number_density_modes(s)[0]) for s in range(2)]
+    dp2 = (C.c_void_p * (len(arrays) + 2))(*([a.ctypes.data for a in arrays] + [m.ctypes.data for m in modes]))
+    assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, dp2) == 0, lib.cylgpu_last_error()
+    hdr, blocks = parse_ref(exe, path, str(tmp_path / "out2"))
+    assert int(hdr["nblocks"]) == 41 + 12 + 4
+    n = 53
+    for s in range(2):
+        for tag, arr in (("Real", modes[s].real), ("Imaginary", modes[s].imag)):
+            b = blocks[n]
+            nm = NAMES[s].decode()
+            assert (b["id"], b["name"], b["units"], b["mesh"], b["stagger"], b["ndims"]) == \
+                (f"number_density_mode/{nm}/{tag}"[:32], f"Number_Density_Mode/{nm}/{tag}", "1/m^3", "mode_grid", "0", "3")
+            got = np.fromfile(os.path.join(str(tmp_path / "out2"), f"{n}.bin")).reshape(d.n_mode, d.ny, d.nx)
+            assert np.array_equal(got, arr[:, NG:-NG, NG:-NG])
+            n += 1
     # selected but not supplied: refused
     assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None) != 0
