@@ -54,6 +54,7 @@ class Laser:     # laser.f90 laser_block restricted to what the decks in scope u
     t_width: float = 0.0      # <= 0 -> constant temporal envelope
     r_width: float = 0.0      # <= 0 -> flat radial profile
     phase: float = 0.0
+    phase_curv: float = 0.0   # phase(y) = phase + phase_curv y^2: the deck's phase function (laser.f90:203-226,454)
 
 
 def normalise_bc_field(bc):
@@ -398,7 +399,7 @@ class Slab:
             if L.r_width > 0.0:
                 a = (yv - 0.0) / L.r_width
                 prof = np.exp(-(a * a))
-            base = t_env * prof * math.sin(L.omega * self.time + L.phase)
+            base = t_env * prof * np.sin(L.omega * self.time + (L.phase + L.phase_curv * (yv * yv)))
             s1 = s1 + base * math.cos(L.pol_angle)
             s2 = s2 + base * math.sin(L.pol_angle)
         return s1, s2

@@ -635,7 +635,7 @@ void World::laser_sources(int bd, const Rank& r, std::vector<double>& s1, std::v
           double a = (yv - 0.0) / L.r_width;
           prof = std::exp(-(a * a));
         }
-        double base = t_env * prof * std::sin(phase_int + L.phase);
+        double base = t_env * prof * std::sin(phase_int + (L.phase + L.phase_curv * (yv * yv)));
         s1[ir] = s1[ir] + base * std::cos(L.pol_angle);
         s2[ir] = s2[ir] + base * std::sin(L.pol_angle);
       }

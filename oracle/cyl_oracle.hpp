@@ -134,6 +134,7 @@ struct Laser {  // laser.f90 laser_block, restricted to what the decks in scope 
   double t_centre, t_width;   // t_profile = gauss(time, t_centre, t_width); t_width<=0 -> 1
   double r_width;             // profile = gauss(y, 0, r_width); r_width<=0 -> 1
   double phase;               // constant phase
+  double phase_curv = 0.0;    // phase(y) = phase + phase_curv * y^2 (the deck's phase function, laser.f90:203-226,454)
 };
 
 // the real-valued particle moments of io/calc_df.F90 (cyl_moments.cpp)

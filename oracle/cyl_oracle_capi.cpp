@@ -47,11 +47,11 @@ int cylo_add_species(void* w, double charge, double mass, const int32_t* bc_part
 }
 
 void cylo_add_laser(void* w, int boundary, double amp, double omega, double pol_angle, double t_start,
-                    double t_end, double t_centre, double t_width, double r_width, double phase) {
+                    double t_end, double t_centre, double t_width, double r_width, double phase, double phase_curv) {
   Laser L;
   L.boundary = boundary; L.amp = amp; L.omega = omega; L.pol_angle = pol_angle;
   L.t_start = t_start; L.t_end = t_end; L.t_centre = t_centre; L.t_width = t_width;
-  L.r_width = r_width; L.phase = phase;
+  L.r_width = r_width; L.phase = phase; L.phase_curv = phase_curv;
   ((World*)w)->lasers.push_back(L);
 }
 

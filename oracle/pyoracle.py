@@ -80,7 +80,7 @@ def lib():
         L.cylo_add_species.argtypes = [C.c_void_p, C.c_double, C.c_double, C.POINTER(C.c_int32), C.c_int,
                                        C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double),
                                        C.POINTER(C.c_double)]
-        L.cylo_add_laser.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 9
+        L.cylo_add_laser.argtypes = [C.c_void_p, C.c_int] + [C.c_double] * 10
         L.cylo_load_uniform.argtypes = [C.c_void_p, C.c_int]
         L.cylo_get_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.cylo_set_dt.argtypes = [C.c_void_p, C.c_double]
@@ -157,9 +157,9 @@ class OracleWorld:
         return i
 
     def add_laser(self, boundary, amp, omega, pol_angle=0.0, t_start=0.0, t_end=1e300, t_centre=0.0,
-                  t_width=0.0, r_width=0.0, phase=0.0):
+                  t_width=0.0, r_width=0.0, phase=0.0, phase_curv=0.0):
         self.L.cylo_add_laser(self.h, boundary, amp, omega, pol_angle, t_start, t_end, t_centre, t_width,
-                              r_width, phase)
+                              r_width, phase, phase_curv)
 
     def load_uniform(self, isp):
         self.L.cylo_load_uniform(self.h, isp)

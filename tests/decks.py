@@ -92,6 +92,25 @@ def drift(nx=48, ny=24, n_mode=3):
     return Deck("drift", nx, ny, n_mode, 0.0, nx * dx, ny * dy, (BC_CLAMP, BC_CLAMP, 0, BC_CLAMP), sp)
 
 
+def gaussian_pulse(nx=500, ny=100):
+    """example_decks/gaussian_pulse.deck of the reference: a CW beam of 1 um light launched from x_min with the
+    curved phase front and width of a Gaussian beam that focuses 10 um into the box to a 1.5 um FWHM spot of
+    1e15 W/cm^2; vacuum, m = 0..1, open x_max / r_max.  The deck's own constants block is restated here."""
+    lam, i_fwhm, i_peak, foc = 1.0e-6, 1.5e-6, 1.0e15, 10.0e-6
+    k = 2.0 * math.pi / lam
+    w0 = i_fwhm / math.sqrt(2.0 * math.log(2.0))
+    zr = math.pi * w0 ** 2 / lam
+    w_b = w0 * math.sqrt(1.0 + (foc / zr) ** 2)
+    i_b = i_peak * (w0 / w_b) ** 2
+    rc = foc * (1.0 + (zr / foc) ** 2)
+    gouy = math.atan(-foc / rc)
+    las = [dict(boundary=BD_X_MIN, amp=laser_amp(i_b), omega=2.0 * math.pi * C_LIGHT / lam, r_width=w_b,
+                phase=-gouy, phase_curv=k / (2.0 * rc), pol_angle=0.0)]
+    d = Deck("gaussian_pulse", nx, ny, 2, 0.0, 20.0e-6, 5.0e-6, (BC_SIMPLE_LASER, BC_OPEN, 0, BC_OPEN), [], las)
+    d.expect = dict(w0=w0, e_peak=math.sqrt(2.0 * i_peak * 1.0e4 / (EPSILON0 * C_LIGHT)), focus=foc, rayleigh=zr)
+    return d
+
+
 def make_oracle(deck, nranks=1, load=True):
     import pyoracle as po
     w = po.OracleWorld(deck.nx, deck.ny, deck.n_mode, deck.x_min, deck.x_max, deck.y_max, list(deck.bc_field),

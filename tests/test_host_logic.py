@@ -77,6 +77,9 @@ def test_laser_sources_match_oracle():
         pass
     s = Stub()
     s.grid = decomp.SlabGrid(32, 24, 1, 0, d.x_min, d.x_max, d.y_max)
+    # second laser: the curved phase front of example_decks/gaussian_pulse.deck (phase function of y)
+    d.lasers.append(dict(decks.gaussian_pulse().lasers[0]))
+    w.add_laser(**d.lasers[-1])
     s.lasers = [hotpath.Laser(**L) for L in d.lasers]
     s.add_laser = [True, False, False, False]
     for t in (0.0, 1.3e-14, 3.0e-14, 4.1e-14):
@@ -84,8 +87,8 @@ def test_laser_sources_match_oracle():
         s.time = t
         r1, r2 = w.laser_sources(BD_X_MIN)
         g1, g2 = hotpath.Slab.laser_sources(s, BD_X_MIN)
-        np.testing.assert_allclose(g1, r1, rtol=1e-14, atol=0)
-        np.testing.assert_allclose(g2, r2, rtol=1e-14, atol=0)
+        np.testing.assert_allclose(g1, r1, rtol=1e-13, atol=1e-13 * np.abs(r1).max())
+        np.testing.assert_allclose(g2, r2, rtol=1e-13, atol=1e-13 * max(np.abs(r2).max(), 1e-300))
 
 
 # ------------------------------------------------------------------ world_size 2 over gloo
