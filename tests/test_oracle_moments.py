@@ -219,6 +219,11 @@ def test_known_answers_of_a_uniform_thermal_load():
     inner = (slice(NG + 2, NG + 24 - 2), slice(NG, NG + 48))
     nd = w.moment("number_density", 0)[0][inner]
     assert abs(nd.mean() / n0 - 1.0) < 0.02
+    # example_decks/uniform_density_load.deck: a uniform load must show a uniform number_density down to the
+    # axis -- the r < dy fold of the weights (triangle/gxfac.inc) and the 2 pi r macro-particle volume
+    # (partlist.F90:999-1013) have to cancel; row means over 48 columns, axis row included
+    rows = w.moment("number_density", 0)[0][NG:NG + 22, NG:NG + 48].mean(axis=1)
+    assert np.abs(rows / n0 - 1.0).max() < 0.03, rows / n0
     rho_m = w.moment("mass_density", 0)[0][inner]
     assert np.abs(rho_m - M0 * nd).max() <= 1e-13 * rho_m.max()
     # every cell holds ppc particles at load time (helper.F90:552-583), weights sum to n0 * cell volume
