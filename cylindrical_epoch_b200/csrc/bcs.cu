@@ -383,42 +383,6 @@ int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min,
   return do_bfield_final_bcs_device(c);
 }
 
-// ---- currents ----
-// current_bcs_r_min_final, boundary.F90:1909-1959: fold the rows below the axis back and set
-// the axis rows.  One thread per column; rows are independent between columns.
-__global__ void __launch_bounds__(128) k_r_min_final(Geom g, cplx* __restrict__ jxm, cplx* __restrict__ jrm,
-                                                     cplx* __restrict__ jtm) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
-  const int im = blockIdx.y;
-  if (ix > g.nx + NG) return;
-  const double mode_sign = (im & 1) ? -1.0 : 1.0;
-  for (int j = 2; j <= JNG; ++j) {
-    const size_t lo = g.at(ix, 1 - j, im);
-    const size_t a = g.at(ix, j - 1, im), b = g.at(ix, j, im);
-    jxm[a] = jxm[a] + mode_sign * jxm[lo];
-    jrm[b] = jrm[b] - mode_sign * jrm[lo];
-    jtm[a] = jtm[a] - mode_sign * jtm[lo];
-    jxm[lo] = C(0.0, 0.0);
-    jrm[lo] = C(0.0, 0.0);
-    jtm[lo] = C(0.0, 0.0);
-  }
-  {
-    const size_t a = g.at(ix, 1, im);
-    jrm[a] = jrm[a] - mode_sign * jrm[g.at(ix, 0, im)];
-  }
-  const size_t a0 = g.at(ix, 0, im), a1 = g.at(ix, 1, im), a2 = g.at(ix, 2, im);
-  if (im > 0) jxm[a0] = C(0.0, 0.0);
-  else jxm[a0] = (4.0 * jxm[a1] - jxm[a2]) / 3.0;
-  if (im == 1) {
-    const cplx jt0 = (C(0.0, -1.0) * (9.0 * jrm[a1] - jrm[a2])) / 8.0;
-    jtm[a0] = jt0;
-    jrm[a0] = C(0.0, 2.0) * jt0 - jrm[a1];
-  } else {
-    jtm[a0] = C(0.0, 0.0);
-    jrm[a0] = -jrm[a1];
-  }
-}
-
 int do_r_min_final(cylgpu_ctx* c) {
   const Geom& g = c->g;
   k_r_min_final<<<dim3((g.SX + 127) / 128, g.M), 128, 0, c->stream>>>(g, c->f[CYLGPU_JXM], c->f[CYLGPU_JRM],

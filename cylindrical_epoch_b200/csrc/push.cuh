@@ -3,7 +3,9 @@
 // gx.inc, hx_dcell.inc), azimuthal-mode field gather (include/triangle/e_part.inc,
 // b_part.inc), Boris rotation, and the charge-conserving mode deposit weights.
 #pragma once
+#ifndef CYL_EMUL   // tests/emul/ compiles this header for the CPU against its own shim + geom.cuh
 #include "ctx.cuh"
+#endif
 
 namespace cylgpu {
 

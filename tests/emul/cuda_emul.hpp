@@ -28,6 +28,9 @@ struct dim3 {
 static thread_local uint3 threadIdx, blockIdx;
 static thread_local dim3 blockDim, gridDim;
 
+// read-only cache load: a plain load
+template <class T> inline T __ldg(const T* p) { return *p; }
+
 // one emulated thread at a time: a plain read-modify-write is the atomic
 inline double atomicAdd(double* p, double v) { const double old = *p; *p = old + v; return old; }
 

@@ -10,11 +10,16 @@
 #include "../../include/cylgpu.h"
 #include "../../cylindrical_epoch_b200/csrc/geom.cuh"
 #include "../../cylindrical_epoch_b200/csrc/philox.cuh"
+// the push arithmetic: IEEE division / square root instead of the PTX seeds (inline asm cannot run here)
+#define CYL_EMUL
+#define CYL_REFERENCE_MATH
+#include "../../cylindrical_epoch_b200/csrc/push.cuh"
 
 namespace cylgpu {
 #include "../../cylindrical_epoch_b200/csrc/bc_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/moments_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
+#include "../../cylindrical_epoch_b200/csrc/push_v0.cuh"
 }  // namespace cylgpu
 
 using namespace cylgpu;
@@ -132,6 +137,81 @@ EMUL_API int emul_particle_moment(int nx, int ny, int kind, int direction, int n
   }
   emul_launch(k_moment_finish, pb, dim3(256), (const cplx*)result, out, np, finish_mode, dof);
   return 0;
+}
+
+// push_particles without particle_bcs for one species of one slab (cylgpu_push_no_bcs with push variant 0):
+// the radial tables of particles.cu::build_tables, the PushConst of push_species, k_push_v0<M> over the list
+// and k_r_min_final.  fields: the six E/B mode arrays, jx/jr/jt: zeroed J arrays to deposit into (complex,
+// with ghosts); soa: 7 arrays of n doubles, updated in place.
+EMUL_API int emul_push_v0(int nx, int ny, int M, const void* const* fields6, void* const* j3, double* const* soa,
+                          int64_t n, double charge, double mass, int zero_current, int hc_push, double dt, double dx,
+                          double dy, double x_grid_min_local, double y_grid_min_local) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  const int ntab = ny + 2 * JNG + 1;
+  std::vector<double> t(4 * (size_t)ntab, 0.0);
+  {   // particles.F90:190-217, r_low accumulated by repeated addition
+    double* rt = t.data();
+    double* xt = rt + ntab;
+    double* vol = xt + ntab;
+    double* ratio = vol + ntab;
+    double r_low = y_grid_min_local - (double)JNG * dy;
+    xt[0] = 1.0 / (2.0 * PI * std::fabs(r_low) * dx);
+    for (int iy = 1 - JNG; iy <= ny + JNG; ++iy) {
+      if (std::lround(2.0 * r_low / dy) == -1) rt[iy + JNG] = 1.0 / (PI * ((0.5 * dy) * (0.5 * dy)));
+      else rt[iy + JNG] = 1.0 / (PI * std::fabs((r_low + dy) * (r_low + dy) - r_low * r_low));
+      xt[iy + JNG] = 1.0 / (2.0 * PI * std::fabs(r_low + dy) * dx);
+      r_low = r_low + dy;
+    }
+    for (int iy = 1 - JNG; iy <= ny + JNG; ++iy) {
+      vol[iy + JNG] = rt[iy + JNG] / dx;
+      ratio[iy + JNG] = xt[iy + JNG] / xt[iy + JNG - 1];
+    }
+  }
+  const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
+  PushConst P;
+  P.g = g;
+  P.exm = (const cplx*)fields6[0]; P.erm = (const cplx*)fields6[1]; P.etm = (const cplx*)fields6[2];
+  P.bxm = (const cplx*)fields6[3]; P.brm = (const cplx*)fields6[4]; P.btm = (const cplx*)fields6[5];
+  P.jx = (double*)j3[0]; P.jr = (double*)j3[1]; P.jt = (double*)j3[2];
+  P.tab = t.data(); P.ntab = ntab;
+  P.x_grid_min_local = x_grid_min_local;
+  P.y_grid_min_local = y_grid_min_local;
+  P.idx = 1.0 / dx; P.idy = 1.0 / dy; P.idt = 1.0 / dt;
+  P.dtco2 = C_LIGHT * (dt / 2.0);
+  const double dtfac = 0.5 * dt * fac;
+  P.part_mc = C_LIGHT * mass;
+  P.ipart_mc = 1.0 / P.part_mc;
+  P.cmratio = charge * dtfac * P.ipart_mc;
+  P.ccmratio = C_LIGHT * P.cmratio;
+  P.q_fac = charge * fac;
+  P.deposit = zero_current ? 0 : 1;
+  P.hc_push = hc_push ? 1 : 0;
+  P.hc_alpha = 0.5 * charge * dt / mass;
+  const dim3 grid((unsigned)((n + 127) / 128)), block(128);
+#define EMUL_V0(MM) emul_launch(k_push_v0<MM>, grid, block, P, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5], (const double*)soa[6], n)
+  switch (M) {
+    case 1: EMUL_V0(1); break;
+    case 2: EMUL_V0(2); break;
+    case 3: EMUL_V0(3); break;
+    case 4: EMUL_V0(4); break;
+    case 5: EMUL_V0(5); break;
+    case 6: EMUL_V0(6); break;
+    default: return 2;
+  }
+#undef EMUL_V0
+  return 0;
+}
+
+// current_bcs_r_min_final (bcs.cu::do_r_min_final) on the three J arrays
+EMUL_API void emul_r_min_final(int nx, int ny, int M, void* const* j3) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  emul_launch(k_r_min_final, dim3((g.SX + 127) / 128, M), dim3(128), g, (cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]);
 }
 
 // window_insert.cu::do_insert_particles_device for the x_max slab: returns the number of particles

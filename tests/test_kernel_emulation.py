@@ -118,3 +118,66 @@ def test_insert_column_kernel_matches_the_oracle_column(emul, ppc):
     assert n == ref.shape[0] and n > 0
     got = np.stack([a[:n] for a in soa], axis=1)
     assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------------------------------------------
+# push variant 0 (csrc/push.cuh + push_v0.cuh): the per-particle physics of the hot path -- half-step drift,
+# azimuthal-mode gather, Boris / Higuera-Cary rotation, charge-conserving mode deposit -- from the product's
+# own source, on the CPU.  The tuned kernels (strips, DMMA deposit) share push.cuh's arithmetic and are
+# checked against this variant and the oracle on the GPU.
+# ------------------------------------------------------------------------------------------------------
+def _emul_push(L, w, d, hc=False):
+    sc, info = w.scalars(), w.rank_info(0)
+    nx, ny, M = info["nx"], info["ny"], d.n_mode
+    L.emul_push_v0.restype = C.c_int
+    L.emul_push_v0.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                               C.POINTER(C.c_void_p), C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int,
+                               C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.emul_r_min_final.restype = None
+    L.emul_r_min_final.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    fields = [np.ascontiguousarray(w.field(0, n)) for n in ("exm", "erm", "etm", "bxm", "brm", "btm")]
+    J = [np.zeros_like(fields[0]) for _ in range(3)]
+    fp = (C.c_void_p * 6)(*[f.ctypes.data for f in fields])
+    jp = (C.c_void_p * 3)(*[j.ctypes.data for j in J])
+    parts = []
+    for i, sp in enumerate(d.species):
+        p = w.particles(0, i).reshape(-1, 7)
+        soa = [np.ascontiguousarray(p[:, c]) for c in range(7)]
+        sp_ptr = (C.c_void_p * 7)(*[a.ctypes.data for a in soa])
+        rc = L.emul_push_v0(nx, ny, M, fp, jp, sp_ptr, p.shape[0], sp.charge, sp.mass, int(sp.zero_current), int(hc),
+                            sc["dt"], sc["dx"], sc["dy"], info["x_grid_min_local"], sc["y_grid_min_local"])
+        assert rc == 0
+        parts.append(np.stack(soa, axis=1))
+    L.emul_r_min_final(nx, ny, M, jp)
+    return J, parts
+
+
+@pytest.mark.parametrize("deck_name,hc,tol", [("lwfa", False, 1e-11), ("lwfa", True, 1e-11), ("drift3", False, 1e-7),
+                                              ("thermal", False, 1e-7), ("modes5", False, 1e-11)])
+def test_push_v0_kernel_matches_the_oracle(emul, deck_name, hc, tol):
+    d = {"lwfa": lambda: decks.lwfa(nx=32, ny=12, n_mode=2, ppc_e=4, ppc_p=1),
+         "drift3": lambda: decks.drift(nx=20, ny=10, n_mode=3),
+         "thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=4),
+         "modes5": lambda: decks.lwfa(nx=24, ny=10, n_mode=5, ppc_e=2, ppc_p=0)}[deck_name]()
+    w = decks.make_oracle(d)
+    if hc:
+        w.set_hc_push(True)
+    w.call("init_half_step")
+    w.step(30 if deck_name in ("lwfa", "modes5") else 3)   # the laser decks: let the pulse reach the plasma
+    w.call("fields_half")                                   # push_particles sees the half-step fields
+    J, parts = _emul_push(emul, w, d, hc)
+    w.call("push_no_bcs")
+    # the charge-conserving deposit cancels terms of size q n c: J carries an absolute rounding floor
+    # (tests/parity.py J_FLOOR); hot decks sit near the reference's Taylor switch (TOL_HOT there)
+    qnc = sum(abs(sp.charge) * sp.density * po.C_LIGHT for sp in d.species)
+    for name, j in zip(("jxm", "jrm", "jtm"), J):
+        ref = w.field(0, name)
+        den = max(np.abs(ref).max(), 1e-3 * qnc)
+        assert np.abs(j - ref).max() <= tol * den, (deck_name, name, np.abs(j - ref).max() / den)
+        assert np.abs(ref).max() > 0
+    for i, got in enumerate(parts):
+        ref = w.particles(0, i).reshape(-1, 7)
+        assert np.array_equal(got[:, 6], ref[:, 6])
+        for cols in (slice(0, 3), slice(3, 6)):
+            den = np.abs(ref[:, cols]).max()
+            assert np.abs(got[:, cols] - ref[:, cols]).max() <= 1e-12 * den, (deck_name, i, cols)
