@@ -49,7 +49,10 @@ class SdfDesc(C.Structure):   # cylgpu_sdf_desc
                 ("time", C.c_double), ("x_min", C.c_double), ("dx", C.c_double), ("dy", C.c_double),
                 ("species_name", C.c_char_p * MAX_SPECIES),
                 ("npart_global", C.c_int64 * MAX_SPECIES), ("npart_offset", C.c_int64 * MAX_SPECIES),
-                ("npart_local", C.c_int64 * MAX_SPECIES), ("part_extents", (C.c_double * 6) * MAX_SPECIES)]
+                ("npart_local", C.c_int64 * MAX_SPECIES), ("part_extents", (C.c_double * 6) * MAX_SPECIES),
+                ("n_constants", C.c_int32), ("constants_found", C.c_uint32),
+                ("constant_id", C.c_char_p * 16), ("constant_name", C.c_char_p * 16),
+                ("constant_value", C.c_double * 16)]
 
 
 # every symbol include/cylgpu.h declares: name -> (restype, argtypes)

@@ -44,7 +44,7 @@ constexpr int ID_LEN = 32, STR_LEN = 64;
 constexpr int64_t FILE_HEADER_LEN = 11 * 4 + 2 * 8 + 8 + 12 + ID_LEN;           // sdf_control.h:20
 constexpr int32_t BLOCK_HEADER_LEN = 4 + 3 * 4 + 3 * 8 + ID_LEN + STR_LEN;      // sdf_control.h:21-22
 constexpr int32_t SDF_ENDIAN = 16911887, SDF_VER = 1, SDF_REV = 4;
-enum { BT_PLAIN_MESH = 1, BT_POINT_MESH = 2, BT_PLAIN_VARIABLE = 3, BT_POINT_VARIABLE = 4 };   // sdf.h:47-59
+enum { BT_PLAIN_MESH = 1, BT_POINT_MESH = 2, BT_PLAIN_VARIABLE = 3, BT_POINT_VARIABLE = 4, BT_CONSTANT = 5 };   // sdf.h:47-61
 constexpr int32_t DT_REAL8 = 4;                                                   // sdf.h:195-200
 constexpr int32_t GEOMETRY_CARTESIAN = 1;                                         // sdf.h:130-132
 // sdf_common.f90:184-195; constants.F90:291-299
@@ -140,6 +140,9 @@ int check_desc(const cylgpu_sdf_desc* d) {
     set_error("sdf: bad descriptor");
     return 2;
   }
+  if (d->n_constants < 0 || d->n_constants > CYLGPU_SDF_MAX_CONSTANTS) { set_error("sdf: bad number of constants"); return 2; }
+  for (int k = 0; k < d->n_constants; ++k)
+    if (!d->constant_id[k] || !d->constant_id[k][0]) { set_error("sdf: constant %d has no id", k); return 2; }
   for (int s = 0; s < d->n_species; ++s) {
     if (!d->species_name[s] || !d->species_name[s][0]) { set_error("sdf: species %d has no name", s); return 2; }
     if (d->npart_local[s] < 0 || d->npart_offset[s] < 0 || d->npart_offset[s] + d->npart_local[s] > d->npart_global[s]) {
@@ -155,6 +158,15 @@ int check_desc(const cylgpu_sdf_desc* d) {
 std::vector<Block> build_blocks(const cylgpu_sdf_desc* d) {
   std::vector<Block> bl;
   const int nxg = d->nx_global, nyg = d->ny_global, M = d->n_mode;
+  for (int k = 0; k < d->n_constants; ++k) {   // sdf_write_srl(id, name, value): the value is the block's metadata
+    Block b;
+    b.id = d->constant_id[k];
+    b.name = d->constant_name[k] ? d->constant_name[k] : d->constant_id[k];
+    b.blocktype = BT_CONSTANT; b.ndims = 1;
+    b.meta.put<double>(d->constant_value[k]);
+    b.data_length = 0;
+    bl.push_back(b);
+  }
   {   // sdf_write_srl_plain_mesh('grid', 'Grid/Grid', xb_global, yb_global), io/diagnostics.F90:872
     Block b;
     b.id = "grid"; b.name = "Grid/Grid"; b.blocktype = BT_PLAIN_MESH; b.ndims = 2;
@@ -492,6 +504,14 @@ int sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, d
   if (f.fd < 0) { set_error("sdf: cannot open %s: %s", path, strerror(errno)); return 1; }
   std::vector<FileBlock> bl;
   TRY(read_blocklist(f.fd, bl, &d->step, &d->time));
+  d->constants_found = 0;
+  for (int k = 0; k < d->n_constants && k < CYLGPU_SDF_MAX_CONSTANTS; ++k) {
+    const FileBlock* b = d->constant_id[k] ? find_file_block(bl, d->constant_id[k]) : nullptr;
+    if (b && b->blocktype == BT_CONSTANT && b->datatype == DT_REAL8 && b->meta.size() >= 8) {
+      memcpy(&d->constant_value[k], b->meta.data(), 8);
+      d->constants_found |= 1u << k;
+    }
+  }
   const int nxg = d->nx_global, nyg = d->ny_global, M = d->n_mode, nxl = d->nx_local;
   const int SX = nxl + 2 * NG, SY = nyg + 2 * NG;
   std::vector<double> row((size_t)nxl);

@@ -268,6 +268,17 @@ class Slab:
                    "temperature_z", "jx", "jy", "jz", "ekflux/x_max", "ekflux/y_max", "ekflux/z_max",
                    "ekflux/x_min", "ekflux/y_min", "ekflux/z_min", "number_density_mode"]
 
+    def _sdf_constants(self, d, ids, values=None):
+        self._sdf_const_keep = [(i.encode(), i.encode()) for i in ids]
+        d.n_constants = len(ids)
+        for k, (bid, name) in enumerate(self._sdf_const_keep):
+            d.constant_id[k], d.constant_name[k] = bid, name
+            if values is not None:
+                d.constant_value[k] = float(values[k])
+
+    # what the driver owns and a restart needs back (sdf_write_srl, io/diagnostics.F90:408-416)
+    SDF_RESTART_CONSTANTS = ("dt", "window_shift_fraction", "x_grid_min", "window_started", "window_shifts_total")
+
     def sdf_dump(self, path, species_names, npart_global=None, npart_offset=None, restart=False, derived=(),
                  derived_sum=True, derived_species=True):
         """one SDF file in the reference's layout (io/diagnostics.F90:497-575,2033-2110,3040-3160) written
@@ -277,6 +288,9 @@ class Slab:
         for name in derived:      # computed on the device from the resident lists (cylgpu_particle_moment)
             d.derived_mask |= 1 << self.SDF_DERIVED.index(name)
         d.derived_sum, d.derived_species = int(derived_sum), int(derived_species)
+        self._sdf_constants(d, self.SDF_RESTART_CONSTANTS,
+                            (self.dt, self.window_shift_fraction, self.grid.x_grid_min, float(self.window_started),
+                             float(self.window_shifts_total)))
         if npart_global is not None:
             for i in range(len(self.species)):
                 d.npart_global[i] = int(npart_global[i])
@@ -289,8 +303,13 @@ class Slab:
         interior of the 15 mode arrays, this slab's particles, step and time; the ghosts are then
         re-derived by the boundary routines"""
         d = self._sdf_desc(species_names)
+        self._sdf_constants(d, self.SDF_RESTART_CONSTANTS)
         self._ck(self.L.cylgpu_sdf_load(self.h, str(path).encode(), C.byref(d)))
         self.step, self.time = int(d.step), float(d.time)
+        if d.constants_found & 2:       # the window state travels in the file (io/diagnostics.F90:411-414)
+            self.window_shift_fraction = float(d.constant_value[1])
+        self.sdf_constants = {i: float(d.constant_value[k]) for k, i in enumerate(self.SDF_RESTART_CONSTANTS)
+                              if d.constants_found & (1 << k)}
         self.efield_bcs()
         self.bfield_bcs(False)
         # J ghosts: the halo of current_finish without smoothing the stored (already smoothed) currents again

@@ -288,6 +288,7 @@ int cylgpu_particle_moment(cylgpu_handle h, int kind, int ispecies, int directio
  * from the global sizes); the rank that owns x_min adds the metadata.  The caller supplies what the
  * reference gets from MPI: npart_global and npart_offset (species_offset) per species.  With
  * have_extents = 0 the particle-grid extents in the metadata are those of the writing rank. */
+#define CYLGPU_SDF_MAX_CONSTANTS 16
 typedef struct {
   int32_t nx_global, ny_global, n_mode, n_species;
   int32_t nx_local, cell_x_min;          /* this rank's global cells cell_x_min .. cell_x_min + nx_local - 1 (1-based) */
@@ -307,6 +308,15 @@ typedef struct {
   const char* species_name[CYLGPU_MAX_SPECIES];
   int64_t npart_global[CYLGPU_MAX_SPECIES], npart_offset[CYLGPU_MAX_SPECIES], npart_local[CYLGPU_MAX_SPECIES];
   double part_extents[CYLGPU_MAX_SPECIES][6];   /* min x, y, z then max x, y, z */
+  /* real-valued constant blocks (sdf_write_srl, io/diagnostics.F90:403-416): what the driver owns and a
+   * restart needs back -- 'dt', 'window_shift_fraction', 'x_grid_min', 'elapsed_time', energies ...  Written
+   * by the rank that owns x_min; on reading, constant_value[k] is filled for every listed id that the file
+   * holds and bit k of constants_found is set */
+  int32_t n_constants;
+  uint32_t constants_found;
+  const char* constant_id[CYLGPU_SDF_MAX_CONSTANTS];
+  const char* constant_name[CYLGPU_SDF_MAX_CONSTANTS];
+  double constant_value[CYLGPU_SDF_MAX_CONSTANTS];
 } cylgpu_sdf_desc;
 /* host arrays in, no device needed: fields15[id] = complex(num) (1-ng:nx_local+ng, 1-ng:ny+ng, 0:n_mode-1)
  * for the 15 field ids above, particles_aos[s] = npart_local[s] records of 7 doubles */

@@ -48,6 +48,11 @@ int main(int argc, char **argv) {
             printf(" labels=");
             for (int k = 0; k < b->ndims; ++k) printf("%s%s", k ? "," : "", b->dim_labels[k]);
         }
+        if (b->blocktype == SDF_BLOCKTYPE_CONSTANT && b->datatype == SDF_DATATYPE_REAL8) {
+            double v;
+            memcpy(&v, b->const_value, sizeof v);
+            printf(" const=%.17g", v);
+        }
         printf("\n");
         if (b->blocktype == SDF_BLOCKTYPE_PLAIN_MESH || b->blocktype == SDF_BLOCKTYPE_POINT_MESH) {
             if (sdf_read_data(h)) { fprintf(stderr, "sdf_read_data failed on %s\n", b->id); return 1; }

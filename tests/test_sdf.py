@@ -83,7 +83,7 @@ def parse_ref(exe, path, outdir):
     for ln in lines[1:]:
         # name= may contain blanks: split on the known keys
         keys = ["n", "id", "name", "blocktype", "datatype", "ndims", "dims", "units", "mesh", "stagger", "species",
-                "geometry", "extents", "labels"]
+                "geometry", "extents", "labels", "const"]
         pos = [(ln.find(" " + k + "="), k) for k in keys if (" " + k + "=") in ln]
         pos.sort()
         b = {}
@@ -346,3 +346,42 @@ def test_derived_variable_blocks(tmp_path, cylgpu_lib):
             n += 1
     # selected but not supplied: refused
     assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None) != 0
+
+
+def test_constant_blocks_round_trip(tmp_path, cylgpu_lib):
+    """sdf_write_srl constants (io/diagnostics.F90:403-416: dt, window_shift_fraction, x_grid_min ...): read by the
+    reference's reader with their values, and handed back by the product's reader for a restart"""
+    exe, _ = ref_tools()
+    lib = _lib.load()
+    d = decks.drift(nx=20, ny=10, n_mode=1)
+    w = decks.make_oracle(d)
+    n0 = w.nparticles(0, 0)
+    desc = make_desc(w, d, 0, 1, [n0], [0], [n0])
+    consts = [(b"dt", b"Time increment", 1.25e-16), (b"window_shift_fraction", b"Window Shift Fraction", 0.375),
+              (b"x_grid_min", b"Minimum grid position", -3.5e-6)]
+    desc.n_constants = len(consts)
+    for k, (bid, name, val) in enumerate(consts):
+        desc.constant_id[k], desc.constant_name[k], desc.constant_value[k] = bid, name, val
+    fields = [np.ascontiguousarray(w.field(0, n)) for n in FIELD_NAMES]
+    parts = [np.ascontiguousarray(w.particles(0, 0).reshape(-1, 7))]
+    fp = (C.c_void_p * 15)(*[f.ctypes.data for f in fields])
+    pp = (C.c_void_p * 8)(*([parts[0].ctypes.data] + [None] * 7))
+    path = str(tmp_path / "c.sdf")
+    assert lib.cylgpu_sdf_write_host(path.encode(), C.byref(desc), fp, pp, None) == 0, lib.cylgpu_last_error()
+    hdr, blocks = parse_ref(exe, path, str(tmp_path / "out"))
+    for k, (bid, name, val) in enumerate(consts):
+        b = blocks[k]
+        assert (b["id"], b["name"], b["blocktype"], b["datatype"]) == (bid.decode(), name.decode(), "5", "4")
+        assert float(b["const"]) == val
+    assert blocks[len(consts)]["id"] == "grid"
+    # reading back: listed ids are filled and flagged, an id the file does not hold is not
+    rd = make_desc(w, d, 0, 1, [0], [0], [0])
+    want = [b"x_grid_min", b"no_such_constant", b"dt"]
+    rd.n_constants = 3
+    for k, bid in enumerate(want):
+        rd.constant_id[k] = bid
+    out = [np.zeros_like(f) for f in fields]
+    op = (C.c_void_p * 15)(*[a.ctypes.data for a in out])
+    assert lib.cylgpu_sdf_read_host(path.encode(), C.byref(rd), op, -1.0, 1.0, None, None) == 0, lib.cylgpu_last_error()
+    assert rd.constants_found == 0b101
+    assert rd.constant_value[0] == -3.5e-6 and rd.constant_value[2] == 1.25e-16
