@@ -33,6 +33,11 @@ template <class T> inline T __ldg(const T* p) { return *p; }
 
 // one emulated thread at a time: a plain read-modify-write is the atomic
 inline double atomicAdd(double* p, double v) { const double old = *p; *p = old + v; return old; }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  const unsigned long long old = *p;
+  *p = old + v;
+  return old;
+}
 
 template <class Kernel, class... Args>
 void emul_launch(Kernel kernel, dim3 grid, dim3 block, Args... args) {

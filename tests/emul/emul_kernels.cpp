@@ -20,6 +20,7 @@ namespace cylgpu {
 #include "../../cylindrical_epoch_b200/csrc/moments_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
 #include "../../cylindrical_epoch_b200/csrc/push_v0.cuh"
+#include "../../cylindrical_epoch_b200/csrc/pbcs_kernels.cuh"
 }  // namespace cylgpu
 
 using namespace cylgpu;
@@ -212,6 +213,34 @@ EMUL_API void emul_r_min_final(int nx, int ny, int M, void* const* j3) {
   g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
   g.plane = (size_t)g.SX * g.SY;
   emul_launch(k_r_min_final, dim3((g.SX + 127) / 128, M), dim3(128), g, (cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]);
+}
+
+// particle_bcs of one species on one slab: particles.cu::make_bcs_const + k_pbcs_classify.  The SoA arrays
+// are modified in place (reflection, periodic shift); hole_list / hole_flag (capacity n) receive the leavers
+// and their fate (1 left, 2 right, 3 gone); counts[0..3] = holes, left, right, gone.
+EMUL_API void emul_pbcs_classify(double* const* soa, int64_t n, const int32_t* bc_particle, double x_min, double x_max,
+                                 double x_min_local, double x_max_local, double y_max, double dx, double dy,
+                                 int x_min_boundary, int x_max_boundary, uint32_t* hole_list, uint8_t* hole_flag,
+                                 unsigned long long* counts) {
+  BcsConst B;
+  B.x_min = x_min; B.x_max = x_max;
+  B.x_min_local = x_min_local; B.x_max_local = x_max_local;
+  B.y_max = y_max;
+  double boundary_shift = dx * (double)((1 + PNG + 0) / 2);   // boundary.F90:1561-1563
+  B.x_min_outer = B.x_min - boundary_shift;
+  B.x_max_outer = B.x_max + boundary_shift;
+  boundary_shift = dy * (double)((1 + PNG + 0) / 2);
+  B.y_max_outer = B.y_max + boundary_shift;
+  B.x_shift = B.x_max - B.x_min;
+  B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
+  B.x_min_boundary = x_min_boundary;
+  B.x_max_boundary = x_max_boundary;
+  for (int k = 0; k < 4; ++k) B.bc[k] = bc_particle[k];
+  unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (n > 0)
+    emul_launch(k_pbcs_classify, dim3((unsigned)((n + 255) / 256)), dim3(256), B, soa[0], soa[1], soa[2], soa[3], soa[4],
+                soa[5], hole_list, hole_flag, (unsigned long long*)cnt, n);
+  for (int k = 0; k < 4; ++k) counts[k] = cnt[k];
 }
 
 // window_insert.cu::do_insert_particles_device for the x_max slab: returns the number of particles

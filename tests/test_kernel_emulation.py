@@ -181,3 +181,63 @@ def test_push_v0_kernel_matches_the_oracle(emul, deck_name, hc, tol):
         for cols in (slice(0, 3), slice(3, 6)):
             den = np.abs(ref[:, cols]).max()
             assert np.abs(got[:, cols] - ref[:, cols]).max() <= 1e-12 * den, (deck_name, i, cols)
+
+
+# ------------------------------------------------------------------------------------------------------
+# particle_bcs (csrc/pbcs_kernels.cuh): the boundary rules whose integer outputs -- leavers per direction,
+# removals, totals -- must equal the reference's exactly.
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("deck_name,nranks", [("drift", 1), ("thermal", 1), ("lwfa", 1), ("thermal", 2), ("lwfa", 2)])
+def test_particle_bcs_kernel_counts_and_survivors_match_the_oracle(emul, deck_name, nranks):
+    L = emul
+    L.emul_pbcs_classify.restype = None
+    L.emul_pbcs_classify.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.POINTER(C.c_int32)] + [C.c_double] * 7 + \
+        [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    d = {"drift": lambda: decks.drift(nx=20, ny=10, n_mode=1),
+         "thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=1, ppc=6, temp_k=5.0e8),   # hot: many crossings
+         "lwfa": lambda: decks.lwfa(nx=32, ny=12, n_mode=2, ppc_e=4, ppc_p=0)}[deck_name]()
+    if deck_name == "lwfa":
+        d.species[0].temp = (2.0e9, 2.0e9, 2.0e9)    # something has to leave through the open walls (2 cells out)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    moved = 0
+    for _ in range(20 if deck_name == "lwfa" else 6):
+        w.call("fields_half")
+        w.call("push_no_bcs")
+        sc = w.scalars()
+        per_rank, survivors = [], []
+        for k in range(nranks):
+            info = w.rank_info(k)
+            p = w.particles(k, 0).reshape(-1, 7)
+            soa = [np.ascontiguousarray(p[:, c]) for c in range(7)]
+            ptrs = (C.c_void_p * 7)(*[a.ctypes.data for a in soa])
+            n = p.shape[0]
+            holes = np.zeros(max(n, 1), dtype=np.uint32)
+            flags = np.zeros(max(n, 1), dtype=np.uint8)
+            cnt = (C.c_ulonglong * 4)()
+            bc = (C.c_int32 * 4)(*w.bc_particle(0))
+            L.emul_pbcs_classify(ptrs, n, bc, sc["x_min"], sc["x_max"], info["x_min_local"], info["x_max_local"],
+                                 sc["y_max"], sc["dx"], sc["dy"], int(info["x_min_boundary"]),
+                                 int(info["x_max_boundary"]), holes.ctypes.data, flags.ctypes.data, cnt)
+            nh, nl, nr_, ng = [int(v) for v in cnt]
+            assert nh == nl + nr_ + ng
+            per_rank.append((nl, nr_, ng))
+            after = np.stack(soa, axis=1)
+            moved += int((after != p).any(axis=1).sum())      # reflected / wrapped particles stay in the list
+            gone = holes[:nh][flags[:nh] == 3]
+            keep = np.ones(n, dtype=bool)
+            keep[gone] = False
+            survivors.append(after[keep])       # kept in place or on their way to a neighbour
+        w.call("particle_bcs")
+        for k in range(nranks):
+            st = w.stats(k)
+            assert per_rank[k] == (st["sent_left"], st["sent_right"], st["removed"]), (deck_name, k)
+            moved += sum(per_rank[k])
+        got = decks.sort_particles(np.concatenate(survivors))
+        ref = decks.sort_particles(np.concatenate([w.particles(k, 0).reshape(-1, 7) for k in range(nranks)]))
+        assert got.shape == ref.shape
+        assert np.array_equal(got, ref)     # reflection / periodic shift reproduce the oracle's arithmetic bit for bit
+        w.call("current_finish")
+        w.call("advance_half_time"); w.call("advance_half_time")
+        w.call("fields_final")
+    assert moved > 0, "the deck never exercised a boundary"
