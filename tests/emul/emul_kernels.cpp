@@ -21,6 +21,7 @@ namespace cylgpu {
 #include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
 #include "../../cylindrical_epoch_b200/csrc/push_v0.cuh"
 #include "../../cylindrical_epoch_b200/csrc/pbcs_kernels.cuh"
+#include "../../cylindrical_epoch_b200/csrc/field_kernels.cuh"
 }  // namespace cylgpu
 
 using namespace cylgpu;
@@ -213,6 +214,32 @@ EMUL_API void emul_r_min_final(int nx, int ny, int M, void* const* j3) {
   g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
   g.plane = (size_t)g.SX * g.SY;
   emul_launch(k_r_min_final, dim3((g.SX + 127) / 128, M), dim3(128), g, (cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]);
+}
+
+// update_e_field / update_b_field of one slab without boundary conditions (fields.cu::launch_update_e / _b).
+// f9: exm erm etm bxm brm btm jxm jrm jtm, complex with ghosts, updated in place.
+EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f9, double dx, double dy, double dt,
+                                double y_grid_min_local) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  cplx* f[9];
+  for (int k = 0; k < 9; ++k) f[k] = (cplx*)f9[k];
+  const dim3 blk(128);
+  if (which == 0) {
+    emul_launch(k_update_e_bulk, dim3((g.nx + 1 + 127) / 128, g.ny, g.M), blk, g, f[0], f[1], f[2], (const cplx*)f[3],
+                (const cplx*)f[4], (const cplx*)f[5], (const cplx*)f[6], (const cplx*)f[7], (const cplx*)f[8], dx, dy, dt,
+                y_grid_min_local);
+    emul_launch(k_update_e_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[0], f[1], f[2], (const cplx*)f[5],
+                (const cplx*)f[6], dy, dt);
+  } else {
+    if (g.ny > 1)
+      emul_launch(k_update_b_bulk, dim3((g.nx + 1 + 127) / 128, g.ny - 1, g.M), blk, g, f[3], f[4], f[5], (const cplx*)f[0],
+                  (const cplx*)f[1], (const cplx*)f[2], dx, dy, dt, y_grid_min_local);
+    emul_launch(k_update_b_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[3], f[4], f[5], (const cplx*)f[0],
+                (const cplx*)f[2], dx, dy, dt);
+  }
 }
 
 // particle_bcs of one species on one slab: particles.cu::make_bcs_const + k_pbcs_classify.  The SoA arrays
