@@ -141,6 +141,80 @@ EMUL_API int emul_particle_moment(int nx, int ny, int kind, int direction, int n
   return 0;
 }
 
+// The density / averaged moments on TWO slabs that are x neighbours (slab 0 owns x_min, slab 1 owns x_max;
+// periodic: they are also each other's outer neighbours, as in a 2-rank ring): deposit, reflection, the
+// additive ghost exchange of moments.cuh::moment_summation_bcs with the send / receive flags of the product,
+// zero-gradient fill, finish.  kind: one of the k_moment_deposit moments.  soa[k]: 7 arrays of slab k.
+EMUL_API int emul_moment_two_slabs(const int* nx2, int ny, int kind, int direction, const double* const* soa,
+                                   const int64_t* n2, double mass, double charge, const double* x_grid_min_local2,
+                                   double y_grid_min_local, double dx, double dy, const int32_t* bca,
+                                   const int32_t* bc_field, double* const* out2) {
+  const bool averaged = (kind == CYLGPU_MOM_EKBAR || kind == CYLGPU_MOM_EKFLUX || kind == CYLGPU_MOM_AVERAGE_MOMENTUM);
+  if (!(averaged || kind == CYLGPU_MOM_MASS_DENSITY || kind == CYLGPU_MOM_NUMBER_DENSITY ||
+        kind == CYLGPU_MOM_SPECIES_CURRENT)) return 2;
+  Geom g[2];
+  std::vector<cplx> A[2];
+  std::vector<cplx> sl[2], sr[2];
+  const bool periodic = bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  for (int k = 0; k < 2; ++k) {
+    g[k].nx = nx2[k]; g[k].ny = ny; g[k].M = 1;
+    g[k].SX = nx2[k] + 2 * NG; g[k].SY = ny + 2 * NG;
+    g[k].plane = (size_t)g[k].SX * g[k].SY;
+    A[k].assign(g[k].plane, C(0.0, 0.0));
+    MomentArgs a;
+    a.x = soa[7 * k + 0]; a.y = soa[7 * k + 1]; a.z = soa[7 * k + 2];
+    a.px = soa[7 * k + 3]; a.py = soa[7 * k + 4]; a.pz = soa[7 * k + 5]; a.w = soa[7 * k + 6];
+    a.n = n2[k];
+    a.x_grid_min_local = x_grid_min_local2[k]; a.y_grid_min_local = y_grid_min_local;
+    a.dx = dx; a.dy = dy; a.mass = mass; a.charge = charge; a.kind = kind; a.direction = direction;
+    if (a.n > 0) emul_launch(k_moment_deposit, dim3((unsigned)((a.n + 255) / 256)), dim3(256), g[k], a, (double*)A[k].data());
+    const bool xminb = (k == 0), xmaxb = (k == 1);
+    const dim3 gx_((g[k].SY + 127) / 128, 1), gy_((g[k].SX + 127) / 128, 1);
+    if (xminb && bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_X_MIN);
+    if (xmaxb && bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_X_MAX);
+    if (bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gy_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_Y_MAX);
+  }
+  // pack on both slabs, then each unpacks what its neighbours sent (moments.cuh: to_l / to_r)
+  bool to_l[2], to_r[2];
+  const size_t elems = (size_t)3 * g[0].SY * NG;
+  for (int k = 0; k < 2; ++k) {
+    const bool xminb = (k == 0), xmaxb = (k == 1);
+    const bool has_l = !xminb || periodic, has_r = !xmaxb || periodic;   // decomp: the ring closes only when periodic
+    to_l[k] = has_l && !(xminb && bca[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC);
+    to_r[k] = has_r && !(xmaxb && bca[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC);
+    sl[k].assign(elems, C(0.0, 0.0)); sr[k].assign(elems, C(0.0, 0.0));
+    Halo3 h;
+    h.f[0] = A[k].data(); h.f[1] = nullptr; h.f[2] = nullptr;
+    h.skip[0] = h.skip[1] = h.skip[2] = 0;
+    const dim3 grd((g[k].SY * NG + 127) / 128, 1, 3);
+    if (to_l[k] || to_r[k])
+      emul_launch(k_halo_pack, grd, dim3(128), g[k], h, to_l[k] ? sl[k].data() : (cplx*)nullptr,
+                  to_r[k] ? sr[k].data() : (cplx*)nullptr, 1, elems);
+  }
+  for (int k = 0; k < 2; ++k) {
+    const int other = 1 - k;   // left and right neighbour of a 2-ring are the same slab
+    Halo3 h;
+    h.f[0] = A[k].data(); h.f[1] = nullptr; h.f[2] = nullptr;
+    h.skip[0] = h.skip[1] = h.skip[2] = 0;
+    const dim3 grd((g[k].SY * NG + 127) / 128, 1, 3);
+    // what arrives from my left is my left neighbour's right-going message, and vice versa
+    const cplx* recv_l = to_l[k] ? sr[other].data() : nullptr;
+    const cplx* recv_r = to_r[k] ? sl[other].data() : nullptr;
+    if (recv_l || recv_r) emul_launch(k_halo_unpack, grd, dim3(128), g[k], h, recv_l, recv_r, 1, elems);
+  }
+  for (int k = 0; k < 2; ++k) {
+    const bool xminb = (k == 0), xmaxb = (k == 1);
+    const dim3 gx_((g[k].SY + 127) / 128, 1), gy_((g[k].SX + 127) / 128, 1);
+    if (bc_field[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC && xminb) emul_launch(k_density_zero_gradient, gx_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_X_MIN);
+    if (bc_field[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC && xmaxb) emul_launch(k_density_zero_gradient, gx_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_X_MAX);
+    if (bc_field[CYLGPU_BD_Y_MIN] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_Y_MIN);
+    if (bc_field[CYLGPU_BD_Y_MAX] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g[k], A[k].data(), (int)CYLGPU_BD_Y_MAX);
+    emul_launch(k_moment_finish, dim3((unsigned)((g[k].plane + 255) / 256)), dim3(256), (const cplx*)A[k].data(), out2[k],
+                g[k].plane, averaged ? 1 : 0, 1.0);
+  }
+  return 0;
+}
+
 // push_particles without particle_bcs for one species of one slab (cylgpu_push_no_bcs with push variant 0):
 // the radial tables of particles.cu::build_tables, the PushConst of push_species, k_push_v0<M> over the list
 // and k_r_min_final.  fields: the six E/B mode arrays, jx/jr/jt: zeroed J arrays to deposit into (complex,

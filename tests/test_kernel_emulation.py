@@ -273,3 +273,44 @@ def test_field_update_kernels_match_the_oracle(emul, n_mode):
         for name, a in zip(names[:6], mine):
             ref = w.field(0, name)
             assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (op, name, n_mode)
+
+
+@pytest.mark.parametrize("deck_name", ["thermal", "lwfa", "drift"])
+def test_moment_exchange_between_two_slabs(emul, deck_name):
+    """the additive ghost exchange of the moments between x neighbours (k_halo_pack / k_halo_unpack with the
+    single-plane geometry and the product's send / receive flags), periodic ring and open / reflecting ends"""
+    L = emul
+    L.emul_moment_two_slabs.restype = C.c_int
+    L.emul_moment_two_slabs.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_int64), C.c_double, C.c_double, C.POINTER(C.c_double), C.c_double,
+                                        C.c_double, C.c_double, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_void_p)]
+    d = {"thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=6),
+         "lwfa": lambda: decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=0),
+         "drift": lambda: decks.drift(nx=20, ny=10, n_mode=2)}[deck_name]()
+    w = decks.make_oracle(d, nranks=2)
+    w.call("init_half_step")
+    w.step(3)
+    sc = w.scalars()
+    infos = [w.rank_info(k) for k in range(2)]
+    soa = []
+    for k in range(2):
+        p = w.particles(k, 0).reshape(-1, 7)
+        soa += [np.ascontiguousarray(p[:, c]) for c in range(7)]
+    ptrs = (C.c_void_p * 14)(*[a.ctypes.data for a in soa])
+    nx2 = (C.c_int * 2)(infos[0]["nx"], infos[1]["nx"])
+    n2 = (C.c_int64 * 2)(w.nparticles(0, 0), w.nparticles(1, 0))
+    xg = (C.c_double * 2)(infos[0]["x_grid_min_local"], infos[1]["x_grid_min_local"])
+    bca = (C.c_int32 * 4)(*w.bc_particle(0))
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    sp = d.species[0]
+    for kind, direction in (("number_density", 0), ("species_current", 1), ("ekbar", 0), ("average_momentum", 3)):
+        outs = [np.zeros((d.ny + 2 * po.NG, infos[k]["nx"] + 2 * po.NG)) for k in range(2)]
+        op = (C.c_void_p * 2)(*[o.ctypes.data for o in outs])
+        rc = L.emul_moment_two_slabs(nx2, d.ny, po.MOMENTS[kind], direction, ptrs, n2, sp.mass, sp.charge, xg,
+                                     sc["y_grid_min_local"], sc["dx"], sc["dy"], bca, bcf, op)
+        assert rc == 0
+        ref = w.moment(kind, 0, direction)
+        scale = max(np.abs(r).max() for r in ref)
+        for k in range(2):
+            assert np.abs(outs[k] - ref[k]).max() <= 1e-13 * scale, (deck_name, kind, k)
