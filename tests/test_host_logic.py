@@ -170,3 +170,71 @@ def test_two_rank_exchange_protocol_gloo(periodic):
     for rank, ok_halo, ok_p in res:
         assert ok_halo, f"rank {rank}: halo columns differ from the oracle's field_mode_bc"
         assert ok_p, f"rank {rank}: particle payload exchange wrong"
+
+
+# ------------------------------------------------------------------ host mirror of the round-1e entry points
+class _FakeLib:
+    """stands in for libcylgpu.so: records the calls of the host mirror and returns success"""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def fn(*args):
+            self.calls.append((name, args))
+            return 0
+        return fn
+
+
+def _stub_slab(move_window=False):
+    d = decks.lwfa(nx=32, ny=24, ppc_e=4, ppc_p=1, window=move_window)
+    s = hotpath.Slab.__new__(hotpath.Slab)
+    s.L = _FakeLib()
+    s.h = None
+    s.grid = decomp.SlabGrid(32, 24, 1, 0, d.x_min, d.x_max, d.y_max)
+    s.n_mode = 2
+    s.species = decks.product_species(d)
+    s.lasers = []
+    s.dt, s.time, s.step = s.grid.dt, 1.5e-15, 12
+    s.window_shift_fraction, s.window_started, s.window_shifts_total = 0.25, True, 7
+    s.device_insert_seed, s.insert_fn = 99, None
+    return s
+
+
+def test_host_mirror_builds_the_sdf_descriptor_and_moment_calls():
+    import ctypes as C
+    s = _stub_slab()
+    d = s.sdf_dump("/tmp/x.sdf", ["electron", "proton"], npart_global=[10, 4], npart_offset=[3, 1], restart=True,
+                   derived=("number_density", "temperature_x", "ekflux/y_min", "number_density_mode"))
+    name, args = s.L.calls[-1]
+    assert name == "cylgpu_sdf_dump" and args[1] == b"/tmp/x.sdf"
+    assert (d.nx_global, d.ny_global, d.n_mode, d.n_species, d.nx_local, d.cell_x_min) == (32, 24, 2, 2, 32, 1)
+    assert (d.step, d.restart) == (12, 1) and d.time == 1.5e-15
+    assert d.derived_mask == (1 << 3) | (1 << 10) | (1 << 20) | (1 << 22) and d.derived_sum == 1 and d.derived_species == 1
+    assert [d.species_name[i] for i in range(2)] == [b"electron", b"proton"]
+    assert list(d.npart_global)[:2] == [10, 4] and list(d.npart_offset)[:2] == [3, 1]
+    assert d.n_constants == 5 and d.constant_id[1] == b"window_shift_fraction" and d.constant_value[1] == 0.25
+    assert d.constant_value[0] == s.dt and d.constant_value[2] == s.grid.x_grid_min
+    assert (d.x_min, d.dx, d.dy) == (s.grid.xb_min, s.grid.dx, s.grid.dy)
+    # restart: the loader's descriptor lists the same constants; the mirror re-derives the ghosts afterwards
+    s.L.calls.clear()
+    s.sdf_load("/tmp/x.sdf", ["electron", "proton"])
+    names = [c[0] for c in s.L.calls]
+    assert names[0] == "cylgpu_sdf_load"
+    assert names[1:4] == ["cylgpu_efield_bcs", "cylgpu_bfield_bcs", "cylgpu_current_finish"]
+    # moments: kind / species / direction reach the C-ABI as the enum of include/cylgpu.h
+    s.L.calls.clear()
+    a = s.moment("species_current", 1, 3)
+    name, args = s.L.calls[-1]
+    assert name == "cylgpu_particle_moment" and args[1:4] == (7, 1, 3) and a.shape == (24 + 10, 32 + 10)
+
+
+def test_host_mirror_device_insertion_uses_the_shift_counter_as_column():
+    s = _stub_slab(move_window=True)
+    s.move_window = True
+    s._shift_window_once()
+    ins = [c for c in s.L.calls if c[0] == "cylgpu_insert_particles_device"]
+    assert len(ins) == 2                       # both species of the deck, in deck order
+    for isp, (_, args) in enumerate(ins):
+        assert args[1] == isp and args[9] == 99 and args[10] == 7      # seed, column = shifts made so far
+    assert s.L.calls[-1][0] == "cylgpu_window_shift" and s.window_shifts_total == 8
