@@ -311,6 +311,8 @@ def run_ours(args, wl_name, wl):
     slab.L.cylgpu_set_timing(slab.h, 1)
     if "BENCH_VARIANT" in os.environ:
         slab.set_push_variant(int(os.environ["BENCH_VARIANT"]))
+    if os.environ.get("BENCH_DEFERRED_BCS", "0") == "1":   # opt-in: particle_bcs completes behind the field phases
+        slab.set_deferred_bcs(True)
     if "BENCH_SORT_INTERVAL" in os.environ:
         slab.set_sort_interval(int(os.environ["BENCH_SORT_INTERVAL"]))
 

@@ -19,11 +19,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-static int check_handle(cylgpu_handle h) {
+// entry points that never look at particle state (field phases, current_finish, field boundary pieces): a
+// deferred particle_bcs stays outstanding across them -- that is the point of deferring it
+static int check_handle_fields(cylgpu_handle h) {
   if (!h) { set_error("null cylgpu handle"); return 1; }
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)); return 1; }
   return 0;
+}
+// everything else first finishes what cylgpu_push left outstanding (no-op unless cylgpu_set_deferred_bcs)
+static int check_handle(cylgpu_handle h) {
+  TRY(check_handle_fields(h));
+  return complete_pending_bcs(h);
 }
 
 static void set_neighbours(cylgpu_ctx* c) {
@@ -136,6 +143,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   c->timers.destroy();
   if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+  if (c->pending.ev) cudaEventDestroy(c->pending.ev);
   if (c->ins_pin) cudaFreeHost(c->ins_pin);
   cudaFree(c->ins_dev);
   if (c->ins_ev) cudaEventDestroy(c->ins_ev);
@@ -168,7 +176,7 @@ int cylgpu_set_species(cylgpu_handle c, int isp, const cylgpu_species* sp) {
 }
 
 int cylgpu_set_dt(cylgpu_handle c, double dt) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   c->dt = dt;
   c->graph_epoch += 1;
   return 0;
@@ -327,6 +335,7 @@ int cylgpu_download_particles(cylgpu_handle c, int isp, int64_t capacity, double
 
 int cylgpu_particle_count(cylgpu_handle c, int isp, int64_t* n_out) {
   if (!c || isp < 0 || isp >= c->cfg.n_species || !n_out) { set_error("bad argument"); return 2; }
+  TRY(complete_pending_bcs(c));   // a deferred particle_bcs still owes its departures and arrivals
   *n_out = c->species[isp].n;
   return 0;
 }
@@ -343,17 +352,17 @@ void* cylgpu_particle_device_ptr(cylgpu_handle c, int isp, int comp) {
 }
 
 // ---- hot path ----
-int cylgpu_update_e_field(cylgpu_handle c) { TRY(check_handle(c)); return launch_update_e(c); }
-int cylgpu_update_b_field(cylgpu_handle c) { TRY(check_handle(c)); return launch_update_b(c); }
-int cylgpu_efield_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_efield_bcs(c); }
-int cylgpu_bfield_bcs(cylgpu_handle c, int mpi_only) { TRY(check_handle(c)); return do_bfield_bcs(c, mpi_only != 0); }
+int cylgpu_update_e_field(cylgpu_handle c) { TRY(check_handle_fields(c)); return launch_update_e(c); }
+int cylgpu_update_b_field(cylgpu_handle c) { TRY(check_handle_fields(c)); return launch_update_b(c); }
+int cylgpu_efield_bcs(cylgpu_handle c) { TRY(check_handle_fields(c)); return do_efield_bcs(c); }
+int cylgpu_bfield_bcs(cylgpu_handle c, int mpi_only) { TRY(check_handle_fields(c)); return do_bfield_bcs(c, mpi_only != 0); }
 int cylgpu_bfield_final_bcs(cylgpu_handle c, const double* a, const double* b, const double* d, const double* e) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   return do_bfield_final_bcs(c, a, b, d, e);
 }
 int cylgpu_particle_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_particle_bcs(c); }
 int cylgpu_push_no_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_push(c); }
-int cylgpu_current_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_current_bcs(c); }
+int cylgpu_current_bcs(cylgpu_handle c) { TRY(check_handle_fields(c)); return do_current_bcs(c); }
 int cylgpu_sort_particles(cylgpu_handle c) { TRY(check_handle(c)); return do_sort(c); }
 int cylgpu_set_pusher(cylgpu_handle c, int higuera_cary) { TRY(check_handle(c)); c->hc_push = higuera_cary != 0; return 0; }
 int cylgpu_set_sort_interval(cylgpu_handle c, int n) { TRY(check_handle(c)); c->sort_interval = n; return 0; }
@@ -422,7 +431,7 @@ static int fields_half_body(cylgpu_ctx* c) {
 
 // fields.f90:316-337
 int cylgpu_fields_half(cylgpu_handle c) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   PhaseTimer t(c, &c->stats.ms_fields);
   return run_field_phase(c, 0, [c]() { return fields_half_body(c); });
 }
@@ -466,7 +475,7 @@ int cylgpu_set_current_smoothing(cylgpu_handle c, int enable, int its, int comp_
 }
 
 int cylgpu_current_finish(cylgpu_handle c) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   PhaseTimer t(c, &c->stats.ms_bcs);
   return run_field_phase(c, 2, [c]() { return do_current_finish(c); });
 }
@@ -474,7 +483,7 @@ int cylgpu_current_finish(cylgpu_handle c) {
 // fields.f90:341-353
 int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2min, const double* s1max,
                         const double* s2max) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   PhaseTimer t(c, &c->stats.ms_fields);
   TRY(upload_laser_sources(c, s1min, s2min, s1max, s2max));
   return run_field_phase(c, 1, [c]() -> int {
@@ -525,7 +534,7 @@ int cylgpu_rng_get_state(cylgpu_handle c, int32_t* xyzw, int* cached, double* ca
   return 0;
 }
 int cylgpu_rng_flush_cache(cylgpu_handle c) {   // random_flush_cache, called by output_routines every step
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));   // host-side generator state only: a deferred particle_bcs stays outstanding
   c->rng.cached = 0;
   return 0;
 }
@@ -729,6 +738,14 @@ int cylgpu_reset_stats(cylgpu_handle c) {
   c->stats.ms_fields = c->stats.ms_push = c->stats.ms_bcs = c->stats.ms_sort = c->stats.ms_exchange = 0.0;
   c->stats.ms_push_kernel = 0.0;
   c->stats.n_push_kernel = 0;
+  return 0;
+}
+// opt-in: cylgpu_push returns without waiting for the leaver counts of the last species; the rest of its
+// particle_bcs runs at the next call that touches particle state (see ctx.cuh PendingBcs).  Results are
+// the same; with several ranks every rank must make the same sequence of calls (the completion exchanges).
+int cylgpu_set_deferred_bcs(cylgpu_handle c, int on) {
+  TRY(check_handle(c));
+  c->deferred_bcs = on != 0;
   return 0;
 }
 int cylgpu_set_timing(cylgpu_handle c, int on) {

@@ -181,6 +181,17 @@ struct cylgpu_ctx {
   bool timing = true;
   bool blocking_wait = false;     // host syncs yield the core instead of spinning (multi-rank hosts)
   cudaEvent_t ev_wait = nullptr;
+  // Deferred completion of particle_bcs (cylgpu_set_deferred_bcs, opt-in): cylgpu_push enqueues the push
+  // kernel and the copy of its leaver counts and returns; the count sync, compaction, exchange and arrivals
+  // of the LAST species happen when the next call that touches particle state comes in -- after the host has
+  // enqueued current_finish and the field phases, so the device never waits for the host behind the sync.
+  bool deferred_bcs = false;
+  struct PendingBcs {
+    bool active = false;
+    int isp = -1;
+    cudaEvent_t ev = nullptr;        // recorded behind the device->host copy of the counters
+    unsigned char B[160];            // the BcsConst of the push (particles.cu), opaque here
+  } pending;
 };
 
 namespace cylgpu {
@@ -208,6 +219,7 @@ int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip
 // particles.cu
 int do_push(cylgpu_ctx* c);
 int do_push_bcs(cylgpu_ctx* c);
+int complete_pending_bcs(cylgpu_ctx* c);   // no-op unless a deferred particle_bcs is outstanding
 int do_particle_bcs(cylgpu_ctx* c);
 int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
                  int64_t* n_out);

@@ -5,6 +5,7 @@
 // remove_particles (window.F90:304-325).
 #include <algorithm>
 #include <cmath>
+#include <cstring>
 
 #include "push.cuh"
 #include "deposit_mma.cuh"
@@ -754,7 +755,7 @@ static int grow_dbuf_keep(double** p, int64_t* cap, int64_t need, int64_t keep, 
 // classification, removal of the leavers (hole filling) and packing of the migrants behind the
 // `off_l` / `off_r` particles already waiting in psend_l / psend_r.  One host sync (the counts).
 static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off_l, int64_t off_r, int64_t* nleft_out,
-                                 int64_t* nright_out, bool classified_by_push = false) {
+                                 int64_t* nright_out, bool classified_by_push = false, bool counts_ready = false) {
   unsigned long long* cnt = c->counters;        // 8 for classify
   unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
   cylgpu::SpeciesState& S = c->species[isp];
@@ -768,9 +769,11 @@ static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off
       c->stats.kernel_launches += 1;
     }
   }
-  CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                           c->stream));
-  TRY(host_wait(c));
+  if (!counts_ready) {   // (deferred completion: the copy was enqueued behind the push kernel and has been waited for)
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                             c->stream));
+    TRY(host_wait(c));
+  }
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
@@ -817,10 +820,10 @@ static int pbcs_exchange(cylgpu_ctx* c, int64_t nleft, int64_t nright, int64_t* 
 }
 
 // particle_bcs of one species: (classification,) compaction, exchange, arrivals appended
-static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classified_by_push) {
+static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classified_by_push, bool counts_ready = false) {
   cylgpu::SpeciesState& S = c->species[isp];
   int64_t nleft = 0, nright = 0, from_l = 0, from_r = 0;
-  TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright, classified_by_push));
+  TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright, classified_by_push, counts_ready));
   TRY(pbcs_exchange(c, nleft, nright, &from_l, &from_r));
   // the reference receives from the right neighbour first (ix = -1 iteration), then left
   const int64_t nrecv = from_l + from_r;
@@ -857,11 +860,26 @@ int do_push_bcs(cylgpu_ctx* c) {
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  int last = -1;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) if (c->species[isp].set) last = isp;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     if (!c->species[isp].set) continue;
     bool fused = false;
     TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
-    TRY(pbcs_species(c, isp, B, fused));
+    if (c->deferred_bcs && fused && isp == last) {
+      // the leaver counts start their way to the host right behind the kernel; nobody waits for them here
+      static_assert(sizeof(BcsConst) <= sizeof(c->pending.B), "PendingBcs::B too small");
+      CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                               c->stream));
+      if (!c->pending.ev)
+        CUDA_TRY(cudaEventCreateWithFlags(&c->pending.ev, cudaEventBlockingSync | cudaEventDisableTiming));
+      CUDA_TRY(cudaEventRecord(c->pending.ev, c->stream));
+      memcpy(c->pending.B, &B, sizeof(BcsConst));
+      c->pending.isp = isp;
+      c->pending.active = true;
+    } else {
+      TRY(pbcs_species(c, isp, B, fused));
+    }
   }
   if (need_sort) {
     c->sorted_valid = true;
@@ -870,6 +888,20 @@ int do_push_bcs(cylgpu_ctx* c) {
   }
   c->pushes_since_sort += 1;
   return do_r_min_final(c);
+}
+
+// The second half of a deferred particle_bcs: by now the host has enqueued current_finish and the field
+// phases behind the push kernel, so the counts are usually waiting already and the device has work queued
+// while the compaction, the exchange and the next sort are being enqueued.  Every entry point that touches
+// particle state comes through here first (api.cu::check_handle); the grid, the boundary conditions and the
+// scratch buffers of the push are therefore still those the kernel classified with.
+int complete_pending_bcs(cylgpu_ctx* c) {
+  if (!c->pending.active) return 0;
+  c->pending.active = false;
+  CUDA_TRY(cudaEventSynchronize(c->pending.ev));
+  BcsConst B;
+  memcpy(&B, c->pending.B, sizeof(BcsConst));
+  return pbcs_species(c, c->pending.isp, B, true, true);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -388,6 +388,11 @@ class Slab:
     def set_pusher(self, higuera_cary):       # -DHC_PUSH, particles.F90:409-421
         self._ck(self.L.cylgpu_set_pusher(self.h, int(bool(higuera_cary))))
 
+    def set_deferred_bcs(self, on):
+        """cylgpu_push returns before the leaver counts are known; particle_bcs completes at the next call that
+        touches particle state (opt-in; removes the device idle time behind the step's host sync)"""
+        self._ck(self.L.cylgpu_set_deferred_bcs(self.h, int(bool(on))))
+
     def set_sort_interval(self, n):
         self._ck(self.L.cylgpu_set_sort_interval(self.h, n))
 

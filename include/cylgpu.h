@@ -344,6 +344,12 @@ int cylgpu_sdf_load(cylgpu_handle h, const char* path, cylgpu_sdf_desc* d);
 int cylgpu_energy(cylgpu_handle h, double* out2);
 int cylgpu_stats(cylgpu_handle h, cylgpu_stats_t* out);
 int cylgpu_reset_stats(cylgpu_handle h);
+/* Opt-in: cylgpu_push enqueues the push and returns without waiting for the leaver counts of the last
+ * species; the count sync, compaction, exchange and arrivals (the rest of particle_bcs) run at the next call
+ * that touches particle state, i.e. after the host has enqueued current_finish and the field phases.  Same
+ * results, no device idle time behind the host sync.  With several ranks every rank must make the same
+ * sequence of calls (the completion contains the neighbour exchange).  Default off. */
+int cylgpu_set_deferred_bcs(cylgpu_handle h, int on);
 /* per-phase CUDA-event timers in cylgpu_stats (adds a host sync per phase); default off */
 int cylgpu_set_timing(cylgpu_handle h, int on);
 
