@@ -11,6 +11,17 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.dirname(os.path.abspath(__
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "timeout: per-test time limit (pytest-timeout)")
+
+
+def pytest_collection_modifyitems(config, items):
+    """Every GPU test gets a time limit (pytest-timeout, when installed): a multi-slab test that ever blocked in
+    an exchange must fail, not hang the run.  The full-size property tests are the slowest (numpy over
+    33.5 M particles on the host)."""
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            limit = 1500 if "fullsize" in item.nodeid else 600
+            item.add_marker(pytest.mark.timeout(limit))
 
 
 @pytest.fixture(scope="session")

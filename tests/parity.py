@@ -94,7 +94,8 @@ class Pair:
                 fn(s)
             except Exception as e:   # noqa: BLE001
                 errs.append(e)
-        ts = [threading.Thread(target=run, args=(s,)) for s in self.slabs]
+        # daemon: a slab thread stuck in an exchange must not keep the interpreter alive after a test timed out
+        ts = [threading.Thread(target=run, args=(s,), daemon=True) for s in self.slabs]
         for t in ts:
             t.start()
         for t in ts:
