@@ -4,7 +4,7 @@ CPU through the emulation shim of tests/emul/ and compared with the oracle.
 
 Why: the container these kernels were written in has no GPU and the round's GPU budget was spent,
 so this is the check of their arithmetic and indexing that could be made before their first run on
-a B200 (tests/test_zz_gpu_*.py are the parity tests proper, through the C-ABI).  It is test
+a B200 (tests/test_zz*_gpu_*.py are the parity tests proper, through the C-ABI).  It is test
 infrastructure, not a CPU path of the product: nothing under cylindrical_epoch_b200/ uses it.
 """
 import ctypes as C

@@ -1,5 +1,5 @@
 """The vectorised property checkers of tests/properties.py against the oracle at small size:
-what the full-size GPU tests (tests/test_zz_gpu_fullsize.py) rely on."""
+what the full-size GPU tests (tests/test_zz5_gpu_fullsize.py) rely on."""
 import numpy as np
 
 import decks

@@ -1,9 +1,10 @@
 """GPU parity of the calc_df.F90 particle moments (cylgpu_particle_moment, csrc/moments.cuh)
 against the oracle (oracle/cyl_moments.cpp), through the C-ABI.
 
-This file sorts after the other test modules on purpose: it was written after the round's GPU
-budget was spent, so its first run on a B200 is the driver's; under `pytest -x` a failure here
-cannot hide the results of the parity tests that were run on the GPU during development.
+The test_zz<n>_gpu_* modules sort after the other test modules on purpose: they were written after the
+round's GPU budget was spent, so their first run on a B200 is the driver's; under `pytest -x` a failure
+here cannot hide the results of the parity tests that were run on the GPU during development.  They are
+numbered by confidence: first those whose kernels were checked on the CPU by the emulation tests.
 """
 import numpy as np
 import pytest

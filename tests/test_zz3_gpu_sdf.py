@@ -3,7 +3,7 @@ the device mirrors equals the file the host-level writer produces from the oracl
 tests/test_sdf.py checks through the reference's own reader), and a run restarted from it continues
 like the uninterrupted one.
 
-Sorts after the other test modules on purpose (see tests/test_zz_gpu_moments.py): written after
+Sorts after the other test modules on purpose (see tests/test_zz1_gpu_moments.py): written after
 the round's GPU budget was spent, first run on a B200 is the driver's.
 """
 import numpy as np

@@ -2,7 +2,7 @@
 deck's own design target): the laser source with a phase function of r evaluated by the host mirror, the
 per-mode FDTD and the outflow boundaries over 300 steps of a 500 x 100 vacuum grid.
 
-Sorts after the other test modules on purpose (see tests/test_zz_gpu_moments.py): written after
+Sorts after the other test modules on purpose (see tests/test_zz1_gpu_moments.py): written after
 the round's GPU budget was spent, first run on a B200 is the driver's.
 """
 import pytest

@@ -3,7 +3,7 @@ cannot run these sizes in seconds): the integral Gauss law of the charge-conserv
 frozen to rounding, particle totals and the multiset of carried weights preserved by the sort /
 push / boundary passes, migration counts adding up, energy drift bounded.
 
-Sorts after the other test modules on purpose (see tests/test_zz_gpu_moments.py): written after
+Sorts after the other test modules on purpose (see tests/test_zz1_gpu_moments.py): written after
 the round's GPU budget was spent, first run on a B200 is the driver's.  The checkers themselves
 are validated against the oracle on the CPU in tests/test_properties_cpu.py.
 """

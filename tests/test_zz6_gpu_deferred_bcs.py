@@ -2,7 +2,7 @@
 (count sync, compaction, neighbour exchange, arrivals) runs at the next call that touches particle state --
 after current_finish and the field phases have been enqueued.  Results must be those of the ordinary order.
 
-Sorts after the other test modules on purpose (see tests/test_zz_gpu_moments.py): written after the round's
+Sorts after the other test modules on purpose (see tests/test_zz1_gpu_moments.py): written after the round's
 GPU budget was spent, first run on a B200 is the driver's.  The mode is opt-in and off by default.
 """
 import numpy as np

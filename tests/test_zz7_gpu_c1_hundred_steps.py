@@ -2,7 +2,7 @@
 16 + 4 particles per cell, laser from x_min -- for the N = 10 and N = 100 steps of SURVEY.md section 8(d)'s
 parity report: integer outputs exact, fields / currents / phase space within the stated tolerance.
 
-Sorts after the other test modules on purpose (see tests/test_zz_gpu_moments.py): added after the round's
+Sorts after the other test modules on purpose (see tests/test_zz1_gpu_moments.py): added after the round's
 GPU budget was spent; it only exercises paths the earlier parity tests verified on B200s, at a size and
 step count they did not reach (the oracle needs about a minute for it).
 """
