@@ -41,6 +41,11 @@ def test_particle_moments(deckname, nranks):
     p = Pair(d, nranks=nranks)
     try:
         p.step(5)
+        # the diagnostics are compared on IDENTICAL particle sets: the oracle's lists go to the device (the
+        # parity of the stepping itself is the business of tests/test_gpu_parity.py)
+        for k, s in enumerate(p.slabs):
+            for isp in range(len(d.species)):
+                s.upload_particles(isp, p.oracle.particles(k, isp))
         for kind, direction in CASES:
             for isp in [-1] + list(range(len(d.species))):
                 ref = p.oracle.moment(kind, isp, direction)
