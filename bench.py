@@ -41,6 +41,9 @@ WORKLOADS = {
     # BASELINE.json configs[2]: laser wakefield, moving window at c, open boundaries (x-slabs over the GPUs)
     "lwfa_8192x512_m2_ppc32": dict(nx=8192, ny=512, n_mode=2, ppc=32, kind="lwfa"),
     "lwfa_1024x128_m2_ppc16": dict(nx=1024, ny=128, n_mode=2, ppc=16, kind="lwfa"),
+    # BASELINE.json configs[4], weak scaling: 4096 x 1024 per GPU at 60 ppc = 2.5e8 particles per GPU (2e9 on 8);
+    # 14 GB of particles per GPU and as much pinned host memory for the e2e leg -- not yet run on a B200
+    "lwfa_4096x1024_m2_ppc60": dict(nx=4096, ny=1024, n_mode=2, ppc=60, kind="lwfa"),
 }
 DEFAULT_WORKLOAD = "thermal_2048x256_m2_ppc64"
 
