@@ -402,7 +402,8 @@ def run_ours(args, wl_name, wl):
                                                             % (slab.window_shifts_total - shifts0) if lwfa
                                                             else "periodic ring"),
                    "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2; no flush needed" % (n0 * 56 / 1e9),
-                   "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host},
+                   "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host,
+                   "deferred_particle_bcs": os.environ.get("BENCH_DEFERRED_BCS", "0") == "1"},
         "field_cell_mode_updates_per_s": field_rate,
         "phase_ms_per_step": {"fields": st.ms_fields / args.steps, "push_total": st.ms_push / args.steps,
                               "push_kernel": st.ms_push_kernel / args.steps, "sort": st.ms_sort / args.steps,
