@@ -392,73 +392,6 @@ int do_r_min_final(cylgpu_ctx* c) {
   return 0;
 }
 
-// particle_reflection_bcs_complex, boundary.F90:918-1015 (the COMPLEX variant's index pairing).
-// x walls: one thread per (row, mode, comp); comp 0 = jx (flip_dir 1), 1 = jr, 2 = jt.
-__global__ void __launch_bounds__(128) k_jreflect_x(Geom g, cplx* jx, cplx* jr, cplx* jt, int side) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
-  if (j > g.ny + NG) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  cplx* a = (k == 0) ? jx : (k == 1) ? jr : jt;
-  const bool flip = (k == 0);
-  if (side == 0) {
-    for (int i = 1; i <= NG - 1; ++i) {
-      if (flip) {
-        const size_t o = g.at(i, j, im), s = g.at(1 - i, j, im);
-        a[o] = a[o] - a[s];
-        a[s] = C(0.0, 0.0);
-      } else {
-        const size_t o = g.at(i, j, im), s = g.at(-i, j, im);
-        a[o] = a[o] + a[s];
-        a[s] = C(0.0, 0.0);
-      }
-    }
-  } else {
-    const int nn = g.nx;
-    for (int i = 1; i <= NG; ++i) {
-      if (flip) {
-        const size_t o = g.at(nn + 1 - i, j, im), s = g.at(nn + i, j, im);
-        a[o] = a[o] - a[s];
-        a[s] = C(0.0, 0.0);
-      } else {
-        const size_t o = g.at(nn - i, j, im), s = g.at(nn + i, j, im);
-        a[o] = a[o] + a[s];
-        a[s] = C(0.0, 0.0);
-      }
-    }
-  }
-}
-
-// r_max wall with the face-radius ratios of boundary.F90:988-1005
-__global__ void __launch_bounds__(128) k_jreflect_y(Geom g, cplx* jx, cplx* jr, cplx* jt, double dy,
-                                                    double y_grid_min_local) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
-  if (ix > g.nx + NG) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  const int nn = g.ny;
-  const double r_max = y_grid_min_local + ((double)g.ny - 0.5) * dy;
-  if (k == 1) {          // jr: flip_dir == 2
-    for (int i = 1; i <= NG; ++i) {
-      const double num = r_max + ((double)i - 0.5) * dy, den = r_max - ((double)i - 0.5) * dy;
-      const size_t o = g.at(ix, nn + 1 - i, im), s = g.at(ix, nn + i, im);
-      jr[o] = jr[o] - (jr[s] * num) / den;
-      jr[s] = C(0.0, 0.0);
-    }
-  } else if (k == 0) {   // jx: flip_dir == 1
-    for (int i = 1; i <= NG; ++i) {
-      const double num = r_max + (double)i * dy, den = r_max - (double)i * dy;
-      const size_t o = g.at(ix, nn - i, im), s = g.at(ix, nn + i, im);
-      jx[o] = jx[o] + (jx[s] * num) / den;
-      jx[s] = C(0.0, 0.0);
-    }
-  } else {
-    for (int i = 1; i <= NG; ++i) {
-      const size_t o = g.at(ix, nn - i, im), s = g.at(ix, nn + i, im);
-      jt[o] = jt[o] + jt[s];
-      jt[s] = C(0.0, 0.0);
-    }
-  }
-}
-
 // bc_allspecies (boundary.F90:60-75): common particle bc of all species, -1 if mixed
 static int bc_allspecies(const cylgpu_ctx* c, int bd) {
   int b = -2;

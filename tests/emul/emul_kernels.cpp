@@ -290,6 +290,38 @@ EMUL_API void emul_r_min_final(int nx, int ny, int M, void* const* j3) {
   emul_launch(k_r_min_final, dim3((g.SX + 127) / 128, M), dim3(128), g, (cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]);
 }
 
+// current_finish without smoothing on ONE slab (bcs.cu::current_bcs_impl + the J halo): reflection of the ghost
+// currents at reflecting walls, the additive ghost exchange and the halo -- as two messages (modes 1 then 0) or as
+// the product's merged single message (mode 2).  periodic: the slab is its own x neighbour.
+EMUL_API void emul_current_finish(int nx, int ny, int M, void* const* j3, const int32_t* bca, const int32_t* bc_field,
+                                  double dy, double y_grid_min_local, int merged) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  cplx *jx = (cplx*)j3[0], *jr = (cplx*)j3[1], *jt = (cplx*)j3[2];
+  if (bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT) emul_launch(k_jreflect_x, dim3((g.SY + 127) / 128, g.M, 3), dim3(128), g, jx, jr, jt, 0);
+  if (bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_jreflect_x, dim3((g.SY + 127) / 128, g.M, 3), dim3(128), g, jx, jr, jt, 1);
+  if (bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT)
+    emul_launch(k_jreflect_y, dim3((g.SX + 127) / 128, g.M, 3), dim3(128), g, jx, jr, jt, dy, y_grid_min_local);
+  const bool ring = bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC || bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  const bool to = ring && bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;            // to_l == to_r on one slab
+  const bool fill = ring && bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;     // fill_l == fill_r
+  Halo3 h;
+  h.f[0] = jx; h.f[1] = jr; h.f[2] = jt;
+  h.skip[0] = h.skip[1] = h.skip[2] = 0;
+  const size_t elems = (size_t)3 * g.M * g.SY * NG;
+  const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+  auto exchange = [&](int mode) {
+    std::vector<cplx> sl(2 * elems), sr(2 * elems);
+    emul_launch(k_halo_pack, grd, dim3(128), g, h, sl.data(), sr.data(), mode, elems);
+    emul_launch(k_halo_unpack, grd, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), mode, elems);
+  };
+  if (merged && to && fill) { exchange(2); return; }
+  if (to) exchange(1);
+  if (fill) exchange(0);
+}
+
 // update_e_field / update_b_field of one slab without boundary conditions (fields.cu::launch_update_e / _b).
 // f9: exm erm etm bxm brm btm jxm jrm jtm, complex with ghosts, updated in place.
 EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f9, double dx, double dy, double dt,

@@ -314,3 +314,40 @@ def test_moment_exchange_between_two_slabs(emul, deck_name):
         scale = max(np.abs(r).max() for r in ref)
         for k in range(2):
             assert np.abs(outs[k] - ref[k]).max() <= 1e-13 * scale, (deck_name, kind, k)
+
+
+# ------------------------------------------------------------------------------------------------------
+# current_finish (csrc/bc_kernels.cuh: k_jreflect_x / k_jreflect_y, the packed exchange): reflection of the
+# ghost currents with the complex variant's index pairing and the face-radius ratios at r_max, the additive
+# ghost exchange and the halo -- and the product's merged one-message form of the last two.
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("deck_name", ["drift", "thermal", "lwfa"])
+@pytest.mark.parametrize("merged", [0, 1])
+def test_current_finish_kernels_match_the_oracle(emul, deck_name, merged):
+    L = emul
+    L.emul_current_finish.restype = None
+    L.emul_current_finish.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_int]
+    d = {"drift": lambda: decks.drift(nx=20, ny=10, n_mode=3),
+         "thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=6),
+         "lwfa": lambda: decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=0)}[deck_name]()
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(2)
+    w.call("fields_half")
+    w.call("push")                      # J with its ghost deposits, r_min_final and particle_bcs done
+    rng = np.random.default_rng(11)
+    names = ("jxm", "jrm", "jtm")
+    for n in names:                     # every ghost cell carries something
+        f = w.field(0, n)
+        f += 1e-2 * np.abs(f).max() * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
+    mine = [np.ascontiguousarray(w.field(0, n)) for n in names]
+    ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in mine])
+    sc, info = w.scalars(), w.rank_info(0)
+    bca = (C.c_int32 * 4)(*w.bc_particle(0))
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    L.emul_current_finish(info["nx"], info["ny"], d.n_mode, ptrs, bca, bcf, sc["dy"], sc["y_grid_min_local"], merged)
+    w.call("current_finish")
+    for n, a in zip(names, mine):
+        ref = w.field(0, n)
+        assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n, merged)
