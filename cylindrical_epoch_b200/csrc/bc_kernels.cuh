@@ -4,6 +4,61 @@
 // kernel-emulation tests (tests/emul/).  Product code: no oracle here.
 #pragma once
 
+// ---- field ghost fill at the domain edges: efield_bcs / bfield_bcs, boundary.F90:1355-1476 ----
+enum { OP_NONE = 0, OP_CLAMP = 1, OP_ZEROGRAD = 2 };
+
+struct Tri {
+  cplx* f[3];
+  int op[3];
+  int stag[3];   // stagger of each array in the direction normal to the boundary
+};
+
+// x_min / x_max ghost fill: boundary.F90:772-829 (clamp) and :654-707 (zero gradient).
+// One thread per (row j, mode, array).
+__global__ void __launch_bounds__(128) k_edge_x(Geom g, Tri t, int side) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (j > g.ny + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int op = t.op[k];
+  if (op == OP_NONE) return;
+  cplx* f = t.f[k];
+  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
+  if (side == CYLGPU_BD_X_MIN) {
+    if (t.stag[k]) {
+      for (int i = 1; i <= NG - 1; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG - i, j, im)];
+      if (op == OP_CLAMP) f[g.at(0, j, im)] = C(0.0, 0.0);
+    } else {
+      for (int i = 1; i <= NG; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG + 1 - i, j, im)];
+    }
+  } else {
+    const int nn = g.nx;
+    if (t.stag[k]) {
+      if (op == OP_CLAMP) f[g.at(nn, j, im)] = C(0.0, 0.0);
+      for (int i = 1; i <= NG - 1; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn - i, j, im)];
+    } else {
+      for (int i = 1; i <= NG; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn + 1 - i, j, im)];
+    }
+  }
+}
+
+// r_max ghost fill; one thread per (column ix, mode, array)
+__global__ void __launch_bounds__(128) k_edge_y(Geom g, Tri t) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  if (ix > g.nx + NG) return;
+  const int im = blockIdx.y, k = blockIdx.z;
+  const int op = t.op[k];
+  if (op == OP_NONE) return;
+  cplx* f = t.f[k];
+  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
+  const int nn = g.ny;
+  if (t.stag[k]) {
+    if (op == OP_CLAMP) f[g.at(ix, nn, im)] = C(0.0, 0.0);
+    for (int i = 1; i <= NG - 1; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn - i, im)];
+  } else {
+    for (int i = 1; i <= NG; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn + 1 - i, im)];
+  }
+}
+
 // ---- x halo: boundary.F90:158-169,500-553.  Buffer layout [comp][im][row][NG]. ----
 struct Halo3 {
   cplx* f[3];

@@ -11,59 +11,7 @@
 
 namespace cylgpu {
 
-enum { OP_NONE = 0, OP_CLAMP = 1, OP_ZEROGRAD = 2 };
-
-struct Tri {
-  cplx* f[3];
-  int op[3];
-  int stag[3];   // stagger of each array in the direction normal to the boundary
-};
-
-// x_min / x_max ghost fill: boundary.F90:772-829 (clamp) and :654-707 (zero gradient).
-// One thread per (row j, mode, array).
-__global__ void __launch_bounds__(128) k_edge_x(Geom g, Tri t, int side) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
-  if (j > g.ny + NG) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  const int op = t.op[k];
-  if (op == OP_NONE) return;
-  cplx* f = t.f[k];
-  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
-  if (side == CYLGPU_BD_X_MIN) {
-    if (t.stag[k]) {
-      for (int i = 1; i <= NG - 1; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG - i, j, im)];
-      if (op == OP_CLAMP) f[g.at(0, j, im)] = C(0.0, 0.0);
-    } else {
-      for (int i = 1; i <= NG; ++i) f[g.at(i - NG, j, im)] = s * f[g.at(NG + 1 - i, j, im)];
-    }
-  } else {
-    const int nn = g.nx;
-    if (t.stag[k]) {
-      if (op == OP_CLAMP) f[g.at(nn, j, im)] = C(0.0, 0.0);
-      for (int i = 1; i <= NG - 1; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn - i, j, im)];
-    } else {
-      for (int i = 1; i <= NG; ++i) f[g.at(nn + i, j, im)] = s * f[g.at(nn + 1 - i, j, im)];
-    }
-  }
-}
-
-// r_max ghost fill; one thread per (column ix, mode, array)
-__global__ void __launch_bounds__(128) k_edge_y(Geom g, Tri t) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
-  if (ix > g.nx + NG) return;
-  const int im = blockIdx.y, k = blockIdx.z;
-  const int op = t.op[k];
-  if (op == OP_NONE) return;
-  cplx* f = t.f[k];
-  const double s = (op == OP_CLAMP) ? -1.0 : 1.0;
-  const int nn = g.ny;
-  if (t.stag[k]) {
-    if (op == OP_CLAMP) f[g.at(ix, nn, im)] = C(0.0, 0.0);
-    for (int i = 1; i <= NG - 1; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn - i, im)];
-  } else {
-    for (int i = 1; i <= NG; ++i) f[g.at(ix, nn + i, im)] = s * f[g.at(ix, nn + 1 - i, im)];
-  }
-}
+#include "bc_kernels.cuh"
 
 static void launch_edge(cylgpu_ctx* c, const Tri& t, int bd) {
   const Geom& g = c->g;
@@ -74,8 +22,6 @@ static void launch_edge(cylgpu_ctx* c, const Tri& t, int bd) {
   }
   c->stats.kernel_launches += 1;
 }
-
-#include "bc_kernels.cuh"
 
 // `gg`: geometry of the arrays when it is not the handle's (the single-plane work arrays of the
 // particle moments, moments.cuh); the staging buffers are sized for the handle's n_mode >= 1.

@@ -290,6 +290,58 @@ EMUL_API void emul_r_min_final(int nx, int ny, int M, void* const* j3) {
   emul_launch(k_r_min_final, dim3((g.SX + 127) / 128, M), dim3(128), g, (cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]);
 }
 
+// efield_bcs (which = 0) / bfield_bcs (which = 1, mpi_only = 0) on ONE slab: bcs.cu::do_efield_bcs / do_bfield_bcs
+// -- the x halo with the one-row shift of the r-staggered arrays, then edge_bcs with its operator tables
+// (conducting walls first, then clamp / zero-gradient by boundary kind), restated here.
+EMUL_API void emul_field_bcs(int which, int nx, int ny, int M, void* const* f3, const int32_t* bc_field) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  static const int STAG_X[6] = {0, 1, 1, 1, 0, 0}, STAG_Y[6] = {1, 0, 1, 0, 1, 0};   // setup.F90:126-136
+  const int base = which ? 3 : 0;
+  Halo3 h;
+  for (int k = 0; k < 3; ++k) h.f[k] = (cplx*)f3[k];
+  h.skip[0] = which ? 0 : 1; h.skip[1] = which ? 1 : 0; h.skip[2] = which ? 0 : 1;
+  if (bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC) {   // the slab is its own neighbour: ghosts <- interior edges
+    const size_t elems = (size_t)3 * g.M * g.SY * NG;
+    std::vector<cplx> sl(elems), sr(elems);
+    const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+    emul_launch(k_halo_pack, grd, dim3(128), g, h, sl.data(), sr.data(), 0, elems);
+    emul_launch(k_halo_unpack, grd, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), 0, elems);
+  }
+  Tri t;
+  for (int k = 0; k < 3; ++k) t.f[k] = (cplx*)f3[k];
+  auto apply = [&](int bd, const int* op) {
+    if (op[0] == OP_NONE && op[1] == OP_NONE && op[2] == OP_NONE) return;
+    if (bc_field[bd] == CYLGPU_BC_PERIODIC) return;
+    for (int k = 0; k < 3; ++k) {
+      t.op[k] = op[k];
+      t.stag[k] = (bd == CYLGPU_BD_Y_MAX) ? STAG_Y[base + k] : STAG_X[base + k];
+    }
+    if (bd == CYLGPU_BD_Y_MAX) emul_launch(k_edge_y, dim3((g.SX + 127) / 128, g.M, 3), dim3(128), g, t);
+    else emul_launch(k_edge_x, dim3((g.SY + 127) / 128, g.M, 3), dim3(128), g, t, bd);
+  };
+  const int ecx[3] = {OP_CLAMP, OP_ZEROGRAD, OP_ZEROGRAD}, ecy[3] = {OP_ZEROGRAD, OP_CLAMP, OP_ZEROGRAD};
+  const int bcx[3] = {OP_ZEROGRAD, OP_CLAMP, OP_CLAMP}, bcy[3] = {OP_CLAMP, OP_ZEROGRAD, OP_CLAMP};
+  const int* cx = which ? bcx : ecx;
+  const int* cy = which ? bcy : ecy;
+  auto conduct = [&](int bc, const int* c3, int* op) {
+    op[0] = op[1] = op[2] = OP_NONE;
+    if (bc == CYLGPU_BC_CONDUCT) { op[0] = c3[0]; op[1] = c3[1]; op[2] = c3[2]; }
+  };
+  auto general = [&](int bc, int* op) {
+    op[0] = op[1] = op[2] = OP_NONE;
+    if (bc == CYLGPU_BC_CLAMP || bc == CYLGPU_BC_SIMPLE_LASER || bc == CYLGPU_BC_SIMPLE_OUTFLOW) op[0] = op[1] = op[2] = OP_CLAMP;
+    if (bc == CYLGPU_BC_ZERO_GRADIENT || bc == CYLGPU_BC_CPML_LASER || bc == CYLGPU_BC_CPML_OUTFLOW) op[0] = op[1] = op[2] = OP_ZEROGRAD;
+  };
+  int op[3];
+  for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX}) { conduct(bc_field[bd], cx, op); apply(bd, op); }
+  conduct(bc_field[CYLGPU_BD_Y_MAX], cy, op);
+  apply(CYLGPU_BD_Y_MAX, op);
+  for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX, (int)CYLGPU_BD_Y_MAX}) { general(bc_field[bd], op); apply(bd, op); }
+}
+
 // current_finish without smoothing on ONE slab (bcs.cu::current_bcs_impl + the J halo): reflection of the ghost
 // currents at reflecting walls, the additive ghost exchange and the halo -- as two messages (modes 1 then 0) or as
 // the product's merged single message (mode 2).  periodic: the slab is its own x neighbour.

@@ -351,3 +351,45 @@ def test_current_finish_kernels_match_the_oracle(emul, deck_name, merged):
     for n, a in zip(names, mine):
         ref = w.field(0, n)
         assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n, merged)
+
+
+# ------------------------------------------------------------------------------------------------------
+# efield_bcs / bfield_bcs (csrc/bc_kernels.cuh: k_edge_x / k_edge_y + the x halo with the one-row shift of the
+# r-staggered arrays) for every field boundary kind the reference distinguishes, including the conducting and
+# zero-gradient walls that none of the GPU parity decks uses.
+# ------------------------------------------------------------------------------------------------------
+FIELD_BC_SETS = {
+    "laser/outflow": (po.BC_SIMPLE_LASER, po.BC_OPEN, 0, po.BC_OPEN),          # open -> simple_outflow: clamp
+    "periodic/zero_b": (po.BC_PERIODIC, po.BC_PERIODIC, 0, po.BC_ZERO_B),
+    "clamp": (po.BC_CLAMP, po.BC_CLAMP, 0, po.BC_CLAMP),
+    "conduct": (po.BC_CONDUCT, po.BC_CONDUCT, 0, po.BC_CONDUCT),
+    "zero_gradient": (po.BC_ZERO_GRADIENT, po.BC_ZERO_GRADIENT, 0, po.BC_ZERO_GRADIENT),
+    "mixed": (po.BC_CONDUCT, po.BC_ZERO_GRADIENT, 0, po.BC_CLAMP),
+}
+
+
+@pytest.mark.parametrize("bc_name", sorted(FIELD_BC_SETS))
+def test_field_boundary_kernels_match_the_oracle(emul, bc_name):
+    L = emul
+    L.emul_field_bcs.restype = None
+    L.emul_field_bcs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    bc = FIELD_BC_SETS[bc_name]
+    periodic = bc[0] == po.BC_PERIODIC
+    bcp = (po.BC_PERIODIC, po.BC_PERIODIC, po.BC_OPEN, po.BC_REFLECT) if periodic else (po.BC_OPEN,) * 4
+    sp = [decks.SpeciesSpec(-po.Q0, po.M0, bcp, 1, 1.0e24)]
+    d = decks.Deck("bcs", 18, 9, 3, 0.0, 18 * 0.5e-6, 9 * 0.5e-6, bc, sp)
+    w = decks.make_oracle(d)
+    rng = np.random.default_rng(5)
+    names = ("exm", "erm", "etm", "bxm", "brm", "btm")
+    for n in names:                    # every interior, boundary and ghost value is distinct
+        f = w.field(0, n)
+        f[...] = rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape)
+    info = w.rank_info(0)
+    bcf = (C.c_int32 * 4)(*w.bc_field())          # as normalised by setup_boundaries
+    for which, op, group in ((0, "efield_bcs", names[:3]), (1, "bfield_bcs", names[3:])):
+        mine = [np.ascontiguousarray(w.field(0, n)) for n in group]
+        ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in mine])
+        L.emul_field_bcs(which, info["nx"], info["ny"], d.n_mode, ptrs, bcf)
+        w.call(op)
+        for n, a in zip(group, mine):
+            assert np.array_equal(a, w.field(0, n)), (bc_name, op, n)
