@@ -283,3 +283,116 @@ __global__ void __launch_bounds__(128) k_jreflect_y(Geom g, cplx* jx, cplx* jr, 
     }
   }
 }
+
+// ---- laser / outflow line updates: laser.f90:411-690 ----
+struct FieldSet {
+  cplx *exm, *erm, *etm, *bxm, *brm, *btm, *jxm, *jrm, *jtm;
+  const cplx *bxo, *bro, *bto, *jxo, *jro, *jto;
+};
+
+// side 0: x_min (laser.f90:411-520), side 1: x_max (:524-633).  One thread per (ir, im).
+// REFERENCE QUIRKS reproduced: `r_d_vals` is declared (0:ny) but used whole-array against
+// (1:ny) sections, so element ir pairs with r_d_vals(ir-1); on x_max the same holds for
+// source_t (laser.f90:604).
+__global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cplx* __restrict__ snap_er,
+                                                   const cplx* __restrict__ snap_et,
+                                                   const cplx* __restrict__ snap_bx,
+                                                   const cplx* __restrict__ snap_br,
+                                                   const cplx* __restrict__ snap_bt,
+                                                   const double* __restrict__ s1, const double* __restrict__ s2,
+                                                   int side, double dx, double dy, double dt,
+                                                   double y_grid_min_local) {
+  const int ir = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ny
+  const int im = blockIdx.y;
+  if (ir > g.ny) return;
+  const double c = C_LIGHT;
+  const double dtc2 = dt * (c * c);
+  const double lx = dtc2 / dx, lr = dtc2 / dy;
+  const double sum = 1.0 / (lx + c), diff = lx - c, dt_eps = dt / EPSILON0;
+  const size_t sn = (size_t)im * g.SY + (ir + NG - 1);   // snapshot (ir, im)
+  const int nx = g.nx;
+  if (side == 0) {
+    F.bxm[g.at(0, ir, im)] = snap_bx[sn];
+    if (ir >= 1) {
+      const cplx source_t = (im == 1) ? C(s1[ir], s2[ir]) : C(0.0, 0.0);
+      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);   // r_d_vals(ir-1)
+      F.btm[g.at(1, ir, im)] =
+          sum * (4.0 * source_t + 2.0 * (snap_er[sn] + c * snap_bt[sn]) - 2.0 * F.erm[g.at(1, ir, im)]
+                 + (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(1, ir, im)]) / r_d_q
+                 + dt_eps * F.jrm[g.at(1, ir, im)] + diff * F.btm[g.at(2, ir, im)]);
+    }
+    if (ir >= 1 && ir <= g.ny - 1) {
+      // source_r = -i*s1 + s2
+      const cplx source_r = (im == 1) ? C(s2[ir], -s1[ir]) : C(0.0, 0.0);
+      F.brm[g.at(1, ir, im)] =
+          sum * (-4.0 * source_r - 2.0 * (snap_et[sn] + c * snap_br[sn]) + 2.0 * F.etm[g.at(1, ir, im)]
+                 - lr * (F.bxm[g.at(1, ir + 1, im)] - F.bxm[g.at(1, ir, im)])
+                 - dt_eps * F.jtm[g.at(1, ir, im)] + diff * F.brm[g.at(2, ir, im)]);
+    }
+  } else {
+    F.bxm[g.at(nx, ir, im)] = snap_bx[sn];
+    if (ir >= 1) {
+      const cplx source_t = (im == 1) ? C(s1[ir - 1], s2[ir - 1]) : C(0.0, 0.0);
+      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);
+      F.btm[g.at(nx, ir, im)] =
+          sum * (-4.0 * source_t - 2.0 * (snap_er[sn] + c * snap_bt[sn]) + 2.0 * F.erm[g.at(nx - 1, ir, im)]
+                 - (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(nx - 1, ir, im)]) / r_d_q
+                 - dt_eps * F.jrm[g.at(nx - 1, ir, im)] + diff * F.btm[g.at(nx - 1, ir, im)]);
+    }
+    if (ir >= 1 && ir <= g.ny - 1) {
+      const cplx source_r = (im == 1) ? C(s2[ir], -s1[ir]) : C(0.0, 0.0);
+      F.brm[g.at(nx, ir, im)] =
+          sum * (4.0 * source_r + 2.0 * (snap_et[sn] + c * snap_br[sn]) - 2.0 * F.etm[g.at(nx - 1, ir, im)]
+                 + lr * (F.bxm[g.at(nx - 1, ir + 1, im)] - F.bxm[g.at(nx - 1, ir, im)])
+                 + dt_eps * F.jtm[g.at(nx - 1, ir, im)] + diff * F.brm[g.at(nx - 1, ir, im)]);
+    }
+  }
+}
+
+// laser.f90:637-690.  REFERENCE QUIRK reproduced: icdt_2r is declared REAL(num) but assigned
+// a purely imaginary value, so it is 0 and the azimuthal coupling terms vanish.
+__global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int ix_l, int ix_h, double dx,
+                                                       double dy, double dt, double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
+  const int im = blockIdx.y;
+  if (ix > g.nx) return;
+  const int ny = g.ny;
+  const double c = C_LIGHT;
+  const double dtc2 = dt * (c * c);
+  const double inv_r = 1.0 / ((double)((float)ny - 1.5f) * dy + y_grid_min_local);
+  const double dtc2_4r = 0.25 * dtc2 * inv_r;
+  const double icdt_2r = 0.0;
+  const double lx = dtc2 / dx, ly = dtc2 / dy;
+  const double sum_x = 1.0 / (ly + c);
+  const double sum_t = 1.0 / (ly + c + dtc2_4r);
+  const double dt_2eps = 0.5 * dt / EPSILON0;
+  if (ix >= ix_l && ix <= ix_h) {
+    F.bxm[g.at(ix, ny, im)] =
+        sum_x * ((-F.bxm[g.at(ix, ny - 1, im)]) * (c - ly) - F.bxo[g.at(ix, ny, im)] * (-c + ly)
+                 - F.bxo[g.at(ix, ny - 1, im)] * (-c - ly) - ((c * dt) * inv_r) * F.etm[g.at(ix, ny - 1, im)]
+                 + (0.5 * lx) * (F.brm[g.at(ix + 1, ny - 1, im)] - F.brm[g.at(ix, ny - 1, im)]
+                                 + F.bro[g.at(ix + 1, ny - 1, im)] - F.bro[g.at(ix, ny - 1, im)])
+                 - (icdt_2r * (double)im) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)])
+                 - dt_2eps * (F.jtm[g.at(ix, ny - 1, im)] + F.jto[g.at(ix, ny - 1, im)]));
+  }
+  if (ix >= 1) {
+    F.btm[g.at(ix, ny, im)] =
+        sum_t * ((-F.btm[g.at(ix, ny - 1, im)]) * (c - ly + dtc2_4r) - F.bto[g.at(ix, ny, im)] * (-c + ly + dtc2_4r)
+                 - F.bto[g.at(ix, ny - 1, im)] * (-c - ly + dtc2_4r)
+                 - ((0.5 * lx) / c) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)]
+                                       - F.erm[g.at(ix - 1, ny, im)] - F.erm[g.at(ix - 1, ny - 1, im)])
+                 - ((icdt_2r * (double)im) * c) * (F.brm[g.at(ix, ny - 1, im)] + F.bro[g.at(ix, ny - 1, im)])
+                 + dt_2eps * (F.jxm[g.at(ix, ny - 1, im)] + F.jxo[g.at(ix, ny - 1, im)]));
+  }
+}
+
+// boundary.F90:1528-1531 zero_b on r_max
+__global__ void __launch_bounds__(128) k_zero_b_rmax(Geom g, cplx* bxm, cplx* brm, cplx* btm) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1 - NG;
+  const int im = blockIdx.y;
+  if (ix > g.nx + NG) return;
+  const size_t o = g.at(ix, g.ny, im);
+  bxm[o] = C(0.0, 0.0);
+  brm[o] = C(0.0, 0.0);
+  btm[o] = C(0.0, 0.0);
+}

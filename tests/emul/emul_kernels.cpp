@@ -342,6 +342,52 @@ EMUL_API void emul_field_bcs(int which, int nx, int ny, int M, void* const* f3, 
   for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX, (int)CYLGPU_BD_Y_MAX}) { general(bc_field[bd], op); apply(bd, op); }
 }
 
+// bfield_final_bcs on ONE slab (bcs.cu::do_bfield_final_bcs_device): bfield_bcs, the laser / outflow line
+// updates on x_min, x_max and r_max (or zero_b), then the halo.  f15: the 15 mode arrays in field-id order;
+// snaps12: the boundary snapshots in snapshot-id order; src4: source1/2 of x_min then x_max, ny + 1 values each.
+extern "C" void emul_field_bcs(int which, int nx, int ny, int M, void* const* f3, const int32_t* bc_field);
+EMUL_API void emul_bfield_final_bcs(int nx, int ny, int M, void* const* f15, const void* const* snaps12,
+                                    const double* const* src4, const int32_t* bc_field, double dx, double dy,
+                                    double dt, double y_grid_min_local) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  emul_field_bcs(1, nx, ny, M, f15 + 3, bc_field);
+  FieldSet F;
+  F.exm = (cplx*)f15[0]; F.erm = (cplx*)f15[1]; F.etm = (cplx*)f15[2];
+  F.bxm = (cplx*)f15[3]; F.brm = (cplx*)f15[4]; F.btm = (cplx*)f15[5];
+  F.jxm = (cplx*)f15[6]; F.jrm = (cplx*)f15[7]; F.jtm = (cplx*)f15[8];
+  F.bxo = (const cplx*)f15[9]; F.bro = (const cplx*)f15[10]; F.bto = (const cplx*)f15[11];
+  F.jxo = (const cplx*)f15[12]; F.jro = (const cplx*)f15[13]; F.jto = (const cplx*)f15[14];
+  const dim3 grd((g.ny + 1 + 127) / 128, g.M);
+  auto snap = [&](int k) { return (const cplx*)snaps12[k]; };
+  int b = bc_field[CYLGPU_BD_X_MIN];
+  if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
+    emul_launch(k_outflow_x, grd, dim3(128), g, F, snap(1), snap(2), snap(3), snap(4), snap(5), src4[0], src4[1], 0, dx, dy,
+                dt, y_grid_min_local);
+  b = bc_field[CYLGPU_BD_X_MAX];
+  if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
+    emul_launch(k_outflow_x, grd, dim3(128), g, F, snap(7), snap(8), snap(9), snap(10), snap(11), src4[2], src4[3], 1, dx,
+                dy, dt, y_grid_min_local);
+  if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
+    emul_launch(k_outflow_r_max, dim3((g.nx + 1 + 127) / 128, g.M), dim3(128), g, F, 1, g.nx - 1, dx, dy, dt,
+                y_grid_min_local);
+  } else if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
+    emul_launch(k_zero_b_rmax, dim3((g.SX + 127) / 128, g.M), dim3(128), g, F.bxm, F.brm, F.btm);
+  }
+  if (bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC) {   // bfield_bcs(mpi_only): the halo alone
+    Halo3 h;
+    h.f[0] = F.bxm; h.f[1] = F.brm; h.f[2] = F.btm;
+    h.skip[0] = 0; h.skip[1] = 1; h.skip[2] = 0;
+    const size_t elems = (size_t)3 * g.M * g.SY * NG;
+    std::vector<cplx> sl(elems), sr(elems);
+    const dim3 hg((g.SY * NG + 127) / 128, g.M, 3);
+    emul_launch(k_halo_pack, hg, dim3(128), g, h, sl.data(), sr.data(), 0, elems);
+    emul_launch(k_halo_unpack, hg, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), 0, elems);
+  }
+}
+
 // current_finish without smoothing on ONE slab (bcs.cu::current_bcs_impl + the J halo): reflection of the ghost
 // currents at reflecting walls, the additive ghost exchange and the halo -- as two messages (modes 1 then 0) or as
 // the product's merged single message (mode 2).  periodic: the slab is its own x neighbour.

@@ -393,3 +393,54 @@ def test_field_boundary_kernels_match_the_oracle(emul, bc_name):
         w.call(op)
         for n, a in zip(group, mine):
             assert np.array_equal(a, w.field(0, n)), (bc_name, op, n)
+
+
+# ------------------------------------------------------------------------------------------------------
+# bfield_final_bcs (csrc/bc_kernels.cuh: k_outflow_x, k_outflow_r_max, k_zero_b_rmax): laser injection into
+# m = 1 and the first-order absorbing update of laser.f90:411-690, with the reference quirks reproduced.
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("deck_name", ["lwfa", "gaussian", "thermal", "laser_both_ends"])
+def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name):
+    L = emul
+    L.emul_bfield_final_bcs.restype = None
+    L.emul_bfield_final_bcs.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_double, C.c_double,
+                                        C.c_double, C.c_double]
+    if deck_name == "lwfa":
+        d = decks.lwfa(nx=32, ny=12, n_mode=3, ppc_e=2, ppc_p=0, t_centre=6e-15)
+    elif deck_name == "gaussian":
+        d = decks.gaussian_pulse(nx=60, ny=20)
+    elif deck_name == "thermal":
+        d = decks.thermal(nx=24, ny=12, n_mode=2, ppc=4)
+    else:   # a second laser from x_max (laser.f90:524-633, with its own index quirk)
+        d = decks.lwfa(nx=32, ny=12, n_mode=2, ppc_e=2, ppc_p=0, t_centre=6e-15)
+        d.bc_field = (po.BC_SIMPLE_LASER, po.BC_SIMPLE_LASER, 0, po.BC_OPEN)
+        las = dict(d.lasers[0])
+        las.update(boundary=po.BD_X_MAX, pol_angle=0.7, phase=0.3)
+        d.lasers.append(las)
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(12)
+    rng = np.random.default_rng(8)
+    from pyoracle import FIELD_NAMES, SNAP_NAMES
+    for n in FIELD_NAMES + SNAP_NAMES:     # old arrays, currents and snapshots all carry something
+        f = w.field(0, n)
+        f += 1e-2 * max(np.abs(f).max(), 1.0) * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
+    sc, info = w.scalars(), w.rank_info(0)
+    mine = [np.ascontiguousarray(w.field(0, n)) for n in FIELD_NAMES]
+    snaps = [np.ascontiguousarray(w.field(0, n)) for n in SNAP_NAMES]
+    s1a, s2a = w.laser_sources(po.BD_X_MIN)
+    s1b, s2b = w.laser_sources(po.BD_X_MAX)
+    src = [np.ascontiguousarray(a, dtype=np.float64) for a in (s1a, s2a, s1b, s2b)]
+    fp = (C.c_void_p * 15)(*[a.ctypes.data for a in mine])
+    sp = (C.c_void_p * 12)(*[a.ctypes.data for a in snaps])
+    rp = (C.c_void_p * 4)(*[a.ctypes.data for a in src])
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    L.emul_bfield_final_bcs(info["nx"], info["ny"], d.n_mode, fp, sp, rp, bcf, sc["dx"], sc["dy"], sc["dt"],
+                            sc["y_grid_min_local"])
+    w.call("bfield_final_bcs")
+    for n, a in zip(FIELD_NAMES[:6], mine[:6]):
+        ref = w.field(0, n)
+        assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n)
+    if deck_name != "thermal":
+        assert max(np.abs(s).max() for s in src) > 0      # the laser was on
