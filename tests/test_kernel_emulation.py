@@ -135,7 +135,7 @@ def _emul_push(L, w, d, hc=False):
                                C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
     L.emul_r_min_final.restype = None
     L.emul_r_min_final.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-    fields = [np.ascontiguousarray(w.field(0, n)) for n in ("exm", "erm", "etm", "bxm", "brm", "btm")]
+    fields = [w.field(0, n).copy() for n in ("exm", "erm", "etm", "bxm", "brm", "btm")]
     J = [np.zeros_like(fields[0]) for _ in range(3)]
     fp = (C.c_void_p * 6)(*[f.ctypes.data for f in fields])
     jp = (C.c_void_p * 3)(*[j.ctypes.data for j in J])
@@ -265,7 +265,7 @@ def test_field_update_kernels_match_the_oracle(emul, n_mode):
         f += 1e-3 * scale * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
     sc, info = w.scalars(), w.rank_info(0)
     for which, op in ((0, "update_e"), (1, "update_b"), (0, "update_e"), (1, "update_b")):
-        mine = [np.ascontiguousarray(w.field(0, n)) for n in names]
+        mine = [w.field(0, n).copy() for n in names]
         ptrs = (C.c_void_p * 9)(*[a.ctypes.data for a in mine])
         L.emul_update_field(which, info["nx"], info["ny"], n_mode, ptrs, sc["dx"], sc["dy"], sc["dt"],
                             sc["y_grid_min_local"])
@@ -341,7 +341,7 @@ def test_current_finish_kernels_match_the_oracle(emul, deck_name, merged):
     for n in names:                     # every ghost cell carries something
         f = w.field(0, n)
         f += 1e-2 * np.abs(f).max() * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
-    mine = [np.ascontiguousarray(w.field(0, n)) for n in names]
+    mine = [w.field(0, n).copy() for n in names]
     ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in mine])
     sc, info = w.scalars(), w.rank_info(0)
     bca = (C.c_int32 * 4)(*w.bc_particle(0))
@@ -387,7 +387,7 @@ def test_field_boundary_kernels_match_the_oracle(emul, bc_name):
     info = w.rank_info(0)
     bcf = (C.c_int32 * 4)(*w.bc_field())          # as normalised by setup_boundaries
     for which, op, group in ((0, "efield_bcs", names[:3]), (1, "bfield_bcs", names[3:])):
-        mine = [np.ascontiguousarray(w.field(0, n)) for n in group]
+        mine = [w.field(0, n).copy() for n in group]
         ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in mine])
         L.emul_field_bcs(which, info["nx"], info["ny"], d.n_mode, ptrs, bcf)
         w.call(op)
@@ -427,8 +427,8 @@ def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name):
         f = w.field(0, n)
         f += 1e-2 * max(np.abs(f).max(), 1.0) * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
     sc, info = w.scalars(), w.rank_info(0)
-    mine = [np.ascontiguousarray(w.field(0, n)) for n in FIELD_NAMES]
-    snaps = [np.ascontiguousarray(w.field(0, n)) for n in SNAP_NAMES]
+    mine = [w.field(0, n).copy() for n in FIELD_NAMES]
+    snaps = [w.field(0, n).copy() for n in SNAP_NAMES]
     s1a, s2a = w.laser_sources(po.BD_X_MIN)
     s1b, s2b = w.laser_sources(po.BD_X_MAX)
     src = [np.ascontiguousarray(a, dtype=np.float64) for a in (s1a, s2a, s1b, s2b)]
@@ -444,3 +444,145 @@ def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name):
         assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n)
     if deck_name != "thermal":
         assert max(np.abs(s).max() for s in src) > 0      # the laser was on
+
+
+# ------------------------------------------------------------------------------------------------------
+# All of it together: N whole steps of one slab driven from the emulated product kernels in the order of the
+# library (api.cu fields_half_body / do_push / do_current_finish / cylgpu_fields_final) against the oracle's
+# step.  Open or conducting boxes (no self-exchange needed for the B halo of the half step).
+# ------------------------------------------------------------------------------------------------------
+class EmulSlab:
+    def __init__(self, L, w, d):
+        from pyoracle import FIELD_NAMES, SNAP_NAMES
+        self.L, self.d = L, d
+        self.sc, self.info = w.scalars(), w.rank_info(0)
+        self.f = {n: w.field(0, n).copy() for n in FIELD_NAMES}
+        self.snaps = [w.field(0, n).copy() for n in SNAP_NAMES]
+        self.parts = [w.particles(0, i).reshape(-1, 7).copy() for i in range(len(d.species))]
+        self.bcf = (C.c_int32 * 4)(*w.bc_field())
+        self.names = FIELD_NAMES
+        self.time = self.sc["time"]
+        self.nx, self.ny, self.M = self.info["nx"], self.info["ny"], d.n_mode
+        for fn, at in (("emul_update_field", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + [C.c_double] * 4),
+                       ("emul_field_bcs", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
+                       ("emul_bfield_final_bcs", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int32)] + [C.c_double] * 4),
+                       ("emul_current_finish", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                                C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_int]),
+                       ("emul_push_v0", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_void_p), C.c_int64, C.c_double, C.c_double, C.c_int, C.c_int] +
+                        [C.c_double] * 5),
+                       ("emul_r_min_final", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+                       ("emul_pbcs_classify", [C.POINTER(C.c_void_p), C.c_int64, C.POINTER(C.c_int32)] + [C.c_double] * 7 +
+                        [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p])):
+            getattr(L, fn).argtypes = at
+            getattr(L, fn).restype = C.c_int if fn == "emul_push_v0" else None
+
+    def ptrs(self, names):
+        return (C.c_void_p * len(names))(*[self.f[n].ctypes.data for n in names])
+
+    def update(self, which):
+        sc = self.sc
+        self.L.emul_update_field(which, self.nx, self.ny, self.M, self.ptrs(self.names[:9]), sc["dx"], sc["dy"], sc["dt"],
+                                 sc["y_grid_min_local"])
+
+    def field_bcs(self, which):
+        grp = self.names[:3] if which == 0 else self.names[3:6]
+        self.L.emul_field_bcs(which, self.nx, self.ny, self.M, self.ptrs(grp), self.bcf)
+
+    def fields_half(self):                      # api.cu fields_half_body
+        self.update(0)
+        self.field_bcs(0)
+        for n in ("bxm", "brm", "btm"):
+            self.f[n + "_old"][...] = self.f[n]
+        self.update(1)                          # (bfield_bcs(mpi_only): nothing to exchange on one open slab)
+
+    def push(self, w):                          # particles.cu do_push + do_particle_bcs, push variant 0
+        sc, info = self.sc, self.info
+        for n in ("jxm", "jrm", "jtm"):
+            self.f[n + "_old"][...] = self.f[n]
+            self.f[n][...] = 0.0
+        for i, sp in enumerate(self.d.species):
+            p = self.parts[i]
+            soa = [np.ascontiguousarray(p[:, c]) for c in range(7)]
+            sp_ptr = (C.c_void_p * 7)(*[a.ctypes.data for a in soa])
+            rc = self.L.emul_push_v0(self.nx, self.ny, self.M, self.ptrs(self.names[:6]), self.ptrs(("jxm", "jrm", "jtm")),
+                                     sp_ptr, p.shape[0], sp.charge, sp.mass, int(sp.zero_current), 0, sc["dt"], sc["dx"],
+                                     sc["dy"], info["x_grid_min_local"], sc["y_grid_min_local"])
+            assert rc == 0
+            self.parts[i] = np.stack(soa, axis=1)
+        self.L.emul_r_min_final(self.nx, self.ny, self.M, self.ptrs(("jxm", "jrm", "jtm")))
+        for i in range(len(self.d.species)):
+            p = self.parts[i]
+            n = p.shape[0]
+            soa = [np.ascontiguousarray(p[:, c]) for c in range(7)]
+            sp_ptr = (C.c_void_p * 7)(*[a.ctypes.data for a in soa])
+            holes = np.zeros(max(n, 1), dtype=np.uint32)
+            flags = np.zeros(max(n, 1), dtype=np.uint8)
+            cnt = (C.c_ulonglong * 4)()
+            bc = (C.c_int32 * 4)(*w.bc_particle(i))
+            self.L.emul_pbcs_classify(sp_ptr, n, bc, sc["x_min"], sc["x_max"], info["x_min_local"], info["x_max_local"],
+                                      sc["y_max"], sc["dx"], sc["dy"], 1, 1, holes.ctypes.data, flags.ctypes.data, cnt)
+            nh = int(cnt[0])
+            assert int(cnt[1]) == 0 and int(cnt[2]) == 0      # one non-periodic slab: nobody migrates
+            keep = np.ones(n, dtype=bool)
+            keep[holes[:nh]] = False
+            self.parts[i] = np.stack(soa, axis=1)[keep]
+
+    def current_finish(self, w):
+        bca = (C.c_int32 * 4)(*w.bc_particle(0))
+        self.L.emul_current_finish(self.nx, self.ny, self.M, self.ptrs(("jxm", "jrm", "jtm")), bca, self.bcf, self.sc["dy"],
+                                   self.sc["y_grid_min_local"], 1)
+
+    def fields_final(self, w):                  # cylgpu_fields_final
+        sc = self.sc
+        self.update(1)
+        w.set_time(self.time)
+        src = [np.ascontiguousarray(a, dtype=np.float64) for bd in (po.BD_X_MIN, po.BD_X_MAX) for a in w.laser_sources(bd)]
+        sp = (C.c_void_p * 12)(*[a.ctypes.data for a in self.snaps])
+        rp = (C.c_void_p * 4)(*[a.ctypes.data for a in src])
+        self.L.emul_bfield_final_bcs(self.nx, self.ny, self.M, self.ptrs(self.names), sp, rp, self.bcf, sc["dx"], sc["dy"],
+                                     sc["dt"], sc["y_grid_min_local"])
+        self.update(0)
+        self.field_bcs(0)
+
+    def step(self, w):                          # epoch2d.F90:189-266, hotpath.Slab.step_once
+        self.fields_half()
+        self.push(w)
+        self.current_finish(w)
+        self.time = self.time + self.sc["dt"] / 2.0
+        self.time = self.time + self.sc["dt"] / 2.0
+        self.fields_final(w)
+
+
+@pytest.mark.parametrize("deck_name,steps,tol", [("lwfa", 40, 1e-10), ("drift", 12, 1e-6)])
+def test_whole_steps_from_the_product_kernels_track_the_oracle(emul, deck_name, steps, tol):
+    d = {"lwfa": lambda: decks.lwfa(nx=48, ny=16, n_mode=2, ppc_e=4, ppc_p=1, t_centre=8e-15),
+         "drift": lambda: decks.drift(nx=24, ny=12, n_mode=2)}[deck_name]()
+    w = decks.make_oracle(d)            # the uninterrupted oracle run
+    w.call("init_half_step")
+    w.step(2)
+    v = decks.make_oracle(d)            # a second world only lends its laser-source evaluator and boundary codes
+    v.call("init_half_step")
+    v.step(2)
+    e = EmulSlab(emul, w, d)
+    assert not np.shares_memory(e.f["exm"], w.field(0, "exm"))     # pyoracle.field() is a view: the slab owns copies
+    for _ in range(steps):
+        e.step(v)
+        w.step(1)
+    assert abs(e.time - w.scalars()["time"]) < 1e-25
+    qnc = sum(abs(sp.charge) * sp.density * po.C_LIGHT for sp in d.species)
+    for n in e.names[:9]:
+        ref = w.field(0, n)
+        den = np.abs(ref).max()
+        if n.startswith("j"):
+            den = max(den, 1e-3 * qnc)
+        assert den > 0 and np.abs(e.f[n] - ref).max() <= tol * den, (deck_name, n, np.abs(e.f[n] - ref).max() / den)
+    for i in range(len(d.species)):
+        ref = w.particles(0, i).reshape(-1, 7)
+        got = e.parts[i]
+        assert got.shape == ref.shape                      # counts: exact
+        assert np.array_equal(got[:, 6], ref[:, 6])        # the same particles in the same order
+        for cols in (slice(0, 3), slice(3, 6)):
+            den = np.abs(ref[:, cols]).max()
+            assert np.abs(got[:, cols] - ref[:, cols]).max() <= tol * den, (deck_name, i, cols)
