@@ -342,6 +342,22 @@ EMUL_API void emul_field_bcs(int which, int nx, int ny, int M, void* const* f3, 
   for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX, (int)CYLGPU_BD_Y_MAX}) { general(bc_field[bd], op); apply(bd, op); }
 }
 
+// bfield_bcs(mpi_only = true) on one periodic slab: the halo alone (Bxm, Brm with its row shift, Btm)
+EMUL_API void emul_bfield_halo(int nx, int ny, int M, void* const* b3) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  Halo3 h;
+  for (int k = 0; k < 3; ++k) h.f[k] = (cplx*)b3[k];
+  h.skip[0] = 0; h.skip[1] = 1; h.skip[2] = 0;
+  const size_t elems = (size_t)3 * g.M * g.SY * NG;
+  std::vector<cplx> sl(elems), sr(elems);
+  const dim3 hg((g.SY * NG + 127) / 128, g.M, 3);
+  emul_launch(k_halo_pack, hg, dim3(128), g, h, sl.data(), sr.data(), 0, elems);
+  emul_launch(k_halo_unpack, hg, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), 0, elems);
+}
+
 // bfield_final_bcs on ONE slab (bcs.cu::do_bfield_final_bcs_device): bfield_bcs, the laser / outflow line
 // updates on x_min, x_max and r_max (or zero_b), then the halo.  f15: the 15 mode arrays in field-id order;
 // snaps12: the boundary snapshots in snapshot-id order; src4: source1/2 of x_min then x_max, ny + 1 values each.

@@ -463,6 +463,9 @@ class EmulSlab:
         self.names = FIELD_NAMES
         self.time = self.sc["time"]
         self.nx, self.ny, self.M = self.info["nx"], self.info["ny"], d.n_mode
+        self.periodic = w.bc_field()[0] == po.BC_PERIODIC
+        L.emul_bfield_halo.restype = None
+        L.emul_bfield_halo.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         for fn, at in (("emul_update_field", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + [C.c_double] * 4),
                        ("emul_field_bcs", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
                        ("emul_bfield_final_bcs", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -495,7 +498,9 @@ class EmulSlab:
         self.field_bcs(0)
         for n in ("bxm", "brm", "btm"):
             self.f[n + "_old"][...] = self.f[n]
-        self.update(1)                          # (bfield_bcs(mpi_only): nothing to exchange on one open slab)
+        self.update(1)
+        if self.periodic:                       # bfield_bcs(mpi_only): the slab is its own x neighbour
+            self.L.emul_bfield_halo(self.nx, self.ny, self.M, self.ptrs(("bxm", "brm", "btm")))
 
     def push(self, w):                          # particles.cu do_push + do_particle_bcs, push variant 0
         sc, info = self.sc, self.info
@@ -524,10 +529,18 @@ class EmulSlab:
             self.L.emul_pbcs_classify(sp_ptr, n, bc, sc["x_min"], sc["x_max"], info["x_min_local"], info["x_max_local"],
                                       sc["y_max"], sc["dx"], sc["dy"], 1, 1, holes.ctypes.data, flags.ctypes.data, cnt)
             nh = int(cnt[0])
-            assert int(cnt[1]) == 0 and int(cnt[2]) == 0      # one non-periodic slab: nobody migrates
+            after = np.stack(soa, axis=1)
             keep = np.ones(n, dtype=bool)
             keep[holes[:nh]] = False
-            self.parts[i] = np.stack(soa, axis=1)[keep]
+            if self.periodic:
+                # the slab is its own neighbour: what goes left comes back in from the right and is appended first
+                # (partlist_sendrecv order, boundary.F90:1867-1877), then what went right; list order within each
+                left = holes[:nh][flags[:nh] == 1]
+                right = holes[:nh][flags[:nh] == 2]
+                self.parts[i] = np.concatenate([after[keep], after[left], after[right]])
+            else:
+                assert int(cnt[1]) == 0 and int(cnt[2]) == 0      # one non-periodic slab: nobody migrates
+                self.parts[i] = after[keep]
 
     def current_finish(self, w):
         bca = (C.c_int32 * 4)(*w.bc_particle(0))
@@ -555,10 +568,12 @@ class EmulSlab:
         self.fields_final(w)
 
 
-@pytest.mark.parametrize("deck_name,steps,tol", [("lwfa", 40, 1e-10), ("drift", 12, 1e-6)])
+@pytest.mark.parametrize("deck_name,steps,tol", [("lwfa", 40, 1e-10), ("drift", 12, 1e-6), ("thermal", 12, 1e-6)])
 def test_whole_steps_from_the_product_kernels_track_the_oracle(emul, deck_name, steps, tol):
     d = {"lwfa": lambda: decks.lwfa(nx=48, ny=16, n_mode=2, ppc_e=4, ppc_p=1, t_centre=8e-15),
-         "drift": lambda: decks.drift(nx=24, ny=12, n_mode=2)}[deck_name]()
+         "drift": lambda: decks.drift(nx=24, ny=12, n_mode=2),
+         # the shape of BASELINE.json configs[1]: periodic x, reflecting r_max with zero_b, thermal, m = 0..1
+         "thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=6, temp_k=2.0e8)}[deck_name]()
     w = decks.make_oracle(d)            # the uninterrupted oracle run
     w.call("init_half_step")
     w.step(2)
