@@ -12,7 +12,12 @@
 // oracle is therefore anchored only by (i) the analytic expectation of
 // example_decks/current_density_test.deck (DOCUMENTATION.pdf section 7.2), (ii) exact
 // discrete charge continuity of the deposit, (iii) the axis-condition identities and
-// (iv) vacuum-propagation sanity checks -- see tests/test_oracle_*.py.
+// (iv) vacuum-propagation sanity checks, (v) the reference's gaussian_pulse example deck reaching the focus its
+// own constants block designs, (vi) Boris rotation, plasma oscillation and Gauss-law invariants -- see
+// tests/test_oracle*.py.  Only the SDF container (cylindrical_epoch_b200/csrc/sdf_io.cu) is checked by
+// reference code proper: the reference's SDF C reader, compiled into oracle/_ref by oracle/sdf_ref/Makefile.
+// tools/check_against_reference_dumps.py pins this oracle against two restart dumps of the real reference
+// for anyone who can build it.
 //
 // Conventions (all mirror the reference so arrays can be compared element by element):
 //   * mode arrays are Fortran column-major (ix, ir, im), lower bounds (1-ng, 1-ng, 0),
