@@ -396,3 +396,54 @@ __global__ void __launch_bounds__(128) k_zero_b_rmax(Geom g, cplx* bxm, cplx* br
   brm[o] = C(0.0, 0.0);
   btm[o] = C(0.0, 0.0);
 }
+
+// ---- calc_number_density_modes, calc_df.F90:588-661 ----
+// particle_to_grid.inc + triangle/gxfac.inc (with the r < dy fold onto the axis cell), number density =
+// weight / macro-particle volume (partlist.F90:999-1013), mode factor 1 or 2 e^{i m theta}.  A
+// diagnostic (dump steps only): per-particle REDs.
+__global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __restrict__ x, const double* __restrict__ y,
+                                                        const double* __restrict__ z, const double* __restrict__ w,
+                                                        int64_t n, double* __restrict__ out, double x_grid_min_local,
+                                                        double y_grid_min_local, double dx, double dy, double wfac,
+                                                        int nmodes) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double Y = y[i], Z = z[i];
+  const double part_r = sqrt(Y * Y + Z * Z);
+  const double cell_x_r = (x[i] - x_grid_min_local) / dx;
+  const double cell_y_r = (part_r - y_grid_min_local) / dy;
+  int cell_x = (int)floor(cell_x_r + 0.5);
+  int cell_y = (int)floor(cell_y_r + 0.5);
+  const double cell_frac_x = (double)cell_x - cell_x_r;
+  const double cell_frac_y = (double)cell_y - cell_y_r;
+  cell_x += 1;
+  cell_y += 1;
+  const double cx2 = cell_frac_x * cell_frac_x;
+  const double gx[3] = {0.5 * (0.25 + cx2 + cell_frac_x), 0.75 - cx2, 0.5 * (0.25 + cx2 - cell_frac_x)};
+  const double cy2 = cell_frac_y * cell_frac_y;
+  double gy[3] = {0.5 * (0.25 + cy2 + cell_frac_y), 0.75 - cy2, 0.5 * (0.25 + cy2 - cell_frac_y)};
+  if (part_r < dy) {
+    gy[1] = gy[1] + gy[0];
+    gy[0] = 0.0;
+  }
+  const double part_num_dens = (wfac * w[i]) / (2.0 * PI * dx * dy * part_r);   // wfac = 1, or the charge (calc_df.F90:479)
+  const cplx exp_itheta = C(Y, Z) / part_r;
+  cplx exp_imtheta = C(1.0, 0.0);
+  for (int im = 0; im < nmodes; ++im) {
+    cplx mode_fac = C(1.0, 0.0);
+    if (im > 0) {
+      exp_imtheta = exp_imtheta * exp_itheta;
+      mode_fac = 2.0 * exp_imtheta;
+    }
+#pragma unroll
+    for (int iy = -1; iy <= 1; ++iy)
+#pragma unroll
+      for (int ix = -1; ix <= 1; ++ix) {
+        const double v = (gx[ix + 1] * gy[iy + 1]) * part_num_dens;
+        if (v == 0.0) continue;
+        const size_t o = 2 * g.at(cell_x + ix, cell_y + iy, im);
+        atomicAdd(out + o, v * mode_fac.x);
+        if (im > 0) atomicAdd(out + o + 1, v * mode_fac.y);
+      }
+  }
+}

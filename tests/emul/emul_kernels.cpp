@@ -141,6 +141,43 @@ EMUL_API int emul_particle_moment(int nx, int ny, int kind, int direction, int n
   return 0;
 }
 
+// calc_number_density_modes (charge = 0) / calc_charge_density (charge = 1) on ONE slab: bcs.cu::
+// do_number_density_modes -- deposit with the mode factors, reflection, additive ghost exchange, zero gradient.
+// out: complex (nx+2ng, ny+2ng, M) array, zeroed by the caller.
+EMUL_API void emul_number_density_modes(int nx, int ny, int M, int nsel, const double* const* soa, const int64_t* n,
+                                        const double* charge_of, int charge, double x_grid_min_local,
+                                        double y_grid_min_local, double dx, double dy, const int32_t* bca,
+                                        const int32_t* bc_field, void* out) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  cplx* a = (cplx*)out;
+  for (int s = 0; s < nsel; ++s)
+    if (n[s] > 0)
+      emul_launch(k_number_density, dim3((unsigned)((n[s] + 255) / 256)), dim3(256), g, soa[7 * s + 0], soa[7 * s + 1],
+                  soa[7 * s + 2], soa[7 * s + 6], n[s], (double*)a, x_grid_min_local, y_grid_min_local, dx, dy,
+                  charge ? charge_of[s] : 1.0, charge ? 1 : M);
+  const dim3 gx_((g.SY + 127) / 128, g.M), gy_((g.SX + 127) / 128, g.M);
+  if (bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g, a, (int)CYLGPU_BD_X_MIN);
+  if (bca[CYLGPU_BD_X_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gx_, dim3(128), g, a, (int)CYLGPU_BD_X_MAX);
+  if (bca[CYLGPU_BD_Y_MAX] == CYLGPU_BC_REFLECT) emul_launch(k_density_reflect, gy_, dim3(128), g, a, (int)CYLGPU_BD_Y_MAX);
+  if (bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC && bca[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC) {
+    Halo3 h;
+    h.f[0] = a; h.f[1] = nullptr; h.f[2] = nullptr;
+    h.skip[0] = h.skip[1] = h.skip[2] = 0;
+    const size_t elems = (size_t)3 * g.M * g.SY * NG;
+    std::vector<cplx> sl(elems), sr(elems);
+    const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+    emul_launch(k_halo_pack, grd, dim3(128), g, h, sl.data(), sr.data(), 1, elems);
+    emul_launch(k_halo_unpack, grd, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), 1, elems);
+  }
+  if (bc_field[CYLGPU_BD_X_MIN] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gx_, dim3(128), g, a, (int)CYLGPU_BD_X_MIN);
+  if (bc_field[CYLGPU_BD_X_MAX] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gx_, dim3(128), g, a, (int)CYLGPU_BD_X_MAX);
+  if (bc_field[CYLGPU_BD_Y_MIN] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g, a, (int)CYLGPU_BD_Y_MIN);
+  if (bc_field[CYLGPU_BD_Y_MAX] != CYLGPU_BC_PERIODIC) emul_launch(k_density_zero_gradient, gy_, dim3(128), g, a, (int)CYLGPU_BD_Y_MAX);
+}
+
 // The density / averaged moments on TWO slabs that are x neighbours (slab 0 owns x_min, slab 1 owns x_max;
 // periodic: they are also each other's outer neighbours, as in a 2-rank ring): deposit, reflection, the
 // additive ghost exchange of moments.cuh::moment_summation_bcs with the send / receive flags of the product,

@@ -601,3 +601,43 @@ def test_whole_steps_from_the_product_kernels_track_the_oracle(emul, deck_name, 
         for cols in (slice(0, 3), slice(3, 6)):
             den = np.abs(ref[:, cols]).max()
             assert np.abs(got[:, cols] - ref[:, cols]).max() <= tol * den, (deck_name, i, cols)
+
+
+@pytest.mark.parametrize("deck_name", ["thermal", "drift", "lwfa"])
+def test_number_density_modes_kernel_matches_the_oracle(emul, deck_name):
+    """calc_number_density_modes / calc_charge_density (k_number_density with the 2 e^{i m theta} mode factors)"""
+    L = emul
+    L.emul_number_density_modes.restype = None
+    L.emul_number_density_modes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_double), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double,
+                                            C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_void_p]
+    d = {"thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=3, ppc=6),
+         "drift": lambda: decks.drift(nx=20, ny=10, n_mode=2),
+         "lwfa": lambda: decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=2)}[deck_name]()
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(3)
+    sc, info = w.scalars(), w.rank_info(0)
+    bca = (C.c_int32 * 4)(*w.bc_particle(0))
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    for species in [-1] + list(range(len(d.species))):
+        sel = [i for i in range(len(d.species)) if species < 0 or i == species]
+        soa = []
+        for i in sel:
+            p = w.particles(0, i).reshape(-1, 7)
+            soa += [np.ascontiguousarray(p[:, c]) for c in range(7)]
+        ptrs = (C.c_void_p * len(soa))(*[a.ctypes.data for a in soa])
+        n = (C.c_int64 * len(sel))(*[w.nparticles(0, i) for i in sel])
+        q = (C.c_double * len(sel))(*[d.species[i].charge for i in sel])
+        for charge in (0, 1):
+            out = np.zeros((d.n_mode, info["ny"] + 2 * po.NG, info["nx"] + 2 * po.NG), dtype=np.complex128)
+            L.emul_number_density_modes(info["nx"], info["ny"], d.n_mode, len(sel), ptrs, n, q, charge,
+                                        info["x_grid_min_local"], sc["y_grid_min_local"], sc["dx"], sc["dy"], bca, bcf,
+                                        out.ctypes.data)
+            if charge:
+                want = w.charge_density(species)[0]
+                got = out[0].real
+            else:
+                want = w.number_density_modes(species)[0]
+                got = out
+            assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), (deck_name, species, charge)
