@@ -447,3 +447,26 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
       }
   }
 }
+
+// ---- smooth_mode_array, current_smooth.F90:145-196: strided compensated binomial filter ----
+struct Tri3 { cplx* f[3]; };
+// dst(1:nx,1:ny) = alpha*src + (src(ix-s) + src(ix+s) + src(iy-s) + src(iy+s))*beta, three arrays
+__global__ void __launch_bounds__(128) k_smooth(Geom g, Tri3 src, Tri3 dst, double alpha, double beta, int stride) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ix > g.nx) return;
+  const int iy = blockIdx.y + 1;
+  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
+  const cplx* w = src.f[k];
+  const size_t o = g.at(ix, iy, im);
+  const size_t sy = (size_t)stride * g.SX;
+  dst.f[k][o] = alpha * w[o] + (w[o - stride] + w[o + stride] + w[o - sy] + w[o + sy]) * beta;
+}
+// dst(1:nx,1:ny) = src(1:nx,1:ny)
+__global__ void __launch_bounds__(128) k_copy_interior(Geom g, Tri3 src, Tri3 dst) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (ix > g.nx) return;
+  const int iy = blockIdx.y + 1;
+  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
+  const size_t o = g.at(ix, iy, im);
+  dst.f[k][o] = src.f[k][o];
+}

@@ -287,29 +287,6 @@ static int current_bcs_impl(cylgpu_ctx* c, bool with_halo, bool* halo_done) {
 
 int do_current_bcs(cylgpu_ctx* c) { return current_bcs_impl(c, false, nullptr); }
 
-// ---- smooth_mode_array, current_smooth.F90:145-196: strided compensated binomial filter ----
-struct Tri3 { cplx* f[3]; };
-// dst(1:nx,1:ny) = alpha*src + (src(ix-s) + src(ix+s) + src(iy-s) + src(iy+s))*beta, three arrays
-__global__ void __launch_bounds__(128) k_smooth(Geom g, Tri3 src, Tri3 dst, double alpha, double beta, int stride) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (ix > g.nx) return;
-  const int iy = blockIdx.y + 1;
-  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
-  const cplx* w = src.f[k];
-  const size_t o = g.at(ix, iy, im);
-  const size_t sy = (size_t)stride * g.SX;
-  dst.f[k][o] = alpha * w[o] + (w[o - stride] + w[o + stride] + w[o - sy] + w[o + sy]) * beta;
-}
-// dst(1:nx,1:ny) = src(1:nx,1:ny)
-__global__ void __launch_bounds__(128) k_copy_interior(Geom g, Tri3 src, Tri3 dst) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (ix > g.nx) return;
-  const int iy = blockIdx.y + 1;
-  const int im = blockIdx.z / 3, k = blockIdx.z % 3;
-  const size_t o = g.at(ix, iy, im);
-  dst.f[k][o] = src.f[k][o];
-}
-
 static int halo_ptrs(cylgpu_ctx* c, cplx* f0, cplx* f1, cplx* f2) {   // field_mode_bc on three arrays
   Halo3 h;
   h.f[0] = f0; h.f[1] = f1; h.f[2] = f2;

@@ -473,6 +473,48 @@ EMUL_API void emul_current_finish(int nx, int ny, int M, void* const* j3, const 
   if (fill) exchange(0);
 }
 
+// smooth_current on ONE slab (bcs.cu::do_smooth_current): the strided compensated binomial filter on the three J
+// arrays with two ping-pong work sets, the halo of the work set before every pass (self halo when periodic).
+EMUL_API void emul_smooth_current(int nx, int ny, int M, void* const* j3, int its, int comp_its, int nstrides,
+                                  const int32_t* strides_in, int periodic) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  std::vector<int> strides(strides_in, strides_in + nstrides);
+  if (strides.empty()) strides.push_back(1);
+  const size_t nel = g.plane * g.M;
+  cplx* J[3] = {(cplx*)j3[0], (cplx*)j3[1], (cplx*)j3[2]};
+  std::vector<cplx> wk[2][3];
+  for (int s = 0; s < 2; ++s)
+    for (int k = 0; k < 3; ++k) wk[s][k].assign(J[k], J[k] + nel);
+  double alpha = 0.5;
+  const double beta = (1.0 - alpha) * 0.25;
+  int cur = 0;
+  const dim3 grd((g.nx + 127) / 128, g.ny, 3 * g.M);
+  for (int it = 1; it <= its + comp_its; ++it) {
+    for (int stride : strides) {
+      cplx* W[3] = {wk[cur][0].data(), wk[cur][1].data(), wk[cur][2].data()};
+      cplx* D[3] = {wk[cur ^ 1][0].data(), wk[cur ^ 1][1].data(), wk[cur ^ 1][2].data()};
+      if (periodic) {
+        Halo3 h;
+        for (int k = 0; k < 3; ++k) { h.f[k] = W[k]; h.skip[k] = 0; }
+        const size_t elems = (size_t)3 * g.M * g.SY * NG;
+        std::vector<cplx> sl(elems), sr(elems);
+        const dim3 hg((g.SY * NG + 127) / 128, g.M, 3);
+        emul_launch(k_halo_pack, hg, dim3(128), g, h, sl.data(), sr.data(), 0, elems);
+        emul_launch(k_halo_unpack, hg, dim3(128), g, h, (const cplx*)sr.data(), (const cplx*)sl.data(), 0, elems);
+      }
+      Tri3 src{{W[0], W[1], W[2]}}, dst{{D[0], D[1], D[2]}};
+      emul_launch(k_smooth, grd, dim3(128), g, src, dst, alpha, beta, stride);
+      cur ^= 1;
+    }
+    if (it > its) alpha = (double)its * 0.5 + 1.0;
+  }
+  Tri3 src{{wk[cur][0].data(), wk[cur][1].data(), wk[cur][2].data()}}, dst{{J[0], J[1], J[2]}};
+  emul_launch(k_copy_interior, grd, dim3(128), g, src, dst);
+}
+
 // update_e_field / update_b_field of one slab without boundary conditions (fields.cu::launch_update_e / _b).
 // f9: exm erm etm bxm brm btm jxm jrm jtm, complex with ghosts, updated in place.
 EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f9, double dx, double dy, double dt,

@@ -641,3 +641,40 @@ def test_number_density_modes_kernel_matches_the_oracle(emul, deck_name):
                 want = w.number_density_modes(species)[0]
                 got = out
             assert np.abs(got - want).max() <= 1e-13 * np.abs(want).max(), (deck_name, species, charge)
+
+
+@pytest.mark.parametrize("deck_name", ["thermal", "lwfa"])
+@pytest.mark.parametrize("setting", [dict(its=1, comp_its=0, strides=()), dict(its=2, comp_its=1, strides=(1, 2)),
+                                     dict(its=1, comp_its=1, strides=(1, 3, 4))])
+def test_current_smoothing_kernels_match_the_oracle(emul, deck_name, setting):
+    """smooth_current (current_smooth.F90:49-57,145-196) behind current_finish: k_smooth / k_copy_interior with the
+    ping-pong work sets, including the reference's beta / alpha quirk for the compensation pass"""
+    L = emul
+    L.emul_current_finish.restype = None
+    L.emul_current_finish.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.c_double, C.c_double, C.c_int]
+    L.emul_smooth_current.restype = None
+    L.emul_smooth_current.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_int32), C.c_int]
+    d = {"thermal": lambda: decks.thermal(nx=24, ny=12, n_mode=2, ppc=6),
+         "lwfa": lambda: decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=0)}[deck_name]()
+    w = decks.make_oracle(d)
+    w.set_smoothing(True, **setting)
+    w.call("init_half_step")
+    w.step(2)
+    w.call("fields_half")
+    w.call("push")
+    names = ("jxm", "jrm", "jtm")
+    mine = [w.field(0, n).copy() for n in names]
+    ptrs = (C.c_void_p * 3)(*[a.ctypes.data for a in mine])
+    sc, info = w.scalars(), w.rank_info(0)
+    bca = (C.c_int32 * 4)(*w.bc_particle(0))
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    L.emul_current_finish(info["nx"], info["ny"], d.n_mode, ptrs, bca, bcf, sc["dy"], sc["y_grid_min_local"], 1)
+    st = (C.c_int32 * max(len(setting["strides"]), 1))(*setting["strides"])
+    L.emul_smooth_current(info["nx"], info["ny"], d.n_mode, ptrs, setting["its"], setting["comp_its"],
+                          len(setting["strides"]), st, int(w.bc_field()[0] == po.BC_PERIODIC))
+    w.call("current_finish")
+    for n, a in zip(names, mine):
+        ref = w.field(0, n)
+        assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n, setting)
