@@ -53,7 +53,10 @@ def test_dump_from_device_then_restart(tmp_path, nranks):
                     n = ids.index(bid + suffix)
                     got = np.fromfile(os.path.join(out, f"{n}.bin")).reshape(d.ny, d.nx)
                     ref = np.concatenate([m[5:-5, 5:-5] for m in p.oracle.moment(kind, isp, direction)], axis=1)
-                    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), (bid, suffix)
+                    # the device computed them from ITS particles, the oracle from its own (equal to ~1e-12 after
+                    # 4 steps); the temperature of this cold beam (drift / spread = 3400) amplifies that difference
+                    tol = 1e-5 if bid == "temperature" else 1e-9
+                    assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (bid, suffix)
         # a second pair of slabs restarts from the file and both continue
         q = Pair(d, nranks=nranks)
         q.oracle = p.oracle            # one oracle: it is the uninterrupted run
