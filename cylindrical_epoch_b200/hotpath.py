@@ -423,7 +423,13 @@ class Slab:
             if L.r_width > 0.0:
                 a = (yv - 0.0) / L.r_width
                 prof = np.exp(-(a * a))
-            base = t_env * prof * np.sin(L.omega * self.time + (L.phase + L.phase_curv * (yv * yv)))
+            # libm's sin, element by element: the sources then equal the reference's (and the oracle's) bit for
+            # bit, which numpy's vectorised sin does not guarantee
+            if L.phase_curv == 0.0:
+                base = t_env * prof * math.sin(L.omega * self.time + (L.phase + 0.0))
+            else:
+                arg = L.omega * self.time + (L.phase + L.phase_curv * (yv * yv))
+                base = t_env * prof * np.array([math.sin(v) for v in arg])
             s1 = s1 + base * math.cos(L.pol_angle)
             s2 = s2 + base * math.sin(L.pol_angle)
         return s1, s2

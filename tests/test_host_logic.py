@@ -87,8 +87,8 @@ def test_laser_sources_match_oracle():
         s.time = t
         r1, r2 = w.laser_sources(BD_X_MIN)
         g1, g2 = hotpath.Slab.laser_sources(s, BD_X_MIN)
-        np.testing.assert_allclose(g1, r1, rtol=1e-13, atol=1e-13 * np.abs(r1).max())
-        np.testing.assert_allclose(g2, r2, rtol=1e-13, atol=1e-13 * max(np.abs(r2).max(), 1e-300))
+        np.testing.assert_allclose(g1, r1, rtol=1e-14, atol=1e-15 * np.abs(r1).max())
+        np.testing.assert_allclose(g2, r2, rtol=1e-14, atol=1e-15 * max(np.abs(r2).max(), 1e-300))
 
 
 # ------------------------------------------------------------------ world_size 2 over gloo
