@@ -40,7 +40,10 @@ def node_charge(pos, weight, q, x_grid_min, y_grid_min_local, dx, dy, nx, ny):
             ix = cx2 - 1 + b + NG - 1
             iy = cy2 - 1 + a + NG - 1
             ok = (ix >= 0) & (ix < SX) & (iy >= 0) & (iy < SY)
-            Q += np.bincount((iy * SX + ix)[ok], weights=(qw * wx[b] * wy[a])[ok], minlength=SX * SY)
+            idx, val = iy * SX + ix, qw * wx[b] * wy[a]
+            if not ok.all():          # (full-size runs: everything is inside, no masked copies)
+                idx, val = idx[ok], val[ok]
+            Q += np.bincount(idx, weights=val, minlength=SX * SY)
     return Q.reshape(SY, SX)
 
 
