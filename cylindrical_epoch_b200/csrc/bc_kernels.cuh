@@ -470,3 +470,59 @@ __global__ void __launch_bounds__(128) k_copy_interior(Geom g, Tri3 src, Tri3 ds
   const size_t o = g.at(ix, iy, im);
   dst.f[k][o] = src.f[k][o];
 }
+
+// ---- setup_field_boundaries, setup.F90:393-423 (no cpml: nx0 = 1, nx1 = nx) ----
+struct Snaps { cplx* s[CYLGPU_NSNAPS]; };
+__global__ void __launch_bounds__(128) k_snapshot(Geom g, FieldSet F, Snaps S) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (row >= g.SY) return;
+  const int j = row + 1 - NG;
+  const size_t sn = (size_t)im * g.SY + row;
+  const int nx0 = 1, nx1 = g.nx;
+  S.s[0][sn] = 0.5 * (F.exm[g.at(nx0, j, im)] + F.exm[g.at(nx0 - 1, j, im)]);
+  S.s[1][sn] = F.erm[g.at(nx0 - 1, j, im)];
+  S.s[2][sn] = F.etm[g.at(nx0 - 1, j, im)];
+  S.s[3][sn] = F.bxm[g.at(nx0 - 1, j, im)];
+  S.s[4][sn] = 0.5 * (F.brm[g.at(nx0, j, im)] + F.brm[g.at(nx0 - 1, j, im)]);
+  S.s[5][sn] = 0.5 * (F.btm[g.at(nx0, j, im)] + F.btm[g.at(nx0 - 1, j, im)]);
+  S.s[6][sn] = 0.5 * (F.exm[g.at(nx1, j, im)] + F.exm[g.at(nx1 + 1, j, im)]);
+  S.s[7][sn] = F.erm[g.at(nx1, j, im)];
+  S.s[8][sn] = F.etm[g.at(nx1, j, im)];
+  S.s[9][sn] = F.bxm[g.at(nx1, j, im)];
+  S.s[10][sn] = 0.5 * (F.brm[g.at(nx1, j, im)] + F.brm[g.at(nx1 + 1, j, im)]);
+  S.s[11][sn] = 0.5 * (F.btm[g.at(nx1, j, im)] + F.btm[g.at(nx1 + 1, j, im)]);
+}
+
+// ---- shift_fields of the moving window, window.F90:98-153 ----
+// Out-of-place shift by one cell into a spare array, then the pointers are swapped: a
+// pure streaming copy (1 read + 1 write per element) with no in-place hazard.
+__global__ void __launch_bounds__(256) k_shift_x(Geom g, const cplx* __restrict__ src, cplx* __restrict__ dst) {
+  const size_t n = g.plane * g.M;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+    const int col = (int)(t % g.SX);
+    dst[t] = (col < g.SX - 1) ? src[t + 1] : src[t];   // last ghost column keeps its value
+  }
+}
+
+__global__ void __launch_bounds__(128) k_window_fill_xmax(Geom g, FieldSet F, Snaps S) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int im = blockIdx.y;
+  if (row >= g.SY) return;
+  const int j = row + 1 - NG;
+  const int nx = g.nx;
+  const size_t sn = (size_t)im * g.SY + row;
+  // window.F90:114-131, statement order kept
+  F.exm[g.at(nx + 1, j, im)] = S.s[6][sn];
+  F.erm[g.at(nx, j, im)] = S.s[7][sn];
+  F.etm[g.at(nx, j, im)] = S.s[8][sn];
+  F.exm[g.at(nx, j, im)] = 0.5 * (F.exm[g.at(nx - 1, j, im)] + F.exm[g.at(nx + 1, j, im)]);
+  F.erm[g.at(nx - 1, j, im)] = 0.5 * (F.erm[g.at(nx - 2, j, im)] + F.erm[g.at(nx, j, im)]);
+  F.etm[g.at(nx - 1, j, im)] = 0.5 * (F.etm[g.at(nx - 2, j, im)] + F.etm[g.at(nx, j, im)]);
+  F.bxm[g.at(nx, j, im)] = S.s[9][sn];
+  F.brm[g.at(nx + 1, j, im)] = S.s[10][sn];
+  F.btm[g.at(nx + 1, j, im)] = S.s[11][sn];
+  F.bxm[g.at(nx - 1, j, im)] = 0.5 * (F.bxm[g.at(nx - 2, j, im)] + F.bxm[g.at(nx, j, im)]);
+  F.brm[g.at(nx, j, im)] = 0.5 * (F.brm[g.at(nx - 1, j, im)] + F.brm[g.at(nx + 1, j, im)]);
+  F.btm[g.at(nx, j, im)] = 0.5 * (F.btm[g.at(nx - 1, j, im)] + F.btm[g.at(nx + 1, j, im)]);
+}

@@ -473,6 +473,48 @@ EMUL_API void emul_current_finish(int nx, int ny, int M, void* const* j3, const 
   if (fill) exchange(0);
 }
 
+// setup_field_boundaries (bcs.cu::do_snapshot): the twelve x_min / x_max boundary snapshots of E and B
+EMUL_API void emul_snapshot(int nx, int ny, int M, void* const* f15, void* const* snaps12) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  FieldSet F;
+  F.exm = (cplx*)f15[0]; F.erm = (cplx*)f15[1]; F.etm = (cplx*)f15[2];
+  F.bxm = (cplx*)f15[3]; F.brm = (cplx*)f15[4]; F.btm = (cplx*)f15[5];
+  F.jxm = (cplx*)f15[6]; F.jrm = (cplx*)f15[7]; F.jtm = (cplx*)f15[8];
+  F.bxo = (const cplx*)f15[9]; F.bro = (const cplx*)f15[10]; F.bto = (const cplx*)f15[11];
+  F.jxo = (const cplx*)f15[12]; F.jro = (const cplx*)f15[13]; F.jto = (const cplx*)f15[14];
+  Snaps S;
+  for (int k = 0; k < CYLGPU_NSNAPS; ++k) S.s[k] = (cplx*)snaps12[k];
+  emul_launch(k_snapshot, dim3((g.SY + 127) / 128, g.M), dim3(128), g, F, S);
+}
+
+// shift_fields of the moving window on ONE non-periodic slab (bcs.cu::do_shift_fields): the nine arrays move one
+// cell towards x_min (out of place), the x_max columns are refilled from the snapshots
+EMUL_API void emul_shift_fields(int nx, int ny, int M, void* const* f15, void* const* snaps12) {
+  Geom g;
+  g.nx = nx; g.ny = ny; g.M = M;
+  g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
+  g.plane = (size_t)g.SX * g.SY;
+  const size_t nel = g.plane * g.M;
+  std::vector<cplx> spare(nel);
+  const int blocks = (int)((nel + 255) / 256 < 148 * 16 ? (nel + 255) / 256 : 148 * 16);
+  for (int k = 0; k < 9; ++k) {
+    emul_launch(k_shift_x, dim3((unsigned)blocks), dim3(256), g, (const cplx*)f15[k], spare.data());
+    memcpy(f15[k], spare.data(), nel * sizeof(cplx));     // the product swaps the pointers instead
+  }
+  FieldSet F;
+  F.exm = (cplx*)f15[0]; F.erm = (cplx*)f15[1]; F.etm = (cplx*)f15[2];
+  F.bxm = (cplx*)f15[3]; F.brm = (cplx*)f15[4]; F.btm = (cplx*)f15[5];
+  F.jxm = (cplx*)f15[6]; F.jrm = (cplx*)f15[7]; F.jtm = (cplx*)f15[8];
+  F.bxo = (const cplx*)f15[9]; F.bro = (const cplx*)f15[10]; F.bto = (const cplx*)f15[11];
+  F.jxo = (const cplx*)f15[12]; F.jro = (const cplx*)f15[13]; F.jto = (const cplx*)f15[14];
+  Snaps S;
+  for (int k = 0; k < CYLGPU_NSNAPS; ++k) S.s[k] = (cplx*)snaps12[k];
+  emul_launch(k_window_fill_xmax, dim3((g.SY + 127) / 128, g.M), dim3(128), g, F, S);
+}
+
 // smooth_current on ONE slab (bcs.cu::do_smooth_current): the strided compensated binomial filter on the three J
 // arrays with two ping-pong work sets, the halo of the work set before every pass (self halo when periodic).
 EMUL_API void emul_smooth_current(int nx, int ny, int M, void* const* j3, int its, int comp_its, int nstrides,

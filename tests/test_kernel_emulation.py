@@ -678,3 +678,44 @@ def test_current_smoothing_kernels_match_the_oracle(emul, deck_name, setting):
     for n, a in zip(names, mine):
         ref = w.field(0, n)
         assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n, setting)
+
+
+def test_snapshot_and_window_shift_kernels_match_the_oracle(emul):
+    """setup_field_boundaries (setup.F90:393-423) and shift_fields (window.F90:98-153): k_snapshot, k_shift_x,
+    k_window_fill_xmax -- a vacuum laser box whose window moves by one cell"""
+    from pyoracle import FIELD_NAMES, SNAP_NAMES
+    L = emul
+    for fn in ("emul_snapshot", "emul_shift_fields"):
+        getattr(L, fn).restype = None
+        getattr(L, fn).argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    d = decks.lwfa(nx=40, ny=12, n_mode=2, ppc_e=0, ppc_p=0, window=True, t_centre=6e-15)
+    d.species = []
+    w = decks.make_oracle(d)
+    w.call("init_half_step")
+    w.step(6)
+    rng = np.random.default_rng(2)
+    for n in FIELD_NAMES:
+        f = w.field(0, n)
+        f += 1e-2 * max(np.abs(f).max(), 1.0) * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
+    info = w.rank_info(0)
+    # snapshots
+    mine = [w.field(0, n).copy() for n in FIELD_NAMES]
+    snaps = [np.zeros_like(w.field(0, n)) for n in SNAP_NAMES]
+    fp = (C.c_void_p * 15)(*[a.ctypes.data for a in mine])
+    sp = (C.c_void_p * 12)(*[a.ctypes.data for a in snaps])
+    L.emul_snapshot(info["nx"], info["ny"], d.n_mode, fp, sp)
+    w.call("snapshot_boundaries")
+    for n, a in zip(SNAP_NAMES, snaps):
+        assert np.array_equal(a, w.field(0, n)), n
+    # one window shift: the oracle's moving_window shifts as soon as the accumulated fraction passes one cell
+    shifts0 = w.scalars()["window_shifts_total"]
+    for _ in range(4):
+        before = [w.field(0, n).copy() for n in FIELD_NAMES]
+        w.call("moving_window")
+        if w.scalars()["window_shifts_total"] == shifts0 + 1:
+            break
+    assert w.scalars()["window_shifts_total"] == shifts0 + 1
+    fp = (C.c_void_p * 15)(*[a.ctypes.data for a in before])
+    L.emul_shift_fields(info["nx"], info["ny"], d.n_mode, fp, sp)
+    for n, a in zip(FIELD_NAMES[:9], before[:9]):
+        assert np.array_equal(a, w.field(0, n)), n
