@@ -109,6 +109,7 @@ SYMBOLS = {
     "cylgpu_current_bcs": (C.c_int, [H]),
     "cylgpu_sort_particles": (C.c_int, [H]),
     "cylgpu_set_pusher": (C.c_int, [H, C.c_int]),
+    "cylgpu_set_taylor_switch": (C.c_int, [H, C.c_double]),
     "cylgpu_set_sort_interval": (C.c_int, [H, C.c_int]),
     "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
     "cylgpu_number_density_modes": (C.c_int, [H, C.c_int, C.c_void_p]),

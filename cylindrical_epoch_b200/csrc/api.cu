@@ -364,6 +364,7 @@ int cylgpu_particle_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_parti
 int cylgpu_push_no_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_push(c); }
 int cylgpu_current_bcs(cylgpu_handle c) { TRY(check_handle_fields(c)); return do_current_bcs(c); }
 int cylgpu_sort_particles(cylgpu_handle c) { TRY(check_handle(c)); return do_sort(c); }
+int cylgpu_set_taylor_switch(cylgpu_handle c, double v) { TRY(check_handle(c)); c->taylor_switch = v; return 0; }
 int cylgpu_set_pusher(cylgpu_handle c, int higuera_cary) { TRY(check_handle(c)); c->hc_push = higuera_cary != 0; return 0; }
 int cylgpu_set_sort_interval(cylgpu_handle c, int n) { TRY(check_handle(c)); c->sort_interval = n; return 0; }
 int cylgpu_set_push_variant(cylgpu_handle c, int v) { TRY(check_handle(c)); c->push_variant = v; return 0; }

@@ -169,6 +169,7 @@ struct cylgpu_ctx {
   int64_t host_chunk = 1 << 21;   // particles per chunk of the host-resident path (117 MB)
 
   int sort_interval = 1;
+  double taylor_switch = 1.0e-4;  // particles.F90:593; moved only by the conditioning test (cylgpu_set_taylor_switch)
   bool hc_push = false;           // Higuera-Cary instead of Boris (the reference's -DHC_PUSH build)
   // 0 per-particle REDs, 1 warp-window shuffle deposit, 2 strip CTAs + shared-memory field patch,
   // 3 strip CTAs + DMMA outer-product deposit

@@ -81,7 +81,7 @@ __device__ __forceinline__ void deposit_mma(const PushConst& P, const DepositIn&
     for (int im = 1; im < M; ++im) {
       e0 = e0 * D.exp_itheta_05;
       ed = ed * D.exp_idtheta;
-      const ModeFac mf = mode_factors(im, D.dtheta, e0, ed);
+      const ModeFac mf = mode_factors(im, D.dtheta, e0, ed, P.taylor_switch);
       f2[im - 1] = mf.f2; f3[im - 1] = mf.f3; f4[im - 1] = mf.f4;
     }
   }

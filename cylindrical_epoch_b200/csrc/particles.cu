@@ -145,7 +145,7 @@ __device__ __forceinline__ void deposit_window(const PushConst& P, const Deposit
     for (int im = 1; im < M; ++im) {
       e0 = e0 * D.exp_itheta_05;
       ed = ed * D.exp_idtheta;
-      const ModeFac mf = mode_factors(im, D.dtheta, e0, ed);
+      const ModeFac mf = mode_factors(im, D.dtheta, e0, ed, P.taylor_switch);
       f2[im - 1] = mf.f2; f3[im - 1] = mf.f3; f4[im - 1] = mf.f4;
     }
   }
@@ -511,6 +511,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   P.q_fac = S.sp.charge * fac;
   P.deposit = S.sp.zero_current ? 0 : 1;
   P.hc_push = c->hc_push ? 1 : 0;
+  P.taylor_switch = c->taylor_switch;
   P.hc_alpha = 0.5 * S.sp.charge * dt / S.sp.mass;
   const int64_t nb = (S.n + 127) / 128;
   PhaseTimer kernel_timer(c, &c->stats.ms_push_kernel, &c->stats.n_push_kernel, time_kernel);

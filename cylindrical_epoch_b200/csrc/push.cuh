@@ -22,6 +22,7 @@ struct PushConst {
   double hc_alpha;           // 0.5 * part_q * dt / part_m (Higuera-Cary, particles.F90:413)
   int deposit;
   int hc_push;               // the reference's -DHC_PUSH build
+  double taylor_switch;      // |m dtheta| below which m_fac_1..4 use the series: 1.0e-4 (particles.F90:593)
 };
 
 // triangle weights (unnormalised, sum = 2): gx.inc / hx_dcell.inc
@@ -431,12 +432,13 @@ __device__ __forceinline__ void push_one(const PushConst& P, double& part_x, dou
 struct ModeFac {
   cplx f2, f3, f4;
 };
-__device__ __forceinline__ ModeFac mode_factors(int im, double dtheta, cplx exp_imtheta0, cplx exp_imdtheta) {
+__device__ __forceinline__ ModeFac mode_factors(int im, double dtheta, cplx exp_imtheta0, cplx exp_imdtheta,
+                                                 double taylor_switch) {
   const double third = 1.0 / 3.0, sixth = 0.5 * third;
   const double mdth = (double)im * dtheta;
   const double m2dth2 = mdth * mdth;
   ModeFac F;
-  if (fabs(mdth) < 1.0e-4) {
+  if (fabs(mdth) < taylor_switch) {
     const cplx f1 = 2.0 * exp_imtheta0;
     F.f2 = f1 * C(1.0 - sixth * m2dth2, 0.5 * mdth);
     F.f3 = f1 * C(0.5 - 0.125 * m2dth2, third * mdth);

@@ -27,7 +27,7 @@ __device__ __forceinline__ void deposit_global(const PushConst& P, const Deposit
     if (im > 0) {
       exp_imtheta0 = exp_imtheta0 * D.exp_itheta_05;
       exp_imdtheta = exp_imdtheta * D.exp_idtheta;
-      mf = mode_factors(im, D.dtheta, exp_imtheta0, exp_imdtheta);
+      mf = mode_factors(im, D.dtheta, exp_imtheta0, exp_imdtheta, P.taylor_switch);
     }
     cplx jyh[5];
 #pragma unroll

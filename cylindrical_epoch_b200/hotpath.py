@@ -388,6 +388,10 @@ class Slab:
     def set_pusher(self, higuera_cary):       # -DHC_PUSH, particles.F90:409-421
         self._ck(self.L.cylgpu_set_pusher(self.h, int(bool(higuera_cary))))
 
+    def set_taylor_switch(self, v):
+        """test knob: |m dtheta| below which the deposit uses the small-angle series (particles.F90:593, 1.0e-4)"""
+        self._ck(self.L.cylgpu_set_taylor_switch(self.h, float(v)))
+
     def set_deferred_bcs(self, on):
         """cylgpu_push returns before the leaver counts are known; particle_bcs completes at the next call that
         touches particle state (opt-in; removes the device idle time behind the step's host sync)"""

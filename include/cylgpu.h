@@ -249,6 +249,10 @@ int cylgpu_current_bcs(cylgpu_handle h);                    /* boundary.F90:1893
 /* Momentum rotation: 0 = Boris (default build), 1 = Higuera-Cary (the reference's -DHC_PUSH
  * build, particles.F90:409-421). */
 int cylgpu_set_pusher(cylgpu_handle h, int higuera_cary);
+/* Test knob: |m dtheta| below which the deposit factors m_fac_1..4 use the small-angle series.  The reference
+ * hard-codes 1.0e-4 (particles.F90:593), which is the default and what every run uses; tests/ move it on both
+ * sides to show that the closed forms just above the switch, not the kernels, set the parity of hot decks. */
+int cylgpu_set_taylor_switch(cylgpu_handle h, double threshold);
 /* cell-tile sort of the SoA arrays (no reference counterpart: replaces the linked list) */
 int cylgpu_sort_particles(cylgpu_handle h);
 int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = never */

@@ -1059,7 +1059,7 @@ void World::push_rank(Rank& r) {
       for (int im = 0; im < M; ++im) {
         double mdth = (double)im * dtheta;
         double m2dth2 = mdth * mdth;
-        bool small = std::abs(mdth) < 1.0e-4;
+        bool small = std::abs(mdth) < taylor_switch;   // particles.F90:593 (1.0e-4; a test knob moves it)
         double inv_mdth = 0.0, inv_m2dth2 = 0.0;
         if (!small && im > 0) {
           inv_mdth = 1.0 / mdth;

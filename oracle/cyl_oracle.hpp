@@ -227,6 +227,7 @@ struct World {
   void moment_summation_bcs(Arr3 Rank::*f);      // calc_boundary, calc_df.F90:24-31
   void centre_zero_gradient(Arr3 Rank::*f);      // boundary.F90:597-707, c_stagger_centre
   bool smooth_currents = false;                  // shared_data.F90:468-472
+  double taylor_switch = 1.0e-4;                 // |m dtheta| below which particles.F90:593-598 use the series (test knob)
   bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
   int smooth_its = 1, smooth_comp_its = 0;
   std::vector<int> smooth_strides;

@@ -68,6 +68,7 @@ void cylo_get_scalars(void* wp, double* out) {
 }
 void cylo_set_dt(void* w, double dt) { ((World*)w)->dt = dt; }
 void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
+void cylo_set_taylor_switch(void* w, double v) { ((World*)w)->taylor_switch = v; }
 // calc_number_density_modes into each rank's work array; returns rank k's pointer afterwards via cylo_wk_ptr
 void cylo_number_density_modes(void* w, int species) { ((World*)w)->calc_number_density_modes(species); }
 void cylo_charge_density(void* w, int species) { ((World*)w)->calc_charge_density(species); }

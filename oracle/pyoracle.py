@@ -99,6 +99,8 @@ def lib():
         L.cylo_charge_density.argtypes = [C.c_void_p, C.c_int]
         L.cylo_wk_ptr.restype = C.c_void_p
         L.cylo_wk_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_set_taylor_switch.restype = None
+        L.cylo_set_taylor_switch.argtypes = [C.c_void_p, C.c_double]
         L.cylo_set_hc_push.restype = None
         L.cylo_set_hc_push.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_smoothing.restype = None
@@ -217,6 +219,11 @@ class OracleWorld:
             buf = (C.c_double * (2 * shape[0] * shape[1] * shape[2])).from_address(self.L.cylo_wk_ptr(self.h, k))
             out.append(np.frombuffer(buf, dtype=np.complex128).reshape(shape).copy())
         return out
+
+    def set_taylor_switch(self, v):
+        """|m dtheta| below which the deposit uses the small-angle series (particles.F90:593: 1.0e-4); moved only by
+        the test that isolates the conditioning of the closed forms just above the switch"""
+        self.L.cylo_set_taylor_switch(self.h, float(v))
 
     def set_hc_push(self, on):
         """the reference's -DHC_PUSH build: Higuera-Cary gamma instead of Boris'"""

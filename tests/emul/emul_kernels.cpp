@@ -258,7 +258,7 @@ EMUL_API int emul_moment_two_slabs(const int* nx2, int ny, int kind, int directi
 // with ghosts); soa: 7 arrays of n doubles, updated in place.
 EMUL_API int emul_push_v0(int nx, int ny, int M, const void* const* fields6, void* const* j3, double* const* soa,
                           int64_t n, double charge, double mass, int zero_current, int hc_push, double dt, double dx,
-                          double dy, double x_grid_min_local, double y_grid_min_local) {
+                          double dy, double x_grid_min_local, double y_grid_min_local, double taylor_switch) {
   Geom g;
   g.nx = nx; g.ny = ny; g.M = M;
   g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
@@ -302,6 +302,7 @@ EMUL_API int emul_push_v0(int nx, int ny, int M, const void* const* fields6, voi
   P.q_fac = charge * fac;
   P.deposit = zero_current ? 0 : 1;
   P.hc_push = hc_push ? 1 : 0;
+  P.taylor_switch = taylor_switch;   // 1.0e-4 (particles.F90:593) unless the conditioning test moves it
   P.hc_alpha = 0.5 * charge * dt / mass;
   const dim3 grid((unsigned)((n + 127) / 128)), block(128);
 #define EMUL_V0(MM) emul_launch(k_push_v0<MM>, grid, block, P, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5], (const double*)soa[6], n)

@@ -18,6 +18,9 @@ TOL = 1.0e-10
 # in those particles' J_theta terms.  Any 1-ulp change (libm ATAN2, FMA contraction, compiler)
 # therefore moves J by up to ~1e-8 of |J|max on thermal decks; the reference has the same
 # sensitivity to its own compiler flags.  Thermal/drift decks are held to TOL_HOT.
+# ISOLATED by test_hot_decks_reach_tol_with_the_taylor_switch_moved (GPU) and
+# test_hot_deck_tolerance_is_the_taylor_switch_not_the_kernel (CPU emulation of the kernel source): with the switch
+# moved from 1e-4 to 1e-2 on both sides -- nothing else changed -- the same hot decks agree to TOL.
 TOL_HOT = 1.0e-6
 # The charge-conserving deposit adds terms of size ~ q n c per cell that cancel down to the
 # physical current, so J carries an ABSOLUTE rounding noise ~ 1e-16 * ppc * q n c whatever
@@ -36,7 +39,7 @@ class Pair:
     """oracle world + product slabs (one per rank; >1 rank uses the in-process fabric)."""
 
     def __init__(self, deck, nranks=1, init_half_step=True, variant=None, sort_interval=None, host_resident=False,
-                 host_chunk=None, smoothing=None, hc_push=False, prepare=None, slab_kw=None):
+                 host_chunk=None, smoothing=None, hc_push=False, prepare=None, slab_kw=None, taylor_switch=None):
         self.deck = deck
         self.nranks = nranks
         self.oracle = decks.make_oracle(deck, nranks=nranks)
@@ -61,6 +64,10 @@ class Pair:
                 s.set_current_smoothing(True, **smoothing)
         if smoothing is not None:
             self.oracle.set_smoothing(True, **smoothing)
+        if taylor_switch is not None:   # test knob on both sides (particles.F90:593), see TOL_HOT
+            self.oracle.set_taylor_switch(taylor_switch)
+            for s in self.slabs:
+                s.set_taylor_switch(taylor_switch)
         if hc_push:
             self.oracle.set_hc_push(True)
             for s in self.slabs:

@@ -359,3 +359,26 @@ def test_oracle_reproduces_golden_vectors():
         assert a.shape == b.shape, k
         den = np.abs(a).max()
         assert np.abs(a - b).max() <= 1e-12 * max(den, 1e-300), k
+
+
+def test_high_modes_need_a_smaller_dt_multiplier():
+    """A property of the reference's scheme that BASELINE.json's configs[3] (m = 0..4) runs into: with dx = dy the
+    per-mode FDTD (fields.f90:53-312) is unstable on the axis rows for m = 4 at the default dt_multiplier = 0.95 --
+    the i m / r coupling at r = dy / 2 tightens the CFL bound -- and bounded for dt_multiplier <= 0.6.  The thermal
+    noise of a few steps is enough to seed it.  The C4 workload of bench.py and tests/test_zz5_gpu_fullsize.py
+    therefore sets dt_multiplier = 0.5 in its control block (setup.F90:639)."""
+    def top_mode_growth(dtm, steps=45):
+        d = decks.thermal(nx=24, ny=24, n_mode=5, ppc=8)
+        d.dt_multiplier = dtm
+        w = decks.make_oracle(d)
+        w.call("init_half_step")
+        a = []
+        for s in range(steps + 1):
+            if s % 15 == 0 and s:
+                a.append(float(np.abs(w.field(0, "erm")[4]).max()))
+            w.step(1)
+        return a
+    unstable = top_mode_growth(0.95, 30)
+    stable = top_mode_growth(0.5)
+    assert unstable[1] > 1e3 * unstable[0]          # explosive on the axis rows
+    assert stable[2] < 3.0 * stable[0]              # thermal noise level, no growth

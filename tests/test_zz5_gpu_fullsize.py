@@ -37,10 +37,11 @@ def thermal_particles(rng, nx, ny, ppc, dx, dy, x_grid_min_local, temp_k, densit
     return out
 
 
-def _thermal_slab(nx, ny, n_mode, ppc):
+def _thermal_slab(nx, ny, n_mode, ppc, dt_multiplier=0.95):
     bcp = (BC_PERIODIC, BC_PERIODIC, BC_OPEN, BC_REFLECT)
     sp = [ce.Species(-Q0, M0, bcp, False, False, ppc, DENSITY, (TEMP_K,) * 3)]
-    s = ce.Slab(nx, ny, n_mode, 0.0, nx * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], sp)
+    s = ce.Slab(nx, ny, n_mode, 0.0, nx * DXY, ny * DXY, [BC_PERIODIC, BC_PERIODIC, 0, BC_ZERO_B], sp,
+                dt_multiplier=dt_multiplier)
     g = s.grid
     s.upload_particles(0, thermal_particles(np.random.default_rng(7842432), nx, ny, ppc, g.dx, g.dy,
                                             g.x_grid_min_local, TEMP_K, DENSITY))
@@ -56,12 +57,18 @@ def _residual(s, nx, ny):
     return r, f, parts
 
 
-@pytest.mark.parametrize("name,nx,ny,n_mode,ppc", [
-    ("C2 thermal 2048x256 m=0..1 64 ppc", 2048, 256, 2, 64),      # BASELINE.json configs[1], the bench workload
-    ("C4 modes 4096x512 m=0..4 16 ppc", 4096, 512, 5, 16),        # BASELINE.json configs[3]
+# C4's dt_multiplier: the reference's per-mode FDTD is UNSTABLE on the axis rows for m >= 4 at the default
+# dt_multiplier = 0.95 with dx = dy (the i m / r coupling at r = dy / 2 tightens the CFL bound; mode 4 grows ~15x
+# per 3 steps in the oracle, bounded for dt_multiplier <= 0.6: tests/test_oracle.py::
+# test_high_modes_need_a_smaller_dt_multiplier).  Round 1 ran this case at 0.95 and the energy "drift" was 71x in
+# 6 steps on the B200 -- the reference scheme's own instability, reproduced.  A user of m = 0..4 has to set
+# dt_multiplier in the control block (setup.F90:639); 0.5 here.
+@pytest.mark.parametrize("name,nx,ny,n_mode,ppc,dt_multiplier", [
+    ("C2 thermal 2048x256 m=0..1 64 ppc", 2048, 256, 2, 64, 0.95),      # BASELINE.json configs[1]
+    ("C4 modes 4096x512 m=0..4 16 ppc", 4096, 512, 5, 16, 0.5),         # BASELINE.json configs[3]
 ])
-def test_full_size_periodic_plasma_properties(name, nx, ny, n_mode, ppc):
-    s = _thermal_slab(nx, ny, n_mode, ppc)
+def test_full_size_periodic_plasma_properties(name, nx, ny, n_mode, ppc, dt_multiplier):
+    s = _thermal_slab(nx, ny, n_mode, ppc, dt_multiplier)
     try:
         n0 = s.particle_count(0)
         assert n0 == nx * ny * ppc
