@@ -130,7 +130,7 @@ SYMBOLS = {
     "cylgpu_stats": (C.c_int, [H, C.POINTER(Stats)]),
     "cylgpu_reset_stats": (C.c_int, [H]),
     "cylgpu_set_timing": (C.c_int, [H, C.c_int]),
-    "cylgpu_set_deferred_bcs": (C.c_int, [H, C.c_int]),
+    "cylgpu_set_exchange_capacity": (C.c_int, [H, C.c_int64]),
 }
 
 _LIB = None

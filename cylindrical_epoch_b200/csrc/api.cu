@@ -19,18 +19,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// entry points that never look at particle state (field phases, current_finish, field boundary pieces): a
-// deferred particle_bcs stays outstanding across them -- that is the point of deferring it
+// entry points of the step itself (field phases, push, current_finish, window, particle_bcs, column insertion):
+// they work with device-resident particle counts and never wait for the device
 static int check_handle_fields(cylgpu_handle h) {
   if (!h) { set_error("null cylgpu handle"); return 1; }
   cudaError_t e = cudaSetDevice(h->device);
   if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e)); return 1; }
   return 0;
 }
-// everything else first finishes what cylgpu_push left outstanding (no-op unless cylgpu_set_deferred_bcs)
+// everything else sees exact particle counts on the host (no-op unless cylgpu_set_exchange_capacity > 0 has left
+// the counts on the device: then this waits for the newest copy)
 static int check_handle(cylgpu_handle h) {
   TRY(check_handle_fields(h));
-  return complete_pending_bcs(h);
+  return poll_counts(h, true);
 }
 
 static void set_neighbours(cylgpu_ctx* c) {
@@ -105,6 +106,10 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   CUDA_TRY(cudaMemsetAsync(c->counters, 0, 32 * sizeof(unsigned long long), c->stream));
   CUDA_TRY(cudaMallocHost(&c->h_counters, 32 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMalloc(&c->d_energy, 2 * sizeof(double)));
+  CUDA_TRY(cudaMalloc(&c->n_dev, (CYLGPU_MAX_SPECIES + PST_N) * sizeof(int64_t)));
+  CUDA_TRY(cudaMemsetAsync(c->n_dev, 0, (CYLGPU_MAX_SPECIES + PST_N) * sizeof(int64_t), c->stream));
+  CUDA_TRY(cudaMalloc(&c->d_plan, sizeof(CompactPlan)));
+  CUDA_TRY(cudaMallocHost(&c->h_pub, 8 * (CYLGPU_MAX_SPECIES + PST_N) * sizeof(int64_t)));
   if (build_tables(c)) return 1;
   set_neighbours(c);
   c->tr = make_transport(c);
@@ -143,7 +148,14 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   c->timers.destroy();
   if (c->ev_wait) cudaEventDestroy(c->ev_wait);
-  if (c->pending.ev) cudaEventDestroy(c->pending.ev);
+  cudaFree(c->n_dev); cudaFree(c->d_plan);
+  if (c->h_pub) cudaFreeHost(c->h_pub);
+  for (int k = 0; k < 8; ++k) if (c->pub[k].ev) cudaEventDestroy(c->pub[k].ev);
+  for (int k = 0; k < 4; ++k) {
+    if (c->app_pin[k]) cudaFreeHost(c->app_pin[k]);
+    cudaFree(c->app_dev[k]);
+    if (c->app_ev[k]) cudaEventDestroy(c->app_ev[k]);
+  }
   if (c->ins_pin) cudaFreeHost(c->ins_pin);
   cudaFree(c->ins_dev);
   if (c->ins_ev) cudaEventDestroy(c->ins_ev);
@@ -295,8 +307,69 @@ static int append_impl(cylgpu_handle c, int isp, int64_t n, const double* host_a
   S.n += n;
   c->stats.n_particles[isp] = S.n;
   c->sorted_valid = false;
+  return set_count_exact(c, isp);
+}
+
+}  // extern "C"
+
+namespace cylgpu {
+__global__ void k_add_count_api(int64_t* n_dev, long long add) { *n_dev += add; }
+__global__ void __launch_bounds__(256) k_aos_to_soa_dev(const double* __restrict__ aos, double* d0, double* d1,
+                                                        double* d2, double* d3, double* d4, double* d5, double* d6,
+                                                        const int64_t* __restrict__ base_dev, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t base = *base_dev;
+  const double* p = aos + 7 * i;
+  d0[base + i] = p[0]; d1[base + i] = p[1]; d2[base + i] = p[2];
+  d3[base + i] = p[3]; d4[base + i] = p[4]; d5[base + i] = p[5]; d6[base + i] = p[6];
+}
+
+// A freshly generated plasma column (window.F90:157-300) joins the list without a host sync: the records go
+// through a ring of pinned staging buffers (the caller's array is free again on return), the kernel appends
+// them behind the device-side count.  With host-side counts (xcap = 0) the same, at the host's count.
+int append_async(cylgpu_ctx* c, int isp, int64_t n, const double* host_aos) {
+  if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
+  if (n <= 0) return 0;
+  SpeciesState& S = c->species[isp];
+  TRY(reserve_particles(c, isp, S.n + n));
+  const int slot = c->app_slot;
+  c->app_slot = (c->app_slot + 1) & 3;
+  if (c->app_ev[slot]) CUDA_TRY(cudaEventSynchronize(c->app_ev[slot]));   // long done: 4 columns ago
+  else CUDA_TRY(cudaEventCreateWithFlags(&c->app_ev[slot], cudaEventDisableTiming));
+  if (c->app_cap[slot] < n) {
+    if (c->app_pin[slot]) cudaFreeHost(c->app_pin[slot]);
+    if (c->app_dev[slot]) cudaFree(c->app_dev[slot]);
+    const int64_t cap = n + n / 4 + 256;
+    CUDA_TRY(cudaMallocHost(&c->app_pin[slot], (size_t)cap * 7 * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&c->app_dev[slot], (size_t)cap * 7 * sizeof(double)));
+    c->app_cap[slot] = cap;
+  }
+  memcpy(c->app_pin[slot], host_aos, (size_t)n * 7 * sizeof(double));
+  CUDA_TRY(cudaMemcpyAsync(c->app_dev[slot], c->app_pin[slot], (size_t)n * 7 * sizeof(double), cudaMemcpyHostToDevice,
+                           c->stream));
+  CUDA_TRY(cudaEventRecord(c->app_ev[slot], c->stream));
+  if (S.lazy) {
+    k_aos_to_soa_dev<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->app_dev[slot], S.d[0], S.d[1], S.d[2], S.d[3],
+                                                                        S.d[4], S.d[5], S.d[6], c->n_dev + isp, n);
+    k_add_count_api<<<1, 1, 0, c->stream>>>(c->n_dev + isp, (long long)n);
+    c->stats.kernel_launches += 2;
+    S.n += n;   // the bound moves with the count
+  } else {
+    k_aos_to_soa<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->app_dev[slot], S.d[0], S.d[1], S.d[2], S.d[3],
+                                                                    S.d[4], S.d[5], S.d[6], S.n, n);
+    c->stats.kernel_launches += 1;
+    S.n += n;
+    TRY(set_count_exact(c, isp));
+  }
+  CUDA_TRY(cudaGetLastError());
+  c->stats.n_particles[isp] = S.n;
+  c->sorted_valid = false;
   return 0;
 }
+}  // namespace cylgpu
+
+extern "C" {
 
 int cylgpu_upload_particles(cylgpu_handle c, int isp, int64_t n, const double* host_aos) {
   TRY(check_handle(c));
@@ -335,7 +408,7 @@ int cylgpu_download_particles(cylgpu_handle c, int isp, int64_t capacity, double
 
 int cylgpu_particle_count(cylgpu_handle c, int isp, int64_t* n_out) {
   if (!c || isp < 0 || isp >= c->cfg.n_species || !n_out) { set_error("bad argument"); return 2; }
-  TRY(complete_pending_bcs(c));   // a deferred particle_bcs still owes its departures and arrivals
+  TRY(poll_counts(c, true));   // device-resident counts: wait for the newest copy
   *n_out = c->species[isp].n;
   return 0;
 }
@@ -360,7 +433,7 @@ int cylgpu_bfield_final_bcs(cylgpu_handle c, const double* a, const double* b, c
   TRY(check_handle_fields(c));
   return do_bfield_final_bcs(c, a, b, d, e);
 }
-int cylgpu_particle_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_particle_bcs(c); }
+int cylgpu_particle_bcs(cylgpu_handle c) { TRY(check_handle_fields(c)); return do_particle_bcs(c); }
 int cylgpu_push_no_bcs(cylgpu_handle c) { TRY(check_handle(c)); return do_push(c); }
 int cylgpu_current_bcs(cylgpu_handle c) { TRY(check_handle_fields(c)); return do_current_bcs(c); }
 int cylgpu_sort_particles(cylgpu_handle c) { TRY(check_handle(c)); return do_sort(c); }
@@ -439,7 +512,7 @@ int cylgpu_fields_half(cylgpu_handle c) {
 
 // particles.F90:28-734 (push + r_min fold + particle_bcs)
 int cylgpu_push(cylgpu_handle c) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   PhaseTimer t(c, &c->stats.ms_push);
   return do_push_bcs(c);
 }
@@ -498,28 +571,29 @@ int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2mi
 // window.F90:62-94, one cell.  grid5 = {x_grid_min_local, x_min, x_max, x_min_local,
 // x_max_local} AFTER the host's setup_grid_x for the shifted window.
 int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* const* new_aos, const double* grid5) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   if (!grid5) { set_error("window_shift needs the shifted grid"); return 2; }
   c->graph_epoch += 1;   // shift_fields swaps array pointers
   if (n_new && new_aos) {
     for (int isp = 0; isp < c->cfg.n_species; ++isp)
-      if (n_new[isp] > 0) TRY(append_impl(c, isp, n_new[isp], new_aos[isp]));
+      if (n_new[isp] > 0) TRY(append_async(c, isp, n_new[isp], new_aos[isp]));
   }
   c->x_grid_min_local = grid5[0];
   c->x_min = grid5[1]; c->x_max = grid5[2];
   c->x_min_local = grid5[3]; c->x_max_local = grid5[4];
   TRY(do_remove_behind(c));
+  if (c->xcap > 0) TRY(publish_counts(c));
   return do_shift_fields(c);
 }
 
 // ---- moving-window plasma column with the reference's random stream ----
 int cylgpu_rng_init(cylgpu_handle c, int seed) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));   // host-side generator state only
   kiss_init(c->rng, seed);
   return 0;
 }
 int cylgpu_rng_set_state(cylgpu_handle c, const int32_t* xyzw, int cached, double cached_value) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));   // host-side generator state only
   if (!xyzw) { set_error("rng_set_state: null state"); return 2; }
   c->rng.x = (uint32_t)xyzw[0]; c->rng.y = (uint32_t)xyzw[1]; c->rng.z = (uint32_t)xyzw[2]; c->rng.w = (uint32_t)xyzw[3];
   c->rng.cached = cached != 0;
@@ -527,7 +601,7 @@ int cylgpu_rng_set_state(cylgpu_handle c, const int32_t* xyzw, int cached, doubl
   return 0;
 }
 int cylgpu_rng_get_state(cylgpu_handle c, int32_t* xyzw, int* cached, double* cached_value) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));   // host-side generator state only
   if (!xyzw || !cached || !cached_value) { set_error("rng_get_state: null argument"); return 2; }
   xyzw[0] = (int32_t)c->rng.x; xyzw[1] = (int32_t)c->rng.y; xyzw[2] = (int32_t)c->rng.z; xyzw[3] = (int32_t)c->rng.w;
   *cached = c->rng.cached;
@@ -540,7 +614,7 @@ int cylgpu_rng_flush_cache(cylgpu_handle c) {   // random_flush_cache, called by
   return 0;
 }
 int cylgpu_rng_uniform(cylgpu_handle c, double* out) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));   // host-side generator state only
   if (!out) { set_error("rng_uniform: null argument"); return 2; }
   *out = kiss_uniform(c->rng);
   return 0;
@@ -548,14 +622,14 @@ int cylgpu_rng_uniform(cylgpu_handle c, double* out) {
 int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell, const double* density,
                             const double* temperature, const double* drift, double dmin, double dmax,
                             int64_t* n_inserted) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   if (isp < 0 || isp >= c->cfg.n_species || !c->species[isp].set) { set_error("bad species index"); return 2; }
   if (!density || !temperature || !drift) { set_error("insert_particles: null profile"); return 2; }
   std::vector<double> aos;
   TRY(do_insert_particles(c, isp, x_grid_max, npart_per_cell, density, temperature, drift, dmin, dmax, aos));
   const int64_t n = (int64_t)(aos.size() / 7);
   if (n_inserted) *n_inserted = n;
-  if (n > 0) TRY(append_impl(c, isp, n, aos.data()));
+  if (n > 0) TRY(append_async(c, isp, n, aos.data()));
   return 0;
 }
 
@@ -682,7 +756,7 @@ int cylgpu_sdf_load(cylgpu_handle c, const char* path, cylgpu_sdf_desc* d) {
 int cylgpu_insert_particles_device(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell,
                                    const double* density, const double* temperature, const double* drift, double dmin,
                                    double dmax, uint64_t seed, uint64_t column, int64_t* n_inserted) {
-  TRY(check_handle(c));
+  TRY(check_handle_fields(c));
   if (isp < 0 || isp >= c->cfg.n_species || !c->species[isp].set) { set_error("bad species index"); return 2; }
   if (!density || !temperature || !drift) { set_error("insert_particles_device: null profile"); return 2; }
   return do_insert_particles_device(c, isp, x_grid_max, npart_per_cell, density, temperature, drift, dmin, dmax, seed,
@@ -727,6 +801,7 @@ int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return 
 
 int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {
   if (!c || !out) { set_error("bad argument"); return 2; }
+  TRY(poll_counts(c, true));
   c->timers.drain();
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) c->stats.n_particles[i] = c->species[i].n;
   *out = c->stats;
@@ -741,12 +816,13 @@ int cylgpu_reset_stats(cylgpu_handle c) {
   c->stats.n_push_kernel = 0;
   return 0;
 }
-// opt-in: cylgpu_push returns without waiting for the leaver counts of the last species; the rest of its
-// particle_bcs runs at the next call that touches particle state (see ctx.cuh PendingBcs).  Results are
-// the same; with several ranks every rank must make the same sequence of calls (the completion exchanges).
-int cylgpu_set_deferred_bcs(cylgpu_handle c, int on) {
+// Device-resident particle counts (ctx.cuh): capacity > 0 = particles per direction of the fixed-size migration
+// message, and no host sync inside a step; 0 = the exact two-message protocol.  Every rank sets the same value.
+int cylgpu_set_exchange_capacity(cylgpu_handle c, int64_t capacity) {
   TRY(check_handle(c));
-  c->deferred_bcs = on != 0;
+  if (capacity < 0 || capacity > ((int64_t)1 << 28)) { set_error("exchange capacity out of range"); return 2; }
+  c->xcap = capacity;
+  for (int i = 0; i < c->cfg.n_species; ++i) TRY(set_count_exact(c, i));
   return 0;
 }
 int cylgpu_set_timing(cylgpu_handle c, int on) {

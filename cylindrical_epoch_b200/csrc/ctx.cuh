@@ -42,6 +42,10 @@ struct SpeciesState {
   int64_t alt_cap = 0;
   int* cell_start = nullptr;   // exclusive scan of the sort buckets of the last sort, ncell + 1 entries
   int64_t cell_start_n = 0;
+  // Device-resident count (cylgpu_set_exchange_capacity > 0): the exact count then lives on the device
+  // (cylgpu_ctx::n_dev[isp]) and `n` above is an UPPER BOUND of it -- enough for grid sizes and capacities --
+  // until the next publish has been read back (poll_counts).  lazy = false: `n` is exact.
+  bool lazy = false;
 };
 
 struct Timer {
@@ -133,6 +137,28 @@ struct cylgpu_ctx {
   int64_t ncell = 0;
   double* psend_l = nullptr; double* psend_r = nullptr; double* precv = nullptr;
   int64_t psend_l_cap = 0, psend_r_cap = 0, precv_cap = 0;
+  // ---- device-resident particle counts (no host sync inside a step) ----
+  // xcap > 0: migrating particles travel in ONE fixed-size message per neighbour, [count header][xcap slots],
+  // leaver counts, compaction and arrivals are handled by kernels that read the counts on the device, and the
+  // host only keeps upper bounds of the list lengths.  xcap = 0: the exact protocol (counts first, then the
+  // payload: two host syncs per species per step).
+  int64_t xcap = 0;
+  int64_t* n_dev = nullptr;                 // device: [CYLGPU_MAX_SPECIES] exact counts, then [PST_N] statistics
+  cylgpu::CompactPlan* d_plan = nullptr;
+  struct Publish {
+    cudaEvent_t ev = nullptr;
+    int64_t bound_at[CYLGPU_MAX_SPECIES];   // the host's upper bounds when the copy was enqueued
+    bool pending = false;
+  } pub[8];
+  int64_t* h_pub = nullptr;                 // pinned: 8 slots of [CYLGPU_MAX_SPECIES + PST_N]
+  uint64_t pub_head = 0;
+  bool overflowed = false;                  // sticky: a fixed-size exchange met more migrants than xcap
+  // window columns on their way to the device: pinned ring (append_async)
+  double* app_pin[4] = {0, 0, 0, 0};
+  double* app_dev[4] = {0, 0, 0, 0};
+  int64_t app_cap[4] = {0, 0, 0, 0};
+  cudaEvent_t app_ev[4] = {0, 0, 0, 0};
+  int app_slot = 0;
   unsigned long long* counters = nullptr;   // device counters (8 of them)
   unsigned long long* h_counters = nullptr; // pinned mirror
   double* d_energy = nullptr;
@@ -182,17 +208,6 @@ struct cylgpu_ctx {
   bool timing = true;
   bool blocking_wait = false;     // host syncs yield the core instead of spinning (multi-rank hosts)
   cudaEvent_t ev_wait = nullptr;
-  // Deferred completion of particle_bcs (cylgpu_set_deferred_bcs, opt-in): cylgpu_push enqueues the push
-  // kernel and the copy of its leaver counts and returns; the count sync, compaction, exchange and arrivals
-  // of the LAST species happen when the next call that touches particle state comes in -- after the host has
-  // enqueued current_finish and the field phases, so the device never waits for the host behind the sync.
-  bool deferred_bcs = false;
-  struct PendingBcs {
-    bool active = false;
-    int isp = -1;
-    cudaEvent_t ev = nullptr;        // recorded behind the device->host copy of the counters
-    unsigned char B[160];            // the BcsConst of the push (particles.cu), opaque here
-  } pending;
 };
 
 namespace cylgpu {
@@ -220,7 +235,10 @@ int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip
 // particles.cu
 int do_push(cylgpu_ctx* c);
 int do_push_bcs(cylgpu_ctx* c);
-int complete_pending_bcs(cylgpu_ctx* c);   // no-op unless a deferred particle_bcs is outstanding
+int poll_counts(cylgpu_ctx* c, bool block);      // tighten (block: make exact) the host's particle counts
+int publish_counts(cylgpu_ctx* c);               // enqueue the device -> host copy of counts + statistics
+int set_count_exact(cylgpu_ctx* c, int isp);     // the host changed species[isp].n: mirror it on the device
+int append_async(cylgpu_ctx* c, int isp, int64_t n, const double* host_aos);
 int do_particle_bcs(cylgpu_ctx* c);
 int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
                  int64_t* n_out);

@@ -46,4 +46,9 @@ struct Geom {
   }
 };
 
+// particle_bcs with device-resident counts (compact_kernels.cuh): the plan of one compaction and the per-step
+// statistics kept on the device
+enum { PST_SENT_L = 0, PST_SENT_R = 1, PST_REMOVED = 2, PST_RECV = 3, PST_WINDOW_REMOVED = 4, PST_OVERFLOW = 5, PST_N = 8 };
+struct CompactPlan { long long nholes, n_new, n_left, n_right; };
+
 }  // namespace cylgpu

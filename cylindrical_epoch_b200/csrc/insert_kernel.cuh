@@ -10,6 +10,7 @@ struct ColumnArgs {
   const int64_t* row_start;  // ny + 1 entries, row iy -> [row_start[iy-1], row_start[iy])
   double *x, *y, *z, *px, *py, *pz, *w;
   int64_t base;
+  const int64_t* base_dev;   // not null: the list length lives on the device (device-resident counts)
   int ny, iy_global_offset;
   double dx, dy, x0, y_grid_min_local, mass;
 };
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128) k_insert_column(ColumnArgs a) {
     double weight_local = 0.0;
 #pragma unroll
     for (int k = -1; k <= 1; ++k) weight_local = weight_local + gy[k + 1] * a.prof[iy + k];
-    const int64_t o = a.base + r0 + ip;
+    const int64_t o = (a.base_dev ? *a.base_dev : a.base) + r0 + ip;
     a.x[o] = X;
     a.y[o] = part_r * cos(part_theta);
     a.z[o] = part_r * sin(part_theta);

@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
 }
 
 #include "pbcs_kernels.cuh"
+#include "compact_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------
 // variant 2: strip CTAs.  The sort of this push (do_sort) left the particles ordered by the
@@ -474,7 +475,9 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   const double dt = c->dt;
   cylgpu::SpeciesState& S = c->species[isp];
   if (fused_out) *fused_out = false;
+  if (!strips && S.lazy) TRY(poll_counts(c, true));   // k_push_v0 / v1 take the exact count
   if (!S.set || S.sp.immobile || S.n == 0) return 0;
+  if (c->xcap > 0 && fuse_bcs) TRY(reserve_particles(c, isp, S.n + 2 * c->xcap));   // arrivals of this step
   if (need_sort) {
     PhaseTimer sort_timer(c, &c->stats.ms_sort);
     TRY(do_sort_species(c, isp, /*physical=*/!strips));
@@ -622,7 +625,6 @@ __global__ void __launch_bounds__(256) k_flag_behind(const double* __restrict__ 
   if (x[i] < x_min) record_leaver(hole_list, hole_flag, cnt, (uint32_t)i, FL_GONE);
 }
 
-struct Soa { double* d[7]; };
 
 // second pass over the leavers: pack the migrants in pack_particle order (7 doubles), split the
 // holes into those below the new count (to be filled) and those in the tail (marked)
@@ -703,7 +705,7 @@ static int compact(cylgpu_ctx* c, cylgpu::SpeciesState& S, int64_t nholes, int64
   }
   CUDA_TRY(cudaGetLastError());
   S.n = n_new;
-  return 0;
+  return 0;   // (callers mirror the count on the device where device-resident counts are on)
 }
 
 // The step's host syncs (particle counts) wait for the whole push kernel.  With one rank per GPU on
@@ -756,7 +758,7 @@ static int grow_dbuf_keep(double** p, int64_t* cap, int64_t need, int64_t keep, 
 // classification, removal of the leavers (hole filling) and packing of the migrants behind the
 // `off_l` / `off_r` particles already waiting in psend_l / psend_r.  One host sync (the counts).
 static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off_l, int64_t off_r, int64_t* nleft_out,
-                                 int64_t* nright_out, bool classified_by_push = false, bool counts_ready = false) {
+                                 int64_t* nright_out, bool classified_by_push = false) {
   unsigned long long* cnt = c->counters;        // 8 for classify
   unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
   cylgpu::SpeciesState& S = c->species[isp];
@@ -770,11 +772,8 @@ static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off
       c->stats.kernel_launches += 1;
     }
   }
-  if (!counts_ready) {   // (deferred completion: the copy was enqueued behind the push kernel and has been waited for)
-    CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                             c->stream));
-    TRY(host_wait(c));
-  }
+  CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  TRY(host_wait(c));
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
@@ -820,11 +819,166 @@ static int pbcs_exchange(cylgpu_ctx* c, int64_t nleft, int64_t nright, int64_t* 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// particle_bcs with DEVICE-RESIDENT counts (cylgpu_set_exchange_capacity > 0): the same steps as
+// pbcs_classify_compact / pbcs_exchange / the arrivals of pbcs_species, but every count (leavers, migrants per
+// direction, arrivals, the new list length) is read by the kernels from device memory, and the migrants of
+// one direction travel in ONE message of fixed size -- [7-double header: count][xcap slots of 7 doubles] --
+// so that the host never waits for the device inside a step.  The host keeps upper bounds of the list
+// lengths (SpeciesState::n with lazy = true) and tightens them from copies that trail behind (poll_counts).
+// Replaces the two MPI_SENDRECVs per direction of partlist_sendrecv (partlist.F90:842,869: count, then data).
+// ------------------------------------------------------------------------------------------
+// (kernels: compact_kernels.cuh)
+// the host's count of species isp is exact and has just changed: mirror it on the device
+__global__ void k_set_count(int64_t* n_dev, long long v) { *n_dev = v; }
+int set_count_exact(cylgpu_ctx* c, int isp) {
+  if (!c->n_dev) return 0;
+  k_set_count<<<1, 1, 0, c->stream>>>(c->n_dev + isp, (long long)c->species[isp].n);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// enqueue the copy of the device counts and statistics to the host (ring of 8; nobody waits here)
+int publish_counts(cylgpu_ctx* c) {
+  const int slot = (int)(c->pub_head % 8);
+  cylgpu_ctx::Publish& P = c->pub[slot];
+  if (P.pending) TRY(poll_counts(c, false));
+  if (P.pending) {   // the host is 8 publishes ahead of the device: wait for this slot
+    CUDA_TRY(cudaEventSynchronize(P.ev));
+    TRY(poll_counts(c, false));
+  }
+  if (!P.ev) CUDA_TRY(cudaEventCreateWithFlags(&P.ev, cudaEventDisableTiming));
+  const size_t words = CYLGPU_MAX_SPECIES + PST_N;
+  CUDA_TRY(cudaMemcpyAsync(c->h_pub + (size_t)slot * words, c->n_dev, words * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+  CUDA_TRY(cudaEventRecord(P.ev, c->stream));
+  for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) P.bound_at[i] = c->species[i].n;
+  P.pending = true;
+  c->pub_head += 1;
+  return 0;
+}
+
+// Tighten the host's upper bounds with the newest copy that has arrived: bound -= (bound then - exact then).
+// block = true waits for the newest copy, after which every count is exact again (every device-side change of
+// a count is followed by a publish).
+int poll_counts(cylgpu_ctx* c, bool block) {
+  if (!c->n_dev || c->pub_head == 0) return 0;
+  const size_t words = CYLGPU_MAX_SPECIES + PST_N;
+  bool any_lazy = false;
+  for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) any_lazy = any_lazy || c->species[i].lazy;
+  for (uint64_t back = 0; back < 8 && back < c->pub_head; ++back) {
+    const uint64_t id = c->pub_head - 1 - back;
+    cylgpu_ctx::Publish& P = c->pub[id % 8];
+    if (!P.pending) break;   // everything older has been consumed already
+    if (back == 0 && block) CUDA_TRY(cudaEventSynchronize(P.ev));
+    else if (cudaEventQuery(P.ev) != cudaSuccess) { cudaGetLastError(); continue; }
+    const int64_t* h = c->h_pub + (size_t)(id % 8) * words;
+    for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) {
+      cylgpu::SpeciesState& S = c->species[i];
+      if (!S.lazy) continue;
+      const int64_t slack = P.bound_at[i] - h[i];
+      S.n -= slack;
+      // the copies still on their way were enqueued with bounds that contain this slack
+      for (uint64_t b2 = 0; b2 < back; ++b2) c->pub[(c->pub_head - 1 - b2) % 8].bound_at[i] -= slack;
+      if (back == 0) S.lazy = false;   // the newest publish: nothing has changed since
+    }
+    const int64_t* ps = h + CYLGPU_MAX_SPECIES;
+    c->stats.n_sent_left = ps[PST_SENT_L];
+    c->stats.n_sent_right = ps[PST_SENT_R];
+    c->stats.n_removed = ps[PST_REMOVED];
+    c->stats.n_recv = ps[PST_RECV];
+    c->stats.n_window_removed = ps[PST_WINDOW_REMOVED];
+    if (ps[PST_OVERFLOW]) c->overflowed = true;
+    // this copy and all older ones are consumed
+    for (uint64_t b2 = back; b2 < 8 && b2 < c->pub_head; ++b2) c->pub[(c->pub_head - 1 - b2) % 8].pending = false;
+    break;
+  }
+  if (c->overflowed) {
+    set_error("particle exchange overflow: more than %lld particles left a slab towards one neighbour in one step; "
+              "raise cylgpu_set_exchange_capacity (or set it to 0 for the exact protocol)", (long long)c->xcap);
+    return 7;
+  }
+  (void)any_lazy;
+  return 0;
+}
+
+static int ensure_xbufs(cylgpu_ctx* c) {
+  const int64_t need = 7 * c->xcap + XHDR;
+  TRY(ensure_dbuf(&c->psend_l, &c->psend_l_cap, need, c->stream));
+  TRY(ensure_dbuf(&c->psend_r, &c->psend_r_cap, need, c->stream));
+  TRY(ensure_dbuf(&c->precv, &c->precv_cap, 2 * need, c->stream));
+  return 0;
+}
+
+// compaction of species isp after its leavers have been listed (c->hole_list / c->flag / c->counters)
+static int compact_dev(cylgpu_ctx* c, int isp, bool window, bool has_l, bool has_r) {
+  cylgpu::SpeciesState& S = c->species[isp];
+  unsigned long long* cnt = c->counters;
+  unsigned long long* cnt2 = c->counters + 8;
+  Soa s;
+  for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+  int64_t* pstats = c->n_dev + CYLGPU_MAX_SPECIES;
+  k_plan_compact<<<1, 1, 0, c->stream>>>(cnt, cnt2, c->n_dev + isp, c->d_plan, pstats, (long long)c->xcap,
+                                         window ? 1 : 0, has_l ? c->psend_l : nullptr, has_r ? c->psend_r : nullptr);
+  k_clear_tail<<<LEAVER_GRID, 256, 0, c->stream>>>(c->tailmark, c->d_plan);
+  k_collect_dev<<<LEAVER_GRID, 256, 0, c->stream>>>(s, c->hole_list, c->flag, c->d_plan, c->psend_l + XHDR,
+                                                    c->psend_r + XHDR, has_l || has_r ? (long long)c->xcap : 0LL,
+                                                    c->lowhole, c->tailmark, cnt2);
+  k_tail_keepers_dev<<<LEAVER_GRID, 256, 0, c->stream>>>(c->tailmark, c->d_plan, c->hightail, cnt2);
+  k_fill_holes_dev<<<LEAVER_GRID, 256, 0, c->stream>>>(s, c->lowhole, c->hightail, c->d_plan, cnt2);
+  c->stats.kernel_launches += 5;
+  CUDA_TRY(cudaGetLastError());
+  S.lazy = true;   // S.n stays as an upper bound
+  return 0;
+}
+
+static int pbcs_species_fast(cylgpu_ctx* c, int isp, BcsConst B, bool classified_by_push) {
+  cylgpu::SpeciesState& S = c->species[isp];
+  const bool has_l = c->left >= 0, has_r = c->right >= 0;
+  for (int k = 0; k < 4; ++k) B.bc[k] = S.sp.bc_particle[k];
+  TRY(ensure_xbufs(c));
+  if (has_l || has_r) TRY(reserve_particles(c, isp, S.n + 2 * c->xcap));
+  if (!classified_by_push) {
+    TRY(reserve_pscratch(c, S.n));
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (S.n > 0) {
+      k_pbcs_classify_dev<<<nblk(S.n, 256), 256, 0, c->stream>>>(B, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
+                                                                c->hole_list, c->flag, c->counters, c->n_dev + isp);
+      c->stats.kernel_launches += 1;
+    }
+  }
+  TRY(compact_dev(c, isp, false, has_l, has_r));
+  if (has_l || has_r) {
+    const size_t bytes = (size_t)(7 * c->xcap + XHDR) * sizeof(double);
+    double* rl = c->precv;
+    double* rr = c->precv + (7 * c->xcap + XHDR);
+    TRY(transport_sendrecv(c, c->psend_l, has_l ? bytes : 0, rl, has_l ? bytes : 0, c->psend_r, has_r ? bytes : 0, rr,
+                           has_r ? bytes : 0));
+    Soa s;
+    for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
+    k_unpack_dev<<<LEAVER_GRID, 256, 0, c->stream>>>(s, c->n_dev + isp, has_r ? rr : nullptr, has_l ? rl : nullptr);
+    k_bump_count<<<1, 1, 0, c->stream>>>(c->n_dev + isp, c->n_dev + CYLGPU_MAX_SPECIES, has_r ? rr : nullptr,
+                                         has_l ? rl : nullptr);
+    c->stats.kernel_launches += 2;
+    CUDA_TRY(cudaGetLastError());
+    S.n += ((has_l ? 1 : 0) + (has_r ? 1 : 0)) * c->xcap;   // upper bound
+  }
+  return 0;
+}
+
+static int zero_pstats(cylgpu_ctx* c) {
+  if (!c->n_dev) return 0;
+  // sent / removed / received of this particle_bcs (the window's removals and the overflow mark stay)
+  CUDA_TRY(cudaMemsetAsync(c->n_dev + CYLGPU_MAX_SPECIES, 0, 4 * sizeof(int64_t), c->stream));
+  return 0;
+}
+
 // particle_bcs of one species: (classification,) compaction, exchange, arrivals appended
-static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classified_by_push, bool counts_ready = false) {
+static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classified_by_push) {
+  if (c->xcap > 0) return pbcs_species_fast(c, isp, B, classified_by_push);
   cylgpu::SpeciesState& S = c->species[isp];
   int64_t nleft = 0, nright = 0, from_l = 0, from_r = 0;
-  TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright, classified_by_push, counts_ready));
+  TRY(pbcs_classify_compact(c, isp, B, 0, 0, &nleft, &nright, classified_by_push));
   TRY(pbcs_exchange(c, nleft, nright, &from_l, &from_r));
   // the reference receives from the right neighbour first (ix = -1 iteration), then left
   const int64_t nrecv = from_l + from_r;
@@ -842,14 +996,16 @@ static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classifi
     CUDA_TRY(cudaGetLastError());
   }
   c->stats.n_particles[isp] = S.n;
-  return 0;
+  return set_count_exact(c, isp);
 }
 
 int do_particle_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  if (c->xcap > 0) TRY(zero_pstats(c));
   for (int isp = 0; isp < c->cfg.n_species; ++isp)
     if (c->species[isp].set) TRY(pbcs_species(c, isp, B, false));
+  if (c->xcap > 0) TRY(publish_counts(c));
   return 0;
 }
 
@@ -859,29 +1015,19 @@ int do_particle_bcs(cylgpu_ctx* c) {
 int do_push_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  if (c->xcap > 0) {
+    TRY(poll_counts(c, false));   // whatever count copies have arrived tighten the bounds; nobody waits
+    TRY(zero_pstats(c));
+  }
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
-  int last = -1;
-  for (int isp = 0; isp < c->cfg.n_species; ++isp) if (c->species[isp].set) last = isp;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     if (!c->species[isp].set) continue;
     bool fused = false;
     TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
-    if (c->deferred_bcs && fused && isp == last) {
-      // the leaver counts start their way to the host right behind the kernel; nobody waits for them here
-      static_assert(sizeof(BcsConst) <= sizeof(c->pending.B), "PendingBcs::B too small");
-      CUDA_TRY(cudaMemcpyAsync(c->h_counters, c->counters, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                               c->stream));
-      if (!c->pending.ev)
-        CUDA_TRY(cudaEventCreateWithFlags(&c->pending.ev, cudaEventBlockingSync | cudaEventDisableTiming));
-      CUDA_TRY(cudaEventRecord(c->pending.ev, c->stream));
-      memcpy(c->pending.B, &B, sizeof(BcsConst));
-      c->pending.isp = isp;
-      c->pending.active = true;
-    } else {
-      TRY(pbcs_species(c, isp, B, fused));
-    }
+    TRY(pbcs_species(c, isp, B, fused));
   }
+  if (c->xcap > 0) TRY(publish_counts(c));
   if (need_sort) {
     c->sorted_valid = true;
     c->pushes_since_sort = 0;
@@ -889,20 +1035,6 @@ int do_push_bcs(cylgpu_ctx* c) {
   }
   c->pushes_since_sort += 1;
   return do_r_min_final(c);
-}
-
-// The second half of a deferred particle_bcs: by now the host has enqueued current_finish and the field
-// phases behind the push kernel, so the counts are usually waiting already and the device has work queued
-// while the compaction, the exchange and the next sort are being enqueued.  Every entry point that touches
-// particle state comes through here first (api.cu::check_handle); the grid, the boundary conditions and the
-// scratch buffers of the push are therefore still those the kernel classified with.
-int complete_pending_bcs(cylgpu_ctx* c) {
-  if (!c->pending.active) return 0;
-  c->pending.active = false;
-  CUDA_TRY(cudaEventSynchronize(c->pending.ev));
-  BcsConst B;
-  memcpy(&B, c->pending.B, sizeof(BcsConst));
-  return pbcs_species(c, c->pending.isp, B, true, true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1032,6 +1164,7 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
     c->stats.n_recv += nrecv;
     n_out[isp] = out_off + nrecv;
     c->stats.n_particles[isp] = 0;
+    TRY(set_count_exact(c, isp));
   }
   c->sorted_valid = false;
   return do_r_min_final(c);
@@ -1039,6 +1172,8 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
 
 int do_remove_behind(cylgpu_ctx* c) {
   c->stats.n_window_removed = 0;
+  if (c->xcap > 0)   // device-resident counts: the removals of this shift are counted on the device
+    CUDA_TRY(cudaMemsetAsync(c->n_dev + CYLGPU_MAX_SPECIES + PST_WINDOW_REMOVED, 0, sizeof(int64_t), c->stream));
   if (!c->cfg.x_min_boundary) return 0;
   unsigned long long* cnt = c->counters;
   unsigned long long* cnt2 = c->counters + 8;
@@ -1047,6 +1182,14 @@ int do_remove_behind(cylgpu_ctx* c) {
     if (!S.set || S.n == 0) continue;
     TRY(reserve_pscratch(c, S.n));
     CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
+    if (c->xcap > 0) {
+      TRY(ensure_xbufs(c));
+      k_flag_behind_dev<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->hole_list, c->flag, cnt,
+                                                              c->n_dev + isp);
+      c->stats.kernel_launches += 1;
+      TRY(compact_dev(c, isp, true, false, false));
+      continue;
+    }
     k_flag_behind<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->hole_list, c->flag, cnt, S.n);
     c->stats.kernel_launches += 1;
     CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
@@ -1056,6 +1199,7 @@ int do_remove_behind(cylgpu_ctx* c) {
     if (nholes > 0) TRY(compact(c, S, nholes, 0, 0, cnt2));
     c->stats.n_window_removed += nholes;
     c->stats.n_particles[isp] = S.n;
+    TRY(set_count_exact(c, isp));
   }
   return 0;
 }
@@ -1105,8 +1249,9 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortGeom G, const double* __r
                                                    const double* __restrict__ px, const double* __restrict__ py,
                                                    const double* __restrict__ pz, int* __restrict__ count,
                                                    uint32_t* __restrict__ key, uint32_t* __restrict__ rank,
-                                                   int64_t n) {
+                                                   int64_t n, const int64_t* __restrict__ n_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;   // device-resident count: the launch covers an upper bound
   int k = -1;
   if (i < n) {
     int cx, cy;
@@ -1184,8 +1329,9 @@ __global__ void __launch_bounds__(256) k_sort_dest(const int* __restrict__ start
 // sorted slot -> particle index (the strip push gathers through it; no data moves here)
 __global__ void __launch_bounds__(256) k_sort_src(const int* __restrict__ start, const uint32_t* __restrict__ key,
                                                   const uint32_t* __restrict__ rank, uint32_t* __restrict__ src,
-                                                  int64_t n) {
+                                                  int64_t n, const int64_t* __restrict__ n_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n_dev) n = *n_dev;
   if (i >= n) return;
   src[(uint32_t)start[key[i]] + rank[i]] = (uint32_t)i;
 }
@@ -1218,6 +1364,7 @@ int do_sort_species(cylgpu_ctx* c, int isp, bool physical) {
     c->ncell = ncell;
   }
   cylgpu::SpeciesState& S = c->species[isp];
+  if (physical && S.lazy) TRY(poll_counts(c, true));   // the scatter passes take the exact count
   if (!S.set || S.n == 0 || S.sp.immobile) return 0;
   if (S.n >= (int64_t)0x7FFFFFFFLL) { set_error("more than 2^31-1 particles per species per GPU"); return 3; }
   TRY(reserve_pscratch(c, S.cap));
@@ -1234,14 +1381,15 @@ int do_sort_species(cylgpu_ctx* c, int isp, bool physical) {
   CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)nscan * sizeof(int), c->stream));
   G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
   G.dtco2 = C_LIGHT * (c->dt / 2.0);
+  const int64_t* n_dev = S.lazy ? c->n_dev + isp : nullptr;
   k_sort_hist<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], S.d[3], S.d[4], S.d[5],
-                                                    count, key, rank, S.n);
+                                                    count, key, rank, S.n, n_dev);
   k_scan_block<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
   k_scan_sums<<<1, SCAN_B, 0, c->stream>>>(c->scan_blocks, nb);
   k_scan_add<<<nb, SCAN_B, 0, c->stream>>>(count, c->scan_blocks, nscan);
   c->stats.kernel_launches += 4;
   if (!physical) {
-    k_sort_src<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, rank, perm, S.n);
+    k_sort_src<<<nblk(S.n, 256), 256, 0, c->stream>>>(count, key, rank, perm, S.n, n_dev);
     c->stats.kernel_launches += 1;
     if (S.alt_cap < S.cap) {
       CUDA_TRY(cudaStreamSynchronize(c->stream));

@@ -127,6 +127,8 @@ int do_insert_particles(cylgpu_ctx* c, int isp, double x_grid_max, double npart_
 // ------------------------------------------------------------------------------------------
 #include "insert_kernel.cuh"
 
+__global__ void k_add_count_ins(int64_t* n_dev, long long add) { *n_dev += add; }
+
 int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double npart_per_cell_real,
                                const double* density_in, const double* temperature, const double* drift, double dmin,
                                double dmax, uint64_t seed, uint64_t column, int64_t* n_inserted) {
@@ -189,6 +191,7 @@ int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double
   a.row_start = reinterpret_cast<const int64_t*>(c->ins_dev + (size_t)7 * nrow);
   a.x = S.d[0]; a.y = S.d[1]; a.z = S.d[2]; a.px = S.d[3]; a.py = S.d[4]; a.pz = S.d[5]; a.w = S.d[6];
   a.base = S.n;
+  a.base_dev = S.lazy ? c->n_dev + isp : nullptr;
   a.ny = ny;
   a.iy_global_offset = iy_global_offset;
   a.dx = c->cfg.dx; a.dy = c->cfg.dy;
@@ -198,7 +201,13 @@ int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double
   k_insert_column<<<ny, 128, 0, c->stream>>>(a);
   CUDA_TRY(cudaGetLastError());
   c->stats.kernel_launches += 1;
-  S.n += total;
+  S.n += total;   // exact, or the upper bound moving with the device-side count
+  if (S.lazy) {
+    k_add_count_ins<<<1, 1, 0, c->stream>>>(c->n_dev + isp, (long long)total);
+    c->stats.kernel_launches += 1;
+  } else {
+    TRY(set_count_exact(c, isp));
+  }
   c->stats.n_particles[isp] = S.n;
   c->sorted_valid = false;
   return 0;

@@ -91,7 +91,8 @@ class Slab:
                  dt_multiplier=0.95, lasers=(), transport=TRANSPORT_NONE, device=-1, fabric=None,
                  nccl_unique_id=None, sendrecv=None, move_window=False, window_v_x=0.0,
                  window_start_time=0.0, window_stop_time=1e300, bc_x_min_after_move=BC_SIMPLE_OUTFLOW,
-                 bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None, device_insert_seed=None):
+                 bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None, device_insert_seed=None,
+                 exchange_capacity=None):
         self.L = _lib.load()
         self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier)
         g = self.grid
@@ -148,6 +149,12 @@ class Slab:
             sc = _lib.SpeciesC(sp.charge, sp.mass, (C.c_int32 * 4)(*normalise_bc_particle(sp.bc_particle)),
                                int(sp.immobile), int(sp.zero_current))
             self._ck(self.L.cylgpu_set_species(self.h, i, C.byref(sc)))
+        # device-resident particle counts by default: particles move less than a cell per step, so the leavers
+        # towards one neighbour are bounded by the population of its two boundary columns (plus the window's)
+        if exchange_capacity is None:
+            ppc = sum(int(math.ceil(sp.npart_per_cell)) for sp in self.species)
+            exchange_capacity = max(4096, 4 * (g.ny + 2) * max(ppc, 1))
+        self.set_exchange_capacity(exchange_capacity)
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
@@ -392,10 +399,11 @@ class Slab:
         """test knob: |m dtheta| below which the deposit uses the small-angle series (particles.F90:593, 1.0e-4)"""
         self._ck(self.L.cylgpu_set_taylor_switch(self.h, float(v)))
 
-    def set_deferred_bcs(self, on):
-        """cylgpu_push returns before the leaver counts are known; particle_bcs completes at the next call that
-        touches particle state (opt-in; removes the device idle time behind the step's host sync)"""
-        self._ck(self.L.cylgpu_set_deferred_bcs(self.h, int(bool(on))))
+    def set_exchange_capacity(self, particles):
+        """> 0: device-resident particle counts, one fixed-size migration message per neighbour and no host sync
+        inside a step (include/cylgpu.h); 0: the exact count-then-data protocol of partlist.F90:842,869"""
+        self.exchange_capacity = int(particles)
+        self._ck(self.L.cylgpu_set_exchange_capacity(self.h, int(particles)))
 
     def set_sort_interval(self, n):
         self._ck(self.L.cylgpu_set_sort_interval(self.h, n))

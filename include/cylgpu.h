@@ -348,12 +348,19 @@ int cylgpu_sdf_load(cylgpu_handle h, const char* path, cylgpu_sdf_desc* d);
 int cylgpu_energy(cylgpu_handle h, double* out2);
 int cylgpu_stats(cylgpu_handle h, cylgpu_stats_t* out);
 int cylgpu_reset_stats(cylgpu_handle h);
-/* Opt-in: cylgpu_push enqueues the push and returns without waiting for the leaver counts of the last
- * species; the count sync, compaction, exchange and arrivals (the rest of particle_bcs) run at the next call
- * that touches particle state, i.e. after the host has enqueued current_finish and the field phases.  Same
- * results, no device idle time behind the host sync.  With several ranks every rank must make the same
- * sequence of calls (the completion contains the neighbour exchange).  Default off. */
-int cylgpu_set_deferred_bcs(cylgpu_handle h, int on);
+/* Device-resident particle counts: replaces the count-then-data MPI_SENDRECV pair of partlist_sendrecv
+ * (partlist.F90:842,869) and every host-side use of a list length inside a step.
+ * capacity > 0: the migrants of one direction travel in ONE message of fixed size -- a count header and
+ * `capacity` particle slots of 7 doubles -- the leaver counts, the compaction, the arrivals and the window's
+ * removals / insertions are handled by kernels that read the counts on the device, and no call of the step
+ * (fields_half, push, current_finish, fields_final, window_shift, insert_particles, particle_bcs) waits for the
+ * device.  The host keeps upper bounds of the list lengths and tightens them from copies that trail behind;
+ * any other entry point (cylgpu_particle_count, cylgpu_stats, downloads, diagnostics) first waits for the newest
+ * copy and sees exact counts.  More than `capacity` particles leaving towards one neighbour in one step is an
+ * error (sticky, reported by the next such call); particles move less than a cell per step, so
+ * 4 * (ny + 2) * particles-per-cell is a safe capacity for x-slabs.  Every rank must set the same value.
+ * capacity = 0 (default): the exact protocol, counts first and then the payload, two host syncs per species. */
+int cylgpu_set_exchange_capacity(cylgpu_handle h, int64_t capacity);
 /* per-phase CUDA-event timers in cylgpu_stats (adds a host sync per phase); default off */
 int cylgpu_set_timing(cylgpu_handle h, int on);
 

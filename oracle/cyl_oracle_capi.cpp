@@ -1,6 +1,9 @@
 // cyl_oracle_capi.cpp -- flat C entry points over the CPU oracle so that tests/, smoke()
 // and bench.py's cpu_baseline leg can drive it through ctypes.
 // TEST INFRASTRUCTURE ONLY (see cyl_oracle.hpp).
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <chrono>
 #include <cstring>
 
@@ -68,6 +71,22 @@ void cylo_get_scalars(void* wp, double* out) {
 }
 void cylo_set_dt(void* w, double dt) { ((World*)w)->dt = dt; }
 void cylo_set_hc_push(void* w, int on) { ((World*)w)->hc_push = on != 0; }
+// threads of the `omp parallel for` over ranks (the CPU-baseline timing): set explicitly, because launchers such as
+// torchrun export OMP_NUM_THREADS=1 to their children
+void cylo_set_threads(int n) {
+#ifdef _OPENMP
+  omp_set_num_threads(n > 0 ? n : 1);
+#else
+  (void)n;
+#endif
+}
+int cylo_get_max_threads() {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
 void cylo_set_taylor_switch(void* w, double v) { ((World*)w)->taylor_switch = v; }
 // calc_number_density_modes into each rank's work array; returns rank k's pointer afterwards via cylo_wk_ptr
 void cylo_number_density_modes(void* w, int species) { ((World*)w)->calc_number_density_modes(species); }

@@ -99,6 +99,9 @@ def lib():
         L.cylo_charge_density.argtypes = [C.c_void_p, C.c_int]
         L.cylo_wk_ptr.restype = C.c_void_p
         L.cylo_wk_ptr.argtypes = [C.c_void_p, C.c_int]
+        L.cylo_set_threads.restype = None
+        L.cylo_set_threads.argtypes = [C.c_int]
+        L.cylo_get_max_threads.restype = C.c_int
         L.cylo_set_taylor_switch.restype = None
         L.cylo_set_taylor_switch.argtypes = [C.c_void_p, C.c_double]
         L.cylo_set_hc_push.restype = None
@@ -125,6 +128,12 @@ def lib():
                                          C.POINTER(C.c_double)]
         _LIB = L
     return _LIB
+
+
+def set_threads(n):
+    """OpenMP threads of the rank loop (one x-slab per thread): explicit, whatever OMP_NUM_THREADS the launcher set"""
+    lib().cylo_set_threads(int(n))
+    return lib().cylo_get_max_threads()
 
 
 class OracleWorld:

@@ -21,6 +21,7 @@ namespace cylgpu {
 #include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
 #include "../../cylindrical_epoch_b200/csrc/push_v0.cuh"
 #include "../../cylindrical_epoch_b200/csrc/pbcs_kernels.cuh"
+#include "../../cylindrical_epoch_b200/csrc/compact_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/field_kernels.cuh"
 }  // namespace cylgpu
 
@@ -651,6 +652,7 @@ EMUL_API int64_t emul_insert_column(int ny, int isp, double x_grid_max, double n
   a.row_start = row_start;
   a.x = soa[0]; a.y = soa[1]; a.z = soa[2]; a.px = soa[3]; a.py = soa[4]; a.pz = soa[5]; a.w = soa[6];
   a.base = 0;
+  a.base_dev = nullptr;
   a.ny = ny;
   a.iy_global_offset = 0;
   a.dx = dx; a.dy = dy;
@@ -659,6 +661,76 @@ EMUL_API int64_t emul_insert_column(int ny, int isp, double x_grid_max, double n
   a.mass = mass;
   emul_launch(k_insert_column, dim3((unsigned)ny), dim3(128), a);
   return total;
+}
+
+// particle_bcs with device-resident counts for a chain (or periodic ring) of `nslab` x-slabs of one species:
+// particles.cu::pbcs_species_fast restated per slab -- k_pbcs_classify_dev, compact_dev's five kernels, the
+// fixed-size message [7-double header][xcap slots] handed to the neighbour, k_unpack_dev, k_bump_count -- with
+// every count living in "device" memory (n_dev, the plan, the statistics).  soa: nslab x 7 arrays of capacity cap;
+// n: particles per slab in / out; bounds: x_min_local, x_max_local per slab; pstats: nslab x PST_N out.
+EMUL_API int emul_pbcs_fast(int nslab, double* const* soa, int64_t* n, int64_t cap, const int32_t* bc_particle,
+                            double x_min, double x_max, const double* x_min_local, const double* x_max_local,
+                            double y_max, double dx, double dy, int periodic, long long xcap, int64_t* pstats_out) {
+  const size_t msg = (size_t)(7 * xcap + XHDR);
+  std::vector<std::vector<double>> send_l(nslab, std::vector<double>(msg, -7.0)), send_r(nslab, std::vector<double>(msg, -7.0));
+  std::vector<std::vector<int64_t>> ndev(nslab, std::vector<int64_t>(1 + PST_N, 0));
+  const dim3 lg(LEAVER_GRID > 8 ? 8 : LEAVER_GRID), lb(256);   // (a smaller grid: the loops are grid-stride)
+  for (int k = 0; k < nslab; ++k) {
+    BcsConst B;
+    B.x_min = x_min; B.x_max = x_max;
+    B.x_min_local = x_min_local[k]; B.x_max_local = x_max_local[k];
+    B.y_max = y_max;
+    double boundary_shift = dx * (double)((1 + PNG + 0) / 2);
+    B.x_min_outer = B.x_min - boundary_shift;
+    B.x_max_outer = B.x_max + boundary_shift;
+    boundary_shift = dy * (double)((1 + PNG + 0) / 2);
+    B.y_max_outer = B.y_max + boundary_shift;
+    B.x_shift = B.x_max - B.x_min;
+    B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
+    B.x_min_boundary = (k == 0);
+    B.x_max_boundary = (k == nslab - 1);
+    for (int q = 0; q < 4; ++q) B.bc[q] = bc_particle[q];
+    const bool has_l = k > 0 || periodic, has_r = k < nslab - 1 || periodic;
+    Soa s;
+    for (int q = 0; q < 7; ++q) s.d[q] = soa[7 * k + q];
+    // the launches cover an upper bound of the count, as the host's do
+    const int64_t bound = n[k] + 100;
+    std::vector<uint32_t> hole_list((size_t)bound), lowhole((size_t)bound), hightail((size_t)bound);
+    std::vector<uint8_t> flag((size_t)bound), tailmark((size_t)bound, 1);
+    unsigned long long cnt[16] = {0};
+    CompactPlan plan;
+    int64_t* n_dev = ndev[k].data();
+    int64_t* pst = n_dev + 1;
+    *n_dev = n[k];
+    emul_launch(k_pbcs_classify_dev, dim3((unsigned)((bound + 255) / 256)), dim3(256), B, s.d[0], s.d[1], s.d[2], s.d[3],
+                s.d[4], s.d[5], hole_list.data(), flag.data(), (unsigned long long*)cnt, (const int64_t*)n_dev);
+    emul_launch(k_plan_compact, dim3(1), dim3(1), (const unsigned long long*)cnt, cnt + 8, n_dev, &plan, pst, xcap, 0,
+                has_l ? send_l[k].data() : (double*)nullptr, has_r ? send_r[k].data() : (double*)nullptr);
+    emul_launch(k_clear_tail, lg, lb, tailmark.data(), (const CompactPlan*)&plan);
+    emul_launch(k_collect_dev, lg, lb, s, (const uint32_t*)hole_list.data(), (const uint8_t*)flag.data(),
+                (const CompactPlan*)&plan, send_l[k].data() + XHDR, send_r[k].data() + XHDR,
+                (has_l || has_r) ? xcap : 0LL, lowhole.data(), tailmark.data(), cnt + 8);
+    emul_launch(k_tail_keepers_dev, lg, lb, (const uint8_t*)tailmark.data(), (const CompactPlan*)&plan, hightail.data(),
+                cnt + 8);
+    emul_launch(k_fill_holes_dev, lg, lb, s, (const uint32_t*)lowhole.data(), (const uint32_t*)hightail.data(),
+                (const CompactPlan*)&plan, (const unsigned long long*)(cnt + 8));
+  }
+  // the exchange: what a slab sends left is what its left neighbour receives "from the right", and vice versa
+  for (int k = 0; k < nslab; ++k) {
+    const int left = k > 0 ? k - 1 : (periodic ? nslab - 1 : -1), right = k < nslab - 1 ? k + 1 : (periodic ? 0 : -1);
+    const double* rr = right >= 0 ? send_l[right].data() : nullptr;
+    const double* rl = left >= 0 ? send_r[left].data() : nullptr;
+    Soa s;
+    for (int q = 0; q < 7; ++q) s.d[q] = soa[7 * k + q];
+    int64_t* n_dev = ndev[k].data();
+    const long long arriving = (rr ? *reinterpret_cast<const long long*>(rr) : 0) + (rl ? *reinterpret_cast<const long long*>(rl) : 0);
+    if (*n_dev + arriving > cap) return -1;
+    emul_launch(k_unpack_dev, lg, lb, s, (const int64_t*)n_dev, rr, rl);
+    emul_launch(k_bump_count, dim3(1), dim3(1), n_dev, n_dev + 1, rr, rl);
+    n[k] = *n_dev;
+    for (int q = 0; q < PST_N; ++q) pstats_out[k * PST_N + q] = n_dev[1 + q];
+  }
+  return 0;
 }
 
 }  // extern "C"

@@ -269,6 +269,69 @@ def test_particle_bcs_kernel_counts_and_survivors_match_the_oracle(emul, deck_na
     assert moved > 0, "the deck never exercised a boundary"
 
 
+@pytest.mark.parametrize("deck_name,nranks,xcap", [("thermal", 1, 4096), ("thermal", 2, 4096), ("thermal", 3, 4096),
+                                                   ("lwfa", 2, 4096), ("lwfa", 1, 64), ("thermal", 2, 3)])
+def test_particle_bcs_with_device_resident_counts_matches_the_oracle(emul, deck_name, nranks, xcap):
+    """csrc/compact_kernels.cuh (cylgpu_set_exchange_capacity > 0): classification, hole-filling compaction, the
+    fixed-size migration message with its count header, arrivals and the device-side statistics -- the launch
+    sequence of particles.cu::pbcs_species_fast for every slab of a chain / periodic ring -- leave on every slab
+    exactly the oracle's particle_bcs lists (as multisets: the storage order is free) and its counts of particles
+    sent left / right, removed and received.  xcap = 3: more leavers than slots must raise the overflow mark."""
+    L = emul
+    L.emul_pbcs_fast.restype = C.c_int
+    L.emul_pbcs_fast.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int32),
+                                 C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                 C.c_double, C.c_double, C.c_int, C.c_longlong, C.POINTER(C.c_int64)]
+    d = {"drift": lambda: decks.drift(nx=20, ny=10, n_mode=1),
+         "thermal": lambda: decks.thermal(nx=36, ny=12, n_mode=1, ppc=6, temp_k=5.0e8),
+         "lwfa": lambda: decks.lwfa(nx=32, ny=12, n_mode=2, ppc_e=4, ppc_p=0)}[deck_name]()
+    if deck_name == "lwfa":
+        d.species[0].temp = (2.0e9, 2.0e9, 2.0e9)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    periodic = int(w.bc_particle(0)[0] == po.BC_PERIODIC)
+    exercised = overflowed = 0
+    for _ in range(12 if deck_name == "lwfa" else 5):
+        w.call("fields_half")
+        w.call("push_no_bcs")
+        sc = w.scalars()
+        before = [w.particles(k, 0).reshape(-1, 7) for k in range(nranks)]
+        cap = max(p.shape[0] for p in before) + 2 * xcap + 64
+        soa = [[np.zeros(cap) for _ in range(7)] for _ in range(nranks)]
+        for k, p in enumerate(before):
+            for q in range(7):
+                soa[k][q][:p.shape[0]] = p[:, q]
+        ptrs = (C.c_void_p * (7 * nranks))(*[a.ctypes.data for k in range(nranks) for a in soa[k]])
+        n = (C.c_int64 * nranks)(*[p.shape[0] for p in before])
+        xl = (C.c_double * nranks)(*[w.rank_info(k)["x_min_local"] for k in range(nranks)])
+        xr = (C.c_double * nranks)(*[w.rank_info(k)["x_max_local"] for k in range(nranks)])
+        pst = (C.c_int64 * (8 * nranks))()
+        rc = L.emul_pbcs_fast(nranks, ptrs, n, cap, (C.c_int32 * 4)(*w.bc_particle(0)), sc["x_min"], sc["x_max"], xl, xr,
+                              sc["y_max"], sc["dx"], sc["dy"], periodic, xcap, pst)
+        assert rc == 0
+        w.call("particle_bcs")
+        for k in range(nranks):
+            st = w.stats(k)
+            got_st = tuple(int(pst[8 * k + q]) for q in range(4))
+            assert got_st[:3] == (st["sent_left"], st["sent_right"], st["removed"]), (deck_name, k, got_st, st)
+            exercised += sum(got_st)
+            if xcap < 16:     # the overflow case: the surplus is dropped and flagged, nothing else to compare
+                overflowed += int(pst[8 * k + 5])
+                continue
+            assert int(pst[8 * k + 5]) == 0
+            assert got_st[3] == st["received"]
+            ref = w.particles(k, 0).reshape(-1, 7)
+            assert int(n[k]) == ref.shape[0], (deck_name, k)
+            got = np.stack([soa[k][q][:int(n[k])] for q in range(7)], axis=1)
+            assert np.array_equal(decks.sort_particles(got), decks.sort_particles(ref)), (deck_name, k)
+        w.call("current_finish")
+        w.call("advance_half_time"); w.call("advance_half_time")
+        w.call("fields_final")
+    assert exercised > 0, "the deck never exercised a boundary"
+    if xcap < 16:
+        assert overflowed > 0
+
+
 # ------------------------------------------------------------------------------------------------------
 # the per-mode FDTD (csrc/field_kernels.cuh): update_e_field / update_b_field including the r = 0 rows and
 # the mirror rows below the axis, against the oracle's restatement of fields.f90:53-312.
