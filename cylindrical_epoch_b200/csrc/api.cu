@@ -494,12 +494,8 @@ static int run_field_phase(cylgpu_ctx* c, int which, const std::function<int()>&
 static int fields_half_body(cylgpu_ctx* c) {
   TRY(launch_update_e(c));
   TRY(do_efield_bcs(c));
-  // bxm_old = bxm etc. (fields.f90:326-328)
-  const size_t bytes = c->g.plane * c->g.M * sizeof(cplx);
-  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BXM_OLD], c->f[CYLGPU_BXM], bytes, cudaMemcpyDeviceToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BRM_OLD], c->f[CYLGPU_BRM], bytes, cudaMemcpyDeviceToDevice, c->stream));
-  CUDA_TRY(cudaMemcpyAsync(c->f[CYLGPU_BTM_OLD], c->f[CYLGPU_BTM], bytes, cudaMemcpyDeviceToDevice, c->stream));
-  TRY(launch_update_b(c));
+  // bxm_old = bxm etc. (fields.f90:326-328) ride on the B sweep
+  TRY(launch_update_b(c, true));
   return do_bfield_bcs(c, true);
 }
 
@@ -573,7 +569,6 @@ int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2mi
 int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* const* new_aos, const double* grid5) {
   TRY(check_handle_fields(c));
   if (!grid5) { set_error("window_shift needs the shifted grid"); return 2; }
-  c->graph_epoch += 1;   // shift_fields swaps array pointers
   if (n_new && new_aos) {
     for (int isp = 0; isp < c->cfg.n_species; ++isp)
       if (n_new[isp] > 0) TRY(append_async(c, isp, n_new[isp], new_aos[isp]));

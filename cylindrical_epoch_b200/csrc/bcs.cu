@@ -422,16 +422,40 @@ int do_snapshot(cylgpu_ctx* c) {
 }
 
 // ---- moving window: shift_fields, window.F90:98-153 ----
+// All nine arrays move by one cell IN PLACE in one launch: a block owns one row of one array and walks it in
+// chunks of 1024 elements -- every thread reads its four elements' right neighbours, the block synchronises, then
+// writes; the only element a later chunk overwrites (its first) was read by the chunk before.  1 read + 1 write per
+// element like the out-of-place copy (k_shift_x, kept for the CPU emulation), but the array pointers never change,
+// so the captured field-phase graphs stay valid across window shifts.
+struct Nine { cplx* f[9]; };
+#define SHIFT_T 256
+#define SHIFT_E 4
+__global__ void __launch_bounds__(SHIFT_T) k_shift_x_inplace(Geom g, Nine A) {
+  cplx* a = A.f[blockIdx.y] + (size_t)blockIdx.x * g.SX;   // row (im, ir) of array blockIdx.y
+  const int SX = g.SX;
+  for (int base = 0; base < SX; base += SHIFT_T * SHIFT_E) {
+    cplx v[SHIFT_E];
+#pragma unroll
+    for (int k = 0; k < SHIFT_E; ++k) {
+      const int i = base + k * SHIFT_T + threadIdx.x;
+      if (i < SX) v[k] = a[i < SX - 1 ? i + 1 : i];   // the last ghost column keeps its value
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < SHIFT_E; ++k) {
+      const int i = base + k * SHIFT_T + threadIdx.x;
+      if (i < SX) a[i] = v[k];
+    }
+  }
+}
+
 int do_shift_fields(cylgpu_ctx* c) {
   const Geom& g = c->g;
-  const size_t n = g.plane * g.M;
-  const int blocks = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
-  for (int k = 0; k < 9; ++k) {   // exm erm etm bxm brm btm jxm jrm jtm
-    k_shift_x<<<blocks, 256, 0, c->stream>>>(g, c->f[k], c->spare);
+  {
+    Nine A;
+    for (int k = 0; k < 9; ++k) A.f[k] = c->f[k];   // exm erm etm bxm brm btm jxm jrm jtm
+    k_shift_x_inplace<<<dim3((unsigned)(g.SY * g.M), 9), SHIFT_T, 0, c->stream>>>(g, A);
     c->stats.kernel_launches += 1;
-    cplx* t = c->f[k];
-    c->f[k] = c->spare;
-    c->spare = t;
   }
   CUDA_TRY(cudaGetLastError());
   // field_mode_bc on each shifted array (window.F90:147-150): three packed exchanges

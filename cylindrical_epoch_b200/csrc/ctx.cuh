@@ -214,7 +214,7 @@ namespace cylgpu {
 
 // fields.cu
 int launch_update_e(cylgpu_ctx* c);
-int launch_update_b(cylgpu_ctx* c);
+int launch_update_b(cylgpu_ctx* c, bool save_old = false);
 // bcs.cu
 int do_efield_bcs(cylgpu_ctx* c);
 int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only);

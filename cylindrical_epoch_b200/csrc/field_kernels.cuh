@@ -4,13 +4,22 @@
 // (tests/emul/).  Product code: no oracle here.
 #pragma once
 
+// Divisions: the reference divides by dx, dy, epsilon0 and the radii at every point (17 IEEE divisions per E
+// point, 12 per B point); an FP64 division is ~25 instructions, which made these streaming kernels as much
+// FP64-bound as memory-bound (43 % of the HBM rate under ncu).  Here each thread forms 1 / r_d and 1 / r_p once
+// (correctly rounded) and multiplies by them and by the reciprocals of dx, dy, epsilon0 passed in: every factor
+// stays within 1 ulp of the reference's quotient, far inside the 1e-12 the field solver is held to.
+struct FieldRecips {
+  double idx, idy, ieps0;
+};
+
 // E bulk: fields.f90:67-108.  ix = 0..nx, ir = 1..ny (y_min_boundary is always true for
 // x-slab decomposition), all modes.
 __global__ void __launch_bounds__(128) k_update_e_bulk(
     Geom g, cplx* __restrict__ exm, cplx* __restrict__ erm, cplx* __restrict__ etm,
     const cplx* __restrict__ bxm, const cplx* __restrict__ brm, const cplx* __restrict__ btm,
     const cplx* __restrict__ jxm, const cplx* __restrict__ jrm, const cplx* __restrict__ jtm,
-    double dx, double dy, double dt, double y_grid_min_local) {
+    FieldRecips R, double dy, double dt, double y_grid_min_local) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
   const int ir = blockIdx.y + 1;
   const int im = blockIdx.z;
@@ -21,7 +30,8 @@ __global__ void __launch_bounds__(128) k_update_e_bulk(
   const double r_p = r_d + 0.5 * dy;
   const double fac_x = c2 / r_p;
   const cplx im_fac_x = C(0.0, (double)im) * fac_x;
-  const cplx im_fac_r = (C(0.0, (double)im) * c2) / r_d;
+  const cplx im_fac_r = C(0.0, (double)im) * (c2 / r_d);
+  const double c2_dx = c2 * R.idx, c2_dy = c2 * R.idy;
 
   const size_t o = g.at(ix, ir, im);
   const size_t SX = g.SX;
@@ -29,10 +39,10 @@ __global__ void __launch_bounds__(128) k_update_e_bulk(
   const cplx br = brm[o], br_xp = brm[o + 1];
   const cplx bx = bxm[o], bx_rp = bxm[o + SX];
 
-  exm[o] = exm[o] + (((fac_x * 0.5) * (bt_rp + bt) + im_fac_x * br + (c2 * (bt_rp - bt)) / dy
-                      - jxm[o] / EPSILON0) * 0.5) * dt;
-  erm[o] = erm[o] + (((-im_fac_r) * bx - (c2 * (bt_xp - bt)) / dx - jrm[o] / EPSILON0) * 0.5) * dt;
-  etm[o] = etm[o] + (((c2 * (br_xp - br)) / dx - (c2 * (bx_rp - bx)) / dy - jtm[o] / EPSILON0) * 0.5) * dt;
+  exm[o] = exm[o] + (((fac_x * 0.5) * (bt_rp + bt) + im_fac_x * br + c2_dy * (bt_rp - bt)
+                      - jxm[o] * R.ieps0) * 0.5) * dt;
+  erm[o] = erm[o] + (((-im_fac_r) * bx - c2_dx * (bt_xp - bt) - jrm[o] * R.ieps0) * 0.5) * dt;
+  etm[o] = etm[o] + ((c2_dx * (br_xp - br) - c2_dy * (bx_rp - bx) - jtm[o] * R.ieps0) * 0.5) * dt;
 }
 
 // E axis rows and below-axis mirror: fields.f90:116-180, over the FULL extent 1-ng..nx+ng (the
@@ -85,28 +95,51 @@ __global__ void __launch_bounds__(128) k_update_e_axis(
   }
 }
 
-// B bulk: fields.f90:203-241.  ix = 0..nx, ir = 1..ny-1.
+// B bulk: fields.f90:203-241.  ix = 0..nx, ir = 1..ny-1.  SAVE_OLD: the b*_old = b* copies of
+// update_eb_fields_half (fields.f90:326-328) ride on this sweep -- the old values are in registers anyway -- for
+// the points it visits; the remaining rows and ghost columns are copied by k_copy_b_old_rim.
+template <bool SAVE_OLD>
 __global__ void __launch_bounds__(128) k_update_b_bulk(
     Geom g, cplx* __restrict__ bxm, cplx* __restrict__ brm, cplx* __restrict__ btm,
     const cplx* __restrict__ exm, const cplx* __restrict__ erm, const cplx* __restrict__ etm,
-    double dx, double dy, double dt, double y_grid_min_local) {
+    cplx* __restrict__ bxo, cplx* __restrict__ bro, cplx* __restrict__ bto,
+    FieldRecips R, double dy, double dt, double y_grid_min_local) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x;
   const int ir = blockIdx.y + 1;
   const int im = blockIdx.z;
   if (ix > g.nx) return;
   const double r_d = fabs((double)(ir - 1) * dy + y_grid_min_local);
   const double r_p = r_d + 0.5 * dy;
-  const cplx im_fac_x = C(0.0, (double)im) / r_d;
-  const cplx im_fac_r = C(0.0, (double)im) / r_p;
+  const double ir_d = 1.0 / r_d;
+  const cplx im_fac_x = C(0.0, (double)im) * ir_d;
+  const cplx im_fac_r = C(0.0, (double)im) * (1.0 / r_p);
   const size_t o = g.at(ix, ir, im);
   const size_t SX = g.SX;
   const cplx et = etm[o], et_rm = etm[o - SX], et_xm = etm[o - 1];
   const cplx er = erm[o], er_xm = erm[o - 1];
   const cplx ex = exm[o], ex_rm = exm[o - SX];
+  const cplx bx = bxm[o], br = brm[o], bt = btm[o];
+  if (SAVE_OLD) { bxo[o] = bx; bro[o] = br; bto[o] = bt; }
 
-  bxm[o] = bxm[o] - ((im_fac_x * er + (0.5 * (et + et_rm)) / r_d + (et - et_rm) / dy) * 0.5) * dt;
-  brm[o] = brm[o] + ((im_fac_r * ex + (et - et_xm) / dx) * 0.5) * dt;
-  btm[o] = btm[o] + (((-(er - er_xm)) / dx + (ex - ex_rm) / dy) * 0.5) * dt;
+  bxm[o] = bx - ((im_fac_x * er + (0.5 * (et + et_rm)) * ir_d + (et - et_rm) * R.idy) * 0.5) * dt;
+  brm[o] = br + ((im_fac_r * ex + (et - et_xm) * R.idx) * 0.5) * dt;
+  btm[o] = bt + (((-(er - er_xm)) * R.idx + (ex - ex_rm) * R.idy) * 0.5) * dt;
+}
+
+// b*_old = b* for everything k_update_b_bulk<true> does not visit: rows outside 1..ny-1 and the ghost columns
+// outside 0..nx.  Runs BEFORE the B sweep (the axis / mirror rows are rewritten by k_update_b_axis afterwards).
+__global__ void __launch_bounds__(128) k_copy_b_old_rim(Geom g, const cplx* __restrict__ bxm, const cplx* __restrict__ brm,
+                                                        const cplx* __restrict__ btm, cplx* __restrict__ bxo,
+                                                        cplx* __restrict__ bro, cplx* __restrict__ bto) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;   // 0..SX-1
+  const int row = blockIdx.y;                              // 0..SY-1
+  const int im = blockIdx.z;
+  if (col >= g.SX) return;
+  const int ix = col + 1 - NG, ir = row + 1 - NG;
+  const bool swept = ix >= 0 && ix <= g.nx && ir >= 1 && ir <= g.ny - 1;
+  if (swept) return;
+  const size_t o = ((size_t)im * g.SY + row) * g.SX + col;
+  bxo[o] = bxm[o]; bro[o] = brm[o]; bto[o] = btm[o];
 }
 
 // B axis rows and mirror: fields.f90:249-310, one thread per (column, mode, task) as for E.  The

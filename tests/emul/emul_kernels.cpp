@@ -562,7 +562,7 @@ EMUL_API void emul_smooth_current(int nx, int ny, int M, void* const* j3, int it
 // update_e_field / update_b_field of one slab without boundary conditions (fields.cu::launch_update_e / _b).
 // f9: exm erm etm bxm brm btm jxm jrm jtm, complex with ghosts, updated in place.
 EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f9, double dx, double dy, double dt,
-                                double y_grid_min_local) {
+                                double y_grid_min_local, void* const* bold3) {
   Geom g;
   g.nx = nx; g.ny = ny; g.M = M;
   g.SX = nx + 2 * NG; g.SY = ny + 2 * NG;
@@ -570,16 +570,31 @@ EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f
   cplx* f[9];
   for (int k = 0; k < 9; ++k) f[k] = (cplx*)f9[k];
   const dim3 blk(128);
+  FieldRecips R;   // fields.cu::field_recips
+  R.idx = 1.0 / dx; R.idy = 1.0 / dy; R.ieps0 = 1.0 / EPSILON0;
   if (which == 0) {
     emul_launch(k_update_e_bulk, dim3((g.nx + 1 + 127) / 128, g.ny, g.M), blk, g, f[0], f[1], f[2], (const cplx*)f[3],
-                (const cplx*)f[4], (const cplx*)f[5], (const cplx*)f[6], (const cplx*)f[7], (const cplx*)f[8], dx, dy, dt,
+                (const cplx*)f[4], (const cplx*)f[5], (const cplx*)f[6], (const cplx*)f[7], (const cplx*)f[8], R, dy, dt,
                 y_grid_min_local);
     emul_launch(k_update_e_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[0], f[1], f[2], (const cplx*)f[5],
                 (const cplx*)f[6], dy, dt);
   } else {
-    if (g.ny > 1)
-      emul_launch(k_update_b_bulk, dim3((g.nx + 1 + 127) / 128, g.ny - 1, g.M), blk, g, f[3], f[4], f[5], (const cplx*)f[0],
-                  (const cplx*)f[1], (const cplx*)f[2], dx, dy, dt, y_grid_min_local);
+    // which == 2: fields.cu::launch_update_b(save_old = true), the b*_old = b* copies of update_eb_fields_half fused
+    cplx* bo[3] = {nullptr, nullptr, nullptr};
+    if (which == 2) {
+      for (int k = 0; k < 3; ++k) bo[k] = (cplx*)bold3[k];
+      emul_launch(k_copy_b_old_rim, dim3((g.SX + 127) / 128, g.SY, g.M), blk, g, (const cplx*)f[3], (const cplx*)f[4],
+                  (const cplx*)f[5], bo[0], bo[1], bo[2]);
+    }
+    if (g.ny > 1) {
+      const dim3 grd((g.nx + 1 + 127) / 128, g.ny - 1, g.M);
+      if (which == 2)
+        emul_launch(k_update_b_bulk<true>, grd, blk, g, f[3], f[4], f[5], (const cplx*)f[0], (const cplx*)f[1],
+                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local);
+      else
+        emul_launch(k_update_b_bulk<false>, grd, blk, g, f[3], f[4], f[5], (const cplx*)f[0], (const cplx*)f[1],
+                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local);
+    }
     emul_launch(k_update_b_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[3], f[4], f[5], (const cplx*)f[0],
                 (const cplx*)f[2], dx, dy, dt);
   }

@@ -341,7 +341,7 @@ def test_field_update_kernels_match_the_oracle(emul, n_mode):
     L = emul
     L.emul_update_field.restype = None
     L.emul_update_field.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_double, C.c_double,
-                                    C.c_double, C.c_double]
+                                    C.c_double, C.c_double, C.POINTER(C.c_void_p)]
     d = decks.lwfa(nx=40, ny=14, n_mode=n_mode, ppc_e=2, ppc_p=0, t_centre=6e-15)
     w = decks.make_oracle(d)
     w.call("init_half_step")
@@ -353,15 +353,23 @@ def test_field_update_kernels_match_the_oracle(emul, n_mode):
         scale = max(np.abs(f).max(), 1.0)
         f += 1e-3 * scale * (rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape))
     sc, info = w.scalars(), w.rank_info(0)
-    for which, op in ((0, "update_e"), (1, "update_b"), (0, "update_e"), (1, "update_b")):
+    for which, op in ((0, "update_e"), (1, "update_b"), (0, "update_e"), (2, "update_b")):
         mine = [w.field(0, n).copy() for n in names]
         ptrs = (C.c_void_p * 9)(*[a.ctypes.data for a in mine])
+        # which == 2: the B sweep that also saves b*_old = b* (fields.f90:326-328 fused): the saved arrays must be
+        # exact copies of B before the sweep, ghosts and axis rows included
+        b_before = [w.field(0, n).copy() for n in names[3:6]]
+        b_old = [np.full_like(b, np.nan) for b in b_before]
+        bold = (C.c_void_p * 3)(*[a.ctypes.data for a in b_old])
         L.emul_update_field(which, info["nx"], info["ny"], n_mode, ptrs, sc["dx"], sc["dy"], sc["dt"],
-                            sc["y_grid_min_local"])
+                            sc["y_grid_min_local"], bold)
         w.call(op)
         for name, a in zip(names[:6], mine):
             ref = w.field(0, name)
             assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (op, name, n_mode)
+        if which == 2:
+            for saved, before in zip(b_old, b_before):
+                assert np.array_equal(saved, before)
 
 
 @pytest.mark.parametrize("deck_name", ["thermal", "lwfa", "drift"])
@@ -555,7 +563,8 @@ class EmulSlab:
         self.periodic = w.bc_field()[0] == po.BC_PERIODIC
         L.emul_bfield_halo.restype = None
         L.emul_bfield_halo.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
-        for fn, at in (("emul_update_field", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + [C.c_double] * 4),
+        for fn, at in (("emul_update_field", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)] + [C.c_double] * 4 +
+                        [C.POINTER(C.c_void_p)]),
                        ("emul_field_bcs", [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]),
                        ("emul_bfield_final_bcs", [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                   C.POINTER(C.c_void_p), C.POINTER(C.c_int32)] + [C.c_double] * 4),
@@ -576,7 +585,7 @@ class EmulSlab:
     def update(self, which):
         sc = self.sc
         self.L.emul_update_field(which, self.nx, self.ny, self.M, self.ptrs(self.names[:9]), sc["dx"], sc["dy"], sc["dt"],
-                                 sc["y_grid_min_local"])
+                                 sc["y_grid_min_local"], self.ptrs(("bxm_old", "brm_old", "btm_old")))
 
     def field_bcs(self, which):
         grp = self.names[:3] if which == 0 else self.names[3:6]
@@ -585,9 +594,7 @@ class EmulSlab:
     def fields_half(self):                      # api.cu fields_half_body
         self.update(0)
         self.field_bcs(0)
-        for n in ("bxm", "brm", "btm"):
-            self.f[n + "_old"][...] = self.f[n]
-        self.update(1)
+        self.update(2)                          # update_b with b*_old = b* riding on the sweep (fields.f90:326-328)
         if self.periodic:                       # bfield_bcs(mpi_only): the slab is its own x neighbour
             self.L.emul_bfield_halo(self.nx, self.ny, self.M, self.ptrs(("bxm", "brm", "btm")))
 
