@@ -7,7 +7,8 @@ import pytest
 
 import decks
 from parity import Pair, TOL, TOL_HOT, by_weight
-from cylindrical_epoch_b200.constants import FIELD_NAMES
+from cylindrical_epoch_b200.constants import (BC_CLAMP, BC_CONDUCT, BC_OPEN, BC_REFLECT, BC_ZERO_GRADIENT, FIELD_NAMES, M0,
+                                              Q0)
 
 pytestmark = pytest.mark.gpu
 
@@ -86,6 +87,31 @@ def test_hot_decks_reach_tol_with_the_taylor_switch_moved(deckname, variant):
         errs = p.check_fields(tol)
         worst = p.check_particles(tol)
         print(f"{deckname}: worst field error {max(errs.values()):.2e}, particles {worst:.2e}")
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("walls", ["conduct", "zero_gradient", "mixed"])
+def test_conducting_and_zero_gradient_walls(walls):
+    """field_mode_clamp_zero / field_mode_zero_gradient on x_min, x_max and r_max as the conducting and zero-gradient
+    boundary kinds select them per component and stagger (boundary.F90:654-707,772-829,1355-1476) -- round 1 had
+    these only in the CPU emulation of the kernels -- with a hot plasma bouncing off reflecting walls so that every
+    array is live: whole steps against the oracle."""
+    bc = {"conduct": (BC_CONDUCT, BC_CONDUCT, 0, BC_CONDUCT),
+          "zero_gradient": (BC_ZERO_GRADIENT, BC_ZERO_GRADIENT, 0, BC_ZERO_GRADIENT),
+          "mixed": (BC_CONDUCT, BC_ZERO_GRADIENT, 0, BC_CLAMP)}[walls]
+    bcp = (BC_REFLECT, BC_REFLECT, BC_OPEN, BC_REFLECT)
+    sp = [decks.SpeciesSpec(-Q0, M0, bcp, 6, 1.0e24, temp=(3.0e8,) * 3)]
+    d = decks.Deck("walls", 40, 20, 3, 0.0, 40 * 0.5e-6, 20 * 0.5e-6, bc, sp)
+    p = Pair(d)
+    try:
+        for _ in range(2):
+            p.step(10)
+            p.check_counts()
+            errs = p.check_fields(TOL_HOT)
+            p.check_particles(TOL_HOT)
+        assert max(np.abs(p.oracle.field(0, n)).max() for n in ("bxm", "brm", "btm")) > 0
+        print(walls, max(errs.values()))
     finally:
         p.close()
 
