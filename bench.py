@@ -17,9 +17,9 @@ per GPU in a periodic ring (weak).
 
 Prints ONE JSON line (rank 0).  `value` is whole-job particle-steps/s with all state resident in HBM; `e2e`
 is the same step driven through the C-ABI with HOST buffers: the particle list and the nine E/B/J mode arrays
-live in pinned host memory and make the round trip every step (thermal: cylgpu_push_host streams the list
-through the GPU in chunks; moving-window decks: upload -> step -> download, the window's new plasma column
-included).  `cpu_baseline` / `--impl reference`: the CPU restatement of the reference (oracle port; the
+live in pinned host memory and make the round trip every step (cylgpu_push_host streams the list through the
+GPU in chunks, upload | push | download overlapped; a moving window over several slabs: upload -> step ->
+download).  `cpu_baseline` / `--impl reference`: the CPU restatement of the reference (oracle port; the
 Fortran + MPI reference cannot be built in this image) on the same deck shape, all host threads.
 """
 import argparse
@@ -480,9 +480,9 @@ def run_ours(args, wl_name, wl):
         e2e_steps = max(1, min(args.steps, 3 if lwfa else 5))
         h2d = d2h = 0
         nfield_bytes = len(names) * host_f[names[0]].numel() * 16
-        if lwfa:
-            # moving window: the list is uploaded, stepped on the device (the window drops the plasma behind it and
-            # appends the new column) and downloaded again, every step
+        if lwfa and world > 1:
+            # moving window over several slabs: the list is uploaded, stepped on the device (the window drops the
+            # plasma behind it, appends the new column, particles migrate) and downloaded again, every step
             count = [int(nn.value)]
 
             def e2e_step():
@@ -515,7 +515,8 @@ def run_ours(args, wl_name, wl):
                 return n_before, slab.host_counts[0]
             what = ("particle list and the 9 E/B/J mode arrays live in pinned host memory: every step uploads them, runs "
                     "the full step and downloads them (cylgpu_push_host streams the list in chunks, both PCIe "
-                    "directions busy)")
+                    "directions busy" + ("; the window's new column joins the host list, the plasma behind the window "
+                                         "is dropped as the list streams through" if lwfa else "") + ")")
         e2e_step()   # warm-up: staging buffers, streams
         barrier()
         t0 = time.perf_counter()

@@ -131,7 +131,43 @@ SYMBOLS = {
     "cylgpu_reset_stats": (C.c_int, [H]),
     "cylgpu_set_timing": (C.c_int, [H, C.c_int]),
     "cylgpu_set_exchange_capacity": (C.c_int, [H, C.c_int64]),
+    "cylgpu_insert_particles_host": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
+    "cylgpu_driver_configure": (C.c_int, [H, C.c_void_p]),
+    "cylgpu_driver_init_half_step": (C.c_int, [H]),
+    "cylgpu_driver_step": (C.c_int, [H, C.c_int64]),
+    "cylgpu_driver_get_state": (C.c_int, [H, C.c_void_p]),
+    "cylgpu_driver_set_time": (C.c_int, [H, C.c_double, C.c_int64]),
 }
+
+class LaserC(C.Structure):          # include/cylgpu.h: cylgpu_laser
+    _fields_ = [("boundary", C.c_int32), ("pad_", C.c_int32), ("amp", C.c_double), ("omega", C.c_double),
+                ("pol_angle", C.c_double), ("t_start", C.c_double), ("t_end", C.c_double), ("t_centre", C.c_double),
+                ("t_width", C.c_double), ("r_width", C.c_double), ("phase", C.c_double), ("phase_curv", C.c_double)]
+
+
+class InsertProfileC(C.Structure):  # cylgpu_insert_profile
+    _fields_ = [("npart_per_cell", C.c_double), ("density", C.c_double), ("temp", C.c_double * 3),
+                ("drift", C.c_double * 3), ("density_min", C.c_double), ("density_max", C.c_double)]
+
+
+class DriverConfig(C.Structure):    # cylgpu_driver_config
+    _fields_ = [("cell_x_min", C.c_int32), ("move_window", C.c_int32), ("raw_bc_field", C.c_int32 * 4),
+                ("bc_x_min_after_move", C.c_int32), ("bc_x_max_after_move", C.c_int32), ("n_lasers", C.c_int32),
+                ("insert_mode", C.c_int32), ("insert_seed", C.c_uint64), ("x_grid_min", C.c_double),
+                ("window_v_x", C.c_double), ("window_start_time", C.c_double), ("window_stop_time", C.c_double),
+                ("lasers", C.POINTER(LaserC)), ("insert", InsertProfileC * MAX_SPECIES),
+                ("time", C.c_double), ("window_shift_fraction", C.c_double), ("step", C.c_int64),
+                ("window_shifts_total", C.c_int64), ("window_started", C.c_int32), ("pad_", C.c_int32)]
+
+
+class DriverState(C.Structure):     # cylgpu_driver_state
+    _fields_ = [("time", C.c_double), ("step", C.c_int64), ("window_started", C.c_int32), ("pad_", C.c_int32),
+                ("window_shift_fraction", C.c_double), ("window_shifts_total", C.c_int64),
+                ("x_grid_min", C.c_double), ("x_min", C.c_double), ("x_max", C.c_double),
+                ("x_grid_min_local", C.c_double), ("x_min_local", C.c_double), ("x_max_local", C.c_double),
+                ("bc_field", C.c_int32 * 4)]
+
 
 _LIB = None
 

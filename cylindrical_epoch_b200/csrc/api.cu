@@ -49,6 +49,8 @@ static void set_neighbours(cylgpu_ctx* c) {
 
 using namespace cylgpu;
 
+extern "C" void cylgpu_driver_release(void* driver);   // driver.cu
+
 extern "C" {
 
 const char* cylgpu_last_error(void) { return g_err; }
@@ -130,6 +132,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   // the captured field phases hold NCCL send/recv nodes: they go before the communicator
   for (int k = 0; k < 3; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
   destroy_transport(c->tr);
+  if (c->driver) { cylgpu_driver_release(c->driver); c->driver = nullptr; }
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) cudaFree(c->f[k]);
   cudaFree(c->spare);
   for (int k = 0; k < CYLGPU_NSNAPS; ++k) cudaFree(c->snap[k]);
@@ -577,6 +580,7 @@ int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* con
   c->x_min = grid5[1]; c->x_max = grid5[2];
   c->x_min_local = grid5[3]; c->x_max_local = grid5[4];
   TRY(do_remove_behind(c));
+  if (c->cfg.x_min_boundary) { c->host_remove_active = true; c->host_remove_x = c->x_min; }   // (host-resident lists)
   if (c->xcap > 0) TRY(publish_counts(c));
   return do_shift_fields(c);
 }
@@ -625,6 +629,27 @@ int cylgpu_insert_particles(cylgpu_handle c, int isp, double x_grid_max, double 
   const int64_t n = (int64_t)(aos.size() / 7);
   if (n_inserted) *n_inserted = n;
   if (n > 0) TRY(append_async(c, isp, n, aos.data()));
+  return 0;
+}
+
+// insert_particles for a species whose list lives in host memory (cylgpu_push_host): the column goes behind the
+// *n_inout records of host_aos
+int cylgpu_insert_particles_host(cylgpu_handle c, int isp, double x_grid_max, double npart_per_cell, const double* density,
+                                 const double* temperature, const double* drift, double dmin, double dmax,
+                                 double* host_aos, int64_t capacity, int64_t* n_inout) {
+  TRY(check_handle_fields(c));
+  if (isp < 0 || isp >= c->cfg.n_species || !c->species[isp].set) { set_error("bad species index"); return 2; }
+  if (!density || !temperature || !drift || !host_aos || !n_inout) { set_error("insert_particles_host: null argument"); return 2; }
+  std::vector<double> aos;
+  TRY(do_insert_particles(c, isp, x_grid_max, npart_per_cell, density, temperature, drift, dmin, dmax, aos));
+  const int64_t n = (int64_t)(aos.size() / 7);
+  if (*n_inout + n > capacity) {
+    set_error("insert_particles_host: species %d needs room for %lld particles, capacity %lld", isp,
+              (long long)(*n_inout + n), (long long)capacity);
+    return 2;
+  }
+  if (n > 0) memcpy(host_aos + 7 * *n_inout, aos.data(), (size_t)n * 7 * sizeof(double));
+  *n_inout += n;
   return 0;
 }
 

@@ -184,6 +184,7 @@ struct cylgpu_ctx {
   uint64_t graph_epoch = 0;
   bool use_graphs = true;
 
+  void* driver = nullptr;         // driver.cu: the main-loop body run natively (cylgpu_driver_*)
   cylgpu::Transport* tr = nullptr;
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)
@@ -193,6 +194,11 @@ struct cylgpu_ctx {
   size_t ins_cap = 0;
   cudaEvent_t ins_ev = nullptr;
   int64_t host_chunk = 1 << 21;   // particles per chunk of the host-resident path (117 MB)
+  // remove_particles (window.F90:304-325) for host-resident lists: the window shift only notes the new x_min; the
+  // next cylgpu_push_host drops what lies behind it while the chunks stream through (no extra pass over the list)
+  bool host_remove_active = false;
+  bool sort_drops_behind = false;   // set by do_push_host around the sort of a chunk
+  double host_remove_x = 0.0;
 
   int sort_interval = 1;
   double taylor_switch = 1.0e-4;  // particles.F90:593; moved only by the conditioning test (cylgpu_set_taylor_switch)

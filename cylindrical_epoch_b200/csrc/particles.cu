@@ -758,7 +758,8 @@ static int grow_dbuf_keep(double** p, int64_t* cap, int64_t need, int64_t keep, 
 // classification, removal of the leavers (hole filling) and packing of the migrants behind the
 // `off_l` / `off_r` particles already waiting in psend_l / psend_r.  One host sync (the counts).
 static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off_l, int64_t off_r, int64_t* nleft_out,
-                                 int64_t* nright_out, bool classified_by_push = false) {
+                                 int64_t* nright_out, bool classified_by_push = false,
+                                 const int* alive_dev = nullptr) {
   unsigned long long* cnt = c->counters;        // 8 for classify
   unsigned long long* cnt2 = c->counters + 8;   // 8 for collect/compact
   cylgpu::SpeciesState& S = c->species[isp];
@@ -773,7 +774,14 @@ static int pbcs_classify_compact(cylgpu_ctx* c, int isp, BcsConst B, int64_t off
     }
   }
   CUDA_TRY(cudaMemcpyAsync(c->h_counters, cnt, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  if (alive_dev)   // the sort sent the particles behind the window to its extra bucket: the list ends before them
+    CUDA_TRY(cudaMemcpyAsync(c->h_counters + 24, alive_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   TRY(host_wait(c));
+  if (alive_dev) {
+    const int64_t alive = (int64_t)*reinterpret_cast<const int*>(c->h_counters + 24);
+    c->stats.n_window_removed += S.n - alive;
+    S.n = alive;
+  }
   const int64_t nholes = (int64_t)c->h_counters[CNT_HOLE];
   const int64_t nleft = (int64_t)c->h_counters[CNT_LEFT];
   const int64_t nright = (int64_t)c->h_counters[CNT_RIGHT];
@@ -1086,6 +1094,7 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
   TRY(host_stream_setup(c, chunk));
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  if (c->host_remove_active) c->stats.n_window_removed = 0;
   TRY(push_prologue(c));
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     cylgpu::SpeciesState& S = c->species[isp];
@@ -1124,9 +1133,15 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
       c->stats.kernel_launches += 1;
       S.n = m;
       bool fused = false;
-      TRY(push_species(c, isp, c->sort_interval > 0, false, true, &fused));
+      c->sort_drops_behind = c->host_remove_active;
+      const int prc = push_species(c, isp, c->sort_interval > 0, false, true, &fused);
+      if (prc != 0) { c->sort_drops_behind = false; return prc; }
       int64_t nleft = 0, nright = 0;
-      TRY(pbcs_classify_compact(c, isp, B, acc_l, acc_r, &nleft, &nright, fused));   // host sync: counts
+      const bool dropping = c->sort_drops_behind;   // the window moved since the last push (cylgpu_window_shift)
+      if (dropping && !fused) { set_error("push_host: the moving window needs the strip push (variant >= 2, sort every push)"); return 2; }
+      TRY(pbcs_classify_compact(c, isp, B, acc_l, acc_r, &nleft, &nright, fused,
+                                dropping ? S.cell_start + (S.cell_start_n - 1) : nullptr));   // host sync: counts
+      c->sort_drops_behind = false;
       acc_l += nleft;
       acc_r += nright;
       const int64_t kept = S.n;
@@ -1167,6 +1182,7 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
     TRY(set_count_exact(c, isp));
   }
   c->sorted_valid = false;
+  c->host_remove_active = false;
   return do_r_min_final(c);
 }
 
@@ -1212,6 +1228,9 @@ struct SortGeom {
   double x_grid_min_local, y_grid_min_local, dx, dy;
   // prediction of the upcoming half-step position (particles.F90:303-309)
   double ipart_mc, dtco2, idx, idy;
+  // particles behind this x go to the extra bucket behind all cells: no strip owns it, so they are neither pushed
+  // nor kept (remove_particles, window.F90:304-325, for lists that are streamed from host memory)
+  double x_remove;
 };
 
 __device__ __forceinline__ void ref_cell(const SortGeom& G, double x, double y, double z, int& cx, int& cy) {
@@ -1255,8 +1274,9 @@ __global__ void __launch_bounds__(256) k_sort_hist(SortGeom G, const double* __r
   int k = -1;
   if (i < n) {
     int cx, cy;
-    stag_cell(G, x[i], y[i], z[i], px[i], py[i], pz[i], cx, cy);
-    k = cell_key(G, cx, cy);
+    const double X = x[i];
+    stag_cell(G, X, y[i], z[i], px[i], py[i], pz[i], cx, cy);
+    k = (X < G.x_remove) ? G.ncx * G.ncy : cell_key(G, cx, cy);
   }
   // the list is almost sorted from the previous step, so the lanes of a warp share a few
   // buckets: one atomic per distinct bucket per warp instead of one per particle
@@ -1355,8 +1375,11 @@ int do_sort_species(cylgpu_ctx* c, int isp, bool physical) {
   G.y_grid_min_local = c->cfg.y_grid_min_local;
   G.dx = c->cfg.dx; G.dy = c->cfg.dy;
   G.idx = 1.0 / c->cfg.dx; G.idy = 1.0 / c->cfg.dy;
+  G.x_remove = (c->sort_drops_behind && !physical) ? c->host_remove_x : -1.0e300;   // do_push_host only
   const int64_t ncell = (int64_t)G.ncx * G.ncy;
-  const int64_t nscan = ncell + 1;   // one extra zero bucket: its exclusive-scan value is the particle total
+  // one extra bucket behind the cells: empty unless x_remove is set; its exclusive-scan value is the number of
+  // particles the strips own
+  const int64_t nscan = ncell + 1;
   const int nb = (int)((nscan + SCAN_B - 1) / SCAN_B);
   if (!c->scan_blocks || c->ncell != ncell) {
     if (c->scan_blocks) cudaFree(c->scan_blocks);
@@ -1454,6 +1477,7 @@ int do_cells(cylgpu_ctx* c, int isp, int64_t capn, int32_t* out) {
   G.x_grid_min_local = c->x_grid_min_local;
   G.y_grid_min_local = c->cfg.y_grid_min_local;
   G.dx = c->cfg.dx; G.dy = c->cfg.dy;
+  G.x_remove = -1.0e300;
   int32_t* d = nullptr;
   CUDA_TRY(cudaMalloc(&d, (size_t)S.n * 2 * sizeof(int32_t)));
   k_cells<<<nblk(S.n, 256), 256, 0, c->stream>>>(G, S.d[0], S.d[1], S.d[2], d, S.n);

@@ -92,7 +92,7 @@ class Slab:
                  nccl_unique_id=None, sendrecv=None, move_window=False, window_v_x=0.0,
                  window_start_time=0.0, window_stop_time=1e300, bc_x_min_after_move=BC_SIMPLE_OUTFLOW,
                  bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None, device_insert_seed=None,
-                 exchange_capacity=None):
+                 exchange_capacity=None, native_driver=None):
         self.L = _lib.load()
         self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier)
         g = self.grid
@@ -102,8 +102,8 @@ class Slab:
         self.species = list(species)
         self.lasers = list(lasers)
         self.dt = g.dt
-        self.time = 0.0
-        self.step = 0
+        self._time = 0.0
+        self._step = 0
         self.move_window = move_window
         self.window_v_x = window_v_x
         self.window_start_time = window_start_time
@@ -155,6 +155,75 @@ class Slab:
             ppc = sum(int(math.ceil(sp.npart_per_cell)) for sp in self.species)
             exchange_capacity = max(4096, 4 * (g.ny + 2) * max(ppc, 1))
         self.set_exchange_capacity(exchange_capacity)
+        # whole steps run inside the library (csrc/driver.cu: the same loop body, natively) unless the plasma
+        # column of the moving window comes from a Python callback; native_driver=False keeps the step in this
+        # mirror, one entry point at a time, as the Fortran driver would call them
+        self.native = (insert_fn is None) if native_driver is None else bool(native_driver)
+        if self.native:
+            self._configure_driver()
+
+    # ------------------------------------------------------------------ native main-loop body (csrc/driver.cu)
+    def _configure_driver(self):
+        g = self.grid
+        cfg = _lib.DriverConfig()
+        cfg.cell_x_min = g.cell_x_min
+        cfg.move_window = int(bool(self.move_window))
+        cfg.raw_bc_field = (C.c_int32 * 4)(*self.raw_bc_field)
+        cfg.bc_x_min_after_move, cfg.bc_x_max_after_move = self.bc_after_move
+        cfg.n_lasers = len(self.lasers)
+        cfg.insert_mode = 0 if self.device_insert_seed is None else 1
+        cfg.insert_seed = 0 if self.device_insert_seed is None else int(self.device_insert_seed)
+        cfg.x_grid_min = g.x_grid_min
+        cfg.window_v_x, cfg.window_start_time = self.window_v_x, self.window_start_time
+        cfg.window_stop_time = self.window_stop_time
+        arr = (_lib.LaserC * max(len(self.lasers), 1))()
+        for k, L in enumerate(self.lasers):
+            arr[k] = _lib.LaserC(L.boundary, 0, L.amp, L.omega, L.pol_angle, L.t_start, L.t_end, L.t_centre, L.t_width,
+                                 L.r_width, L.phase, L.phase_curv)
+        self._keep.append(arr)
+        cfg.lasers = C.cast(arr, C.POINTER(_lib.LaserC))
+        for i, sp in enumerate(self.species):
+            cfg.insert[i] = _lib.InsertProfileC(float(sp.npart_per_cell), float(sp.density), (C.c_double * 3)(*sp.temp),
+                                                (C.c_double * 3)(*sp.drift), float(sp.density_min), float(sp.density_max))
+        cfg.time, cfg.step = self.time, self.step
+        cfg.window_shift_fraction = self.window_shift_fraction
+        cfg.window_shifts_total = self.window_shifts_total
+        cfg.window_started = int(self.window_started)
+        self._ck(self.L.cylgpu_driver_configure(self.h, C.byref(cfg)))
+
+    def _refresh_from_driver(self):
+        """host-side state the native loop advanced: no device work, no sync"""
+        st = _lib.DriverState()
+        self._ck(self.L.cylgpu_driver_get_state(self.h, C.byref(st)))
+        self._time, self._step = st.time, int(st.step)
+        self.window_started = bool(st.window_started)
+        self.window_shift_fraction = st.window_shift_fraction
+        g = self.grid
+        shifts = int(st.window_shifts_total) - self.window_shifts_total
+        for _ in range(shifts):
+            g.shift()
+        self.window_shifts_total = int(st.window_shifts_total)
+        self.bc_field = list(st.bc_field)
+
+    @property
+    def time(self):
+        return self._time
+
+    @time.setter
+    def time(self, v):
+        self._time = float(v)
+        if getattr(self, "native", False) and getattr(self, "h", None):
+            self._ck(self.L.cylgpu_driver_set_time(self.h, self._time, int(self._step)))
+
+    @property
+    def step(self):
+        return self._step
+
+    @step.setter
+    def step(self, v):
+        self._step = int(v)
+        if getattr(self, "native", False) and getattr(self, "h", None):
+            self._ck(self.L.cylgpu_driver_set_time(self.h, float(self._time), self._step))
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
@@ -317,6 +386,8 @@ class Slab:
             self.window_shift_fraction = float(d.constant_value[1])
         self.sdf_constants = {i: float(d.constant_value[k]) for k, i in enumerate(self.SDF_RESTART_CONSTANTS)
                               if d.constants_found & (1 << k)}
+        if getattr(self, "native", False):
+            self._configure_driver()
         self.efield_bcs()
         self.bfield_bcs(False)
         # J ghosts: the halo of current_finish without smoothing the stored (already smoothed) currents again
@@ -376,6 +447,20 @@ class Slab:
         self._ck(self.L.cylgpu_insert_particles(self.h, isp, self.grid.x_grid_max, float(sp.npart_per_cell),
                                                 dens.ctypes.data, temp.ctypes.data, drift.ctypes.data,
                                                 float(sp.density_min), float(sp.density_max), C.byref(n)))
+        return n.value
+
+    def insert_particles_host(self, isp, host_aos, count):
+        """insert_particles into a list that lives in host memory; returns the new count"""
+        sp = self.species[isp]
+        nrow = self.grid.ny + 2
+        dens = np.full(nrow, float(sp.density))
+        temp = np.repeat(np.asarray(sp.temp, dtype=np.float64), nrow)
+        drift = np.repeat(np.asarray(sp.drift, dtype=np.float64), nrow)
+        n = C.c_int64(int(count))
+        self._ck(self.L.cylgpu_insert_particles_host(
+            self.h, isp, self.grid.x_grid_max, float(sp.npart_per_cell), dens.ctypes.data, temp.ctypes.data,
+            drift.ctypes.data, float(sp.density_min), float(sp.density_max), host_aos.ctypes.data, host_aos.shape[0],
+            C.byref(n)))
         return n.value
 
     def insert_particles_device(self, isp, seed, column):
@@ -530,6 +615,10 @@ class Slab:
         self._ck(self.L.cylgpu_snapshot_field_boundaries(self.h))
 
     def init_half_step(self):                 # epoch2d.F90:143-161
+        if getattr(self, "native", False):
+            self._ck(self.L.cylgpu_driver_init_half_step(self.h))
+            self._refresh_from_driver()
+            return
         self.particle_bcs()
         self.efield_bcs()
         dt_store = self.dt
@@ -565,7 +654,16 @@ class Slab:
         n_new = (C.c_int64 * max(nsp, 1))()
         ptrs = (C.c_void_p * max(nsp, 1))()
         keep = []
-        if self.device_insert_seed is not None:
+        if getattr(self, "host_lists", None) is not None:
+            # the lists live in host memory (cylgpu_push_host): the column joins them there, and the plasma behind
+            # the window is dropped by the next streamed push
+            if self.grid.nranks > 1:
+                raise CylGpuError("host-resident lists with a moving window: one slab only")
+            for isp in range(nsp):
+                if self.species[isp].npart_per_cell > 0 and self.species[isp].density > 0 and \
+                        self.host_lists[isp] is not None:
+                    self.host_counts[isp] = self.insert_particles_host(isp, self.host_lists[isp], self.host_counts[isp])
+        elif self.device_insert_seed is not None:
             for isp in range(nsp):
                 if self.species[isp].npart_per_cell > 0 and self.species[isp].density > 0:
                     self.insert_particles_device(isp, self.device_insert_seed, self.window_shifts_total)
@@ -588,7 +686,17 @@ class Slab:
         self._ck(self.L.cylgpu_window_shift(self.h, n_new, ptrs, grid5))
         self.window_shifts_total += 1
 
+    def run_steps(self, n):
+        """n whole steps inside the library (native driver only)"""
+        assert self.native and self.host_lists is None
+        self._ck(self.L.cylgpu_driver_step(self.h, int(n)))
+        self._refresh_from_driver()
+
     def step_once(self, flush_rng=None):      # epoch2d.F90:189-266 loop body, optional physics off
+        if getattr(self, "native", False) and self.host_lists is None and flush_rng is None:
+            self._ck(self.L.cylgpu_driver_step(self.h, 1))
+            self._refresh_from_driver()
+            return
         self.update_eb_fields_half()
         self.push_particles()
         self.current_finish()
@@ -600,3 +708,5 @@ class Slab:
         self.time = self.time + self.dt / 2.0
         self.update_eb_fields_final()
         self.moving_window()
+        if getattr(self, "native", False):       # this step ran in the mirror: the library's copy of the loop state follows
+            self._configure_driver()

@@ -220,6 +220,14 @@ int cylgpu_insert_particles(cylgpu_handle h, int ispecies, double x_grid_max, do
                             const double* density, const double* temperature, const double* drift, double dmin,
                             double dmax, int64_t* n_inserted);
 
+/* ... and for a species whose list lives in host memory (cylgpu_push_host): the column is written behind the
+ * *n_inout records of host_aos (capacity records of 7 doubles) and *n_inout grows by it.  The removal of the plasma
+ * behind the window (remove_particles, window.F90:304-325) needs no call for such lists: cylgpu_window_shift notes
+ * the new x_min and the next cylgpu_push_host drops what lies behind it while the list streams through the GPU. */
+int cylgpu_insert_particles_host(cylgpu_handle h, int ispecies, double x_grid_max, double npart_per_cell,
+                                 const double* density, const double* temperature, const double* drift, double dmin,
+                                 double dmax, double* host_aos, int64_t capacity, int64_t* n_inout);
+
 /* The same column generated ON THE DEVICE from a counter-based stream: one
  * kernel writes the new particles straight into the SoA list, with no host loop or upload, and
  * the plasma does not depend on the number of ranks.  Same arguments and per-particle arithmetic
@@ -361,6 +369,58 @@ int cylgpu_reset_stats(cylgpu_handle h);
  * 4 * (ny + 2) * particles-per-cell is a safe capacity for x-slabs.  Every rank must set the same value.
  * capacity = 0 (default): the exact protocol, counts first and then the payload, two host syncs per species. */
 int cylgpu_set_exchange_capacity(cylgpu_handle h, int64_t capacity);
+/* ---- the main-loop body, natively ----
+ * What the reference's PROGRAM pic does between the hot-path calls is host work there too: time / step
+ * bookkeeping, the laser source evaluation of outflow_bcs_x_min / x_max (laser.f90:276-328,442-461,556-575), the
+ * moving-window trigger and shift_window's grid update (window.F90:62-94,330-376, utilities.f90:343-372).  A host
+ * that owns these (the Fortran driver) calls the entry points above one by one; a host that does not (a C / C++ /
+ * Python caller, bench.py) configures them once and lets the library run whole steps in the reference's order
+ * (epoch2d.F90:189-266, optional physics packages off) with a handful of launches per step and no interpreter in
+ * between -- with x-slabs over 8 GPUs a step is a few milliseconds. */
+typedef struct cylgpu_laser {      /* laser_block (laser.f90) restricted to what the decks in scope use */
+  int32_t boundary, pad_;          /* CYLGPU_BD_X_MIN / _X_MAX */
+  double amp, omega, pol_angle;    /* amp = 100 sqrt(I[W/cm2] / (c eps0 / 2)), deck_laser_block.f90:135-139 */
+  double t_start, t_end;
+  double t_centre, t_width;        /* t_profile = gauss(time, t_centre, t_width); t_width <= 0: constant */
+  double r_width;                  /* profile = gauss(y, 0, r_width); <= 0: flat */
+  double phase, phase_curv;        /* phase(y) = phase + phase_curv y^2 */
+} cylgpu_laser;
+typedef struct cylgpu_insert_profile {   /* uniform plasma of the window's new column (window.F90:203-220) */
+  double npart_per_cell, density;        /* npart_per_cell <= 0 or density <= 0: nothing is inserted */
+  double temp[3], drift[3];
+  double density_min, density_max;
+} cylgpu_insert_profile;
+typedef struct cylgpu_driver_config {
+  int32_t cell_x_min;              /* first global cell of this rank, 1-based (mpi_routines.F90:312-337) */
+  int32_t move_window;
+  int32_t raw_bc_field[4];         /* the deck's bc_field BEFORE setup_boundaries normalises it */
+  int32_t bc_x_min_after_move, bc_x_max_after_move;
+  int32_t n_lasers;
+  int32_t insert_mode;             /* 0: cylgpu_insert_particles (the rank's KISS stream), 1: _device (Philox) */
+  uint64_t insert_seed;
+  double x_grid_min;               /* global x(1) = x_min + dx / 2 */
+  double window_v_x, window_start_time, window_stop_time;
+  const cylgpu_laser* lasers;
+  cylgpu_insert_profile insert[CYLGPU_MAX_SPECIES];
+  /* where the run stands (0 for a fresh run; from a restart dump otherwise) */
+  double time, window_shift_fraction;
+  int64_t step, window_shifts_total;
+  int32_t window_started, pad_;
+} cylgpu_driver_config;
+typedef struct cylgpu_driver_state {
+  double time;
+  int64_t step;
+  int32_t window_started, pad_;
+  double window_shift_fraction;
+  int64_t window_shifts_total;
+  double x_grid_min, x_min, x_max, x_grid_min_local, x_min_local, x_max_local;
+  int32_t bc_field[4];
+} cylgpu_driver_state;
+int cylgpu_driver_configure(cylgpu_handle h, const cylgpu_driver_config* cfg);
+int cylgpu_driver_init_half_step(cylgpu_handle h);          /* epoch2d.F90:143-161 */
+int cylgpu_driver_step(cylgpu_handle h, int64_t nsteps);    /* epoch2d.F90:189-266, nsteps times */
+int cylgpu_driver_get_state(cylgpu_handle h, cylgpu_driver_state* out);
+int cylgpu_driver_set_time(cylgpu_handle h, double time, int64_t step);
 /* per-phase CUDA-event timers in cylgpu_stats (adds a host sync per phase); default off */
 int cylgpu_set_timing(cylgpu_handle h, int on);
 

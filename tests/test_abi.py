@@ -33,6 +33,32 @@ def test_struct_layouts_match_header(cylgpu_lib):
     assert ctypes.sizeof(_lib.Config) == 4 * 16 + 8 * 10 + 8 * 5
 
 
+def test_struct_layouts_match_the_c_compiler(cylgpu_lib, tmp_path):
+    """sizeof and the offset of every member of the structs that cross the boundary, as gcc lays out include/cylgpu.h,
+    against the ctypes mirrors of _lib.py (what a BIND(C) type of the Fortran shim has to reproduce as well)"""
+    import subprocess
+    from cylindrical_epoch_b200 import _lib
+    structs = {"cylgpu_config": _lib.Config, "cylgpu_species": _lib.SpeciesC, "cylgpu_stats_t": _lib.Stats,
+               "cylgpu_laser": _lib.LaserC, "cylgpu_insert_profile": _lib.InsertProfileC,
+               "cylgpu_driver_config": _lib.DriverConfig, "cylgpu_driver_state": _lib.DriverState,
+               "cylgpu_sdf_desc": _lib.SdfDesc}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "cylgpu.h"', "int main(void) {"]
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(ln.split() for ln in subprocess.check_output([str(exe)], text=True).splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, (cname, fname)
+
+
 def test_no_cpu_fallback(cylgpu_lib):
     import torch
     if torch.cuda.is_available():

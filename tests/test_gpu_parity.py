@@ -247,18 +247,21 @@ def test_two_ranks_fabric(deckname):
         p.close()
 
 
-@pytest.mark.parametrize("deckname,nranks", [("lwfa", 1), ("thermal", 1), ("thermal", 2), ("lwfa", 2)])
+@pytest.mark.parametrize("deckname,nranks", [("lwfa", 1), ("thermal", 1), ("thermal", 2), ("lwfa", 2), ("window", 1)])
 def test_host_resident_lists_streamed_push(deckname, nranks):
     """cylgpu_push_host: the particle lists stay in host memory and are streamed through the GPU
     in chunks (several chunks per step here); same fields, currents, particles and migration
-    counts as the oracle."""
+    counts as the oracle.  "window": with the moving window -- the new column joins the host list
+    (cylgpu_insert_particles_host) and the plasma behind the window is dropped by the next streamed push."""
     if deckname == "lwfa":
         d, tol = decks.lwfa(nx=96, ny=32, n_mode=2, ppc_e=4, ppc_p=1), 1e-9
+    elif deckname == "window":
+        d, tol = decks.lwfa(nx=64, ny=24, n_mode=2, ppc_e=4, ppc_p=1, window=True, t_centre=30e-15), 1e-9
     else:
         d, tol = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8), TOL_HOT
     p = Pair(d, nranks=nranks, host_resident=True, host_chunk=2048)
     try:
-        for _ in range(3):
+        for _ in range(6 if deckname == "window" else 3):
             p.step(5)
             p.check_counts()
             p.check_fields(tol)

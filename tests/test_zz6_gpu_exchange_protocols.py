@@ -63,3 +63,26 @@ def test_overflow_of_the_fixed_size_message_is_reported():
             p.slabs[0].particle_count(0)
     finally:
         p.close()
+
+
+@pytest.mark.parametrize("deckname,nranks", [("window", 1), ("window", 2), ("thermal", 1)])
+def test_loop_body_one_entry_point_at_a_time(deckname, nranks):
+    """every other GPU test runs whole steps inside the library (csrc/driver.cu, cylgpu_driver_step); this one drives
+    the same steps one entry point at a time from the host mirror, as the Fortran driver of INTEGRATION.md would
+    (fields_half, push, current_finish, fields_final with host-evaluated laser sources, the window logic, insertion,
+    window_shift, particle_bcs): same run"""
+    d = DECKS[deckname]()
+    p = Pair(d, nranks=nranks, slab_kw=dict(native_driver=False))
+    try:
+        assert not p.slabs[0].native
+        tol = TOL_HOT if deckname == "thermal" else 1e-9
+        for _ in range(3):
+            p.step(10)
+            p.check_counts()
+            p.check_fields(tol)
+            p.check_particles(tol)
+        if deckname == "window":
+            assert p.slabs[0].window_shifts_total >= 15
+            assert p.slabs[-1].rng_get_state() == p.oracle.rng_state(nranks - 1)
+    finally:
+        p.close()
