@@ -31,6 +31,8 @@ static int check_handle_fields(cylgpu_handle h) {
 // the counts on the device: then this waits for the newest copy)
 static int check_handle(cylgpu_handle h) {
   TRY(check_handle_fields(h));
+  TRY(flush_pending_remove(h));
+  h->r_clean = false;   // whatever this call does to the lists, the next particle_bcs tests every rule
   return poll_counts(h, true);
 }
 
@@ -411,6 +413,7 @@ int cylgpu_download_particles(cylgpu_handle c, int isp, int64_t capacity, double
 
 int cylgpu_particle_count(cylgpu_handle c, int isp, int64_t* n_out) {
   if (!c || isp < 0 || isp >= c->cfg.n_species || !n_out) { set_error("bad argument"); return 2; }
+  TRY(flush_pending_remove(c));
   TRY(poll_counts(c, true));   // device-resident counts: wait for the newest copy
   *n_out = c->species[isp].n;
   return 0;
@@ -574,7 +577,10 @@ int cylgpu_window_shift(cylgpu_handle c, const int64_t* n_new, const double* con
   if (!grid5) { set_error("window_shift needs the shifted grid"); return 2; }
   if (n_new && new_aos) {
     for (int isp = 0; isp < c->cfg.n_species; ++isp)
-      if (n_new[isp] > 0) TRY(append_async(c, isp, n_new[isp], new_aos[isp]));
+      if (n_new[isp] > 0) {
+        TRY(append_async(c, isp, n_new[isp], new_aos[isp]));
+        c->r_clean = false;   // a caller-supplied column: the next particle_bcs tests every rule
+      }
   }
   c->x_grid_min_local = grid5[0];
   c->x_min = grid5[1]; c->x_max = grid5[2];
@@ -821,6 +827,7 @@ int cylgpu_energy(cylgpu_handle c, double* out2) { TRY(check_handle(c)); return 
 
 int cylgpu_stats(cylgpu_handle c, cylgpu_stats_t* out) {
   if (!c || !out) { set_error("bad argument"); return 2; }
+  TRY(flush_pending_remove(c));
   TRY(poll_counts(c, true));
   c->timers.drain();
   for (int i = 0; i < CYLGPU_MAX_SPECIES; ++i) c->stats.n_particles[i] = c->species[i].n;

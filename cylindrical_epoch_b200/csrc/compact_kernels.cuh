@@ -24,6 +24,7 @@ __global__ void k_plan_compact(const unsigned long long* __restrict__ cnt, unsig
     pstats[PST_SENT_L] += nl;
     pstats[PST_SENT_R] += nr;
     pstats[PST_REMOVED] += (long long)cnt[CNT_GONE];
+    pstats[PST_WINDOW_REMOVED] += (long long)cnt[CNT_GONE_WINDOW];   // remove_particles riding on this classification
   }
   if (nl > xcap || nr > xcap) pstats[PST_OVERFLOW] = 1;   // the surplus is lost: reported as an error
   if (nl > xcap) nl = xcap;
@@ -119,6 +120,13 @@ __global__ void __launch_bounds__(256) k_pbcs_classify_dev(BcsConst B, double* _
                                                            const int64_t* __restrict__ n_dev) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *n_dev) return;
+  const double X = x[i];
+  if (X < B.remove_x) {   // behind the window that has just moved (window.F90:304-325)
+    record_leaver(hole_list, hole_flag, cnt, (uint32_t)i, FL_GONE_WINDOW);
+    return;
+  }
+  // a list that was inside before the window moved can only have left through an x face
+  if (B.x_only && X >= B.x_min_local && X < B.x_max_local) return;
   MemParticle a{x + i, y + i, z + i, px + i, py + i, pz + i};
   const uint8_t f = particle_bcs_one(B, a);
   if (f != FL_KEEP) record_leaver(hole_list, hole_flag, cnt, (uint32_t)i, f);

@@ -153,6 +153,10 @@ struct cylgpu_ctx {
   int64_t* h_pub = nullptr;                 // pinned: 8 slots of [CYLGPU_MAX_SPECIES + PST_N]
   uint64_t pub_head = 0;
   bool overflowed = false;                  // sticky: a fixed-size exchange met more migrants than xcap
+  // window shift with device-resident counts: remove_particles waits for the particle_bcs that follows the shift
+  bool pending_remove = false;
+  double pending_remove_x = 0.0;
+  bool r_clean = false;                     // every listed particle is inside in r (the last particle_bcs saw it there)
   // window columns on their way to the device: pinned ring (append_async)
   double* app_pin[4] = {0, 0, 0, 0};
   double* app_dev[4] = {0, 0, 0, 0};
@@ -241,6 +245,7 @@ int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip
 // particles.cu
 int do_push(cylgpu_ctx* c);
 int do_push_bcs(cylgpu_ctx* c);
+int flush_pending_remove(cylgpu_ctx* c);         // remove_particles left pending by a window shift, now
 int poll_counts(cylgpu_ctx* c, bool block);      // tighten (block: make exact) the host's particle counts
 int publish_counts(cylgpu_ctx* c);               // enqueue the device -> host copy of counts + statistics
 int set_count_exact(cylgpu_ctx* c, int isp);     // the host changed species[isp].n: mirror it on the device

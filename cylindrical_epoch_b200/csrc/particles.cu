@@ -560,6 +560,8 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
 }
 
 int do_push(cylgpu_ctx* c) {
+  TRY(flush_pending_remove(c));
+  c->r_clean = false;   // pushed without particle_bcs
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
@@ -737,6 +739,8 @@ static BcsConst make_bcs_const(cylgpu_ctx* c) {
   B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
   B.x_min_boundary = c->cfg.x_min_boundary;
   B.x_max_boundary = c->cfg.x_max_boundary;
+  B.remove_x = -1.0e300;
+  B.x_only = 0;
   return B;
 }
 
@@ -1008,13 +1012,43 @@ static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classifi
 }
 
 int do_particle_bcs(cylgpu_ctx* c) {
-  const BcsConst B = make_bcs_const(c);
+  BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
-  if (c->xcap > 0) TRY(zero_pstats(c));
+  if (c->xcap > 0) {
+    TRY(zero_pstats(c));
+    // after a window shift (window.F90:364): the removal behind the window rides on this classification, and a
+    // list the fused push left inside in r is only tested against the x faces that moved
+    if (c->pending_remove) B.remove_x = c->pending_remove_x;
+    B.x_only = c->r_clean ? 1 : 0;
+  }
   for (int isp = 0; isp < c->cfg.n_species; ++isp)
     if (c->species[isp].set) TRY(pbcs_species(c, isp, B, false));
-  if (c->xcap > 0) TRY(publish_counts(c));
+  if (c->xcap > 0) {
+    c->pending_remove = false;
+    c->r_clean = true;   // everything outside has been dealt with
+    TRY(publish_counts(c));
+  }
   return 0;
+}
+
+// remove_particles that a window shift left pending (device-resident counts): normally it rides on the
+// particle_bcs that follows the shift; anything else that looks at the lists first makes it happen here
+int flush_pending_remove(cylgpu_ctx* c) {
+  if (!c->pending_remove) return 0;
+  c->pending_remove = false;
+  if (!c->cfg.x_min_boundary) return 0;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (!S.set || S.n == 0) continue;
+    TRY(reserve_pscratch(c, S.n));
+    TRY(ensure_xbufs(c));
+    CUDA_TRY(cudaMemsetAsync(c->counters, 0, 8 * sizeof(unsigned long long), c->stream));
+    k_flag_behind_dev<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->pending_remove_x, c->hole_list, c->flag,
+                                                            c->counters, c->n_dev + isp);
+    c->stats.kernel_launches += 1;
+    TRY(compact_dev(c, isp, true, false, false));
+  }
+  return publish_counts(c);
 }
 
 // push_particles including its particle_bcs call (particles.F90:28-734): species by species,
@@ -1024,6 +1058,7 @@ int do_push_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
   if (c->xcap > 0) {
+    TRY(flush_pending_remove(c));
     TRY(poll_counts(c, false));   // whatever count copies have arrived tighten the bounds; nobody waits
     TRY(zero_pstats(c));
   }
@@ -1035,7 +1070,10 @@ int do_push_bcs(cylgpu_ctx* c) {
     TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
     TRY(pbcs_species(c, isp, B, fused));
   }
-  if (c->xcap > 0) TRY(publish_counts(c));
+  if (c->xcap > 0) {
+    c->r_clean = true;   // particle_bcs has seen every particle at its new position
+    TRY(publish_counts(c));
+  }
   if (need_sort) {
     c->sorted_valid = true;
     c->pushes_since_sort = 0;
@@ -1198,13 +1236,10 @@ int do_remove_behind(cylgpu_ctx* c) {
     if (!S.set || S.n == 0) continue;
     TRY(reserve_pscratch(c, S.n));
     CUDA_TRY(cudaMemsetAsync(cnt, 0, 8 * sizeof(unsigned long long), c->stream));
-    if (c->xcap > 0) {
-      TRY(ensure_xbufs(c));
-      k_flag_behind_dev<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->hole_list, c->flag, cnt,
-                                                              c->n_dev + isp);
-      c->stats.kernel_launches += 1;
-      TRY(compact_dev(c, isp, true, false, false));
-      continue;
+    if (c->xcap > 0) {   // rides on the particle_bcs that follows the shift (do_particle_bcs / flush_pending_remove)
+      c->pending_remove = true;
+      c->pending_remove_x = c->x_min;
+      break;
     }
     k_flag_behind<<<nblk(S.n, 256), 256, 0, c->stream>>>(S.d[0], c->x_min, c->hole_list, c->flag, cnt, S.n);
     c->stats.kernel_launches += 1;

@@ -16,10 +16,14 @@ struct BcsConst {
   double y_max2_inside;   // r^2 below this is inside y_max whatever the rounding of the square root
   int x_min_boundary, x_max_boundary;
   int bc[4];
+  // the stand-alone classification after a window shift (k_pbcs_classify_dev): remove_particles (window.F90:304-325)
+  // rides on it (x < remove_x leaves the list), and a list that was inside in r before the shift is only tested in x
+  double remove_x;
+  int x_only;
 };
 
-enum { FL_KEEP = 0, FL_LEFT = 1, FL_RIGHT = 2, FL_GONE = 3 };
-enum { CNT_HOLE = 0, CNT_LEFT = 1, CNT_RIGHT = 2, CNT_GONE = 3, CNT_TAIL = 4, CNT_LOW = 5, CNT_PACK_L = 6, CNT_PACK_R = 7 };
+enum { FL_KEEP = 0, FL_LEFT = 1, FL_RIGHT = 2, FL_GONE = 3, FL_GONE_WINDOW = 4 };
+enum { CNT_HOLE = 0, CNT_LEFT = 1, CNT_RIGHT = 2, CNT_GONE = 3, CNT_GONE_WINDOW = 4, CNT_LOW = 5, CNT_PACK_L = 6, CNT_PACK_R = 7 };
 
 struct MemParticle {   // a particle in the SoA arrays: components are touched only when a rule needs them
   double *x, *y, *z, *px, *py, *pz;

@@ -620,6 +620,8 @@ EMUL_API void emul_pbcs_classify(double* const* soa, int64_t n, const int32_t* b
   B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
   B.x_min_boundary = x_min_boundary;
   B.x_max_boundary = x_max_boundary;
+  B.remove_x = -1.0e300;
+  B.x_only = 0;
   for (int k = 0; k < 4; ++k) B.bc[k] = bc_particle[k];
   unsigned long long cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (n > 0)
@@ -685,7 +687,8 @@ EMUL_API int64_t emul_insert_column(int ny, int isp, double x_grid_max, double n
 // n: particles per slab in / out; bounds: x_min_local, x_max_local per slab; pstats: nslab x PST_N out.
 EMUL_API int emul_pbcs_fast(int nslab, double* const* soa, int64_t* n, int64_t cap, const int32_t* bc_particle,
                             double x_min, double x_max, const double* x_min_local, const double* x_max_local,
-                            double y_max, double dx, double dy, int periodic, long long xcap, int64_t* pstats_out) {
+                            double y_max, double dx, double dy, int periodic, long long xcap, int64_t* pstats_out,
+                            double remove_x, int x_only) {
   const size_t msg = (size_t)(7 * xcap + XHDR);
   std::vector<std::vector<double>> send_l(nslab, std::vector<double>(msg, -7.0)), send_r(nslab, std::vector<double>(msg, -7.0));
   std::vector<std::vector<int64_t>> ndev(nslab, std::vector<int64_t>(1 + PST_N, 0));
@@ -704,6 +707,8 @@ EMUL_API int emul_pbcs_fast(int nslab, double* const* soa, int64_t* n, int64_t c
     B.y_max2_inside = B.y_max * B.y_max * (1.0 - 1.0e-14);
     B.x_min_boundary = (k == 0);
     B.x_max_boundary = (k == nslab - 1);
+    B.remove_x = (k == 0) ? remove_x : -1.0e300;   // remove_particles riding on the classification (x_min slab)
+    B.x_only = x_only;
     for (int q = 0; q < 4; ++q) B.bc[q] = bc_particle[q];
     const bool has_l = k > 0 || periodic, has_r = k < nslab - 1 || periodic;
     Soa s;

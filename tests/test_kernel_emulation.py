@@ -281,7 +281,7 @@ def test_particle_bcs_with_device_resident_counts_matches_the_oracle(emul, deck_
     L.emul_pbcs_fast.restype = C.c_int
     L.emul_pbcs_fast.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int32),
                                  C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
-                                 C.c_double, C.c_double, C.c_int, C.c_longlong, C.POINTER(C.c_int64)]
+                                 C.c_double, C.c_double, C.c_int, C.c_longlong, C.POINTER(C.c_int64), C.c_double, C.c_int]
     d = {"drift": lambda: decks.drift(nx=20, ny=10, n_mode=1),
          "thermal": lambda: decks.thermal(nx=36, ny=12, n_mode=1, ppc=6, temp_k=5.0e8),
          "lwfa": lambda: decks.lwfa(nx=32, ny=12, n_mode=2, ppc_e=4, ppc_p=0)}[deck_name]()
@@ -307,7 +307,7 @@ def test_particle_bcs_with_device_resident_counts_matches_the_oracle(emul, deck_
         xr = (C.c_double * nranks)(*[w.rank_info(k)["x_max_local"] for k in range(nranks)])
         pst = (C.c_int64 * (8 * nranks))()
         rc = L.emul_pbcs_fast(nranks, ptrs, n, cap, (C.c_int32 * 4)(*w.bc_particle(0)), sc["x_min"], sc["x_max"], xl, xr,
-                              sc["y_max"], sc["dx"], sc["dy"], periodic, xcap, pst)
+                              sc["y_max"], sc["dx"], sc["dy"], periodic, xcap, pst, -1.0e300, 0)
         assert rc == 0
         w.call("particle_bcs")
         for k in range(nranks):
@@ -330,6 +330,68 @@ def test_particle_bcs_with_device_resident_counts_matches_the_oracle(emul, deck_
     assert exercised > 0, "the deck never exercised a boundary"
     if xcap < 16:
         assert overflowed > 0
+
+
+@pytest.mark.parametrize("nranks", [1, 2])
+def test_window_shift_classification_with_device_resident_counts(emul, nranks):
+    """after a window shift (window.F90:62-94,364): remove_particles rides on the particle_bcs classification
+    (x < the new x_min leaves the list of the x_min slab and is counted as a window removal) and a list that was
+    inside before the shift is only tested against the x faces -- against the oracle's remove_particles +
+    particle_bcs on the same shifted window"""
+    L = emul
+    L.emul_pbcs_fast.restype = C.c_int
+    L.emul_pbcs_fast.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int64, C.POINTER(C.c_int32),
+                                 C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double,
+                                 C.c_double, C.c_double, C.c_int, C.c_longlong, C.POINTER(C.c_int64), C.c_double, C.c_int]
+    d = decks.lwfa(nx=40, ny=12, n_mode=2, ppc_e=4, ppc_p=0, window=True, t_centre=30e-15)
+    d.species[0].temp = (3.0e7, 3.0e7, 3.0e7)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    seen_shift = 0
+    for _ in range(8):
+        # one step up to the window: the lists are clean (particle_bcs of the push has run)
+        for op in ("fields_half", "push", "current_finish", "advance_half_time", "flush_rng", "advance_half_time",
+                   "fields_final"):
+            w.call(op)
+        shifts0 = int(w.scalars()["window_shifts_total"])
+        before = [w.particles(k, 0).reshape(-1, 7).copy() for k in range(nranks)]
+        w.call("moving_window")          # insert + remove_particles + shift + particle_bcs in the oracle
+        sc = w.scalars()
+        if int(sc["window_shifts_total"]) == shifts0:
+            continue
+        seen_shift += 1
+        after = [w.particles(k, 0).reshape(-1, 7) for k in range(nranks)]
+        # the freshly inserted column (appended to the last slab before the shift): the rows no list held before
+        known = {tuple(r) for p in before for r in p}
+        ins = np.array([r for r in after[-1] if tuple(r) not in known]).reshape(-1, 7)
+        assert ins.shape[0] > 0 and ins[:, 0].min() >= sc["x_max"] - sc["dx"]
+        cap = max(p.shape[0] for p in before) + 8192 + ins.shape[0]
+        soa = [[np.zeros(cap) for _ in range(7)] for _ in range(nranks)]
+        start = []
+        for k, p in enumerate(before):
+            full = np.concatenate([p, ins]) if k == nranks - 1 else p
+            start.append(full)
+            for q in range(7):
+                soa[k][q][:full.shape[0]] = full[:, q]
+        ptrs = (C.c_void_p * (7 * nranks))(*[a.ctypes.data for k in range(nranks) for a in soa[k]])
+        n = (C.c_int64 * nranks)(*[p.shape[0] for p in start])
+        xl = (C.c_double * nranks)(*[w.rank_info(k)["x_min_local"] for k in range(nranks)])
+        xr = (C.c_double * nranks)(*[w.rank_info(k)["x_max_local"] for k in range(nranks)])
+        pst = (C.c_int64 * (8 * nranks))()
+        rc = L.emul_pbcs_fast(nranks, ptrs, n, cap, (C.c_int32 * 4)(*w.bc_particle(0)), sc["x_min"], sc["x_max"], xl, xr,
+                              sc["y_max"], sc["dx"], sc["dy"], 0, 4096, pst, sc["x_min"], 1)
+        assert rc == 0
+        # window removals (statistic 4) + what particle_bcs itself removed through the open walls (statistic 2)
+        removed = sum(int(pst[8 * k + 4]) + int(pst[8 * k + 2]) for k in range(nranks))
+        assert removed == sum(p.shape[0] for p in start) - sum(p.shape[0] for p in after)
+        assert sum(int(pst[8 * k + 4]) for k in range(nranks)) > 0
+        for k in range(nranks):
+            st = w.stats(k)
+            assert tuple(int(pst[8 * k + q]) for q in range(4)) == (st["sent_left"], st["sent_right"], st["removed"],
+                                                                     st["received"])
+            got = np.stack([soa[k][q][:int(n[k])] for q in range(7)], axis=1)
+            assert np.array_equal(decks.sort_particles(got), decks.sort_particles(after[k])), k
+    assert seen_shift >= 3
 
 
 # ------------------------------------------------------------------------------------------------------
