@@ -31,6 +31,7 @@ static int check_handle_fields(cylgpu_handle h) {
 // the counts on the device: then this waits for the newest copy)
 static int check_handle(cylgpu_handle h) {
   TRY(check_handle_fields(h));
+  TRY(presort_join(h, false));
   TRY(flush_pending_remove(h));
   h->r_clean = false;   // whatever this call does to the lists, the next particle_bcs tests every rule
   return poll_counts(h, true);
@@ -102,10 +103,10 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   }
   CUDA_TRY(cudaMalloc(&c->src, 4 * (size_t)(g.ny + 1) * sizeof(double)));
   c->halo_elems = (size_t)3 * g.M * g.SY * NG;
-  CUDA_TRY(cudaMalloc(&c->sbuf_l, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
-  CUDA_TRY(cudaMalloc(&c->sbuf_r, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
-  CUDA_TRY(cudaMalloc(&c->rbuf_l, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
-  CUDA_TRY(cudaMalloc(&c->rbuf_r, 2 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange
+  CUDA_TRY(cudaMalloc(&c->sbuf_l, 3 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange, x3: the window shift
+  CUDA_TRY(cudaMalloc(&c->sbuf_r, 3 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange, x3: the window shift
+  CUDA_TRY(cudaMalloc(&c->rbuf_l, 3 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange, x3: the window shift
+  CUDA_TRY(cudaMalloc(&c->rbuf_r, 3 * c->halo_elems * sizeof(cplx)));   // x2: the merged J exchange, x3: the window shift
   CUDA_TRY(cudaMalloc(&c->counters, 32 * sizeof(unsigned long long)));
   CUDA_TRY(cudaMemsetAsync(c->counters, 0, 32 * sizeof(unsigned long long), c->stream));
   CUDA_TRY(cudaMallocHost(&c->h_counters, 32 * sizeof(unsigned long long)));
@@ -153,6 +154,9 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaFree(c->counters); cudaFreeHost(c->h_counters); cudaFree(c->d_energy);
   c->timers.destroy();
   if (c->ev_wait) cudaEventDestroy(c->ev_wait);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   cudaFree(c->n_dev); cudaFree(c->d_plan);
   if (c->h_pub) cudaFreeHost(c->h_pub);
   for (int k = 0; k < 8; ++k) if (c->pub[k].ev) cudaEventDestroy(c->pub[k].ev);
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(256) k_aos_to_soa_dev(const double* __restrict
 int append_async(cylgpu_ctx* c, int isp, int64_t n, const double* host_aos) {
   if (isp < 0 || isp >= c->cfg.n_species) { set_error("bad species index"); return 2; }
   if (n <= 0) return 0;
+  TRY(presort_join(c, false));
   SpeciesState& S = c->species[isp];
   TRY(reserve_particles(c, isp, S.n + n));
   const int slot = c->app_slot;
@@ -508,6 +513,7 @@ static int fields_half_body(cylgpu_ctx* c) {
 // fields.f90:316-337
 int cylgpu_fields_half(cylgpu_handle c) {
   TRY(check_handle_fields(c));
+  TRY(presort_fork(c));   // the next push's cell sort, on the side stream behind this phase
   PhaseTimer t(c, &c->stats.ms_fields);
   return run_field_phase(c, 0, [c]() { return fields_half_body(c); });
 }

@@ -458,10 +458,31 @@ int do_shift_fields(cylgpu_ctx* c) {
     c->stats.kernel_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
-  // field_mode_bc on each shifted array (window.F90:147-150): three packed exchanges
-  TRY(halo_x(c, CYLGPU_EXM, CYLGPU_ERM, CYLGPU_ETM, 0, 0, 0));
-  TRY(halo_x(c, CYLGPU_BXM, CYLGPU_BRM, CYLGPU_BTM, 0, 0, 0));
-  TRY(halo_x(c, CYLGPU_JXM, CYLGPU_JRM, CYLGPU_JTM, 0, 0, 0));
+  // field_mode_bc on each shifted array (window.F90:147-150): the nine halos travel as ONE message per neighbour
+  {
+    const bool has_l = c->left >= 0, has_r = c->right >= 0;
+    const bool fill_r = has_r && (!c->cfg.x_max_boundary || c->bc_field[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC);
+    const bool fill_l = has_l && (!c->cfg.x_min_boundary || c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC);
+    if (fill_l || fill_r) {
+      const size_t he = c->halo_elems;
+      const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+      Halo3 h[3];
+      for (int q = 0; q < 3; ++q) {
+        for (int k = 0; k < 3; ++k) { h[q].f[k] = c->f[3 * q + k]; h[q].skip[k] = 0; }
+        k_halo_pack<<<grd, 128, 0, c->stream>>>(g, h[q], fill_l ? c->sbuf_l + q * he : nullptr,
+                                                fill_r ? c->sbuf_r + q * he : nullptr, 0, he);
+      }
+      const size_t bytes = 3 * he * sizeof(cplx);
+      TRY(transport_sendrecv(c, fill_l ? c->sbuf_l : nullptr, fill_l ? bytes : 0, fill_l ? c->rbuf_l : nullptr,
+                             fill_l ? bytes : 0, fill_r ? c->sbuf_r : nullptr, fill_r ? bytes : 0,
+                             fill_r ? c->rbuf_r : nullptr, fill_r ? bytes : 0));
+      for (int q = 0; q < 3; ++q)
+        k_halo_unpack<<<grd, 128, 0, c->stream>>>(g, h[q], fill_l ? c->rbuf_l + q * he : nullptr,
+                                                  fill_r ? c->rbuf_r + q * he : nullptr, 0, he);
+      c->stats.kernel_launches += 6;
+      CUDA_TRY(cudaGetLastError());
+    }
+  }
   if (c->cfg.x_max_boundary) {
     Snaps S;
     for (int k = 0; k < CYLGPU_NSNAPS; ++k) S.s[k] = c->snap[k];

@@ -157,6 +157,13 @@ struct cylgpu_ctx {
   bool pending_remove = false;
   double pending_remove_x = 0.0;
   bool r_clean = false;                     // every listed particle is inside in r (the last particle_bcs saw it there)
+  // The cell sort of the next push does not touch the fields and update_eb_fields_half does not touch the
+  // particles: with device-resident counts the sort is enqueued on a side stream at the start of
+  // cylgpu_fields_half and the push joins it.  With a slab per GPU of an 8-GPU run the field phase is a chain of
+  // short launches and neighbour exchanges, i.e. latency, and the sort (bandwidth) hides behind it.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool presorted = false;                   // the side stream holds the sort of the lists as they are now
   // window columns on their way to the device: pinned ring (append_async)
   double* app_pin[4] = {0, 0, 0, 0};
   double* app_dev[4] = {0, 0, 0, 0};
@@ -245,6 +252,8 @@ int halo_x(cylgpu_ctx* c, int f0, int f1, int f2, int skip0, int skip1, int skip
 // particles.cu
 int do_push(cylgpu_ctx* c);
 int do_push_bcs(cylgpu_ctx* c);
+int presort_fork(cylgpu_ctx* c);                 // enqueue the next push's cell sort on the side stream
+int presort_join(cylgpu_ctx* c, bool still_valid);   // main stream waits for it; !still_valid: the lists change, forget it
 int flush_pending_remove(cylgpu_ctx* c);         // remove_particles left pending by a window shift, now
 int poll_counts(cylgpu_ctx* c, bool block);      // tighten (block: make exact) the host's particle counts
 int publish_counts(cylgpu_ctx* c);               // enqueue the device -> host copy of counts + statistics

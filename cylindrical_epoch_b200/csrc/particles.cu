@@ -478,7 +478,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   if (!strips && S.lazy) TRY(poll_counts(c, true));   // k_push_v0 / v1 take the exact count
   if (!S.set || S.sp.immobile || S.n == 0) return 0;
   if (c->xcap > 0 && fuse_bcs) TRY(reserve_particles(c, isp, S.n + 2 * c->xcap));   // arrivals of this step
-  if (need_sort) {
+  if (need_sort && !(c->presorted && strips)) {   // (presorted: the side stream did it behind the field phase)
     PhaseTimer sort_timer(c, &c->stats.ms_sort);
     TRY(do_sort_species(c, isp, /*physical=*/!strips));
   }
@@ -560,6 +560,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
 }
 
 int do_push(cylgpu_ctx* c) {
+  TRY(presort_join(c, false));
   TRY(flush_pending_remove(c));
   c->r_clean = false;   // pushed without particle_bcs
   TRY(push_prologue(c));
@@ -1012,6 +1013,7 @@ static int pbcs_species(cylgpu_ctx* c, int isp, const BcsConst& B, bool classifi
 }
 
 int do_particle_bcs(cylgpu_ctx* c) {
+  TRY(presort_join(c, false));
   BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
   if (c->xcap > 0) {
@@ -1051,6 +1053,51 @@ int flush_pending_remove(cylgpu_ctx* c) {
   return publish_counts(c);
 }
 
+// The cell sort of the next push on the side stream (see ctx.cuh): everything enqueued on the library stream so far
+// precedes it, nothing enqueued on the library stream afterwards touches the particle lists or their scratch until
+// presort_join.  Only with device-resident counts (no host sync inside the sort) and the strip push.
+int presort_fork(cylgpu_ctx* c) {
+  if (c->presorted || c->xcap <= 0 || c->push_variant < 2 || c->sort_interval != 1 || c->pending_remove) return 0;
+  bool any = false;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    const cylgpu::SpeciesState& S = c->species[isp];
+    any = any || (S.set && !S.sp.immobile && S.n > 0);
+  }
+  if (!any) return 0;
+  if (!c->side) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  }
+  TRY(poll_counts(c, false));
+  // capacities first, on the library stream: the sort sizes the second buffer set by them
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) {
+    cylgpu::SpeciesState& S = c->species[isp];
+    if (S.set && !S.sp.immobile && S.n > 0) TRY(reserve_particles(c, isp, S.n + 2 * c->xcap));
+  }
+  CUDA_TRY(cudaEventRecord(c->ev_fork, c->stream));
+  CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+  cudaStream_t lib = c->stream;
+  c->stream = c->side;
+  int rc = 0;
+  {
+    PhaseTimer sort_timer(c, &c->stats.ms_sort);
+    for (int isp = 0; isp < c->cfg.n_species && rc == 0; ++isp) rc = do_sort_species(c, isp, /*physical=*/false);
+  }
+  c->stream = lib;
+  if (rc != 0) return rc;
+  CUDA_TRY(cudaEventRecord(c->ev_join, c->side));
+  c->presorted = true;
+  return 0;
+}
+
+int presort_join(cylgpu_ctx* c, bool still_valid) {
+  if (!c->presorted) return 0;
+  CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+  if (!still_valid) c->presorted = false;
+  return 0;
+}
+
 // push_particles including its particle_bcs call (particles.F90:28-734): species by species,
 // the strip kernel applying the boundary rules to what it stores, so that the list is read
 // once per step
@@ -1058,10 +1105,12 @@ int do_push_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
   if (c->xcap > 0) {
+    if (c->pending_remove) TRY(presort_join(c, false));   // (never in the reference's call order)
     TRY(flush_pending_remove(c));
     TRY(poll_counts(c, false));   // whatever count copies have arrived tighten the bounds; nobody waits
     TRY(zero_pstats(c));
   }
+  TRY(presort_join(c, true));
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
@@ -1070,6 +1119,7 @@ int do_push_bcs(cylgpu_ctx* c) {
     TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
     TRY(pbcs_species(c, isp, B, fused));
   }
+  c->presorted = false;
   if (c->xcap > 0) {
     c->r_clean = true;   // particle_bcs has seen every particle at its new position
     TRY(publish_counts(c));
@@ -1127,6 +1177,7 @@ static int host_stream_setup(cylgpu_ctx* c, int64_t chunk) {
 
 int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, const int64_t* capacity,
                  int64_t* n_out) {
+  TRY(presort_join(c, false));
   cylgpu::HostStream& H = c->hs;
   const int64_t chunk = c->host_chunk;
   TRY(host_stream_setup(c, chunk));
@@ -1225,6 +1276,7 @@ int do_push_host(cylgpu_ctx* c, const int64_t* n_in, double* const* host_aos, co
 }
 
 int do_remove_behind(cylgpu_ctx* c) {
+  TRY(presort_join(c, false));
   c->stats.n_window_removed = 0;
   if (c->xcap > 0)   // device-resident counts: the removals of this shift are counted on the device
     CUDA_TRY(cudaMemsetAsync(c->n_dev + CYLGPU_MAX_SPECIES + PST_WINDOW_REMOVED, 0, sizeof(int64_t), c->stream));

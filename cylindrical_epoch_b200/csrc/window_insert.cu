@@ -182,6 +182,7 @@ int do_insert_particles_device(cylgpu_ctx* c, int isp, double x_grid_max, double
   }
   if (n_inserted) *n_inserted = total;
   if (total == 0) return 0;
+  TRY(presort_join(c, false));
   TRY(reserve_particles(c, isp, S.n + total));
   CUDA_TRY(cudaMemcpyAsync(c->ins_dev, c->ins_pin, words * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CUDA_TRY(cudaEventRecord(c->ins_ev, c->stream));
