@@ -147,6 +147,7 @@ int cylgpu_destroy(cylgpu_handle c) {
     for (int q = 0; q < 7; ++q) cudaFree(c->species[i].d[q]);
     for (int q = 0; q < 7; ++q) cudaFree(c->species[i].alt[q]);
     cudaFree(c->species[i].cell_start);
+    cudaFree(c->species[i].perm);
   }
   cudaFree(c->ptmp); cudaFree(c->perm); cudaFree(c->flag); cudaFree(c->tailmark); cudaFree(c->hole_list);
   cudaFree(c->lowhole); cudaFree(c->hightail); cudaFree(c->scan_blocks);

@@ -42,6 +42,8 @@ struct SpeciesState {
   int64_t alt_cap = 0;
   int* cell_start = nullptr;   // exclusive scan of the sort buckets of the last sort, ncell + 1 entries
   int64_t cell_start_n = 0;
+  uint32_t* perm = nullptr;    // sorted slot -> particle of the last sort (per species: all species are sorted ahead
+  int64_t perm_cap = 0;        // of the push on the side stream, presort_fork)
   // Device-resident count (cylgpu_set_exchange_capacity > 0): the exact count then lives on the device
   // (cylgpu_ctx::n_dev[isp]) and `n` above is an UPPER BOUND of it -- enough for grid sizes and capacities --
   // until the next publish has been read back (poll_counts).  lazy = false: `n` is exact.

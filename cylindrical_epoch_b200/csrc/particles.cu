@@ -531,7 +531,7 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
       CUDA_TRY(cudaFuncSetAttribute(k_push_v2<MM, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shb)); \
       smem_opted_in[c->device & 63] = true;                                                                \
     }                                                                                                      \
-    k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, c->perm, S.cell_start, ncx, nstrip_x, FB); \
+    k_push_v2<MM, MMA><<<(unsigned)(nstrip_x * ncy), 128, shb, c->stream>>>(P, pin, pout, S.perm, S.cell_start, ncx, nstrip_x, FB); \
   } while (0)
 #define LAUNCH_M(MM)                                                                                       \
   do {                                                                                                     \
@@ -1487,7 +1487,14 @@ int do_sort_species(cylgpu_ctx* c, int isp, bool physical) {
   int* count = S.cell_start;
   uint32_t* key = c->hole_list;    // scratch reuse: the particle_bcs lists are idle during a sort
   uint32_t* rank = c->lowhole;
-  uint32_t* perm = c->perm;
+  if (!physical && S.perm_cap < S.cap) {
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (S.perm) CUDA_TRY(cudaFree(S.perm));
+    S.perm = nullptr;
+    CUDA_TRY(cudaMalloc(&S.perm, (size_t)S.cap * sizeof(uint32_t)));
+    S.perm_cap = S.cap;
+  }
+  uint32_t* perm = S.perm;
   CUDA_TRY(cudaMemsetAsync(count, 0, (size_t)nscan * sizeof(int), c->stream));
   G.ipart_mc = 1.0 / (C_LIGHT * S.sp.mass);
   G.dtco2 = C_LIGHT * (c->dt / 2.0);
