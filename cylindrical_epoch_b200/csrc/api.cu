@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" boundary declared in include/cylgpu.h.
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 
@@ -119,6 +120,9 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   set_neighbours(c);
   c->tr = make_transport(c);
   if (!c->tr) return 6;
+  // peer-memory mailboxes for the neighbour exchanges (collective over the neighbours; NCCL stays as the fallback)
+  c->p2p_cap_bytes = 3 * c->halo_elems * sizeof(cplx);
+  if (int rc = p2p_setup(c, c->p2p_cap_bytes)) return rc;
   // several ranks on one host: host syncs yield the core (CYLGPU_BLOCKING_WAIT=0/1 overrides)
   c->blocking_wait = c->cfg.nranks > 1 && c->cfg.transport != CYLGPU_TRANSPORT_FABRIC;
   if (const char* e = getenv("CYLGPU_BLOCKING_WAIT")) c->blocking_wait = atoi(e) != 0;
@@ -193,7 +197,11 @@ int cylgpu_set_species(cylgpu_handle c, int isp, const cylgpu_species* sp) {
   c->species[isp].sp = *sp;
   c->species[isp].set = true;
   c->graph_epoch += 1;
+  const int l0 = c->left, r0 = c->right;
   set_neighbours(c);
+  // a periodic particle boundary closes the chain of slabs into a ring (mpi_routines.F90:186-199): new links,
+  // new mailboxes (every rank registers the same species: collective)
+  if ((c->left != l0 || c->right != r0) && c->p2p_cap_bytes) TRY(p2p_setup(c, c->p2p_cap_bytes));
   return 0;
 }
 
@@ -229,7 +237,7 @@ int cylgpu_set_stream(cylgpu_handle c, void* stream) {
 int cylgpu_synchronize(cylgpu_handle c) {
   TRY(check_handle(c));
   CUDA_TRY(cudaStreamSynchronize(c->stream));
-  return 0;
+  return p2p_check(c);
 }
 
 static int field_ok(cylgpu_handle c, int id, int n) {
@@ -857,6 +865,10 @@ int cylgpu_set_exchange_capacity(cylgpu_handle c, int64_t capacity) {
   if (capacity < 0 || capacity > ((int64_t)1 << 28)) { set_error("exchange capacity out of range"); return 2; }
   c->xcap = capacity;
   for (int i = 0; i < c->cfg.n_species; ++i) TRY(set_count_exact(c, i));
+  // the mailboxes must hold the particle message as well (every rank passes the same capacity: collective)
+  const size_t need = std::max<size_t>(3 * c->halo_elems * sizeof(cplx), (size_t)(7 * capacity + 7) * sizeof(double));
+  if (need > c->p2p_cap_bytes) { TRY(p2p_setup(c, need)); }
+  c->p2p_cap_bytes = std::max(c->p2p_cap_bytes, need);
   return 0;
 }
 int cylgpu_set_timing(cylgpu_handle c, int on) {

@@ -166,6 +166,7 @@ struct cylgpu_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool presorted = false;                   // the side stream holds the sort of the lists as they are now
+  int presort_policy = -1;                  // -1: not decided yet, 0: off, 1: on
   // window columns on their way to the device: pinned ring (append_async)
   double* app_pin[4] = {0, 0, 0, 0};
   double* app_dev[4] = {0, 0, 0, 0};
@@ -199,6 +200,8 @@ struct cylgpu_ctx {
 
   void* driver = nullptr;         // driver.cu: the main-loop body run natively (cylgpu_driver_*)
   cylgpu::Transport* tr = nullptr;
+  size_t p2p_cap_bytes = 0;
+  bool p2p_link_l = false, p2p_link_r = false;   // peer-memory mailboxes mapped on both ends of the link (transport.cu)
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)
   // device-side column (cylgpu_insert_particles_device): profile + row-offset staging
@@ -288,6 +291,8 @@ int sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, d
                   std::vector<std::vector<double>>* particles);
 // transport.cu
 Transport* make_transport(cylgpu_ctx* c);
+int p2p_setup(cylgpu_ctx* c, size_t cap_bytes);   // collective over the neighbours; failure leaves NCCL in charge
+int p2p_check(cylgpu_ctx* c);                     // error if an exchange through the mailboxes timed out
 void destroy_transport(Transport* t);
 int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, size_t rl_b, const void* sr,
                        size_t sr_b, void* rr, size_t rr_b);
