@@ -455,7 +455,9 @@ def run_ours(args, wl_name, wl):
                                                             else "periodic ring"),
                    "l2": "inputs (%.1f GB of particles per GPU) exceed the 126 MB L2; no flush needed" % (n0 * 56 / 1e9),
                    "timing": "CUDA events on the library's stream, max over ranks", "host_wall_s": wall_host,
-                   "exchange_capacity": slab.exchange_capacity},
+                   "exchange_capacity": slab.exchange_capacity,
+                   "neighbour_links": dict(zip(("transport", "left_mailbox", "right_mailbox", "mailbox_slot_KiB"),
+                                               slab.transport_info()))},
         "field_cell_mode_updates_per_s": field_rate,
         "phase_ms_per_step": {"fields": st.ms_fields / args.steps, "push_total": st.ms_push / args.steps,
                               "push_kernel": st.ms_push_kernel / args.steps, "sort": st.ms_sort / args.steps,

@@ -871,6 +871,14 @@ int cylgpu_set_exchange_capacity(cylgpu_handle c, int64_t capacity) {
   c->p2p_cap_bytes = std::max(c->p2p_cap_bytes, need);
   return 0;
 }
+int cylgpu_transport_info(cylgpu_handle c, int32_t* out4) {
+  if (!c || !out4) { set_error("bad argument"); return 2; }
+  out4[0] = c->cfg.transport;
+  out4[1] = c->p2p_link_l ? 1 : 0;
+  out4[2] = c->p2p_link_r ? 1 : 0;
+  out4[3] = (int32_t)(c->p2p_cap_bytes / 1024);
+  return 0;
+}
 int cylgpu_set_timing(cylgpu_handle c, int on) {
   if (!c) return 2;
   c->timing = on != 0;

@@ -484,6 +484,12 @@ class Slab:
         """test knob: |m dtheta| below which the deposit uses the small-angle series (particles.F90:593, 1.0e-4)"""
         self._ck(self.L.cylgpu_set_taylor_switch(self.h, float(v)))
 
+    def transport_info(self):
+        """(transport kind, left link through peer-memory mailboxes, right link, mailbox slot KiB)"""
+        out = (C.c_int32 * 4)()
+        self._ck(self.L.cylgpu_transport_info(self.h, out))
+        return tuple(out)
+
     def set_exchange_capacity(self, particles):
         """> 0: device-resident particle counts, one fixed-size migration message per neighbour and no host sync
         inside a step (include/cylgpu.h); 0: the exact count-then-data protocol of partlist.F90:842,869"""

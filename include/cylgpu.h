@@ -421,6 +421,12 @@ int cylgpu_driver_init_half_step(cylgpu_handle h);          /* epoch2d.F90:143-1
 int cylgpu_driver_step(cylgpu_handle h, int64_t nsteps);    /* epoch2d.F90:189-266, nsteps times */
 int cylgpu_driver_get_state(cylgpu_handle h, cylgpu_driver_state* out);
 int cylgpu_driver_set_time(cylgpu_handle h, double time, int64_t step);
+/* How the neighbour exchanges of this handle travel: out4 = {transport kind (CYLGPU_TRANSPORT_*), 1 if the left
+ * link goes through peer-memory mailboxes over NVLink (CUDA IPC mapping of the neighbour's buffer: one kernel on
+ * each side per message, no rendezvous), the same for the right link, slot size of the mailboxes in bytes / 1024}.
+ * With the NCCL transport the mailboxes are set up at cylgpu_create / cylgpu_set_exchange_capacity where both ends of
+ * a link can map each other (CYLGPU_P2P=0 disables them); ncclSend / ncclRecv remain the fallback per link. */
+int cylgpu_transport_info(cylgpu_handle h, int32_t* out4);
 /* per-phase CUDA-event timers in cylgpu_stats (adds a host sync per phase); default off */
 int cylgpu_set_timing(cylgpu_handle h, int on);
 
