@@ -148,7 +148,15 @@ int p2p_setup(cylgpu_ctx* c, size_t cap) {
   Transport* t = c->tr;
   c->p2p_link_l = c->p2p_link_r = false;
   if (!t || t->kind != CYLGPU_TRANSPORT_NCCL) return 0;
-  if (const char* e = getenv("CYLGPU_P2P")) if (atoi(e) == 0) return 0;
+  // Opt-in (CYLGPU_P2P=1).  Measured on C3 over 8 B200s (profiles/r2d_*): 3.81 ms per step with the mailboxes
+  // against 3.73 ms with ncclSend / ncclRecv -- a message costs four launches here (two sends, two receives, each
+  // with its own wait) against one fused NCCL kernel per exchange, and at ~10 exchanges per step that outweighs the
+  // rendezvous it saves.  Kept for the fused form (pack straight into the neighbour's slot, unpack straight out of
+  // mine: two launches per exchange instead of three), which is the next step for this path.
+  {
+    const char* e = getenv("CYLGPU_P2P");
+    if (!e || atoi(e) == 0) return 0;
+  }
   const int left = c->left, right = c->right, me = c->cfg.rank;
   if ((left < 0 && right < 0) || left == me || right == me) return 0;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
