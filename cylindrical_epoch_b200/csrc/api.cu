@@ -162,6 +162,8 @@ int cylgpu_destroy(cylgpu_handle c) {
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
+  if (c->ev_pfork) cudaEventDestroy(c->ev_pfork);
+  if (c->ev_pdone) cudaEventDestroy(c->ev_pdone);
   cudaFree(c->n_dev); cudaFree(c->d_plan);
   if (c->h_pub) cudaFreeHost(c->h_pub);
   for (int k = 0; k < 8; ++k) if (c->pub[k].ev) cudaEventDestroy(c->pub[k].ev);

@@ -166,6 +166,11 @@ struct cylgpu_ctx {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool presorted = false;                   // the side stream holds the sort of the lists as they are now
+  // ... and after the push kernel the particle chain of the last species (compaction of the leavers, neighbour
+  // exchange, arrivals, count copy) goes to the side stream as well, while the library stream runs current_finish
+  // and update_eb_fields_final: two latency chains side by side instead of one after the other
+  cudaEvent_t ev_pfork = nullptr, ev_pdone = nullptr;
+  bool side_pending = false;                // the library stream has not yet waited for that chain
   int presort_policy = -1;                  // -1: not decided yet, 0: off, 1: on
   // window columns on their way to the device: pinned ring (append_async)
   double* app_pin[4] = {0, 0, 0, 0};
@@ -293,6 +298,7 @@ int sdf_read_host(const char* path, cylgpu_sdf_desc* d, void* const* fields15, d
 Transport* make_transport(cylgpu_ctx* c);
 int p2p_setup(cylgpu_ctx* c, size_t cap_bytes);   // collective over the neighbours; failure leaves NCCL in charge
 int p2p_check(cylgpu_ctx* c);                     // error if an exchange through the mailboxes timed out
+bool transport_two_streams(const cylgpu_ctx* c);  // exchanges may run on the side stream beside the library stream's
 void destroy_transport(Transport* t);
 int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, size_t rl_b, const void* sr,
                        size_t sr_b, void* rr, size_t rr_b);

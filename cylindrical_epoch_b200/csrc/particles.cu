@@ -1056,6 +1056,16 @@ int flush_pending_remove(cylgpu_ctx* c) {
 // The cell sort of the next push on the side stream (see ctx.cuh): everything enqueued on the library stream so far
 // precedes it, nothing enqueued on the library stream afterwards touches the particle lists or their scratch until
 // presort_join.  Only with device-resident counts (no host sync inside the sort) and the strip push.
+static int ensure_side(cylgpu_ctx* c) {
+  if (c->side) return 0;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pfork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&c->ev_pdone, cudaEventDisableTiming));
+  return 0;
+}
+
 int presort_fork(cylgpu_ctx* c) {
   if (c->presorted || c->xcap <= 0 || c->push_variant < 2 || c->sort_interval != 1 || c->pending_remove) return 0;
   // Worth it only where the field phase is latency: a slab of ~1 M cell-modes (C3 over 8 GPUs: 3.73 against 3.81 ms
@@ -1072,10 +1082,10 @@ int presort_fork(cylgpu_ctx* c) {
     any = any || (S.set && !S.sp.immobile && S.n > 0);
   }
   if (!any) return 0;
-  if (!c->side) {
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  TRY(ensure_side(c));
+  if (c->side_pending) {   // (the side stream is in order: the sort follows the chain there; the library stream joins)
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_pdone, 0));
+    c->side_pending = false;
   }
   TRY(poll_counts(c, false));
   // capacities first, on the library stream: the sort sizes the second buffer set by them
@@ -1100,6 +1110,10 @@ int presort_fork(cylgpu_ctx* c) {
 }
 
 int presort_join(cylgpu_ctx* c, bool still_valid) {
+  if (c->side_pending) {   // the particle chain of the last push
+    CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_pdone, 0));
+    c->side_pending = false;
+  }
   if (!c->presorted) return 0;
   CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
   if (!still_valid) c->presorted = false;
@@ -1112,25 +1126,46 @@ int presort_join(cylgpu_ctx* c, bool still_valid) {
 int do_push_bcs(cylgpu_ctx* c) {
   const BcsConst B = make_bcs_const(c);
   c->stats.n_sent_left = c->stats.n_sent_right = c->stats.n_removed = c->stats.n_recv = 0;
+  // the library stream joins what the side stream holds: the particle chain of the last push and the pre-sort
+  // (a removal still pending would change the lists: the pre-sort is then void -- never in the reference's order)
+  TRY(presort_join(c, !c->pending_remove));
   if (c->xcap > 0) {
-    if (c->pending_remove) TRY(presort_join(c, false));   // (never in the reference's call order)
     TRY(flush_pending_remove(c));
     TRY(poll_counts(c, false));   // whatever count copies have arrived tighten the bounds; nobody waits
     TRY(zero_pstats(c));
   }
-  TRY(presort_join(c, true));
   TRY(push_prologue(c));
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
+  int last = -1;
+  for (int isp = 0; isp < c->cfg.n_species; ++isp) if (c->species[isp].set) last = isp;
+  // small slabs (the pre-sort policy): the particle chain of the last species runs beside current_finish
+  const bool side_chain = c->xcap > 0 && c->presort_policy == 1 && transport_two_streams(c);
+  bool published = false;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     if (!c->species[isp].set) continue;
     bool fused = false;
     TRY(push_species(c, isp, need_sort, c->timing, true, &fused));
-    TRY(pbcs_species(c, isp, B, fused));
+    if (isp == last && fused && side_chain) {
+      TRY(ensure_side(c));
+      CUDA_TRY(cudaEventRecord(c->ev_pfork, c->stream));
+      CUDA_TRY(cudaStreamWaitEvent(c->side, c->ev_pfork, 0));
+      cudaStream_t lib = c->stream;
+      c->stream = c->side;
+      int rc = pbcs_species(c, isp, B, fused);
+      if (rc == 0) rc = publish_counts(c);
+      c->stream = lib;
+      if (rc != 0) return rc;
+      CUDA_TRY(cudaEventRecord(c->ev_pdone, c->side));
+      c->side_pending = true;
+      published = true;
+    } else {
+      TRY(pbcs_species(c, isp, B, fused));
+    }
   }
   c->presorted = false;
   if (c->xcap > 0) {
     c->r_clean = true;   // particle_bcs has seen every particle at its new position
-    TRY(publish_counts(c));
+    if (!published) TRY(publish_counts(c));
   }
   if (need_sort) {
     c->sorted_valid = true;

@@ -53,6 +53,7 @@ struct Transport {
   // NCCL
   void* nccl_lib = nullptr;
   void* comm = nullptr;
+  void* comm2 = nullptr;   // a second communicator (ncclCommSplit) for exchanges enqueued on the side stream
   int (*ncclSend)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*ncclRecv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*ncclGroupStart)() = nullptr;
@@ -310,6 +311,11 @@ Transport* make_transport(cylgpu_ctx* c) {
       delete t;
       return nullptr;
     }
+    // The particle exchange of a push runs on the side stream while the field phases exchange halos on the library
+    // stream: two streams need two communicators (every rank splits: collective)
+    typedef int (*split_fn)(void*, int, int, void**, void*);
+    split_fn ncclCommSplit = (split_fn)sym("ncclCommSplit");
+    if (ncclCommSplit && ncclCommSplit(t->comm, 0, c->cfg.rank, &t->comm2, nullptr) != 0) t->comm2 = nullptr;
   } else if (t->kind == CYLGPU_TRANSPORT_CALLBACK) {
     if (!c->cfg.sendrecv) {
       set_error("CALLBACK transport needs cfg.sendrecv");
@@ -329,6 +335,7 @@ Transport* make_transport(cylgpu_ctx* c) {
 void destroy_transport(Transport* t) {
   if (!t) return;
   p2p_release(t->p2p);
+  if (t->comm2 && t->ncclCommDestroy) t->ncclCommDestroy(t->comm2);
   if (t->comm && t->ncclCommDestroy) t->ncclCommDestroy(t->comm);
   delete t;
 }
@@ -357,9 +364,11 @@ int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, siz
       // Each link on its own: peer-memory mailboxes where both ends mapped and the messages fit a slot (both ends
       // see the same sizes, so they take the same branch), ncclSend / ncclRecv otherwise.
       P2P& P = t->p2p;
+      const bool on_side = c->side && c->stream == c->side;   // (the mailboxes belong to the library stream)
+      void* comm = (on_side && t->comm2) ? t->comm2 : t->comm;
       const bool l_on = left >= 0 && (sl_b || rl_b), r_on = right >= 0 && (sr_b || rr_b);
-      const bool l_p2p = l_on && P.ready && c->p2p_link_l && sl_b <= P.cap && rl_b <= P.cap && sl_b % 8 == 0 && rl_b % 8 == 0;
-      const bool r_p2p = r_on && P.ready && c->p2p_link_r && sr_b <= P.cap && rr_b <= P.cap && sr_b % 8 == 0 && rr_b % 8 == 0;
+      const bool l_p2p = !on_side && l_on && P.ready && c->p2p_link_l && sl_b <= P.cap && rl_b <= P.cap && sl_b % 8 == 0 && rl_b % 8 == 0;
+      const bool r_p2p = !on_side && r_on && P.ready && c->p2p_link_r && sr_b <= P.cap && rr_b <= P.cap && sr_b % 8 == 0 && rr_b % 8 == 0;
       if (l_p2p || r_p2p) {
         const size_t box = P2P_FLAGS_BYTES + 2 * P.cap;
         unsigned char* my_from_l = P.mine;
@@ -388,10 +397,10 @@ int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, siz
       // order matters when left == right (2 ranks, periodic): per peer NCCL matches sends
       // and receives in issue order, and my left-going message must land in the peer's
       // "from the right" buffer
-      if (r == 0 && l_nccl && sl_b) r = t->ncclSend(sl, sl_b, 1, left, t->comm, c->stream);
-      if (r == 0 && r_nccl && sr_b) r = t->ncclSend(sr, sr_b, 1, right, t->comm, c->stream);
-      if (r == 0 && r_nccl && rr_b) r = t->ncclRecv(rr, rr_b, 1, right, t->comm, c->stream);
-      if (r == 0 && l_nccl && rl_b) r = t->ncclRecv(rl, rl_b, 1, left, t->comm, c->stream);
+      if (r == 0 && l_nccl && sl_b) r = t->ncclSend(sl, sl_b, 1, left, comm, c->stream);
+      if (r == 0 && r_nccl && sr_b) r = t->ncclSend(sr, sr_b, 1, right, comm, c->stream);
+      if (r == 0 && r_nccl && rr_b) r = t->ncclRecv(rr, rr_b, 1, right, comm, c->stream);
+      if (r == 0 && l_nccl && rl_b) r = t->ncclRecv(rl, rl_b, 1, left, comm, c->stream);
       int r2 = t->ncclGroupEnd();
       if (r == 0) r = r2;
       if (r != 0) {
@@ -430,6 +439,16 @@ int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, siz
       set_error("no transport for a multi-rank exchange");
       return 5;
   }
+}
+
+// may an exchange be enqueued on the side stream while others run on the library stream?
+bool transport_two_streams(const cylgpu_ctx* c) {
+  const Transport* t = c->tr;
+  if (!t) return false;
+  if (c->left < 0 && c->right < 0) return true;
+  if (c->left == c->cfg.rank) return true;                       // periodic wrap onto myself: device copies
+  if (t->kind == CYLGPU_TRANSPORT_NCCL) return t->comm2 != nullptr;
+  return false;   // callback / fabric transports block the host: no point
 }
 
 // a receive that timed out left a mark instead of hanging the device
