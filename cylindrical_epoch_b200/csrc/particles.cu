@@ -1138,8 +1138,12 @@ int do_push_bcs(cylgpu_ctx* c) {
   const bool need_sort = c->sort_interval > 0 && (!c->sorted_valid || c->pushes_since_sort >= c->sort_interval);
   int last = -1;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) if (c->species[isp].set) last = isp;
-  // small slabs (the pre-sort policy): the particle chain of the last species runs beside current_finish
-  const bool side_chain = c->xcap > 0 && c->presort_policy == 1 && transport_two_streams(c);
+  // Opt-in (CYLGPU_SIDE_CHAIN=1): the particle chain of the last species runs on the side stream beside
+  // current_finish / update_eb_fields_final.  Parity-tested, but measured SLOWER with neighbours (small LWFA slab on
+  // 2 GPUs: 0.89 against 0.65 ms per step): the exchanges of the two communicators wait on each other across the
+  // ranks' streams.  The pre-sort, which has no exchange in it, is what stays on by default.
+  static const bool side_chain_env = [] { const char* e = getenv("CYLGPU_SIDE_CHAIN"); return e && atoi(e) != 0; }();
+  const bool side_chain = side_chain_env && c->xcap > 0 && c->presort_policy == 1 && transport_two_streams(c);
   bool published = false;
   for (int isp = 0; isp < c->cfg.n_species; ++isp) {
     if (!c->species[isp].set) continue;
