@@ -134,6 +134,8 @@ SYMBOLS = {
     "cylgpu_insert_particles_host": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                                 C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_void_p]),
     "cylgpu_transport_info": (C.c_int, [H, C.c_void_p]),
+    "cylgpu_load_x": (C.c_int, [H, C.c_void_p]),
+    "cylgpu_calculate_breaks": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "cylgpu_driver_configure": (C.c_int, [H, C.c_void_p]),
     "cylgpu_driver_init_half_step": (C.c_int, [H]),
     "cylgpu_driver_step": (C.c_int, [H, C.c_int64]),

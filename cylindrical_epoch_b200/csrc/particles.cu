@@ -311,8 +311,12 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
 // the window deposit runs as many passes as the warp has distinct windows (normally one), so
 // nothing depends on the sort being exact.
 // ------------------------------------------------------------------------------------------
+// Strip width.  Measured in round 2 with the row-per-warp patch staging (profiles/r2f_push_strip_variants.txt,
+// push kernel ms on C3 / C2 / C4): 16 cells 21.49 / 5.11 / 24.20 (19 of 32 lanes staging), 24 cells 20.52 / 5.07 /
+// 20.98, 29 cells 20.60 / 5.23 / 20.77, 32 cells 21.22 / 5.17 / 22.38; round 1's element-wise staging at 16 cells:
+// 21.07 / 5.06 / 21.50.
 #ifndef STRIP_C
-#define STRIP_C 16
+#define STRIP_C 24
 #endif
 #define STRIP_PC (STRIP_C + 3)
 
@@ -365,18 +369,24 @@ __global__ void __launch_bounds__(128, STRIP_MINB(M)) k_push_v2(PushConst P, Soa
   if (begin >= end) return;
   const int c0 = kx0 + 1 - CELL_PAD, row0 = srow + 1 - CELL_PAD;   // cell_x2 / cell_y2 of the strip origin
   const Geom& g = P.g;
-  // stage the patch: node (c0 - 1 + col, row0 - 1 + r)
+  // stage the patch: node (c0 - 1 + col, row0 - 1 + r).  A warp takes whole patch rows (component, mode, r): the
+  // row's base address is formed once per warp, the lanes walk the columns (round 2: the element-wise index
+  // arithmetic of the first version -- two divisions, two remainders and a six-way pointer select per element --
+  // took 11 % of the kernel's stall samples on the 32-ppc workload, profiles/r2_push_c3_full_summary.txt)
   {
     const int ncol = nk + 3;
-    for (int t = threadIdx.x; t < 6 * M * CS; t += blockDim.x) {
-      const int col = t % PC;
-      int q = t / PC;
-      const int r = q % PATCH_ROWS; q /= PATCH_ROWS;
+    const int warp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    for (int row = warp; row < 6 * M * PATCH_ROWS; row += 4) {
+      const int r = row % PATCH_ROWS;
+      const int q = row / PATCH_ROWS;
       const int im = q % M, comp = q / M;
-      if (col < ncol) {
-        const size_t o = g.at(c0 - 1 + col, row0 - 1 + r, im);
-        if (im == 0) s0[(comp * PATCH_ROWS + r) * PC + col] = __ldg((const double*)(field_ptr(P, comp) + o));
-        else sm[((comp * (M - 1) + im - 1) * PATCH_ROWS + r) * PC + col] = __ldg(field_ptr(P, comp) + o);
+      const cplx* f = field_ptr(P, comp) + g.at(c0 - 1, row0 - 1 + r, im);
+      if (im == 0) {
+        double* d = s0 + (comp * PATCH_ROWS + r) * PC;
+        for (int col = ln; col < ncol; col += 32) d[col] = __ldg((const double*)(f + col));
+      } else {
+        cplx* d = sm + ((comp * (M - 1) + im - 1) * PATCH_ROWS + r) * PC;
+        for (int col = ln; col < ncol; col += 32) d[col] = __ldg(f + col);
       }
     }
   }

@@ -40,6 +40,7 @@ class SlabGrid:
     x_max: float
     y_max: float
     dt_multiplier: float = 0.95
+    bounds: list = None        # [(cell_x_min, cell_x_max)] of every rank after a re-balance; None: the even split
 
     def __post_init__(self):
         self.length_x = self.x_max - self.x_min
@@ -48,7 +49,7 @@ class SlabGrid:
         self.xb_min = self.x_min                      # cell-edge origin
         self.x_grid_min = self.x_min + self.dx / 2.0  # cell-centre origin
         self.y_grid_min_local = 0.0 + self.dy / 2.0
-        self.cell_x_min, self.cell_x_max = slab_bounds(self.nx_global, self.nranks)[self.rank]
+        self.cell_x_min, self.cell_x_max = (self.bounds or slab_bounds(self.nx_global, self.nranks))[self.rank]
         self.nx = self.cell_x_max - self.cell_x_min + 1
         self.ny = self.ny_global
         self.x_min_boundary = self.rank == 0
@@ -56,6 +57,17 @@ class SlabGrid:
         dt = 0.9 * min(self.dx, self.dy) / math.sqrt(2.0) / C_LIGHT   # setup.F90:639
         self.dt = self.dt_multiplier * dt                             # setup.F90:646
         self.setup_grid_x()
+
+    @classmethod
+    def like(cls, other, bounds, rank):
+        """the grid of `rank` for new slab bounds, every scalar of the (possibly shifted) window taken over as it is:
+        x_grid_min and the box edges are running sums of dx (window.F90:76-86), not functions of each other"""
+        g = cls(other.nx_global, other.ny_global, other.nranks, rank, other.x_min, other.x_max, other.y_max,
+                other.dt_multiplier, bounds=[tuple(b) for b in bounds])
+        for name in ("length_x", "dx", "dy", "xb_min", "x_grid_min", "y_grid_min_local", "x_min", "x_max", "dt"):
+            setattr(g, name, getattr(other, name))
+        g.setup_grid_x()
+        return g
 
     def setup_grid_x(self):   # utilities.f90:343-372 with cpml offsets = 0
         self.x_grid_min_local = self.x_grid_min + float(self.cell_x_min - 1) * self.dx

@@ -92,9 +92,18 @@ class Slab:
                  nccl_unique_id=None, sendrecv=None, move_window=False, window_v_x=0.0,
                  window_start_time=0.0, window_stop_time=1e300, bc_x_min_after_move=BC_SIMPLE_OUTFLOW,
                  bc_x_max_after_move=BC_SIMPLE_OUTFLOW, insert_fn=None, device_insert_seed=None,
-                 exchange_capacity=None, native_driver=None):
+                 exchange_capacity=None, native_driver=None, cell_bounds=None, grid_like=None):
         self.L = _lib.load()
-        self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier)
+        # what respawn() (the slab re-balancer) needs to build this slab again with other bounds
+        self._ctor = dict(nx=nx, ny=ny, n_mode=n_mode, y_max=y_max, nranks=nranks, dt_multiplier=dt_multiplier,
+                          transport=transport, device=device, move_window=move_window, window_v_x=window_v_x,
+                          window_start_time=window_start_time, window_stop_time=window_stop_time,
+                          bc_x_min_after_move=bc_x_min_after_move, bc_x_max_after_move=bc_x_max_after_move,
+                          insert_fn=insert_fn, device_insert_seed=device_insert_seed)
+        if grid_like is not None:      # a re-balanced slab: the (possibly shifted) grid of its predecessor, new bounds
+            self.grid = SlabGrid.like(grid_like, cell_bounds, rank)
+        else:
+            self.grid = SlabGrid(nx, ny, nranks, rank, x_min, x_max, y_max, dt_multiplier, bounds=cell_bounds)
         g = self.grid
         self.n_mode = n_mode
         self.raw_bc_field = list(bc_field)
@@ -483,6 +492,55 @@ class Slab:
     def set_taylor_switch(self, v):
         """test knob: |m dtheta| below which the deposit uses the small-angle series (particles.F90:593, 1.0e-4)"""
         self._ck(self.L.cylgpu_set_taylor_switch(self.h, float(v)))
+
+    # ------------------------------------------------------------------ slab re-balancer (balance.py)
+    @property
+    def periodic_x(self):
+        from .constants import BC_PERIODIC
+        return self.bc_field[BD_X_MIN] == BC_PERIODIC
+
+    def load_x(self):
+        """part_load_func (balance.F90:2453-2478) on the device: particles of all species per local column
+        1-ng .. nx+ng"""
+        a = np.zeros(self.grid.nx + 2 * NG, dtype=np.int64)
+        self._ck(self.L.cylgpu_load_x(self.h, a.ctypes.data))
+        return a
+
+    def respawn(self, bounds, **transport_kw):
+        """this rank's slab again for the slab bounds `bounds` of all ranks (balance.F90 redistribute_domain: new
+        extents, same run): same species, lasers, window and loop state, the random stream of the rank, empty arrays
+        -- balance.redistribute_* then brings the columns and particles.  transport_kw: fabric / nccl_unique_id /
+        sendrecv of the new handle (a communicator is good for one handle)."""
+        k = dict(self._ctor)
+        g = self.grid
+        s = Slab(g.nx_global, k["ny"], k["n_mode"], g.x_min, g.x_max, g.y_max, list(self.raw_bc_field), self.species,
+                 rank=g.rank, nranks=k["nranks"], dt_multiplier=k["dt_multiplier"], lasers=self.lasers,
+                 transport=k["transport"], device=k["device"], move_window=k["move_window"],
+                 window_v_x=k["window_v_x"], window_start_time=k["window_start_time"],
+                 window_stop_time=k["window_stop_time"], bc_x_min_after_move=k["bc_x_min_after_move"],
+                 bc_x_max_after_move=k["bc_x_max_after_move"], insert_fn=k["insert_fn"],
+                 device_insert_seed=k["device_insert_seed"], exchange_capacity=self.exchange_capacity,
+                 native_driver=self.native, cell_bounds=bounds, grid_like=g, **transport_kw)
+        s.window_started = self.window_started
+        s.window_shift_fraction = self.window_shift_fraction
+        s.window_shifts_total = self.window_shifts_total
+        s._time, s._step = self._time, self._step
+        sm = getattr(self, "_smoothing", None)
+        if sm is not None:
+            s.set_current_smoothing(*sm)
+        s.rng_set_state(*self.rng_get_state())
+        if s.native:
+            s._configure_driver()
+        return s
+
+    def load_state(self, st):
+        """arrays and particle lists of balance.slab_state / redistribute_*"""
+        for n in FIELD_NAMES:
+            self.upload_field(n, st["fields"][n])
+        for n in SNAP_NAMES:
+            self.upload_snapshot(n, st["snaps"][n])
+        for i, p in enumerate(st["particles"]):
+            self.upload_particles(i, p)
 
     def transport_info(self):
         """(transport kind, left link through peer-memory mailboxes, right link, mailbox slot KiB)"""

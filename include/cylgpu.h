@@ -421,6 +421,17 @@ int cylgpu_driver_init_half_step(cylgpu_handle h);          /* epoch2d.F90:143-1
 int cylgpu_driver_step(cylgpu_handle h, int64_t nsteps);    /* epoch2d.F90:189-266, nsteps times */
 int cylgpu_driver_get_state(cylgpu_handle h, cylgpu_driver_state* out);
 int cylgpu_driver_set_time(cylgpu_handle h, double time, int64_t step);
+/* ---- slab re-balancer (balance.F90 for nprocy = 1) ----
+ * cylgpu_load_x: part_load_func (balance.F90:2453-2478) from the device-resident lists: macro-particles of all
+ * species per column of this slab, load_out[ix + ng - 1] for ix = 1-ng .. nx+ng (nx + 2 ng entries).  The caller
+ * sums the slabs' columns into the global profile (the reference's MPI_ALLREDUCE), multiplies by push_per_field
+ * (5, shared_data.F90:761) and adds ny_global per interior column (get_load, balance.F90:2322-2365).
+ * cylgpu_calculate_breaks: calculate_breaks (balance.F90:2510-2653) on such a profile, load[0 .. sz + 2 ng) =
+ * load(1-ng : sz+ng); mins / maxs receive the 1-based inclusive cell range of each of the nproc slabs.  Host
+ * arithmetic, no device needed.  Moving the columns and particles to their new owners (redistribute_domain,
+ * distribute_particles) is done by the host through download / create / upload: cylindrical_epoch_b200/balance.py. */
+int cylgpu_load_x(cylgpu_handle h, int64_t* load_out);
+int cylgpu_calculate_breaks(const int64_t* load, int32_t sz, int32_t nproc, int32_t* mins, int32_t* maxs);
 /* How the neighbour exchanges of this handle travel: out4 = {transport kind (CYLGPU_TRANSPORT_*), 1 if the left
  * link goes through peer-memory mailboxes over NVLink (CUDA IPC mapping of the neighbour's buffer: one kernel on
  * each side per message, no rendezvous), the same for the right link, slot size of the mailboxes in bytes / 1024}.

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Extract the numbers bench.py quotes from an `ncu --set full` capture of the push kernel into
-profiles/push_kernel_ncu.json.  Usage: python profiles/make_push_json.py REP SUMMARY_TXT_NAME"""
+profiles/push_kernel_ncu.json.  Usage: python profiles/make_push_json.py REP SUMMARY_TXT_NAME [WORKLOAD]"""
 import csv
 import json
 import os
@@ -8,6 +8,7 @@ import subprocess
 import sys
 
 rep, src = sys.argv[1], sys.argv[2]
+workload = sys.argv[3] if len(sys.argv) > 3 else "thermal_2048x256_m2_ppc64"
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 d = dict(zip(rows[0], zip(rows[1], rows[2])))
@@ -20,7 +21,7 @@ def val(k):
 
 
 j = {
-    "workload": "thermal_2048x256_m2_ppc64",
+    "workload": workload,
     "kernel": "k_push_v2<2,true> (strip CTAs + DMMA deposit + fused particle_bcs)",
     "source": f"profiles/{src} (ncu --set full --clock-control none, one launch)",
     "dram_bytes_read": val("dram__bytes_read.sum"),

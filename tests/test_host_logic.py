@@ -238,3 +238,50 @@ def test_host_mirror_device_insertion_uses_the_shift_counter_as_column():
     for isp, (_, args) in enumerate(ins):
         assert args[1] == isp and args[9] == 99 and args[10] == 7      # seed, column = shifts made so far
     assert s.L.calls[-1][0] == "cylgpu_window_shift" and s.window_shifts_total == 8
+
+
+def test_calculate_breaks_matches_the_literal_restatement(cylgpu_lib):
+    """cylgpu_calculate_breaks (csrc/balance.cu) against oracle/balance_ref.py, the literal restatement of
+    balance.F90:2510-2653, on uniform, ramped, lopsided and random load profiles; plus the properties the reference
+    relies on: contiguous cover of 1..sz, at least ncell_min cells per slab, and a spread of the slab loads that is no
+    worse than the equal-width split's on the lopsided profiles."""
+    import ctypes as C
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import balance_ref as br
+    L = cylgpu_lib
+    rng = np.random.default_rng(11)
+
+    def product(load, nproc):
+        a = np.ascontiguousarray(load, dtype=np.int64)
+        mins = (C.c_int32 * nproc)()
+        maxs = (C.c_int32 * nproc)()
+        assert L.cylgpu_calculate_breaks(a.ctypes.data, len(load) - 2 * br.NG, nproc, mins, maxs) == 0
+        return list(mins), list(maxs)
+
+    cases = []
+    for sz in (40, 97, 256):
+        x = np.arange(sz + 2 * br.NG)
+        cases += [np.full(sz + 2 * br.NG, 7), 3 + x, 1 + (x > sz // 4) * 50, 1 + 400 * (np.abs(x - sz * 0.7) < 4),
+                  rng.integers(0, 1000, sz + 2 * br.NG), 5 * rng.poisson(3.0, sz + 2 * br.NG) + 12]
+    for load in cases:
+        sz = len(load) - 2 * br.NG
+        for nproc in (1, 2, 3, 8):
+            if nproc * br.NCELL_MIN > sz:
+                continue
+            got = product(load, nproc)
+            ref = br.calculate_breaks(list(load), nproc)
+            assert got == (ref[0], ref[1]), (sz, nproc, got, ref)
+            mins, maxs = got
+            assert mins[0] == 1 and maxs[-1] == sz
+            assert all(mins[p] == maxs[p - 1] + 1 for p in range(1, nproc))
+            assert all(maxs[p] - mins[p] + 1 >= br.NCELL_MIN for p in range(nproc))
+    # a plasma slab in the left fifth of the box: the equal split leaves most slabs empty, the breaks do not
+    sz, nproc = 200, 4
+    load = np.full(sz + 2 * br.NG, 50, dtype=np.int64)
+    load[br.NG:br.NG + 40] += 5 * 3000
+    mins, maxs = product(load, nproc)
+    per = [int(load[br.NG + mins[p] - 1: br.NG + maxs[p]].sum()) for p in range(nproc)]
+    equal = [int(load[br.NG + p * 50: br.NG + (p + 1) * 50].sum()) for p in range(nproc)]
+    assert max(per) < 0.5 * max(equal)
