@@ -60,21 +60,7 @@ extern "C" {
 const char* cylgpu_last_error(void) { return g_err; }
 int cylgpu_version(void) { return 100; }
 
-int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
-  if (!cfg || !out) { set_error("null argument"); return 1; }
-  *out = nullptr;
-  if (cfg->nx < 2 * NG || cfg->ny < 2 * NG) { set_error("nx and ny must be >= %d", 2 * NG); return 2; }
-  if (cfg->n_mode < 1 || cfg->n_mode > 16) { set_error("n_mode out of range"); return 2; }
-  if (cfg->n_species < 0 || cfg->n_species > CYLGPU_MAX_SPECIES) { set_error("n_species out of range"); return 2; }
-  if (cfg->rank < 0 || cfg->rank >= cfg->nranks) { set_error("bad rank/nranks"); return 2; }
-  int ndev = 0;
-  cudaError_t e = cudaGetDeviceCount(&ndev);
-  if (e != cudaSuccess || ndev == 0) {
-    set_error("no CUDA device available (%s); this library has no CPU fallback",
-              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
-    return 10;
-  }
-  cylgpu_ctx* c = new cylgpu_ctx();
+static int create_impl(const cylgpu_config* cfg, cylgpu_ctx* c) {
   c->cfg = *cfg;
   if (cfg->device >= 0) c->device = cfg->device;
   else CUDA_TRY(cudaGetDevice(&c->device));
@@ -128,6 +114,35 @@ int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
   if (const char* e = getenv("CYLGPU_BLOCKING_WAIT")) c->blocking_wait = atoi(e) != 0;
   if (const char* e = getenv("CYLGPU_GRAPHS")) c->use_graphs = atoi(e) != 0;
   CUDA_TRY(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+
+int cylgpu_destroy(cylgpu_handle c);
+
+int cylgpu_create(const cylgpu_config* cfg, cylgpu_handle* out) {
+  if (!cfg || !out) { set_error("null argument"); return 1; }
+  *out = nullptr;
+  if (cfg->nx < 2 * NG || cfg->ny < 2 * NG) { set_error("nx and ny must be >= %d", 2 * NG); return 2; }
+  if (cfg->n_mode < 1 || cfg->n_mode > 6) { set_error("n_mode must be 1..6 (the push kernels are instantiated for these)"); return 2; }
+  if (cfg->n_species < 0 || cfg->n_species > CYLGPU_MAX_SPECIES) { set_error("n_species out of range"); return 2; }
+  if (cfg->rank < 0 || cfg->rank >= cfg->nranks) { set_error("bad rank/nranks"); return 2; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return 10;
+  }
+  cylgpu_ctx* c = new cylgpu_ctx();
+  const int rc = create_impl(cfg, c);
+  if (rc != 0) {   // nothing of a half-built handle survives (device allocations, streams, communicator)
+    char msg[1024];
+    snprintf(msg, sizeof(msg), "%s", cylgpu_last_error());
+    cylgpu_destroy(c);
+    set_error("%s", msg);
+    return rc;
+  }
   *out = c;
   return 0;
 }

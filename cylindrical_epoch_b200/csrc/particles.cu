@@ -278,7 +278,11 @@ __global__ void __launch_bounds__(128, PUSH_MINB) k_push_v1(PushConst P, double*
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool valid = i < n;
-  DepositIn D;
+  // idle lanes of the tail warp take part in the window deposit (shuffles): their D must be finite -- zero weights,
+  // zero angle -- or 0 * Inf from an uninitialised register would reach the warp totals
+  DepositIn D = {};
+  D.exp_itheta_05 = C(1.0, 0.0);
+  D.exp_idtheta = C(1.0, 0.0);
   D.cell_x2 = 0x3fffffff; D.cell_y2 = 0x3fffffff;
   if (valid) {
     double X = x[i], Y = y[i], Z = z[i], PX = px[i], PY = py[i], PZ = pz[i];
