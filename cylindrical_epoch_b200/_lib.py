@@ -158,7 +158,7 @@ class DriverConfig(C.Structure):    # cylgpu_driver_config
     _fields_ = [("cell_x_min", C.c_int32), ("move_window", C.c_int32), ("raw_bc_field", C.c_int32 * 4),
                 ("bc_x_min_after_move", C.c_int32), ("bc_x_max_after_move", C.c_int32), ("n_lasers", C.c_int32),
                 ("insert_mode", C.c_int32), ("insert_seed", C.c_uint64), ("x_grid_min", C.c_double),
-                ("window_v_x", C.c_double), ("window_start_time", C.c_double), ("window_stop_time", C.c_double),
+                ("xb_min", C.c_double), ("window_v_x", C.c_double), ("window_start_time", C.c_double), ("window_stop_time", C.c_double),
                 ("lasers", C.POINTER(LaserC)), ("insert", InsertProfileC * MAX_SPECIES),
                 ("time", C.c_double), ("window_shift_fraction", C.c_double), ("step", C.c_int64),
                 ("window_shifts_total", C.c_int64), ("window_started", C.c_int32), ("pad_", C.c_int32)]
@@ -169,7 +169,7 @@ class DriverState(C.Structure):     # cylgpu_driver_state
                 ("window_shift_fraction", C.c_double), ("window_shifts_total", C.c_int64),
                 ("x_grid_min", C.c_double), ("x_min", C.c_double), ("x_max", C.c_double),
                 ("x_grid_min_local", C.c_double), ("x_min_local", C.c_double), ("x_max_local", C.c_double),
-                ("bc_field", C.c_int32 * 4)]
+                ("bc_field", C.c_int32 * 4), ("raw_bc_field", C.c_int32 * 4)]
 
 
 _LIB = None

@@ -250,7 +250,7 @@ def redistribute_dist(state, old_bounds, new_bounds, nx_global, x_edges, rank, p
 
 
 # ------------------------------------------------------------------------------------------------ handles
-def rebalance_slabs(slabs, transport_kw=lambda k: {}, over_ride=False, dlb_threshold=DLB_THRESHOLD):
+def rebalance_slabs(slabs, transport_kw=lambda k: {}, over_ride=False, dlb_threshold=DLB_THRESHOLD, force_bounds=None):
     """balance_workload for slabs held in ONE process (tests, single-process drivers).  transport_kw(rank): the
     transport arguments of the new handle of `rank` (e.g. the in-process fabric); returns (slabs, report)."""
     lib = slabs[0].L
@@ -258,6 +258,8 @@ def rebalance_slabs(slabs, transport_kw=lambda k: {}, over_ride=False, dlb_thres
     bounds = [(s.grid.cell_x_min, s.grid.cell_x_max) for s in slabs]
     counts = [s.load_x() for s in slabs]
     new_bounds, frac, frac_final = plan(lib, counts, bounds, g0.nx_global, g0.ny_global, over_ride, dlb_threshold)
+    if force_bounds is not None:     # (tests: a prescribed split, e.g. the present one = a pure hand-over of the state)
+        new_bounds = [tuple(b) for b in force_bounds]
     report = dict(balance=frac, after=frac_final, redistributed=new_bounds is not None, bounds=new_bounds or bounds)
     if new_bounds is None:
         return slabs, report

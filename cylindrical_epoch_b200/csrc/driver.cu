@@ -176,7 +176,7 @@ int cylgpu_driver_configure(cylgpu_handle c, const cylgpu_driver_config* cfg) {
   D->cell_x_min = cfg->cell_x_min;
   D->cell_x_max = cfg->cell_x_min + c->cfg.nx - 1;
   D->x_grid_min = cfg->x_grid_min;
-  D->xb_min = cfg->x_grid_min - 0.5 * c->cfg.dx;
+  D->xb_min = cfg->xb_min;
   D->x_min = c->x_min; D->x_max = c->x_max;
   setup_grid_x(*D);
   for (int i = 0; i < 4; ++i) D->raw_bc_field[i] = cfg->raw_bc_field[i];
@@ -233,7 +233,7 @@ int cylgpu_driver_get_state(cylgpu_handle c, cylgpu_driver_state* out) {
   out->window_shifts_total = D->window_shifts_total;
   out->x_grid_min = D->x_grid_min; out->x_min = D->x_min; out->x_max = D->x_max;
   out->x_grid_min_local = D->x_grid_min_local; out->x_min_local = D->x_min_local; out->x_max_local = D->x_max_local;
-  for (int i = 0; i < 4; ++i) out->bc_field[i] = D->bc_field[i];
+  for (int i = 0; i < 4; ++i) { out->bc_field[i] = D->bc_field[i]; out->raw_bc_field[i] = D->raw_bc_field[i]; }
   return 0;
 }
 

@@ -183,6 +183,7 @@ class Slab:
         cfg.insert_mode = 0 if self.device_insert_seed is None else 1
         cfg.insert_seed = 0 if self.device_insert_seed is None else int(self.device_insert_seed)
         cfg.x_grid_min = g.x_grid_min
+        cfg.xb_min = g.xb_min
         cfg.window_v_x, cfg.window_start_time = self.window_v_x, self.window_start_time
         cfg.window_stop_time = self.window_stop_time
         arr = (_lib.LaserC * max(len(self.lasers), 1))()
@@ -213,6 +214,8 @@ class Slab:
             g.shift()
         self.window_shifts_total = int(st.window_shifts_total)
         self.bc_field = list(st.bc_field)
+        self.raw_bc_field = list(st.raw_bc_field)
+        self.add_laser = normalise_bc_field(self.raw_bc_field)[1]
 
     @property
     def time(self):

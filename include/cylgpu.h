@@ -399,6 +399,8 @@ typedef struct cylgpu_driver_config {
   int32_t insert_mode;             /* 0: cylgpu_insert_particles (the rank's KISS stream), 1: _device (Philox) */
   uint64_t insert_seed;
   double x_grid_min;               /* global x(1) = x_min + dx / 2 */
+  double xb_min;                   /* global cell-edge origin: window.F90 advances it beside x_grid_min, so a run taken
+                                      over mid-way hands both (a fresh run: x_min) */
   double window_v_x, window_start_time, window_stop_time;
   const cylgpu_laser* lasers;
   cylgpu_insert_profile insert[CYLGPU_MAX_SPECIES];
@@ -415,6 +417,7 @@ typedef struct cylgpu_driver_state {
   int64_t window_shifts_total;
   double x_grid_min, x_min, x_max, x_grid_min_local, x_min_local, x_max_local;
   int32_t bc_field[4];
+  int32_t raw_bc_field[4];         /* the deck's values, bc_x_*_after_move once the window started (window.F90:342-350) */
 } cylgpu_driver_state;
 int cylgpu_driver_configure(cylgpu_handle h, const cylgpu_driver_config* cfg);
 int cylgpu_driver_init_half_step(cylgpu_handle h);          /* epoch2d.F90:143-161 */

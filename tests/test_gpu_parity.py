@@ -204,6 +204,28 @@ def test_push_only_currents():
         p.close()
 
 
+@pytest.mark.parametrize("n_mode", [2, 3])
+def test_unsorted_warp_window_push_with_a_partial_tail_warp(n_mode):
+    """push variant 1 without the sort (sort_interval = 0: the path k_push_v1 takes then) on a list whose length
+    is not a multiple of 32: the idle lanes of the tail warp take part in the window deposit's shuffles and must
+    contribute exact zeros (their deposit inputs were uninitialised registers)"""
+    d = decks.thermal(nx=40, ny=20, n_mode=n_mode, ppc=5, temp_k=3e8)
+    p = Pair(d, variant=1, sort_interval=0)
+    try:
+        n = p.slabs[0].particle_count(0)
+        if n % 32 == 0:      # make the tail warp partial
+            a = p.slabs[0].download_particles(0)[:-3]
+            p.slabs[0].upload_particles(0, a)
+            p.oracle.set_particles(0, 0, np.ascontiguousarray(a))
+        assert p.slabs[0].particle_count(0) % 32 != 0
+        p.step(6)
+        errs = p.check_fields(TOL_HOT)
+        assert all(np.isfinite(v) for v in errs.values())
+        p.check_particles(TOL_HOT)
+    finally:
+        p.close()
+
+
 def test_sort_is_a_permutation():
     d = decks.thermal(nx=48, ny=24, n_mode=2, ppc=5)
     p = Pair(d, init_half_step=False)

@@ -36,7 +36,11 @@ def _compare_global(p, tol):
             den = max(den, J_FLOOR * qnc)
         if den > 0:
             worst = max(worst, np.abs(got - ref).max() / den)
-        assert np.abs(got - ref).max() <= tol * den, (name, np.abs(got - ref).max() / max(den, 1e-300))
+        if not np.abs(got - ref).max() <= tol * den:
+            where = np.unravel_index(np.abs(got - ref).argmax(), ref.shape)
+            bad_cols = np.unique(np.nonzero(np.abs(got - ref) > tol * den)[2])
+            raise AssertionError((name, np.abs(got - ref).max() / max(den, 1e-300), "worst at (mode, row, col)", where,
+                                  "columns off", bad_cols.tolist(), "oracle bounds", ob, "slab bounds", sb))
     for isp in range(len(p.deck.species)):
         ref = np.concatenate([p.oracle.particles(k, isp).reshape(-1, 7) for k in range(p.nranks)])
         got = np.concatenate([s.download_particles(isp) for s in p.slabs])
@@ -77,5 +81,26 @@ def test_rebalance_mid_run(deckname, nranks):
             assert p.slabs[-1].rng_get_state() == p.oracle.rng_state(nranks - 1)
         print(deckname, "bounds", even, "->", new, "balance %.3f -> %.3f" % (report["balance"], report["after"]),
               "worst field error after 8 more steps %.2e" % worst)
+    finally:
+        p.close()
+
+
+@pytest.mark.parametrize("bounds", [[(1, 32), (33, 64)], [(1, 20), (21, 64)], [(1, 12), (13, 64)], [(1, 10), (11, 64)]])
+def test_window_deck_prescribed_splits(bounds):
+    """the moving-window deck handed over to new handles with a prescribed split (the first = the split it has: a
+    pure hand-over of the state), then 8 more steps"""
+    d = decks.lwfa(nx=64, ny=16, n_mode=2, ppc_e=4, ppc_p=1, window=True, t_centre=30e-15)
+    p = Pair(d, nranks=2, prepare=lambda o: _lopsided(o, 2, 0.3, d.x_max))
+    try:
+        p.step(6)
+        p.slabs, report = balance.rebalance_slabs(p.slabs, transport_kw=lambda k: dict(fabric=p.fabric), over_ride=True,
+                                                  force_bounds=bounds)
+        _compare_global(p, 1e-9)
+        for k in range(8):
+            p.step(1)
+            try:
+                _compare_global(p, 1e-9)
+            except AssertionError as e:
+                raise AssertionError(("step after hand-over", k + 1, str(e)[:600]))
     finally:
         p.close()
