@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SOURCES = ["api.cu", "fields.cu", "bcs.cu", "particles.cu", "transport.cu", "window_insert.cu", "sdf_io.cu", "driver.cu", "balance.cu"]
 HEADERS = ["ctx.cuh", "push.cuh", "deposit_mma.cuh", "moments.cuh", "philox.cuh", "geom.cuh", "bc_kernels.cuh", "moments_kernels.cuh",
-           "insert_kernel.cuh", "push_v0.cuh", "pbcs_kernels.cuh", "field_kernels.cuh", "compact_kernels.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
+           "insert_kernel.cuh", "push_v0.cuh", "pbcs_kernels.cuh", "field_kernels.cuh", "compact_kernels.cuh", "field_ranges.cuh", os.path.join("..", "..", "include", "cylgpu.h")]
 LIB = os.path.join(HERE, "libcylgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -152,7 +152,7 @@ int cylgpu_destroy(cylgpu_handle c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   // the captured field phases hold NCCL send/recv nodes: they go before the communicator
-  for (int k = 0; k < 3; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
+  for (int k = 0; k < 4; ++k) if (c->graphs[k].exec) { cudaGraphExecDestroy(c->graphs[k].exec); c->graphs[k].exec = nullptr; }
   destroy_transport(c->tr);
   if (c->driver) { cylgpu_driver_release(c->driver); c->driver = nullptr; }
   for (int k = 0; k < CYLGPU_NFIELDS; ++k) cudaFree(c->f[k]);
@@ -529,6 +529,13 @@ static int run_field_phase(cylgpu_ctx* c, int which, const std::function<int()>&
 }
 
 static int fields_half_body(cylgpu_ctx* c) {
+  if (wide_fields(c)) {   // field_ranges.cuh: ghost columns advanced here, ONE closing exchange for E and B
+    const FieldRanges R = wide_ranges(c, 0);
+    TRY(launch_update_e(c, R.e_lo, R.e_hi));
+    TRY(efield_edges(c));
+    TRY(launch_update_b(c, true, R.b_lo, R.b_hi));
+    return halo_eb(c);
+  }
   TRY(launch_update_e(c));
   TRY(do_efield_bcs(c));
   // bxm_old = bxm etc. (fields.f90:326-328) ride on the B sweep
@@ -594,7 +601,19 @@ int cylgpu_fields_final(cylgpu_handle c, const double* s1min, const double* s2mi
   TRY(check_handle_fields(c));
   PhaseTimer t(c, &c->stats.ms_fields);
   TRY(upload_laser_sources(c, s1min, s2min, s1max, s2max));
-  return run_field_phase(c, 1, [c]() -> int {
+  // final_shift_follows (driver.cu): shift_fields comes next and ends with its own exchange of all nine arrays;
+  // this phase then advances column nx+1 -- the one the shift moves into the interior -- itself and leaves the
+  // ghosts to the window's halo: no exchange here at all
+  const bool to_shift = c->final_shift_follows && wide_fields(c);
+  return run_field_phase(c, to_shift ? 3 : 1, [c, to_shift]() -> int {
+    if (wide_fields(c)) {
+      const FieldRanges R = wide_ranges(c, to_shift ? 2 : 1);
+      TRY(launch_update_b(c, false, R.b_lo, R.b_hi));
+      TRY(do_bfield_final_bcs_device(c, true, to_shift ? 2 : 1));
+      TRY(launch_update_e(c, R.e_lo, R.e_hi));
+      TRY(efield_edges(c));
+      return to_shift ? 0 : halo_eb(c);
+    }
     TRY(launch_update_b(c));
     TRY(do_bfield_final_bcs_device(c));
     TRY(launch_update_e(c));

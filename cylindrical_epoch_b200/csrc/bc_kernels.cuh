@@ -351,11 +351,14 @@ __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cpl
 
 // laser.f90:637-690.  REFERENCE QUIRK reproduced: icdt_2r is declared REAL(num) but assigned
 // a purely imaginary value, so it is 0 and the azimuthal coupling terms vanish.
-__global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int ix_l, int ix_h, double dx,
-                                                       double dy, double dt, double y_grid_min_local) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
+// Columns: Bx on ix_l..ix_h, Btheta on it_l..it_h (the reference: 0..nx without the domain-boundary column,
+// and 1..nx; wider with field_ranges.cuh); the grid starts at column ix0.
+__global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int ix_l, int ix_h, int it_l, int it_h,
+                                                       int ix0, double dx, double dy, double dt,
+                                                       double y_grid_min_local) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + ix0;
   const int im = blockIdx.y;
-  if (ix > g.nx) return;
+  if (ix > ix_h && ix > it_h) return;
   const int ny = g.ny;
   const double c = C_LIGHT;
   const double dtc2 = dt * (c * c);
@@ -375,7 +378,7 @@ __global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int i
                  - (icdt_2r * (double)im) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)])
                  - dt_2eps * (F.jtm[g.at(ix, ny - 1, im)] + F.jto[g.at(ix, ny - 1, im)]));
   }
-  if (ix >= 1) {
+  if (ix >= it_l && ix <= it_h) {
     F.btm[g.at(ix, ny, im)] =
         sum_t * ((-F.btm[g.at(ix, ny - 1, im)]) * (c - ly + dtc2_4r) - F.bto[g.at(ix, ny, im)] * (-c + ly + dtc2_4r)
                  - F.bto[g.at(ix, ny - 1, im)] * (-c - ly + dtc2_4r)

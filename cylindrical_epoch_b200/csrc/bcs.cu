@@ -117,19 +117,83 @@ static int edge_bcs(cylgpu_ctx* c, int base, const int cond_x[3], const int cond
   return 0;
 }
 
-int do_efield_bcs(cylgpu_ctx* c) {
-  TRY(halo_x(c, CYLGPU_EXM, CYLGPU_ERM, CYLGPU_ETM, 1, 0, 1));
+// the ghost fills of efield_bcs / bfield_bcs on the domain boundaries, without the halo
+int efield_edges(cylgpu_ctx* c) {
   const int cx[3] = {OP_CLAMP, OP_ZEROGRAD, OP_ZEROGRAD};
   const int cy[3] = {OP_ZEROGRAD, OP_CLAMP, OP_ZEROGRAD};
   return edge_bcs(c, CYLGPU_EXM, cx, cy);
+}
+int bfield_edges(cylgpu_ctx* c) {
+  const int cx[3] = {OP_ZEROGRAD, OP_CLAMP, OP_CLAMP};
+  const int cy[3] = {OP_CLAMP, OP_ZEROGRAD, OP_CLAMP};
+  return edge_bcs(c, CYLGPU_BXM, cx, cy);
+}
+
+int do_efield_bcs(cylgpu_ctx* c) {
+  TRY(halo_x(c, CYLGPU_EXM, CYLGPU_ERM, CYLGPU_ETM, 1, 0, 1));
+  return efield_edges(c);
 }
 
 int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only) {
   TRY(halo_x(c, CYLGPU_BXM, CYLGPU_BRM, CYLGPU_BTM, 0, 1, 0));
   if (mpi_only) return 0;
-  const int cx[3] = {OP_ZEROGRAD, OP_CLAMP, OP_CLAMP};
-  const int cy[3] = {OP_CLAMP, OP_ZEROGRAD, OP_CLAMP};
-  return edge_bcs(c, CYLGPU_BXM, cx, cy);
+  return bfield_edges(c);
+}
+
+// which sides the field halo fills (boundary.F90:531,544)
+void halo_sides(const cylgpu_ctx* c, bool* fill_l, bool* fill_r) {
+  const bool has_l = c->left >= 0, has_r = c->right >= 0;
+  *fill_r = has_r && (!c->cfg.x_max_boundary || c->bc_field[CYLGPU_BD_X_MAX] == CYLGPU_BC_PERIODIC);
+  *fill_l = has_l && (!c->cfg.x_min_boundary || c->bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC);
+}
+
+// The communication-avoiding field phases (field_ranges.cuh) apply when a real neighbour fills the ghosts (a
+// periodic wrap onto the slab itself is a local copy: nothing to save), the slab is at least two halos wide,
+// and the currents are not smoothed (current_smooth.F90 leaves the ghosts of J unsmoothed, so a ghost column
+// could not be advanced the way its owner advances it).  CYLGPU_WIDE_FIELDS=0 keeps the reference's exchanges.
+bool wide_fields(const cylgpu_ctx* c) {
+  static const bool env_on = [] { const char* e = getenv("CYLGPU_WIDE_FIELDS"); return !e || atoi(e) != 0; }();
+  if (!env_on || c->smooth_currents || c->g.nx < 2 * NG) return false;
+  bool fill_l, fill_r;
+  halo_sides(c, &fill_l, &fill_r);
+  if (!fill_l && !fill_r) return false;
+  if (c->left == c->cfg.rank || c->right == c->cfg.rank) return false;
+  return true;
+}
+
+FieldRanges wide_ranges(const cylgpu_ctx* c, int phase) {
+  bool fill_l, fill_r;
+  halo_sides(c, &fill_l, &fill_r);
+  return field_ranges(phase, wide_fields(c), fill_l, fill_r, c->cfg.x_min_boundary != 0, c->cfg.x_max_boundary != 0,
+                      c->g.nx);
+}
+
+// field_mode_bc on the six field arrays at once: the closing exchange of a wide field phase, one message per
+// neighbour (the E block, then the B block; row skips as in efield_bcs / bfield_bcs)
+int halo_eb(cylgpu_ctx* c) {
+  const Geom& g = c->g;
+  bool fill_l, fill_r;
+  halo_sides(c, &fill_l, &fill_r);
+  if (!fill_l && !fill_r) return 0;
+  const size_t he = c->halo_elems;
+  const dim3 grd((g.SY * NG + 127) / 128, g.M, 3);
+  Halo3 h[2];
+  for (int k = 0; k < 3; ++k) { h[0].f[k] = c->f[CYLGPU_EXM + k]; h[1].f[k] = c->f[CYLGPU_BXM + k]; }
+  h[0].skip[0] = 1; h[0].skip[1] = 0; h[0].skip[2] = 1;
+  h[1].skip[0] = 0; h[1].skip[1] = 1; h[1].skip[2] = 0;
+  for (int q = 0; q < 2; ++q)
+    k_halo_pack<<<grd, 128, 0, c->stream>>>(g, h[q], fill_l ? c->sbuf_l + q * he : nullptr,
+                                            fill_r ? c->sbuf_r + q * he : nullptr, 0, he);
+  const size_t bytes = 2 * he * sizeof(cplx);
+  TRY(transport_sendrecv(c, fill_l ? c->sbuf_l : nullptr, fill_l ? bytes : 0, fill_l ? c->rbuf_l : nullptr,
+                         fill_l ? bytes : 0, fill_r ? c->sbuf_r : nullptr, fill_r ? bytes : 0,
+                         fill_r ? c->rbuf_r : nullptr, fill_r ? bytes : 0));
+  for (int q = 0; q < 2; ++q)
+    k_halo_unpack<<<grd, 128, 0, c->stream>>>(g, h[q], fill_l ? c->rbuf_l + q * he : nullptr,
+                                              fill_r ? c->rbuf_r + q * he : nullptr, 0, he);
+  c->stats.kernel_launches += 4;
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 static FieldSet fieldset(cylgpu_ctx* c) {
@@ -172,9 +236,12 @@ int upload_laser_sources(cylgpu_ctx* c, const double* s1min, const double* s2min
 }
 
 // bfield_final_bcs, boundary.F90:1505-1537, with the sources already in c->src
-int do_bfield_final_bcs_device(cylgpu_ctx* c) {
+// wide: inside a communication-avoiding final phase -- no halo before or after, the r_max line update also on
+// the ghost columns field_ranges.cuh allows
+int do_bfield_final_bcs_device(cylgpu_ctx* c, bool wide, int phase) {
   const Geom& g = c->g;
-  TRY(do_bfield_bcs(c, false));
+  if (wide) TRY(bfield_edges(c));
+  else TRY(do_bfield_bcs(c, false));
   FieldSet F = fieldset(c);
   const int nsrc = g.ny + 1;
   dim3 grd((g.ny + 1 + 127) / 128, g.M);
@@ -197,23 +264,26 @@ int do_bfield_final_bcs_device(cylgpu_ctx* c) {
     }
   }
   if (c->bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
-    const int ix_l = c->cfg.x_min_boundary ? 1 : 0;
-    const int ix_h = c->cfg.x_max_boundary ? g.nx - 1 : g.nx;
-    k_outflow_r_max<<<dim3((g.nx + 1 + 127) / 128, g.M), 128, 0, c->stream>>>(
-        g, F, ix_l, ix_h, c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
+    FieldRanges R = wide_ranges(c, phase);
+    if (!wide) R = field_ranges(1, false, false, false, c->cfg.x_min_boundary != 0, c->cfg.x_max_boundary != 0, g.nx);
+    const int ix0 = R.obx_lo < R.obt_lo ? R.obx_lo : R.obt_lo;
+    const int ix1 = R.obx_hi > R.obt_hi ? R.obx_hi : R.obt_hi;
+    k_outflow_r_max<<<dim3((ix1 - ix0 + 1 + 127) / 128, g.M), 128, 0, c->stream>>>(
+        g, F, R.obx_lo, R.obx_hi, R.obt_lo, R.obt_hi, ix0, c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
     c->stats.kernel_launches += 1;
   } else if (c->bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
     k_zero_b_rmax<<<dim3((g.SX + 127) / 128, g.M), 128, 0, c->stream>>>(g, F.bxm, F.brm, F.btm);
     c->stats.kernel_launches += 1;
   }
   CUDA_TRY(cudaGetLastError());
+  if (wide) return 0;
   return do_bfield_bcs(c, true);
 }
 
 int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
                         const double* s2max) {
   TRY(upload_laser_sources(c, s1min, s2min, s1max, s2max));
-  return do_bfield_final_bcs_device(c);
+  return do_bfield_final_bcs_device(c, false);
 }
 
 int do_r_min_final(cylgpu_ctx* c) {

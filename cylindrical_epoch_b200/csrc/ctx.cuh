@@ -10,6 +10,7 @@
 #include "../../include/cylgpu.h"
 
 #include "geom.cuh"
+#include "field_ranges.cuh"
 
 namespace cylgpu {
 
@@ -199,13 +200,16 @@ struct cylgpu_ctx {
     int64_t launches = 0;         // kernel launches inside (for the statistics)
     bool failed = false;
   };
-  PhaseGraph graphs[3];          // fields_half, fields_final, current_finish
+  PhaseGraph graphs[4];          // fields_half, fields_final, current_finish, fields_final before a window shift
+  bool final_shift_follows = false;   // driver.cu: the window moves right after this update_eb_fields_final
   uint64_t graph_epoch = 0;
   bool use_graphs = true;
 
   void* driver = nullptr;         // driver.cu: the main-loop body run natively (cylgpu_driver_*)
   cylgpu::Transport* tr = nullptr;
   size_t p2p_cap_bytes = 0;
+  int p2p_policy = 0;            // CYLGPU_P2P: 0 NCCL only, 1 every message that fits a slot, 2 ("particles") the counted ones
+  bool msg_counted = false;      // the message being exchanged is [7-double header: count][slots] (particles)
   bool p2p_link_l = false, p2p_link_r = false;   // peer-memory mailboxes mapped on both ends of the link (transport.cu)
   cylgpu::HostStream hs;
   cylgpu::KissState rng;          // this rank's random stream (window insertion)
@@ -242,6 +246,8 @@ namespace cylgpu {
 // fields.cu
 int launch_update_e(cylgpu_ctx* c);
 int launch_update_b(cylgpu_ctx* c, bool save_old = false);
+int launch_update_e(cylgpu_ctx* c, int ix_lo, int ix_hi);
+int launch_update_b(cylgpu_ctx* c, bool save_old, int ix_lo, int ix_hi);
 // bcs.cu
 int do_efield_bcs(cylgpu_ctx* c);
 int do_bfield_bcs(cylgpu_ctx* c, bool mpi_only);
@@ -249,7 +255,12 @@ int do_bfield_final_bcs(cylgpu_ctx* c, const double* s1min, const double* s2min,
                         const double* s2max);
 int upload_laser_sources(cylgpu_ctx* c, const double* s1min, const double* s2min, const double* s1max,
                          const double* s2max);
-int do_bfield_final_bcs_device(cylgpu_ctx* c);
+int do_bfield_final_bcs_device(cylgpu_ctx* c, bool wide = false, int phase = 1);
+int efield_edges(cylgpu_ctx* c);
+int bfield_edges(cylgpu_ctx* c);
+int halo_eb(cylgpu_ctx* c);
+bool wide_fields(const cylgpu_ctx* c);
+FieldRanges wide_ranges(const cylgpu_ctx* c, int phase);
 int do_current_bcs(cylgpu_ctx* c);
 int do_current_finish(cylgpu_ctx* c);
 int do_number_density_modes(cylgpu_ctx* c, int species, bool charge);

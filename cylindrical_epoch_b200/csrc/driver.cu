@@ -130,6 +130,15 @@ static int shift_window_once(cylgpu_ctx* c, Driver& D) {
   return 0;
 }
 
+// what moving_window is about to decide, with its own arithmetic: the window is already moving and this step
+// completes at least one cell.  (The step that STARTS the window changes bc_field first: not predicted.)
+static bool window_will_shift(const Driver& D) {
+  if (!D.cfg.move_window || !D.window_started) return false;
+  if (D.time >= D.cfg.window_stop_time || D.cfg.window_v_x <= 0.0) return false;
+  const double frac = D.window_shift_fraction + D.dt * D.cfg.window_v_x / D.dx;
+  return (int)std::floor(frac) > 0;
+}
+
 // moving_window, window.F90:330-376
 static int moving_window(cylgpu_ctx* c, Driver& D) {
   if (!D.cfg.move_window) return 0;
@@ -218,7 +227,10 @@ int cylgpu_driver_step(cylgpu_handle c, int64_t nsteps) {
     TRY(cylgpu_rng_flush_cache(c));                     // output_routines -> random_flush_cache, diagnostics.F90:235
     D->time = D->time + D->dt / 2.0;
     all_sources(c, *D);
-    TRY(cylgpu_fields_final(c, D->src[0].data(), D->src[1].data(), D->src[2].data(), D->src[3].data()));   // :263
+    c->final_shift_follows = window_will_shift(*D);
+    const int rc_final = cylgpu_fields_final(c, D->src[0].data(), D->src[1].data(), D->src[2].data(), D->src[3].data());   // :263
+    c->final_shift_follows = false;
+    TRY(rc_final);
     TRY(moving_window(c, *D));                          // :265
   }
   return 0;

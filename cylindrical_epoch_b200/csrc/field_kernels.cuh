@@ -13,17 +13,17 @@ struct FieldRecips {
   double idx, idy, ieps0;
 };
 
-// E bulk: fields.f90:67-108.  ix = 0..nx, ir = 1..ny (y_min_boundary is always true for
-// x-slab decomposition), all modes.
+// E bulk: fields.f90:67-108.  ix = ix_lo..ix_hi (the reference's 0..nx, or the wider range of
+// field_ranges.cuh), ir = 1..ny (y_min_boundary is always true for x-slab decomposition), all modes.
 __global__ void __launch_bounds__(128) k_update_e_bulk(
     Geom g, cplx* __restrict__ exm, cplx* __restrict__ erm, cplx* __restrict__ etm,
     const cplx* __restrict__ bxm, const cplx* __restrict__ brm, const cplx* __restrict__ btm,
     const cplx* __restrict__ jxm, const cplx* __restrict__ jrm, const cplx* __restrict__ jtm,
-    FieldRecips R, double dy, double dt, double y_grid_min_local) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;   // 0..nx
+    FieldRecips R, double dy, double dt, double y_grid_min_local, int ix_lo, int ix_hi) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + ix_lo;
   const int ir = blockIdx.y + 1;
   const int im = blockIdx.z;
-  if (ix > g.nx) return;
+  if (ix > ix_hi) return;
   const double c = C_LIGHT;
   const double c2 = c * c;
   const double r_d = fabs((double)(ir - 1) * dy + y_grid_min_local);
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(128) k_update_e_axis(
   }
 }
 
-// B bulk: fields.f90:203-241.  ix = 0..nx, ir = 1..ny-1.  SAVE_OLD: the b*_old = b* copies of
+// B bulk: fields.f90:203-241.  ix = ix_lo..ix_hi (0..nx in the reference), ir = 1..ny-1.  SAVE_OLD: the b*_old = b* copies of
 // update_eb_fields_half (fields.f90:326-328) ride on this sweep -- the old values are in registers anyway -- for
 // the points it visits; the remaining rows and ghost columns are copied by k_copy_b_old_rim.
 template <bool SAVE_OLD>
@@ -103,11 +103,11 @@ __global__ void __launch_bounds__(128) k_update_b_bulk(
     Geom g, cplx* __restrict__ bxm, cplx* __restrict__ brm, cplx* __restrict__ btm,
     const cplx* __restrict__ exm, const cplx* __restrict__ erm, const cplx* __restrict__ etm,
     cplx* __restrict__ bxo, cplx* __restrict__ bro, cplx* __restrict__ bto,
-    FieldRecips R, double dy, double dt, double y_grid_min_local) {
-  const int ix = blockIdx.x * blockDim.x + threadIdx.x;
+    FieldRecips R, double dy, double dt, double y_grid_min_local, int ix_lo, int ix_hi) {
+  const int ix = blockIdx.x * blockDim.x + threadIdx.x + ix_lo;
   const int ir = blockIdx.y + 1;
   const int im = blockIdx.z;
-  if (ix > g.nx) return;
+  if (ix > ix_hi) return;
   const double r_d = fabs((double)(ir - 1) * dy + y_grid_min_local);
   const double r_p = r_d + 0.5 * dy;
   const double ir_d = 1.0 / r_d;
@@ -127,16 +127,17 @@ __global__ void __launch_bounds__(128) k_update_b_bulk(
 }
 
 // b*_old = b* for everything k_update_b_bulk<true> does not visit: rows outside 1..ny-1 and the ghost columns
-// outside 0..nx.  Runs BEFORE the B sweep (the axis / mirror rows are rewritten by k_update_b_axis afterwards).
+// outside ix_lo..ix_hi.  Runs BEFORE the B sweep (the axis / mirror rows are rewritten by k_update_b_axis afterwards).
 __global__ void __launch_bounds__(128) k_copy_b_old_rim(Geom g, const cplx* __restrict__ bxm, const cplx* __restrict__ brm,
                                                         const cplx* __restrict__ btm, cplx* __restrict__ bxo,
-                                                        cplx* __restrict__ bro, cplx* __restrict__ bto) {
+                                                        cplx* __restrict__ bro, cplx* __restrict__ bto, int ix_lo,
+                                                        int ix_hi) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;   // 0..SX-1
   const int row = blockIdx.y;                              // 0..SY-1
   const int im = blockIdx.z;
   if (col >= g.SX) return;
   const int ix = col + 1 - NG, ir = row + 1 - NG;
-  const bool swept = ix >= 0 && ix <= g.nx && ir >= 1 && ir <= g.ny - 1;
+  const bool swept = ix >= ix_lo && ix <= ix_hi && ir >= 1 && ir <= g.ny - 1;
   if (swept) return;
   const size_t o = ((size_t)im * g.SY + row) * g.SX + col;
   bxo[o] = bxm[o]; bro[o] = brm[o]; bto[o] = btm[o];

@@ -979,8 +979,11 @@ static int pbcs_species_fast(cylgpu_ctx* c, int isp, BcsConst B, bool classified
     const size_t bytes = (size_t)(7 * c->xcap + XHDR) * sizeof(double);
     double* rl = c->precv;
     double* rr = c->precv + (7 * c->xcap + XHDR);
-    TRY(transport_sendrecv(c, c->psend_l, has_l ? bytes : 0, rl, has_l ? bytes : 0, c->psend_r, has_r ? bytes : 0, rr,
-                           has_r ? bytes : 0));
+    c->msg_counted = true;    // (a mailbox link moves the slots in use only)
+    const int xr = transport_sendrecv(c, c->psend_l, has_l ? bytes : 0, rl, has_l ? bytes : 0, c->psend_r,
+                                      has_r ? bytes : 0, rr, has_r ? bytes : 0);
+    c->msg_counted = false;
+    TRY(xr);
     Soa s;
     for (int q = 0; q < 7; ++q) s.d[q] = S.d[q];
     k_unpack_dev<<<LEAVER_GRID, 256, 0, c->stream>>>(s, c->n_dev + isp, has_r ? rr : nullptr, has_l ? rl : nullptr);

@@ -10,6 +10,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include <condition_variable>
@@ -66,48 +67,74 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
   return *reinterpret_cast<const volatile unsigned long long*>(p);
 }
 
-// One message to a neighbour: wait until the slot is free (the receiver acknowledged the message two back), copy,
-// publish.  seq_ctr: my count of messages sent this way (device memory, so that a captured graph can be replayed);
-// my_hdr: the header of MY mailbox for messages from that neighbour (it holds the neighbour's acknowledgements).
-__global__ void __launch_bounds__(256) k_p2p_send(const double* __restrict__ src, size_t n8, unsigned char* peer_box,
-                                                  size_t cap, unsigned long long* seq_ctr,
-                                                  const P2PBoxHeader* my_hdr, unsigned int* done, int* status) {
+// One leg of an exchange through the mailboxes.  send: src -> the peer's box, hdr = the header of MY box for messages
+// from that neighbour (it holds the neighbour's acknowledgements); receive: my box -> dst, hdr = the PEER's header
+// that takes my acknowledgement.  seq_ctr: my count of messages on this leg (device memory, so that a captured graph
+// can be replayed).
+struct P2PLeg {
+  const double* src; double* dst; size_t n8;
+  unsigned char* box; unsigned long long* seq_ctr; P2PBoxHeader* hdr; unsigned int* done;
+};
+
+// words of a message that carry data: all of it, or -- a particle message, [7-double header: count][slots] -- the
+// header and the slots in use
+__device__ __forceinline__ size_t p2p_live_words(double count_word, size_t n8, int counted) {
+  if (!counted) return n8;
+  const long long bits = __double_as_longlong(count_word);   // (the count travels as an int64 in the first word)
+  const size_t want = 7 + 7 * (size_t)(bits > 0 ? bits : 0);
+  return want < n8 ? want : n8;
+}
+
+// Both sends of an exchange in one launch (blockIdx.y = leg): wait until the slot is free (the receiver acknowledged
+// the message two back), copy, publish.
+__global__ void __launch_bounds__(256) k_p2p_send(P2PLeg legs0, P2PLeg legs1, size_t cap, int counted, int* status) {
+  const P2PLeg L = blockIdx.y == 0 ? legs0 : legs1;
+  if (L.n8 == 0) return;
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) {
-    const unsigned long long seq = ld_volatile_u64(seq_ctr) + 1ULL;
+    const unsigned long long seq = ld_volatile_u64(L.seq_ctr) + 1ULL;
     const long long t0 = clock64();
-    while (seq > 2 && ld_volatile_u64(&my_hdr->ack) + 2ULL < seq) {
+    while (seq > 2 && ld_volatile_u64(&L.hdr->ack) + 2ULL < seq) {
       if (clock64() - t0 > P2P_TIMEOUT_CLOCKS) { *status = 1; break; }   // never hang the device: report instead
     }
     s_seq = seq;
   }
   __syncthreads();
   const unsigned long long seq = s_seq;
-  double* dst = reinterpret_cast<double*>(peer_box + P2P_FLAGS_BYTES + (seq & 1ULL) * cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = src[i];
+  const size_t n = p2p_live_words(L.src[0], L.n8, counted);
+  double* dst = reinterpret_cast<double*>(L.box + P2P_FLAGS_BYTES + (seq & 1ULL) * cap);
+  if (((reinterpret_cast<uintptr_t>(L.src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(L.src);
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += (size_t)gridDim.x * blockDim.x)
+      d2[i] = s2[i];
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[n - 1] = L.src[n - 1];
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      dst[i] = L.src[i];
+  }
   __threadfence_system();
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(done, 1u);
+    const unsigned int t = atomicAdd(L.done, 1u);
     if (t == gridDim.x - 1) {      // the last block: everything is on its way, publish
-      *done = 0u;
-      *seq_ctr = seq;
+      *L.done = 0u;
+      *L.seq_ctr = seq;
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&reinterpret_cast<P2PBoxHeader*>(peer_box)->flag[seq & 1ULL]) = seq;
+      *reinterpret_cast<volatile unsigned long long*>(&reinterpret_cast<P2PBoxHeader*>(L.box)->flag[seq & 1ULL]) = seq;
     }
   }
 }
 
-// ... and its arrival: wait for the flag of the next sequence number in MY mailbox, copy out (L2 loads: the data
+// ... and both arrivals: wait for the flag of the next sequence number in MY mailbox, copy out (L2 loads: the data
 // came from the peer), acknowledge in the PEER's header.
-__global__ void __launch_bounds__(256) k_p2p_recv(double* __restrict__ dst, size_t n8, const unsigned char* my_box,
-                                                  size_t cap, unsigned long long* seq_ctr, P2PBoxHeader* peer_hdr,
-                                                  unsigned int* done, int* status) {
+__global__ void __launch_bounds__(256) k_p2p_recv(P2PLeg legs0, P2PLeg legs1, size_t cap, int counted, int* status) {
+  const P2PLeg L = blockIdx.y == 0 ? legs0 : legs1;
+  if (L.n8 == 0) return;
   __shared__ unsigned long long s_seq;
   if (threadIdx.x == 0) {
-    const unsigned long long seq = ld_volatile_u64(seq_ctr) + 1ULL;
-    const P2PBoxHeader* hdr = reinterpret_cast<const P2PBoxHeader*>(my_box);
+    const unsigned long long seq = ld_volatile_u64(L.seq_ctr) + 1ULL;
+    const P2PBoxHeader* hdr = reinterpret_cast<const P2PBoxHeader*>(L.box);
     const long long t0 = clock64();
     while (ld_volatile_u64(&hdr->flag[seq & 1ULL]) != seq) {
       if (clock64() - t0 > P2P_TIMEOUT_CLOCKS) { *status = 2; break; }
@@ -116,17 +143,26 @@ __global__ void __launch_bounds__(256) k_p2p_recv(double* __restrict__ dst, size
   }
   __syncthreads();
   const unsigned long long seq = s_seq;
-  const double* src = reinterpret_cast<const double*>(my_box + P2P_FLAGS_BYTES + (seq & 1ULL) * cap);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x)
-    dst[i] = __ldcg(src + i);
+  const double* src = reinterpret_cast<const double*>(L.box + P2P_FLAGS_BYTES + (seq & 1ULL) * cap);
+  const size_t n = p2p_live_words(__ldcg(src), L.n8, counted);
+  if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(L.dst)) & 15) == 0) {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    double2* d2 = reinterpret_cast<double2*>(L.dst);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n / 2; i += (size_t)gridDim.x * blockDim.x)
+      d2[i] = __ldcg(s2 + i);
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) L.dst[n - 1] = __ldcg(src + n - 1);
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+      L.dst[i] = __ldcg(src + i);
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int t = atomicAdd(done, 1u);
+    const unsigned int t = atomicAdd(L.done, 1u);
     if (t == gridDim.x - 1) {
-      *done = 0u;
-      *seq_ctr = seq;
+      *L.done = 0u;
+      *L.seq_ctr = seq;
       __threadfence_system();
-      *reinterpret_cast<volatile unsigned long long*>(&peer_hdr->ack) = seq;
+      *reinterpret_cast<volatile unsigned long long*>(&L.hdr->ack) = seq;
     }
   }
 }
@@ -156,7 +192,8 @@ int p2p_setup(cylgpu_ctx* c, size_t cap) {
   // mine: two launches per exchange instead of three), which is the next step for this path.
   {
     const char* e = getenv("CYLGPU_P2P");
-    if (!e || atoi(e) == 0) return 0;
+    c->p2p_policy = !e ? 0 : (strcmp(e, "particles") == 0 ? 2 : (atoi(e) != 0 ? 1 : 0));
+    if (c->p2p_policy == 0) return 0;
   }
   const int left = c->left, right = c->right, me = c->cfg.rank;
   if ((left < 0 && right < 0) || left == me || right == me) return 0;
@@ -367,27 +404,28 @@ int transport_sendrecv(cylgpu_ctx* c, const void* sl, size_t sl_b, void* rl, siz
       const bool on_side = c->side && c->stream == c->side;   // (the mailboxes belong to the library stream)
       void* comm = (on_side && t->comm2) ? t->comm2 : t->comm;
       const bool l_on = left >= 0 && (sl_b || rl_b), r_on = right >= 0 && (sr_b || rr_b);
-      const bool l_p2p = !on_side && l_on && P.ready && c->p2p_link_l && sl_b <= P.cap && rl_b <= P.cap && sl_b % 8 == 0 && rl_b % 8 == 0;
-      const bool r_p2p = !on_side && r_on && P.ready && c->p2p_link_r && sr_b <= P.cap && rr_b <= P.cap && sr_b % 8 == 0 && rr_b % 8 == 0;
+      const bool p2p_msg = c->p2p_policy == 1 || (c->p2p_policy == 2 && c->msg_counted);
+      const bool l_p2p = p2p_msg && !on_side && l_on && P.ready && c->p2p_link_l && sl_b <= P.cap && rl_b <= P.cap && sl_b % 8 == 0 && rl_b % 8 == 0;
+      const bool r_p2p = p2p_msg && !on_side && r_on && P.ready && c->p2p_link_r && sr_b <= P.cap && rr_b <= P.cap && sr_b % 8 == 0 && rr_b % 8 == 0;
       if (l_p2p || r_p2p) {
         const size_t box = P2P_FLAGS_BYTES + 2 * P.cap;
         unsigned char* my_from_l = P.mine;
         unsigned char* my_from_r = P.mine + box;
-        auto blocks = [](size_t bytes) { return (unsigned)std::min<size_t>(std::max<size_t>(bytes / 8 / 1024, 1), 32); };
-        // sends first (nobody waits for me before I have written), then the arrivals
-        if (l_p2p && sl_b)   // my left-going message lands in the left neighbour's from_right box
-          k_p2p_send<<<blocks(sl_b), 256, 0, c->stream>>>((const double*)sl, sl_b / 8, P.peer_l + box, P.cap, P.seq + 0,
-                                                          (const P2PBoxHeader*)my_from_l, P.done + 0, P.status);
-        if (r_p2p && sr_b)
-          k_p2p_send<<<blocks(sr_b), 256, 0, c->stream>>>((const double*)sr, sr_b / 8, P.peer_r, P.cap, P.seq + 1,
-                                                          (const P2PBoxHeader*)my_from_r, P.done + 1, P.status);
-        if (r_p2p && rr_b)   // acknowledged in the header that holds my acks about the right neighbour's left-going messages
-          k_p2p_recv<<<blocks(rr_b), 256, 0, c->stream>>>((double*)rr, rr_b / 8, my_from_r, P.cap, P.seq + 3,
-                                                          (P2PBoxHeader*)P.peer_r, P.done + 2, P.status);
-        if (l_p2p && rl_b)
-          k_p2p_recv<<<blocks(rl_b), 256, 0, c->stream>>>((double*)rl, rl_b / 8, my_from_l, P.cap, P.seq + 2,
-                                                          (P2PBoxHeader*)(P.peer_l + box), P.done + 3, P.status);
-        c->stats.kernel_launches += (l_p2p && sl_b) + (r_p2p && sr_b) + (l_p2p && rl_b) + (r_p2p && rr_b);
+        const int counted = c->msg_counted ? 1 : 0;
+        const size_t big = std::max(std::max(l_p2p ? sl_b : 0, r_p2p ? sr_b : 0), std::max(l_p2p ? rl_b : 0, r_p2p ? rr_b : 0));
+        // (a counted message usually carries a fraction of its capacity)
+        const unsigned nb = (unsigned)std::min<size_t>(std::max<size_t>(big / (counted ? 64 : 16) / 1024, 1), 64);
+        // sends first (nobody waits for me before I have written), then the arrivals.  My left-going message lands
+        // in the left neighbour's from_right box; arrivals are acknowledged in the header that holds my acks about
+        // that neighbour's messages.
+        P2PLeg s0 = {}, s1 = {}, r0 = {}, r1 = {};
+        if (l_p2p && sl_b) s0 = P2PLeg{(const double*)sl, nullptr, sl_b / 8, P.peer_l + box, P.seq + 0, (P2PBoxHeader*)my_from_l, P.done + 0};
+        if (r_p2p && sr_b) s1 = P2PLeg{(const double*)sr, nullptr, sr_b / 8, P.peer_r, P.seq + 1, (P2PBoxHeader*)my_from_r, P.done + 1};
+        if (r_p2p && rr_b) r0 = P2PLeg{nullptr, (double*)rr, rr_b / 8, my_from_r, P.seq + 3, (P2PBoxHeader*)P.peer_r, P.done + 2};
+        if (l_p2p && rl_b) r1 = P2PLeg{nullptr, (double*)rl, rl_b / 8, my_from_l, P.seq + 2, (P2PBoxHeader*)(P.peer_l + box), P.done + 3};
+        if (s0.n8 || s1.n8) k_p2p_send<<<dim3(nb, 2), 256, 0, c->stream>>>(s0, s1, P.cap, counted, P.status);
+        if (r0.n8 || r1.n8) k_p2p_recv<<<dim3(nb, 2), 256, 0, c->stream>>>(r0, r1, P.cap, counted, P.status);
+        c->stats.kernel_launches += ((s0.n8 || s1.n8) ? 1 : 0) + ((r0.n8 || r1.n8) ? 1 : 0);
         CUDA_TRY(cudaGetLastError());
       }
       const bool l_nccl = l_on && !l_p2p, r_nccl = r_on && !r_p2p;

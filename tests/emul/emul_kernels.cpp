@@ -9,6 +9,7 @@
 
 #include "../../include/cylgpu.h"
 #include "../../cylindrical_epoch_b200/csrc/geom.cuh"
+#include "../../cylindrical_epoch_b200/csrc/field_ranges.cuh"
 #include "../../cylindrical_epoch_b200/csrc/philox.cuh"
 // the push arithmetic: IEEE division / square root instead of the PTX seeds (inline asm cannot run here)
 #define CYL_EMUL
@@ -426,7 +427,7 @@ EMUL_API void emul_bfield_final_bcs(int nx, int ny, int M, void* const* f15, con
     emul_launch(k_outflow_x, grd, dim3(128), g, F, snap(7), snap(8), snap(9), snap(10), snap(11), src4[2], src4[3], 1, dx,
                 dy, dt, y_grid_min_local);
   if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
-    emul_launch(k_outflow_r_max, dim3((g.nx + 1 + 127) / 128, g.M), dim3(128), g, F, 1, g.nx - 1, dx, dy, dt,
+    emul_launch(k_outflow_r_max, dim3((g.nx + 1 + 127) / 128, g.M), dim3(128), g, F, 1, g.nx - 1, 1, g.nx, 0, dx, dy, dt,
                 y_grid_min_local);
   } else if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
     emul_launch(k_zero_b_rmax, dim3((g.SX + 127) / 128, g.M), dim3(128), g, F.bxm, F.brm, F.btm);
@@ -575,7 +576,7 @@ EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f
   if (which == 0) {
     emul_launch(k_update_e_bulk, dim3((g.nx + 1 + 127) / 128, g.ny, g.M), blk, g, f[0], f[1], f[2], (const cplx*)f[3],
                 (const cplx*)f[4], (const cplx*)f[5], (const cplx*)f[6], (const cplx*)f[7], (const cplx*)f[8], R, dy, dt,
-                y_grid_min_local);
+                y_grid_min_local, 0, g.nx);
     emul_launch(k_update_e_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[0], f[1], f[2], (const cplx*)f[5],
                 (const cplx*)f[6], dy, dt);
   } else {
@@ -584,16 +585,16 @@ EMUL_API void emul_update_field(int which, int nx, int ny, int M, void* const* f
     if (which == 2) {
       for (int k = 0; k < 3; ++k) bo[k] = (cplx*)bold3[k];
       emul_launch(k_copy_b_old_rim, dim3((g.SX + 127) / 128, g.SY, g.M), blk, g, (const cplx*)f[3], (const cplx*)f[4],
-                  (const cplx*)f[5], bo[0], bo[1], bo[2]);
+                  (const cplx*)f[5], bo[0], bo[1], bo[2], 0, g.nx);
     }
     if (g.ny > 1) {
       const dim3 grd((g.nx + 1 + 127) / 128, g.ny - 1, g.M);
       if (which == 2)
         emul_launch(k_update_b_bulk<true>, grd, blk, g, f[3], f[4], f[5], (const cplx*)f[0], (const cplx*)f[1],
-                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local);
+                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local, 0, g.nx);
       else
         emul_launch(k_update_b_bulk<false>, grd, blk, g, f[3], f[4], f[5], (const cplx*)f[0], (const cplx*)f[1],
-                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local);
+                    (const cplx*)f[2], bo[0], bo[1], bo[2], R, dy, dt, y_grid_min_local, 0, g.nx);
     }
     emul_launch(k_update_b_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, f[3], f[4], f[5], (const cplx*)f[0],
                 (const cplx*)f[2], dx, dy, dt);
@@ -754,3 +755,213 @@ EMUL_API int emul_pbcs_fast(int nslab, double* const* soa, int64_t* n, int64_t c
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------------
+// update_eb_fields_half (phase 0) / update_eb_fields_final (phase 1) of a ROW OF SLABS, in the launch order of
+// api.cu (fields_half_body / cylgpu_fields_final) with the halos between the slabs done by the product's pack /
+// unpack kernels.  wide = 1: the communication-avoiding order (field_ranges.cuh: ghost columns advanced by the
+// slab itself, one closing exchange of E and B; wide = 2 with phase 1: the final phase right before the window's
+// shift_fields, no exchange at all); wide = 0: the reference's five exchanges.
+// f15: nranks x 15 mode arrays in field-id order; snaps12: nranks x 12 boundary snapshots; src4: source1/2 of
+// x_min then x_max.
+// ------------------------------------------------------------------------------------------------------
+namespace {
+struct Row {
+  int n, ny, M;
+  std::vector<Geom> g;
+  std::vector<cplx*> f;   // [rank * 15 + id]
+  bool periodic;
+  int left(int k) const { return k > 0 ? k - 1 : (periodic ? n - 1 : -1); }
+  int right(int k) const { return k < n - 1 ? k + 1 : (periodic ? 0 : -1); }
+  bool fill_l(int k) const { return left(k) >= 0; }    // (a non-periodic domain boundary has no neighbour)
+  bool fill_r(int k) const { return right(k) >= 0; }
+};
+
+// field_mode_bc on `narr` groups of three arrays of every slab (base ids in `bases`, row skips per group)
+void row_halo(const Row& R, const int* bases, const int (*skips)[3], int ngroups) {
+  const size_t he = (size_t)3 * R.M * (R.ny + 2 * NG) * NG;
+  std::vector<std::vector<cplx>> sl(R.n), sr(R.n);
+  for (int k = 0; k < R.n; ++k) {
+    sl[k].assign(ngroups * he, cplx{0.0, 0.0});
+    sr[k].assign(ngroups * he, cplx{0.0, 0.0});
+    const dim3 grd((R.g[k].SY * NG + 127) / 128, R.M, 3);
+    for (int q = 0; q < ngroups; ++q) {
+      Halo3 h;
+      for (int a = 0; a < 3; ++a) { h.f[a] = R.f[k * 15 + bases[q] + a]; h.skip[a] = skips[q][a]; }
+      emul_launch(k_halo_pack, grd, dim3(128), R.g[k], h, R.fill_l(k) ? sl[k].data() + q * he : (cplx*)nullptr,
+                  R.fill_r(k) ? sr[k].data() + q * he : (cplx*)nullptr, 0, he);
+    }
+  }
+  for (int k = 0; k < R.n; ++k) {
+    const dim3 grd((R.g[k].SY * NG + 127) / 128, R.M, 3);
+    for (int q = 0; q < ngroups; ++q) {
+      Halo3 h;
+      for (int a = 0; a < 3; ++a) { h.f[a] = R.f[k * 15 + bases[q] + a]; h.skip[a] = skips[q][a]; }
+      const cplx* rl = R.fill_l(k) ? sr[R.left(k)].data() + q * he : nullptr;    // my left neighbour's right-going block
+      const cplx* rr = R.fill_r(k) ? sl[R.right(k)].data() + q * he : nullptr;
+      emul_launch(k_halo_unpack, grd, dim3(128), R.g[k], h, rl, rr, 0, he);
+    }
+  }
+}
+
+// bcs.cu::edge_bcs of slab k (only on the domain boundaries it owns)
+void row_edges(const Row& R, int k, int which, const int32_t* bc_field) {
+  static const int STAG_X[6] = {0, 1, 1, 1, 0, 0}, STAG_Y[6] = {1, 0, 1, 0, 1, 0};
+  const Geom& g = R.g[k];
+  const int base = which ? 3 : 0;
+  Tri t;
+  for (int a = 0; a < 3; ++a) t.f[a] = R.f[k * 15 + base + a];
+  auto apply = [&](int bd, const int* op) {
+    if (op[0] == OP_NONE && op[1] == OP_NONE && op[2] == OP_NONE) return;
+    if (bc_field[bd] == CYLGPU_BC_PERIODIC) return;
+    if (bd == CYLGPU_BD_X_MIN && k != 0) return;
+    if (bd == CYLGPU_BD_X_MAX && k != R.n - 1) return;
+    for (int a = 0; a < 3; ++a) {
+      t.op[a] = op[a];
+      t.stag[a] = (bd == CYLGPU_BD_Y_MAX) ? STAG_Y[base + a] : STAG_X[base + a];
+    }
+    if (bd == CYLGPU_BD_Y_MAX) emul_launch(k_edge_y, dim3((g.SX + 127) / 128, g.M, 3), dim3(128), g, t);
+    else emul_launch(k_edge_x, dim3((g.SY + 127) / 128, g.M, 3), dim3(128), g, t, bd);
+  };
+  const int ecx[3] = {OP_CLAMP, OP_ZEROGRAD, OP_ZEROGRAD}, ecy[3] = {OP_ZEROGRAD, OP_CLAMP, OP_ZEROGRAD};
+  const int bcx[3] = {OP_ZEROGRAD, OP_CLAMP, OP_CLAMP}, bcy[3] = {OP_CLAMP, OP_ZEROGRAD, OP_CLAMP};
+  const int* cx = which ? bcx : ecx;
+  const int* cy = which ? bcy : ecy;
+  auto conduct = [&](int bc, const int* c3, int* op) {
+    op[0] = op[1] = op[2] = OP_NONE;
+    if (bc == CYLGPU_BC_CONDUCT) { op[0] = c3[0]; op[1] = c3[1]; op[2] = c3[2]; }
+  };
+  auto general = [&](int bc, int* op) {
+    op[0] = op[1] = op[2] = OP_NONE;
+    if (bc == CYLGPU_BC_CLAMP || bc == CYLGPU_BC_SIMPLE_LASER || bc == CYLGPU_BC_SIMPLE_OUTFLOW) op[0] = op[1] = op[2] = OP_CLAMP;
+    if (bc == CYLGPU_BC_ZERO_GRADIENT || bc == CYLGPU_BC_CPML_LASER || bc == CYLGPU_BC_CPML_OUTFLOW) op[0] = op[1] = op[2] = OP_ZEROGRAD;
+  };
+  int op[3];
+  for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX}) { conduct(bc_field[bd], cx, op); apply(bd, op); }
+  conduct(bc_field[CYLGPU_BD_Y_MAX], cy, op);
+  apply(CYLGPU_BD_Y_MAX, op);
+  for (int bd : {(int)CYLGPU_BD_X_MIN, (int)CYLGPU_BD_X_MAX, (int)CYLGPU_BD_Y_MAX}) { general(bc_field[bd], op); apply(bd, op); }
+}
+}  // namespace
+
+extern "C" EMUL_API void emul_field_phase_slabs(int phase, int wide, int nranks, const int* nx_each, int ny, int M,
+                                     void* const* f15, const void* const* snaps12, const double* const* src4,
+                                     const int32_t* bc_field, double dx, double dy, double dt,
+                                     double y_grid_min_local) {
+  Row R;
+  R.n = nranks; R.ny = ny; R.M = M;
+  R.periodic = bc_field[CYLGPU_BD_X_MIN] == CYLGPU_BC_PERIODIC;
+  for (int k = 0; k < nranks; ++k) {
+    Geom g;
+    g.nx = nx_each[k]; g.ny = ny; g.M = M;
+    g.SX = g.nx + 2 * NG; g.SY = ny + 2 * NG;
+    g.plane = (size_t)g.SX * g.SY;
+    R.g.push_back(g);
+    for (int a = 0; a < 15; ++a) R.f.push_back((cplx*)f15[k * 15 + a]);
+  }
+  FieldRecips Rc;
+  Rc.idx = 1.0 / dx; Rc.idy = 1.0 / dy; Rc.ieps0 = 1.0 / EPSILON0;
+  const dim3 blk(128);
+  auto F = [&](int k, int id) { return R.f[k * 15 + id]; };
+  auto ranges = [&](int k) {
+    const bool w = wide != 0 && nranks > 1 && R.g[k].nx >= 2 * NG && (R.fill_l(k) || R.fill_r(k));   // bcs.cu::wide_fields
+    return field_ranges(phase == 1 && wide == 2 ? 2 : phase, w, R.fill_l(k), R.fill_r(k), k == 0, k == nranks - 1, R.g[k].nx);
+  };
+  auto sweep_e = [&](int k, int lo, int hi) {   // fields.cu::launch_update_e
+    const Geom& g = R.g[k];
+    emul_launch(k_update_e_bulk, dim3((hi - lo + 1 + 127) / 128, g.ny, g.M), blk, g, F(k, 0), F(k, 1), F(k, 2),
+                (const cplx*)F(k, 3), (const cplx*)F(k, 4), (const cplx*)F(k, 5), (const cplx*)F(k, 6),
+                (const cplx*)F(k, 7), (const cplx*)F(k, 8), Rc, dy, dt, y_grid_min_local, lo, hi);
+    emul_launch(k_update_e_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, F(k, 0), F(k, 1), F(k, 2),
+                (const cplx*)F(k, 5), (const cplx*)F(k, 6), dy, dt);
+  };
+  auto sweep_b = [&](int k, bool save_old, int lo, int hi) {   // fields.cu::launch_update_b
+    const Geom& g = R.g[k];
+    if (save_old)
+      emul_launch(k_copy_b_old_rim, dim3((g.SX + 127) / 128, g.SY, g.M), blk, g, (const cplx*)F(k, 3), (const cplx*)F(k, 4),
+                  (const cplx*)F(k, 5), F(k, 9), F(k, 10), F(k, 11), lo, hi);
+    if (g.ny > 1) {
+      const dim3 grd((hi - lo + 1 + 127) / 128, g.ny - 1, g.M);
+      if (save_old)
+        emul_launch(k_update_b_bulk<true>, grd, blk, g, F(k, 3), F(k, 4), F(k, 5), (const cplx*)F(k, 0), (const cplx*)F(k, 1),
+                    (const cplx*)F(k, 2), F(k, 9), F(k, 10), F(k, 11), Rc, dy, dt, y_grid_min_local, lo, hi);
+      else
+        emul_launch(k_update_b_bulk<false>, grd, blk, g, F(k, 3), F(k, 4), F(k, 5), (const cplx*)F(k, 0), (const cplx*)F(k, 1),
+                    (const cplx*)F(k, 2), F(k, 9), F(k, 10), F(k, 11), Rc, dy, dt, y_grid_min_local, lo, hi);
+    }
+    emul_launch(k_update_b_axis, dim3((g.SX + 127) / 128, g.M, NG), blk, g, F(k, 3), F(k, 4), F(k, 5), (const cplx*)F(k, 0),
+                (const cplx*)F(k, 2), dx, dy, dt);
+  };
+  auto outflow = [&](int k, const FieldRanges& X) {   // bcs.cu::do_bfield_final_bcs_device between its two halos
+    const Geom& g = R.g[k];
+    FieldSet S;
+    S.exm = F(k, 0); S.erm = F(k, 1); S.etm = F(k, 2); S.bxm = F(k, 3); S.brm = F(k, 4); S.btm = F(k, 5);
+    S.jxm = F(k, 6); S.jrm = F(k, 7); S.jtm = F(k, 8); S.bxo = F(k, 9); S.bro = F(k, 10); S.bto = F(k, 11);
+    S.jxo = F(k, 12); S.jro = F(k, 13); S.jto = F(k, 14);
+    const dim3 grd((g.ny + 1 + 127) / 128, g.M);
+    auto snap = [&](int q) { return (const cplx*)snaps12[k * 12 + q]; };
+    if (k == 0) {
+      const int b = bc_field[CYLGPU_BD_X_MIN];
+      if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
+        emul_launch(k_outflow_x, grd, dim3(128), g, S, snap(1), snap(2), snap(3), snap(4), snap(5), src4[0], src4[1], 0, dx,
+                    dy, dt, y_grid_min_local);
+    }
+    if (k == nranks - 1) {
+      const int b = bc_field[CYLGPU_BD_X_MAX];
+      if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
+        emul_launch(k_outflow_x, grd, dim3(128), g, S, snap(7), snap(8), snap(9), snap(10), snap(11), src4[2], src4[3], 1,
+                    dx, dy, dt, y_grid_min_local);
+    }
+    if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
+      const int ix0 = X.obx_lo < X.obt_lo ? X.obx_lo : X.obt_lo;
+      const int ix1 = X.obx_hi > X.obt_hi ? X.obx_hi : X.obt_hi;
+      emul_launch(k_outflow_r_max, dim3((ix1 - ix0 + 1 + 127) / 128, g.M), dim3(128), g, S, X.obx_lo, X.obx_hi, X.obt_lo,
+                  X.obt_hi, ix0, dx, dy, dt, y_grid_min_local);
+    } else if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
+      emul_launch(k_zero_b_rmax, dim3((g.SX + 127) / 128, g.M), dim3(128), g, S.bxm, S.brm, S.btm);
+    }
+  };
+  const int baseE[1] = {0}, baseB[1] = {3}, baseEB[2] = {0, 3};
+  const int skipE[1][3] = {{1, 0, 1}}, skipB[1][3] = {{0, 1, 0}}, skipEB[2][3] = {{1, 0, 1}, {0, 1, 0}};
+  if (wide) {
+    if (phase == 0) {
+      for (int k = 0; k < nranks; ++k) {
+        const FieldRanges X = ranges(k);
+        sweep_e(k, X.e_lo, X.e_hi);
+        row_edges(R, k, 0, bc_field);
+        sweep_b(k, true, X.b_lo, X.b_hi);
+      }
+      row_halo(R, baseEB, skipEB, 2);
+    } else {
+      for (int k = 0; k < nranks; ++k) {
+        const FieldRanges X = ranges(k);
+        sweep_b(k, false, X.b_lo, X.b_hi);
+        row_edges(R, k, 1, bc_field);
+        outflow(k, X);
+        sweep_e(k, X.e_lo, X.e_hi);
+        row_edges(R, k, 0, bc_field);
+      }
+      if (wide != 2) row_halo(R, baseEB, skipEB, 2);   // wide == 2: shift_fields follows and exchanges (api.cu to_shift)
+    }
+    return;
+  }
+  // the reference's order: every slab sweeps, the row exchanges, every slab fills its domain edges
+  auto all = [&](auto fn) { for (int k = 0; k < nranks; ++k) fn(k); };
+  if (phase == 0) {
+    all([&](int k) { sweep_e(k, 0, R.g[k].nx); });
+    row_halo(R, baseE, skipE, 1);
+    all([&](int k) { row_edges(R, k, 0, bc_field); });
+    all([&](int k) { sweep_b(k, true, 0, R.g[k].nx); });
+    row_halo(R, baseB, skipB, 1);
+  } else {
+    all([&](int k) { sweep_b(k, false, 0, R.g[k].nx); });
+    row_halo(R, baseB, skipB, 1);
+    all([&](int k) { row_edges(R, k, 1, bc_field); });
+    all([&](int k) { outflow(k, ranges(k)); });
+    row_halo(R, baseB, skipB, 1);
+    all([&](int k) { sweep_e(k, 0, R.g[k].nx); });
+    row_halo(R, baseE, skipE, 1);
+    all([&](int k) { row_edges(R, k, 0, bc_field); });
+  }
+}

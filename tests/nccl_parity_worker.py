@@ -48,7 +48,7 @@ def main():
         tol = TOL_HOT if deckname == "thermal" else (TOL if deckname == "lwfa" else 1e-9)
         w = decks.make_oracle(d, nranks=world)        # every process steps the whole oracle world
         s = decks.make_slab(d, rank=rank, nranks=world, device=local, **kw)
-        if mode == "nccl" and os.environ.get("CYLGPU_P2P", "0") == "1" and deckname != "thermal":
+        if mode == "nccl" and os.environ.get("CYLGPU_P2P", "0") in ("1", "particles") and deckname != "thermal":
             # (the thermal ring of two ranks has left == right: mailboxes as well; open decks: one link per rank)
             info = s.transport_info()
             if not (info[1] or info[2]):

@@ -11,17 +11,17 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-@pytest.mark.parametrize("mode", ["nccl", "callback", "mailboxes"])
+@pytest.mark.parametrize("mode", ["nccl", "callback", "mailboxes", "mailboxes-particles"])
 def test_two_gpu_parity(mode, cylgpu_lib):
     """mailboxes: the NCCL transport with its opt-in peer-memory data path (CYLGPU_P2P=1, csrc/transport.cu)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
-    if mode == "mailboxes":
-        env["CYLGPU_P2P"] = "1"
+    if mode.startswith("mailboxes"):   # -particles: the counted particle messages only, halos through NCCL
+        env["CYLGPU_P2P"] = "1" if mode == "mailboxes" else "particles"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "nccl_parity_worker.py"),
-           "nccl" if mode == "mailboxes" else mode]
+           "nccl" if mode.startswith("mailboxes") else mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "NCCL_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

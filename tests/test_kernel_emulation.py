@@ -877,3 +877,144 @@ def test_snapshot_and_window_shift_kernels_match_the_oracle(emul):
     L.emul_shift_fields(info["nx"], info["ny"], d.n_mode, fp, sp)
     for n, a in zip(FIELD_NAMES[:9], before[:9]):
         assert np.array_equal(a, w.field(0, n)), n
+
+
+# ------------------------------------------------------------------------------------------------------
+# The communication-avoiding field phases (csrc/field_ranges.cuh, api.cu fields_half_body / cylgpu_fields_final):
+# a row of slabs advances its own ghost columns and exchanges E and B once per phase.  The emulated row must
+# (a) give bit for bit the arrays of the reference's order of exchanges run through the same kernels -- ghost
+# columns, ghost rows and b*_old included -- and (b) follow the oracle's ranks through whole steps.
+# ------------------------------------------------------------------------------------------------------
+def _row_state(w, nranks):
+    from pyoracle import FIELD_NAMES, SNAP_NAMES
+    f = [[w.field(k, n).copy() for n in FIELD_NAMES] for k in range(nranks)]
+    s = [[w.field(k, n).copy() for n in SNAP_NAMES] for k in range(nranks)]
+    return f, s
+
+
+def _run_phase(L, phase, wide, w, f, s, d, src):
+    nranks = len(f)
+    sc = w.scalars()
+    nx = (C.c_int * nranks)(*[w.rank_info(k)["nx"] for k in range(nranks)])
+    fp = (C.c_void_p * (15 * nranks))(*[a.ctypes.data for row in f for a in row])
+    sp = (C.c_void_p * (12 * nranks))(*[a.ctypes.data for row in s for a in row])
+    rp = (C.c_void_p * 4)(*[a.ctypes.data for a in src])
+    bcf = (C.c_int32 * 4)(*w.bc_field())
+    L.emul_field_phase_slabs(phase, wide, nranks, nx, w.rank_info(0)["ny"], d.n_mode, fp, sp, rp, bcf, sc["dx"], sc["dy"],
+                             sc["dt"], sc["y_grid_min_local"])
+
+
+@pytest.mark.parametrize("deck_name,nranks", [("lwfa", 3), ("lwfa", 2), ("thermal", 2), ("thermal", 3), ("walls", 2)])
+def test_wide_field_phases_match_the_exchanged_ones(emul, deck_name, nranks):
+    from pyoracle import FIELD_NAMES
+    L = emul
+    L.emul_field_phase_slabs.restype = None
+    L.emul_field_phase_slabs.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_int32)] + [C.c_double] * 4
+    if deck_name == "lwfa":      # laser from x_min, open x, simple_outflow on r_max: every line update is live
+        d = decks.lwfa(nx=20 * nranks, ny=12, n_mode=3, ppc_e=3, ppc_p=1, t_centre=10e-15)
+    elif deck_name == "thermal":  # periodic ring (two ranks: left == right), zero_b on r_max
+        d = decks.thermal(nx=12 * nranks, ny=10, n_mode=2, ppc=6, temp_k=2.0e8)
+    else:                        # conducting walls all round
+        d = decks.thermal(nx=12 * nranks, ny=10, n_mode=2, ppc=6, temp_k=2.0e8)
+        d.bc_field = (po.BC_CONDUCT, po.BC_CONDUCT, 0, po.BC_CONDUCT)
+        for sp in d.species:
+            sp.bc_particle = (po.BC_REFLECT, po.BC_REFLECT, po.BC_OPEN, po.BC_REFLECT)
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    w.step(30 if deck_name == "lwfa" else 6)      # the pulse has crossed the first slab boundary
+    worst = 0.0
+    for step in range(6):
+        for phase in (0, 1):
+            if phase == 1:
+                w.call("push")
+                w.call("current_finish")
+                w.call("advance_half_time")
+                w.call("flush_rng")
+                w.call("advance_half_time")
+            src = [np.ascontiguousarray(a, dtype=np.float64) for bd in (po.BD_X_MIN, po.BD_X_MAX)
+                   for a in w.laser_sources(bd)]
+            f_wide, s = _row_state(w, nranks)
+            f_ref, _ = _row_state(w, nranks)
+            _run_phase(L, phase, 1, w, f_wide, s, d, src)
+            _run_phase(L, phase, 0, w, f_ref, s, d, src)
+            w.call("fields_half" if phase == 0 else "fields_final")
+            for k in range(nranks):
+                for name, a, b in zip(FIELD_NAMES, f_wide[k], f_ref[k]):
+                    assert np.array_equal(a, b), (deck_name, step, phase, k, name,
+                                                  np.unique(np.nonzero(a != b)[2]).tolist())
+                    ref = w.field(k, name)
+                    den = np.abs(ref).max()
+                    if den > 0:
+                        worst = max(worst, np.abs(a - ref).max() / den)
+                        assert np.abs(a - ref).max() <= 1e-13 * den, (deck_name, step, phase, k, name)
+            assert np.abs(w.field(nranks - 1, "exm")).max() > 0      # the fields are live in the last slab too
+    assert worst < 1e-13
+
+
+def test_wide_final_phase_before_a_window_shift(emul):
+    """api.cu `to_shift`: when the moving window's shift_fields follows, update_eb_fields_final advances column
+    nx+1 itself and leaves every exchange to the window's nine-array halo.  Shift and halo are done here in numpy
+    (window.F90:98-153); the slabs must then hold the oracle's arrays, ghost columns included."""
+    from pyoracle import FIELD_NAMES
+    L = emul
+    L.emul_field_phase_slabs.restype = None
+    L.emul_field_phase_slabs.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                         C.POINTER(C.c_int32)] + [C.c_double] * 4
+    nranks = 3
+    d = decks.lwfa(nx=20 * nranks, ny=12, n_mode=2, ppc_e=3, ppc_p=1, window=True, t_centre=10e-15)
+    d.window_start_time = 8.0e-15        # the leading half of the pulse fills the box before the window sets off
+    w = decks.make_oracle(d, nranks=nranks)
+    w.call("init_half_step")
+    for _ in range(400):
+        if w.scalars()["window_shifts_total"] >= 3:
+            break
+        w.step(1)
+    assert w.scalars()["window_shifts_total"] >= 3
+    NG = 5
+    shifted = 0
+    for step in range(14):
+        w.call("fields_half")
+        w.call("push")
+        w.call("current_finish")
+        w.call("advance_half_time")
+        w.call("flush_rng")
+        w.call("advance_half_time")
+        src = [np.ascontiguousarray(a, dtype=np.float64) for bd in (po.BD_X_MIN, po.BD_X_MAX) for a in w.laser_sources(bd)]
+        f, s = _row_state(w, nranks)
+        before = w.scalars()["window_shifts_total"]
+        w.call("fields_final")
+        w.call("moving_window")
+        cells = int(w.scalars()["window_shifts_total"] - before)
+        assert cells in (0, 1)
+        if cells == 0:
+            continue
+        shifted += 1
+        _run_phase(L, 1, 2, w, f, s, d, src)
+        for k in range(nranks):           # shift_field_modes: a(ix) = a(ix+1) over the whole extent but the last column
+            for a in f[k][:9]:
+                a[..., :-1] = a[..., 1:].copy()
+        new = [[a.copy() for a in row] for row in f]
+        for k in range(nranks):           # field_mode_bc: the neighbours' interior edge columns, every row
+            nxk = w.rank_info(k)["nx"]
+            for i in range(9):
+                if k > 0:
+                    nxl = w.rank_info(k - 1)["nx"]
+                    new[k][i][..., 0:NG] = f[k - 1][i][..., nxl:nxl + NG]
+                if k < nranks - 1:
+                    new[k][i][..., NG + nxk:] = f[k + 1][i][..., NG:2 * NG]
+        for k in range(nranks):
+            nxk = w.rank_info(k)["nx"]
+            hi = NG + nxk - 2 if k == nranks - 1 else None     # (the last slab's new columns come from the fill)
+            for name, a in zip(FIELD_NAMES[:9], new[k]):
+                ref = w.field(k, name)
+                den = np.abs(ref).max()
+                if den > 0:
+                    err = np.abs(a[..., :hi] - ref[..., :hi])
+                    assert err.max() <= 1e-13 * den, (step, k, name, np.unique(np.nonzero(err > 1e-13 * den)[2]).tolist())
+    assert shifted >= 5, shifted
+    for k in range(nranks):               # ... with live fields at every slab boundary (what the test is about)
+        e = np.abs(w.field(k, "erm"))
+        assert e[..., NG:NG + 2].max() > 1e-3 * e.max() and e[..., -NG - 2:-NG].max() > 1e-3 * e.max()

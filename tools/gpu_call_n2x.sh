@@ -1,0 +1,21 @@
+#!/bin/bash
+# 2 GPUs: the transport tests, then the particle-exchange variants of the bench at N=2 (per-rank phases on stderr)
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_nccl.py -m gpu -q 2>&1 | tail -5 | cut -c1-600
+run() {  # name n env...
+  name=$1; n=$2; shift 2
+  env "$@" BENCH_RANK_PHASES=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29577 \
+     bench.py --gpus $n --steps 20 --warmup 5 --no-e2e > gpurun_out/bench_x_$name.json 2> gpurun_out/bench_x_$name.err
+  echo "== $name"; python - gpurun_out/bench_x_$name.json <<'P'
+import json,sys
+try:
+    d=json.load(open(sys.argv[1]))
+    print("value %.4e ms/step %.3f"%(d['value'],d['ms_per_step']), d['config'].get('neighbour_links'), d['config'].get('exchange_capacity'))
+except Exception as e:
+    print("ERR", e)
+P
+  grep "^rank" gpurun_out/bench_x_$name.err | sort -u | cut -c1-200
+  grep -i "error\|overflow" gpurun_out/bench_x_$name.err | head -3 | cut -c1-300
+}
+run n2_p2p_particles 2 CYLGPU_P2P=particles
