@@ -185,14 +185,15 @@ int p2p_setup(cylgpu_ctx* c, size_t cap) {
   Transport* t = c->tr;
   c->p2p_link_l = c->p2p_link_r = false;
   if (!t || t->kind != CYLGPU_TRANSPORT_NCCL) return 0;
-  // Opt-in (CYLGPU_P2P=1).  Measured on C3 over 8 B200s (profiles/r2d_*): 3.81 ms per step with the mailboxes
-  // against 3.73 ms with ncclSend / ncclRecv -- a message costs four launches here (two sends, two receives, each
-  // with its own wait) against one fused NCCL kernel per exchange, and at ~10 exchanges per step that outweighs the
-  // rendezvous it saves.  Kept for the fused form (pack straight into the neighbour's slot, unpack straight out of
-  // mine: two launches per exchange instead of three), which is the next step for this path.
+  // On by default for every message that fits a slot; CYLGPU_P2P=0: ncclSend / ncclRecv only, CYLGPU_P2P=particles:
+  // the counted particle messages only.  Measured on C3 over 8 B200s with the communication-avoiding field phases
+  // (profiles/r2g_*): 3.46 ms per step through the mailboxes (3.47 with the particle messages only) against 3.98 ms
+  // through NCCL alone.  The first version (round 2, r2d: four launches per exchange, 32 blocks, whole fixed-size
+  // particle messages) was slower than NCCL (3.81 against 3.73 ms); what changed: both legs of an exchange in one
+  // launch, 16-byte copies on up to 64 blocks, and only the slots in use of a particle message cross the link.
   {
     const char* e = getenv("CYLGPU_P2P");
-    c->p2p_policy = !e ? 0 : (strcmp(e, "particles") == 0 ? 2 : (atoi(e) != 0 ? 1 : 0));
+    c->p2p_policy = !e ? 1 : (strcmp(e, "particles") == 0 ? 2 : (atoi(e) != 0 ? 1 : 0));
     if (c->p2p_policy == 0) return 0;
   }
   const int left = c->left, right = c->right, me = c->cfg.rank;

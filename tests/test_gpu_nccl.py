@@ -13,13 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 @pytest.mark.parametrize("mode", ["nccl", "callback", "mailboxes", "mailboxes-particles"])
 def test_two_gpu_parity(mode, cylgpu_lib):
-    """mailboxes: the NCCL transport with its opt-in peer-memory data path (CYLGPU_P2P=1, csrc/transport.cu)"""
+    """nccl: ncclSend / ncclRecv only (CYLGPU_P2P=0); mailboxes: the NCCL transport with its peer-memory data path
+    (the default, csrc/transport.cu); mailboxes-particles: the mailboxes for the counted particle messages only"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
-    if mode.startswith("mailboxes"):   # -particles: the counted particle messages only, halos through NCCL
-        env["CYLGPU_P2P"] = "1" if mode == "mailboxes" else "particles"
+    env["CYLGPU_P2P"] = {"mailboxes": "1", "mailboxes-particles": "particles"}.get(mode, "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "nccl_parity_worker.py"),
            "nccl" if mode.startswith("mailboxes") else mode]
