@@ -25,3 +25,18 @@ def test_two_gpu_parity(mode, cylgpu_lib):
            "nccl" if mode.startswith("mailboxes") else mode]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "NCCL_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("mode", ["mailboxes", "nccl"])
+def test_four_gpu_parity(mode, cylgpu_lib):
+    """interior ranks: two different neighbours per rank (two mailbox links, two NCCL peers), the closing exchange of
+    the communication-avoiding field phases in both directions at once, the window deck over four slabs"""
+    import torch
+    if torch.cuda.device_count() < 4:
+        pytest.skip("needs 4 GPUs")
+    env = dict(os.environ)
+    env["CYLGPU_P2P"] = "1" if mode == "mailboxes" else "0"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(HERE, "nccl_parity_worker.py"), "nccl"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)
+    assert "NCCL_PARITY_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,4 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python tools/compare_math_variants.py 2>&1 | tail -8 | tee gpurun_out/r2g_math_variants.txt
-CYLGPU_LIB=$PWD/cylindrical_epoch_b200/libcylgpu_refmath.so python -m pytest tests/test_gpu_parity.py -m gpu -q 2>&1 | tail -2 | tee -a gpurun_out/r2g_math_variants.txt
+timeout 1200 python -m pytest tests/test_gpu_nccl.py -m gpu -q -k "four" 2>&1 | tail -12 | cut -c1-600 | tee gpurun_out/r2g_pytest_nccl_4gpu.txt
