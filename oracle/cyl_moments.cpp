@@ -30,9 +30,9 @@ namespace cylo {
 
 namespace {
 
-struct ToGrid {   // include/particle_to_grid.inc, triangle/gxfac.inc
+struct ToGrid {   // include/particle_to_grid.inc, <shape>/gxfac.inc (cyl_oracle.hpp particle_to_grid)
   int cell_x, cell_y;
-  double gx[3], gy[3];
+  double gx[NW], gy[NW];   // offsets -3..3 at [k + WO]
   double part_r;
 };
 
@@ -40,26 +40,8 @@ inline ToGrid particle_to_grid(const Particle& p, double x_grid_min_local, doubl
                                double dy) {
   ToGrid t;
   t.part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
-  const double cell_x_r = (p.pos[0] - x_grid_min_local) / dx;
-  const double cell_y_r = (t.part_r - y_grid_min_local) / dy;
-  t.cell_x = (int)std::floor(cell_x_r + 0.5);
-  t.cell_y = (int)std::floor(cell_y_r + 0.5);
-  const double cell_frac_x = (double)t.cell_x - cell_x_r;
-  const double cell_frac_y = (double)t.cell_y - cell_y_r;
-  t.cell_x = t.cell_x + 1;
-  t.cell_y = t.cell_y + 1;
-  const double cx2 = cell_frac_x * cell_frac_x;
-  t.gx[0] = 0.5 * (0.25 + cx2 + cell_frac_x);
-  t.gx[1] = 0.75 - cx2;
-  t.gx[2] = 0.5 * (0.25 + cx2 - cell_frac_x);
-  const double cy2 = cell_frac_y * cell_frac_y;
-  t.gy[0] = 0.5 * (0.25 + cy2 + cell_frac_y);
-  t.gy[1] = 0.75 - cy2;
-  t.gy[2] = 0.5 * (0.25 + cy2 - cell_frac_y);
-  if (t.part_r < dy) {
-    t.gy[1] = t.gy[1] + t.gy[0];
-    t.gy[0] = 0.0;
-  }
+  cylo::particle_to_grid(p.pos[0] - x_grid_min_local, t.part_r - y_grid_min_local, t.part_r, dx, dy, &t.cell_x,
+                         &t.cell_y, t.gx, t.gy);
   return t;
 }
 
@@ -150,8 +132,9 @@ void World::calc_moment(int kind, int current_species, int direction) {
         if (skip(isp)) continue;
         for (const Particle& p : r.parts[isp]) {
           const double part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
-          const double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx + 0.5;
-          const double cell_y_r = (part_r - y_grid_min_local) / dy + 0.5;
+          // (top-hat: without the half cell, calc_df.F90:696-702, 757-763)
+          const double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx + (0.5 - SHAPE_CELL_SHIFT);
+          const double cell_y_r = (part_r - y_grid_min_local) / dy + (0.5 - SHAPE_CELL_SHIFT);
           const int cell_x = (int)std::floor(cell_x_r) + 1;
           const int cell_y = (int)std::floor(cell_y_r) + 1;
           if (kind == MOM_PPC) {
@@ -182,9 +165,9 @@ void World::calc_moment(int kind, int current_species, int direction) {
           const double part_pmy = p.p[1] / sqrt_part_m;
           const double part_pmz = p.p[2] / sqrt_part_m;
           const ToGrid t = particle_to_grid(p, r.x_grid_min_local, y_grid_min_local, dx, dy);
-          for (int iy = -1; iy <= 1; ++iy)
-            for (int ix = -1; ix <= 1; ++ix) {
-              const double gf = t.gx[ix + 1] * t.gy[iy + 1] * part_w;
+          for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
+            for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+              const double gf = t.gx[ix + WO] * t.gy[iy + WO] * part_w;
               const int cx = t.cell_x + ix, cy = t.cell_y + iy;
               if (dir == 1 || dir == -1) re(r.m1, cx, cy) = re(r.m1, cx, cy) + gf * part_pmx;
               if (dir == 2 || dir == -1) re(r.m2, cx, cy) = re(r.m2, cx, cy) + gf * part_pmy;
@@ -218,9 +201,9 @@ void World::calc_moment(int kind, int current_species, int direction) {
           const double part_pmy = p.p[1] / sqrt_part_m;
           const double part_pmz = p.p[2] / sqrt_part_m;
           const ToGrid t = particle_to_grid(p, r.x_grid_min_local, y_grid_min_local, dx, dy);
-          for (int iy = -1; iy <= 1; ++iy)
-            for (int ix = -1; ix <= 1; ++ix) {
-              const double gf = t.gx[ix + 1] * t.gy[iy + 1];
+          for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
+            for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+              const double gf = t.gx[ix + WO] * t.gy[iy + WO];
               const int cx = t.cell_x + ix, cy = t.cell_y + iy;
               double wdata;
               const double ddx = part_pmx - re(r.m1, cx, cy);
@@ -303,11 +286,11 @@ void World::calc_moment(int kind, int current_species, int direction) {
           } break;
           default: assert(!"unknown moment");
         }
-        for (int iy = -1; iy <= 1; ++iy)
-          for (int ix = -1; ix <= 1; ++ix) {
+        for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
+          for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
             const int cx = t.cell_x + ix, cy = t.cell_y + iy;
-            re(r.m0, cx, cy) = re(r.m0, cx, cy) + t.gx[ix + 1] * t.gy[iy + 1] * wdata;
-            if (averaged) re(r.m1, cx, cy) = re(r.m1, cx, cy) + t.gx[ix + 1] * t.gy[iy + 1] * part_w;
+            re(r.m0, cx, cy) = re(r.m0, cx, cy) + t.gx[ix + WO] * t.gy[iy + WO] * wdata;
+            if (averaged) re(r.m1, cx, cy) = re(r.m1, cx, cy) + t.gx[ix + WO] * t.gy[iy + WO] * part_w;
           }
       }
     }

@@ -194,32 +194,19 @@ void World::load_uniform(int isp) {
     auto cidx = [&](int cx, int cy) { return (size_t)(cy + NG - 1) * (r.nx + 2 * NG) + (cx + NG - 1); };
     for (Particle& p : pl) {
       double part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
-      double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx;
-      double cell_y_r = (part_r - y_grid_min_local) / dy;
-      int cell_x = (int)std::floor(cell_x_r + 0.5);
-      int cell_y = (int)std::floor(cell_y_r + 0.5);
-      double cfx = (double)cell_x - cell_x_r;
-      double cfy = (double)cell_y - cell_y_r;
-      cell_x += 1;
-      cell_y += 1;
-      double gx[3], gy[3];
-      double cx2 = cfx * cfx;
-      gx[0] = 0.5 * (0.25 + cx2 + cfx);
-      gx[1] = 0.75 - cx2;
-      gx[2] = 0.5 * (0.25 + cx2 - cfx);
-      double cy2 = cfy * cfy;
-      gy[0] = 0.5 * (0.25 + cy2 + cfy);
-      gy[1] = 0.75 - cy2;
-      gy[2] = 0.5 * (0.25 + cy2 - cfy);
-      if (part_r < dy) {
-        gy[1] = gy[1] + gy[0];
-        gy[0] = 0.0;
-      }
+      int cell_x, cell_y;
+      double gx[NW], gy[NW];
+      particle_to_grid(p.pos[0] - r.x_grid_min_local, part_r - y_grid_min_local, part_r, dx, dy, &cell_x, &cell_y, gx, gy);
       double wdata = 0.0;
-      for (int isuby = -1; isuby <= 1; ++isuby)
-        for (int isubx = -1; isubx <= 1; ++isubx)
-          wdata = wdata + gx[isubx + 1] * gy[isuby + 1] * s.density;   // uniform density map
+      for (int isuby = SF_MIN; isuby <= SF_MAX; ++isuby)
+        for (int isubx = SF_MIN; isubx <= SF_MAX; ++isubx)
+          wdata = wdata + gx[isubx + WO] * gy[isuby + WO] * s.density;   // uniform density map
       p.w = wdata;
+#if CYLO_SHAPE == 1
+      // top-hat: (cell_x, cell_y) may not be the cell that holds the particle (helper.F90:752-757)
+      if (gx[1 + WO] > gx[0 + WO]) cell_x = cell_x + 1;
+      if (gy[1 + WO] > gy[0 + WO]) cell_y = cell_y + 1;
+#endif
       npart_in_cell[cidx(cell_x, cell_y)] += 1;
     }
     // second pass: macro-particle volume / particles in cell
@@ -236,30 +223,14 @@ void World::load_uniform(int isp) {
         // uniform temperature/drift: the 3x3 normalised interpolation is restated so the
         // rounding matches (particle_temperature.F90:54-63)
         double part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
-        double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx;
-        double cell_y_r = (part_r - y_grid_min_local) / dy;
-        int cell_x = (int)std::floor(cell_x_r + 0.5);
-        int cell_y = (int)std::floor(cell_y_r + 0.5);
-        double cfx = (double)cell_x - cell_x_r;
-        double cfy = (double)cell_y - cell_y_r;
-        double gx[3], gy[3];
-        double cx2 = cfx * cfx;
-        gx[0] = 0.5 * (0.25 + cx2 + cfx);
-        gx[1] = 0.75 - cx2;
-        gx[2] = 0.5 * (0.25 + cx2 - cfx);
-        double cy2 = cfy * cfy;
-        gy[0] = 0.5 * (0.25 + cy2 + cfy);
-        gy[1] = 0.75 - cy2;
-        gy[2] = 0.5 * (0.25 + cy2 - cfy);
-        if (part_r < dy) {
-          gy[1] = gy[1] + gy[0];
-          gy[0] = 0.0;
-        }
+        int cell_x, cell_y;
+        double gx[NW], gy[NW];
+        particle_to_grid(p.pos[0] - r.x_grid_min_local, part_r - y_grid_min_local, part_r, dx, dy, &cell_x, &cell_y, gx, gy);
         double temp_local = 0.0, drift_local = 0.0;
-        for (int iy = 0; iy < 3; ++iy)
-          for (int ix = 0; ix < 3; ++ix) {
-            temp_local = temp_local + gx[ix] * gy[iy] * s.temp[n];
-            drift_local = drift_local + gx[ix] * gy[iy] * s.drift[n];
+        for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
+          for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+            temp_local = temp_local + gx[ix + WO] * gy[iy + WO] * s.temp[n];
+            drift_local = drift_local + gx[ix + WO] * gy[iy + WO] * s.drift[n];
           }
         double stdev = std::sqrt(temp_local * KB * s.mass);
         p.p[n] = r.rng.box_muller(stdev, drift_local);
@@ -833,7 +804,7 @@ void World::push_rank(Rank& r) {
   r.jrm.zero();
   r.jtm.zero();
 
-  const double fac = 0.25;   // (0.5)**c_ndims, c_ndims = 2 (particles.F90:152)
+  const double fac = SHAPE_FAC;   // particles.F90:145-153: (0.5)**c_ndims for the triangle, c_ndims = 2
   double idx = 1.0 / dx, idy = 1.0 / dy, idt = 1.0 / dt;
   double dto2 = dt / 2.0, dtco2 = c * dto2, dtfac = 0.5 * dt * fac;
   double third = 1.0 / 3.0, sixth = 0.5 * third;
@@ -888,8 +859,8 @@ void World::push_rank(Rank& r) {
       cplx exp_min_itheta_05 = exp_min_itheta;
       cplx exp_itheta_05 = recip(exp_min_itheta_05);
 
-      double cell_x_r = part_x_local * idx;
-      double cell_y_r = part_r_local * idy;
+      double cell_x_r = part_x_local * idx - SHAPE_CELL_SHIFT;   // (top-hat: - 0.5, particles.F90:336-342)
+      double cell_y_r = part_r_local * idy - SHAPE_CELL_SHIFT;
       int cell_x1 = ifloor(cell_x_r + 0.5);
       double cell_frac_x = (double)cell_x1 - cell_x_r;
       cell_x1 = cell_x1 + 1;
@@ -897,17 +868,11 @@ void World::push_rank(Rank& r) {
       double cell_frac_y = (double)cell_y1 - cell_y_r;
       cell_y1 = cell_y1 + 1;
 
-      // arrays indexed -2..2 -> [k+2]
-      double gx[5] = {0, 0, 0, 0, 0}, gy[5] = {0, 0, 0, 0, 0};
-      double hx[5] = {0, 0, 0, 0, 0}, hy[5] = {0, 0, 0, 0, 0};
-      double cf2 = cell_frac_x * cell_frac_x;
-      gx[1] = 0.25 + cf2 + cell_frac_x;
-      gx[2] = 1.5 - 2.0 * cf2;
-      gx[3] = 0.25 + cf2 - cell_frac_x;
-      cf2 = cell_frac_y * cell_frac_y;
-      gy[1] = 0.25 + cf2 + cell_frac_y;
-      gy[2] = 1.5 - 2.0 * cf2;
-      gy[3] = 0.25 + cf2 - cell_frac_y;
+      // arrays indexed -3..3 -> [k + WO] (sf_min-1 : sf_max+1 of the widest shape)
+      double gx[NW] = {0, 0, 0, 0, 0, 0, 0}, gy[NW] = {0, 0, 0, 0, 0, 0, 0};
+      double hx[NW] = {0, 0, 0, 0, 0, 0, 0}, hy[NW] = {0, 0, 0, 0, 0, 0, 0};
+      shape_weights(cell_frac_x, 0, gx);   // <shape>/gx.inc
+      shape_weights(cell_frac_y, 0, gy);
 
       int cell_x2 = ifloor(cell_x_r);
       cell_frac_x = (double)cell_x2 - cell_x_r + 0.5;
@@ -917,27 +882,28 @@ void World::push_rank(Rank& r) {
       cell_y2 = cell_y2 + 1;
 
       int dcellx = 0, dcelly = 0;
-      cf2 = cell_frac_x * cell_frac_x;
-      hx[dcellx + 1] = 0.25 + cf2 + cell_frac_x;
-      hx[dcellx + 2] = 1.5 - 2.0 * cf2;
-      hx[dcellx + 3] = 0.25 + cf2 - cell_frac_x;
-      cf2 = cell_frac_y * cell_frac_y;
-      hy[dcelly + 1] = 0.25 + cf2 + cell_frac_y;
-      hy[dcelly + 2] = 1.5 - 2.0 * cf2;
-      hy[dcelly + 3] = 0.25 + cf2 - cell_frac_y;
+      shape_weights(cell_frac_x, dcellx, hx);   // <shape>/hx_dcell.inc
+      shape_weights(cell_frac_y, dcelly, hy);
 
-      // gather (e_part.inc / b_part.inc).  W(a,b,F,cx,cy): a weights rows (r), b columns (x)
+      // gather (<shape>/e_part.inc, b_part.inc): rows in r weighted by wy, columns in x by wx, summed in the
+      // includes' order (left to right)
       auto gather = [&](const Arr3& F, const double* wy, const double* wx, int cx, int cy, int im) -> cplx {
-        // sum_{iy} wy(iy) * ( wx(-1)*F(cx-1,cy+iy) + wx(0)*F(cx,cy+iy) + wx(1)*F(cx+1,cy+iy) )
-        cplx rows[3];
-        for (int iy = -1; iy <= 1; ++iy) {
-          cplx s = wx[1] * F(cx - 1, cy + iy, im);
-          s = s + wx[2] * F(cx, cy + iy, im);
-          s = s + wx[3] * F(cx + 1, cy + iy, im);
-          rows[iy + 1] = wy[iy + 2] * s;
+        cplx total;
+        for (int iy = SF_MIN; iy <= SF_MAX; ++iy) {
+          cplx sacc = wx[SF_MIN + WO] * F(cx + SF_MIN, cy + iy, im);
+          for (int ix = SF_MIN + 1; ix <= SF_MAX; ++ix) sacc = sacc + wx[ix + WO] * F(cx + ix, cy + iy, im);
+          const cplx row = wy[iy + WO] * sacc;
+          total = (iy == SF_MIN) ? row : total + row;
         }
-        return (rows[0] + rows[1]) + rows[2];
+        return total;
       };
+      // which cell pair each B component is read at: the top-hat include pairs them differently from the other
+      // two (tophat/b_part.inc: bxm at (cell_x1, cell_y2), brm at (cell_x2, cell_y1), btm at (cell_x2, cell_y2))
+#if CYLO_SHAPE == 1
+      const int bx_cx = cell_x1, bx_cy = cell_y2, br_cx = cell_x2, br_cy = cell_y1, bt_cx = cell_x2, bt_cy = cell_y2;
+#else
+      const int bx_cx = cell_x2, bx_cy = cell_y1, br_cx = cell_x1, br_cy = cell_y2, bt_cx = cell_x1, bt_cy = cell_y1;
+#endif
       cplx exp_min_imtheta(1.0);
       double ex_part = 0, er_part = 0, et_part = 0;
       for (int im = 0; im < M; ++im) {
@@ -952,9 +918,9 @@ void World::push_rank(Rank& r) {
       exp_min_imtheta = cplx(1.0);
       double bx_part = 0, br_part = 0, bt_part = 0;
       for (int im = 0; im < M; ++im) {
-        bx_part = bx_part + (exp_min_imtheta * gather(r.bxm, gy, hx, cell_x2, cell_y1, im)).re;
-        br_part = br_part + (exp_min_imtheta * gather(r.brm, hy, gx, cell_x1, cell_y2, im)).re;
-        bt_part = bt_part + (exp_min_imtheta * gather(r.btm, gy, gx, cell_x1, cell_y1, im)).re;
+        bx_part = bx_part + (exp_min_imtheta * gather(r.bxm, gy, hx, bx_cx, bx_cy, im)).re;
+        br_part = br_part + (exp_min_imtheta * gather(r.brm, hy, gx, br_cx, br_cy, im)).re;
+        bt_part = bt_part + (exp_min_imtheta * gather(r.btm, gy, gx, bt_cx, bt_cy, im)).re;
         exp_min_imtheta = exp_min_imtheta * exp_min_itheta;
       }
       double by_part = br_part * exp_min_itheta.re + bt_part * exp_min_itheta.im;
@@ -1022,10 +988,10 @@ void World::push_rank(Rank& r) {
       cplx exp_idtheta = exp_itheta_15 * exp_min_itheta_05;
       double dtheta = theta_15 - theta_05;
 
-      for (int k = 0; k < 5; ++k) { gx[k] = hx[k]; gy[k] = hy[k]; }
+      for (int k = 0; k < NW; ++k) { gx[k] = hx[k]; gy[k] = hy[k]; }
 
-      cell_x_r = part_x_local * idx;
-      cell_y_r = part_r_local * idy;
+      cell_x_r = part_x_local * idx - SHAPE_CELL_SHIFT;
+      cell_y_r = part_r_local * idy - SHAPE_CELL_SHIFT;
       int cell_x3 = ifloor(cell_x_r);
       cell_frac_x = (double)cell_x3 - cell_x_r + 0.5;
       cell_x3 = cell_x3 + 1;
@@ -1033,21 +999,15 @@ void World::push_rank(Rank& r) {
       cell_frac_y = (double)cell_y3 - cell_y_r + 0.5;
       cell_y3 = cell_y3 + 1;
 
-      for (int k = 0; k < 5; ++k) { hx[k] = 0.0; hy[k] = 0.0; }
+      for (int k = 0; k < NW; ++k) { hx[k] = 0.0; hy[k] = 0.0; }
       dcellx = cell_x3 - cell_x2;
       dcelly = cell_y3 - cell_y2;
-      cf2 = cell_frac_x * cell_frac_x;
-      hx[dcellx + 1] = 0.25 + cf2 + cell_frac_x;
-      hx[dcellx + 2] = 1.5 - 2.0 * cf2;
-      hx[dcellx + 3] = 0.25 + cf2 - cell_frac_x;
-      cf2 = cell_frac_y * cell_frac_y;
-      hy[dcelly + 1] = 0.25 + cf2 + cell_frac_y;
-      hy[dcelly + 2] = 1.5 - 2.0 * cf2;
-      hy[dcelly + 3] = 0.25 + cf2 - cell_frac_y;
-      for (int k = 0; k < 5; ++k) { hx[k] = hx[k] - gx[k]; hy[k] = hy[k] - gy[k]; }
+      shape_weights(cell_frac_x, dcellx, hx);
+      shape_weights(cell_frac_y, dcelly, hy);
+      for (int k = 0; k < NW; ++k) { hx[k] = hx[k] - gx[k]; hy[k] = hy[k] - gy[k]; }
 
-      int xmin = -1 + (dcellx - 1) / 2, xmax = 1 + (dcellx + 1) / 2;   // truncating division
-      int ymin = -1 + (dcelly - 1) / 2, ymax = 1 + (dcelly + 1) / 2;
+      int xmin = SF_MIN + (dcellx - 1) / 2, xmax = SF_MAX + (dcellx + 1) / 2;   // truncating division
+      int ymin = SF_MIN + (dcelly - 1) / 2, ymax = SF_MAX + (dcelly + 1) / 2;
 
       double q_weight_fac = part_q * part_weight * fac;
       double fcx = q_weight_fac * idt;
@@ -1084,32 +1044,32 @@ void World::push_rank(Rank& r) {
                                  (exp_imdtheta * ((cplx(-m2dth2) - (2.0 * IMAGI) * mdth) + cplx(2.0)) - cplx(2.0)));
           }
         }
-        cplx jyh[5];
+        cplx jyh[NW];
         for (int iy = ymin; iy <= ymax; ++iy) {
           int cy = cell_y2 + iy;
           cplx w_rt, ym_fac_1;
           if (im == 0) {
-            w_rt = cplx(gy[iy + 2] + 0.5 * hy[iy + 2]);
-            ym_fac_1 = cplx(0.5 * gy[iy + 2] + third * hy[iy + 2]);
+            w_rt = cplx(gy[iy + WO] + 0.5 * hy[iy + WO]);
+            ym_fac_1 = cplx(0.5 * gy[iy + WO] + third * hy[iy + WO]);
           } else {
-            w_rt = m_fac_2 * gy[iy + 2] + m_fac_3 * hy[iy + 2];
-            ym_fac_1 = m_fac_3 * gy[iy + 2] + m_fac_4 * hy[iy + 2];
+            w_rt = m_fac_2 * gy[iy + WO] + m_fac_3 * hy[iy + WO];
+            ym_fac_1 = m_fac_3 * gy[iy + WO] + m_fac_4 * hy[iy + WO];
           }
           double fjx = fcx * T(inv_area_rt_v, cy);
-          double fjy = fcy * hy[iy + 2] * T(inv_area_xt_v, cy);
+          double fjy = fcy * hy[iy + WO] * T(inv_area_xt_v, cy);
           double fjz = fcz * T(inv_volume_v, cy);
           cplx jxh(0.0);
           for (int ix = xmin; ix <= xmax; ++ix) {
             int cx = cell_x2 + ix;
             cplx w_xt;
-            if (im == 0) w_xt = cplx(gx[ix + 2] + 0.5 * hx[ix + 2]);
-            else w_xt = m_fac_2 * gx[ix + 2] + m_fac_3 * hx[ix + 2];
-            cplx w_xr = gx[ix + 2] * w_rt + hx[ix + 2] * ym_fac_1;
-            jxh = jxh - (fjx * hx[ix + 2]) * w_rt;
-            jyh[ix + 2] = jyh[ix + 2] * T(ratio_v, cy) - fjy * w_xt;
+            if (im == 0) w_xt = cplx(gx[ix + WO] + 0.5 * hx[ix + WO]);
+            else w_xt = m_fac_2 * gx[ix + WO] + m_fac_3 * hx[ix + WO];
+            cplx w_xr = gx[ix + WO] * w_rt + hx[ix + WO] * ym_fac_1;
+            jxh = jxh - (fjx * hx[ix + WO]) * w_rt;
+            jyh[ix + WO] = jyh[ix + WO] * T(ratio_v, cy) - fjy * w_xt;
             cplx jzh = fjz * w_xr;
             r.jxm(cx + 1, cy, im) += jxh;
-            r.jrm(cx, cy + 1, im) += jyh[ix + 2];
+            r.jrm(cx, cy + 1, im) += jyh[ix + WO];
             r.jtm(cx, cy, im) += jzh;
           }
         }
@@ -1507,22 +1467,9 @@ void World::density_deposit_and_bcs(int current_species, bool charge) {
       if (spec_sum && species[isp].zero_current) continue;
       for (const Particle& p : r.parts[isp]) {
         const double part_r = std::sqrt(p.pos[1] * p.pos[1] + p.pos[2] * p.pos[2]);
-        const double cell_x_r = (p.pos[0] - r.x_grid_min_local) / dx;
-        const double cell_y_r = (part_r - y_grid_min_local) / dy;
-        int cell_x = (int)std::floor(cell_x_r + 0.5);
-        int cell_y = (int)std::floor(cell_y_r + 0.5);
-        const double cell_frac_x = (double)cell_x - cell_x_r;
-        const double cell_frac_y = (double)cell_y - cell_y_r;
-        cell_x = cell_x + 1;
-        cell_y = cell_y + 1;
-        const double cx2 = cell_frac_x * cell_frac_x;
-        double gx[3] = {0.5 * (0.25 + cx2 + cell_frac_x), 0.75 - cx2, 0.5 * (0.25 + cx2 - cell_frac_x)};
-        const double cy2 = cell_frac_y * cell_frac_y;
-        double gy[3] = {0.5 * (0.25 + cy2 + cell_frac_y), 0.75 - cy2, 0.5 * (0.25 + cy2 - cell_frac_y)};
-        if (part_r < dy) {
-          gy[1] = gy[1] + gy[0];
-          gy[0] = 0.0;
-        }
+        int cell_x, cell_y;
+        double gx[NW], gy[NW];
+        particle_to_grid(p.pos[0] - r.x_grid_min_local, part_r - y_grid_min_local, part_r, dx, dy, &cell_x, &cell_y, gx, gy);
         const double macro_part_volume = 2.0 * PI * dx * dy * part_r;
         const double wdata = charge ? species[isp].charge * p.w : p.w;
         const double part_num_dens = wdata / macro_part_volume;
@@ -1536,10 +1483,10 @@ void World::density_deposit_and_bcs(int current_species, bool charge) {
             exp_imtheta = exp_imtheta * exp_itheta;
             mode_fac = 2.0 * exp_imtheta;
           }
-          for (int iy = -1; iy <= 1; ++iy)
-            for (int ix = -1; ix <= 1; ++ix)
+          for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
+            for (int ix = SF_MIN; ix <= SF_MAX; ++ix)
               r.wk(cell_x + ix, cell_y + iy, im) =
-                  r.wk(cell_x + ix, cell_y + iy, im) + ((gx[ix + 1] * gy[iy + 1]) * part_num_dens) * mode_fac;
+                  r.wk(cell_x + ix, cell_y + iy, im) + ((gx[ix + WO] * gy[iy + WO]) * part_num_dens) * mode_fac;
         }
       }
     }

@@ -33,9 +33,120 @@
 
 namespace cylo {
 
-constexpr int NG = 5;    // constants.F90:544  ng = png + 2 (triangle shape, png = 3)
-constexpr int JNG = 5;   // constants.F90:545
-constexpr int PNG = 3;   // constants.F90:537
+// The particle shape is a compile-time choice of the reference (-DPARTICLE_SHAPE_TOPHAT / _BSPLINE3, else the
+// triangle; constants.F90:524-545) and so it is here: -DCYLO_SHAPE=0 triangle (default), 1 top-hat, 2 third-order
+// B-spline.  It sets the ghost widths -- i.e. the layout of every array -- besides the weights.
+#ifndef CYLO_SHAPE
+#define CYLO_SHAPE 0
+#endif
+#if CYLO_SHAPE == 2
+constexpr int SF_MIN = -2, SF_MAX = 2, PNG = 4;   // constants.F90:526-529
+#elif CYLO_SHAPE == 1
+constexpr int SF_MIN = 0, SF_MAX = 1, PNG = 2;    // constants.F90:530-533
+#else
+constexpr int SF_MIN = -1, SF_MAX = 1, PNG = 3;   // constants.F90:534-537
+#endif
+constexpr int NG = PNG + 2;   // constants.F90:544
+constexpr int JNG = NG;       // constants.F90:545  MAX(ng, png)
+constexpr int WO = 3;         // weight arrays hold offsets -3..3 (sf_min-1 : sf_max+1 of the widest shape): w[k + WO]
+constexpr int NW = 7;
+
+inline double pow4(double x) { const double t = x * x; return t * t; }   // x**4 by repeated squaring
+
+// <shape>/gx.inc and hx_dcell.inc: the UNNORMALISED weights of one direction, placed at shift+sf_min .. shift+sf_max
+// (shift = 0 for gx / gy, dcell for hx / hy).  w[] must be zeroed by the caller where the reference zeroes it.
+inline void shape_weights(double cf, int shift, double* w) {
+#if CYLO_SHAPE == 2
+  const double cf2 = cf * cf;
+  w[shift - 2 + WO] = pow4(0.5 + cf);
+  w[shift - 1 + WO] = 4.75 + 11.0 * cf + 4.0 * cf2 * (1.5 - cf - cf2);
+  w[shift + WO] = 14.375 + 6.0 * cf2 * (cf2 - 2.5);
+  w[shift + 1 + WO] = 4.75 - 11.0 * cf + 4.0 * cf2 * (1.5 + cf - cf2);
+  w[shift + 2 + WO] = pow4(0.5 - cf);
+#elif CYLO_SHAPE == 1
+  w[shift + WO] = 0.5 + cf;
+  w[shift + 1 + WO] = 0.5 - cf;
+#else
+  const double cf2 = cf * cf;
+  w[shift - 1 + WO] = 0.25 + cf2 + cf;
+  w[shift + WO] = 1.5 - 2.0 * cf2;
+  w[shift + 1 + WO] = 0.25 + cf2 - cf;
+#endif
+}
+// the factor the weights above still need per direction pair (particles.F90:145-153)
+#if CYLO_SHAPE == 2
+constexpr double SHAPE_FAC = (1.0 / 24.0) * (1.0 / 24.0);
+#elif CYLO_SHAPE == 1
+constexpr double SHAPE_FAC = 1.0;
+#else
+constexpr double SHAPE_FAC = 0.25;
+#endif
+// top-hat: positions are measured from the cell edge (particles.F90:336-342, 540-546)
+constexpr double SHAPE_CELL_SHIFT = (CYLO_SHAPE == 1) ? 0.5 : 0.0;
+
+// <shape>/gxfac.inc without its fold at the axis: the NORMALISED weights of particle_to_grid.inc, w[k + WO]
+inline void shape_weights_fac(double cf, double* w) {
+#if CYLO_SHAPE == 2
+  const double third = 1.0 / 3.0;
+  const double fac1 = 0.125 * third, fac2 = 0.5 * third, fac3 = 7.1875 * third;   // particle_head.inc
+  const double c2 = cf * cf;
+  w[-2 + WO] = fac1 * pow4(0.5 + cf);
+  w[-1 + WO] = fac2 * (1.1875 + 2.75 * cf + c2 * (1.5 - cf - c2));
+  w[0 + WO] = 0.25 * (fac3 + c2 * (c2 - 2.5));
+  w[1 + WO] = fac2 * (1.1875 - 2.75 * cf + c2 * (1.5 + cf - c2));
+  w[2 + WO] = fac1 * pow4(0.5 - cf);
+#elif CYLO_SHAPE == 1
+  w[0 + WO] = 0.5 + cf;
+  w[1 + WO] = 0.5 - cf;
+#else
+  const double c2 = cf * cf;
+  w[-1 + WO] = 0.5 * (0.25 + c2 + cf);
+  w[0 + WO] = 0.75 - c2;
+  w[1 + WO] = 0.5 * (0.25 + c2 - cf);
+#endif
+}
+// the fold of the radial weights of gxfac.inc for a particle next to the axis
+inline void shape_axis_fold(double part_r, double dy, double* gy) {
+#if CYLO_SHAPE == 2
+  if (part_r < 2.0 * dy) {
+    if (part_r < dy) {
+      gy[0 + WO] = gy[0 + WO] + gy[-1 + WO];
+      gy[1 + WO] = gy[1 + WO] + gy[-2 + WO];
+      gy[-1 + WO] = 0.0;
+      gy[-2 + WO] = 0.0;
+    } else {
+      gy[-1 + WO] = gy[-1 + WO] + gy[-2 + WO];
+      gy[-2 + WO] = 0.0;
+    }
+  }
+#elif CYLO_SHAPE == 1
+  if (part_r < 0.5 * dy) {
+    gy[1 + WO] = 1.0;
+    gy[0 + WO] = 0.0;
+  }
+#else
+  if (part_r < dy) {
+    gy[0 + WO] = gy[0 + WO] + gy[-1 + WO];
+    gy[-1 + WO] = 0.0;
+  }
+#endif
+}
+// include/particle_to_grid.inc: nearest cell, fractions and normalised weights of a particle at (x, r)
+inline void particle_to_grid(double x_local, double r_local, double part_r, double dx, double dy, int* cell_x,
+                             int* cell_y, double* gx, double* gy) {
+  const double cell_x_r = x_local / dx - SHAPE_CELL_SHIFT;
+  const double cell_y_r = r_local / dy - SHAPE_CELL_SHIFT;
+  int cx = (int)std::floor(cell_x_r + 0.5);
+  int cy = (int)std::floor(cell_y_r + 0.5);
+  const double cfx = (double)cx - cell_x_r;
+  const double cfy = (double)cy - cell_y_r;
+  *cell_x = cx + 1;
+  *cell_y = cy + 1;
+  for (int k = 0; k < NW; ++k) { gx[k] = 0.0; gy[k] = 0.0; }
+  shape_weights_fac(cfx, gx);
+  shape_weights_fac(cfy, gy);
+  shape_axis_fold(part_r, dy, gy);
+}
 
 // Boundary-condition codes, constants.F90:55-72
 enum BC {

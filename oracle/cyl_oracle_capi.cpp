@@ -180,6 +180,10 @@ enum Op {
 };
 
 // returns elapsed seconds of the call
+// ghost cells of the arrays of this build (ng = png + 2: the particle shape is compiled in)
+int cylo_ng() { return NG; }
+int cylo_shape() { return CYLO_SHAPE; }
+
 double cylo_call(void* wp, int op) {
   World* w = (World*)wp;
   auto t0 = std::chrono::steady_clock::now();

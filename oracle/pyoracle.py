@@ -12,7 +12,11 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-NG = 5
+# The particle shape is a compile-time choice (cyl_oracle.hpp CYLO_SHAPE, as -DPARTICLE_SHAPE_* is in the reference):
+# CYL_SHAPE = triangle (default) | tophat | bspline3 selects the library of that shape for the whole process, on the
+# oracle's side here and on the product's side in cylindrical_epoch_b200/_lib.py.  ng = png + 2 follows the shape.
+SHAPE = os.environ.get("CYL_SHAPE", "triangle") or "triangle"
+NG = {"triangle": 5, "tophat": 4, "bspline3": 6}[SHAPE]
 # boundary-condition codes (constants.F90:55-72)
 BC_PERIODIC, BC_OTHER, BC_SIMPLE_LASER, BC_SIMPLE_OUTFLOW, BC_OPEN = 1, 2, 3, 4, 5
 BC_ZERO_GRADIENT, BC_CLAMP, BC_REFLECT, BC_CONDUCT, BC_THERMAL = 7, 8, 9, 10, 11
@@ -50,10 +54,10 @@ class CyloConfig(C.Structure):
 
 def build(force=False):
     """Compile oracle/libcyl_oracle.so with the committed Makefile (g++, no FMA contraction)."""
-    so = os.path.join(_HERE, "libcyl_oracle.so")
+    so = os.path.join(_HERE, "libcyl_oracle.so" if SHAPE == "triangle" else f"libcyl_oracle_{SHAPE}.so")
     srcs = [os.path.join(_HERE, f) for f in ("cyl_oracle.cpp", "cyl_moments.cpp", "cyl_philox.cpp", "cyl_oracle_capi.cpp", "cyl_oracle.hpp")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", os.path.basename(so)])
     return so
 
 
@@ -73,6 +77,8 @@ def lib():
         # the test box is usually oversubscribed
         os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
         L = C.CDLL(build())
+        L.cylo_ng.restype = C.c_int
+        assert L.cylo_ng() == NG, (SHAPE, NG, L.cylo_ng())
         L.cylo_create.restype = C.c_void_p
         L.cylo_create.argtypes = [C.POINTER(CyloConfig)]
         L.cylo_destroy.argtypes = [C.c_void_p]

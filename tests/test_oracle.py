@@ -20,7 +20,24 @@ import pytest
 import decks
 from cylindrical_epoch_b200.constants import *  # noqa: F401,F403
 
-NGH = 5
+NGH = po.NG          # ng = png + 2 follows the particle shape the oracle was built for (CYL_SHAPE)
+TRIANGLE = po.SHAPE == "triangle"
+
+
+def stag_weights(c_r):
+    """staggered shape weights of one direction, <shape>/hx_dcell.inc with its factor: (first node, weights)"""
+    if po.SHAPE == "tophat":
+        c_r = c_r - 0.5
+    c2 = math.floor(c_r)
+    f = c2 - c_r + 0.5
+    if po.SHAPE == "tophat":
+        return c2 + 1, [0.5 + f, 0.5 - f]
+    if po.SHAPE == "bspline3":
+        f2 = f * f
+        w = [(0.5 + f) ** 4, 4.75 + 11.0 * f + 4.0 * f2 * (1.5 - f - f2), 14.375 + 6.0 * f2 * (f2 - 2.5),
+             4.75 - 11.0 * f + 4.0 * f2 * (1.5 + f - f2), (0.5 - f) ** 4]
+        return c2 + 1 - 2, [v / 24.0 for v in w]
+    return c2 + 1 - 1, [0.5 * (0.25 + f * f + f), 0.5 * (1.5 - 2 * f * f), 0.5 * (0.25 + f * f - f)]
 
 
 def fidx(ix, ir):
@@ -95,25 +112,20 @@ def test_mode0_deposit_is_exactly_charge_conserving():
         xr = (pos[:, 0] - sc["x_grid_min"]) / dx
         rr = (np.hypot(pos[:, 1], pos[:, 2]) - sc["y_grid_min_local"]) / dy
         for k in range(npart):
-            out = []
-            for c_r in (xr[k], rr[k]):
-                c2 = math.floor(c_r)
-                f = c2 - c_r + 0.5
-                out.append((c2 + 1, [0.25 + f * f + f, 1.5 - 2 * f * f, 0.25 + f * f - f]))
-            (cx2, wx), (cy2, wy) = out
-            for a in range(3):
-                for b in range(3):
-                    Qg[fidx(cx2 - 1 + b, cy2 - 1 + a)] += -Q0 * after[k, 6] * 0.25 * wx[b] * wy[a]
+            (cx0, wx), (cy0, wy) = stag_weights(xr[k]), stag_weights(rr[k])
+            for a in range(len(wy)):
+                for b in range(len(wx)):
+                    Qg[fidx(cx0 + b, cy0 + a)] += -Q0 * after[k, 6] * wx[b] * wy[a]
         return Qg
 
     dQ = (charge(after[:, 0:3] + delta) - charge(after[:, 0:3] - delta)) / dt
     jx = w.field(0, "jxm")[0].real
     jr = w.field(0, "jrm")[0].real
     div = np.zeros_like(dQ)
-    for cy in range(3, ny - 2):
+    for cy in range(4, ny - 3):
         a_rt, a_xt = tabs[cy]
         a_xt_m = tabs[cy - 1][1]
-        for cx in range(3, nx - 2):
+        for cx in range(4, nx - 3):
             div[fidx(cx, cy)] = (a_rt * (jx[fidx(cx + 1, cy)] - jx[fidx(cx, cy)])
                                  + a_xt * jr[fidx(cx, cy + 1)] - a_xt_m * jr[fidx(cx, cy)])
     scale = np.abs(dQ).max()
@@ -263,7 +275,9 @@ def test_cold_plasma_oscillates_at_omega_p():
           if sig[k] * sig[k + 1] < 0]
     assert len(zc) >= 4
     period = 2.0 * np.mean(np.diff(zc))
-    assert abs(period * omega_p / (2.0 * math.pi) - 1.0) < 0.03, period * omega_p / (2.0 * math.pi)
+    # (five zero crossings of a noisy start: the estimate scatters by 1-3 % with the loading -- triangle 0.1 % at 8 ppc
+    # and 1.3 % at 32 ppc, top-hat 3.2 % and 1.6 %)
+    assert abs(period * omega_p / (2.0 * math.pi) - 1.0) < (0.03 if TRIANGLE else 0.04), period * omega_p / (2.0 * math.pi)
 
 
 def _node_charge(pos, weight, q, sc, nx, ny):
@@ -274,15 +288,10 @@ def _node_charge(pos, weight, q, sc, nx, ny):
     xr = (pos[:, 0] - sc["x_grid_min"]) / dx
     rr = (np.hypot(pos[:, 1], pos[:, 2]) - sc["y_grid_min_local"]) / dy
     for k in range(pos.shape[0]):
-        out = []
-        for c_r in (xr[k], rr[k]):
-            c2 = math.floor(c_r)
-            f = c2 - c_r + 0.5
-            out.append((c2 + 1, [0.25 + f * f + f, 1.5 - 2 * f * f, 0.25 + f * f - f]))
-        (cx2, wx), (cy2, wy) = out
-        for a in range(3):
-            for b in range(3):
-                Qg[fidx(cx2 - 1 + b, cy2 - 1 + a)] += q * weight[k] * 0.25 * wx[b] * wy[a]
+        (cx0, wx), (cy0, wy) = stag_weights(xr[k]), stag_weights(rr[k])
+        for a in range(len(wy)):
+            for b in range(len(wx)):
+                Qg[fidx(cx0 + b, cy0 + a)] += q * weight[k] * wx[b] * wy[a]
     return Qg
 
 
@@ -306,10 +315,10 @@ def test_gauss_law_residual_is_frozen():
         Q = 0.5 * (_node_charge(pr[:, 0:3] + delta, pr[:, 6], -Q0, sc, nx, ny) +
                    _node_charge(pr[:, 0:3] - delta, pr[:, 6], -Q0, sc, nx, ny))
         res = np.zeros((ny, nx))
-        for cy in range(3, ny - 3):
+        for cy in range(4, ny - 4):
             a_rt, a_xt = tabs[cy]
             a_xt_m = tabs[cy - 1][1]
-            for cx in range(3, nx - 3):
+            for cx in range(4, nx - 4):
                 flux = (a_rt * (ex[fidx(cx + 1, cy)] - ex[fidx(cx, cy)])
                         + a_xt * er[fidx(cx, cy + 1)] - a_xt_m * er[fidx(cx, cy)])
                 res[cy, cx] = flux - Q[fidx(cx, cy)] / EPSILON0
@@ -349,6 +358,7 @@ def test_rng_and_loader_statistics():
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lwfa_48x16_m2_20steps.npz")
 
 
+@pytest.mark.skipif(not TRIANGLE, reason="the committed vectors are the triangle build's")
 def test_oracle_reproduces_golden_vectors():
     """fixture made by tests/golden/make_golden.py from the oracle itself: guards the restatement
     (and its compiler flags) against drift; the GPU suite checks the CUDA path against the same file"""
@@ -422,6 +432,7 @@ def _doc_single_particle_tables(q):
     return t1, t2, t3, outside
 
 
+@pytest.mark.skipif(not TRIANGLE, reason="the documentation's tables are for the default (triangle) shape")
 def test_documentation_section_6_3_single_particle_tables():
     from scipy.optimize import least_squares
 

@@ -13,6 +13,7 @@ import pytest
 
 import decks
 import pyoracle as po
+import pyoracle
 from pyoracle import NG, BC_PERIODIC, BC_REFLECT, BD_X_MIN, BD_X_MAX, BD_Y_MAX, C_LIGHT, KB, M0, Q0
 
 C_TINY = np.finfo(np.float64).tiny
@@ -182,6 +183,10 @@ def _deck(name):
     return decks.lwfa(nx=24, ny=10, n_mode=2, ppc_e=4, ppc_p=2)
 
 
+TRIANGLE_ONLY = pytest.mark.skipif(pyoracle.SHAPE != "triangle", reason="the numpy restatement in this file is the triangle's")
+
+
+@TRIANGLE_ONLY
 @pytest.mark.parametrize("deck_name", ["thermal", "drift", "lwfa"])
 def test_moments_match_independent_numpy_restatement(deck_name):
     d = _deck(deck_name)
@@ -212,6 +217,7 @@ def test_species_sum_skips_tracers_and_adds_the_rest():
     assert np.abs(rho - d.species[0].charge * nd).max() <= 1e-13 * np.abs(rho).max()
 
 
+@TRIANGLE_ONLY
 def test_known_answers_of_a_uniform_thermal_load():
     T, n0 = 1.16e7, 1.0e24
     d = decks.thermal(nx=48, ny=24, n_mode=1, ppc=64, temp_k=T, density=n0)
@@ -269,6 +275,8 @@ def test_known_answers_of_a_cold_drifting_beam():
     assert abs(px / (M0 * g * v) - 1.0) < 1e-12
 
 
+@pytest.mark.skipif(pyoracle.SHAPE == "tophat", reason="top-hat: calc_ppc counts into ghost cells that nothing sums "
+                    "back (calc_df.F90:696-706 has no calc_boundary), so it depends on the decomposition in the reference too")
 @pytest.mark.parametrize("deck_name", ["thermal", "lwfa"])
 def test_two_slabs_give_the_one_slab_answer(deck_name):
     d = _deck(deck_name)
