@@ -3,8 +3,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CYLGPU_LIB: an alternative build of the same library (kernel-tuning experiments)
-LIB_PATH = os.environ.get("CYLGPU_LIB") or os.path.join(_HERE, "libcylgpu.so")
+from .constants import NG, SHAPE
+
+# CYL_SHAPE: the library of that particle shape (constants.py); CYLGPU_LIB: an alternative build of the same library
+# (kernel-tuning experiments)
+LIB_PATH = os.environ.get("CYLGPU_LIB") or os.path.join(
+    _HERE, "libcylgpu.so" if SHAPE == "triangle" else f"libcylgpu_{SHAPE}.so")
 MAX_SPECIES = 8
 
 SENDRECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_int,
@@ -112,6 +116,8 @@ SYMBOLS = {
     "cylgpu_set_taylor_switch": (C.c_int, [H, C.c_double]),
     "cylgpu_set_sort_interval": (C.c_int, [H, C.c_int]),
     "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
+    "cylgpu_shape": (C.c_int, []),
+    "cylgpu_ghost_cells": (C.c_int, []),
     "cylgpu_number_density_modes": (C.c_int, [H, C.c_int, C.c_void_p]),
     "cylgpu_charge_density": (C.c_int, [H, C.c_int, C.c_void_p]),
     "cylgpu_insert_particles_device": (C.c_int, [H, C.c_int, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -182,12 +188,14 @@ def load():
         return _LIB
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
-            f"{LIB_PATH} is missing: build it with `python -m cylindrical_epoch_b200.build` "
+            f"{LIB_PATH} is missing: build it with `python -m cylindrical_epoch_b200.build [--shape=...]` "
             "(there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)   # AttributeError if the .so does not export it
         fn.restype = res
         fn.argtypes = args
+    if lib.cylgpu_ghost_cells() != NG:
+        raise RuntimeError(f"{LIB_PATH} was built for ng = {lib.cylgpu_ghost_cells()}, CYL_SHAPE = {SHAPE} needs ng = {NG}")
     _LIB = lib
     return lib

@@ -1,5 +1,11 @@
 """Constants shared with the reference (constants.F90:55-72,171-201,526-548)."""
-NG = 5            # ng = jng = png + 2 for the triangle shape
+import os as _os
+
+# The particle shape is a compile-time choice of the reference and of the library (csrc/shape.cuh): CYL_SHAPE =
+# triangle (default) | tophat | bspline3 selects the library of that shape for the whole process (_lib.py).
+# ng = jng = png + 2 follows the shape (constants.F90:524-545): the layout of every array that crosses the C-ABI.
+SHAPE = _os.environ.get("CYL_SHAPE", "triangle") or "triangle"
+NG = {"triangle": 5, "tophat": 4, "bspline3": 6}[SHAPE]
 # boundary-condition codes
 BC_PERIODIC, BC_OTHER, BC_SIMPLE_LASER, BC_SIMPLE_OUTFLOW, BC_OPEN = 1, 2, 3, 4, 5
 BC_ZERO_GRADIENT, BC_CLAMP, BC_REFLECT, BC_CONDUCT, BC_THERMAL = 7, 8, 9, 10, 11

@@ -477,7 +477,18 @@ int cylgpu_sort_particles(cylgpu_handle c) { TRY(check_handle(c)); return do_sor
 int cylgpu_set_taylor_switch(cylgpu_handle c, double v) { TRY(check_handle(c)); c->taylor_switch = v; return 0; }
 int cylgpu_set_pusher(cylgpu_handle c, int higuera_cary) { TRY(check_handle(c)); c->hc_push = higuera_cary != 0; return 0; }
 int cylgpu_set_sort_interval(cylgpu_handle c, int n) { TRY(check_handle(c)); c->sort_interval = n; return 0; }
-int cylgpu_set_push_variant(cylgpu_handle c, int v) { TRY(check_handle(c)); c->push_variant = v; return 0; }
+int cylgpu_set_push_variant(cylgpu_handle c, int v) {
+  TRY(check_handle(c));
+  if (v < 0 || v > 4) { set_error("push variant must be 0..4"); return 2; }
+#if CYL_SHAPE != 0
+  if (v != 4) { set_error("this build (particle shape %d) only has the generic push kernel (variant 4)", CYL_SHAPE); return 2; }
+#endif
+  c->push_variant = v;
+  return 0;
+}
+// the particle shape this library was built for (0 triangle, 1 top-hat, 2 third-order B-spline) and its ng
+int cylgpu_shape(void) { return CYL_SHAPE; }
+int cylgpu_ghost_cells(void) { return NG; }
 
 // Run one field phase: directly, or -- once its parameters have been the same for three calls and
 // the transport can be captured (none / NCCL) -- as a replayed CUDA graph, so that the ~15 short

@@ -413,6 +413,13 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
   if (i >= n) return;
   const double Y = y[i], Z = z[i];
   const double part_r = sqrt(Y * Y + Z * Z);
+#if CYL_SHAPE != 0
+  int cell_x, cell_y;
+  double gx[NWT], gy[NWT];
+  shape_particle_to_grid(x[i] - x_grid_min_local, part_r - y_grid_min_local, part_r, dx, dy, &cell_x, &cell_y, gx, gy);
+  constexpr int G0 = WO;
+#else
+  constexpr int G0 = 1;
   const double cell_x_r = (x[i] - x_grid_min_local) / dx;
   const double cell_y_r = (part_r - y_grid_min_local) / dy;
   int cell_x = (int)floor(cell_x_r + 0.5);
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
     gy[1] = gy[1] + gy[0];
     gy[0] = 0.0;
   }
+#endif
   const double part_num_dens = (wfac * w[i]) / (2.0 * PI * dx * dy * part_r);   // wfac = 1, or the charge (calc_df.F90:479)
   const cplx exp_itheta = C(Y, Z) / part_r;
   cplx exp_imtheta = C(1.0, 0.0);
@@ -439,10 +447,10 @@ __global__ void __launch_bounds__(256) k_number_density(Geom g, const double* __
       mode_fac = 2.0 * exp_imtheta;
     }
 #pragma unroll
-    for (int iy = -1; iy <= 1; ++iy)
+    for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
 #pragma unroll
-      for (int ix = -1; ix <= 1; ++ix) {
-        const double v = (gx[ix + 1] * gy[iy + 1]) * part_num_dens;
+      for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+        const double v = (gx[ix + G0] * gy[iy + G0]) * part_num_dens;
         if (v == 0.0) continue;
         const size_t o = 2 * g.at(cell_x + ix, cell_y + iy, im);
         atomicAdd(out + o, v * mode_fac.x);

@@ -230,7 +230,7 @@ struct cylgpu_ctx {
   bool hc_push = false;           // Higuera-Cary instead of Boris (the reference's -DHC_PUSH build)
   // 0 per-particle REDs, 1 warp-window shuffle deposit, 2 strip CTAs + shared-memory field patch,
   // 3 strip CTAs + DMMA outer-product deposit
-  int push_variant = 3;
+  int push_variant = (CYL_SHAPE == 0) ? 3 : 4;   // 4: the generic per-particle kernel of push_shapes.cuh
   int64_t pushes_since_sort = 0;
   bool sorted_valid = false;
 

@@ -8,9 +8,20 @@
 #include <stddef.h>
 #include <stdint.h>
 
-#define NG 5     // constants.F90:544
-#define JNG 5    // constants.F90:545
+// The particle shape is a compile-time choice of the reference and of this library (shape.cuh): -DCYL_SHAPE=0
+// triangle (default), 1 top-hat, 2 third-order B-spline.  It sets the ghost widths, constants.F90:524-545.
+#ifndef CYL_SHAPE
+#define CYL_SHAPE 0
+#endif
+#if CYL_SHAPE == 2
+#define PNG 4
+#elif CYL_SHAPE == 1
+#define PNG 2
+#else
 #define PNG 3    // constants.F90:537
+#endif
+#define NG (PNG + 2)   // constants.F90:544
+#define JNG NG         // constants.F90:545  MAX(ng, png)
 #define CELL_PAD 3   // ghost cells on each side covered by the particle sort buckets
 
 namespace cylgpu {
@@ -45,6 +56,8 @@ struct Geom {
     return ((size_t)im * SY + (size_t)(ir + NG - 1)) * SX + (size_t)(ix + NG - 1);
   }
 };
+
+#include "shape.cuh"
 
 // particle_bcs with device-resident counts (compact_kernels.cuh): the plan of one compaction and the per-step
 // statistics kept on the device

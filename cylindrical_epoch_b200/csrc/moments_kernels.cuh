@@ -13,9 +13,18 @@ struct MomentArgs {
   int kind, direction;
 };
 
-struct ToGrid {   // include/particle_to_grid.inc + triangle/gxfac.inc
+#if CYL_SHAPE == 0
+#define GW0 1        // index of offset 0 in the weight arrays below
+#else
+#define GW0 WO
+#endif
+struct ToGrid {   // include/particle_to_grid.inc + <shape>/gxfac.inc
   int cell_x, cell_y;
+#if CYL_SHAPE == 0
   double gx[3], gy[3];
+#else
+  double gx[NWT], gy[NWT];
+#endif
   double part_r;
 };
 
@@ -23,6 +32,11 @@ __device__ __forceinline__ ToGrid particle_to_grid(const MomentArgs& a, int64_t 
   ToGrid t;
   const double Y = a.y[i], Z = a.z[i];
   t.part_r = sqrt(Y * Y + Z * Z);
+#if CYL_SHAPE != 0
+  shape_particle_to_grid(a.x[i] - a.x_grid_min_local, t.part_r - a.y_grid_min_local, t.part_r, a.dx, a.dy, &t.cell_x,
+                         &t.cell_y, t.gx, t.gy);
+  return t;
+#else
   const double cell_x_r = (a.x[i] - a.x_grid_min_local) / a.dx;
   const double cell_y_r = (t.part_r - a.y_grid_min_local) / a.dy;
   t.cell_x = (int)floor(cell_x_r + 0.5);
@@ -44,6 +58,7 @@ __device__ __forceinline__ ToGrid particle_to_grid(const MomentArgs& a, int64_t 
     t.gy[0] = 0.0;
   }
   return t;
+#endif
 }
 
 // mass density, number density, per-species current (re only); ekbar, ekflux, average momentum
@@ -98,10 +113,10 @@ __global__ void __launch_bounds__(256) k_moment_deposit(Geom g, MomentArgs a, do
     default: return;
   }
 #pragma unroll
-  for (int iy = -1; iy <= 1; ++iy)
+  for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
 #pragma unroll
-    for (int ix = -1; ix <= 1; ++ix) {
-      const double gg = t.gx[ix + 1] * t.gy[iy + 1];
+    for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+      const double gg = t.gx[ix + GW0] * t.gy[iy + GW0];
       if (gg == 0.0) continue;
       const size_t o = 2 * g.at(t.cell_x + ix, t.cell_y + iy, 0);
       atomicAdd(out + o, gg * wdata);
@@ -115,8 +130,9 @@ __global__ void __launch_bounds__(256) k_moment_count(Geom g, MomentArgs a, doub
   if (i >= a.n) return;
   const double Y = a.y[i], Z = a.z[i];
   const double part_r = sqrt(Y * Y + Z * Z);
-  const double cell_x_r = (a.x[i] - a.x_grid_min_local) / a.dx + 0.5;
-  const double cell_y_r = (part_r - a.y_grid_min_local) / a.dy + 0.5;
+  // (top-hat: without the half cell, calc_df.F90:696-702, 757-763)
+  const double cell_x_r = (a.x[i] - a.x_grid_min_local) / a.dx + (0.5 - SHAPE_CELL_SHIFT);
+  const double cell_y_r = (part_r - a.y_grid_min_local) / a.dy + (0.5 - SHAPE_CELL_SHIFT);
   const int cell_x = (int)floor(cell_x_r) + 1;
   const int cell_y = (int)floor(cell_y_r) + 1;
   const size_t o = 2 * g.at(cell_x, cell_y, 0);
@@ -139,10 +155,10 @@ __global__ void __launch_bounds__(256) k_temperature_means(Geom g, MomentArgs a,
   const double pmx = a.px[i] / sqrt_part_m, pmy = a.py[i] / sqrt_part_m, pmz = a.pz[i] / sqrt_part_m;
   const int dir = a.direction;
 #pragma unroll
-  for (int iy = -1; iy <= 1; ++iy)
+  for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
 #pragma unroll
-    for (int ix = -1; ix <= 1; ++ix) {
-      const double gf = t.gx[ix + 1] * t.gy[iy + 1] * part_w;
+    for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+      const double gf = t.gx[ix + GW0] * t.gy[iy + GW0] * part_w;
       if (gf == 0.0) continue;
       const size_t o = 2 * g.at(t.cell_x + ix, t.cell_y + iy, 0);
       if (dir <= 0 || dir == 1) atomicAdd(A + o, gf * pmx);
@@ -176,10 +192,10 @@ __global__ void __launch_bounds__(256) k_temperature_sigma(Geom g, MomentArgs a,
   const double pmx = a.px[i] / sqrt_part_m, pmy = a.py[i] / sqrt_part_m, pmz = a.pz[i] / sqrt_part_m;
   const int dir = a.direction;
 #pragma unroll
-  for (int iy = -1; iy <= 1; ++iy)
+  for (int iy = SF_MIN; iy <= SF_MAX; ++iy)
 #pragma unroll
-    for (int ix = -1; ix <= 1; ++ix) {
-      const double gf = t.gx[ix + 1] * t.gy[iy + 1];
+    for (int ix = SF_MIN; ix <= SF_MAX; ++ix) {
+      const double gf = t.gx[ix + GW0] * t.gy[iy + GW0];
       if (gf == 0.0) continue;
       const size_t o = g.at(t.cell_x + ix, t.cell_y + iy, 0);
       const cplx ma = A[o], mb = B[o];

@@ -47,6 +47,7 @@ int build_tables(cylgpu_ctx* c) {
 }
 
 #include "push_v0.cuh"
+#include "push_shapes.cuh"
 
 // ------------------------------------------------------------------------------------------
 // variant 1: warp-window deposit.
@@ -484,8 +485,8 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   const Geom& g = c->g;
   // strip kernels read through the sort permutation and write the second buffer set: the sort
   // then only has to build the permutation (no scatter passes)
-  const bool strips = c->push_variant >= 2 && c->sort_interval == 1;
-  const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
+  const bool strips = (c->push_variant == 2 || c->push_variant == 3) && c->sort_interval == 1;
+  const double fac = SHAPE_FAC;   // particles.F90:145-153: (0.5)**c_ndims for the triangle
   const double dt = c->dt;
   cylgpu::SpeciesState& S = c->species[isp];
   if (fused_out) *fused_out = false;
@@ -549,7 +550,8 @@ static int push_species(cylgpu_ctx* c, int isp, bool need_sort, bool time_kernel
   } while (0)
 #define LAUNCH_M(MM)                                                                                       \
   do {                                                                                                     \
-    if (strips && c->push_variant == 3) LAUNCH_STRIP(MM, true);                                            \
+    if (c->push_variant == 4) k_push_generic<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);         \
+    else if (strips && c->push_variant == 3) LAUNCH_STRIP(MM, true);                                       \
     else if (strips) LAUNCH_STRIP(MM, false);                                                              \
     else if (c->push_variant >= 1) k_push_v1<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);         \
     else k_push_v0<MM><<<(unsigned)nb, 128, 0, c->stream>>>(PUSH_ARGS);                                   \
@@ -1084,7 +1086,7 @@ static int ensure_side(cylgpu_ctx* c) {
 }
 
 int presort_fork(cylgpu_ctx* c) {
-  if (c->presorted || c->xcap <= 0 || c->push_variant < 2 || c->sort_interval != 1 || c->pending_remove) return 0;
+  if (c->presorted || c->xcap <= 0 || (c->push_variant != 2 && c->push_variant != 3) || c->sort_interval != 1 || c->pending_remove) return 0;
   // Worth it only where the field phase is latency: a slab of ~1 M cell-modes (C3 over 8 GPUs: 3.73 against 3.81 ms
   // per step).  On a big slab both are bandwidth and overlapping them gains nothing (measured on C3 at 1 and 2
   // GPUs: 24.9 / 13.0 ms per step either way).  CYLGPU_PRESORT=0/1 overrides.

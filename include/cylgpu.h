@@ -264,8 +264,16 @@ int cylgpu_set_taylor_switch(cylgpu_handle h, double threshold);
 /* cell-tile sort of the SoA arrays (no reference counterpart: replaces the linked list) */
 int cylgpu_sort_particles(cylgpu_handle h);
 int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = never */
-/* 0 = one thread per particle, global atomics; 1 = cell-tile kernel (default) */
+/* 0 = one thread per particle, reductions at L2; 1 = warp-window reduce-scatter; 2 = strip CTAs; 3 = strip CTAs with
+ * the FP64 tensor-op deposit (default); 4 = the shape-generic per-particle kernel (csrc/push_shapes.cuh), the only
+ * one in the top-hat / B-spline builds */
 int cylgpu_set_push_variant(cylgpu_handle h, int variant);
+/* The particle shape is a compile-time choice of the reference (-DPARTICLE_SHAPE_TOPHAT / _BSPLINE3, constants.F90:
+ * 524-545) and of this library (-DCYL_SHAPE=1 / 2: libcylgpu_tophat.so, libcylgpu_bspline3.so): it sets ng = png + 2,
+ * i.e. the layout (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1) of every array that crosses this interface.  cylgpu_shape: 0
+ * triangle, 1 top-hat, 2 third-order B-spline; cylgpu_ghost_cells: ng (5, 4, 6). */
+int cylgpu_shape(void);
+int cylgpu_ghost_cells(void);
 
 /* calc_number_density_modes (calc_df.F90:588-661) of one species (ispecies >= 0) or of all
  * current-carrying species (ispecies < 0), computed from the device-resident lists including

@@ -21,6 +21,7 @@ namespace cylgpu {
 #include "../../cylindrical_epoch_b200/csrc/moments_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/insert_kernel.cuh"
 #include "../../cylindrical_epoch_b200/csrc/push_v0.cuh"
+#include "../../cylindrical_epoch_b200/csrc/push_shapes.cuh"
 #include "../../cylindrical_epoch_b200/csrc/pbcs_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/compact_kernels.cuh"
 #include "../../cylindrical_epoch_b200/csrc/field_kernels.cuh"
@@ -255,6 +256,10 @@ EMUL_API int emul_moment_two_slabs(const int* nx2, int ny, int kind, int directi
 }
 
 // push_particles without particle_bcs for one species of one slab (cylgpu_push_no_bcs with push variant 0):
+static int g_push_generic = 0;
+EMUL_API void emul_set_push_generic(int on) { g_push_generic = on; }
+EMUL_API int emul_ghost_cells() { return NG; }
+
 // the radial tables of particles.cu::build_tables, the PushConst of push_species, k_push_v0<M> over the list
 // and k_r_min_final.  fields: the six E/B mode arrays, jx/jr/jt: zeroed J arrays to deposit into (complex,
 // with ghosts); soa: 7 arrays of n doubles, updated in place.
@@ -285,7 +290,7 @@ EMUL_API int emul_push_v0(int nx, int ny, int M, const void* const* fields6, voi
       ratio[iy + JNG] = xt[iy + JNG] / xt[iy + JNG - 1];
     }
   }
-  const double fac = 0.25;   // (0.5)**c_ndims, particles.F90:152
+  const double fac = SHAPE_FAC;   // particles.F90:145-153
   PushConst P;
   P.g = g;
   P.exm = (const cplx*)fields6[0]; P.erm = (const cplx*)fields6[1]; P.etm = (const cplx*)fields6[2];
@@ -307,7 +312,14 @@ EMUL_API int emul_push_v0(int nx, int ny, int M, const void* const* fields6, voi
   P.taylor_switch = taylor_switch;   // 1.0e-4 (particles.F90:593) unless the conditioning test moves it
   P.hc_alpha = 0.5 * charge * dt / mass;
   const dim3 grid((unsigned)((n + 127) / 128)), block(128);
-#define EMUL_V0(MM) emul_launch(k_push_v0<MM>, grid, block, P, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5], (const double*)soa[6], n)
+  // push variant 4 (push_shapes.cuh) where asked for, and always in the builds of the other particle shapes
+#define EMUL_V0(MM)                                                                                                   \
+  do {                                                                                                                \
+    if (CYL_SHAPE != 0 || g_push_generic)                                                                             \
+      emul_launch(k_push_generic<MM>, grid, block, P, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5], (const double*)soa[6], n); \
+    else                                                                                                              \
+      emul_launch(k_push_v0<MM>, grid, block, P, soa[0], soa[1], soa[2], soa[3], soa[4], soa[5], (const double*)soa[6], n); \
+  } while (0)
   switch (M) {
     case 1: EMUL_V0(1); break;
     case 2: EMUL_V0(2); break;

@@ -7,6 +7,7 @@ import numpy as np
 import cylindrical_epoch_b200 as ce
 from cylindrical_epoch_b200.constants import FIELD_NAMES, TRANSPORT_FABRIC, TRANSPORT_NONE
 import decks
+import pyoracle as po
 
 # Relative tolerance (max-norm, relative to the array's max magnitude) on fields, currents and
 # particle phase space: deposit summation order differs (atomics) and nvcc contracts FMAs.
@@ -57,7 +58,8 @@ class Pair:
             decks.copy_state(self.oracle, s, k)
             s.rng_set_state(*self.oracle.rng_state(k))   # the loader's stream continues in the product
             if variant is not None:
-                s.set_push_variant(variant)
+                # (the top-hat / B-spline builds, CYL_SHAPE, only have the generic kernel: variant 4)
+                s.set_push_variant(variant if po.SHAPE == "triangle" else 4)
             if sort_interval is not None:
                 s.set_sort_interval(sort_interval)
             if smoothing is not None:
@@ -188,8 +190,9 @@ class Pair:
                 info = self.oracle.rank_info(k)
                 sc = self.oracle.scalars()
                 r = np.sqrt(ref[:, 1] ** 2 + ref[:, 2] ** 2)
-                cx = np.floor((ref[:, 0] - info["x_grid_min_local"]) / sc["dx"] + 1.5).astype(np.int32)
-                cy = np.floor((r - sc["y_grid_min_local"]) / sc["dy"] + 1.5).astype(np.int32)
+                half = 0.0 if po.SHAPE == "tophat" else 0.5      # split_particle.F90:57-63
+                cx = np.floor((ref[:, 0] - info["x_grid_min_local"]) / sc["dx"] + 1.0 + half).astype(np.int32)
+                cy = np.floor((r - sc["y_grid_min_local"]) / sc["dy"] + 1.0 + half).astype(np.int32)
                 got = s.download_particles(isp)
                 cells = s.particle_cells(isp)
                 o_ref = np.lexsort((ref[:, 0], ref[:, 6]))

@@ -32,7 +32,7 @@ def test_field_solver_vacuum_laser():
         p.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_lwfa_steps(variant):
     d = decks.lwfa(nx=96, ny=32, n_mode=2, ppc_e=4, ppc_p=1)
     p = Pair(d, variant=variant)
@@ -50,7 +50,7 @@ def test_lwfa_steps(variant):
         p.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_thermal_periodic_reflect(variant):
     d = decks.thermal(nx=64, ny=32, n_mode=2, ppc=8)
     p = Pair(d, variant=variant)
@@ -174,10 +174,10 @@ def test_sparse_plasma_multi_window(variant, ppc):
 
 
 def test_variants_agree_on_current():
-    """all four deposit implementations produce the same J from the same particles (1e-12 of |J|max)"""
+    """all five deposit implementations produce the same J from the same particles (1e-12 of |J|max)"""
     d = decks.thermal(nx=48, ny=24, n_mode=3, ppc=9, temp_k=5e8)
     js = []
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         p = Pair(d, init_half_step=False, variant=variant)
         try:
             p.slabs[0].push_particles_no_bcs()
@@ -186,7 +186,7 @@ def test_variants_agree_on_current():
             p.close()
     for k in range(3):
         den = np.abs(js[0][k]).max()
-        for v in range(1, 4):
+        for v in range(1, 5):
             assert np.abs(js[v][k] - js[0][k]).max() <= 1e-12 * den, (k, v)
 
 

@@ -25,8 +25,10 @@ CASES = [("mass_density", 0), ("number_density", 0), ("ekbar", 0), ("ekflux", 1)
 
 @pytest.fixture(scope="module")
 def emul():
-    subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s"])
-    L = C.CDLL(os.path.join(HERE, "emul", "libemul_kernels.so"))
+    name = "libemul_kernels.so" if po.SHAPE == "triangle" else f"libemul_kernels_{po.SHAPE}.so"   # (csrc/shape.cuh)
+    subprocess.check_call(["make", "-C", os.path.join(HERE, "emul"), "-s", name])
+    L = C.CDLL(os.path.join(HERE, "emul", name))
+    assert L.emul_ghost_cells() == po.NG
     L.emul_particle_moment.restype = C.c_int
     L.emul_particle_moment.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_double), C.POINTER(C.c_double),
@@ -726,8 +728,13 @@ class EmulSlab:
         self.fields_final(w)
 
 
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("deck_name,steps,tol", [("lwfa", 40, 1e-10), ("drift", 12, 1e-6), ("thermal", 12, 1e-6)])
-def test_whole_steps_from_the_product_kernels_track_the_oracle(emul, deck_name, steps, tol):
+def test_whole_steps_from_the_product_kernels_track_the_oracle(emul, deck_name, steps, tol, generic):
+    """generic: push variant 4, the shape-generic per-particle kernel of csrc/push_shapes.cuh (the only push kernel of
+    the top-hat / B-spline builds, which this file also runs under CYL_SHAPE) instead of k_push_v0"""
+    emul.emul_set_push_generic.restype = None
+    emul.emul_set_push_generic(int(generic))
     d = {"lwfa": lambda: decks.lwfa(nx=48, ny=16, n_mode=2, ppc_e=4, ppc_p=1, t_centre=8e-15),
          "drift": lambda: decks.drift(nx=24, ny=12, n_mode=2),
          # the shape of BASELINE.json configs[1]: periodic x, reflecting r_max with zero_b, thermal, m = 0..1
@@ -923,7 +930,7 @@ def test_wide_field_phases_match_the_exchanged_ones(emul, deck_name, nranks):
             sp.bc_particle = (po.BC_REFLECT, po.BC_REFLECT, po.BC_OPEN, po.BC_REFLECT)
     w = decks.make_oracle(d, nranks=nranks)
     w.call("init_half_step")
-    w.step(30 if deck_name == "lwfa" else 6)      # the pulse has crossed the first slab boundary
+    w.step(45 if deck_name == "lwfa" else 6)      # the pulse has crossed the slab boundaries
     worst = 0.0
     for step in range(6):
         for phase in (0, 1):
@@ -973,7 +980,7 @@ def test_wide_final_phase_before_a_window_shift(emul):
             break
         w.step(1)
     assert w.scalars()["window_shifts_total"] >= 3
-    NG = 5
+    NG = po.NG
     shifted = 0
     for step in range(14):
         w.call("fields_half")

@@ -24,3 +24,17 @@ def test_oracle_pins_hold_for_the_shape(shape):
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
     assert int(tail.split(" passed")[0].split()[-1]) >= 13, tail
+
+
+@pytest.mark.parametrize("shape", ["tophat", "bspline3"])
+def test_product_kernels_of_the_shape_track_its_oracle(shape):
+    """tests/test_kernel_emulation.py under CYL_SHAPE: the product's kernel sources compiled for the shape
+    (-DCYL_SHAPE, csrc/shape.cuh, csrc/push_shapes.cuh) and run on the CPU against the oracle build of the same shape --
+    whole steps from the generic push kernel (laser-plasma deck to 1e-10), the nine particle moments, number and
+    charge density, particle_bcs, the field kernels with ng = 4 / 6, the communication-avoiding field phases."""
+    env = dict(os.environ, CYL_SHAPE=shape)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_kernel_emulation.py"), "-q", "-x",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=ROOT, env=env, timeout=1500)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
+    assert int(tail.split(" passed")[0].split()[-1]) >= 60, tail
