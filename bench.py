@@ -70,10 +70,18 @@ def algorithmic_bytes_per_particle_step(n_mode, ppc):
     return 104.0 + 144.0 * n_mode / ppc
 
 
+def ce_shape():
+    """particle shape of the library in use (CYL_SHAPE: triangle unless a top-hat / B-spline build is selected)"""
+    from cylindrical_epoch_b200.constants import SHAPE
+    return SHAPE
+
+
 def committed_ncu(workload):
     """ncu --set full capture of the dominant kernel on this workload, committed under profiles/
     (bench.py cannot run under a profiler): DRAM traffic per launch and the pipe utilisations
     that explain the roofline fraction."""
+    if ce_shape() != "triangle":
+        return None
     try:
         with open(os.path.join(ROOT, "profiles", "push_kernel_ncu.json")) as f:
             d = json.load(f)
@@ -433,7 +441,8 @@ def run_ours(args, wl_name, wl):
         ncu = committed_ncu(wl_name)
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu["dram_bytes_per_launch"] if ncu else None, "peak_source": peak_kind,
-                "kernel": "k_push_v2 (strip CTAs: gather + Boris + DMMA deposit)",
+                "kernel": ("k_push_v2 (strip CTAs: gather + Boris + DMMA deposit)" if ce_shape() == "triangle" else
+                           "k_push_generic (one thread per particle, %s shape: gather + Boris + deposit by L2 reductions)" % ce_shape()),
                 "algorithmic_bytes_per_launch": bp * per_launch,
                 "binding_pipes_from_ncu": ({k: ncu[k] for k in ncu if k not in ("workload", "dram_bytes_per_launch")}
                                            if ncu else None),
@@ -448,7 +457,7 @@ def run_ours(args, wl_name, wl):
         "metric": "particle-steps/sec (push+gather+deposit)", "value": value, "unit": "particle-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl_name, "grid_global": [nxg, ny], "grid_per_gpu": [nx, ny], "n_mode": M, "ppc": ppc,
+        "config": {"workload": wl_name, "particle_shape": ce_shape(), "grid_global": [nxg, ny], "grid_per_gpu": [nx, ny], "n_mode": M, "ppc": ppc,
                    "particles_per_gpu": n0, "dt_multiplier": wl.get("dt_multiplier", 0.95),
                    "decomposition": f"{world} x-slabs, " + ("open ends, moving window (%d shifts in the timed steps)"
                                                             % (slab.window_shifts_total - shifts0) if lwfa

@@ -38,7 +38,30 @@ def calculate_breaks(lib, load, nproc):
     maxs = (C.c_int32 * nproc)()
     if lib.cylgpu_calculate_breaks(a.ctypes.data, sz, nproc, mins, maxs) != 0:
         raise RuntimeError(lib.cylgpu_last_error().decode())
-    return [(int(mins[p]), int(maxs[p])) for p in range(nproc)]
+    return widen_narrow_slabs([(int(mins[p]), int(maxs[p])) for p in range(nproc)], sz)
+
+
+def widen_narrow_slabs(bounds, sz, width=2 * NG):
+    """The reference lets a slab shrink to ncell_min = (png + 1) / 2 + 1 cells (constants.F90:548); a handle needs
+    two halos' worth of columns (cylgpu_create: nx >= 2 ng).  Breaks that cut narrower are moved with the
+    reference's own backwards / forwards passes (balance.F90:2572-2577, 2646-2651) at that width -- the one place
+    where the slabs may differ from the reference's, and only where it would cut below 2 ng columns."""
+    n = len(bounds)
+    if n * width > sz:
+        raise RuntimeError(f"{sz} columns cannot hold {n} slabs of at least {width}")
+    mx = [hi for _, hi in bounds]
+    o = sz
+    for p in range(n - 2, -1, -1):
+        if o - mx[p] < width:
+            mx[p] = o - width
+        o = mx[p]
+    o = 0
+    for p in range(n - 1):
+        if mx[p] - o < width:
+            mx[p] = o + width
+        o = mx[p]
+    mx[n - 1] = sz
+    return [(1 if p == 0 else mx[p - 1] + 1, mx[p]) for p in range(n)]
 
 
 def global_load_x(column_counts, bounds, nx_global, ny_global):

@@ -17,7 +17,11 @@ __global__ void __launch_bounds__(256) k_load_x(const double* __restrict__ x, in
                                                 double idx, int nx, unsigned long long* __restrict__ load) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+#if CYL_SHAPE == 1   // balance.F90:2470-2473
+  int cell = (int)floor((x[i] - x_grid_min_local) * idx) + 1;
+#else
   int cell = (int)floor((x[i] - x_grid_min_local) * idx + 1.5);
+#endif
   cell = max(1 - NG, min(nx + NG, cell));
   atomicAdd(&load[cell - (1 - NG)], 1ULL);
 }

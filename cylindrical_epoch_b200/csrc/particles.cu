@@ -1388,8 +1388,13 @@ struct SortGeom {
 
 __device__ __forceinline__ void ref_cell(const SortGeom& G, double x, double y, double z, int& cx, int& cy) {
   const double r = sqrt(y * y + z * z);
+#if CYL_SHAPE == 1   // split_particle.F90:57-63: the top-hat counts from the cell edge
+  cx = (int)floor((x - G.x_grid_min_local) / G.dx) + 1;
+  cy = (int)floor((r - G.y_grid_min_local) / G.dy) + 1;
+#else
   cx = (int)floor((x - G.x_grid_min_local) / G.dx + 1.5);
   cy = (int)floor((r - G.y_grid_min_local) / G.dy + 1.5);
+#endif
 }
 
 // The sort bucket is the STAGGERED cell (cell_x2, cell_y2) the particle will have after the

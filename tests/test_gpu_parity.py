@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import decks
+import pyoracle as po
 from parity import Pair, TOL, TOL_HOT, by_weight
 from cylindrical_epoch_b200.constants import (BC_CLAMP, BC_CONDUCT, BC_OPEN, BC_REFLECT, BC_ZERO_GRADIENT, FIELD_NAMES, M0,
                                               Q0)
@@ -271,6 +272,8 @@ def test_two_ranks_fabric(deckname):
 
 @pytest.mark.parametrize("deckname,nranks", [("lwfa", 1), ("thermal", 1), ("thermal", 2), ("lwfa", 2), ("window", 1)])
 def test_host_resident_lists_streamed_push(deckname, nranks):
+    if deckname == "window" and po.SHAPE != "triangle":
+        pytest.skip("host-resident lists under a moving window ride on the strip push, which is the triangle build's")
     """cylgpu_push_host: the particle lists stay in host memory and are streamed through the GPU
     in chunks (several chunks per step here); same fields, currents, particles and migration
     counts as the oracle.  "window": with the moving window -- the new column joins the host list
@@ -440,6 +443,7 @@ def test_energy_diagnostic_thermal():
         p.close()
 
 
+@pytest.mark.skipif(po.SHAPE != "triangle", reason="the committed vectors are the triangle build's")
 def test_against_committed_golden_vectors():
     """CUDA path vs tests/golden/lwfa_48x16_m2_20steps.npz (made by tests/golden/make_golden.py):
     no oracle call at run time"""

@@ -7,7 +7,7 @@ import pytest
 
 import decks
 from cylindrical_epoch_b200 import balance
-from cylindrical_epoch_b200.constants import FIELD_NAMES
+from cylindrical_epoch_b200.constants import FIELD_NAMES, NG
 from parity import Pair, TOL_HOT, J_FLOOR
 
 pytestmark = pytest.mark.gpu
@@ -85,7 +85,7 @@ def test_rebalance_mid_run(deckname, nranks):
         p.close()
 
 
-@pytest.mark.parametrize("bounds", [[(1, 32), (33, 64)], [(1, 20), (21, 64)], [(1, 12), (13, 64)], [(1, 10), (11, 64)]])
+@pytest.mark.parametrize("bounds", [[(1, 32), (33, 64)], [(1, 20), (21, 64)], [(1, 12), (13, 64)], [(1, 2 * NG), (2 * NG + 1, 64)]])
 def test_window_deck_prescribed_splits(bounds):
     """the moving-window deck handed over to new handles with a prescribed split (the first = the split it has: a
     pure hand-over of the state), then 8 more steps"""

@@ -1,0 +1,31 @@
+"""The top-hat and third-order B-spline builds of the library on the GPU: libcylgpu_tophat.so /
+libcylgpu_bspline3.so (-DCYL_SHAPE=1 / 2: ng = 4 / 6, the shape's weights, gather pairing and deposit ranges in the
+generic push kernel, the moments by shape) against the oracle build of the same shape.  The shape is fixed for a whole
+process (CYL_SHAPE), so the GPU parity files run once more in a subprocess per shape: the step against the oracle on
+one to four slabs, every boundary kind, Higuera-Cary, the window, the nine particle moments and the densities, the
+device-side window column, the gaussian_pulse deck, both exchange protocols, the slab re-balancer."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+FILES = ["test_gpu_parity.py", "test_zz1_gpu_moments.py", "test_zz2_gpu_counter_insert.py", "test_zz4_gpu_gaussian_pulse.py",
+         "test_zz6_gpu_exchange_protocols.py", "test_zz8_gpu_rebalance.py"]
+
+
+@pytest.mark.parametrize("shape", ["tophat", "bspline3"])
+def test_gpu_parity_files_on_the_build_of_the_shape(shape, cylgpu_lib):
+    lib = os.path.join(ROOT, "cylindrical_epoch_b200", f"libcylgpu_{shape}.so")
+    assert os.path.exists(lib), f"{lib} is missing: python -m cylindrical_epoch_b200.build --all"
+    env = dict(os.environ, CYL_SHAPE=shape)
+    env.pop("CYLGPU_LIB", None)
+    r = subprocess.run([sys.executable, "-m", "pytest"] + [os.path.join(HERE, f) for f in FILES] +
+                       ["-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=ROOT,
+                       env=env, timeout=1500)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
+    assert int(tail.split(" passed")[0].split()[-1]) >= 80, tail
