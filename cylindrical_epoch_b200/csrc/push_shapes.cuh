@@ -21,9 +21,11 @@ struct DepositG {
 __device__ __forceinline__ cplx gather_g(const cplx* __restrict__ F, const Geom& g, const double* wy, const double* wx,
                                          int cx, int cy, int im) {
   cplx total = C(0.0, 0.0);
+#pragma unroll
   for (int iy = SF_MIN; iy <= SF_MAX; ++iy) {
     const size_t o = g.at(cx, cy + iy, im);
     cplx s = wx[SF_MIN + WO] * __ldg(&F[o + SF_MIN]);
+#pragma unroll
     for (int ix = SF_MIN + 1; ix <= SF_MAX; ++ix) s = s + wx[ix + WO] * __ldg(&F[o + ix]);
     const cplx row = wy[iy + WO] * s;
     total = (iy == SF_MIN) ? row : total + row;
@@ -60,6 +62,7 @@ __device__ __forceinline__ void push_one_g(const PushConst& P, double& part_x, d
   double cell_frac_y = (double)cell_y1 - cell_y_r;
   cell_y1 += 1;
   double gx[NWT], gy[NWT], hx[NWT], hy[NWT];
+#pragma unroll
   for (int k = 0; k < NWT; ++k) { gx[k] = 0.0; gy[k] = 0.0; hx[k] = 0.0; hy[k] = 0.0; }
   shape_weights(cell_frac_x, 0, gx);
   shape_weights(cell_frac_y, 0, gy);
@@ -82,6 +85,7 @@ __device__ __forceinline__ void push_one_g(const PushConst& P, double& part_x, d
   double ex_part = 0.0, er_part = 0.0, et_part = 0.0, bx_part = 0.0, br_part = 0.0, bt_part = 0.0;
   {
     cplx e = C(1.0, 0.0);
+#pragma unroll
     for (int im = 0; im < M; ++im) {
       ex_part = ex_part + re_mul(e, gather_g(P.exm, g, hy, gx, cell_x1, cell_y2, im));
       er_part = er_part + re_mul(e, gather_g(P.erm, g, gy, hx, cell_x2, cell_y1, im));
@@ -158,7 +162,8 @@ __device__ __forceinline__ void push_one_g(const PushConst& P, double& part_x, d
   D.dtheta = atan2(z15, y15) - atan2(-emi.y, emi.x);
 #endif
 
-  for (int k = 0; k < NWT; ++k) { D.gx[k] = hx[k]; D.gy[k] = hy[k]; D.hx[k] = 0.0; D.hy[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NWT; ++k) { D.gx[k] = hx[k]; D.gy[k] = hy[k]; }
   cell_x_r = part_x_local * P.idx - SHAPE_CELL_SHIFT;
   cell_y_r = part_r_local * P.idy - SHAPE_CELL_SHIFT;
   int cell_x3 = (int)floor(cell_x_r);
@@ -168,8 +173,9 @@ __device__ __forceinline__ void push_one_g(const PushConst& P, double& part_x, d
   cell_frac_y = (double)cell_y3 - cell_y_r + 0.5;
   cell_y3 += 1;
   const int dcellx = cell_x3 - cell_x2, dcelly = cell_y3 - cell_y2;
-  shape_weights(cell_frac_x, dcellx, D.hx);
-  shape_weights(cell_frac_y, dcelly, D.hy);
+  shape_weights_placed(cell_frac_x, dcellx, D.hx);   // (every index a constant: the vectors stay in registers)
+  shape_weights_placed(cell_frac_y, dcelly, D.hy);
+#pragma unroll
   for (int k = 0; k < NWT; ++k) { D.hx[k] = D.hx[k] - D.gx[k]; D.hy[k] = D.hy[k] - D.gy[k]; }
   // Fortran integer division truncates toward zero like C
   D.xmin = SF_MIN + (dcellx - 1) / 2;
@@ -201,9 +207,13 @@ __device__ __forceinline__ void deposit_global_g(const PushConst& P, const Depos
       mf = mode_factors(im, D.dtheta, exp_imtheta0, exp_imdtheta, P.taylor_switch);
     }
     cplx jyh[NWT];
+#pragma unroll
     for (int k = 0; k < NWT; ++k) jyh[k] = C(0.0, 0.0);
-    for (int iy = D.ymin; iy <= D.ymax; ++iy) {
-      const int ky = iy + WO;
+    // sf_min - 1 .. sf_max + 1 with compile-time indices; the run-time range of this particle as a predicate
+#pragma unroll
+    for (int ky = SF_MIN - 1 + WO; ky <= SF_MAX + 1 + WO; ++ky) {
+      const int iy = ky - WO;
+      if (iy < D.ymin || iy > D.ymax) continue;
       const int cy = D.cell_y2 + iy;
       cplx w_rt, ym_fac_1;
       if (im == 0) {
@@ -218,8 +228,10 @@ __device__ __forceinline__ void deposit_global_g(const PushConst& P, const Depos
       const double fjz = D.fcz * __ldg(&inv_volume[cy]);
       const double ratio = __ldg(&ratio_area_xt[cy]);
       cplx jxh = C(0.0, 0.0);
-      for (int ix = D.xmin; ix <= D.xmax; ++ix) {
-        const int kx = ix + WO;
+#pragma unroll
+      for (int kx = SF_MIN - 1 + WO; kx <= SF_MAX + 1 + WO; ++kx) {
+        const int ix = kx - WO;
+        if (ix < D.xmin || ix > D.xmax) continue;
         const int cx = D.cell_x2 + ix;
         cplx w_xt;
         if (im == 0) w_xt = C(D.gx[kx] + 0.5 * D.hx[kx], 0.0);

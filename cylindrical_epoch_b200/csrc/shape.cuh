@@ -48,6 +48,27 @@ __host__ __device__ __forceinline__ void shape_weights(double cf, int shift, dou
 #endif
 }
 
+// The same weights placed at shift+sf_min .. shift+sf_max of a 7-vector through selects, every index a compile-time
+// constant (shift = dcell is -1, 0 or 1): the vector stays in registers where shape_weights' run-time index would
+// send it to local memory.  Entries outside the support are set to zero.
+#define NSUP (SF_MAX - SF_MIN + 1)
+__host__ __device__ __forceinline__ void shape_weights_placed(double cf, int shift, double* w) {
+  double t[NWT];
+#pragma unroll
+  for (int k = 0; k < NWT; ++k) t[k] = 0.0;
+  shape_weights(cf, 0, t);   // t[SF_MIN + WO .. SF_MAX + WO]
+#pragma unroll
+  for (int k = 0; k < NWT; ++k) {
+    double v = 0.0;
+#pragma unroll
+    for (int d = -1; d <= 1; ++d) {
+      const int src = k - d;   // w[k] = t[k - shift]
+      if (src >= SF_MIN + WO && src <= SF_MAX + WO) v = (shift == d) ? t[src] : v;
+    }
+    w[k] = v;
+  }
+}
+
 // <shape>/gxfac.inc without its fold at the axis: the NORMALISED weights of particle_to_grid.inc
 __host__ __device__ __forceinline__ void shape_weights_fac(double cf, double* w) {
 #if CYL_SHAPE == 2
