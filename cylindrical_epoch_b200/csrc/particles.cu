@@ -1089,7 +1089,8 @@ int presort_fork(cylgpu_ctx* c) {
   if (c->presorted || c->xcap <= 0 || (c->push_variant != 2 && c->push_variant != 3) || c->sort_interval != 1 || c->pending_remove) return 0;
   // Worth it only where the field phase is latency: a slab of ~1 M cell-modes (C3 over 8 GPUs: 3.73 against 3.81 ms
   // per step).  On a big slab both are bandwidth and overlapping them gains nothing (measured on C3 at 1 and 2
-  // GPUs: 24.9 / 13.0 ms per step either way).  CYLGPU_PRESORT=0/1 overrides.
+  // GPUs: 24.9 / 13.0 ms per step either way; at 4 GPUs 6.44 against 6.48, profiles/r2j_bench_c3_n4_presort_forced.json).
+  // CYLGPU_PRESORT=0/1 overrides.
   if (c->presort_policy < 0) {
     c->presort_policy = ((size_t)c->g.nx * c->g.ny * c->g.M <= ((size_t)3 << 19)) ? 1 : 0;
     if (const char* e = getenv("CYLGPU_PRESORT")) c->presort_policy = atoi(e) != 0;
