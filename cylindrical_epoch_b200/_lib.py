@@ -116,6 +116,7 @@ SYMBOLS = {
     "cylgpu_set_taylor_switch": (C.c_int, [H, C.c_double]),
     "cylgpu_set_sort_interval": (C.c_int, [H, C.c_int]),
     "cylgpu_set_push_variant": (C.c_int, [H, C.c_int]),
+    "cylgpu_set_reference_quirks": (C.c_int, [H, C.c_int]),
     "cylgpu_shape": (C.c_int, []),
     "cylgpu_ghost_cells": (C.c_int, []),
     "cylgpu_number_density_modes": (C.c_int, [H, C.c_int, C.c_void_p]),

@@ -486,6 +486,12 @@ int cylgpu_set_push_variant(cylgpu_handle c, int v) {
   c->push_variant = v;
   return 0;
 }
+int cylgpu_set_reference_quirks(cylgpu_handle c, int on) {
+  TRY(check_handle(c));
+  c->reference_quirks = on != 0;
+  c->graph_epoch += 1;   // (kernel arguments of the captured field phases)
+  return 0;
+}
 // the particle shape this library was built for (0 triangle, 1 top-hat, 2 third-order B-spline) and its ng
 int cylgpu_shape(void) { return CYL_SHAPE; }
 int cylgpu_ghost_cells(void) { return NG; }

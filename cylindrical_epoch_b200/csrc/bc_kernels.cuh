@@ -291,9 +291,9 @@ struct FieldSet {
 };
 
 // side 0: x_min (laser.f90:411-520), side 1: x_max (:524-633).  One thread per (ir, im).
-// REFERENCE QUIRKS reproduced: `r_d_vals` is declared (0:ny) but used whole-array against
-// (1:ny) sections, so element ir pairs with r_d_vals(ir-1); on x_max the same holds for
-// source_t (laser.f90:604).
+// REFERENCE QUIRKS reproduced (quirks = 1, the default): `r_d_vals` is declared (0:ny) but used whole-array
+// against (1:ny) sections, so element ir pairs with r_d_vals(ir-1); on x_max the same holds for source_t
+// (laser.f90:604).  quirks = 0 (cylgpu_set_reference_quirks): element for element, r_d_vals(ir), source_t(ir).
 __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cplx* __restrict__ snap_er,
                                                    const cplx* __restrict__ snap_et,
                                                    const cplx* __restrict__ snap_bx,
@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cpl
                                                    const cplx* __restrict__ snap_bt,
                                                    const double* __restrict__ s1, const double* __restrict__ s2,
                                                    int side, double dx, double dy, double dt,
-                                                   double y_grid_min_local) {
+                                                   double y_grid_min_local, int quirks) {
+  const int qk = quirks ? 1 : 0;
   const int ir = blockIdx.x * blockDim.x + threadIdx.x;   // 0..ny
   const int im = blockIdx.y;
   if (ir > g.ny) return;
@@ -315,7 +316,7 @@ __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cpl
     F.bxm[g.at(0, ir, im)] = snap_bx[sn];
     if (ir >= 1) {
       const cplx source_t = (im == 1) ? C(s1[ir], s2[ir]) : C(0.0, 0.0);
-      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);   // r_d_vals(ir-1)
+      const double r_d_q = fabs((double)((ir - qk) - 1) * dy + y_grid_min_local);   // r_d_vals(ir-1) with the quirk
       F.btm[g.at(1, ir, im)] =
           sum * (4.0 * source_t + 2.0 * (snap_er[sn] + c * snap_bt[sn]) - 2.0 * F.erm[g.at(1, ir, im)]
                  + (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(1, ir, im)]) / r_d_q
@@ -332,8 +333,8 @@ __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cpl
   } else {
     F.bxm[g.at(nx, ir, im)] = snap_bx[sn];
     if (ir >= 1) {
-      const cplx source_t = (im == 1) ? C(s1[ir - 1], s2[ir - 1]) : C(0.0, 0.0);
-      const double r_d_q = fabs((double)((ir - 1) - 1) * dy + y_grid_min_local);
+      const cplx source_t = (im == 1) ? C(s1[ir - qk], s2[ir - qk]) : C(0.0, 0.0);
+      const double r_d_q = fabs((double)((ir - qk) - 1) * dy + y_grid_min_local);
       F.btm[g.at(nx, ir, im)] =
           sum * (-4.0 * source_t - 2.0 * (snap_er[sn] + c * snap_bt[sn]) + 2.0 * F.erm[g.at(nx - 1, ir, im)]
                  - (((C(0.0, (double)im) * (c * c)) * dt) * F.bxm[g.at(nx - 1, ir, im)]) / r_d_q
@@ -350,12 +351,13 @@ __global__ void __launch_bounds__(128) k_outflow_x(Geom g, FieldSet F, const cpl
 }
 
 // laser.f90:637-690.  REFERENCE QUIRK reproduced: icdt_2r is declared REAL(num) but assigned
-// a purely imaginary value, so it is 0 and the azimuthal coupling terms vanish.
+// a purely imaginary value, so it is 0 and the azimuthal coupling terms vanish.  quirks = 0
+// (cylgpu_set_reference_quirks): the coefficient as the right-hand side spells it, 0.5 i c dt / r.
 // Columns: Bx on ix_l..ix_h, Btheta on it_l..it_h (the reference: 0..nx without the domain-boundary column,
 // and 1..nx; wider with field_ranges.cuh); the grid starts at column ix0.
 __global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int ix_l, int ix_h, int it_l, int it_h,
                                                        int ix0, double dx, double dy, double dt,
-                                                       double y_grid_min_local) {
+                                                       double y_grid_min_local, int quirks) {
   const int ix = blockIdx.x * blockDim.x + threadIdx.x + ix0;
   const int im = blockIdx.y;
   if (ix > ix_h && ix > it_h) return;
@@ -377,6 +379,11 @@ __global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int i
                                  + F.bro[g.at(ix + 1, ny - 1, im)] - F.bro[g.at(ix, ny - 1, im)])
                  - (icdt_2r * (double)im) * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)])
                  - dt_2eps * (F.jtm[g.at(ix, ny - 1, im)] + F.jto[g.at(ix, ny - 1, im)]));
+    if (!quirks) {
+      const cplx ic = C(0.0, ((0.5 * c) * dt) * inv_r) * (double)im;
+      F.bxm[g.at(ix, ny, im)] = F.bxm[g.at(ix, ny, im)]
+                                - sum_x * (ic * (F.erm[g.at(ix, ny, im)] + F.erm[g.at(ix, ny - 1, im)]));
+    }
   }
   if (ix >= it_l && ix <= it_h) {
     F.btm[g.at(ix, ny, im)] =
@@ -386,6 +393,11 @@ __global__ void __launch_bounds__(128) k_outflow_r_max(Geom g, FieldSet F, int i
                                        - F.erm[g.at(ix - 1, ny, im)] - F.erm[g.at(ix - 1, ny - 1, im)])
                  - ((icdt_2r * (double)im) * c) * (F.brm[g.at(ix, ny - 1, im)] + F.bro[g.at(ix, ny - 1, im)])
                  + dt_2eps * (F.jxm[g.at(ix, ny - 1, im)] + F.jxo[g.at(ix, ny - 1, im)]));
+    if (!quirks) {
+      const cplx ic = (C(0.0, ((0.5 * c) * dt) * inv_r) * (double)im) * c;
+      F.btm[g.at(ix, ny, im)] = F.btm[g.at(ix, ny, im)]
+                                - sum_t * (ic * (F.brm[g.at(ix, ny - 1, im)] + F.bro[g.at(ix, ny - 1, im)]));
+    }
   }
 }
 

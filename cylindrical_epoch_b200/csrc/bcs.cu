@@ -250,7 +250,7 @@ int do_bfield_final_bcs_device(cylgpu_ctx* c, bool wide, int phase) {
     if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW) {
       k_outflow_x<<<grd, 128, 0, c->stream>>>(g, F, c->snap[1], c->snap[2], c->snap[3], c->snap[4], c->snap[5],
                                               c->src, c->src + nsrc, 0, c->cfg.dx, c->cfg.dy, c->dt,
-                                              c->cfg.y_grid_min_local);
+                                              c->cfg.y_grid_min_local, c->reference_quirks ? 1 : 0);
       c->stats.kernel_launches += 1;
     }
   }
@@ -259,7 +259,7 @@ int do_bfield_final_bcs_device(cylgpu_ctx* c, bool wide, int phase) {
     if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW) {
       k_outflow_x<<<grd, 128, 0, c->stream>>>(g, F, c->snap[7], c->snap[8], c->snap[9], c->snap[10], c->snap[11],
                                               c->src + 2 * nsrc, c->src + 3 * nsrc, 1, c->cfg.dx, c->cfg.dy,
-                                              c->dt, c->cfg.y_grid_min_local);
+                                              c->dt, c->cfg.y_grid_min_local, c->reference_quirks ? 1 : 0);
       c->stats.kernel_launches += 1;
     }
   }
@@ -269,7 +269,8 @@ int do_bfield_final_bcs_device(cylgpu_ctx* c, bool wide, int phase) {
     const int ix0 = R.obx_lo < R.obt_lo ? R.obx_lo : R.obt_lo;
     const int ix1 = R.obx_hi > R.obt_hi ? R.obx_hi : R.obt_hi;
     k_outflow_r_max<<<dim3((ix1 - ix0 + 1 + 127) / 128, g.M), 128, 0, c->stream>>>(
-        g, F, R.obx_lo, R.obx_hi, R.obt_lo, R.obt_hi, ix0, c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local);
+        g, F, R.obx_lo, R.obx_hi, R.obt_lo, R.obt_hi, ix0, c->cfg.dx, c->cfg.dy, c->dt, c->cfg.y_grid_min_local,
+        c->reference_quirks ? 1 : 0);
     c->stats.kernel_launches += 1;
   } else if (c->bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
     k_zero_b_rmax<<<dim3((g.SX + 127) / 128, g.M), 128, 0, c->stream>>>(g, F.bxm, F.brm, F.btm);

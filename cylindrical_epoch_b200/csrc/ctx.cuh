@@ -201,6 +201,7 @@ struct cylgpu_ctx {
     bool failed = false;
   };
   PhaseGraph graphs[4];          // fields_half, fields_final, current_finish, fields_final before a window shift
+  bool reference_quirks = true;       // laser.f90's section / REAL-for-imaginary quirks reproduced (cylgpu_set_reference_quirks)
   bool final_shift_follows = false;   // driver.cu: the window moves right after this update_eb_fields_final
   uint64_t graph_epoch = 0;
   bool use_graphs = true;

@@ -557,6 +557,10 @@ class Slab:
         self.exchange_capacity = int(particles)
         self._ck(self.L.cylgpu_set_exchange_capacity(self.h, int(particles)))
 
+    def set_reference_quirks(self, on):
+        """laser.f90's array-section and REAL-for-imaginary quirks (include/cylgpu.h); reproduced by default"""
+        self._ck(self.L.cylgpu_set_reference_quirks(self.h, int(bool(on))))
+
     def set_sort_interval(self, n):
         self._ck(self.L.cylgpu_set_sort_interval(self.h, n))
 

@@ -268,6 +268,13 @@ int cylgpu_set_sort_interval(cylgpu_handle h, int every_n_pushes);   /* 0 = neve
  * the FP64 tensor-op deposit (default); 4 = the shape-generic per-particle kernel (csrc/push_shapes.cuh), the only
  * one in the top-hat / B-spline builds */
 int cylgpu_set_push_variant(cylgpu_handle h, int variant);
+/* The absorbing / laser boundaries of laser.f90 hold two pieces of non-conforming Fortran whose outcome the library
+ * reproduces by default (on = 1), because that is what a gfortran build of the reference computes: r_d_vals(0:ny)
+ * and, on x_max, source_t(0:ny) are used whole against (1:ny) sections (laser.f90:474,587,604), so element ir takes
+ * the radius and the source of ir - 1; and icdt_2r of outflow_bcs_r_max is declared REAL but assigned 0.5 i c dt / r
+ * (:640,648), so the azimuthal coupling terms of the r_max line updates vanish.  on = 0: element for element, and the
+ * coefficient as the right-hand side spells it -- for a reference built with those lines corrected. */
+int cylgpu_set_reference_quirks(cylgpu_handle h, int on);
 /* The particle shape is a compile-time choice of the reference (-DPARTICLE_SHAPE_TOPHAT / _BSPLINE3, constants.F90:
  * 524-545) and of this library (-DCYL_SHAPE=1 / 2: libcylgpu_tophat.so, libcylgpu_bspline3.so): it sets ng = png + 2,
  * i.e. the layout (1-ng:nx+ng, 1-ng:ny+ng, 0:M-1) of every array that crosses this interface.  cylgpu_shape: 0

@@ -628,6 +628,7 @@ void World::outflow_bcs_x_min(Rank& r) {
     for (int ir = 0; ir <= ny; ++ir) r.bxm(0, ir, im) = r.bxm_x_min(ir, im);
   std::vector<double> r_d_vals(ny + 1);
   for (int ir = 0; ir <= ny; ++ir) r_d_vals[ir] = std::abs((double)(ir - 1) * dy + y_grid_min_local);
+  const int qk = reference_quirks ? 1 : 0;   // the reference's (0:ny)-against-(1:ny) pairing, or element for element
   for (int im = 0; im < M; ++im) {
     std::vector<cplx> bt_new(ny + 1), br_new(ny + 1);
     for (int ir = 1; ir <= ny; ++ir) {
@@ -635,7 +636,7 @@ void World::outflow_bcs_x_min(Rank& r) {
       bt_new[ir] = sum * (4.0 * source_t
                           + 2.0 * (r.erm_x_min(ir, im) + c * r.btm_x_min(ir, im))
                           - 2.0 * r.erm(1, ir, im)
-                          + ((((IMAGI * (double)im) * (c * c)) * dt) * r.bxm(1, ir, im)) / r_d_vals[ir - 1]
+                          + ((((IMAGI * (double)im) * (c * c)) * dt) * r.bxm(1, ir, im)) / r_d_vals[ir - qk]
                           + dt_eps * r.jrm(1, ir, im)
                           + diff * r.btm(2, ir, im));
     }
@@ -668,14 +669,15 @@ void World::outflow_bcs_x_max(Rank& r) {
     for (int ir = 0; ir <= ny; ++ir) r.bxm(nx, ir, im) = r.bxm_x_max(ir, im);
   std::vector<double> r_d_vals(ny + 1);
   for (int ir = 0; ir <= ny; ++ir) r_d_vals[ir] = std::abs((double)(ir - 1) * dy + y_grid_min_local);
+  const int qk = reference_quirks ? 1 : 0;   // the reference's (0:ny)-against-(1:ny) pairing, or element for element
   for (int im = 0; im < M; ++im) {
     std::vector<cplx> bt_new(ny + 1), br_new(ny + 1);
     for (int ir = 1; ir <= ny; ++ir) {
-      cplx source_t = (im == 1) ? (cplx(s1[ir - 1]) + IMAGI * s2[ir - 1]) : cplx(0.0);
+      cplx source_t = (im == 1) ? (cplx(s1[ir - qk]) + IMAGI * s2[ir - qk]) : cplx(0.0);
       bt_new[ir] = sum * (-4.0 * source_t
                           - 2.0 * (r.erm_x_max(ir, im) + c * r.btm_x_max(ir, im))
                           + 2.0 * r.erm(nx - 1, ir, im)
-                          - ((((IMAGI * (double)im) * (c * c)) * dt) * r.bxm(nx - 1, ir, im)) / r_d_vals[ir - 1]
+                          - ((((IMAGI * (double)im) * (c * c)) * dt) * r.bxm(nx - 1, ir, im)) / r_d_vals[ir - qk]
                           - dt_eps * r.jrm(nx - 1, ir, im)
                           + diff * r.btm(nx - 1, ir, im));
     }
@@ -704,6 +706,8 @@ void World::outflow_bcs_r_max(Rank& r) {   // laser.f90:637-690
   // the purely imaginary 0.5*imagi*c*dt*inv_r, so Fortran keeps only its real part = 0 and
   // the two azimuthal (im) coupling terms below vanish identically.
   double icdt_2r = ((((0.5 * IMAGI) * c) * dt) * inv_r).re;
+  // reference_quirks off: the coefficient as the right-hand side spells it, purely imaginary
+  const cplx icdt_2r_c = reference_quirks ? cplx(0.0) : (((0.5 * IMAGI) * c) * dt) * inv_r;
   double lx = dtc2 / dx, ly = dtc2 / dy;
   double sum_x = 1.0 / (ly + c);
   double sum_t = 1.0 / (ly + c + dtc2_4r);
@@ -720,6 +724,9 @@ void World::outflow_bcs_r_max(Rank& r) {   // laser.f90:637-690
                           + r.brm_old(ix + 1, ny - 1, im) - r.brm_old(ix, ny - 1, im))
           - (icdt_2r * (double)im) * (r.erm(ix, ny, im) + r.erm(ix, ny - 1, im))
           - dt_2eps * (r.jtm(ix, ny - 1, im) + r.jtm_old(ix, ny - 1, im)));
+      if (!reference_quirks)
+        r.bxm(ix, ny, im) = r.bxm(ix, ny, im)
+            - sum_x * ((icdt_2r_c * (double)im) * (r.erm(ix, ny, im) + r.erm(ix, ny - 1, im)));
     }
     // RHS uses only rows ny-1 / *_old of btm, so in-place is safe
     for (int ix = 1; ix <= nx; ++ix) {
@@ -730,6 +737,9 @@ void World::outflow_bcs_r_max(Rank& r) {   // laser.f90:637-690
                                 - r.erm(ix - 1, ny, im) - r.erm(ix - 1, ny - 1, im))
           - ((icdt_2r * (double)im) * c) * (r.brm(ix, ny - 1, im) + r.brm_old(ix, ny - 1, im))
           + dt_2eps * (r.jxm(ix, ny - 1, im) + r.jxm_old(ix, ny - 1, im)));
+      if (!reference_quirks)
+        r.btm(ix, ny, im) = r.btm(ix, ny, im)
+            - sum_t * (((icdt_2r_c * (double)im) * c) * (r.brm(ix, ny - 1, im) + r.brm_old(ix, ny - 1, im)));
     }
   }
 }

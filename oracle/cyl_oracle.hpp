@@ -340,6 +340,10 @@ struct World {
   bool smooth_currents = false;                  // shared_data.F90:468-472
   double taylor_switch = 1.0e-4;                 // |m dtheta| below which particles.F90:593-598 use the series (test knob)
   bool hc_push = false;                          // -DHC_PUSH, particles.F90:409-421
+  // laser.f90: r_d_vals(0:ny) / source_t(0:ny) used whole against (1:ny) sections (:474,:587,:604) and icdt_2r
+  // declared REAL but assigned an imaginary value (:640,:648).  true: what gfortran makes of that (the default, the
+  // reference's behaviour); false: element for element and the imaginary coefficient (what the code spells)
+  bool reference_quirks = true;
   int smooth_its = 1, smooth_comp_its = 0;
   std::vector<int> smooth_strides;
   void moving_window();                          // window.F90:330-376

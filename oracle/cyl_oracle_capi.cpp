@@ -180,6 +180,8 @@ enum Op {
 };
 
 // returns elapsed seconds of the call
+void cylo_set_reference_quirks(void* wp, int on) { ((World*)wp)->reference_quirks = on != 0; }
+
 // ghost cells of the arrays of this build (ng = png + 2: the particle shape is compiled in)
 int cylo_ng() { return NG; }
 int cylo_shape() { return CYLO_SHAPE; }

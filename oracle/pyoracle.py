@@ -110,6 +110,8 @@ def lib():
         L.cylo_get_max_threads.restype = C.c_int
         L.cylo_set_taylor_switch.restype = None
         L.cylo_set_taylor_switch.argtypes = [C.c_void_p, C.c_double]
+        L.cylo_set_reference_quirks.restype = None
+        L.cylo_set_reference_quirks.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_hc_push.restype = None
         L.cylo_set_hc_push.argtypes = [C.c_void_p, C.c_int]
         L.cylo_set_smoothing.restype = None
@@ -234,6 +236,10 @@ class OracleWorld:
             buf = (C.c_double * (2 * shape[0] * shape[1] * shape[2])).from_address(self.L.cylo_wk_ptr(self.h, k))
             out.append(np.frombuffer(buf, dtype=np.complex128).reshape(shape).copy())
         return out
+
+    def set_reference_quirks(self, on):
+        """laser.f90's array-section and REAL-for-imaginary quirks (cyl_oracle.hpp reference_quirks); default on"""
+        self.L.cylo_set_reference_quirks(self.h, int(bool(on)))
 
     def set_taylor_switch(self, v):
         """|m dtheta| below which the deposit uses the small-angle series (particles.F90:593: 1.0e-4); moved only by

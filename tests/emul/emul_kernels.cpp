@@ -256,6 +256,8 @@ EMUL_API int emul_moment_two_slabs(const int* nx2, int ny, int kind, int directi
 }
 
 // push_particles without particle_bcs for one species of one slab (cylgpu_push_no_bcs with push variant 0):
+static int g_reference_quirks = 1;
+EMUL_API void emul_set_reference_quirks(int on) { g_reference_quirks = on; }
 static int g_push_generic = 0;
 EMUL_API void emul_set_push_generic(int on) { g_push_generic = on; }
 EMUL_API int emul_ghost_cells() { return NG; }
@@ -433,14 +435,14 @@ EMUL_API void emul_bfield_final_bcs(int nx, int ny, int M, void* const* f15, con
   int b = bc_field[CYLGPU_BD_X_MIN];
   if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
     emul_launch(k_outflow_x, grd, dim3(128), g, F, snap(1), snap(2), snap(3), snap(4), snap(5), src4[0], src4[1], 0, dx, dy,
-                dt, y_grid_min_local);
+                dt, y_grid_min_local, g_reference_quirks);
   b = bc_field[CYLGPU_BD_X_MAX];
   if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
     emul_launch(k_outflow_x, grd, dim3(128), g, F, snap(7), snap(8), snap(9), snap(10), snap(11), src4[2], src4[3], 1, dx,
-                dy, dt, y_grid_min_local);
+                dy, dt, y_grid_min_local, g_reference_quirks);
   if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
     emul_launch(k_outflow_r_max, dim3((g.nx + 1 + 127) / 128, g.M), dim3(128), g, F, 1, g.nx - 1, 1, g.nx, 0, dx, dy, dt,
-                y_grid_min_local);
+                y_grid_min_local, g_reference_quirks);
   } else if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
     emul_launch(k_zero_b_rmax, dim3((g.SX + 127) / 128, g.M), dim3(128), g, F.bxm, F.brm, F.btm);
   }
@@ -917,19 +919,19 @@ extern "C" EMUL_API void emul_field_phase_slabs(int phase, int wide, int nranks,
       const int b = bc_field[CYLGPU_BD_X_MIN];
       if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
         emul_launch(k_outflow_x, grd, dim3(128), g, S, snap(1), snap(2), snap(3), snap(4), snap(5), src4[0], src4[1], 0, dx,
-                    dy, dt, y_grid_min_local);
+                    dy, dt, y_grid_min_local, g_reference_quirks);
     }
     if (k == nranks - 1) {
       const int b = bc_field[CYLGPU_BD_X_MAX];
       if (b == CYLGPU_BC_SIMPLE_LASER || b == CYLGPU_BC_SIMPLE_OUTFLOW)
         emul_launch(k_outflow_x, grd, dim3(128), g, S, snap(7), snap(8), snap(9), snap(10), snap(11), src4[2], src4[3], 1,
-                    dx, dy, dt, y_grid_min_local);
+                    dx, dy, dt, y_grid_min_local, g_reference_quirks);
     }
     if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_SIMPLE_OUTFLOW) {
       const int ix0 = X.obx_lo < X.obt_lo ? X.obx_lo : X.obt_lo;
       const int ix1 = X.obx_hi > X.obt_hi ? X.obx_hi : X.obt_hi;
       emul_launch(k_outflow_r_max, dim3((ix1 - ix0 + 1 + 127) / 128, g.M), dim3(128), g, S, X.obx_lo, X.obx_hi, X.obt_lo,
-                  X.obt_hi, ix0, dx, dy, dt, y_grid_min_local);
+                  X.obt_hi, ix0, dx, dy, dt, y_grid_min_local, g_reference_quirks);
     } else if (bc_field[CYLGPU_BD_Y_MAX] == CYLGPU_BC_ZERO_B) {
       emul_launch(k_zero_b_rmax, dim3((g.SX + 127) / 128, g.M), dim3(128), g, S.bxm, S.brm, S.btm);
     }

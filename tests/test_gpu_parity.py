@@ -476,3 +476,30 @@ def test_against_committed_golden_vectors():
         assert [s.particle_count(0), s.particle_count(1)] == list(ref["counts"][:2])
     finally:
         s.close()
+
+
+def test_reference_quirks_switched_off_on_both_sides():
+    """cylgpu_set_reference_quirks(0): laser.f90's boundary lines element for element and with the imaginary
+    icdt_2r, against the oracle with the same switch -- laser from x_min, absorbing x_max and r_max, m = 0..2"""
+    d = decks.lwfa(nx=96, ny=24, n_mode=3, ppc_e=4, ppc_p=1, t_centre=12e-15)
+    p = Pair(d, init_half_step=False)
+    try:
+        p.oracle.set_reference_quirks(False)
+        for s in p.slabs:
+            s.set_reference_quirks(False)
+        p.oracle.call("init_half_step")
+        p.each(lambda s: s.init_half_step())
+        p.step(40)
+        p.check_counts()
+        p.check_fields()
+        p.check_particles()
+        # and it is a different run from the default one
+        q = Pair(d)
+        try:
+            q.step(40)
+            a, b = p.slabs[0].download_field("btm"), q.slabs[0].download_field("btm")
+            assert np.abs(a - b).max() > 1e-8 * np.abs(b).max()
+        finally:
+            q.close()
+    finally:
+        p.close()

@@ -560,9 +560,15 @@ def test_field_boundary_kernels_match_the_oracle(emul, bc_name):
 # bfield_final_bcs (csrc/bc_kernels.cuh: k_outflow_x, k_outflow_r_max, k_zero_b_rmax): laser injection into
 # m = 1 and the first-order absorbing update of laser.f90:411-690, with the reference quirks reproduced.
 # ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("quirks", [True, False])
 @pytest.mark.parametrize("deck_name", ["lwfa", "gaussian", "thermal", "laser_both_ends"])
-def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name):
+def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name, quirks):
+    """quirks: laser.f90's (0:ny)-against-(1:ny) sections and the REAL icdt_2r as a gfortran build computes them (the
+    default on both sides), or element for element with the imaginary coefficient (cylgpu_set_reference_quirks(0) /
+    the oracle's reference_quirks = false): the kernels follow the oracle in both, and the two differ"""
     L = emul
+    L.emul_set_reference_quirks.restype = None
+    L.emul_set_reference_quirks(int(quirks))
     L.emul_bfield_final_bcs.restype = None
     L.emul_bfield_final_bcs.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                         C.POINTER(C.c_void_p), C.POINTER(C.c_int32), C.c_double, C.c_double,
@@ -599,10 +605,24 @@ def test_bfield_final_bcs_kernels_match_the_oracle(emul, deck_name):
     bcf = (C.c_int32 * 4)(*w.bc_field())
     L.emul_bfield_final_bcs(info["nx"], info["ny"], d.n_mode, fp, sp, rp, bcf, sc["dx"], sc["dy"], sc["dt"],
                             sc["y_grid_min_local"])
+    L.emul_set_reference_quirks(1)
+    before = {n: w.field(0, n).copy() for n in FIELD_NAMES[:6]}
+    w.set_reference_quirks(quirks)
     w.call("bfield_final_bcs")
     for n, a in zip(FIELD_NAMES[:6], mine[:6]):
         ref = w.field(0, n)
-        assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n)
+        assert np.abs(a - ref).max() <= 1e-14 * np.abs(ref).max(), (deck_name, n, quirks)
+    if not quirks and deck_name != "thermal":
+        # ... and the switch does something: the same state through the default rules gives other boundary lines
+        v = decks.make_oracle(d)
+        for n in FIELD_NAMES:
+            v.field(0, n)[...] = before[n] if n in before else w.field(0, n)
+        for n in SNAP_NAMES:
+            v.field(0, n)[...] = w.field(0, n)
+        v.set_time(w.scalars()["time"])
+        v.call("bfield_final_bcs")
+        assert any(np.abs(v.field(0, n) - w.field(0, n)).max() > 1e-6 * np.abs(w.field(0, n)).max()
+                   for n in ("btm", "bxm"))
     if deck_name != "thermal":
         assert max(np.abs(s).max() for s in src) > 0      # the laser was on
 

@@ -38,3 +38,38 @@ def test_product_kernels_of_the_shape_track_its_oracle(shape):
     tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
     assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]
     assert int(tail.split(" passed")[0].split()[-1]) >= 60, tail
+
+
+@pytest.mark.parametrize("shape,code,ng", [("triangle", 0, 5), ("tophat", 1, 4), ("bspline3", 2, 6)])
+def test_every_shape_build_exports_the_whole_abi(shape, code, ng):
+    """libcylgpu.so / libcylgpu_tophat.so / libcylgpu_bspline3.so: the same entry points (include/cylgpu.h), each
+    telling its shape and its ng -- what the Fortran shim checks against its own -DPARTICLE_SHAPE_* """
+    import ctypes as C
+    from cylindrical_epoch_b200 import _lib, build
+    path = build.lib_path(shape)
+    if not os.path.exists(path):
+        if not os.path.exists(build.NVCC):
+            pytest.skip("no nvcc here and the library of this shape is not built")
+        build.build(shape=shape)
+    lib = C.CDLL(path)     # (RTLD_LOCAL: three builds of the same symbols side by side)
+    for name in _lib.SYMBOLS:
+        assert hasattr(lib, name), (shape, name)
+    lib.cylgpu_shape.restype = C.c_int
+    lib.cylgpu_ghost_cells.restype = C.c_int
+    assert (lib.cylgpu_shape(), lib.cylgpu_ghost_cells()) == (code, ng)
+
+
+def test_balancer_keeps_slabs_two_halos_wide():
+    """calculate_breaks may cut down to ncell_min = (png + 1) / 2 + 1 columns (constants.F90:548); a handle needs
+    2 ng: balance.widen_narrow_slabs moves such breaks with the reference's own backwards / forwards passes"""
+    from cylindrical_epoch_b200.balance import widen_narrow_slabs
+    from cylindrical_epoch_b200.constants import NG
+    w = 2 * NG
+    assert widen_narrow_slabs([(1, 32), (33, 64)], 64) == [(1, 32), (33, 64)]                 # nothing to do
+    assert widen_narrow_slabs([(1, 3), (4, 64)], 64) == [(1, w), (w + 1, 64)]                 # first slab too narrow
+    assert widen_narrow_slabs([(1, 61), (62, 64)], 64) == [(1, 64 - w), (64 - w + 1, 64)]     # last slab too narrow
+    out = widen_narrow_slabs([(1, 40), (41, 43), (44, 64)], 64)                               # a narrow one in the middle
+    assert out[0][0] == 1 and out[-1][1] == 64
+    assert all(hi - lo + 1 >= w for lo, hi in out) and all(out[k + 1][0] == out[k][1] + 1 for k in range(2))
+    with pytest.raises(RuntimeError):
+        widen_narrow_slabs([(1, 5), (6, 10), (11, 15)], 15)                                   # 15 columns cannot hold three
