@@ -368,6 +368,8 @@ def run_ours(args, wl_name, wl):
     # run the library on a torch-owned stream so that torch.cuda.Event brackets its work
     tstream = torch.cuda.Stream(device=local)
     slab.set_stream(tstream.cuda_stream)
+    if dist is not None:
+        dist.barrier()   # the ranks' host-side set-up took different times; the first neighbour exchange is next
     slab.init_half_step()
     slab.L.cylgpu_set_timing(slab.h, 1)
     if "BENCH_VARIANT" in os.environ:

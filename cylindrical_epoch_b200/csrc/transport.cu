@@ -29,7 +29,9 @@ namespace cylgpu {
 // no rendezvous, no proxy thread, ~3 us instead of ~20 us per exchange, and capturable in CUDA graphs because the
 // sequence numbers live in device memory.  A slab of an 8-GPU run makes ~10 exchanges per 3.5 ms step.
 #define P2P_FLAGS_BYTES 256
-#define P2P_TIMEOUT_CLOCKS 6000000000LL   // ~3 s at 2 GHz
+// A wait gives up after ~2 minutes (a sticky error instead of a hung device).  Generous on purpose: the ranks of a run
+// reach their first exchange as far apart as their set-up times differ (seconds), and NCCL would simply wait.
+#define P2P_TIMEOUT_CLOCKS 240000000000LL   // ~120 s at 2 GHz
 struct P2PBoxHeader {               // at the start of each mailbox (written by the PEER unless noted)
   unsigned long long flag[2];       // sequence number of the message in slot 0 / 1
   unsigned long long ack;           // highest sequence number the OWNER of the box the peer writes to has consumed:

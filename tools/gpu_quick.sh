@@ -1,4 +1,5 @@
 #!/bin/bash
-# 1 GPU, final build: the boundary-line kernels after the reference-quirks switch (default path and switch off)
+# 2 GPUs, final binaries: the mailbox transport test and a short N=2 bench (barrier before the first exchange)
 mkdir -p gpurun_out
-timeout 200 python -m pytest tests/test_gpu_parity.py tests/test_zz4_gpu_gaussian_pulse.py -m gpu -q -x 2>&1 | tail -3 | cut -c1-300 | tee gpurun_out/r2k_pytest_quirks.txt
+timeout 300 python -m pytest tests/test_gpu_nccl.py -m gpu -q -k "two_gpu_parity and mailboxes and not particles" 2>&1 | tail -2 | cut -c1-300 | tee gpurun_out/r2k_pytest_nccl_mailboxes.txt
+timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29577 bench.py --gpus 2 --steps 5 --warmup 3 --no-e2e --workload lwfa_1024x128_m2_ppc16 2>&1 | tail -1 | cut -c1-400
