@@ -931,7 +931,8 @@ def _run_phase(L, phase, wide, w, f, s, d, src):
                              sc["dt"], sc["y_grid_min_local"])
 
 
-@pytest.mark.parametrize("deck_name,nranks", [("lwfa", 3), ("lwfa", 2), ("thermal", 2), ("thermal", 3), ("walls", 2)])
+@pytest.mark.parametrize("deck_name,nranks", [("lwfa", 3), ("lwfa", 2), ("lwfa_m5", 4), ("thermal", 2), ("thermal", 3), ("walls", 2),
+                                              ("walls", 3)])
 def test_wide_field_phases_match_the_exchanged_ones(emul, deck_name, nranks):
     from pyoracle import FIELD_NAMES
     L = emul
@@ -939,8 +940,9 @@ def test_wide_field_phases_match_the_exchanged_ones(emul, deck_name, nranks):
     L.emul_field_phase_slabs.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int,
                                          C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                          C.POINTER(C.c_int32)] + [C.c_double] * 4
-    if deck_name == "lwfa":      # laser from x_min, open x, simple_outflow on r_max: every line update is live
-        d = decks.lwfa(nx=20 * nranks, ny=12, n_mode=3, ppc_e=3, ppc_p=1, t_centre=10e-15)
+    if deck_name.startswith("lwfa"):      # laser from x_min, open x, simple_outflow on r_max: every line update is live
+        d = decks.lwfa(nx=(14 if deck_name == "lwfa_m5" else 20) * nranks, ny=12, n_mode=5 if deck_name == "lwfa_m5" else 3,
+                       ppc_e=3, ppc_p=1, t_centre=10e-15)
     elif deck_name == "thermal":  # periodic ring (two ranks: left == right), zero_b on r_max
         d = decks.thermal(nx=12 * nranks, ny=10, n_mode=2, ppc=6, temp_k=2.0e8)
     else:                        # conducting walls all round
@@ -950,7 +952,7 @@ def test_wide_field_phases_match_the_exchanged_ones(emul, deck_name, nranks):
             sp.bc_particle = (po.BC_REFLECT, po.BC_REFLECT, po.BC_OPEN, po.BC_REFLECT)
     w = decks.make_oracle(d, nranks=nranks)
     w.call("init_half_step")
-    w.step(45 if deck_name == "lwfa" else 6)      # the pulse has crossed the slab boundaries
+    w.step(45 if deck_name.startswith("lwfa") else 6)      # the pulse has crossed the slab boundaries
     worst = 0.0
     for step in range(6):
         for phase in (0, 1):
