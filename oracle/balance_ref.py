@@ -5,7 +5,9 @@ import math
 
 import numpy as np
 
-NG, PNG = 5, 3
+from pyoracle import NG   # ng = png + 2 of the particle shape in use (CYL_SHAPE)
+
+PNG = NG - 2
 NCELL_MIN = (PNG + 1) // 2 + 1       # constants.F90:548
 PUSH_PER_FIELD = 5                   # shared_data.F90:761
 

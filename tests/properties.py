@@ -6,7 +6,7 @@ import numpy as np
 
 from cylindrical_epoch_b200.constants import C_LIGHT, EPSILON0
 
-NG = 5
+from cylindrical_epoch_b200.constants import NG, SHAPE  # ng = png + 2 and the particle shape of the build in use (CYL_SHAPE)
 
 
 def area_tables(ny, dx, dy):
@@ -20,25 +20,37 @@ def area_tables(ny, dx, dy):
     return area_rt, area_xt
 
 
+def stag_weights(c_r):
+    """staggered shape weights of one direction with their factor (<shape>/hx_dcell.inc; particles.F90:145-153) for
+    the particle shape of the build in use: (first node index, tuple of weight arrays)"""
+    if SHAPE == "tophat":
+        c_r = c_r - 0.5
+    c2 = np.floor(c_r)
+    f = c2 - c_r + 0.5
+    first = c2.astype(np.int64) + 1
+    if SHAPE == "tophat":
+        return first, (0.5 + f, 0.5 - f)
+    f2 = f * f
+    if SHAPE == "bspline3":
+        w = ((0.5 + f) ** 4, 4.75 + 11.0 * f + 4.0 * f2 * (1.5 - f - f2), 14.375 + 6.0 * f2 * (f2 - 2.5),
+             4.75 - 11.0 * f + 4.0 * f2 * (1.5 + f - f2), (0.5 - f) ** 4)
+        return first - 2, tuple(v / 24.0 for v in w)
+    return first - 1, (0.5 * (0.25 + f2 + f), 0.5 * (1.5 - 2 * f2), 0.5 * (0.25 + f2 - f))
+
+
 def node_charge(pos, weight, q, x_grid_min, y_grid_min_local, dx, dy, nx, ny):
-    """charge on the staggered nodes with the deposit's own (unnormalised triangle) weights
-    (particles.F90:369-388, DOCUMENTATION eq. 96): Q(cx, cy) = q w / 4 * hx hy, as a
-    [ir + NG - 1, ix + NG - 1] array.  np.bincount: 9 passes over the list."""
+    """charge on the staggered nodes with the deposit's own weights (particles.F90:369-388, DOCUMENTATION eq. 96):
+    Q(cx, cy) = q w fac hx hy, as a [ir + NG - 1, ix + NG - 1] array.  np.bincount: one pass per node of the shape."""
     SX, SY = nx + 2 * NG, ny + 2 * NG
     xr = (pos[:, 0] - x_grid_min) / dx
     rr = (np.hypot(pos[:, 1], pos[:, 2]) - y_grid_min_local) / dy
-    out = []
-    for c_r in (xr, rr):
-        c2 = np.floor(c_r)
-        f = c2 - c_r + 0.5
-        out.append((c2.astype(np.int64) + 1, (0.25 + f * f + f, 1.5 - 2 * f * f, 0.25 + f * f - f)))
-    (cx2, wx), (cy2, wy) = out
-    qw = (0.25 * q) * weight
+    (cx0, wx), (cy0, wy) = stag_weights(xr), stag_weights(rr)
+    qw = q * weight
     Q = np.zeros(SX * SY)
-    for a in range(3):
-        for b in range(3):
-            ix = cx2 - 1 + b + NG - 1
-            iy = cy2 - 1 + a + NG - 1
+    for a in range(len(wy)):
+        for b in range(len(wx)):
+            ix = cx0 + b + NG - 1
+            iy = cy0 + a + NG - 1
             ok = (ix >= 0) & (ix < SX) & (iy >= 0) & (iy < SY)
             idx, val = iy * SX + ix, qw * wx[b] * wy[a]
             if not ok.all():          # (full-size runs: everything is inside, no masked copies)

@@ -6,6 +6,7 @@ import socket
 import sys
 
 import numpy as np
+from cylindrical_epoch_b200.constants import NG
 import pytest
 import torch
 import torch.multiprocessing as mp
@@ -119,7 +120,7 @@ def _ring_worker(rank, world, port, periodic, q):
         f[...] = rng.standard_normal(f.shape) + 1j * rng.standard_normal(f.shape)
     mine = w.field(rank, "erm").copy()
     nx = w.rank_info(rank)["nx"]
-    NGH = 5
+    from cylindrical_epoch_b200.constants import NG as NGH
     send_l = torch.from_numpy(np.ascontiguousarray(mine[:, :, NGH:2 * NGH]))              # columns 1..ng
     send_r = torch.from_numpy(np.ascontiguousarray(mine[:, :, nx:nx + NGH]))              # nx+1-ng..nx
     recv_l = torch.zeros_like(send_l)
@@ -226,7 +227,7 @@ def test_host_mirror_builds_the_sdf_descriptor_and_moment_calls():
     s.L.calls.clear()
     a = s.moment("species_current", 1, 3)
     name, args = s.L.calls[-1]
-    assert name == "cylgpu_particle_moment" and args[1:4] == (7, 1, 3) and a.shape == (24 + 10, 32 + 10)
+    assert name == "cylgpu_particle_moment" and args[1:4] == (7, 1, 3) and a.shape == (24 + 2 * NG, 32 + 2 * NG)
 
 
 def test_host_mirror_device_insertion_uses_the_shift_counter_as_column():

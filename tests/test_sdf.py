@@ -19,7 +19,7 @@ from cylindrical_epoch_b200.constants import FIELD_NAMES
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
-NG = 5
+from cylindrical_epoch_b200.constants import NG  # ng = png + 2 of the build in use (CYL_SHAPE)
 
 # io/diagnostics.F90:497-575: block order, names, units; stagger codes constants.F90:291-299 / sdf_common.f90:184-195
 GROUPS = [("Electric Field Modes", "V/m", [("exm", 2), ("erm", 1), ("etm", 3)]),

@@ -73,3 +73,18 @@ def test_balancer_keeps_slabs_two_halos_wide():
     assert all(hi - lo + 1 >= w for lo, hi in out) and all(out[k + 1][0] == out[k][1] + 1 for k in range(2))
     with pytest.raises(RuntimeError):
         widen_narrow_slabs([(1, 5), (6, 10), (11, 15)], 15)                                   # 15 columns cannot hold three
+
+
+@pytest.mark.parametrize("shape", ["tophat", "bspline3"])
+def test_host_side_files_under_the_shape(shape):
+    """the rest of the CPU suite with ng = 4 / 6: the SDF writer read back by the reference's own reader, the host
+    mirror, the ABI, the counter-based column, the property checkers (Gauss law with the shape's weights), the slab
+    re-balancer over gloo"""
+    env = dict(os.environ, CYL_SHAPE=shape)
+    files = ["test_sdf.py", "test_host_logic.py", "test_abi.py", "test_counter_insert.py", "test_properties_cpu.py",
+             "test_balance_redistribute.py"]
+    r = subprocess.run([sys.executable, "-m", "pytest"] + [os.path.join(HERE, f) for f in files] +
+                       ["-q", "-x", "-m", "not gpu", "-p", "no:cacheprovider"], capture_output=True, text=True, cwd=ROOT,
+                       env=env, timeout=1500)
+    tail = r.stdout.strip().splitlines()[-1] if r.stdout.strip() else r.stderr[-500:]
+    assert r.returncode == 0 and " passed" in tail and "failed" not in tail, r.stdout[-3000:]

@@ -15,6 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 FILES = ["test_gpu_parity.py", "test_zz1_gpu_moments.py", "test_zz2_gpu_counter_insert.py", "test_zz4_gpu_gaussian_pulse.py",
          "test_zz6_gpu_exchange_protocols.py", "test_zz8_gpu_rebalance.py"]
+# (test_zz3_gpu_sdf.py, the dump / restart through the device mirrors, is not in the list: its host-level twin
+# tests/test_sdf.py runs under both shapes on the CPU, tests/test_shapes.py, but the GPU file has not been run on them)
 
 
 @pytest.mark.parametrize("shape", ["tophat", "bspline3"])

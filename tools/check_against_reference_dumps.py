@@ -38,7 +38,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-NG = 5
+from cylindrical_epoch_b200.constants import NG  # noqa: E402  (ng of the build in use, CYL_SHAPE)
 
 
 def read_dump(path, deck, k, info):
