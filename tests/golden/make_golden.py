@@ -1,4 +1,5 @@
-"""Generates tests/golden/lwfa_48x16_m2_20steps.npz from the CPU oracle.
+"""Generates tests/golden/lwfa_48x16_m2_20steps.npz from the CPU oracle (and, run under CYL_SHAPE=tophat / bspline3,
+lwfa_48x16_m2_20steps_<shape>.npz from the oracle build of that particle shape).
 
 The reference ships no fixtures for the cylindrical path and cannot be built here (Fortran +
 MPI), so these vectors come from the oracle restatement; they pin it against drift and give
@@ -43,6 +44,12 @@ def run_case():
     return out
 
 
+def golden_path():
+    import pyoracle
+    tag = "" if pyoracle.SHAPE == "triangle" else "_" + pyoracle.SHAPE
+    return os.path.join(HERE, f"lwfa_48x16_m2_20steps{tag}.npz")
+
+
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(HERE, "lwfa_48x16_m2_20steps.npz"), **run_case())
-    print("written")
+    np.savez_compressed(golden_path(), **run_case())
+    print("written", golden_path())

@@ -355,15 +355,11 @@ def test_rng_and_loader_statistics():
     assert not np.array_equal(w2.particles(0, 0)[:50, 1], w2.particles(1, 0)[:50, 1])
 
 
-GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lwfa_48x16_m2_20steps.npz")
-
-
-@pytest.mark.skipif(not TRIANGLE, reason="the committed vectors are the triangle build's")
 def test_oracle_reproduces_golden_vectors():
-    """fixture made by tests/golden/make_golden.py from the oracle itself: guards the restatement
-    (and its compiler flags) against drift; the GPU suite checks the CUDA path against the same file"""
-    from golden.make_golden import run_case
-    ref = np.load(GOLDEN)
+    """fixture made by tests/golden/make_golden.py from the oracle itself (one file per particle shape): guards the
+    restatement (and its compiler flags) against drift; the GPU suite checks the CUDA path against the same file"""
+    from golden.make_golden import golden_path, run_case
+    ref = np.load(golden_path())
     got = run_case()
     for k in ref.files:
         a, b = ref[k], got[k]
