@@ -79,3 +79,18 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "pyoracle" not in txt and "cyl_oracle" not in txt, f
                 assert not re.search(r"(import|from|include)\s+.*\boracle\b", txt), f
+
+
+def test_integration_shim_binds_only_what_the_library_exports():
+    """every BIND(C, NAME='cylgpu_...') of the Fortran shim in INTEGRATION.md names an entry point of include/cylgpu.h
+    (the shim cannot be compiled in this image, so at least its names are held against the header)"""
+    import re
+    from cylindrical_epoch_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"NAME='(cylgpu_[a-z_0-9]+)'", text))
+    assert len(bound) >= 30
+    header = open(os.path.join(root, "include", "cylgpu.h")).read()
+    for name in sorted(bound):
+        assert name in _lib.SYMBOLS, name
+        assert re.search(r"\b%s\s*\(" % name, header), name
