@@ -94,3 +94,13 @@ def test_integration_shim_binds_only_what_the_library_exports():
     for name in sorted(bound):
         assert name in _lib.SYMBOLS, name
         assert re.search(r"\b%s\s*\(" % name, header), name
+    # ... with as many dummy arguments as the C prototype has parameters
+    flat = re.sub(r"&\s*\n\s*", " ", text)
+    n_checked = 0
+    for m in re.finditer(r"FUNCTION\s+\w+\s*\(([^)]*)\)\s*(?:RESULT\(\w+\)\s*)?BIND\(C,\s*NAME='(cylgpu_\w+)'\)", flat):
+        fargs = [a for a in m.group(1).split(",") if a.strip()]
+        proto = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % m.group(2), header, re.S)
+        cargs = [a for a in proto.group(1).split(",") if a.strip() and a.strip() != "void"]
+        assert len(fargs) == len(cargs), (m.group(2), fargs, cargs)
+        n_checked += 1
+    assert n_checked >= 30
