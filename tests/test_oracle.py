@@ -335,6 +335,59 @@ def test_gauss_law_residual_is_frozen():
     assert np.abs(r1 - r0).max() < 1e-8 * moved, np.abs(r1 - r0).max() / moved   # measured 5e-12
 
 
+def test_linear_laser_wakefield_matches_one_dimensional_theory():
+    """The chain the headline configuration lives on, against an analytic answer: a linearly polarised Gaussian pulse
+    (pure m = 1, injected at x_min) drives a plasma wave in m = 0 through the ponderomotive force -- mode-1 gather and
+    its factor in the pusher, the quiver current, the charge-conserving mode-0 deposit, the field solver.  Cold
+    linear theory for the on-axis field behind a pulse a^2 = a0^2 exp(-xi^2 / L^2):
+        E_max / E_0 = (sqrt(pi) / 4) a0^2 k_p L exp(-k_p^2 L^2 / 4),   E_0 = m c omega_p / e,
+    at the resonant density k_p L = sqrt(2); wavelength 2 pi / k_p.  a0 = 0.3 (a0^2 / 4 = 2 % of nonlinear
+    correction), 6 particles per cell: measured 0.92 (triangle) / 0.95 (B-spline) of the amplitude, 0.94-0.96 of the
+    wavelength."""
+    lam = 0.8e-6
+    omega = 2.0 * math.pi * C_LIGHT / lam
+    a0, tw, w0 = 0.3, 10.0e-15, 6.0e-6                    # field envelope exp(-((t - tc) / tw)^2)
+    L = C_LIGHT * tw / math.sqrt(2.0)
+    kp = math.sqrt(2.0) / L
+    dens = kp ** 2 * C_LIGHT ** 2 * EPSILON0 * M0 / Q0 ** 2
+    e0 = M0 * C_LIGHT * (kp * C_LIGHT) / Q0
+    dx, dy, nr = lam / 16.0, lam / 2.0, 8
+    nx, ny = int(27.0e-6 / dx) // nr * nr, int(13.0e-6 / dy)
+    sp = [decks.SpeciesSpec(-Q0, M0, (BC_OPEN,) * 4, 6, dens)]          # electrons on an implicit ion background
+    las = [dict(boundary=po.BD_X_MIN, amp=a0 * M0 * C_LIGHT * omega / Q0, omega=omega, t_centre=3.0 * tw, t_width=tw,
+                r_width=w0, phase=0.0, pol_angle=0.0)]
+    d = decks.Deck("wake", nx, ny, 2, 0.0, nx * dx, ny * dy, (BC_SIMPLE_LASER, BC_OPEN, 0, BC_OPEN), sp, las)
+    w = decks.make_oracle(d, nranks=nr)
+    w.call("init_half_step")
+    t_end = 3.0 * tw + (nx * dx - 5.0e-6) / C_LIGHT        # the pulse centre 5 um short of x_max
+    w.step(int(t_end / w.scalars()["dt"]))
+    ex = np.concatenate([w.field(k, "exm")[0, NGH - 1, NGH:-NGH].real for k in range(nr)])    # mode 0, the axis row
+    ex = np.convolve(ex, np.ones(16) / 16.0, mode="same")   # average over one laser wavelength (the 2 omega ripple)
+    x = (np.arange(ex.size) + 0.5) * dx
+    tail = (t_end - 3.0 * tw) * C_LIGHT - 3.0 * C_LIGHT * tw        # where the pulse has passed
+    lam_p = 2.0 * math.pi / kp
+    first = (x > tail - 1.25 * lam_p) & (x < tail)          # the first period behind the pulse
+    amp = 0.5 * (ex[first].max() - ex[first].min())
+    theory = e0 * (math.sqrt(math.pi) * a0 * a0 / 4.0) * kp * L * math.exp(-(kp * L) ** 2 / 4.0)
+    if po.SHAPE == "tophat":
+        # The reference's top-hat gather reads bxm / brm / btm at the cell pair of the OTHER stagger
+        # (include/tophat/b_part.inc against triangle/ and bspline3/b_part.inc; restated as written, cyl_oracle.cpp):
+        # the particle sees B half a cell out of phase with E, v x B no longer averages to the ponderomotive force
+        # alone, and the wake comes out ~1.45 of theory where the other two shapes give 0.92-0.95 (and where the
+        # top-hat itself gives 0.95 once its B components are read at the cell pair of the other shapes: checked).
+        assert 1.15 < amp / theory < 1.8, amp / theory
+    else:
+        assert 0.85 < amp / theory < 1.10, amp / theory      # triangle 0.92, third-order B-spline 0.95
+    # wavelength: zero crossings of the field smoothed over a third of a plasma wavelength (particle noise makes the
+    # raw signal cross zero several times where it is small; the smoothing does not move the crossings of the wave)
+    smooth = np.convolve(ex, np.ones(64) / 64.0, mode="same")
+    behind = (x > 2.0e-6) & (x < tail)
+    xs, ss = x[behind], smooth[behind]
+    zc = [xs[i] - ss[i] * (xs[i + 1] - xs[i]) / (ss[i + 1] - ss[i]) for i in range(len(ss) - 1) if ss[i] * ss[i + 1] < 0]
+    assert len(zc) >= 2 and min(np.diff(zc)) > 0.3 * lam_p, zc
+    assert abs(2.0 * np.mean(np.diff(zc)) / lam_p - 1.0) < 0.08, 2.0 * np.mean(np.diff(zc)) / lam_p
+
+
 def test_rng_and_loader_statistics():
     import pyoracle
     d = decks.thermal(nx=32, ny=16, ppc=16, temp_k=1.0e7)
